@@ -1,0 +1,251 @@
+/*
+ * raysect_b200.h -- C ABI of libraysect_b200.so: Raysect's ray/scene intersection and spectral
+ * trace hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (raysect v0.9.1) has no FFI: its extension seams are Python-subclassable Cython
+ * classes.  Each entry point below names the reference interface it stands behind; the Python
+ * plugin classes that bind them (CudaAccelerator, CudaRenderEngine) are in source_b200/plugin.py
+ * and INTEGRATION.md shows the stub a Raysect maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with a message available
+ * from rsb_last_error() (thread-local).  Handles are opaque 64-bit integers.  Host arrays passed
+ * IN are copied during the call (the caller keeps ownership); host arrays passed OUT are
+ * caller-allocated.  Functions with the suffix _dev take DEVICE pointers plus a CUDA stream and
+ * return after enqueueing.  One context per device; a context is not thread-safe (neither are the
+ * reference's primitives, which cache next_intersection() state).  There is no CPU fallback: every
+ * compute entry point fails with RSB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RAYSECT_B200_H
+#define RAYSECT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB_OK 0
+#define RSB_ERR_ARG 1
+#define RSB_ERR_CUDA 2
+#define RSB_ERR_UNSUPPORTED 3
+#define RSB_ERR_OVERFLOW 4
+
+/* primitive rows: raysect/primitive/{sphere,box,cylinder,cone,csg}.pyx, raysect/primitive/mesh/mesh.pyx */
+#define RSB_PRIM_SPHERE 0
+#define RSB_PRIM_BOX 1
+#define RSB_PRIM_CYLINDER 2
+#define RSB_PRIM_CONE 3
+#define RSB_PRIM_MESH 4
+#define RSB_PRIM_UNION 5
+#define RSB_PRIM_INTERSECT 6
+#define RSB_PRIM_SUBTRACT 7
+
+/* materials: raysect/optical/material/{absorber,lambert,dielectric}.pyx, emitter/uniform.pyx */
+#define RSB_MAT_ABSORBER 0
+#define RSB_MAT_EMITTER 1
+#define RSB_MAT_LAMBERT 2
+#define RSB_MAT_DIELECTRIC 3
+
+#define RSB_RNG_MT19937_64 0 /* raysect/core/math/random.pyx:99-265, one stream per pixel = seed(seed + y*nx + x) */
+#define RSB_RNG_PHILOX 1     /* counter based, keyed on (seed, pixel, sample) */
+
+/* MeshData arrays (raysect/primitive/mesh/mesh.pxd:44-60) + its kd-tree stream (kdtree3d.pyx:864-984) */
+typedef struct RsbMeshDesc {
+    const float* vertices;       /* [n_vertices][3] */
+    const int32_t* triangles;    /* [n_triangles][tri_stride]: v1 v2 v3 [n1 n2 n3] */
+    const float* vertex_normals; /* [n_vertex_normals][3] or NULL */
+    const float* face_normals;   /* [n_triangles][3] or NULL: computed as mesh.pyx:428-462 does */
+    const uint8_t* kdtree;       /* serialised KDTree3DCore stream */
+    int64_t kdtree_bytes;
+    int32_t n_vertices;
+    int32_t n_triangles;
+    int32_t tri_stride;          /* 3 or 6 */
+    int32_t n_vertex_normals;
+    int32_t smoothing;
+    int32_t closed;
+} RsbMeshDesc;
+
+/*
+ * Flattened scenegraph.  Rows [0, n_world) are World.primitives in list order (that order defines the
+ * primitive ids stored in the world kd-tree, raysect/core/acceleration/kdtree.pyx:52-55); further rows are
+ * CSG operands, whose transforms and boxes are relative to their CSGRoot (raysect/primitive/csg.pyx:70-79).
+ */
+typedef struct RsbSceneDesc {
+    int32_t n_primitives;
+    int32_t n_world;
+    const int32_t* prim_type;
+    const int32_t* prim_material;   /* material row, -1 for CSG operands */
+    const int32_t* prim_child_a;    /* CSG operand rows, else -1 */
+    const int32_t* prim_child_b;
+    const int32_t* prim_mesh;       /* mesh row, else -1 */
+    const int32_t* prim_parent;     /* enclosing CSG row, -1 for world-level primitives */
+    const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone r,h */
+    const double* prim_to_local;    /* [n][12] rows 0..2 of Node.to_local() (parent space -> local) */
+    const double* prim_to_root;     /* [n][12] rows 0..2 of Node.to_root() */
+    const double* prim_root_inv;    /* [n][12] rows 0..2 of to_root().inverse() (Normal3D.transform, normal.pyx:241) */
+    const double* prim_bbox;        /* [n][6] Primitive.bounding_box() lower,upper in the parent space */
+    const uint8_t* world_kdtree;    /* serialised _PrimitiveKDTree stream */
+    int64_t world_kdtree_bytes;
+    int32_t n_meshes;
+    int32_t n_materials;
+    const RsbMeshDesc* meshes;
+    const int32_t* mat_type;        /* [n_materials] */
+    const int32_t* mat_transmission_only;
+    /* ImportanceManager input (raysect/optical/scenegraph/world.pyx:88-132): primitives with material.importance > 0 */
+    int32_t n_important;
+    int32_t pad;
+    const double* imp_sphere;       /* [n_important][4] bounding sphere centre xyz, radius */
+    const double* imp_weight;       /* [n_important] */
+} RsbSceneDesc;
+
+/* PinholeCamera state after _update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-167) */
+typedef struct RsbCamera {
+    int32_t nx, ny;
+    int32_t pixel_samples;
+    int32_t pad;
+    double image_delta, image_start_x, image_start_y;
+    double sensitivity;
+    double to_root[12];
+} RsbCamera;
+
+/* optical Ray template (raysect/optical/ray.pyx:85-126) for one spectral slice */
+typedef struct RsbRayConfig {
+    int32_t bins;
+    int32_t extinction_min_depth;
+    int32_t max_depth;
+    int32_t importance_sampling;
+    double min_wavelength, max_wavelength;
+    double extinction_prob;
+    double important_path_weight;
+    double max_distance;
+} RsbRayConfig;
+
+/* what SpectralFunction.sample(min,max,bins) / .average(min,max) return for each material in this slice */
+typedef struct RsbSpectral {
+    int32_t bins;
+    int32_t n_materials;
+    const double* tables;     /* [n_materials][bins] reflectivity | emission | transmission */
+    const double* scale;      /* [n_materials] emitter scale */
+    const double* index_in;   /* [n_materials] dielectric index.average() */
+    const double* index_out;  /* [n_materials] dielectric external_index.average() */
+} RsbSpectral;
+
+typedef struct RsbRngDesc {
+    int32_t mode;
+    int32_t pad;
+    uint64_t seed;            /* must be >= 1 */
+} RsbRngDesc;
+
+/* traversal counters behind the algorithmic-bytes roofline model */
+typedef struct RsbCounters {
+    uint64_t rays;        /* World.hit queries */
+    uint64_t branches;    /* kd branch nodes visited (world + mesh trees) */
+    uint64_t leaves;      /* kd leaves visited */
+    uint64_t items;       /* leaf item ids read */
+    uint64_t prim_tests;  /* BoundPrimitive.hit calls on world-level primitives */
+    uint64_t tri_tests;   /* _hit_triangle calls */
+    uint64_t paths;       /* primary rays traced by rsb_render */
+    uint64_t contains;    /* World.contains queries */
+} RsbCounters;
+
+const char* rsb_last_error(void);
+int rsb_version(void);
+void rsb_free(void* p);
+
+/* ---- host-only helpers (no device needed) ---- */
+
+/* KDTree3DCore.__init__ (raysect/core/math/spatial/kdtree3d.pyx:126-459): SAH build over item boxes
+ * (boxes[i] = lower xyz, upper xyz; item id = i); returns the serialised stream of save() (:864-912),
+ * to be released with rsb_free(). */
+int rsb_kdtree_build(const double* boxes, int64_t n_items, int32_t max_depth, int32_t min_items,
+                     double hit_cost, double empty_bonus, uint8_t** stream, int64_t* stream_bytes);
+
+/* MeshData._generate_face_normals (raysect/primitive/mesh/mesh.pyx:428-462) */
+int rsb_mesh_face_normals(const float* vertices, int32_t n_vertices, const int32_t* triangles,
+                          int32_t n_triangles, int32_t tri_stride, float* face_normals);
+
+/* MeshData._generate_bounding_box for every triangle (mesh.pyx:467-504): boxes[i] = lower xyz, upper xyz */
+int rsb_mesh_triangle_boxes(const float* vertices, int32_t n_vertices, const int32_t* triangles,
+                            int32_t n_triangles, int32_t tri_stride, double* boxes);
+
+/* ---- device ---- */
+
+int rsb_context_create(int device, uint64_t* ctx);
+int rsb_context_destroy(uint64_t ctx);
+int rsb_device_info(uint64_t ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, uint64_t* total_mem);
+
+/* Accelerator.build (raysect/core/acceleration/accelerator.pxd:37-41, kdtree.pyx:167-168) */
+int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* desc, uint64_t* scene);
+int rsb_scene_destroy(uint64_t ctx, uint64_t scene);
+
+/*
+ * Accelerator.hit == World.hit (raysect/core/scenegraph/world.pyx:125-146) over a batch of rays.
+ * origins, directions: [n][3]; max_distance: [n] or NULL (= +inf).
+ * out_prim[n]: world-level primitive id or -1 (miss); out_t[n]: Intersection.ray_distance;
+ * out_sub[n]: triangle id (mesh) | face code (analytic) ; out_flags[n]: bit0 = Intersection.exiting;
+ * out_node[n][2]: (world kd leaf id, mesh kd leaf id or -1) using the reference's node numbering;
+ * out_geom[n][12] or NULL: hit_point, inside_point, outside_point, normal in primitive-local space;
+ * out_uvw[n][3] or NULL: MeshIntersection.u,v,w.
+ */
+int rsb_hit_batch(uint64_t ctx, uint64_t scene, int64_t n, const double* origins, const double* directions,
+                  const double* max_distance, int32_t* out_prim, double* out_t, int32_t* out_sub,
+                  uint8_t* out_flags, int32_t* out_node, double* out_geom, float* out_uvw);
+int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, const double* origins,
+                      const double* directions, const double* max_distance, int32_t* out_prim, double* out_t,
+                      int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom, float* out_uvw,
+                      int32_t count);
+
+/*
+ * Ray-batch sweep (BASELINE config 5): n primary rays generated ON DEVICE from (seed, index), from
+ * `origin` toward a jittered window centred on `target` (half-width `half_window` in x and y),
+ * hit results reduced to (hits, sum of t, xor of primitive ids) so that 1e9 rays need no ray arrays.
+ */
+int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, int64_t first_index, uint64_t seed,
+                      const double* origin, const double* target, double half_window,
+                      uint64_t* out_hits_dev, double* out_sum_t_dev, uint64_t* out_xor_prim_dev, int32_t count);
+
+/*
+ * Accelerator.contains == World.contains (world.pyx:148-168): points [n][3]; out_count[n];
+ * out_prims[n][cap] primitive ids in the reference's list order (kd leaf order).
+ */
+int rsb_contains_batch(uint64_t ctx, uint64_t scene, int64_t n, const double* points, int32_t cap,
+                       int32_t* out_count, int32_t* out_prims);
+
+/* raysect.core.math.random: seed(seed) then n x uniform() (random.pyx:215-265), evaluated on the device */
+int rsb_rng_uniform(uint64_t ctx, uint64_t seed, int64_t n, double* out);
+
+/*
+ * RenderEngine.run for a PinholeCamera + SpectralPowerPipeline2D slice
+ * (raysect/core/workflow.py:78-91 ; observer.pyx:363-419 ; pipeline/spectral/power.pyx:468-486):
+ * renders pixel_samples samples for each listed pixel (pixels = [n_pixels][2] (x, y), or NULL for the
+ * whole nx*ny frame) and writes, for pixel (x, y) and slice bin b, frame index (x*ny + y)*bins + b:
+ *   mean, variance = StatsArray1D after pixel_samples x add_sample(); unlisted pixels are untouched.
+ * ray_count += the reference's ray counter (primary rays + daughters spawned).
+ */
+int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+               const RsbSpectral* spectral, const RsbRngDesc* rng, int64_t n_pixels, const int32_t* pixels,
+               double* mean, double* variance, uint64_t* ray_count);
+int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera,
+                   const RsbRayConfig* config, const RsbSpectral* spectral, const RsbRngDesc* rng,
+                   int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
+                   uint64_t* ray_count_dev, int32_t count);
+
+/*
+ * SpectralPowerPipeline2D.update -> StatsArray3D.combine_samples (power.pyx:424-437, statsarray.pyx:780-857):
+ * merges a freshly rendered slice (mean, variance, samples_per_pixel; [n_pixels_total][slice_bins]) into an
+ * accumulating frame (frame_* [n_pixels_total][frame_bins]) at bin offset slice_offset, for the listed pixels.
+ */
+int rsb_frame_combine_dev(uint64_t ctx, void* cuda_stream, int64_t n_pixels_total, int32_t frame_bins,
+                          int32_t slice_offset, int32_t slice_bins, int64_t n_pixels, const int32_t* pixels_dev,
+                          int32_t ny, const double* mean_dev, const double* variance_dev, int32_t samples,
+                          double* frame_mean_dev, double* frame_variance_dev, int32_t* frame_samples_dev);
+
+/* counters of the last *_dev / host call made with count != 0 (host calls always count) */
+int rsb_counters(uint64_t ctx, RsbCounters* out);
+/* device time (ms, CUDA events on the launch stream) of the dominant kernel of the last host-buffer call */
+int rsb_last_kernel_ms(uint64_t ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYSECT_B200_H */

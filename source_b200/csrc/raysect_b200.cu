@@ -1,0 +1,732 @@
+// raysect_b200.cu -- C ABI (include/raysect_b200.h): context, scene upload, kernel launches.
+#include "../../include/raysect_b200.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "kdtree_host.h"
+#include "rsb_kernels.cuh"
+#include "scene_pack.h"
+
+using namespace rsb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+#define RSB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(RSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+struct DeviceScene {
+    Scene sc;
+    std::vector<void*> allocs;
+    int32_t n_world_items = 0;
+    int32_t n_materials = 0;
+    std::vector<int32_t> mat_type, mat_transmission_only;
+    int32_t stage_bytes = 0;   // shared memory needed to stage world tree + prims (0 = do not stage)
+};
+
+struct Context {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevCounters* d_counters = nullptr;
+    unsigned long long* d_scalars = nullptr;   // [0] work counter, [1] ray count, [2] overflow flag (as int)
+    unsigned long long* d_mt = nullptr;
+    size_t mt_threads = 0;
+    LogEntry* d_log = nullptr;
+    size_t log_entries = 0;
+    Material* d_mats = nullptr;
+    double* d_tables = nullptr;
+    size_t mats_cap = 0, tables_cap = 0;
+    float last_ms = 0.f;
+    RsbCounters last_counters{};
+    std::vector<DeviceScene*> scenes;
+};
+
+const size_t kMaxStageBytes = 96 * 1024;
+
+template <class T>
+int upload(DeviceScene* ds, const T* host, size_t count, const T** dev, size_t pad_to_bytes = 16) {
+    size_t bytes = count * sizeof(T);
+    size_t alloc = ((bytes + pad_to_bytes - 1) / pad_to_bytes) * pad_to_bytes;
+    if (alloc == 0) alloc = pad_to_bytes;
+    void* p = nullptr;
+    RSB_CUDA(cudaMalloc(&p, alloc));
+    ds->allocs.push_back(p);
+    RSB_CUDA(cudaMemset(p, 0, alloc));
+    if (bytes) RSB_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<const T*>(p);
+    return RSB_OK;
+}
+
+int upload_tree(DeviceScene* ds, const HostKdTree& h, KdTree* out) {
+    int rc = upload(ds, h.nodes.data(), h.nodes.size(), &out->nodes);
+    if (rc) return rc;
+    rc = upload(ds, h.items.data(), h.items.size(), &out->items);
+    if (rc) return rc;
+    memcpy(out->bounds, h.bounds, sizeof(h.bounds));
+    out->n_nodes = (int32_t)h.nodes.size();
+    out->max_depth = h.depth;
+    return RSB_OK;
+}
+
+Context* as_ctx(uint64_t h) { return reinterpret_cast<Context*>(h); }
+DeviceScene* as_scene(uint64_t h) { return reinterpret_cast<DeviceScene*>(h); }
+
+void free_scene(DeviceScene* ds) {
+    for (void* p : ds->allocs) cudaFree(p);
+    delete ds;
+}
+
+int grid_for(Context* c, long long n, int threads, int blocks_per_sm) {
+    long long need = (n + threads - 1) / threads;
+    long long cap = (long long)c->sm_count * blocks_per_sm;
+    return (int)std::max(1LL, std::min(need, cap));
+}
+
+int read_counters(Context* c, cudaStream_t st) {
+    DevCounters h;
+    RSB_CUDA(cudaMemcpyAsync(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaStreamSynchronize(st));
+    c->last_counters.rays = h.rays;
+    c->last_counters.branches = h.branches;
+    c->last_counters.leaves = h.leaves;
+    c->last_counters.items = h.items;
+    c->last_counters.prim_tests = h.prim_tests;
+    c->last_counters.tri_tests = h.tri_tests;
+    c->last_counters.paths = h.paths;
+    c->last_counters.contains = h.contains;
+    return RSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rsb_last_error(void) { return g_error.c_str(); }
+int rsb_version(void) { return 100; }
+void rsb_free(void* p) { free(p); }
+
+int rsb_kdtree_build(const double* boxes, int64_t n_items, int32_t max_depth, int32_t min_items, double hit_cost,
+                     double empty_bonus, uint8_t** stream, int64_t* stream_bytes) {
+    if (!boxes || n_items <= 0 || !stream || !stream_bytes) return fail(RSB_ERR_ARG, "rsb_kdtree_build: bad arguments");
+    if (empty_bonus < 0.0 || empty_bonus > 1.0)
+        return fail(RSB_ERR_ARG, "The empty_bonus cost modifier must lie in the range [0.0, 1.0].");
+    HostKdTree t;
+    kd_build(boxes, n_items, max_depth, min_items, hit_cost, empty_bonus, &t);
+    std::vector<uint8_t> bytes;
+    kd_write_stream(t, &bytes);
+    uint8_t* out = (uint8_t*)malloc(bytes.size());
+    if (!out) return fail(RSB_ERR_ARG, "rsb_kdtree_build: out of memory");
+    memcpy(out, bytes.data(), bytes.size());
+    *stream = out;
+    *stream_bytes = (int64_t)bytes.size();
+    return RSB_OK;
+}
+
+int rsb_mesh_face_normals(const float* vertices, int32_t n_vertices, const int32_t* triangles, int32_t n_triangles,
+                          int32_t tri_stride, float* face_normals) {
+    if (!vertices || !triangles || !face_normals || (tri_stride != 3 && tri_stride != 6))
+        return fail(RSB_ERR_ARG, "rsb_mesh_face_normals: bad arguments");
+    for (int32_t i = 0; i < n_triangles; ++i) {
+        const int32_t* row = triangles + (size_t)i * tri_stride;
+        for (int k = 0; k < 3; ++k)
+            if (row[k] < 0 || row[k] >= n_vertices) return fail(RSB_ERR_ARG, "The triangle array references non-existent vertices.");
+        mesh_face_normal(vertices, row, face_normals + 3 * (size_t)i);
+    }
+    return RSB_OK;
+}
+
+int rsb_mesh_triangle_boxes(const float* vertices, int32_t n_vertices, const int32_t* triangles, int32_t n_triangles,
+                            int32_t tri_stride, double* boxes) {
+    if (!vertices || !triangles || !boxes || (tri_stride != 3 && tri_stride != 6))
+        return fail(RSB_ERR_ARG, "rsb_mesh_triangle_boxes: bad arguments");
+    const double BOX_PADDING = 1e-6;
+    for (int32_t i = 0; i < n_triangles; ++i) {
+        const int32_t* row = triangles + (size_t)i * tri_stride;
+        for (int k = 0; k < 3; ++k)
+            if (row[k] < 0 || row[k] >= n_vertices) return fail(RSB_ERR_ARG, "The triangle array references non-existent vertices.");
+        const float* a = vertices + 3 * (size_t)row[0];
+        const float* b = vertices + 3 * (size_t)row[1];
+        const float* c = vertices + 3 * (size_t)row[2];
+        double* o = boxes + 6 * (size_t)i;
+        for (int k = 0; k < 3; ++k) {
+            // min()/max() over float32 values, then stored as double (mesh.pyx:484-497)
+            float lo = std::min(std::min(a[k], b[k]), c[k]);
+            float hi = std::max(std::max(a[k], b[k]), c[k]);
+            o[k] = (double)lo;
+            o[3 + k] = (double)hi;
+        }
+        // bbox.pad(max(BOX_PADDING, bbox.largest_extent() * BOX_PADDING)) (mesh.pyx:502)
+        double ex = std::max(0.0, o[3] - o[0]), ey = std::max(0.0, o[4] - o[1]), ez = std::max(0.0, o[5] - o[2]);
+        double pad = std::max(BOX_PADDING, std::max(std::max(ex, ey), ez) * BOX_PADDING);
+        for (int k = 0; k < 3; ++k) {
+            o[k] = o[k] - pad;
+            o[3 + k] = o[3 + k] + pad;
+        }
+    }
+    return RSB_OK;
+}
+
+int rsb_context_create(int device, uint64_t* ctx) {
+    if (!ctx) return fail(RSB_ERR_ARG, "rsb_context_create: null handle pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RSB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                      "); libraysect_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(RSB_ERR_ARG, "rsb_context_create: device index out of range");
+    RSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(RSB_ERR_CUDA, "libraysect_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor));
+    Context* c = new Context();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->total_mem = prop.totalGlobalMem;
+    RSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RSB_CUDA(cudaEventCreate(&c->ev0));
+    RSB_CUDA(cudaEventCreate(&c->ev1));
+    RSB_CUDA(cudaMalloc(&c->d_counters, sizeof(DevCounters)));
+    RSB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+    RSB_CUDA(cudaMalloc(&c->d_scalars, 8 * sizeof(unsigned long long)));
+    RSB_CUDA(cudaMemset(c->d_scalars, 0, 8 * sizeof(unsigned long long)));
+    *ctx = reinterpret_cast<uint64_t>(c);
+    return RSB_OK;
+}
+
+int rsb_context_destroy(uint64_t ctx) {
+    Context* c = as_ctx(ctx);
+    if (!c) return fail(RSB_ERR_ARG, "null context");
+    cudaSetDevice(c->device);
+    for (DeviceScene* s : c->scenes) free_scene(s);
+    cudaFree(c->d_counters);
+    cudaFree(c->d_scalars);
+    cudaFree(c->d_mt);
+    cudaFree(c->d_log);
+    cudaFree(c->d_mats);
+    cudaFree(c->d_tables);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return RSB_OK;
+}
+
+int rsb_device_info(uint64_t ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, uint64_t* total_mem) {
+    Context* c = as_ctx(ctx);
+    if (!c) return fail(RSB_ERR_ARG, "null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (total_mem) *total_mem = c->total_mem;
+    return RSB_OK;
+}
+
+int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
+    Context* c = as_ctx(ctx);
+    if (!c || !d || !scene) return fail(RSB_ERR_ARG, "rsb_scene_create: null argument");
+    RSB_CUDA(cudaSetDevice(c->device));
+    PackedScene ps;
+    std::string err;
+    int prc = pack_scene(d, &ps, &err);
+    if (prc) return fail(prc, err);
+
+    DeviceScene* ds = new DeviceScene();
+    auto bail = [&](int rc) { free_scene(ds); return rc; };
+    memset(&ds->sc, 0, sizeof(ds->sc));
+    int rc = upload(ds, ps.prims.data(), ps.prims.size(), &ds->sc.prims);
+    if (rc) return bail(rc);
+    ds->sc.n_prims = (int32_t)ps.prims.size();
+    ds->sc.n_world = ps.n_world;
+    rc = upload_tree(ds, ps.world, &ds->sc.world);
+    if (rc) return bail(rc);
+    ds->n_world_items = (int32_t)ps.world.items.size();
+    {
+        StageLayout l = stage_layout((int)ps.world.nodes.size(), (int)ps.world.items.size(), (int)ps.prims.size());
+        ds->stage_bytes = (size_t)l.total <= kMaxStageBytes ? l.total : 0;
+    }
+    std::vector<Mesh> meshes(std::max<size_t>(1, ps.meshes.size()));
+    memset(meshes.data(), 0, meshes.size() * sizeof(Mesh));
+    for (size_t mi = 0; mi < ps.meshes.size(); ++mi) {
+        const PackedMesh& pm = ps.meshes[mi];
+        Mesh& m = meshes[mi];
+        rc = upload(ds, pm.tri.data(), pm.tri.size(), &m.tri);
+        if (rc) return bail(rc);
+        rc = upload(ds, pm.tri_idx.data(), pm.tri_idx.size(), &m.tri_idx);
+        if (rc) return bail(rc);
+        m.vnormals = nullptr;
+        if (!pm.vnormals.empty()) {
+            rc = upload(ds, pm.vnormals.data(), pm.vnormals.size(), &m.vnormals);
+            if (rc) return bail(rc);
+        }
+        rc = upload_tree(ds, pm.tree, &m.tree);
+        if (rc) return bail(rc);
+        m.n_tri = pm.n_tri;
+        m.idx_stride = pm.idx_stride;
+        m.smoothing = pm.smoothing;
+        m.closed = pm.closed;
+    }
+    rc = upload(ds, meshes.data(), meshes.size(), &ds->sc.meshes);
+    if (rc) return bail(rc);
+    ds->sc.n_meshes = (int32_t)ps.meshes.size();
+    ds->n_materials = (int32_t)ps.mat_type.size();
+    ds->mat_type = ps.mat_type;
+    ds->mat_transmission_only = ps.mat_transmission_only;
+    ds->sc.n_important = (int32_t)ps.imp_weight.size();
+    ds->sc.imp_total = ps.imp_total;
+    if (!ps.imp_weight.empty()) {
+        rc = upload(ds, ps.imp_sphere.data(), ps.imp_sphere.size(), &ds->sc.imp_sphere);
+        if (rc) return bail(rc);
+        rc = upload(ds, ps.imp_weight.data(), ps.imp_weight.size(), &ds->sc.imp_weight);
+        if (rc) return bail(rc);
+        rc = upload(ds, ps.imp_cdf.data(), ps.imp_cdf.size(), &ds->sc.imp_cdf);
+        if (rc) return bail(rc);
+    }
+    c->scenes.push_back(ds);
+    *scene = reinterpret_cast<uint64_t>(ds);
+    return RSB_OK;
+}
+
+int rsb_scene_destroy(uint64_t ctx, uint64_t scene) {
+    Context* c = as_ctx(ctx);
+    DeviceScene* ds = as_scene(scene);
+    if (!c || !ds) return fail(RSB_ERR_ARG, "null handle");
+    auto it = std::find(c->scenes.begin(), c->scenes.end(), ds);
+    if (it == c->scenes.end()) return fail(RSB_ERR_ARG, "scene does not belong to this context");
+    c->scenes.erase(it);
+    cudaSetDevice(c->device);
+    free_scene(ds);
+    return RSB_OK;
+}
+
+int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, const double* origins,
+                      const double* directions, const double* max_distance, int32_t* out_prim, double* out_t,
+                      int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom, float* out_uvw,
+                      int32_t count) {
+    Context* c = as_ctx(ctx);
+    DeviceScene* ds = as_scene(scene);
+    if (!c || !ds) return fail(RSB_ERR_ARG, "null handle");
+    if (n <= 0) return RSB_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    RSB_CUDA(cudaSetDevice(c->device));
+    int grid = grid_for(c, n, 128, 16);
+    size_t smem = ds->stage_bytes;
+    if (count) {
+        RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hit_batch<true><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance,
+                                                  out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters);
+    } else {
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hit_batch<false><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance,
+                                                   out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters);
+    }
+    RSB_CUDA(cudaGetLastError());
+    if (count) {
+        int rc = read_counters(c, st);
+        if (rc) return rc;
+        c->last_counters.rays = (uint64_t)n;
+    }
+    return RSB_OK;
+}
+
+int rsb_hit_batch(uint64_t ctx, uint64_t scene, int64_t n, const double* origins, const double* directions,
+                  const double* max_distance, int32_t* out_prim, double* out_t, int32_t* out_sub, uint8_t* out_flags,
+                  int32_t* out_node, double* out_geom, float* out_uvw) {
+    Context* c = as_ctx(ctx);
+    if (!c || !as_scene(scene)) return fail(RSB_ERR_ARG, "null handle");
+    if (n < 0 || !origins || !directions || !out_prim || !out_t || !out_sub || !out_flags)
+        return fail(RSB_ERR_ARG, "rsb_hit_batch: null array");
+    if (n == 0) return RSB_OK;
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    double *d_o = nullptr, *d_d = nullptr, *d_m = nullptr, *d_t = nullptr, *d_g = nullptr;
+    int32_t *d_p = nullptr, *d_s = nullptr, *d_n = nullptr;
+    uint8_t* d_f = nullptr;
+    float* d_u = nullptr;
+    int rc = RSB_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_o); cudaFree(d_d); cudaFree(d_m); cudaFree(d_t); cudaFree(d_g);
+        cudaFree(d_p); cudaFree(d_s); cudaFree(d_n); cudaFree(d_f); cudaFree(d_u);
+    };
+#define RSB_TRY(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) { cleanup(); return fail(RSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
+    } while (0)
+    RSB_TRY(cudaMalloc(&d_o, n * 24));
+    RSB_TRY(cudaMalloc(&d_d, n * 24));
+    if (max_distance) RSB_TRY(cudaMalloc(&d_m, n * 8));
+    RSB_TRY(cudaMalloc(&d_t, n * 8));
+    RSB_TRY(cudaMalloc(&d_p, n * 4));
+    RSB_TRY(cudaMalloc(&d_s, n * 4));
+    RSB_TRY(cudaMalloc(&d_f, n));
+    if (out_node) RSB_TRY(cudaMalloc(&d_n, n * 8));
+    if (out_geom) RSB_TRY(cudaMalloc(&d_g, n * 96));
+    if (out_uvw) RSB_TRY(cudaMalloc(&d_u, n * 12));
+    RSB_TRY(cudaMemcpyAsync(d_o, origins, n * 24, cudaMemcpyHostToDevice, st));
+    RSB_TRY(cudaMemcpyAsync(d_d, directions, n * 24, cudaMemcpyHostToDevice, st));
+    if (max_distance) RSB_TRY(cudaMemcpyAsync(d_m, max_distance, n * 8, cudaMemcpyHostToDevice, st));
+    RSB_TRY(cudaEventRecord(c->ev0, st));
+    rc = rsb_hit_batch_dev(ctx, scene, st, n, d_o, d_d, d_m, d_p, d_t, d_s, d_f, d_n, d_g, d_u, 1);
+    if (rc) { cleanup(); return rc; }
+    RSB_TRY(cudaEventRecord(c->ev1, st));
+    RSB_TRY(cudaMemcpyAsync(out_prim, d_p, n * 4, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(out_t, d_t, n * 8, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(out_sub, d_s, n * 4, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(out_flags, d_f, n, cudaMemcpyDeviceToHost, st));
+    if (out_node) RSB_TRY(cudaMemcpyAsync(out_node, d_n, n * 8, cudaMemcpyDeviceToHost, st));
+    if (out_geom) RSB_TRY(cudaMemcpyAsync(out_geom, d_g, n * 96, cudaMemcpyDeviceToHost, st));
+    if (out_uvw) RSB_TRY(cudaMemcpyAsync(out_uvw, d_u, n * 12, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    cleanup();
+    return RSB_OK;
+}
+
+int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, int64_t first_index, uint64_t seed,
+                      const double* origin, const double* target, double half_window, uint64_t* out_hits_dev,
+                      double* out_sum_t_dev, uint64_t* out_xor_prim_dev, int32_t count) {
+    Context* c = as_ctx(ctx);
+    DeviceScene* ds = as_scene(scene);
+    if (!c || !ds || !origin || !target || !out_hits_dev || !out_sum_t_dev || !out_xor_prim_dev) return fail(RSB_ERR_ARG, "null argument");
+    if (n <= 0) return RSB_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    RSB_CUDA(cudaSetDevice(c->device));
+    int grid = grid_for(c, n, 128, 8);
+    size_t smem = ds->stage_bytes;
+    if (count) {
+        RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hit_sweep<true><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2],
+                                                  target[0], target[1], target[2], half_window,
+                                                  (unsigned long long*)out_hits_dev, out_sum_t_dev, (unsigned long long*)out_xor_prim_dev, c->d_counters);
+    } else {
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hit_sweep<false><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2],
+                                                   target[0], target[1], target[2], half_window,
+                                                   (unsigned long long*)out_hits_dev, out_sum_t_dev, (unsigned long long*)out_xor_prim_dev, c->d_counters);
+    }
+    RSB_CUDA(cudaGetLastError());
+    if (count) {
+        int rc = read_counters(c, st);
+        if (rc) return rc;
+        c->last_counters.rays = (uint64_t)n;
+    }
+    return RSB_OK;
+}
+
+int rsb_contains_batch(uint64_t ctx, uint64_t scene, int64_t n, const double* points, int32_t cap, int32_t* out_count,
+                       int32_t* out_prims) {
+    Context* c = as_ctx(ctx);
+    DeviceScene* ds = as_scene(scene);
+    if (!c || !ds) return fail(RSB_ERR_ARG, "null handle");
+    if (n < 0 || !points || !out_count || !out_prims || cap <= 0) return fail(RSB_ERR_ARG, "rsb_contains_batch: bad arguments");
+    if (n == 0) return RSB_OK;
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    double* d_p = nullptr;
+    int32_t *d_c = nullptr, *d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_p); cudaFree(d_c); cudaFree(d_o); };
+    RSB_TRY(cudaMalloc(&d_p, n * 24));
+    RSB_TRY(cudaMalloc(&d_c, n * 4));
+    RSB_TRY(cudaMalloc(&d_o, n * 4 * cap));
+    RSB_TRY(cudaMemsetAsync(d_o, 0xff, n * 4 * cap, st));
+    RSB_TRY(cudaMemcpyAsync(d_p, points, n * 24, cudaMemcpyHostToDevice, st));
+    k_contains_batch<<<grid_for(c, n, 128, 16), 128, 0, st>>>(ds->sc, n, d_p, cap, d_c, d_o);
+    RSB_TRY(cudaGetLastError());
+    RSB_TRY(cudaMemcpyAsync(out_count, d_c, n * 4, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(out_prims, d_o, n * 4 * cap, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaStreamSynchronize(st));
+    cleanup();
+    c->last_counters.contains = (uint64_t)n;
+    return RSB_OK;
+}
+
+int rsb_rng_uniform(uint64_t ctx, uint64_t seed, int64_t n, double* out) {
+    Context* c = as_ctx(ctx);
+    if (!c) return fail(RSB_ERR_ARG, "null context");
+    if (seed == 0) return fail(RSB_ERR_ARG, "seed must be >= 1 (the reference treats seed(0) as 'reseed from urandom')");
+    if (n <= 0 || !out) return fail(RSB_ERR_ARG, "rsb_rng_uniform: bad arguments");
+    RSB_CUDA(cudaSetDevice(c->device));
+    unsigned long long* d_s = nullptr;
+    double* d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_o); };
+    RSB_TRY(cudaMalloc(&d_s, RSB_MT_NN * 8));
+    RSB_TRY(cudaMalloc(&d_o, n * 8));
+    k_rng_uniform<<<1, 1, 0, c->stream>>>(seed, n, d_s, d_o);
+    RSB_TRY(cudaGetLastError());
+    RSB_TRY(cudaMemcpyAsync(out, d_o, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    RSB_TRY(cudaStreamSynchronize(c->stream));
+    cleanup();
+    return RSB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int RNGMODE, bool COUNT>
+int launch_render(Context* c, const RenderArgs& args, int blocks_per_sm_cap, size_t smem, cudaStream_t st, size_t* threads_out) {
+    auto kern = k_render<RNGMODE, COUNT>;
+    if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RSB_RENDER_THREADS, smem));
+    if (per_sm < 1) return fail(RSB_ERR_CUDA, "render kernel does not fit on an SM");
+    per_sm = std::min(per_sm, blocks_per_sm_cap);
+    int grid = c->sm_count * per_sm;
+    *threads_out = (size_t)grid * RSB_RENDER_THREADS;
+    (void)args;
+    return grid;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
+                   const RsbSpectral* spectral, const RsbRngDesc* rng, int64_t n_pixels, const int32_t* pixels_dev,
+                   double* mean_dev, double* variance_dev, uint64_t* ray_count_dev, int32_t count) {
+    Context* c = as_ctx(ctx);
+    DeviceScene* ds = as_scene(scene);
+    if (!c || !ds || !camera || !config || !spectral || !rng || !mean_dev || !variance_dev || !ray_count_dev)
+        return fail(RSB_ERR_ARG, "rsb_render: null argument");
+    if (camera->nx < 1 || camera->ny < 1 || camera->pixel_samples < 1) return fail(RSB_ERR_ARG, "rsb_render: bad camera");
+    if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
+    if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");
+    if (spectral->n_materials != ds->n_materials) return fail(RSB_ERR_ARG, "rsb_render: spectral tables do not match the scene's materials");
+    if (config->important_path_weight < 0 || config->important_path_weight > 1.0)
+        return fail(RSB_ERR_ARG, "Important path weight must be in the range [0, 1].");
+    if (rng->seed == 0) return fail(RSB_ERR_ARG, "rng seed must be >= 1");
+    if (rng->mode != RSB_RNG_MT19937_64 && rng->mode != RSB_RNG_PHILOX) return fail(RSB_ERR_ARG, "unknown rng mode");
+    if (n_pixels <= 0) return RSB_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    RSB_CUDA(cudaSetDevice(c->device));
+
+    // ---- per-slice material table -----------------------------------------------------------------
+    int nm = ds->n_materials;
+    std::vector<Material> mats((size_t)nm);
+    for (int i = 0; i < nm; ++i) {
+        Material& m = mats[i];
+        memset(&m, 0, sizeof(m));
+        m.type = ds->mat_type[i];
+        m.transmission_only = ds->mat_transmission_only[i];
+        m.table = i;
+        m.scale = spectral->scale ? spectral->scale[i] : 1.0;
+        m.index_in = spectral->index_in ? spectral->index_in[i] : 1.0;
+        m.index_out = spectral->index_out ? spectral->index_out[i] : 1.0;
+    }
+    size_t mat_bytes = (((size_t)nm * sizeof(Material) + 15) / 16) * 16;
+    size_t tab_bytes = (((size_t)nm * spectral->bins * 8 + 15) / 16) * 16;
+    if (c->mats_cap < mat_bytes) {
+        cudaFree(c->d_mats);
+        c->d_mats = nullptr; c->mats_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_mats, mat_bytes));
+        c->mats_cap = mat_bytes;
+    }
+    if (c->tables_cap < tab_bytes) {
+        cudaFree(c->d_tables);
+        c->d_tables = nullptr; c->tables_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_tables, tab_bytes));
+        c->tables_cap = tab_bytes;
+    }
+    RSB_CUDA(cudaMemcpyAsync(c->d_mats, mats.data(), (size_t)nm * sizeof(Material), cudaMemcpyHostToDevice, st));
+    RSB_CUDA(cudaMemcpyAsync(c->d_tables, spectral->tables, (size_t)nm * spectral->bins * 8, cudaMemcpyHostToDevice, st));
+    // the two host staging buffers above are stack/heap temporaries: make the copies complete before returning
+    RSB_CUDA(cudaStreamSynchronize(st));
+
+    RenderArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sc = ds->sc;
+    a.sp.mats = c->d_mats;
+    a.sp.tables = c->d_tables;
+    a.sp.bins = spectral->bins;
+    a.sp.n_materials = nm;
+    a.cfg.bins = config->bins;
+    a.cfg.extinction_min_depth = config->extinction_min_depth;
+    a.cfg.max_depth = config->max_depth;
+    a.cfg.importance_sampling = config->importance_sampling;
+    a.cfg.min_wavelength = config->min_wavelength;
+    a.cfg.max_wavelength = config->max_wavelength;
+    a.cfg.extinction_prob = config->extinction_prob;
+    a.cfg.important_path_weight = config->important_path_weight;
+    a.cfg.max_distance = config->max_distance;
+    a.cam.nx = camera->nx;
+    a.cam.ny = camera->ny;
+    a.cam.pixel_samples = camera->pixel_samples;
+    a.cam.image_delta = camera->image_delta;
+    a.cam.image_start_x = camera->image_start_x;
+    a.cam.image_start_y = camera->image_start_y;
+    a.cam.sensitivity = camera->sensitivity;
+    memcpy(a.cam.to_root, camera->to_root, sizeof(a.cam.to_root));
+    a.n_pixels = n_pixels;
+    a.pixels = pixels_dev;
+    a.mean = mean_dev;
+    a.variance = variance_dev;
+    a.ray_count = (unsigned long long*)ray_count_dev;
+    a.work_counter = c->d_scalars;
+    a.overflow_flag = (int32_t*)(c->d_scalars + 2);
+    a.counters = c->d_counters;
+    a.seed = rng->seed;
+    a.n_items = ds->n_world_items;
+    a.staged = ds->stage_bytes ? 1 : 0;
+    size_t smem = ds->stage_bytes;
+    if (smem + mat_bytes + tab_bytes <= kMaxStageBytes) {
+        a.tables_staged = 1;
+        smem += mat_bytes + tab_bytes;
+    }
+    // a path of D segments logs at most 3 surface + 1 roulette entries per segment plus one per enclosing
+    // dielectric; budget 6 per segment
+    long long cap = 6LL * ((long long)std::max(config->max_depth, config->extinction_min_depth) + 2);
+    a.log_capacity = (int32_t)std::min(cap, 1LL << 20);
+
+    size_t threads = 0;
+    int grid;
+    const int kBlocksCap = 8;
+    bool mt = rng->mode == RSB_RNG_MT19937_64;
+    if (mt) grid = count ? launch_render<RNG_MT19937_64, true>(c, a, kBlocksCap, smem, st, &threads)
+                         : launch_render<RNG_MT19937_64, false>(c, a, kBlocksCap, smem, st, &threads);
+    else grid = count ? launch_render<RNG_PHILOX, true>(c, a, kBlocksCap, smem, st, &threads)
+                      : launch_render<RNG_PHILOX, false>(c, a, kBlocksCap, smem, st, &threads);
+    if (threads == 0) return grid;   // error code
+    // do not launch more pixel streams than there are pixels (small frames)
+    {
+        long long need_blocks = (n_pixels + RSB_RENDER_THREADS - 1) / RSB_RENDER_THREADS;
+        if (need_blocks < grid) { grid = (int)need_blocks; threads = (size_t)grid * RSB_RENDER_THREADS; }
+    }
+    // ---- per-thread pools -------------------------------------------------------------------------
+    size_t log_need = threads * (size_t)a.log_capacity;
+    if (c->log_entries < log_need) {
+        cudaFree(c->d_log);
+        c->d_log = nullptr; c->log_entries = 0;
+        RSB_CUDA(cudaMalloc(&c->d_log, log_need * sizeof(LogEntry)));
+        c->log_entries = log_need;
+    }
+    a.log_pool = c->d_log;
+    if (mt) {
+        if (c->mt_threads < threads) {
+            cudaFree(c->d_mt);
+            c->d_mt = nullptr; c->mt_threads = 0;
+            RSB_CUDA(cudaMalloc(&c->d_mt, threads * 2 * RSB_MT_NN * sizeof(unsigned long long)));
+            c->mt_threads = threads;
+        }
+        a.mt_state = c->d_mt;
+    }
+    RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
+    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+    if (mt) {
+        if (count) k_render<RNG_MT19937_64, true><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
+        else k_render<RNG_MT19937_64, false><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
+    } else {
+        if (count) k_render<RNG_PHILOX, true><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
+        else k_render<RNG_PHILOX, false><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
+    }
+    RSB_CUDA(cudaGetLastError());
+    if (count) {
+        int rc = read_counters(c, st);
+        if (rc) return rc;
+        int32_t overflow = 0;
+        RSB_CUDA(cudaMemcpyAsync(&overflow, a.overflow_flag, 4, cudaMemcpyDeviceToHost, st));
+        RSB_CUDA(cudaStreamSynchronize(st));
+        if (overflow) return fail(RSB_ERR_OVERFLOW, "rsb_render: a path exceeded the per-path log capacity");
+    }
+    return RSB_OK;
+}
+
+int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+               const RsbRngDesc* rng, int64_t n_pixels, const int32_t* pixels, double* mean, double* variance, uint64_t* ray_count) {
+    Context* c = as_ctx(ctx);
+    if (!c || !as_scene(scene) || !camera || !config || !mean || !variance || !ray_count) return fail(RSB_ERR_ARG, "rsb_render: null argument");
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    size_t frame = (size_t)camera->nx * camera->ny * config->bins;
+    if (!pixels) n_pixels = (int64_t)camera->nx * camera->ny;
+    if (n_pixels <= 0) return RSB_OK;
+    double *d_mean = nullptr, *d_var = nullptr;
+    int32_t* d_pix = nullptr;
+    unsigned long long* d_rc = nullptr;
+    auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_pix); cudaFree(d_rc); };
+    RSB_TRY(cudaMalloc(&d_mean, frame * 8));
+    RSB_TRY(cudaMalloc(&d_var, frame * 8));
+    RSB_TRY(cudaMalloc(&d_rc, 8));
+    RSB_TRY(cudaMemsetAsync(d_rc, 0, 8, st));
+    if (pixels) {
+        // unlisted pixels must come back untouched: start from the caller's arrays
+        RSB_TRY(cudaMemcpyAsync(d_mean, mean, frame * 8, cudaMemcpyHostToDevice, st));
+        RSB_TRY(cudaMemcpyAsync(d_var, variance, frame * 8, cudaMemcpyHostToDevice, st));
+        RSB_TRY(cudaMalloc(&d_pix, n_pixels * 8));
+        RSB_TRY(cudaMemcpyAsync(d_pix, pixels, n_pixels * 8, cudaMemcpyHostToDevice, st));
+    }
+    RSB_TRY(cudaEventRecord(c->ev0, st));
+    int rc = rsb_render_dev(ctx, scene, st, camera, config, spectral, rng, n_pixels, d_pix, d_mean, d_var, (uint64_t*)d_rc, 1);
+    if (rc) { cleanup(); return rc; }
+    RSB_TRY(cudaEventRecord(c->ev1, st));
+    unsigned long long rays = 0;
+    RSB_TRY(cudaMemcpyAsync(mean, d_mean, frame * 8, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(variance, d_var, frame * 8, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaMemcpyAsync(&rays, d_rc, 8, cudaMemcpyDeviceToHost, st));
+    RSB_TRY(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    *ray_count += rays;
+    cleanup();
+    return RSB_OK;
+}
+
+int rsb_frame_combine_dev(uint64_t ctx, void* cuda_stream, int64_t n_pixels_total, int32_t frame_bins, int32_t slice_offset,
+                          int32_t slice_bins, int64_t n_pixels, const int32_t* pixels_dev, int32_t ny, const double* mean_dev,
+                          const double* variance_dev, int32_t samples, double* frame_mean_dev, double* frame_variance_dev,
+                          int32_t* frame_samples_dev) {
+    Context* c = as_ctx(ctx);
+    if (!c || !mean_dev || !variance_dev || !frame_mean_dev || !frame_variance_dev || !frame_samples_dev) return fail(RSB_ERR_ARG, "null argument");
+    if (samples < 1) return fail(RSB_ERR_ARG, "Number of samples must not be less than 1.");
+    if (slice_offset < 0 || slice_bins < 1 || slice_offset + slice_bins > frame_bins)
+        return fail(RSB_ERR_ARG, "The slice offset plus the bin count extends beyond the full bin count.");
+    if (!pixels_dev) n_pixels = n_pixels_total;
+    if (n_pixels <= 0) return RSB_OK;
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    long long total = (long long)n_pixels * slice_bins;
+    k_frame_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, ny, frame_bins, slice_offset, slice_bins, mean_dev,
+                                                                 variance_dev, samples, frame_mean_dev, frame_variance_dev, frame_samples_dev);
+    RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+int rsb_counters(uint64_t ctx, RsbCounters* out) {
+    Context* c = as_ctx(ctx);
+    if (!c || !out) return fail(RSB_ERR_ARG, "null argument");
+    *out = c->last_counters;
+    return RSB_OK;
+}
+
+int rsb_last_kernel_ms(uint64_t ctx, float* ms) {
+    Context* c = as_ctx(ctx);
+    if (!c || !ms) return fail(RSB_ERR_ARG, "null argument");
+    *ms = c->last_ms;
+    return RSB_OK;
+}
+
+}  // extern "C"

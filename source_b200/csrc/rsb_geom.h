@@ -1,0 +1,954 @@
+// rsb_geom.h -- ray/primitive intersection, kd-tree traversal, World.hit / World.contains.
+//
+// Restates, in iterative GPU form, the reference call stack of SURVEY 3.4:
+//   World.hit -> KDTree.hit -> KDTree3DCore._trace/_trace_branch -> _PrimitiveKDTree._trace_leaf
+//   -> BoundPrimitive.hit -> {Sphere,Box,Cylinder,Cone,CSG,Mesh}.hit
+// The reference recurses and allocates an Intersection per candidate; here the leaf loop keeps
+// only (t, primitive, face code) for the running closest candidate and the full intersection
+// geometry is generated once, for the winner, by re-running the same arithmetic.
+#pragma once
+#include "rsb_scene.h"
+
+namespace rsb {
+
+#define RSB_KD_STACK 64       // far-child stack entries shared by the world tree and a nested mesh tree
+#define RSB_CSG_MAX_EVENTS 12 // surface crossings materialised per CSG node (<= 6 convex leaves)
+#define RSB_CSG_MAX_DEPTH 4   // nesting of CSG operators below a world-level CSG primitive
+
+// face / surface-type codes carried from hit() to _generate_intersection()
+//  box      : code = axis*2 + (face==UPPER)         raysect/primitive/box.pyx:42-55
+//  cylinder : 0 = CYLINDER body, 1 = SLAB lower, 2 = SLAB upper   cylinder.pyx:44-55
+//  cone     : 0 = CONE, 1 = BASE                                    cone.pyx:44-47
+struct Crossing {
+    double t;
+    int32_t code;
+};
+
+struct KdStackEntry {
+    double tmax;
+    int32_t node;
+    int32_t pad;
+};
+
+// Full intersection record in the hit primitive's local space
+// (raysect/core/intersection.pxd:37-53 + mesh.pxd:37-41).
+struct Isect {
+    double t;
+    V3 hit, inside, outside, normal;
+    int32_t prim;       // world-level primitive row
+    int32_t leaf;       // row of the analytic leaf that was hit (== prim unless CSG)
+    int32_t code;       // face code | triangle id
+    int32_t exiting;
+    float u, v, w;      // mesh barycentrics (MeshIntersection)
+};
+
+// Compact result of the closest-hit search
+struct HitRec {
+    double t;
+    int32_t prim;
+    int32_t leaf;
+    int32_t code;
+    int32_t flip;       // bit0: CSG Subtract parity (normal negated, inside/outside swapped); bit1: CSG exiting flag
+    int32_t node;       // world kd-tree leaf (reference node id) in which the hit was accepted
+    int32_t mesh_node;  // mesh kd-tree leaf for mesh hits, else -1
+    float u, v, w;
+};
+
+struct TraverseStats {   // roofline counters; only touched when a kernel is built with counting on
+    unsigned long long branches, leaves, items, prim_tests, tri_tests;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Analytic primitives.  Each *_crossings returns the 0, 1 or 2 surface crossings that the
+// reference's hit() followed by next_intersection() would report for a local-space ray
+// (o, d, max_distance), in that order.
+// ---------------------------------------------------------------------------------------------
+
+// raysect/primitive/sphere.pyx:115-163
+RSB_HD int sphere_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    double radius = params[0];
+    double a = d.x * d.x + d.y * d.y + d.z * d.z;
+    double b = 2 * (d.x * o.x + d.y * o.y + d.z * o.z);
+    double c = o.x * o.x + o.y * o.y + o.z * o.z - radius * radius;
+    double t0, t1;
+    if (!solve_quadratic(a, b, c, &t0, &t1)) return 0;
+    if (t0 > t1) { double tmp = t0; t0 = t1; t1 = tmp; }
+    if (t0 > max_distance || t1 < 0.0) return 0;
+    if (t0 >= 0.0) {
+        out[0].t = t0; out[0].code = 0;
+        if (t1 <= max_distance) { out[1].t = t1; out[1].code = 0; return 2; }
+        return 1;
+    } else if (t1 <= max_distance) {
+        out[0].t = t1; out[0].code = 0;
+        return 1;
+    }
+    return 0;
+}
+
+// raysect/primitive/sphere.pyx:165-200 (_generate_intersection)
+RSB_HD void sphere_geometry(const V3& o, const V3& d, double t, Isect* is) {
+    const double EPSILON = 1e-9;
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    V3 n = normalise(hit);
+    double dx = EPSILON * n.x, dy = EPSILON * n.y, dz = EPSILON * n.z;
+    is->hit = hit;
+    is->normal = n;
+    is->inside = v3(hit.x - dx, hit.y - dy, hit.z - dz);
+    is->outside = v3(hit.x + dx, hit.y + dy, hit.z + dz);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
+// raysect/primitive/box.pyx:232-287 (_slab with face/axis tracking)
+RSB_HD void prim_box_slab(int axis, double origin, double direction, double lower, double upper,
+                          double* near_t, double* far_t, int* near_code, int* far_code) {
+    double tmin, tmax;
+    int fmin, fmax;   // -1 NO_FACE, 0 LOWER_FACE, 1 UPPER_FACE
+    if (direction != 0.0) {
+        double reciprocal = 1.0 / direction;
+        if (direction > 0) {
+            tmin = (lower - origin) * reciprocal;
+            tmax = (upper - origin) * reciprocal;
+            fmin = 0; fmax = 1;
+        } else {
+            tmin = (upper - origin) * reciprocal;
+            tmax = (lower - origin) * reciprocal;
+            fmin = 1; fmax = 0;
+        }
+    } else {
+        if (origin < lower) { tmin = -RSB_INF; tmax = -RSB_INF; }
+        else if (origin > upper) { tmin = RSB_INF; tmax = RSB_INF; }
+        else { tmin = -RSB_INF; tmax = RSB_INF; }
+        fmin = -1; fmax = -1;
+    }
+    // code = axis*2 + upper; NO_FACE is encoded as "upper" because the reference's normal
+    // selection is `-1 if face == LOWER_FACE else +1` (box.pyx:303-306)
+    if (tmin > *near_t) { *near_t = tmin; *near_code = axis * 2 + (fmin == 0 ? 0 : 1); }
+    if (tmax < *far_t) { *far_t = tmax; *far_code = axis * 2 + (fmax == 0 ? 0 : 1); }
+}
+
+// raysect/primitive/box.pyx:157-219
+RSB_HD int box_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    double near_t = -RSB_INF, far_t = RSB_INF;
+    int near_code = 0, far_code = 0;
+    prim_box_slab(0, o.x, d.x, params[0], params[3], &near_t, &far_t, &near_code, &far_code);
+    prim_box_slab(1, o.y, d.y, params[1], params[4], &near_t, &far_t, &near_code, &far_code);
+    prim_box_slab(2, o.z, d.z, params[2], params[5], &near_t, &far_t, &near_code, &far_code);
+    if (near_t > far_t) return 0;
+    if (near_t > max_distance || far_t < 0.0) return 0;
+    if (near_t >= 0.0) {
+        out[0].t = near_t; out[0].code = near_code;
+        if (far_t <= max_distance) { out[1].t = far_t; out[1].code = far_code; return 2; }
+        return 1;
+    } else if (far_t <= max_distance) {
+        out[0].t = far_t; out[0].code = far_code;
+        return 1;
+    }
+    return 0;
+}
+
+// raysect/primitive/box.pyx:330-342 (_interior_offset)
+RSB_HD double box_interior_offset(double hit, double lower, double upper) {
+    const double EPSILON = 1e-9;
+    if (fabs(hit - lower) < EPSILON) return EPSILON;
+    else if (fabs(hit - upper) < EPSILON) return -EPSILON;
+    return 0.0;
+}
+
+// raysect/primitive/box.pyx:289-328 (_generate_intersection)
+RSB_HD void box_geometry(const double* params, const V3& o, const V3& d, double t, int code, Isect* is) {
+    const double EPSILON = 1e-9;
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    int axis = code >> 1;
+    double s = (code & 1) ? 1.0 : -1.0;
+    V3 n = v3(0, 0, 0);
+    if (axis == 0) n.x = s; else if (axis == 1) n.y = s; else n.z = s;
+    is->hit = hit;
+    is->normal = n;
+    is->inside = v3(hit.x + box_interior_offset(hit.x, params[0], params[3]),
+                    hit.y + box_interior_offset(hit.y, params[1], params[4]),
+                    hit.z + box_interior_offset(hit.z, params[2], params[5]));
+    is->outside = v3(hit.x + EPSILON * n.x, hit.y + EPSILON * n.y, hit.z + EPSILON * n.z);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
+// raysect/primitive/cylinder.pyx:148-271
+RSB_HD int cylinder_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    double radius = params[0], height = params[1];
+    double near_t, far_t;
+    int near_code, far_code;   // 0 body, 1 lower slab, 2 upper slab
+    if (d.x == 0 && d.y == 0) {
+        // ray parallel to the axis: inside the infinite cylinder or a miss (cylinder.pyx:166-181)
+        if ((o.x * o.x + o.y * o.y) <= (radius * radius)) {
+            near_t = -RSB_INF; far_t = RSB_INF;
+            // NO_TYPE/NO_FACE: the reference's normal selection falls to "slab, not LOWER_FACE" => +z
+            near_code = 2; far_code = 2;
+        } else {
+            return 0;
+        }
+    } else {
+        double a = d.x * d.x + d.y * d.y;
+        double b = 2.0 * (d.x * o.x + d.y * o.y);
+        double c = o.x * o.x + o.y * o.y - radius * radius;
+        double t0, t1;
+        if (!solve_quadratic(a, b, c, &t0, &t1)) return 0;
+        if (t0 > t1) { double tmp = t0; t0 = t1; t1 = tmp; }
+        near_t = t0; far_t = t1;
+        near_code = 0; far_code = 0;
+    }
+    if (d.z != 0.0) {
+        double temp = 1.0 / d.z;
+        double t0, t1;
+        int f0, f1;
+        if (d.z > 0) {
+            t0 = -o.z * temp;
+            t1 = (height - o.z) * temp;
+            f0 = 1; f1 = 2;
+        } else {
+            t0 = (height - o.z) * temp;
+            t1 = -o.z * temp;
+            f0 = 2; f1 = 1;
+        }
+        if (t0 > near_t) { near_t = t0; near_code = f0; }
+        if (t1 < far_t) { far_t = t1; far_code = f1; }
+    }
+    if (near_t > far_t) return 0;
+    if (near_t > max_distance || far_t < 0.0) return 0;
+    if (near_t >= 0.0) {
+        out[0].t = near_t; out[0].code = near_code;
+        if (far_t <= max_distance) { out[1].t = far_t; out[1].code = far_code; return 2; }
+        return 1;
+    } else if (far_t <= max_distance) {
+        out[0].t = far_t; out[0].code = far_code;
+        return 1;
+    }
+    return 0;
+}
+
+// raysect/primitive/cylinder.pyx:282-349 (_generate_intersection, _interior_offset)
+RSB_HD void cylinder_geometry(const double* params, const V3& o, const V3& d, double t, int code, Isect* is) {
+    const double EPSILON = 1e-9;
+    double radius = params[0], height = params[1];
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    V3 n;
+    if (code == 0) n = normalise(v3(hit.x, hit.y, 0));
+    else if (code == 1) n = v3(0, 0, -1);
+    else n = v3(0, 0, 1);
+    double x, y, z;
+    if (code == 0) {
+        x = -EPSILON * n.x;
+        y = -EPSILON * n.y;
+    } else {
+        x = 0; y = 0;
+        if (hit.x != 0.0 && hit.y != 0.0) {
+            double len = sqrt(hit.x * hit.x + hit.y * hit.y);
+            if ((len - radius) < EPSILON) {
+                len = 1.0 / len;
+                x = -EPSILON * len * hit.x;
+                y = -EPSILON * len * hit.y;
+            }
+        }
+    }
+    if (fabs(hit.z) < EPSILON) z = EPSILON;
+    else if (fabs(hit.z - height) < EPSILON) z = -EPSILON;
+    else z = 0;
+    is->hit = hit;
+    is->normal = n;
+    is->inside = v3(hit.x + x, hit.y + y, hit.z + z);
+    is->outside = v3(hit.x + EPSILON * n.x, hit.y + EPSILON * n.y, hit.z + EPSILON * n.z);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
+// raysect/primitive/cone.pyx:142-262.  Codes: 0 CONE, 1 BASE.
+RSB_HD int cone_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    double radius = params[0], height = params[1];
+    double k = radius / height;
+    k = k * k;
+    double a = d.x * d.x + d.y * d.y - k * d.z * d.z;
+    double b = 2 * (d.x * o.x + d.y * o.y - k * d.z * (o.z - height));
+    double c = o.x * o.x + o.y * o.y - k * (o.z - height) * (o.z - height);
+    double t0, t1;
+    int t0_type, t1_type;
+    if (!solve_quadratic(a, b, c, &t0, &t1)) return 0;
+    if (t0 == t1) {
+        // ray passes through the tip (cone.pyx:176-191, including the reference's
+        // `direction.y**2` placement at :185, reproduced verbatim)
+        t0 = -b / (2.0 * a);
+        t0_type = 0;
+        k = -o.z / d.z;
+        double ex = o.x + k * d.x;
+        double r2 = ex * ex + (o.y + k * (d.y * d.y));
+        if (r2 <= (radius * radius)) { t1 = k; t1_type = 1; }
+        else { t1 = t0; t1_type = t0_type; }
+    } else {
+        double t0_z = o.z + t0 * d.z;
+        double t1_z = o.z + t1 * d.z;
+        bool t0_outside = t0_z < 0 || t0_z > height;
+        bool t1_outside = t1_z < 0 || t1_z > height;
+        if (t0_outside && t1_outside) return 0;
+        else if (!t0_outside && t1_outside) { t0_type = 0; t1 = -o.z / d.z; t1_type = 1; }
+        else if (t0_outside && !t1_outside) { t0_type = 1; t0 = -o.z / d.z; t1_type = 0; }
+        else { t0_type = 0; t1_type = 0; }
+    }
+    if (t0 > t1) {
+        double tmp = t0; t0 = t1; t1 = tmp;
+        int ti = t0_type; t0_type = t1_type; t1_type = ti;
+    }
+    if (t0 > max_distance || t1 < 0.0) return 0;
+    if (t0 >= 0.0) {
+        out[0].t = t0; out[0].code = t0_type;
+        if (t1 <= max_distance) { out[1].t = t1; out[1].code = t1_type; return 2; }
+        return 1;
+    } else if (t1 <= max_distance) {
+        out[0].t = t1; out[0].code = t1_type;
+        return 1;
+    }
+    return 0;
+}
+
+// raysect/primitive/cone.pyx:273-357 (_generate_intersection, _interior_point)
+RSB_HD void cone_geometry(const double* params, const V3& o, const V3& d, double t, int code, Isect* is) {
+    const double EPSILON = 1e-9;
+    double radius = params[0], height = params[1];
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    V3 n;
+    if (code == 1) {
+        n = v3(0, 0, -1);
+    } else if (hit.z >= height) {
+        n = v3(0, 0, 1);
+    } else {
+        double a = hit.y / hit.x;
+        double b = height / sqrt(1 + a * a);
+        b = hit.x < 0 ? -b : b;
+        n = normalise(v3(b, b * a, radius));
+    }
+    // _interior_point
+    V3 inside;
+    {
+        double x = hit.x - EPSILON * n.x;
+        double y = hit.y - EPSILON * n.y;
+        double z = hit.z - EPSILON * n.z;
+        double k = radius / height;
+        double inner_height = height - EPSILON * sqrt(1 + k * k) / k;
+        if (z > inner_height) {
+            inside = v3(0, 0, inner_height);
+        } else if (z < EPSILON) {
+            double inner_radius = k * (height - EPSILON) - EPSILON * sqrt(1 + k * k);
+            double scale = inner_radius / sqrt(hit.x * hit.x + hit.y * hit.y);
+            inside = v3(scale * hit.x, scale * hit.y, EPSILON);
+        } else {
+            inside = v3(x, y, z);
+        }
+    }
+    is->hit = hit;
+    is->normal = n;
+    is->inside = inside;
+    is->outside = v3(hit.x + EPSILON * n.x, hit.y + EPSILON * n.y, hit.z + EPSILON * n.z);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
+RSB_HD int analytic_crossings(int type, const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    switch (type) {
+        case PRIM_SPHERE: return sphere_crossings(params, o, d, max_distance, out);
+        case PRIM_BOX: return box_crossings(params, o, d, max_distance, out);
+        case PRIM_CYLINDER: return cylinder_crossings(params, o, d, max_distance, out);
+        case PRIM_CONE: return cone_crossings(params, o, d, max_distance, out);
+        default: return 0;
+    }
+}
+
+RSB_HD void analytic_geometry(int type, const double* params, const V3& o, const V3& d, double t, int code, Isect* is) {
+    switch (type) {
+        case PRIM_SPHERE: sphere_geometry(o, d, t, is); break;
+        case PRIM_BOX: box_geometry(params, o, d, t, code, is); break;
+        case PRIM_CYLINDER: cylinder_geometry(params, o, d, t, code, is); break;
+        default: cone_geometry(params, o, d, t, code, is); break;
+    }
+}
+
+// point-in-primitive tests on a LOCAL-space point
+// sphere.pyx:202-214, box.pyx:344-359, cylinder.pyx:351-367, cone.pyx:359-380
+RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
+    switch (type) {
+        case PRIM_SPHERE: {
+            double d2 = p.x * p.x + p.y * p.y + p.z * p.z;
+            return d2 <= params[0] * params[0];
+        }
+        case PRIM_BOX: {
+            if ((p.x < params[0]) || (p.x > params[3])) return false;
+            if ((p.y < params[1]) || (p.y > params[4])) return false;
+            if ((p.z < params[2]) || (p.z > params[5])) return false;
+            return true;
+        }
+        case PRIM_CYLINDER: {
+            bool slab = (0.0 <= p.z) && (p.z <= params[1]);
+            return slab && ((p.x * p.x + p.y * p.y) <= (params[0] * params[0]));
+        }
+        case PRIM_CONE: {
+            double radius = params[0], height = params[1];
+            if (p.z < 0 || p.z > height) return false;
+            double pr2 = p.x * p.x + p.y * p.y;
+            double cr = (height - p.z) * radius / height;
+            cr *= cr;
+            return pr2 <= cr;
+        }
+        default: return false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kd-tree traversal (raysect/core/math/spatial/kdtree3d.pyx:589-700), recursion unrolled onto an
+// explicit far-child stack.  `leaf(item_offset, item_count, max_range)` returns true on a hit.
+// When the near subtree finishes without a hit the far child resumes with
+// min_range = plane_distance, which equals the max_range of the last leaf visited (front-to-back
+// order), so only (node, max_range) is stacked.
+// ---------------------------------------------------------------------------------------------
+template <class LeafFn, class Stats>
+RSB_HD bool kd_trace(const KdTree& tree, const V3& o, const V3& d, KdStackEntry* stack, LeafFn& leaf, Stats& stats, int* hit_node) {
+    double min_range, max_range;
+    if (!box_intersect(tree.bounds, o, d, &min_range, &max_range)) return false;
+    int node = 0;
+    int sp = 0;
+    for (;;) {
+        KdNode n = tree.nodes[node];
+        if (n.axis < 0) {
+            stats.leaf(n.leaf.item_count);
+            if (leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) { *hit_node = node; return true; }
+            if (sp == 0) return false;
+            --sp;
+            node = stack[sp].node;
+            min_range = max_range;
+            max_range = stack[sp].tmax;
+            continue;
+        }
+        stats.branch();
+        double origin = v3_get(o, n.axis);
+        double direction = v3_get(d, n.axis);
+        int lower_id = node + 1;
+        int upper_id = n.upper;
+        if (direction == 0) {
+            node = (origin < n.split) ? lower_id : upper_id;
+            continue;
+        }
+        double plane_distance = (n.split - origin) / direction;
+        bool below_split = origin < n.split || (origin == n.split && direction < 0);
+        int near_id = below_split ? lower_id : upper_id;
+        int far_id = below_split ? upper_id : lower_id;
+        if (plane_distance > max_range || plane_distance <= 0) { node = near_id; continue; }
+        if (plane_distance < min_range) { node = far_id; continue; }
+        stack[sp].node = far_id;
+        stack[sp].tmax = max_range;
+        ++sp;
+        node = near_id;
+        max_range = plane_distance;
+    }
+}
+
+// raysect/core/math/spatial/kdtree3d.pyx:736-792 (_items_containing*): descend to the one leaf
+// holding the point.  Returns false when the point is outside the tree bounds.
+RSB_HD bool kd_locate(const KdTree& tree, const V3& p, int* item_offset, int* item_count) {
+    if (!box_contains(tree.bounds, p)) return false;
+    int node = 0;
+    for (;;) {
+        KdNode n = tree.nodes[node];
+        if (n.axis < 0) {
+            *item_offset = n.leaf.item_offset;
+            *item_count = n.leaf.item_count;
+            return true;
+        }
+        node = (v3_get(p, n.axis) < n.split) ? node + 1 : n.upper;
+    }
+}
+
+struct NoStats {
+    RSB_HD void branch() {}
+    RSB_HD void leaf(int) {}
+    RSB_HD void prim_test() {}
+    RSB_HD void tri_test() {}
+};
+
+struct CountStats {
+    unsigned long long branches = 0, leaves = 0, items = 0, prim_tests = 0, tri_tests = 0;
+    RSB_HD void branch() { ++branches; }
+    RSB_HD void leaf(int n) { ++leaves; items += (unsigned long long)n; }
+    RSB_HD void prim_test() { ++prim_tests; }
+    RSB_HD void tri_test() { ++tri_tests; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Triangle mesh (raysect/primitive/mesh/mesh.pyx:506-713): Woop-Benthin-Wald watertight test in
+// float32 with the reference's exact double promotions.
+// ---------------------------------------------------------------------------------------------
+struct RaySpace {
+    int ix, iy, iz;
+    float sx, sy, sz;
+};
+
+// mesh.pyx:566-610 (_calc_rayspace_transform)
+RSB_HD RaySpace mesh_rayspace(const V3& d) {
+    RaySpace rs;
+    int ix, iy, iz;
+    if (fabs(d.x) > fabs(d.y) && fabs(d.x) > fabs(d.z)) { ix = 1; iy = 2; iz = 0; }
+    else if (fabs(d.y) > fabs(d.x) && fabs(d.y) > fabs(d.z)) { ix = 2; iy = 0; iz = 1; }
+    else { ix = 0; iy = 1; iz = 2; }
+    float rdz = (float)v3_get(d, iz);
+    if (rdz < 0.0f) { int tmp = ix; ix = iy; iy = tmp; }
+    rs.sz = (float)(1.0 / (double)rdz);
+    rs.sx = (float)(v3_get(d, ix) * (double)rs.sz);
+    rs.sy = (float)(v3_get(d, iy) * (double)rs.sz);
+    rs.ix = ix; rs.iy = iy; rs.iz = iz;
+    return rs;
+}
+
+RSB_HD float f3_get(const float* v, int axis) { return axis == 0 ? v[0] : (axis == 1 ? v[1] : v[2]); }
+
+// mesh.pyx:616-713 (_hit_triangle).  out = (u, v, w, t) as float32.
+RSB_HD bool mesh_hit_triangle(const F4* tri, const V3& o, double max_distance, const RaySpace& rs, float* out) {
+    F4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
+    // centre on the ray origin: float vertex minus double origin, rounded back to float (mesh.pyx:639-649)
+    float v1[3], v2[3], v3_[3];
+    v1[0] = (float)((double)q0.x - o.x); v1[1] = (float)((double)q0.y - o.y); v1[2] = (float)((double)q0.z - o.z);
+    v2[0] = (float)((double)q0.w - o.x); v2[1] = (float)((double)q1.x - o.y); v2[2] = (float)((double)q1.y - o.z);
+    v3_[0] = (float)((double)q1.z - o.x); v3_[1] = (float)((double)q1.w - o.y); v3_[2] = (float)((double)q2.x - o.z);
+    float sx = rs.sx, sy = rs.sy, sz = rs.sz;
+    float v1z = f3_get(v1, rs.iz), v2z = f3_get(v2, rs.iz), v3z = f3_get(v3_, rs.iz);
+    float x1 = f3_get(v1, rs.ix) - sx * v1z;
+    float x2 = f3_get(v2, rs.ix) - sx * v2z;
+    float x3 = f3_get(v3_, rs.ix) - sx * v3z;
+    float y1 = f3_get(v1, rs.iy) - sy * v1z;
+    float y2 = f3_get(v2, rs.iy) - sy * v2z;
+    float y3 = f3_get(v3_, rs.iy) - sy * v3z;
+    float u = x3 * y2 - y3 * x2;
+    float v = x1 * y3 - y1 * x3;
+    float w = x2 * y1 - y2 * x1;
+    if (u == 0.0f || v == 0.0f || w == 0.0f) {
+        u = (float)((double)x3 * (double)y2 - (double)y3 * (double)x2);
+        v = (float)((double)x1 * (double)y3 - (double)y1 * (double)x3);
+        w = (float)((double)x2 * (double)y1 - (double)y2 * (double)x1);
+    }
+    if ((u < 0.0f || v < 0.0f || w < 0.0f) && (u > 0.0f || v > 0.0f || w > 0.0f)) return false;
+    float det = u + v + w;
+    if (det == 0.0f) return false;
+    float z1 = sz * v1z;
+    float z2 = sz * v2z;
+    float z3 = sz * v3z;
+    float t = u * z1 + v * z2 + w * z3;
+    if (det > 0.0f) {
+        if (t < 0.0f || (double)t > max_distance * (double)det) return false;
+    } else {
+        if (t > 0.0f || (double)t < max_distance * (double)det) return false;
+    }
+    float det_reciprocal = (float)(1.0 / (double)det);
+    out[0] = u * det_reciprocal;
+    out[1] = v * det_reciprocal;
+    out[2] = w * det_reciprocal;
+    out[3] = t * det_reciprocal;
+    return true;
+}
+
+struct MeshHit {
+    double t;       // == (double)(float)t, mesh.pyx:557-561
+    int32_t tri;
+    int32_t node;   // mesh kd-tree leaf that produced the hit
+    float u, v, w;
+};
+
+template <class Stats>
+struct MeshLeaf {
+    const Mesh* mesh;
+    V3 o;
+    double max_distance;
+    RaySpace rs;
+    MeshHit* result;
+    Stats* stats;
+    // mesh.pyx:520-563 (_trace_leaf): strict `t < distance`, first of equal-t triangles wins
+    RSB_HD bool operator()(int offset, int count, double max_range) {
+        double distance = max_distance < max_range ? max_distance : max_range;   // min(ray.max_distance, max_range)
+        int closest = -1;
+        float cu = 0, cv = 0, cw = 0;
+        for (int i = 0; i < count; ++i) {
+            int tri = mesh->tree.items[offset + i];
+            float h[4];
+            stats->tri_test();
+            if (mesh_hit_triangle(mesh->tri + 3 * (size_t)tri, o, max_distance, rs, h)) {
+                double t = (double)h[3];
+                if (t < distance) {
+                    distance = t;
+                    closest = tri;
+                    cu = h[0]; cv = h[1]; cw = h[2];
+                }
+            }
+        }
+        if (closest < 0) return false;
+        result->t = (double)(float)distance;
+        result->tri = closest;
+        result->u = cu; result->v = cv; result->w = cw;
+        return true;
+    }
+};
+
+// mesh.pyx:506-518 (MeshData.trace) on a mesh-local ray
+template <class Stats>
+RSB_HD bool mesh_trace(const Mesh& mesh, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, MeshHit* out, Stats& stats) {
+    MeshLeaf<Stats> leaf;
+    leaf.mesh = &mesh;
+    leaf.o = o;
+    leaf.max_distance = max_distance;
+    leaf.rs = mesh_rayspace(d);
+    leaf.result = out;
+    leaf.stats = &stats;
+    return kd_trace(mesh.tree, o, d, stack, leaf, stats, &out->node);
+}
+
+// mesh.pyx:718-800 (calc_intersection, _intersection_normal) in mesh-local space
+RSB_HD void mesh_geometry(const Mesh& mesh, const V3& o, const V3& d, const MeshHit& h, Isect* is) {
+    const double EPSILON = 1e-6;
+    F4 q2 = mesh.tri[3 * (size_t)h.tri + 2];
+    V3 fn = v3((double)q2.y, (double)q2.z, (double)q2.w);
+    double t = h.t;
+    V3 hit = v3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);
+    is->hit = hit;
+    is->inside = v3(hit.x - fn.x * EPSILON, hit.y - fn.y * EPSILON, hit.z - fn.z * EPSILON);
+    is->outside = v3(hit.x + fn.x * EPSILON, hit.y + fn.y * EPSILON, hit.z + fn.z * EPSILON);
+    V3 n;
+    if (mesh.smoothing && mesh.vnormals != nullptr) {
+        const int32_t* row = mesh.tri_idx + (size_t)h.tri * mesh.idx_stride;
+        const float* n1 = mesh.vnormals + 3 * (size_t)row[3];
+        const float* n2 = mesh.vnormals + 3 * (size_t)row[4];
+        const float* n3 = mesh.vnormals + 3 * (size_t)row[5];
+        // float32 arithmetic, left to right (mesh.pyx:788-792)
+        float nx = h.u * n1[0] + h.v * n2[0] + h.w * n3[0];
+        float ny = h.u * n1[1] + h.v * n2[1] + h.w * n3[1];
+        float nz = h.u * n1[2] + h.v * n2[2] + h.w * n3[2];
+        n = normalise(v3((double)nx, (double)ny, (double)nz));
+    } else {
+        n = normalise(fn);
+    }
+    is->normal = n;
+    is->exiting = dot(d, fn) > 0.0;   // strict, mesh.pyx:756
+    is->code = h.tri;
+    is->u = h.u; is->v = h.v; is->w = h.w;
+}
+
+// mesh.pyx:805-830 (MeshData.contains): +z ray, orientation of the first face hit
+template <class Stats>
+RSB_HD bool mesh_contains(const Mesh& mesh, const V3& p, KdStackEntry* stack, Stats& stats) {
+    MeshHit h;
+    if (!mesh_trace(mesh, p, v3(0, 0, 1), RSB_INF, stack, &h, stats)) return false;
+    return mesh.tri[3 * (size_t)h.tri + 2].w > 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSG (raysect/primitive/csg.pyx:132-241 + operator rules :326-348, :424-446, :526-568).
+// The reference pulls crossings lazily from two stateful children; all analytic leaves are convex
+// (<= 2 crossings), so each node's full, ordered crossing list is materialised bottom-up and the
+// operator automaton is run over the two child lists.  The emitted sequence is exactly what
+// hit() + repeated next_intersection() would yield.
+// ---------------------------------------------------------------------------------------------
+struct CsgEvent {
+    double t;
+    int32_t leaf;       // analytic leaf row
+    int16_t code;
+    int8_t exiting;
+    int8_t flip;
+};
+
+RSB_HD bool csg_valid(int op, bool inside_a, bool inside_b, bool closest_is_a) {
+    if (op == PRIM_UNION) {
+        if (!inside_a && !inside_b) return true;
+        else if (inside_a && !inside_b && closest_is_a) return true;
+        else if (!inside_a && inside_b && !closest_is_a) return true;
+        return false;
+    } else if (op == PRIM_INTERSECT) {
+        if (inside_a && inside_b) return true;
+        else if (inside_a && !inside_b && !closest_is_a) return true;
+        else if (!inside_a && inside_b && closest_is_a) return true;
+        return false;
+    } else {
+        if (!inside_a && !inside_b && closest_is_a) return true;
+        else if (inside_a && !inside_b) return true;
+        else if (inside_a && inside_b && !closest_is_a) return true;
+        return false;
+    }
+}
+
+// Crossings of primitive row `id` for a ray (o, d) given in the row's PARENT space, behind the
+// BoundPrimitive AABB pre-test (raysect/core/acceleration/boundprimitive.pyx:42-51).
+// Children always see max_distance = +inf (csg.pyx:142-144).
+template <int DEPTH>
+struct CsgEval {
+    static RSB_HD_NOINLINE int run(const Scene& sc, int id, const V3& o, const V3& d, CsgEvent* out) {
+        const Prim& p = sc.prims[id];
+        if (!box_hit(p.bbox, o, d)) return 0;
+        V3 lo = xform_point(p.to_local, o);
+        V3 ld = xform_vector(p.to_local, d);
+        if (p.type <= PRIM_CONE) {
+            Crossing c[2];
+            int n = analytic_crossings(p.type, p.params, lo, ld, RSB_INF, c);
+            for (int i = 0; i < n; ++i) {
+                Isect is;
+                analytic_geometry(p.type, p.params, lo, ld, c[i].t, c[i].code, &is);
+                out[i].t = c[i].t;
+                out[i].leaf = id;
+                out[i].code = (int16_t)c[i].code;
+                out[i].exiting = (int8_t)is.exiting;
+                out[i].flip = 0;
+            }
+            return n;
+        }
+        if (p.type == PRIM_MESH) return 0;   // rejected at scene creation
+        CsgEvent a[RSB_CSG_MAX_EVENTS], b[RSB_CSG_MAX_EVENTS];
+        int na = CsgEval<DEPTH - 1>::run(sc, p.child_a, lo, ld, a);
+        if (na == 0 && p.type != PRIM_UNION) return 0;   // terminate_early (csg.pyx:421-422, 523-524)
+        int nb = CsgEval<DEPTH - 1>::run(sc, p.child_b, lo, ld, b);
+        int ia = 0, ib = 0, n = 0;
+        while (ia < na || ib < nb) {
+            bool has_a = ia < na, has_b = ib < nb;
+            bool closest_is_a = has_a && (!has_b || a[ia].t < b[ib].t);   // _closest_intersection, csg.pyx:226-234
+            bool inside_a = has_a && a[ia].exiting;
+            bool inside_b = has_b && b[ib].exiting;
+            if (csg_valid(p.type, inside_a, inside_b, closest_is_a) && n < RSB_CSG_MAX_EVENTS) {
+                CsgEvent e = closest_is_a ? a[ia] : b[ib];
+                if (p.type == PRIM_SUBTRACT && !closest_is_a) {   // _modify_intersection, csg.pyx:550-568
+                    e.exiting = !e.exiting;
+                    e.flip ^= 1;
+                }
+                out[n++] = e;
+            }
+            if (closest_is_a) ++ia; else ++ib;
+        }
+        return n;
+    }
+};
+
+template <>
+struct CsgEval<0> {
+    static RSB_HD int run(const Scene& sc, int id, const V3& o, const V3& d, CsgEvent* out) {
+        const Prim& p = sc.prims[id];
+        if (p.type > PRIM_CONE) return 0;   // nesting deeper than RSB_CSG_MAX_DEPTH is rejected at scene creation
+        if (!box_hit(p.bbox, o, d)) return 0;
+        V3 lo = xform_point(p.to_local, o);
+        V3 ld = xform_vector(p.to_local, d);
+        Crossing c[2];
+        int n = analytic_crossings(p.type, p.params, lo, ld, RSB_INF, c);
+        for (int i = 0; i < n; ++i) {
+            Isect is;
+            analytic_geometry(p.type, p.params, lo, ld, c[i].t, c[i].code, &is);
+            out[i].t = c[i].t;
+            out[i].leaf = id;
+            out[i].code = (int16_t)c[i].code;
+            out[i].exiting = (int8_t)is.exiting;
+            out[i].flip = 0;
+        }
+        return n;
+    }
+};
+
+// CSGPrimitive.hit for a world-level CSG row: first valid crossing, provided it lies within
+// ray.max_distance (csg.pyx:181-212); the AABB pre-test was done by the caller.
+RSB_HD_NOINLINE bool csg_first_hit(const Scene& sc, int id, const V3& o, const V3& d, double max_distance, CsgEvent* ev) {
+    const Prim& p = sc.prims[id];
+    V3 lo = xform_point(p.to_local, o);
+    V3 ld = xform_vector(p.to_local, d);
+    CsgEvent a[RSB_CSG_MAX_EVENTS], b[RSB_CSG_MAX_EVENTS];
+    int na = CsgEval<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_a, lo, ld, a);
+    if (na == 0 && p.type != PRIM_UNION) return false;
+    int nb = CsgEval<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_b, lo, ld, b);
+    int ia = 0, ib = 0;
+    while (ia < na || ib < nb) {
+        bool has_a = ia < na, has_b = ib < nb;
+        bool closest_is_a = has_a && (!has_b || a[ia].t < b[ib].t);
+        bool inside_a = has_a && a[ia].exiting;
+        bool inside_b = has_b && b[ib].exiting;
+        if (csg_valid(p.type, inside_a, inside_b, closest_is_a)) {
+            CsgEvent e = closest_is_a ? a[ia] : b[ib];
+            if (!(e.t <= max_distance)) return false;
+            if (p.type == PRIM_SUBTRACT && !closest_is_a) {
+                e.exiting = !e.exiting;
+                e.flip ^= 1;
+            }
+            *ev = e;
+            return true;
+        }
+        if (closest_is_a) ++ia; else ++ib;
+    }
+    return false;
+}
+
+// CSG contains (csg.pyx:350-352, 448-450, 570-572) behind BoundPrimitive.contains; p in parent space
+template <int DEPTH>
+struct CsgContains {
+    static RSB_HD_NOINLINE bool run(const Scene& sc, int id, const V3& pt) {
+        const Prim& p = sc.prims[id];
+        if (!box_contains(p.bbox, pt)) return false;
+        V3 lp = xform_point(p.to_local, pt);
+        if (p.type <= PRIM_CONE) return analytic_contains(p.type, p.params, lp);
+        if (p.type == PRIM_MESH) return false;
+        bool ca = CsgContains<DEPTH - 1>::run(sc, p.child_a, lp);
+        if (p.type == PRIM_UNION) return ca || CsgContains<DEPTH - 1>::run(sc, p.child_b, lp);
+        if (p.type == PRIM_INTERSECT) return ca && CsgContains<DEPTH - 1>::run(sc, p.child_b, lp);
+        return ca && !CsgContains<DEPTH - 1>::run(sc, p.child_b, lp);
+    }
+};
+template <>
+struct CsgContains<0> {
+    static RSB_HD bool run(const Scene& sc, int id, const V3& pt) {
+        const Prim& p = sc.prims[id];
+        if (p.type > PRIM_CONE) return false;
+        if (!box_contains(p.bbox, pt)) return false;
+        return analytic_contains(p.type, p.params, xform_point(p.to_local, pt));
+    }
+};
+
+// Geometry of a CSG crossing, re-expressed level by level up to the world-level CSG primitive's
+// local space exactly as _identify_intersection does (csg.pyx:200-208): points by each child's
+// to_root, the normal by the inverse-transpose of that same matrix.
+RSB_HD_NOINLINE void csg_geometry(const Scene& sc, int top, const CsgEvent& ev, const V3& o, const V3& d, Isect* is) {
+    // chain of rows from the leaf up to (excluding) the world-level CSG primitive
+    int chain[RSB_CSG_MAX_DEPTH + 1];
+    int n = 0;
+    for (int id = ev.leaf; id != top && n <= RSB_CSG_MAX_DEPTH; id = sc.prims[id].parent) chain[n++] = id;
+    // ray into the leaf's local space, through every level top-down
+    V3 lo = xform_point(sc.prims[top].to_local, o);
+    V3 ld = xform_vector(sc.prims[top].to_local, d);
+    for (int i = n - 1; i >= 0; --i) {
+        const Prim& p = sc.prims[chain[i]];
+        lo = xform_point(p.to_local, lo);
+        ld = xform_vector(p.to_local, ld);
+    }
+    const Prim& leaf = sc.prims[ev.leaf];
+    analytic_geometry(leaf.type, leaf.params, lo, ld, ev.t, ev.code, is);
+    for (int i = 0; i < n; ++i) {
+        const Prim& p = sc.prims[chain[i]];
+        is->hit = xform_point(p.to_root, is->hit);
+        is->inside = xform_point(p.to_root, is->inside);
+        is->outside = xform_point(p.to_root, is->outside);
+        is->normal = xform_normal_with_inverse(p.root_inv, is->normal);
+    }
+    if (ev.flip) {
+        V3 tmp = is->inside; is->inside = is->outside; is->outside = tmp;
+        is->normal = v3(-is->normal.x, -is->normal.y, -is->normal.z);
+    }
+    is->exiting = ev.exiting;
+    is->code = ev.code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// World.hit  (raysect/core/scenegraph/world.pyx:125-146 -> acceleration/kdtree.pyx:73-175)
+// ---------------------------------------------------------------------------------------------
+template <class Stats>
+struct WorldLeaf {
+    const Scene* sc;
+    V3 o, d;
+    double max_distance;
+    KdStackEntry* mesh_stack;   // stack space above the world traversal's own entries
+    HitRec* best;
+    Stats* stats;
+
+    // _PrimitiveKDTree._trace_leaf (acceleration/kdtree.pyx:73-122): `<=` => last of equal-t items wins
+    RSB_HD bool operator()(int offset, int count, double max_range) {
+        double distance = max_distance < max_range ? max_distance : max_range;
+        bool found = false;
+        for (int i = 0; i < count; ++i) {
+            int id = sc->world.items[offset + i];
+            const Prim& p = sc->prims[id];
+            stats->prim_test();
+            if (!box_hit(p.bbox, o, d)) continue;   // BoundPrimitive.hit, boundprimitive.pyx:42-51
+            if (p.type <= PRIM_CONE) {
+                V3 lo = xform_point(p.to_local, o);
+                V3 ld = xform_vector(p.to_local, d);
+                Crossing c[2];
+                if (analytic_crossings(p.type, p.params, lo, ld, max_distance, c) > 0 && c[0].t <= distance) {
+                    distance = c[0].t;
+                    best->t = c[0].t; best->prim = id; best->leaf = id; best->code = c[0].code; best->flip = 0;
+                    best->mesh_node = -1;
+                    found = true;
+                }
+            } else if (p.type == PRIM_MESH) {
+                V3 lo = xform_point(p.to_local, o);
+                V3 ld = xform_vector(p.to_local, d);
+                MeshHit mh;
+                if (mesh_trace(sc->meshes[p.mesh], lo, ld, max_distance, mesh_stack, &mh, *stats) && mh.t <= distance) {
+                    distance = mh.t;
+                    best->t = mh.t; best->prim = id; best->leaf = id; best->code = mh.tri; best->flip = 0;
+                    best->mesh_node = mh.node;
+                    best->u = mh.u; best->v = mh.v; best->w = mh.w;
+                    found = true;
+                }
+            } else {
+                CsgEvent ev;
+                if (csg_first_hit(*sc, id, o, d, max_distance, &ev) && ev.t <= distance) {
+                    distance = ev.t;
+                    best->t = ev.t; best->prim = id; best->leaf = ev.leaf; best->code = ev.code;
+                    best->flip = ev.flip | (ev.exiting << 1);
+                    best->mesh_node = -1;
+                    found = true;
+                }
+            }
+        }
+        return found;
+    }
+};
+
+// Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries.
+template <class Stats>
+RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats) {
+    WorldLeaf<Stats> leaf;
+    leaf.sc = &sc;
+    leaf.o = o;
+    leaf.d = d;
+    leaf.max_distance = max_distance;
+    leaf.mesh_stack = stack + (RSB_KD_STACK / 2);
+    leaf.best = rec;
+    leaf.stats = &stats;
+    rec->u = rec->v = rec->w = 0.0f;
+    rec->node = -1;
+    rec->mesh_node = -1;
+    return kd_trace(sc.world, o, d, stack, leaf, stats, &rec->node);
+}
+
+// Intersection geometry for a HitRec, in the world-level primitive's local space.
+RSB_HD void world_hit_geometry(const Scene& sc, const V3& o, const V3& d, const HitRec& rec, Isect* is) {
+    const Prim& p = sc.prims[rec.prim];
+    is->t = rec.t;
+    is->prim = rec.prim;
+    is->leaf = rec.leaf;
+    is->code = rec.code;
+    is->u = rec.u; is->v = rec.v; is->w = rec.w;
+    if (p.type <= PRIM_CONE) {
+        V3 lo = xform_point(p.to_local, o);
+        V3 ld = xform_vector(p.to_local, d);
+        analytic_geometry(p.type, p.params, lo, ld, rec.t, rec.code, is);
+    } else if (p.type == PRIM_MESH) {
+        V3 lo = xform_point(p.to_local, o);
+        V3 ld = xform_vector(p.to_local, d);
+        MeshHit mh;
+        mh.t = rec.t; mh.tri = rec.code; mh.node = rec.mesh_node; mh.u = rec.u; mh.v = rec.v; mh.w = rec.w;
+        mesh_geometry(sc.meshes[p.mesh], lo, ld, mh, is);
+    } else {
+        CsgEvent ev;
+        ev.t = rec.t; ev.leaf = rec.leaf; ev.code = (int16_t)rec.code;
+        ev.flip = (int8_t)(rec.flip & 1);
+        ev.exiting = (int8_t)((rec.flip >> 1) & 1);
+        csg_geometry(sc, rec.prim, ev, o, d, is);
+    }
+}
+
+// Primitive.contains for a world-level row behind BoundPrimitive.contains (boundprimitive.pyx:62-66)
+template <class Stats>
+RSB_HD bool prim_contains(const Scene& sc, int id, const V3& pt, KdStackEntry* stack, Stats& stats) {
+    const Prim& p = sc.prims[id];
+    if (!box_contains(p.bbox, pt)) return false;
+    if (p.type <= PRIM_CONE) return analytic_contains(p.type, p.params, xform_point(p.to_local, pt));
+    if (p.type == PRIM_MESH) {
+        const Mesh& m = sc.meshes[p.mesh];
+        if (!m.closed) return false;   // mesh.pyx:1290-1292
+        return mesh_contains(m, xform_point(p.to_local, pt), stack, stats);
+    }
+    V3 lp = xform_point(p.to_local, pt);
+    bool ca = CsgContains<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_a, lp);
+    if (p.type == PRIM_UNION) return ca || CsgContains<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_b, lp);
+    if (p.type == PRIM_INTERSECT) return ca && CsgContains<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_b, lp);
+    return ca && !CsgContains<RSB_CSG_MAX_DEPTH - 1>::run(sc, p.child_b, lp);
+}
+
+}  // namespace rsb

@@ -1,0 +1,168 @@
+// rsb_math.h -- scalar fp64 building blocks of the ray/scene hot path.
+//
+// Every expression here is written in the exact operation order of the reference
+// (file:line cited per function) and the library is compiled with -fmad=false, so the
+// results are bit-identical to the reference's x86-64 (no-FMA) build for +,-,*,/,sqrt.
+// The header compiles both as CUDA device code and as plain host C++ (tests build a
+// host harness from the same source to pin parity without a GPU; the product library
+// never exports a CPU path).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RSB_HD __host__ __device__ __forceinline__
+#define RSB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RSB_HD inline
+#define RSB_HD_NOINLINE inline
+#endif
+
+#ifndef RSB_INF
+#define RSB_INF ((double)INFINITY)
+#endif
+
+namespace rsb {
+
+struct V3 {
+    double x, y, z;
+};
+
+RSB_HD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RSB_HD double v3_get(const V3& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+// raysect/core/math/vector.pyx:~280 (dot): x*x' + y*y' + z*z', summed left to right
+RSB_HD double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// raysect/core/math/vector.pyx:306-310 (cross)
+RSB_HD V3 cross(const V3& a, const V3& b) {
+    return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+
+// raysect/core/math/_vec3.pyx:152 (get_length)
+RSB_HD double length(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+// raysect/core/math/vector.pyx:313-337, normal.pyx:~205-219 (normalise): t = 1/sqrt(|v|^2), then scale
+RSB_HD V3 normalise(const V3& a) {
+    double t = a.x * a.x + a.y * a.y + a.z * a.z;
+    t = 1.0 / sqrt(t);
+    return v3(a.x * t, a.y * t, a.z * t);
+}
+
+// raysect/core/math/point.pyx:253-281 (Point3D.transform).  m = rows 0..2 of an affine
+// 4x4 (row-major 3x4).  The reference also forms w = m30*x+m31*y+m32*z+m33 and multiplies
+// by 1/w; for an affine matrix w == 1.0 exactly, so the product is the identity.
+RSB_HD V3 xform_point(const double* m, const V3& p) {
+    return v3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3],
+              m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+
+// raysect/core/math/vector.pyx:339-366 (Vector3D.transform)
+RSB_HD V3 xform_vector(const double* m, const V3& v) {
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z,
+              m[4] * v.x + m[5] * v.y + m[6] * v.z,
+              m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+
+// raysect/core/math/normal.pyx:222-248 (Normal3D.transform / transform_with_inverse):
+// multiply by the TRANSPOSE of the inverse matrix.  minv = rows 0..2 of the inverse (3x4).
+RSB_HD V3 xform_normal_with_inverse(const double* minv, const V3& n) {
+    return v3(minv[0] * n.x + minv[4] * n.y + minv[8] * n.z,
+              minv[1] * n.x + minv[5] * n.y + minv[9] * n.z,
+              minv[2] * n.x + minv[6] * n.y + minv[10] * n.z);
+}
+
+// 3x3 transforms used by the surface-space code (row-major 3x3)
+RSB_HD V3 xform_vector33(const double* m, const V3& v) {
+    return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z,
+              m[3] * v.x + m[4] * v.y + m[5] * v.z,
+              m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+
+// raysect/core/math/vector.pyx:442-470, normal.pyx:346-370 (orthogonal)
+RSB_HD V3 orthogonal(const V3& a) {
+    V3 n = normalise(a);
+    V3 v = v3(1, 0, 0);
+    if (fabs(dot(n, v)) > 0.5) v = v3(0, 1, 0);
+    double m = dot(n, v);
+    v = v3(v.x - m * n.x, v.y - m * n.y, v.z - m * n.z);
+    return normalise(v);
+}
+
+// raysect/core/math/cython/utility.pyx:376-420 (solve_quadratic, PBRT-stable form)
+RSB_HD bool solve_quadratic(double a, double b, double c, double* t0, double* t1) {
+    double d = b * b - 4 * a * c;
+    if (d < 0) return false;
+    double q;
+    if (b < 0) q = -0.5 * (b - sqrt(d));
+    else q = -0.5 * (b + sqrt(d));
+    *t0 = q / a;
+    *t1 = c / q;
+    return true;
+}
+
+// raysect/core/boundingbox.pyx:200-245 (_slab)
+RSB_HD void box_slab(double origin, double direction, double lower, double upper, double* front, double* back) {
+    double tmin, tmax;
+    if (direction != 0.0) {
+        double reciprocal = 1.0 / direction;
+        if (direction > 0) {
+            tmin = (lower - origin) * reciprocal;
+            tmax = (upper - origin) * reciprocal;
+        } else {
+            tmin = (upper - origin) * reciprocal;
+            tmax = (lower - origin) * reciprocal;
+        }
+    } else {
+        if (origin < lower) { tmin = -RSB_INF; tmax = -RSB_INF; }
+        else if (origin > upper) { tmin = RSB_INF; tmax = RSB_INF; }
+        else { tmin = -RSB_INF; tmax = RSB_INF; }
+    }
+    if (tmin > *front) *front = tmin;
+    if (tmax < *back) *back = tmax;
+}
+
+// raysect/core/boundingbox.pyx:180-198 (intersect).  box = lower xyz, upper xyz.
+RSB_HD bool box_intersect(const double* box, const V3& o, const V3& d, double* front, double* back) {
+    double f = -RSB_INF, b = RSB_INF;
+    box_slab(o.x, d.x, box[0], box[3], &f, &b);
+    box_slab(o.y, d.y, box[1], box[4], &f, &b);
+    box_slab(o.z, d.z, box[2], box[5], &f, &b);
+    *front = f;
+    *back = b;
+    if (f > b) return false;
+    if ((f < 0.0) && (b < 0.0)) return false;
+    return true;
+}
+
+// raysect/core/boundingbox.pyx:146-158 (hit)
+RSB_HD bool box_hit(const double* box, const V3& o, const V3& d) {
+    double f, b;
+    return box_intersect(box, o, d, &f, &b);
+}
+
+// raysect/core/boundingbox.pyx:247-263 (contains)
+RSB_HD bool box_contains(const double* box, const V3& p) {
+    if ((p.x < box[0]) || (p.x > box[3])) return false;
+    if ((p.y < box[1]) || (p.y > box[4])) return false;
+    if ((p.z < box[2]) || (p.z > box[5])) return false;
+    return true;
+}
+
+// raysect/core/math/cython/utility.pyx:40-94 (find_index): bisection over a monotonic array
+RSB_HD int find_index(const double* x, int n, double v) {
+    if (v < x[0]) return -1;
+    int top = n - 1;
+    if (v >= x[top]) return top;
+    int bottom = 0;
+    int bis = top / 2;
+    while ((top - bottom) != 1) {
+        if (v >= x[bis]) bottom = bis;
+        else top = bis;
+        bis = (top + bottom) / 2;
+    }
+    return bottom;
+}
+
+}  // namespace rsb

@@ -1,0 +1,419 @@
+// rsb_path.h -- the per-ray spectral trace loop as an iterative path.
+//
+// The reference recurses: Ray.trace -> material.evaluate_surface -> daughter.trace -> ... and
+// multiplies the returned Spectrum (float64[bins]) on the way back up.  Every material on this
+// path spawns at most one daughter, so the recursion is a chain: RNG draws and geometry on the
+// way down, per-bin multiplies on the way up.  Here the way down appends the multiplicative
+// factors of each segment to a per-path LOG (16-B entries in HBM); only when a path ends on an
+// emitter is the log replayed backwards over the bins, applying the SAME multiplies in the SAME
+// order as the reference's unwind.  Paths that end in a miss / absorber / roulette contribute an
+// all-zero spectrum and skip the replay.
+#pragma once
+#include "rsb_geom.h"
+#include "rsb_rng.h"
+
+namespace rsb {
+
+#define RSB_PI 3.14159265358979323846
+#define RSB_1_PI 0.31830988618379067154
+
+struct RayConfig {   // optical Ray template fields, raysect/optical/ray.pyx:85-126
+    int32_t bins;
+    int32_t extinction_min_depth;
+    int32_t max_depth;
+    int32_t importance_sampling;
+    double min_wavelength, max_wavelength;
+    double extinction_prob;
+    double important_path_weight;
+    double max_distance;
+};
+
+struct Spectral {    // per spectral slice: what SpectralFunction.sample()/average() cache on the host
+    const Material* mats;
+    const double* tables;   // [n_materials][bins]
+    int32_t bins;
+    int32_t n_materials;
+};
+
+struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207
+    int32_t nx, ny;
+    int32_t pixel_samples;
+    int32_t pad;
+    double image_delta, image_start_x, image_start_y;
+    double sensitivity;
+    double to_root[12];
+};
+
+enum LogOp : int32_t {
+    LOG_MULS = 0,   // s *= v                      Spectrum.mul_scalar / div_scalar (spectrum.pyx:449-468)
+    LOG_MULA = 1,   // s *= table[i]               Spectrum.mul_array (spectrum.pyx:491)
+    LOG_POWA = 2,   // s *= pow(table[i], v)       Dielectric.evaluate_volume (dielectric.pyx:313-330)
+    LOG_EMIT = 3,   // s  = table[i] * v           UniformSurfaceEmitter.evaluate_surface (uniform.pyx:67-81)
+};
+
+struct __attribute__((aligned(16))) LogEntry {
+    int32_t op;
+    int32_t table;
+    double v;
+};
+
+struct PathLog {
+    LogEntry* base;
+    size_t stride;      // entries are interleaved across threads: entry k at base[k*stride]
+    int32_t n;
+    int32_t capacity;
+    int32_t overflow;
+    RSB_HD void push(int op, int table, double v) {
+        if (n < capacity) {
+            LogEntry e; e.op = op; e.table = table; e.v = v;
+            base[(size_t)n * stride] = e;
+            ++n;
+        } else {
+            overflow = 1;
+        }
+    }
+    RSB_HD LogEntry get(int k) const { return base[(size_t)k * stride]; }
+};
+
+// ----- random direction generators (raysect/core/math/random.pyx:375-445, sampler/solidangle.pyx:223-237)
+RSB_HD double max0(double x) { return x > 0 ? x : 0.0; }   // Cython max(0, x)
+
+RSB_HD V3 vector_sphere(Rng& rng) {
+    double z = 1.0 - 2.0 * rng.uniform();
+    double r = sqrt(max0(1.0 - z * z));
+    double phi = 2.0 * RSB_PI * rng.uniform();
+    return v3(r * cos(phi), r * sin(phi), z);
+}
+
+RSB_HD V3 vector_cone_uniform(Rng& rng, double theta) {
+    theta *= 0.017453292519943295;
+    double phi = 2.0 * RSB_PI * rng.uniform();
+    double cos_theta = cos(theta);
+    double z = rng.uniform() * (1 - cos_theta) + cos_theta;
+    double r = sqrt(max0(1.0 - z * z));
+    return v3(r * cos(phi), r * sin(phi), z);
+}
+
+RSB_HD V3 hemisphere_cosine_sample(Rng& rng) {
+    double r = sqrt(rng.uniform());
+    double phi = 2.0 * RSB_PI * rng.uniform();
+    double x = r * cos(phi);
+    double y = r * sin(phi);
+    return v3(x, y, sqrt(max0(1.0 - x * x - y * y)));
+}
+
+RSB_HD double hemisphere_cosine_pdf(const V3& s) {
+    if (s.z >= 0.0) return RSB_1_PI * s.z;
+    return 0.0;
+}
+
+// ----- ImportanceManager (raysect/optical/scenegraph/world.pyx:134-253)
+RSB_HD V3 important_direction_sample(const Scene& sc, Rng& rng, const V3& origin) {
+    int index = find_index(sc.imp_cdf, sc.n_important, rng.uniform()) + 1;
+    if (index >= sc.n_important) index = sc.n_important - 1;
+    const double* s = sc.imp_sphere + 4 * index;
+    V3 direction = v3(s[0] - origin.x, s[1] - origin.y, s[2] - origin.z);
+    double distance = length(direction);
+    double radius = s[3];
+    if (distance == 0 || distance < radius) return vector_sphere(rng);
+    double angular_radius = asin(radius / distance);
+    V3 sample = vector_cone_uniform(rng, angular_radius * 180 / RSB_PI);
+    direction = normalise(direction);
+    // rotate_basis(direction, direction.orthogonal()), raysect/core/math/transform.pyx:234-286
+    V3 up = orthogonal(direction);
+    V3 z = normalise(direction);
+    V3 y = normalise(up);
+    double yz = dot(y, z);
+    y = v3(y.x - yz * z.x, y.y - yz * z.y, y.z - yz * z.z);
+    y = normalise(y);
+    V3 x = cross(y, z);
+    return v3(x.x * sample.x + y.x * sample.y + z.x * sample.z,
+              x.y * sample.x + y.y * sample.y + z.y * sample.z,
+              x.z * sample.x + y.z * sample.y + z.z * sample.z);
+}
+
+RSB_HD double important_direction_pdf(const Scene& sc, const V3& origin, const V3& direction) {
+    double pdf_all = 0;
+    for (int i = 0; i < sc.n_important; ++i) {
+        const double* s = sc.imp_sphere + 4 * i;
+        V3 cone_axis = v3(s[0] - origin.x, s[1] - origin.y, s[2] - origin.z);
+        double distance = length(cone_axis);
+        double radius = s[3];
+        double solid_angle;
+        if (distance == 0 || distance < radius) {
+            solid_angle = 4 * RSB_PI;
+        } else {
+            double t = radius / distance;
+            double angular_radius_cos = sqrt(1 - t * t);
+            cone_axis = normalise(cone_axis);
+            if (dot(direction, cone_axis) < angular_radius_cos) continue;
+            solid_angle = 2 * RSB_PI * (1 - angular_radius_cos);
+        }
+        double pdf_sphere = 1 / solid_angle;
+        double selection_weight = sc.imp_weight[i] / sc.imp_total;
+        pdf_all += selection_weight * pdf_sphere;
+    }
+    return pdf_all;
+}
+
+// ----- volumes: Ray._sample_volumes (raysect/optical/ray.pyx:422-455) ---------------------------
+// world.contains(ray.origin) -> the one world leaf holding the origin, items in leaf order; each
+// containing primitive's material.evaluate_volume(start = world hit point, end = ray origin).
+// Entries are pushed in REVERSE so that the backward replay applies them in forward order.
+template <class Stats>
+RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, const V3& w_hit,
+                        KdStackEntry* stack, PathLog& log, Stats& stats) {
+    int offset, count;
+    if (!kd_locate(sc.world, origin, &offset, &count)) return;
+    for (int i = count - 1; i >= 0; --i) {
+        int id = sc.world.items[offset + i];
+        const Material& m = sp.mats[sc.prims[id].material];
+        if (m.type != MAT_DIELECTRIC) continue;   // Lambert/emitter/absorber: evaluate_volume is the identity
+        if (!prim_contains(sc, id, origin, stack, stats)) continue;
+        // length = start_point.vector_to(end_point).get_length()
+        V3 v = v3(origin.x - w_hit.x, origin.y - w_hit.y, origin.z - w_hit.z);
+        log.push(LOG_POWA, m.table, length(v));
+    }
+}
+
+enum PathEnd : int32_t { PATH_ZERO = 0, PATH_EMITTED = 1, PATH_CONTINUE = 2 };
+
+struct PathState {
+    V3 o, d;            // world-space ray of the current segment
+    int32_t depth;
+    uint32_t rays;      // the reference's ray counter for this primary ray (1 + daughters spawned)
+};
+
+RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
+    ps.o = o;
+    ps.d = d;
+    ps.depth = 0;
+    ps.rays = 1;
+    log.n = 0;
+}
+
+// One segment of the Ray.trace recursion (raysect/optical/ray.pyx:338-401): roulette, World.hit,
+// material.evaluate_surface up to the point where it would call daughter.trace(), volumes.
+// PATH_CONTINUE: ps holds the daughter ray.  PATH_EMITTED: the log now ends with a LOG_EMIT entry.
+// PATH_ZERO: the path's spectrum is identically zero.
+template <class Stats>
+RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, Rng& rng,
+                     KdStackEntry* stack, PathLog& log, Stats& stats) {
+    const V3 o = ps.o, d = ps.d;
+    const int depth = ps.depth;
+    {
+        // -- Russian roulette (ray.pyx:380-388)
+        double normalisation;
+        if (depth < cfg.extinction_min_depth) {
+            normalisation = 1.0;
+        } else {
+            if (depth >= cfg.max_depth || rng.probability(cfg.extinction_prob)) return PATH_ZERO;
+            normalisation = 1 / (1 - cfg.extinction_prob);
+        }
+        // -- closest hit (ray.pyx:391-393)
+        HitRec rec;
+        if (!world_hit(sc, o, d, cfg.max_distance, stack, &rec, stats)) return PATH_ZERO;
+        Isect is;
+        world_hit_geometry(sc, o, d, rec, &is);
+        const Prim& prim = sc.prims[rec.prim];
+        const Material& mat = sp.mats[prim.material];
+        const double* w2p = prim.to_local;
+        const double* p2w = prim.to_root;
+
+        // entries of this segment, pushed in reverse application order: normalisation, volumes, surface
+        if (normalisation != 1.0) log.push(LOG_MULS, 0, normalisation);
+        V3 w_hit = xform_point(p2w, is.hit);
+        log_volumes(sc, sp, o, w_hit, stack, log, stats);
+
+        if (mat.type == MAT_EMITTER) {
+            log.push(LOG_EMIT, mat.table, mat.scale);
+            return PATH_EMITTED;
+        }
+        if (mat.type == MAT_ABSORBER) return PATH_ZERO;
+
+        V3 next_o, next_d;
+        if (mat.type == MAT_LAMBERT) {
+            // ContinuousBSDF.evaluate_surface (material.pyx:291-361) + Lambert (lambert.pyx:71-105)
+            V3 normal = is.normal;
+            V3 w_reflection_origin;
+            if (is.exiting) {
+                w_reflection_origin = xform_point(p2w, is.inside);
+                normal = v3(-normal.x, -normal.y, -normal.z);
+            } else {
+                w_reflection_origin = xform_point(p2w, is.outside);
+            }
+            // _generate_surface_transforms (material.pyx:393-422)
+            V3 tangent = orthogonal(normal);
+            V3 bitangent = cross(normal, tangent);
+            double p2s[9] = {tangent.x, tangent.y, tangent.z, bitangent.x, bitangent.y, bitangent.z, normal.x, normal.y, normal.z};
+            double s2p[9] = {tangent.x, bitangent.x, normal.x, tangent.y, bitangent.y, normal.y, tangent.z, bitangent.z, normal.z};
+            // AffineMatrix3D.mul (affinematrix.pyx:254-273), 3x3 block; the 4th product of each sum is 0*0
+            double w2s[9], s2w[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    w2s[3 * r + c] = p2s[3 * r + 0] * w2p[0 + c] + p2s[3 * r + 1] * w2p[4 + c] + p2s[3 * r + 2] * w2p[8 + c] + 0.0 * 0.0;
+                    s2w[3 * r + c] = p2w[4 * r + 0] * s2p[0 + c] + p2w[4 * r + 1] * s2p[3 + c] + p2w[4 * r + 2] * s2p[6 + c] + p2w[4 * r + 3] * 0.0;
+                }
+            V3 s_outgoing, w_outgoing;
+            double pdf;
+            bool mis = cfg.importance_sampling && sc.imp_total > 0;
+            if (mis) {
+                if (rng.probability(cfg.important_path_weight)) {
+                    w_outgoing = important_direction_sample(sc, rng, w_hit);
+                    s_outgoing = xform_vector33(w2s, w_outgoing);
+                } else {
+                    s_outgoing = hemisphere_cosine_sample(rng);
+                    w_outgoing = xform_vector33(s2w, s_outgoing);
+                }
+                double pdf_important = important_direction_pdf(sc, w_hit, w_outgoing);
+                double pdf_bsdf = hemisphere_cosine_pdf(s_outgoing);
+                pdf = cfg.important_path_weight * pdf_important + (1 - cfg.important_path_weight) * pdf_bsdf;
+            } else {
+                s_outgoing = hemisphere_cosine_sample(rng);
+                pdf = hemisphere_cosine_pdf(s_outgoing);
+            }
+            // Lambert.evaluate_shading (lambert.pyx:77-105)
+            double pdf_cos = hemisphere_cosine_pdf(s_outgoing);
+            if (pdf_cos == 0.0) return PATH_ZERO;
+            next_o = w_reflection_origin;
+            next_d = xform_vector33(s2w, s_outgoing);
+            // unwind order: mul_array(reflectivity), mul_scalar(pdf_cos), div_scalar(pdf) => pushed reversed
+            log.push(LOG_MULS, 0, 1.0 / pdf);
+            log.push(LOG_MULS, 0, pdf_cos);
+            log.push(LOG_MULA, mat.table, 0.0);
+        } else {
+            // Dielectric.evaluate_surface (dielectric.pyx:153-303)
+            V3 incident = normalise(xform_vector(w2p, d));
+            V3 normal = normalise(is.normal);
+            double c1 = -dot(normal, incident);
+            double n1, n2;
+            if (c1 < 0.0) { n1 = mat.index_in; n2 = mat.index_out; }
+            else { n1 = mat.index_out; n2 = mat.index_in; }
+            double gamma = n1 / n2;
+            double c2s = 1 - (gamma * gamma) * (1 - c1 * c1);
+            bool reflect;
+            V3 transmitted = v3(0, 0, 0);
+            if (c2s <= 0) {
+                if (mat.transmission_only) return PATH_ZERO;
+                reflect = true;   // total internal reflection
+            } else {
+                double temp;
+                if (c1 < 0.0) temp = gamma * c1 + sqrt(c2s);
+                else temp = gamma * c1 - sqrt(c2s);
+                transmitted = v3(gamma * incident.x + temp * normal.x,
+                                 gamma * incident.y + temp * normal.y,
+                                 gamma * incident.z + temp * normal.z);
+                // _fresnel (dielectric.pyx:305-308)
+                double ci = c1, ct = -dot(normal, transmitted);
+                double ra = (n1 * ci - n2 * ct) / (n1 * ci + n2 * ct);
+                double rb = (n1 * ct - n2 * ci) / (n1 * ct + n2 * ci);
+                double reflectivity = 0.5 * (ra * ra + rb * rb);
+                double transmission = 1 - reflectivity;
+                reflect = !(mat.transmission_only || rng.probability(transmission));
+            }
+            if (reflect) {
+                double temp = 2 * c1;
+                V3 reflected = v3(incident.x + temp * normal.x, incident.y + temp * normal.y, incident.z + temp * normal.z);
+                next_d = xform_vector(p2w, reflected);
+                next_o = (c1 < 0.0) ? xform_point(p2w, is.inside) : xform_point(p2w, is.outside);
+            } else {
+                next_d = xform_vector(p2w, transmitted);
+                next_o = (c1 < 0.0) ? xform_point(p2w, is.outside) : xform_point(p2w, is.inside);
+            }
+        }
+        // spawn_daughter (ray.pyx:506-549)
+        ps.o = next_o;
+        ps.d = next_d;
+        ps.depth = depth + 1;
+        ps.rays += 1;
+        return PATH_CONTINUE;
+    }
+}
+
+// A whole path (used by the serial harness; the render kernel steps segment by segment so that
+// a warp never waits for its longest path).
+template <class Stats>
+RSB_HD int trace_path(const Scene& sc, const Spectral& sp, const RayConfig& cfg, const V3& o, const V3& d, Rng& rng,
+                      KdStackEntry* stack, PathLog& log, uint32_t* ray_count, Stats& stats) {
+    PathState ps;
+    path_begin(ps, log, o, d);
+    int r;
+    do { r = path_step(sc, sp, cfg, ps, rng, stack, log, stats); } while (r == PATH_CONTINUE);
+    *ray_count = ps.rays;
+    return r;
+}
+
+// Backward replay of a path log for one bin (the reference's unwind for samples_mv[bin]).
+RSB_HD double replay_bin(const PathLog& log, const Spectral& sp, int bin) {
+    double s = 0.0;
+    for (int k = log.n - 1; k >= 0; --k) {
+        LogEntry e = log.get(k);
+        if (e.op == LOG_MULS) s *= e.v;
+        else if (e.op == LOG_MULA) s *= sp.tables[(size_t)e.table * sp.bins + bin];
+        else if (e.op == LOG_POWA) s *= pow(sp.tables[(size_t)e.table * sp.bins + bin], e.v);
+        else s = sp.tables[(size_t)e.table * sp.bins + bin] * e.v;
+    }
+    return s;
+}
+
+// raysect/core/math/statsarray.pyx:743-777 (_add_sample), n is the count BEFORE this sample
+RSB_HD void welford_add(double sample, double* m, double* v, int n) {
+    if (n == 0) {
+        *m = sample;
+        *v = 0;
+    } else {
+        double prev_m = *m, prev_v = *v;
+        int prev_n = n > 1 ? n : 2;
+        int nn = n + 1;
+        *m = prev_m + (sample - prev_m) / nn;
+        *v = (prev_v * (prev_n - 1) + (sample - prev_m) * (sample - *m)) / (nn - 1);
+    }
+}
+
+// raysect/core/math/statsarray.pyx:780-857 (_combine_samples)
+RSB_HD void stats_combine(double mx, double vx, int nx, double my, double vy, int ny, double* mt, double* vt, int* nt) {
+    if (nx < ny) {
+        int ti = nx; nx = ny; ny = ti;
+        double td = mx; mx = my; my = td;
+        td = vx; vx = vy; vy = td;
+    }
+    if (nx > 1 && ny > 1) {
+        *nt = nx + ny;
+        *mt = (nx * mx + ny * my) / (double)*nt;
+        vx = (nx - 1) * vx / (double)nx;
+        vy = (ny - 1) * vy / (double)ny;
+        *vt = (nx * (mx * mx + vx) + ny * (my * my + vy)) / (double)*nt - *mt * *mt;
+        *vt = *nt * *vt / (double)(*nt - 1);
+        return;
+    }
+    if (nx == 0 && ny == 0) { *nt = 0; *mt = 0; *vt = 0; }
+    else if (nx == 1) {
+        if (ny == 0) { *nt = 1; *mt = mx; *vt = 0; }
+        else {
+            *nt = 2;
+            *mt = 0.5 * (mx + my);
+            double temp = mx - *mt;
+            *vt = 2 * temp * temp;
+        }
+    } else if (nx > 1) {
+        *nt = nx; *mt = mx; *vt = vx;
+        if (ny == 1) { welford_add(my, mt, vt, *nt); *nt += 1; }
+    }
+}
+
+// PinholeCamera._generate_rays for one sample (pinhole.pyx:169-204): jitter (u1, u2) -> local
+// direction + projection weight, then _render_pixel's camera->world transform (observer.pyx:400-403).
+RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2, V3* o, V3* d, double* weight) {
+    double pixel_x = cam.image_start_x - cam.image_delta * (px + 0.5);
+    double pixel_y = cam.image_start_y - cam.image_delta * (py + 0.5);
+    // RectangleSampler3D.sample (surface3d.pyx:197-198): width = height = image_delta, offsets 0.5*width
+    double half = 0.5 * cam.image_delta;
+    double jx = u1 * cam.image_delta - half;
+    double jy = u2 * cam.image_delta - half;
+    V3 dir = normalise(v3(jx + pixel_x, jy + pixel_y, 0.0 + 1.0));
+    *weight = dir.z;
+    *o = xform_point(cam.to_root, v3(0, 0, 0));
+    *d = xform_vector(cam.to_root, dir);
+}
+
+}  // namespace rsb

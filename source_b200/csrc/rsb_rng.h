@@ -1,0 +1,153 @@
+// rsb_rng.h -- random streams for the trace loop.
+//
+//  * Mt19937_64: bit-exact restatement of the reference's global generator
+//    (raysect/core/math/random.pyx:99-265: init_genrand64, init_by_array64, _rand_uint64, seed,
+//    uniform).  The reference has ONE process-global stream; here every pixel owns a stream
+//    seeded exactly as `seed(seed_base + pixel_index)` would, so a frame is independent of the
+//    pixel -> thread -> GPU mapping and can be reproduced on the reference with a RenderEngine that
+//    re-seeds before each pixel task.  State (312 x u64) lives in HBM, word-interleaved across
+//    threads (word i of stream s at state[i*stride + s]) so that a warp's accesses coalesce.
+//  * Philox4x32-10: counter-based generator keyed on (seed, pixel, sample) for throughput runs;
+//    no state in memory.  Same uniform() mapping: 53 random bits * 2^-53.
+#pragma once
+#include "rsb_math.h"
+
+namespace rsb {
+
+#define RSB_MT_NN 312
+#define RSB_MT_MM 156
+
+struct Mt19937_64 {
+    uint64_t* mt;       // base of this stream's words
+    size_t stride;      // distance (in words) between consecutive words of the stream
+    int mti;
+
+    RSB_HD uint64_t& w(int i) { return mt[(size_t)i * stride]; }
+
+    // random.pyx:110-122
+    RSB_HD void init_genrand64(uint64_t seed) {
+        w(0) = seed;
+        uint64_t prev = seed;
+        for (int i = 1; i < RSB_MT_NN; ++i) {
+            prev = 6364136223846793005ULL * (prev ^ (prev >> 62)) + (uint64_t)i;
+            w(i) = prev;
+        }
+        mti = RSB_MT_NN;
+    }
+
+    // random.pyx:125-164 specialised to the key seed(d) builds for 0 < d < 2^64 (random.pyx:215-243):
+    // d.to_bytes(8*312, 'big') => key[0..310] = 0, key[311] = d.
+    RSB_HD void seed(uint64_t d) {
+        init_genrand64(19650218ULL);
+        unsigned int i = 1, j = 0;
+        for (int k = 0; k < RSB_MT_NN; ++k) {
+            uint64_t key = (j == RSB_MT_NN - 1) ? d : 0ULL;
+            uint64_t prev = w(i - 1);
+            w(i) = (w(i) ^ ((prev ^ (prev >> 62)) * 3935559000370003845ULL)) + key + (uint64_t)j;
+            ++i;
+            if (i >= RSB_MT_NN) { w(0) = w(RSB_MT_NN - 1); i = 1; }
+            ++j;
+            if (j >= RSB_MT_NN) j = 0;
+        }
+        for (int k = 0; k < RSB_MT_NN - 1; ++k) {
+            uint64_t prev = w(i - 1);
+            w(i) = (w(i) ^ ((prev ^ (prev >> 62)) * 2862933555777941757ULL)) - (uint64_t)i;
+            ++i;
+            if (i >= RSB_MT_NN) { w(0) = w(RSB_MT_NN - 1); i = 1; }
+        }
+        w(0) = 9223372036854775808ULL;
+        mti = RSB_MT_NN;
+    }
+
+    // random.pyx:167-212
+    RSB_HD uint64_t next_u64() {
+        if (mti >= RSB_MT_NN) {
+            const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL, MAG = 0xB5026F5AA96619E9ULL;
+            int i;
+            for (i = 0; i < RSB_MT_NN - RSB_MT_MM; ++i) {
+                uint64_t x = (w(i) & UM) | (w(i + 1) & LM);
+                w(i) = w(i + RSB_MT_MM) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
+            }
+            for (; i < RSB_MT_NN - 1; ++i) {
+                uint64_t x = (w(i) & UM) | (w(i + 1) & LM);
+                w(i) = w(i + (RSB_MT_MM - RSB_MT_NN)) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
+            }
+            uint64_t x = (w(RSB_MT_NN - 1) & UM) | (w(0) & LM);
+            w(RSB_MT_NN - 1) = w(RSB_MT_MM - 1) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
+            mti = 0;
+        }
+        uint64_t x = w(mti++);
+        x ^= (x >> 29) & 0x5555555555555555ULL;
+        x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+        x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+        x ^= (x >> 43);
+        return x;
+    }
+};
+
+struct Philox4x32 {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t out[4];
+    int have;   // buffered 64-bit words available (0..2)
+
+    RSB_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
+        uint64_t p = (uint64_t)a * (uint64_t)b;
+        *hi = (uint32_t)(p >> 32);
+        *lo = (uint32_t)p;
+    }
+
+    RSB_HD void init(uint64_t seed, uint64_t stream, uint32_t sub) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0;
+        ctr[1] = sub;
+        ctr[2] = (uint32_t)stream;
+        ctr[3] = (uint32_t)(stream >> 32);
+        have = 0;
+    }
+
+    RSB_HD void block() {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+        uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, c0, &hi0, &lo0);
+            mulhilo(0xCD9E8D57u, c2, &hi1, &lo1);
+            uint32_t n0 = hi1 ^ c1 ^ k0;
+            uint32_t n2 = hi0 ^ c3 ^ k1;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+        ctr[0] += 1;
+        have = 2;
+    }
+
+    RSB_HD uint64_t next_u64() {
+        if (have == 0) block();
+        --have;
+        return ((uint64_t)out[2 * have + 1] << 32) | (uint64_t)out[2 * have];
+    }
+};
+
+enum RngMode : int32_t { RNG_MT19937_64 = 0, RNG_PHILOX = 1 };
+
+// One stream handle used by the trace loop.
+struct Rng {
+    int32_t mode;
+    Mt19937_64 mt;
+    Philox4x32 px;
+
+    RSB_HD uint64_t next_u64() { return mode == RNG_MT19937_64 ? mt.next_u64() : px.next_u64(); }
+
+    // random.pyx:247-265 (uniform): (x >> 11) * 2^-53
+    RSB_HD double uniform() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+
+    // random.pyx:308-332 (probability)
+    RSB_HD bool probability(double prob) { return uniform() < prob; }
+};
+
+}  // namespace rsb

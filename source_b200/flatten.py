@@ -1,0 +1,286 @@
+"""Scenegraph -> flat arrays (``RsbSceneDesc``), the host half of ``Accelerator.build``.
+
+Works on any object model that quacks like Raysect's (the real ``raysect`` classes when the plugin is
+installed into a Raysect program, or this package's own mirror in ``source_b200.scenegraph``):
+
+* ``world.primitives``  list order = primitive id (raysect/core/acceleration/kdtree.pyx:52-55)
+* ``primitive.to_local()/to_root()`` indexable ``m[i, j]``, with ``.inverse()``
+* ``primitive.bounding_box()`` -> ``.lower/.upper`` with ``.x .y .z``; ``bounding_sphere()`` -> ``.centre, .radius``
+* shape attributes ``radius``, ``height``, ``lower``, ``upper``, ``primitive_a/primitive_b``, ``data`` (mesh)
+* ``primitive.material`` with ``importance`` and the spectral functions of the four supported materials
+
+Everything numeric that feeds parity (AABBs, bounding spheres, matrices) is taken from the object
+model's own methods, so when driven by real Raysect objects the device sees bit-identical inputs.
+"""
+import ctypes as C
+import io
+import struct
+
+import numpy as np
+
+from . import _cabi as cabi
+
+_SHAPES = {
+    "Sphere": cabi.PRIM_SPHERE, "Box": cabi.PRIM_BOX, "Cylinder": cabi.PRIM_CYLINDER, "Cone": cabi.PRIM_CONE,
+    "Mesh": cabi.PRIM_MESH, "Union": cabi.PRIM_UNION, "Intersect": cabi.PRIM_INTERSECT, "Subtract": cabi.PRIM_SUBTRACT,
+}
+_MATERIALS = {
+    "AbsorbingSurface": cabi.MAT_ABSORBER, "UniformSurfaceEmitter": cabi.MAT_EMITTER,
+    "Lambert": cabi.MAT_LAMBERT, "Dielectric": cabi.MAT_DIELECTRIC,
+}
+
+# world tree parameters of _PrimitiveKDTree (raysect/core/acceleration/kdtree.pyx:43)
+WORLD_KD = dict(max_depth=0, min_items=1, hit_cost=80.0, empty_bonus=0.2)
+
+
+def _classify(obj, table, what):
+    for cls in type(obj).__mro__:
+        if cls.__name__ in table:
+            return table[cls.__name__]
+    raise NotImplementedError(
+        "%s %r is not supported by the B200 path (supported: %s); there is no CPU fallback"
+        % (what, type(obj).__name__, ", ".join(sorted(table))))
+
+
+def mat34(m):
+    return [float(m[i, j]) for i in range(3) for j in range(4)]
+
+
+def _box6(b):
+    return [b.lower.x, b.lower.y, b.lower.z, b.upper.x, b.upper.y, b.upper.z]
+
+
+def lambert_reflectivity(material):
+    """``Lambert.reflectivity`` is a private cdef field in Raysect; its pickle state exposes it."""
+    if hasattr(material, "reflectivity"):
+        return material.reflectivity
+    return material.__reduce__()[2][-1]
+
+
+def kdtree_build(boxes, max_depth=0, min_items=1, hit_cost=20.0, empty_bonus=0.2):
+    """SAH kd-tree over item AABBs -> the reference's serialised stream (bytes).  Host-only C++."""
+    lib = cabi.load()
+    boxes = cabi.as_f64(boxes).reshape(-1, 6)
+    out = C.c_void_p()
+    nbytes = C.c_int64()
+    cabi.check(lib.rsb_kdtree_build(cabi.ptr(boxes, C.c_double), boxes.shape[0], max_depth, min_items, hit_cost,
+                                    empty_bonus, C.byref(out), C.byref(nbytes)))
+    try:
+        return C.string_at(out, nbytes.value)
+    finally:
+        lib.rsb_free(out)
+
+
+def rsm_kdtree_stream(blob):
+    """Offset of the KDTree3DCore stream inside an .rsm blob (raysect/primitive/mesh/mesh.pyx:864-931)."""
+    if blob[:3] != b"RSM":
+        raise ValueError("Specified file is not a Raysect mesh file.")
+    major, minor = struct.unpack_from("<BB", blob, 3)
+    if (major, minor) != (1, 0):
+        raise ValueError("Unsupported Raysect mesh version.")
+    nv, nn, nt = struct.unpack_from("<iii", blob, 8)
+    width = 6 if nn > 0 else 3
+    return 20 + 12 * nv + 12 * nn + 4 * width * nt
+
+
+class FlatScene:
+    """Flat arrays + the ctypes descriptor that points into them (keeps everything alive)."""
+
+    def __init__(self):
+        self.primitives = []        # world-level primitive objects, id order
+        self.materials = []         # material objects, row order
+        self.rows = []
+        self.meshes = []
+        self.desc = None
+
+    # ---- per-slice spectral tables ------------------------------------------------------------------
+    def spectral(self, min_wavelength, max_wavelength, bins):
+        """What SpectralFunction.sample()/average() return for every material on this slice
+        (raysect/optical/spectralfunction.pyx:140-216); evaluated by the object model itself."""
+        n = len(self.materials)
+        tables = np.zeros((n, bins), dtype=np.float64)
+        scale = np.ones(n, dtype=np.float64)
+        index_in = np.ones(n, dtype=np.float64)
+        index_out = np.ones(n, dtype=np.float64)
+        for i, (m, t) in enumerate(zip(self.materials, self.mat_type)):
+            if t == cabi.MAT_LAMBERT:
+                tables[i] = np.asarray(lambert_reflectivity(m).sample(min_wavelength, max_wavelength, bins))
+            elif t == cabi.MAT_EMITTER:
+                tables[i] = np.asarray(m.emission_spectrum.sample(min_wavelength, max_wavelength, bins))
+                scale[i] = m.scale
+            elif t == cabi.MAT_DIELECTRIC:
+                tables[i] = np.asarray(m.transmission.sample(min_wavelength, max_wavelength, bins))
+                index_in[i] = m.index.average(min_wavelength, max_wavelength)
+                index_out[i] = m.external_index.average(min_wavelength, max_wavelength)
+        s = cabi.RsbSpectral()
+        s.bins = bins
+        s.n_materials = n
+        s.tables = cabi.ptr(tables, C.c_double)
+        s.scale = cabi.ptr(scale, C.c_double)
+        s.index_in = cabi.ptr(index_in, C.c_double)
+        s.index_out = cabi.ptr(index_out, C.c_double)
+        s._keep = (tables, scale, index_in, index_out)
+        return s
+
+
+def _mesh_desc(data, keep):
+    vertices = np.ascontiguousarray(data.vertices, dtype=np.float32)
+    triangles = np.ascontiguousarray(data.triangles, dtype=np.int32)
+    vnormals = getattr(data, "vertex_normals", None)
+    if vnormals is not None:
+        vnormals = np.ascontiguousarray(vnormals, dtype=np.float32)
+    fnormals = getattr(data, "face_normals", None)
+    if fnormals is not None:
+        fnormals = np.ascontiguousarray(fnormals, dtype=np.float32)
+    stream = getattr(data, "kdtree_stream", None)
+    if stream is None:
+        buf = io.BytesIO()
+        data.save(buf)                      # MeshData.save -> .rsm blob (arrays + the mesh's own kd-tree)
+        blob = buf.getvalue()
+        stream = blob[rsm_kdtree_stream(blob):]
+    stream = np.frombuffer(stream, dtype=np.uint8)
+    d = cabi.RsbMeshDesc()
+    d.vertices = cabi.ptr(vertices, C.c_float)
+    d.triangles = cabi.ptr(triangles, C.c_int32)
+    d.vertex_normals = cabi.ptr(vnormals, C.c_float)
+    d.face_normals = cabi.ptr(fnormals, C.c_float)
+    d.kdtree = cabi.ptr(stream, C.c_uint8)
+    d.kdtree_bytes = stream.size
+    d.n_vertices = vertices.shape[0]
+    d.n_triangles = triangles.shape[0]
+    d.tri_stride = triangles.shape[1]
+    d.n_vertex_normals = 0 if vnormals is None else vnormals.shape[0]
+    d.smoothing = int(bool(data.smoothing))
+    d.closed = int(bool(data.closed))
+    keep.extend([vertices, triangles, vnormals, fnormals, stream])
+    return d
+
+
+def flatten_world(world, world_kdtree=None):
+    """Flattens ``world`` (Raysect ``World`` or this package's mirror) into a ``FlatScene``.
+
+    ``world_kdtree``: optional pre-serialised world tree (bytes); by default the tree is built by this
+    package's own bit-exact SAH builder with the reference's parameters.
+    """
+    flat = FlatScene()
+    prims = list(world.primitives)
+    if not prims:
+        raise ValueError("The world contains no primitives.")
+    flat.primitives = prims
+    rows = []          # dict rows
+    mesh_descs, mesh_index, keep = [], {}, []
+    material_index = {}
+
+    def material_row(material):
+        key = id(material)
+        if key not in material_index:
+            _classify(material, _MATERIALS, "material")
+            material_index[key] = len(flat.materials)
+            flat.materials.append(material)
+        return material_index[key]
+
+    def add(p, parent_row, top_level):
+        t = _classify(p, _SHAPES, "primitive")
+        row = dict(type=t, material=-1, a=-1, b=-1, mesh=-1, parent=parent_row, params=[0.0] * 6,
+                   to_local=mat34(p.to_local()), to_root=mat34(p.to_root()), root_inv=mat34(p.to_local()),
+                   bbox=_box6(p.bounding_box()))
+        idx = len(rows) if not top_level else None
+        if not top_level:
+            # Normal3D.transform(primitive_to_world) re-inverts the matrix (normal.pyx:241)
+            row["root_inv"] = mat34(p.to_root().inverse())
+            rows.append(row)
+        if t == cabi.PRIM_SPHERE:
+            row["params"][0] = p.radius
+        elif t == cabi.PRIM_BOX:
+            row["params"] = [p.lower.x, p.lower.y, p.lower.z, p.upper.x, p.upper.y, p.upper.z]
+        elif t in (cabi.PRIM_CYLINDER, cabi.PRIM_CONE):
+            row["params"][0] = p.radius
+            row["params"][1] = p.height
+        elif t == cabi.PRIM_MESH:
+            key = id(p.data)
+            if key not in mesh_index:
+                mesh_index[key] = len(mesh_descs)
+                mesh_descs.append(_mesh_desc(p.data, keep))
+            row["mesh"] = mesh_index[key]
+        return row, idx
+
+    # world-level rows first, in World.primitives order
+    for p in prims:
+        row, _ = add(p, -1, True)
+        row["material"] = material_row(p.material)
+        rows.append(row)
+    # then CSG operands, depth first
+    def expand(p, my_row):
+        t = rows[my_row]["type"]
+        if t < cabi.PRIM_UNION:
+            return
+        for key, child in (("a", p.primitive_a), ("b", p.primitive_b)):
+            _, idx = add(child, my_row, False)
+            rows[my_row][key] = idx
+            expand(child, idx)
+
+    for i, p in enumerate(prims):
+        expand(p, i)
+
+    n = len(rows)
+    flat.rows = rows
+    flat.prim_type = cabi.as_i32([r["type"] for r in rows])
+    flat.prim_material = cabi.as_i32([r["material"] for r in rows])
+    flat.prim_child_a = cabi.as_i32([r["a"] for r in rows])
+    flat.prim_child_b = cabi.as_i32([r["b"] for r in rows])
+    flat.prim_mesh = cabi.as_i32([r["mesh"] for r in rows])
+    flat.prim_parent = cabi.as_i32([r["parent"] for r in rows])
+    flat.prim_params = cabi.as_f64([r["params"] for r in rows], (n, 6))
+    flat.prim_to_local = cabi.as_f64([r["to_local"] for r in rows], (n, 12))
+    flat.prim_to_root = cabi.as_f64([r["to_root"] for r in rows], (n, 12))
+    flat.prim_root_inv = cabi.as_f64([r["root_inv"] for r in rows], (n, 12))
+    flat.prim_bbox = cabi.as_f64([r["bbox"] for r in rows], (n, 6))
+
+    if world_kdtree is None:
+        world_kdtree = kdtree_build(flat.prim_bbox[:len(prims)], **WORLD_KD)
+    flat.world_kdtree = np.frombuffer(world_kdtree, dtype=np.uint8)
+
+    flat.mat_type = cabi.as_i32([_classify(m, _MATERIALS, "material") for m in flat.materials])
+    flat.mat_transmission_only = cabi.as_i32(
+        [int(bool(getattr(m, "transmission_only", False))) for m in flat.materials])
+
+    # ImportanceManager._process_primitives (raysect/optical/scenegraph/world.pyx:88-108)
+    spheres, weights = [], []
+    for p in prims:
+        importance = getattr(p.material, "importance", 0.0)
+        if importance > 0:
+            s = p.bounding_sphere()
+            spheres.append([s.centre.x, s.centre.y, s.centre.z, s.radius])
+            weights.append(importance)
+    flat.imp_sphere = cabi.as_f64(spheres if spheres else np.zeros((0, 4)), (-1, 4))
+    flat.imp_weight = cabi.as_f64(weights)
+
+    flat.meshes = (cabi.RsbMeshDesc * max(1, len(mesh_descs)))(*mesh_descs)
+    flat._keep = keep
+
+    d = cabi.RsbSceneDesc()
+    d.n_primitives = n
+    d.n_world = len(prims)
+    d.prim_type = cabi.ptr(flat.prim_type, C.c_int32)
+    d.prim_material = cabi.ptr(flat.prim_material, C.c_int32)
+    d.prim_child_a = cabi.ptr(flat.prim_child_a, C.c_int32)
+    d.prim_child_b = cabi.ptr(flat.prim_child_b, C.c_int32)
+    d.prim_mesh = cabi.ptr(flat.prim_mesh, C.c_int32)
+    d.prim_parent = cabi.ptr(flat.prim_parent, C.c_int32)
+    d.prim_params = cabi.ptr(flat.prim_params, C.c_double)
+    d.prim_to_local = cabi.ptr(flat.prim_to_local, C.c_double)
+    d.prim_to_root = cabi.ptr(flat.prim_to_root, C.c_double)
+    d.prim_root_inv = cabi.ptr(flat.prim_root_inv, C.c_double)
+    d.prim_bbox = cabi.ptr(flat.prim_bbox, C.c_double)
+    d.world_kdtree = cabi.ptr(flat.world_kdtree, C.c_uint8)
+    d.world_kdtree_bytes = flat.world_kdtree.size
+    d.n_meshes = len(mesh_descs)
+    d.n_materials = len(flat.materials)
+    d.meshes = C.cast(flat.meshes, C.POINTER(cabi.RsbMeshDesc))
+    d.mat_type = cabi.ptr(flat.mat_type, C.c_int32)
+    d.mat_transmission_only = cabi.ptr(flat.mat_transmission_only, C.c_int32)
+    d.n_important = len(weights)
+    d.imp_sphere = cabi.ptr(flat.imp_sphere, C.c_double)
+    d.imp_weight = cabi.ptr(flat.imp_weight, C.c_double)
+    flat.desc = d
+    return flat
