@@ -119,17 +119,14 @@ RSB_HD V3 important_direction_sample(const Scene& sc, Rng& rng, const V3& origin
     double angular_radius = asin(radius / distance);
     V3 sample = vector_cone_uniform(rng, angular_radius * 180 / RSB_PI);
     direction = normalise(direction);
-    // rotate_basis(direction, direction.orthogonal()), raysect/core/math/transform.pyx:234-286
+    // rotate_basis(direction, direction.orthogonal()) -- the cdef version in
+    // raysect/core/math/cython/transform.pyx:45-70 (no re-normalisation: right = up x forward,
+    // columns right | up | forward), NOT the public raysect.core.math.transform.rotate_basis
     V3 up = orthogonal(direction);
-    V3 z = normalise(direction);
-    V3 y = normalise(up);
-    double yz = dot(y, z);
-    y = v3(y.x - yz * z.x, y.y - yz * z.y, y.z - yz * z.z);
-    y = normalise(y);
-    V3 x = cross(y, z);
-    return v3(x.x * sample.x + y.x * sample.y + z.x * sample.z,
-              x.y * sample.x + y.y * sample.y + z.y * sample.z,
-              x.z * sample.x + y.z * sample.y + z.z * sample.z);
+    V3 right = cross(up, direction);
+    return v3(right.x * sample.x + up.x * sample.y + direction.x * sample.z,
+              right.y * sample.x + up.y * sample.y + direction.y * sample.z,
+              right.z * sample.x + up.z * sample.y + direction.z * sample.z);
 }
 
 RSB_HD double important_direction_pdf(const Scene& sc, const V3& origin, const V3& direction) {
@@ -268,6 +265,9 @@ RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, 
                 double pdf_important = important_direction_pdf(sc, w_hit, w_outgoing);
                 double pdf_bsdf = hemisphere_cosine_pdf(s_outgoing);
                 pdf = cfg.important_path_weight * pdf_important + (1 - cfg.important_path_weight) * pdf_bsdf;
+#ifdef RSB_DEBUG_MIS
+                fprintf(stderr, "MIS w_hit=(%.17g, %.17g, %.17g) w_out=(%.17g, %.17g, %.17g) pdf_imp=%.17g pdf_bsdf=%.17g pdf=%.17g\n", w_hit.x, w_hit.y, w_hit.z, w_outgoing.x, w_outgoing.y, w_outgoing.z, pdf_important, pdf_bsdf, pdf);
+#endif
             } else {
                 s_outgoing = hemisphere_cosine_sample(rng);
                 pdf = hemisphere_cosine_pdf(s_outgoing);
@@ -407,9 +407,12 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
     double pixel_x = cam.image_start_x - cam.image_delta * (px + 0.5);
     double pixel_y = cam.image_start_y - cam.image_delta * (py + 0.5);
     // RectangleSampler3D.sample (surface3d.pyx:197-198): width = height = image_delta, offsets 0.5*width
+    // The two uniform() calls are arguments of one C call in the Cython output,
+    // new_point3d(uniform()*w - ow, uniform()*h - oh, 0), and gcc evaluates call arguments right to left:
+    // the FIRST draw of a sample lands in y, the SECOND in x (verified against the compiled reference).
     double half = 0.5 * cam.image_delta;
-    double jx = u1 * cam.image_delta - half;
-    double jy = u2 * cam.image_delta - half;
+    double jy = u1 * cam.image_delta - half;
+    double jx = u2 * cam.image_delta - half;
     V3 dir = normalise(v3(jx + pixel_x, jy + pixel_y, 0.0 + 1.0));
     *weight = dir.z;
     *o = xform_point(cam.to_root, v3(0, 0, 0));

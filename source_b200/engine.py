@@ -1,0 +1,204 @@
+"""Device context + scene accelerator: the Python face of the C ABI.
+
+``Device``       one ``rsb_context`` (one per GPU / process).
+``Accelerator``  one uploaded scene; mirrors ``raysect.core.acceleration.Accelerator``
+                 (build / hit / contains, accelerator.pxd:37-41) and adds the batched forms the GPU wants.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _cabi as cabi
+from .flatten import flatten_world
+
+_default = None
+
+
+def default_device():
+    global _default
+    if _default is None:
+        _default = Device(0)
+    return _default
+
+
+class Device:
+    def __init__(self, index=0):
+        self.lib = cabi.load()
+        h = C.c_uint64()
+        cabi.check(self.lib.rsb_context_create(int(index), C.byref(h)))
+        self.ctx = h.value
+        self.index = int(index)
+        sm, major, minor, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+        cabi.check(self.lib.rsb_device_info(self.ctx, C.byref(sm), C.byref(major), C.byref(minor), C.byref(mem)))
+        self.sm_count, self.cc, self.total_mem = sm.value, (major.value, minor.value), mem.value
+
+    def close(self):
+        if self.ctx:
+            self.lib.rsb_context_destroy(self.ctx)
+            self.ctx = 0
+
+    def build(self, world, world_kdtree=None):
+        """Accelerator.build(world.primitives)"""
+        return Accelerator(self, flatten_world(world, world_kdtree))
+
+    def rng_uniform(self, seed, n):
+        """raysect.core.math.random: seed(seed); [uniform() for _ in range(n)] -- on the device"""
+        out = np.zeros(int(n), dtype=np.float64)
+        cabi.check(self.lib.rsb_rng_uniform(self.ctx, int(seed), int(n), cabi.ptr(out, C.c_double)))
+        return out
+
+    def counters(self):
+        c = cabi.RsbCounters()
+        cabi.check(self.lib.rsb_counters(self.ctx, C.byref(c)))
+        return c.as_dict()
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        cabi.check(self.lib.rsb_last_kernel_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+
+class HitBatch:
+    """Arrays returned by ``hit_batch`` (one row per ray)."""
+    __slots__ = ("primitive", "distance", "sub", "exiting", "node", "geometry", "uvw")
+
+    def __init__(self, n, geometry):
+        self.primitive = np.zeros(n, dtype=np.int32)
+        self.distance = np.zeros(n, dtype=np.float64)
+        self.sub = np.zeros(n, dtype=np.int32)
+        self.exiting = np.zeros(n, dtype=np.uint8)
+        self.node = np.zeros((n, 2), dtype=np.int32)
+        self.geometry = np.zeros((n, 12), dtype=np.float64) if geometry else None
+        self.uvw = np.zeros((n, 3), dtype=np.float32) if geometry else None
+
+
+class Accelerator:
+    def __init__(self, device, flat):
+        self.device = device
+        self.lib = device.lib
+        self.flat = flat
+        h = C.c_uint64()
+        cabi.check(self.lib.rsb_scene_create(device.ctx, C.byref(flat.desc), C.byref(h)))
+        self.scene = h.value
+
+    def close(self):
+        if self.scene and self.device.ctx:
+            self.lib.rsb_scene_destroy(self.device.ctx, self.scene)
+        self.scene = 0
+
+    # ---- World.hit ------------------------------------------------------------------------------------
+    def hit_batch(self, origins, directions, max_distance=None, geometry=False):
+        o = cabi.as_f64(origins).reshape(-1, 3)
+        d = cabi.as_f64(directions).reshape(-1, 3)
+        if o.shape != d.shape:
+            raise ValueError("origins and directions must have the same shape")
+        n = o.shape[0]
+        md = None if max_distance is None else cabi.as_f64(np.broadcast_to(max_distance, (n,)))
+        out = HitBatch(n, geometry)
+        cabi.check(self.lib.rsb_hit_batch(
+            self.device.ctx, self.scene, n, cabi.ptr(o, C.c_double), cabi.ptr(d, C.c_double), cabi.ptr(md, C.c_double),
+            cabi.ptr(out.primitive, C.c_int32), cabi.ptr(out.distance, C.c_double), cabi.ptr(out.sub, C.c_int32),
+            cabi.ptr(out.exiting, C.c_uint8), cabi.ptr(out.node, C.c_int32), cabi.ptr(out.geometry, C.c_double),
+            cabi.ptr(out.uvw, C.c_float)))
+        return out
+
+    def hit(self, ray, point_cls=None, vector_cls=None, intersection_cls=None):
+        """Accelerator.hit(ray) -> Intersection or None (1-element batch; API parity, not the fast path)"""
+        from .math3d import Point3D, Vector3D
+        from .scenegraph import Intersection
+        P = point_cls or Point3D
+        V = vector_cls or Vector3D
+        o, d = ray.origin, ray.direction
+        r = self.hit_batch([[o.x, o.y, o.z]], [[d.x, d.y, d.z]], [ray.max_distance], geometry=True)
+        if r.primitive[0] < 0:
+            return None
+        prim = self.flat.primitives[int(r.primitive[0])]
+        g = r.geometry[0]
+        make = intersection_cls or Intersection
+        it = make(ray, float(r.distance[0]), prim, P(g[0], g[1], g[2]), P(g[3], g[4], g[5]), P(g[6], g[7], g[8]),
+                  V(g[9], g[10], g[11]), bool(r.exiting[0]), prim.to_local(), prim.to_root())
+        if self.flat.prim_type[int(r.primitive[0])] == cabi.PRIM_MESH:
+            it.triangle = int(r.sub[0])
+            it.u, it.v, it.w = (float(x) for x in r.uvw[0])
+        return it
+
+    # ---- World.contains -------------------------------------------------------------------------------
+    def contains_batch(self, points, cap=8):
+        p = cabi.as_f64(points).reshape(-1, 3)
+        n = p.shape[0]
+        count = np.zeros(n, dtype=np.int32)
+        prims = np.full((n, cap), -1, dtype=np.int32)
+        cabi.check(self.lib.rsb_contains_batch(self.device.ctx, self.scene, n, cabi.ptr(p, C.c_double), int(cap),
+                                               cabi.ptr(count, C.c_int32), cabi.ptr(prims, C.c_int32)))
+        return count, prims
+
+    def contains(self, point):
+        cap = 8
+        while True:
+            count, prims = self.contains_batch([[point.x, point.y, point.z]], cap)
+            if count[0] <= cap:
+                return [self.flat.primitives[int(i)] for i in prims[0, :count[0]]]
+            cap = int(count[0])
+
+    # ---- Observer._render_pixel over a pixel list ---------------------------------------------------------
+    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
+        """camera: RsbCamera, config: RsbRayConfig, spectral: RsbSpectral (from FlatScene.spectral()).
+        Returns (mean, variance, ray_count); mean/variance are (nx, ny, bins) float64."""
+        nx, ny, bins = camera.nx, camera.ny, config.bins
+        if mean is None:
+            mean = np.zeros((nx, ny, bins), dtype=np.float64)
+        if variance is None:
+            variance = np.zeros((nx, ny, bins), dtype=np.float64)
+        rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
+        rays = C.c_uint64(0)
+        pix = None
+        n = nx * ny
+        if pixels is not None:
+            pix = cabi.as_i32(pixels).reshape(-1, 2)
+            n = pix.shape[0]
+        cabi.check(self.lib.rsb_render(self.device.ctx, self.scene, C.byref(camera), C.byref(config), C.byref(spectral),
+                                       C.byref(rng), n, cabi.ptr(pix, C.c_int32), cabi.ptr(mean, C.c_double),
+                                       cabi.ptr(variance, C.c_double), C.byref(rays)))
+        return mean, variance, rays.value
+
+
+def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root):
+    """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160)"""
+    max_pixels = max(nx, ny)
+    if max_pixels <= 1:
+        raise RuntimeError("Number of Pinhole camera Pixels must be > 1.")
+    image_max_width = 2 * math.tan(math.pi / 180 * 0.5 * fov)
+    image_delta = image_max_width / max_pixels
+    cam = cabi.RsbCamera()
+    cam.nx, cam.ny, cam.pixel_samples = int(nx), int(ny), int(pixel_samples)
+    cam.image_delta = image_delta
+    cam.image_start_x = 0.5 * nx * image_delta
+    cam.image_start_y = 0.5 * ny * image_delta
+    cam.sensitivity = float(sensitivity)
+    for k, v in enumerate(float(to_root[i, j]) for i in range(3) for j in range(4)):
+        cam.to_root[k] = v
+    return cam
+
+
+def ray_config(bins, min_wavelength, max_wavelength, extinction_prob=0.1, extinction_min_depth=3, max_depth=100,
+               importance_sampling=True, important_path_weight=0.25, max_distance=math.inf):
+    """optical Ray defaults, raysect/optical/ray.pyx:85-96"""
+    if bins < 1:
+        raise ValueError("Number of bins cannot be less than 1.")
+    if min_wavelength <= 0.0 or max_wavelength <= 0.0:
+        raise ValueError("Wavelength must be greater than to zero.")
+    if min_wavelength >= max_wavelength:
+        raise ValueError("Minimum wavelength must be less than the maximum wavelength.")
+    if important_path_weight < 0 or important_path_weight > 1.0:
+        raise ValueError("Important path weight must be in the range [0, 1].")
+    c = cabi.RsbRayConfig()
+    c.bins = int(bins)
+    c.extinction_min_depth = int(extinction_min_depth)
+    c.max_depth = int(max_depth)
+    c.importance_sampling = int(bool(importance_sampling))
+    c.min_wavelength, c.max_wavelength = float(min_wavelength), float(max_wavelength)
+    c.extinction_prob = float(extinction_prob)
+    c.important_path_weight = float(important_path_weight)
+    c.max_distance = float(max_distance)
+    return c

@@ -3,6 +3,7 @@
 // the CUDA kernels execute can be pinned against the reference in a container without a GPU.
 // It is built by tests/conftest.py into tests/_build/, is never imported by source_b200, and is
 // not a fallback: the product library fails loudly when no sm_100 device is present.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -230,7 +231,20 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
             PathLog log;
             log.base = logbuf.data(); log.stride = 1; log.capacity = cap; log.n = 0; log.overflow = 0;
             uint32_t rays = 0;
-            int res = trace_path(h->sc, sp, cfg, o, d, rng, stack, log, &rays, stats);
+            int res;
+            if (getenv("HS_DEBUG")) {
+                PathState ps;
+                path_begin(ps, log, o, d);
+                do {
+                    fprintf(stderr, "seg depth=%d o=(%.17g %.17g %.17g) d=(%.17g %.17g %.17g)\n", ps.depth, ps.o.x, ps.o.y, ps.o.z, ps.d.x, ps.d.y, ps.d.z);
+                    res = path_step(h->sc, sp, cfg, ps, rng, stack, log, stats);
+                } while (res == PATH_CONTINUE);
+                rays = ps.rays;
+                fprintf(stderr, "end res=%d rays=%u logn=%d\n", res, rays, log.n);
+                for (int k = log.n - 1; k >= 0; --k) { LogEntry e = log.get(k); fprintf(stderr, "  log op=%d table=%d v=%.17g\n", e.op, e.table, e.v); }
+            } else {
+                res = trace_path(h->sc, sp, cfg, o, d, rng, stack, log, &rays, stats);
+            }
             if (log.overflow) { g_err = "path log overflow"; return RSB_ERR_OVERFLOW; }
             *ray_count += rays;
             paths += 1;

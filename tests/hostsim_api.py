@@ -1,0 +1,118 @@
+"""Loader for tests/_build/libhostsim.so: the product's device headers compiled as host C++ and driven
+serially (tests/hostsim/hostsim.cpp).  TEST INFRASTRUCTURE ONLY -- lets the CPU test-suite pin the
+arithmetic the CUDA kernels execute against the reference; never imported by source_b200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from source_b200 import _cabi as cabi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "_build", "libhostsim.so")
+SOURCES = [os.path.join(HERE, "hostsim", "hostsim.cpp"),
+           os.path.join(ROOT, "source_b200", "csrc", "scene_pack.cpp"),
+           os.path.join(ROOT, "source_b200", "csrc", "kdtree_host.cpp")]
+HEADERS = [os.path.join(ROOT, "source_b200", "csrc", h) for h in
+           ("rsb_math.h", "rsb_scene.h", "rsb_geom.h", "rsb_rng.h", "rsb_path.h", "scene_pack.h", "kdtree_host.h")]
+
+
+def build(force=False):
+    newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO] + SOURCES)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.hs_last_error.restype = C.c_char_p
+        _lib.hs_scene_create.argtypes = [C.POINTER(cabi.RsbSceneDesc), C.POINTER(C.c_uint64)]
+        _lib.hs_scene_destroy.argtypes = [C.c_uint64]
+        _lib.hs_hit_batch.argtypes = [C.c_uint64, C.c_int64] + [C.c_void_p] * 11
+        _lib.hs_contains_batch.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        _lib.hs_rng_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
+        _lib.hs_render.argtypes = [C.c_uint64, C.POINTER(cabi.RsbCamera), C.POINTER(cabi.RsbRayConfig),
+                                   C.POINTER(cabi.RsbSpectral), C.POINTER(cabi.RsbRngDesc), C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+        _lib.hs_frame_combine.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class HostScene:
+    """Same surface as source_b200.engine.Accelerator, evaluated by the host build of the device code."""
+
+    def __init__(self, flat):
+        self.flat = flat
+        h = C.c_uint64()
+        rc = lib().hs_scene_create(C.byref(flat.desc), C.byref(h))
+        if rc:
+            raise cabi.RsbError(rc, lib().hs_last_error().decode())
+        self.scene = h.value
+        self.counters = None
+
+    def close(self):
+        if self.scene:
+            lib().hs_scene_destroy(self.scene)
+            self.scene = 0
+
+    def hit_batch(self, origins, directions, max_distance=None, geometry=True):
+        from source_b200.engine import HitBatch
+        o = cabi.as_f64(origins).reshape(-1, 3)
+        d = cabi.as_f64(directions).reshape(-1, 3)
+        n = o.shape[0]
+        md = None if max_distance is None else cabi.as_f64(np.broadcast_to(max_distance, (n,)))
+        out = HitBatch(n, True)
+        counters = np.zeros(5, dtype=np.uint64)
+        lib().hs_hit_batch(self.scene, n, _p(o), _p(d), _p(md), _p(out.primitive), _p(out.distance), _p(out.sub),
+                           _p(out.exiting), _p(out.node), _p(out.geometry), _p(out.uvw), _p(counters))
+        self.counters = dict(zip(("branches", "leaves", "items", "prim_tests", "tri_tests"), (int(c) for c in counters)))
+        return out
+
+    def contains_batch(self, points, cap=8):
+        p = cabi.as_f64(points).reshape(-1, 3)
+        n = p.shape[0]
+        count = np.zeros(n, dtype=np.int32)
+        prims = np.full((n, cap), -1, dtype=np.int32)
+        lib().hs_contains_batch(self.scene, n, _p(p), cap, _p(count), _p(prims))
+        return count, prims
+
+    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
+        nx, ny, bins = camera.nx, camera.ny, config.bins
+        if mean is None:
+            mean = np.zeros((nx, ny, bins))
+        if variance is None:
+            variance = np.zeros((nx, ny, bins))
+        rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
+        rays = C.c_uint64(0)
+        pix, n = None, nx * ny
+        if pixels is not None:
+            pix = cabi.as_i32(pixels).reshape(-1, 2)
+            n = pix.shape[0]
+        counters = np.zeros(7, dtype=np.uint64)
+        rc = lib().hs_render(self.scene, C.byref(camera), C.byref(config), C.byref(spectral), C.byref(rng), n, _p(pix),
+                             _p(mean), _p(variance), C.byref(rays), _p(counters))
+        if rc:
+            raise cabi.RsbError(rc, lib().hs_last_error().decode())
+        self.counters = dict(zip(("branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "segments"),
+                                 (int(c) for c in counters)))
+        return mean, variance, rays.value
+
+
+def rng_uniform(seed, n):
+    out = np.zeros(n)
+    lib().hs_rng_uniform(int(seed), n, _p(out))
+    return out

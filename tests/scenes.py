@@ -1,0 +1,149 @@
+"""Scene definitions shared by the golden-vector generator (run against the real reference) and the
+parity tests (run against source_b200's mirror object model).  Each builder takes an ``api`` namespace
+exposing Raysect's names (World, Node, Sphere, Box, ..., translate, rotate, Point3D, materials), so the
+SAME construction code produces the reference scene and the device scene.
+"""
+import numpy as np
+
+# ---- spectra of the physical Cornell box, as tabulated in the reference's demos/cornell_box.py:28-57 ----
+CB_WAVELENGTHS = list(range(400, 704, 4))
+CB_WHITE = [0.343, 0.445, 0.551, 0.624, 0.665, 0.687, 0.708, 0.723, 0.715, 0.71, 0.745, 0.758, 0.739, 0.767, 0.777, 0.765,
+            0.751, 0.745, 0.748, 0.729, 0.745, 0.757, 0.753, 0.75, 0.746, 0.747, 0.735, 0.732, 0.739, 0.734, 0.725, 0.721,
+            0.733, 0.725, 0.732, 0.743, 0.744, 0.748, 0.728, 0.716, 0.733, 0.726, 0.713, 0.74, 0.754, 0.764, 0.752, 0.736,
+            0.734, 0.741, 0.74, 0.732, 0.745, 0.755, 0.751, 0.744, 0.731, 0.733, 0.744, 0.731, 0.712, 0.708, 0.729, 0.73,
+            0.727, 0.707, 0.703, 0.729, 0.75, 0.76, 0.751, 0.739, 0.724, 0.73, 0.74, 0.737]
+CB_GREEN = [0.092, 0.096, 0.098, 0.097, 0.098, 0.095, 0.095, 0.097, 0.095, 0.094, 0.097, 0.098, 0.096, 0.101, 0.103, 0.104,
+            0.107, 0.109, 0.112, 0.115, 0.125, 0.14, 0.16, 0.187, 0.229, 0.285, 0.343, 0.39, 0.435, 0.464, 0.472, 0.476, 0.481,
+            0.462, 0.447, 0.441, 0.426, 0.406, 0.373, 0.347, 0.337, 0.314, 0.285, 0.277, 0.266, 0.25, 0.23, 0.207, 0.186,
+            0.171, 0.16, 0.148, 0.141, 0.136, 0.13, 0.126, 0.123, 0.121, 0.122, 0.119, 0.114, 0.115, 0.117, 0.117, 0.118, 0.12,
+            0.122, 0.128, 0.132, 0.139, 0.144, 0.146, 0.15, 0.152, 0.157, 0.159]
+CB_RED = [0.04, 0.046, 0.048, 0.053, 0.049, 0.05, 0.053, 0.055, 0.057, 0.056, 0.059, 0.057, 0.061, 0.061, 0.06, 0.062, 0.062,
+          0.062, 0.061, 0.062, 0.06, 0.059, 0.057, 0.058, 0.058, 0.058, 0.056, 0.055, 0.056, 0.059, 0.057, 0.055, 0.059,
+          0.059, 0.058, 0.059, 0.061, 0.061, 0.063, 0.063, 0.067, 0.068, 0.072, 0.08, 0.09, 0.099, 0.124, 0.154, 0.192,
+          0.255, 0.287, 0.349, 0.402, 0.443, 0.487, 0.513, 0.558, 0.584, 0.62, 0.606, 0.609, 0.651, 0.612, 0.61, 0.65, 0.638,
+          0.627, 0.62, 0.63, 0.628, 0.642, 0.639, 0.657, 0.639, 0.635, 0.642]
+CB_LIGHT = ([400, 500, 600, 700], [0.0, 8.0, 15.6, 18.4])
+
+
+def cornell_box(api, glass=True, extra=None):
+    """World of demos/cornell_box.py:63-121: 5 zero-thickness Lambert walls, 1 emitter box, a glass box
+    and a glass sphere (N-BK7).  ``extra(api, world)`` may add more primitives (e.g. the bunny)."""
+    a = api
+    white = a.InterpolatedSF(CB_WAVELENGTHS, CB_WHITE)
+    red = a.InterpolatedSF(CB_WAVELENGTHS, CB_RED)
+    green = a.InterpolatedSF(CB_WAVELENGTHS, CB_GREEN)
+    light_spectrum = a.InterpolatedSF(*CB_LIGHT)
+    world = a.World()
+    enclosure = a.Node(world)
+    lo, hi = a.Point3D(-1, -1, 0), a.Point3D(1, 1, 0)
+    a.Box(lo, hi, parent=enclosure, transform=a.translate(0, 0, 1) * a.rotate(0, 0, 0), material=a.Lambert(white))
+    a.Box(lo, hi, parent=enclosure, transform=a.translate(0, -1, 0) * a.rotate(0, -90, 0), material=a.Lambert(white))
+    a.Box(lo, hi, parent=enclosure, transform=a.translate(0, 1, 0) * a.rotate(0, 90, 0), material=a.Lambert(white))
+    a.Box(lo, hi, parent=enclosure, transform=a.translate(1, 0, 0) * a.rotate(-90, 0, 0), material=a.Lambert(red))
+    a.Box(lo, hi, parent=enclosure, transform=a.translate(-1, 0, 0) * a.rotate(90, 0, 0), material=a.Lambert(green))
+    a.Box(a.Point3D(-0.4, -0.4, -0.01), a.Point3D(0.4, 0.4, 0.0), parent=enclosure,
+          transform=a.translate(0, 1, 0) * a.rotate(0, 90, 0), material=a.UniformSurfaceEmitter(light_spectrum, 2))
+    if glass:
+        a.Box(a.Point3D(-0.4, 0, -0.4), a.Point3D(0.3, 1.4, 0.3), parent=world,
+              transform=a.translate(0.4, -1 + 1e-6, 0.4) * a.rotate(30, 0, 0), material=a.schott("N-BK7"))
+        a.Sphere(0.4, parent=world, transform=a.translate(-0.4, -0.6 + 1e-6, -0.4) * a.rotate(0, 0, 0),
+                 material=a.schott("N-BK7"))
+    if extra is not None:
+        extra(a, world)
+    return world
+
+
+def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_rays=1, min_depth=3, max_depth=500,
+                   extinction=0.01, path_weight=0.25, importance=True):
+    """Camera of demos/cornell_box.py:147-156 with a SpectralPowerPipeline2D and a full-frame sampler."""
+    a = api
+    pipeline = a.SpectralPowerPipeline2D()
+    camera = a.PinholeCamera(pixels, parent=world, transform=a.translate(0, 0, -3.3) * a.rotate(0, 0, 0),
+                             pipelines=[pipeline], frame_sampler=a.FullFrameSampler2D())
+    camera.spectral_rays = spectral_rays
+    camera.spectral_bins = bins
+    camera.pixel_samples = samples
+    camera.ray_importance_sampling = importance
+    camera.ray_important_path_weight = path_weight
+    camera.ray_max_depth = max_depth
+    camera.ray_extinction_min_depth = min_depth
+    camera.ray_extinction_prob = extinction
+    camera.quiet = True
+    return camera, pipeline
+
+
+def random_spheres(api, n, seed=7, uniform=None):
+    """BASELINE config 5: n spheres, centres uniform in [-1,1]^3, radii uniform in [0.01,0.03]; the draws
+    come from ``uniform`` (the reference RNG after seed(7) when generating goldens) or numpy."""
+    a = api
+    if uniform is None:
+        rng = np.random.default_rng(seed)
+        uniform = lambda: float(rng.random())
+    world = a.World()
+    mat = a.AbsorbingSurface()
+    for _ in range(n):
+        c = [2 * uniform() - 1 for _ in range(3)]
+        r = 0.01 + 0.02 * uniform()
+        a.Sphere(r, world, a.translate(*c), mat)
+    return world
+
+
+def primitive_zoo(api):
+    """One of every analytic primitive, rotated/translated, plus CSG combinations of every operator
+    including the nested prism/screen shapes of demos/prism.py:21-41,77-98."""
+    a = api
+    world = a.World()
+    m = a.AbsorbingSurface()
+    a.Sphere(0.5, world, a.translate(-2.0, 0.3, 0.2) * a.rotate(10, 20, 30), m)
+    a.Box(a.Point3D(-0.4, -0.3, -0.2), a.Point3D(0.5, 0.6, 0.7), world, a.translate(-0.7, -0.2, 0.1) * a.rotate(25, -15, 40), m)
+    a.Cylinder(0.35, 1.1, world, a.translate(0.6, -0.5, 0.0) * a.rotate(-35, 60, 5), m)
+    a.Cone(0.45, 0.9, world, a.translate(1.8, -0.4, 0.3) * a.rotate(15, -70, 0), m)
+    # every CSG operator on a sphere/box pair
+    a.Union(a.Sphere(0.4, transform=a.translate(0.2, 0, 0)), a.Box(a.Point3D(-0.3, -0.3, -0.3), a.Point3D(0.3, 0.3, 0.3)),
+            world, a.translate(-2.0, 1.5, 0.0) * a.rotate(20, 10, 0), m)
+    a.Intersect(a.Sphere(0.45), a.Box(a.Point3D(-0.35, -0.35, -0.35), a.Point3D(0.35, 0.35, 0.35)),
+                world, a.translate(-0.7, 1.5, 0.0) * a.rotate(-20, 30, 10), m)
+    a.Subtract(a.Box(a.Point3D(-0.4, -0.4, -0.4), a.Point3D(0.4, 0.4, 0.4)), a.Sphere(0.5),
+               world, a.translate(0.6, 1.5, 0.0) * a.rotate(40, 20, -10), m)
+    # cylinder/cone operands
+    a.Intersect(a.Cylinder(0.3, 1.0, transform=a.rotate(0, 90, 0) * a.translate(0, 0, -0.5)),
+                a.Cone(0.5, 0.8, transform=a.translate(0, 0, -0.3)), world, a.translate(1.9, 1.5, 0.0) * a.rotate(10, 10, 10), m)
+    # nested: prism of demos/prism.py (Subtract(Subtract(Box, Box), Box))
+    prism = a.Subtract(
+        a.Subtract(a.Box(a.Point3D(-0.5, 0, -0.5), a.Point3D(0.5, 0.8, 0.5)),
+                   a.Box(a.Point3D(-0.5, -0.1, -0.1), a.Point3D(1.5, 1.0, 0.9), transform=a.translate(0.5, 0, 0) * a.rotate(30, 0, 0))),
+        a.Box(a.Point3D(-1.5, -0.1, -0.1), a.Point3D(0.5, 1.0, 0.9), transform=a.translate(-0.5, 0, 0) * a.rotate(-30, 0, 0)),
+        world, a.translate(-1.2, -1.9, 0.2) * a.rotate(5, 0, 0), m)
+    # nested: slotted screen (Intersect(Box, Subtract(Cylinder, Cylinder)))
+    a.Intersect(a.Box(a.Point3D(-0.5, -0.4, -1), a.Point3D(0.5, 0.4, 1)),
+                a.Subtract(a.Cylinder(0.6, 0.5, transform=a.rotate(0, 90, 0) * a.translate(0, 0, -0.25)),
+                           a.Cylinder(0.45, 0.7, transform=a.rotate(0, 90, 0) * a.translate(0, 0, -0.35))),
+                world, a.translate(0.9, -1.8, 0.0) * a.rotate(-15, 25, 0), m)
+    # Union of unions (depth 2, 4 leaves)
+    a.Union(a.Union(a.Sphere(0.25, transform=a.translate(-0.3, 0, 0)), a.Sphere(0.25, transform=a.translate(0.3, 0, 0))),
+            a.Union(a.Cylinder(0.1, 1.2, transform=a.translate(0, 0, -0.6)), a.Cone(0.3, 0.5, transform=a.translate(0, 0.2, 0))),
+            world, a.translate(2.4, -1.8, 0.4) * a.rotate(30, 30, 30), m)
+    return world
+
+
+def zoo_rays(n, seed=3):
+    """Rays aimed from a shell of random origins at random points inside the zoo's extent, plus rays
+    started INSIDE primitives (so exiting hits and t0 < 0 branches are exercised)."""
+    rng = np.random.default_rng(seed)
+    n_out = (2 * n) // 3
+    theta = rng.uniform(0, 2 * np.pi, n_out)
+    z = rng.uniform(-1, 1, n_out)
+    r = np.sqrt(1 - z * z)
+    o_out = 6.0 * np.c_[r * np.cos(theta), r * np.sin(theta), z]
+    tgt = np.c_[rng.uniform(-2.8, 2.8, n_out), rng.uniform(-2.6, 2.2, n_out), rng.uniform(-0.6, 0.8, n_out)]
+    d_out = tgt - o_out
+    d_out /= np.linalg.norm(d_out, axis=1)[:, None]
+    n_in = n - n_out
+    o_in = np.c_[rng.uniform(-2.6, 2.6, n_in), rng.uniform(-2.4, 2.0, n_in), rng.uniform(-0.4, 0.6, n_in)]
+    d_in = rng.normal(size=(n_in, 3))
+    d_in /= np.linalg.norm(d_in, axis=1)[:, None]
+    # some axis-aligned directions (zero components exercise the parallel-ray branches)
+    k = min(60, n_in)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=float)
+    d_in[:k] = axes[np.arange(k) % 6]
+    return np.ascontiguousarray(np.r_[o_out, o_in]), np.ascontiguousarray(np.r_[d_out, d_in])
