@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Generates the committed golden vectors in tests/golden/ from the UNMODIFIED compiled reference
+(oracle/_ref, built by oracle/build_ref.py from /root/reference).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated deterministically by tests/scenes.py on both sides, so the fixtures hold only the
+reference's OUTPUTS (plus digests of the reference-built kd-trees)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from oracle import harness  # noqa: E402
+import scenes  # noqa: E402
+
+api = harness.ref_api()
+
+
+def digest(b):
+    return np.frombuffer(hashlib.sha256(b).digest(), dtype=np.uint8)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("%-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def hits(world, o, d, md=None):
+    r = harness.oracle_hit(world, o, d, md)
+    stream = harness.world_kdtree_stream(world)
+    return dict(primitive=r["primitive"], distance=r["distance"], exiting=r["exiting"], geometry=r["geometry"],
+                triangle=r["triangle"], uvw=r["uvw"], tree_sha256=digest(stream), tree_bytes=np.int64(len(stream)))
+
+
+def render(world, camera_kwargs, seed):
+    cam, pipe = scenes.cornell_camera(api, world, **camera_kwargs)
+    mean, var, n = harness.oracle_render(cam, pipe, seed)
+    return cam, dict(mean=mean, variance=var, samples=n)
+
+
+def main():
+    # 1. RNG known answers: the reference's own test vector (raysect/core/math/tests/test_random.py:37-253)
+    from raysect.core.math.tests.test_random import _random_reference
+    kat = np.array(_random_reference)
+    assert np.array_equal(harness.oracle_uniform(1234567890, len(kat)), kat)
+    save("rng_kat", seed=np.uint64(1234567890), uniform=kat, seed77=harness.oracle_uniform(77, 700))
+
+    # 2. analytic primitives + CSG
+    world = scenes.primitive_zoo(api)
+    o, d = scenes.zoo_rays(6000)
+    g = hits(world, o, d)
+    md = np.random.default_rng(4).uniform(0.5, 7.0, len(o))
+    g2 = harness.oracle_hit(world, o, d, md)
+    pts = np.random.default_rng(5).uniform([-2.8, -2.6, -0.6], [2.8, 2.2, 0.8], (4000, 3))
+    cc, cp = harness.oracle_contains(world, pts)
+    save("zoo_hits", **g, md_primitive=g2["primitive"], md_distance=g2["distance"], contains_count=cc, contains_prims=cp)
+
+    # 3. config-5 style sphere field (2,000 spheres for the fixture; the bench uses 10,000)
+    world = scenes.random_spheres(api, 2000, seed=7)
+    rng = np.random.default_rng(1)
+    o = np.tile(np.array([0, 0, -4.0]), (5000, 1))
+    tgt = np.c_[rng.uniform(-1, 1, 5000), rng.uniform(-1, 1, 5000), np.zeros(5000)]
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    save("spheres_hits", **hits(world, np.ascontiguousarray(o), np.ascontiguousarray(d)))
+
+    # 4. triangle mesh (float32 watertight test, smoothing normals, instancing, contains)
+    for smoothing in (True, False):
+        world = scenes.mesh_scene(api, smoothing)
+        o, d = scenes.mesh_rays(5000)
+        g = hits(world, o, d)
+        pts = np.random.default_rng(6).uniform([-1.0, -0.8, -0.5], [1.1, 0.6, 0.8], (3000, 3))
+        cc, cp = harness.oracle_contains(world, pts)
+        import io
+        buf = io.BytesIO()
+        world.primitives[0].data.save(buf)
+        from source_b200.flatten import rsm_kdtree_stream
+        blob = buf.getvalue()
+        stream = blob[rsm_kdtree_stream(blob):]
+        save("mesh_hits_smooth" if smoothing else "mesh_hits_flat", **g, contains_count=cc, contains_prims=cp,
+             mesh_tree_sha256=digest(stream), mesh_tree_bytes=np.int64(len(stream)),
+             face_normals=np.array(world.primitives[0].data.face_normals))
+
+    # 5. Cornell box renders (SerialEngine semantics, per-pixel re-seeding; seed base 1000)
+    world = scenes.cornell_box(api)
+    cam, r = render(world, dict(pixels=(32, 32), samples=4, bins=15), 1000)
+    save("cornell_32x32_s4_b15", **r)
+    cam, r = render(world, dict(pixels=(16, 12), samples=3, bins=16, spectral_rays=4, path_weight=0.5), 4242)
+    save("cornell_16x12_s3_b16_r4", **r)
+    world = scenes.cornell_box(api, glass=False)
+    cam, r = render(world, dict(pixels=(24, 24), samples=2, bins=8, importance=False, min_depth=2, max_depth=6, extinction=0.2), 77)
+    save("cornell_noglass_noimp_24", **r)
+
+    # 6. dispersive CSG prism: one spectral ray per bin
+    world = scenes.prism_scene(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(24, 24), samples=6, bins=6, spectral_rays=6, path_weight=0.75)
+    cam.transform = api.translate(0.3, 0.2, -2.2) * api.rotate(5, -3, 0)
+    mean, var, n = harness.oracle_render(cam, pipe, 31337)
+    save("prism_24x24_s6_b6_r6", mean=mean, variance=var, samples=n)
+
+    # 7. host object model: transforms, bounding volumes, spectral resampling
+    world = scenes.primitive_zoo(api)
+    rows = []
+    for p in world.primitives:
+        b, s = p.bounding_box(), p.bounding_sphere()
+        rows.append([p.to_local()[i, j] for i in range(3) for j in range(4)] + [p.to_root()[i, j] for i in range(3) for j in range(4)]
+                    + [b.lower.x, b.lower.y, b.lower.z, b.upper.x, b.upper.y, b.upper.z, s.centre.x, s.centre.y, s.centre.z, s.radius])
+    glass = api.schott("N-BK7")
+    sf11 = api.schott("SF11")
+    white = api.InterpolatedSF(scenes.CB_WAVELENGTHS, scenes.CB_WHITE)
+    light = api.InterpolatedSF(*scenes.CB_LIGHT)
+    spec = {}
+    for tag, (lo, hi, bins) in dict(a=(375.0, 740.0, 15), b=(400.0, 700.0, 64), c=(520.5, 530.25, 3), d=(300.0, 420.0, 7)).items():
+        spec["white_" + tag] = np.array(white.sample(lo, hi, bins))
+        spec["light_" + tag] = np.array(light.sample(lo, hi, bins))
+        spec["bk7_t_" + tag] = np.array(glass.transmission.sample(lo, hi, bins))
+        spec["bk7_n_" + tag] = np.float64(glass.index.average(lo, hi))
+        spec["sf11_t_" + tag] = np.array(sf11.transmission.sample(lo, hi, bins))
+        spec["sf11_n_" + tag] = np.float64(sf11.index.average(lo, hi))
+    save("object_model", zoo_rows=np.array(rows), **spec)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,3 +147,94 @@ def zoo_rays(n, seed=3):
     axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=float)
     d_in[:k] = axes[np.arange(k) % 6]
     return np.ascontiguousarray(np.r_[o_out, o_in]), np.ascontiguousarray(np.r_[d_out, d_in])
+
+
+def icosphere(subdivisions=3, radius=0.5, bumps=0.08, seed=5):
+    """Deterministic closed triangle mesh: subdivided icosahedron with a smooth radial perturbation.
+    Returns (vertices f32 [n,3], triangles i32 [m,6], normals f32 [n,3]) with per-vertex normals."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+         (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[key] = len(v) - 1
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    v = np.array(v)
+    rng = np.random.default_rng(seed)
+    k = rng.normal(size=(4, 3))
+    scale = 1.0 + bumps * sum(np.sin(3.0 * v @ k[i] + i) for i in range(4)) / 4.0
+    verts = (radius * v * scale[:, None]).astype(np.float32)
+    tris = np.array(f, dtype=np.int32)
+    # area-weighted vertex normals
+    p = verts.astype(np.float64)
+    fn = np.cross(p[tris[:, 1]] - p[tris[:, 0]], p[tris[:, 2]] - p[tris[:, 0]])
+    vn = np.zeros_like(p)
+    for i in range(3):
+        np.add.at(vn, tris[:, i], fn)
+    vn /= np.linalg.norm(vn, axis=1)[:, None]
+    return verts, np.ascontiguousarray(np.c_[tris, tris]), vn.astype(np.float32)
+
+
+def mesh_scene(api, smoothing=True):
+    """Two instances of the bumpy icosphere (one via Mesh.instance) plus a floor box."""
+    a = api
+    verts, tris, normals = icosphere()
+    world = a.World()
+    m = a.AbsorbingSurface()
+    mesh = a.Mesh(verts, tris, normals, smoothing=smoothing, closed=True, parent=world,
+                  transform=a.translate(-0.45, 0.1, 0.0) * a.rotate(20, 35, 10), material=m)
+    mesh.instance(parent=world, transform=a.translate(0.55, -0.05, 0.2) * a.rotate(-40, 10, 70), material=m)
+    a.Box(a.Point3D(-2, -0.05, -2), a.Point3D(2, 0, 2), world, a.translate(0, -0.7, 0), m)
+    return world
+
+
+def mesh_rays(n, seed=9):
+    rng = np.random.default_rng(seed)
+    o = np.c_[rng.uniform(-1.5, 1.5, n), rng.uniform(-0.5, 1.5, n), np.full(n, -3.0)]
+    tgt = np.c_[rng.uniform(-1.1, 1.2, n), rng.uniform(-0.7, 0.7, n), rng.uniform(-0.4, 0.6, n)]
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    # a third of the rays start inside the meshes' bounding region
+    k = n // 3
+    o[:k] = np.c_[rng.uniform(-0.9, 1.0, k), rng.uniform(-0.5, 0.6, k), rng.uniform(-0.5, 0.7, k)]
+    d[:k] = rng.normal(size=(k, 3))
+    d[:k] /= np.linalg.norm(d[:k], axis=1)[:, None]
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+def prism_scene(api):
+    """Dispersive CSG scene in the spirit of demos/prism.py:16-107: an SF11 glass prism
+    (Subtract(Subtract(Box, Box), Box)), a Lambert screen cut by Intersect(Box, Subtract(Cylinder,
+    Cylinder)), a small box emitter and an absorbing backdrop."""
+    a = api
+    world = a.World()
+    glass = a.schott("SF11")
+    glass.importance = 9
+    a.Subtract(
+        a.Subtract(a.Box(a.Point3D(-0.3, 0, -0.3), a.Point3D(0.3, 0.5, 0.3)),
+                   a.Box(a.Point3D(-0.3, -0.1, -0.1), a.Point3D(1.0, 0.7, 0.9), transform=a.translate(0.3, 0, 0) * a.rotate(30, 0, 0))),
+        a.Box(a.Point3D(-1.0, -0.1, -0.1), a.Point3D(0.3, 0.7, 0.9), transform=a.translate(-0.3, 0, 0) * a.rotate(-30, 0, 0)),
+        world, a.translate(0, -0.25, 0.3) * a.rotate(15, 0, 0), glass)
+    a.Intersect(a.Box(a.Point3D(-1.2, -0.6, -0.05), a.Point3D(1.2, 0.6, 0.05)),
+                a.Subtract(a.Cylinder(1.3, 0.2, transform=a.translate(0, 0, -0.1)),
+                           a.Cylinder(0.15, 0.4, transform=a.translate(0.4, 0.1, -0.2))),
+                world, a.translate(0, 0, 1.6), a.Lambert(a.ConstantSF(0.8)))
+    a.Box(a.Point3D(-0.2, -0.2, -0.02), a.Point3D(0.2, 0.2, 0.0), world, a.translate(0.1, 0.9, 0.2) * a.rotate(0, 90, 0),
+          a.UniformSurfaceEmitter(a.InterpolatedSF(*CB_LIGHT), 5.0))
+    a.Box(a.Point3D(-3, -3, 0), a.Point3D(3, 3, 0.1), world, a.translate(0, 0, 3), a.AbsorbingSurface())
+    return world
