@@ -146,6 +146,8 @@ typedef struct RsbCounters {
     uint64_t tri_tests;   /* _hit_triangle calls */
     uint64_t paths;       /* primary rays traced by rsb_render */
     uint64_t contains;    /* World.contains queries */
+    uint64_t table_reads; /* per-bin spectral table rows consumed (surface + volume + emission interactions) */
+    uint64_t reserved[3];
 } RsbCounters;
 
 const char* rsb_last_error(void);

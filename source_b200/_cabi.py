@@ -125,10 +125,11 @@ class RsbRngDesc(C.Structure):
 
 class RsbCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
-                ("rays", "branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "contains")]
+                ("rays", "branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "contains",
+                 "table_reads")] + [("reserved", C.c_uint64 * 3)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
 
 
 # every symbol include/raysect_b200.h declares: name -> (restype, argtypes)

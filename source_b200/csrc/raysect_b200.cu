@@ -114,6 +114,7 @@ int read_counters(Context* c, cudaStream_t st) {
     c->last_counters.tri_tests = h.tri_tests;
     c->last_counters.paths = h.paths;
     c->last_counters.contains = h.contains;
+    c->last_counters.table_reads = h.table_reads;
     return RSB_OK;
 }
 

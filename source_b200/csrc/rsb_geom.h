@@ -445,16 +445,20 @@ RSB_HD bool kd_trace(const KdTree& tree, const V3& o, const V3& d, KdStackEntry*
 
 // raysect/core/math/spatial/kdtree3d.pyx:736-792 (_items_containing*): descend to the one leaf
 // holding the point.  Returns false when the point is outside the tree bounds.
-RSB_HD bool kd_locate(const KdTree& tree, const V3& p, int* item_offset, int* item_count) {
+template <class Stats>
+RSB_HD bool kd_locate(const KdTree& tree, const V3& p, int* item_offset, int* item_count, Stats& stats) {
+    stats.contains_query();
     if (!box_contains(tree.bounds, p)) return false;
     int node = 0;
     for (;;) {
         KdNode n = tree.nodes[node];
         if (n.axis < 0) {
+            stats.leaf(n.leaf.item_count);
             *item_offset = n.leaf.item_offset;
             *item_count = n.leaf.item_count;
             return true;
         }
+        stats.branch();
         node = (v3_get(p, n.axis) < n.split) ? node + 1 : n.upper;
     }
 }
@@ -464,10 +468,14 @@ struct NoStats {
     RSB_HD void leaf(int) {}
     RSB_HD void prim_test() {}
     RSB_HD void tri_test() {}
+    RSB_HD void contains_query() {}
+    RSB_HD void table_read() {}
 };
 
 struct CountStats {
-    unsigned long long branches = 0, leaves = 0, items = 0, prim_tests = 0, tri_tests = 0;
+    unsigned long long branches = 0, leaves = 0, items = 0, prim_tests = 0, tri_tests = 0, contains = 0, tables = 0;
+    RSB_HD void contains_query() { ++contains; }
+    RSB_HD void table_read() { ++tables; }
     RSB_HD void branch() { ++branches; }
     RSB_HD void leaf(int n) { ++leaves; items += (unsigned long long)n; }
     RSB_HD void prim_test() { ++prim_tests; }

@@ -20,7 +20,7 @@ namespace rsb {
 #define RSB_RENDER_THREADS 128
 
 struct DevCounters {   // mirrors RsbCounters
-    unsigned long long rays, branches, leaves, items, prim_tests, tri_tests, paths, contains;
+    unsigned long long rays, branches, leaves, items, prim_tests, tri_tests, paths, contains, table_reads, reserved[3];
 };
 
 template <bool COUNT>
@@ -38,8 +38,11 @@ __device__ __forceinline__ void flush_stats(const NoStats&, DevCounters*) {}
 __device__ __forceinline__ void flush_stats(const CountStats& s, DevCounters* c) {
     // all lanes of the warp reach here together (kernel epilogue)
     unsigned long long b = warp_sum(s.branches), l = warp_sum(s.leaves), i = warp_sum(s.items),
-                       p = warp_sum(s.prim_tests), t = warp_sum(s.tri_tests);
+                       p = warp_sum(s.prim_tests), t = warp_sum(s.tri_tests), cq = warp_sum(s.contains),
+                       tb = warp_sum(s.tables);
     if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&c->contains, cq);
+        atomicAdd(&c->table_reads, tb);
         atomicAdd(&c->branches, b);
         atomicAdd(&c->leaves, l);
         atomicAdd(&c->items, i);
@@ -190,7 +193,7 @@ k_contains_batch(Scene sc, long long n, const double* __restrict__ points, int c
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         V3 p = v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
         int offset, count, found = 0;
-        if (kd_locate(sc.world, p, &offset, &count)) {
+        if (kd_locate(sc.world, p, &offset, &count, stats)) {
             for (int k = 0; k < count; ++k) {
                 int id = sc.world.items[offset + k];
                 if (prim_contains(sc, id, p, stack, stats)) {

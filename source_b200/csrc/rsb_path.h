@@ -161,12 +161,14 @@ template <class Stats>
 RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, const V3& w_hit,
                         KdStackEntry* stack, PathLog& log, Stats& stats) {
     int offset, count;
-    if (!kd_locate(sc.world, origin, &offset, &count)) return;
+    if (!kd_locate(sc.world, origin, &offset, &count, stats)) return;
     for (int i = count - 1; i >= 0; --i) {
         int id = sc.world.items[offset + i];
         const Material& m = sp.mats[sc.prims[id].material];
         if (m.type != MAT_DIELECTRIC) continue;   // Lambert/emitter/absorber: evaluate_volume is the identity
+        stats.prim_test();
         if (!prim_contains(sc, id, origin, stack, stats)) continue;
+        stats.table_read();
         // length = start_point.vector_to(end_point).get_length()
         V3 v = v3(origin.x - w_hit.x, origin.y - w_hit.y, origin.z - w_hit.z);
         log.push(LOG_POWA, m.table, length(v));
@@ -224,6 +226,7 @@ RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, 
 
         if (mat.type == MAT_EMITTER) {
             log.push(LOG_EMIT, mat.table, mat.scale);
+            stats.table_read();
             return PATH_EMITTED;
         }
         if (mat.type == MAT_ABSORBER) return PATH_ZERO;
@@ -281,6 +284,7 @@ RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, 
             log.push(LOG_MULS, 0, 1.0 / pdf);
             log.push(LOG_MULS, 0, pdf_cos);
             log.push(LOG_MULA, mat.table, 0.0);
+            stats.table_read();
         } else {
             // Dielectric.evaluate_surface (dielectric.pyx:153-303)
             V3 incident = normalise(xform_vector(w2p, d));

@@ -59,24 +59,20 @@ struct Mt19937_64 {
         mti = RSB_MT_NN;
     }
 
-    // random.pyx:167-212
+    // random.pyx:167-212 (_rand_uint64).  The reference regenerates all 312 words when the cursor runs
+    // out; the recurrence only ever reads word i (old), word i+1 (old, or new word 0 for i = 311) and word
+    // i+156 mod 312 (old for i < 156, already regenerated for i >= 156), so regenerating word i lazily,
+    // in place, at the moment it is drawn yields the identical sequence -- with 3 loads + 1 store per draw
+    // and no 312-trip refill loop for a diverged warp to serialise on.
     RSB_HD uint64_t next_u64() {
-        if (mti >= RSB_MT_NN) {
-            const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL, MAG = 0xB5026F5AA96619E9ULL;
-            int i;
-            for (i = 0; i < RSB_MT_NN - RSB_MT_MM; ++i) {
-                uint64_t x = (w(i) & UM) | (w(i + 1) & LM);
-                w(i) = w(i + RSB_MT_MM) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
-            }
-            for (; i < RSB_MT_NN - 1; ++i) {
-                uint64_t x = (w(i) & UM) | (w(i + 1) & LM);
-                w(i) = w(i + (RSB_MT_MM - RSB_MT_NN)) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
-            }
-            uint64_t x = (w(RSB_MT_NN - 1) & UM) | (w(0) & LM);
-            w(RSB_MT_NN - 1) = w(RSB_MT_MM - 1) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
-            mti = 0;
-        }
-        uint64_t x = w(mti++);
+        const uint64_t UM = 0xFFFFFFFF80000000ULL, LM = 0x7FFFFFFFULL, MAG = 0xB5026F5AA96619E9ULL;
+        int i = (mti >= RSB_MT_NN) ? 0 : mti;
+        int i1 = (i + 1 == RSB_MT_NN) ? 0 : i + 1;
+        int im = (i + RSB_MT_MM >= RSB_MT_NN) ? i + RSB_MT_MM - RSB_MT_NN : i + RSB_MT_MM;
+        uint64_t x = (w(i) & UM) | (w(i1) & LM);
+        x = w(im) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
+        w(i) = x;
+        mti = i + 1;
         x ^= (x >> 29) & 0x5555555555555555ULL;
         x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
         x ^= (x << 37) & 0xFFF7EEE000000000ULL;

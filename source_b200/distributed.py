@@ -1,0 +1,136 @@
+"""One process per GPU: image tiles are partitioned across ranks, each rank renders every sample of its
+own tiles into an otherwise-zero frame, and ONE NCCL reduce(sum) over NVLink assembles the spectral frame
+on rank 0 (exact: non-owned entries are zero, so the sum only ever adds zeros).
+
+The reference's only parallelism is the same pixel-task data parallelism over forked processes with
+pickled (mean, variance) tuples (raysect/core/workflow.py:123-327); pixel random streams are keyed on the
+pixel, so the frame does not depend on the number of ranks.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as cabi
+from .engine import camera_desc, ray_config
+
+
+def tile_pixels(nx, ny, tile, rank, world_size):
+    """Pixels (x, y) of the tiles owned by `rank`: tile t (row-major over the tile grid) -> rank t % world_size."""
+    tx, ty = (nx + tile - 1) // tile, (ny + tile - 1) // tile
+    t = np.arange(tx * ty)
+    mine = t[t % world_size == rank]
+    ox, oy = (mine // ty) * tile, (mine % ty) * tile
+    dx, dy = np.meshgrid(np.arange(tile), np.arange(tile), indexing="ij")
+    x = (ox[:, None, None] + dx[None]).reshape(-1)
+    y = (oy[:, None, None] + dy[None]).reshape(-1)
+    keep = (x < nx) & (y < ny)
+    return np.ascontiguousarray(np.stack([x[keep], y[keep]], axis=1).astype(np.int32))
+
+
+class FrameRenderer:
+    """Renders one spectral slice of a PinholeCamera frame on `world_size` GPUs (this process = `rank`)."""
+
+    def __init__(self, camera, accel, rank=0, world_size=1, tile=16, backend_reduce=None):
+        import torch
+        self.torch = torch
+        self.camera, self.accel = camera, accel
+        self.rank, self.world_size = rank, world_size
+        nx, ny = camera.pixels
+        self.nx, self.ny, self.bins = nx, ny, camera.spectral_bins
+        if camera.spectral_rays != 1:
+            raise NotImplementedError("FrameRenderer handles one spectral slice per call")
+        self.dev = torch.device("cuda", accel.device.index)
+        self.cam = camera_desc(nx, ny, camera.pixel_samples, camera.fov, camera.sensitivity, camera.to_root())
+        self.cfg = ray_config(self.bins, camera.min_wavelength, camera.max_wavelength, camera.ray_extinction_prob,
+                              camera.ray_extinction_min_depth, camera.ray_max_depth, camera.ray_importance_sampling,
+                              camera.ray_important_path_weight)
+        self.spectral = accel.flat.spectral(camera.min_wavelength, camera.max_wavelength, self.bins)
+        self.host_pixels = None
+        self.dev_pixels = None
+        if world_size > 1:
+            px = tile_pixels(nx, ny, tile, rank, world_size)
+            self.host_pixels = torch.from_numpy(px).pin_memory()
+            self.dev_pixels = self.host_pixels.to(self.dev)
+        # [0] mean, [1] variance: one tensor so that the frame crosses NVLink in a single reduce
+        self.stats = torch.zeros((2, nx, ny, self.bins), dtype=torch.float64, device=self.dev)
+        self.out = torch.zeros_like(self.stats) if (world_size > 1 and rank == 0) else None
+        self.host_stats = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._reduce = backend_reduce
+
+    def _render(self, seed, pixels, count=False):
+        return self.accel.render_device(self.cam, self.cfg, self.spectral, self.camera.rng_mode, seed, pixels,
+                                        self.stats[0], self.stats[1], count=count)[2]
+
+    def _assemble(self):
+        """single reduce(sum) of the (mean, variance) frame to rank 0"""
+        if self.world_size == 1:
+            return self.stats
+        import torch.distributed as dist
+        if self.rank == 0:
+            self.out.copy_(self.stats)      # keep this rank's buffer zero outside its own tiles for the next step
+            dist.reduce(self.out, dst=0, op=dist.ReduceOp.SUM)
+            return self.out
+        dist.reduce(self.stats, dst=0, op=dist.ReduceOp.SUM)
+        return None
+
+    def step_device(self, seed, kernel_events=None):
+        """One frame with everything resident in HBM.  Returns this rank's ray counter (device tensor)."""
+        if kernel_events:
+            kernel_events[0].record()
+        rays = self._render(seed, self.dev_pixels)
+        if kernel_events:
+            kernel_events[1].record()
+        self._assemble()
+        return rays
+
+    def step_host(self, seed):
+        """One frame through host buffers: pixel list and tables host->device, frame device->host (pinned),
+        installed as the pipeline's StatsArray3D.  Returns this rank's ray count (int)."""
+        torch = self.torch
+        h2d = self.accel.flat.materials.__len__() * self.bins * 8
+        pixels = None
+        if self.host_pixels is not None:
+            pixels = self.host_pixels.to(self.dev, non_blocking=True)
+            h2d += self.host_pixels.numel() * 4
+        rays = self._render(seed, pixels)
+        frame = self._assemble()
+        d2h = 8
+        if self.rank == 0:
+            if self.host_stats is None:
+                self.host_stats = torch.zeros(self.stats.shape, dtype=torch.float64).pin_memory()
+            self.host_stats.copy_(frame, non_blocking=True)
+            d2h += self.host_stats.numel() * 8
+        n = int(rays.item())    # device->host read of the step's ray counter; synchronises the stream
+        if self.rank == 0:
+            torch.cuda.current_stream(self.dev).synchronize()
+            pipe = self.camera.pipelines[0]
+            hs = self.host_stats.numpy()
+            if pipe.frame is None or pipe.frame.shape != (self.nx, self.ny, self.bins) or not pipe.accumulate:
+                from .observer import StatsArray3D
+                f = StatsArray3D.__new__(StatsArray3D)
+                f.nx, f.ny, f.nz = self.nx, self.ny, self.bins
+                f.mean, f.variance = hs[0], hs[1]
+                f.samples = np.full((self.nx, self.ny, self.bins), self.camera.pixel_samples, dtype=np.int32) \
+                    if getattr(self, "_samples", None) is None else self._samples
+                self._samples = f.samples
+                pipe.frame = f
+            else:
+                pipe._samples = self.camera.pixel_samples
+                pipe._spectral_slices = self.camera._slice_spectrum()
+                pipe.update_slice(None, 0, hs[0], hs[1])
+        self.h2d_bytes, self.d2h_bytes = h2d, d2h
+        return n
+
+    def count_pass(self, seed):
+        """Untimed pass with the traversal counters switched on (roofline model inputs)."""
+        self._render(seed, self.dev_pixels, count=True)
+        c = self.accel.device.counters()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            keys = sorted(c)
+            t = self.torch.tensor([c[k] for k in keys], dtype=self.torch.int64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            c = {k: int(v) for k, v in zip(keys, t.tolist())}
+        return c

@@ -142,9 +142,33 @@ class Accelerator:
             cap = int(count[0])
 
     # ---- Observer._render_pixel over a pixel list ---------------------------------------------------------
+    def render_device(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None,
+                      count=False, stream=None):
+        """Device-resident form: ``mean``/``variance`` are torch CUDA float64 tensors of shape (nx, ny, bins)
+        (allocated zero-filled when None), ``pixels`` an int32 CUDA tensor [n, 2] or None for the whole frame.
+        Enqueues on torch's current stream and returns (mean, variance, ray_count_tensor) without synchronising
+        (unless ``count``, which reads the traversal counters back)."""
+        import torch
+        dev = torch.device("cuda", self.device.index)
+        nx, ny, bins = camera.nx, camera.ny, config.bins
+        if mean is None:
+            mean = torch.zeros((nx, ny, bins), dtype=torch.float64, device=dev)
+        if variance is None:
+            variance = torch.zeros((nx, ny, bins), dtype=torch.float64, device=dev)
+        rays = torch.zeros(1, dtype=torch.int64, device=dev)
+        n = nx * ny if pixels is None else int(pixels.shape[0])
+        rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        cabi.check(self.lib.rsb_render_dev(
+            self.device.ctx, self.scene, C.c_void_p(st.cuda_stream), C.byref(camera), C.byref(config), C.byref(spectral),
+            C.byref(rng), n, C.c_void_p(0 if pixels is None else pixels.data_ptr()), C.c_void_p(mean.data_ptr()),
+            C.c_void_p(variance.data_ptr()), C.c_void_p(rays.data_ptr()), int(bool(count))))
+        return mean, variance, rays
+
     def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
-        """camera: RsbCamera, config: RsbRayConfig, spectral: RsbSpectral (from FlatScene.spectral()).
-        Returns (mean, variance, ray_count); mean/variance are (nx, ny, bins) float64."""
+        """Host-buffer form (the call the observer makes): camera: RsbCamera, config: RsbRayConfig, spectral:
+        RsbSpectral (from FlatScene.spectral()).  Returns (mean, variance, ray_count); mean/variance are
+        (nx, ny, bins) float64 numpy arrays; only the listed pixels are written."""
         nx, ny, bins = camera.nx, camera.ny, config.bins
         if mean is None:
             mean = np.zeros((nx, ny, bins), dtype=np.float64)

@@ -131,7 +131,7 @@ int hs_contains_batch(uint64_t scene, int64_t n, const double* points, int32_t c
         V3 p = v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
         int offset, count, found = 0;
         for (int k = 0; k < cap; ++k) out_prims[i * cap + k] = -1;
-        if (kd_locate(h->sc.world, p, &offset, &count)) {
+        if (kd_locate(h->sc.world, p, &offset, &count, stats)) {
             for (int k = 0; k < count; ++k) {
                 int id = h->sc.world.items[offset + k];
                 if (prim_contains(h->sc, id, p, stack, stats)) {
