@@ -49,10 +49,10 @@ struct Context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevCounters* d_counters = nullptr;
     unsigned long long* d_scalars = nullptr;   // [0] work counter, [1] ray count, [2] overflow flag (as int)
-    unsigned long long* d_mt = nullptr;
-    size_t mt_threads = 0;
-    LogEntry* d_log = nullptr;
-    size_t log_entries = 0;
+    unsigned char* d_slots = nullptr;   // wavefront slot state (rsb_kernels.cuh: WfSlots)
+    size_t slot_bytes = 0;
+    unsigned int* h_idle = nullptr;     // pinned
+    long long last_waves = 0;
     Material* d_mats = nullptr;
     double* d_tables = nullptr;
     size_t mats_cap = 0, tables_cap = 0;
@@ -214,6 +214,7 @@ int rsb_context_create(int device, uint64_t* ctx) {
     RSB_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     RSB_CUDA(cudaMalloc(&c->d_scalars, 8 * sizeof(unsigned long long)));
     RSB_CUDA(cudaMemset(c->d_scalars, 0, 8 * sizeof(unsigned long long)));
+    RSB_CUDA(cudaMallocHost(&c->h_idle, sizeof(unsigned int)));
     *ctx = reinterpret_cast<uint64_t>(c);
     return RSB_OK;
 }
@@ -225,8 +226,8 @@ int rsb_context_destroy(uint64_t ctx) {
     for (DeviceScene* s : c->scenes) free_scene(s);
     cudaFree(c->d_counters);
     cudaFree(c->d_scalars);
-    cudaFree(c->d_mt);
-    cudaFree(c->d_log);
+    cudaFree(c->d_slots);
+    cudaFreeHost(c->h_idle);
     cudaFree(c->d_mats);
     cudaFree(c->d_tables);
     cudaEventDestroy(c->ev0);
@@ -490,18 +491,73 @@ int rsb_rng_uniform(uint64_t ctx, uint64_t seed, int64_t n, double* out) {
 
 namespace {
 
+// carve the slot state out of one allocation
+struct Carver {
+    unsigned char* base;
+    size_t off = 0;
+    template <class T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, WfSlots* st) {
+    Carver c{base};
+    st->ray = c.take<double>(6 * P);
+    st->weight = c.take<double>(P);
+    st->norm = c.take<double>(P);
+    st->hit_t = c.take<double>(P);
+    st->hit_a = c.take<int4>(P);
+    st->hit_uvw = c.take<float4>(P);
+    st->depth = c.take<int32_t>(P);
+    st->rays = c.take<uint32_t>(P);
+    st->sample = c.take<int32_t>(P);
+    st->px = c.take<int32_t>(P);
+    st->py = c.take<int32_t>(P);
+    st->status = c.take<int32_t>(P);
+    st->log_n = c.take<int32_t>(P);
+    st->philox_idx = c.take<uint32_t>(P);
+    st->mti = c.take<int32_t>(2 * P);
+    st->ended = c.take<int32_t>(2 * P);
+    st->n_ended = c.take<unsigned int>(2);
+    st->mt = mt ? c.take<unsigned long long>(P * 2 * RSB_MT_NN) : nullptr;
+    st->log = c.take<LogEntry>(P * cap);
+    return (c.off + 255) & ~(size_t)255;
+}
+
 template <int RNGMODE, bool COUNT>
-int launch_render(Context* c, const RenderArgs& args, int blocks_per_sm_cap, size_t smem, cudaStream_t st, size_t* threads_out) {
-    auto kern = k_render<RNGMODE, COUNT>;
-    if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    RSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RSB_RENDER_THREADS, smem));
-    if (per_sm < 1) return fail(RSB_ERR_CUDA, "render kernel does not fit on an SM");
-    per_sm = std::min(per_sm, blocks_per_sm_cap);
-    int grid = c->sm_count * per_sm;
-    *threads_out = (size_t)grid * RSB_RENDER_THREADS;
-    (void)args;
-    return grid;
+int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st) {
+    const int threads = 128;
+    const int grid = (a.n_slots + threads - 1) / threads;
+    const int fin_grid = std::max(1, std::min(grid, c->sm_count * 16));
+    if (smem_shade > 48 * 1024) {
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
+    }
+    if (smem_tables > 48 * 1024)
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+    a.wave = 0;
+    k_wf_init<RNGMODE><<<grid, threads, 0, st>>>(a);
+    RSB_CUDA(cudaGetLastError());
+    unsigned int* h_idle = c->h_idle;
+    const int kBatch = 32;
+    for (long long wave = 0;;) {
+        for (int b = 0; b < kBatch; ++b, ++wave) {
+            a.wave = (int32_t)(wave & 0x7fffffff);
+            k_wf_trace<RNGMODE, COUNT><<<grid, threads, smem_scene, st>>>(a);
+            k_wf_shade<RNGMODE, COUNT><<<grid, threads, smem_shade, st>>>(a);
+            k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, st>>>(a);
+        }
+        RSB_CUDA(cudaGetLastError());
+        RSB_CUDA(cudaMemcpyAsync(h_idle, a.n_idle, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        RSB_CUDA(cudaStreamSynchronize(st));
+        if (*h_idle >= (unsigned int)a.n_slots) break;
+    }
+    c->last_waves = 0;
+    return RSB_OK;
 }
 
 }  // namespace
@@ -559,7 +615,7 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     // the two host staging buffers above are stack/heap temporaries: make the copies complete before returning
     RSB_CUDA(cudaStreamSynchronize(st));
 
-    RenderArgs a;
+    WfArgs a;
     memset(&a, 0, sizeof(a));
     a.sc = ds->sc;
     a.sp.mats = c->d_mats;
@@ -589,70 +645,55 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     a.variance = variance_dev;
     a.ray_count = (unsigned long long*)ray_count_dev;
     a.work_counter = c->d_scalars;
+    a.n_idle = (unsigned int*)(c->d_scalars + 1);
     a.overflow_flag = (int32_t*)(c->d_scalars + 2);
     a.counters = c->d_counters;
     a.seed = rng->seed;
     a.n_items = ds->n_world_items;
     a.staged = ds->stage_bytes ? 1 : 0;
-    size_t smem = ds->stage_bytes;
-    if (smem + mat_bytes + tab_bytes <= kMaxStageBytes) {
+    size_t smem_scene = ds->stage_bytes, smem_shade = ds->stage_bytes, smem_tables = 0;
+    if (smem_shade + mat_bytes <= kMaxStageBytes && tab_bytes <= kMaxStageBytes) {
         a.tables_staged = 1;
-        smem += mat_bytes + tab_bytes;
+        smem_shade += mat_bytes;
+        smem_tables = tab_bytes;
     }
     // a path of D segments logs at most 3 surface + 1 roulette entries per segment plus one per enclosing
     // dielectric; budget 6 per segment
     long long cap = 6LL * ((long long)std::max(config->max_depth, config->extinction_min_depth) + 2);
-    a.log_capacity = (int32_t)std::min(cap, 1LL << 20);
+    a.log_capacity = (int32_t)std::min(cap, 1LL << 16);
 
-    size_t threads = 0;
-    int grid;
-    const int kBlocksCap = 8;
+    // ---- slot pool: one pixel stream per slot, two CTA waves of 1024 threads per SM ---------------------
     bool mt = rng->mode == RSB_RNG_MT19937_64;
-    if (mt) grid = count ? launch_render<RNG_MT19937_64, true>(c, a, kBlocksCap, smem, st, &threads)
-                         : launch_render<RNG_MT19937_64, false>(c, a, kBlocksCap, smem, st, &threads);
-    else grid = count ? launch_render<RNG_PHILOX, true>(c, a, kBlocksCap, smem, st, &threads)
-                      : launch_render<RNG_PHILOX, false>(c, a, kBlocksCap, smem, st, &threads);
-    if (threads == 0) return grid;   // error code
-    // do not launch more pixel streams than there are pixels (small frames)
-    {
-        long long need_blocks = (n_pixels + RSB_RENDER_THREADS - 1) / RSB_RENDER_THREADS;
-        if (need_blocks < grid) { grid = (int)need_blocks; threads = (size_t)grid * RSB_RENDER_THREADS; }
+    long long P = std::min<long long>(n_pixels, (long long)c->sm_count * 2048);
+    P = std::max<long long>(P, 1);
+    a.n_slots = (int32_t)P;
+    WfSlots probe;
+    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, &probe);
+    if (c->slot_bytes < need) {
+        cudaFree(c->d_slots);
+        c->d_slots = nullptr; c->slot_bytes = 0;
+        RSB_CUDA(cudaMalloc(&c->d_slots, need));
+        c->slot_bytes = need;
     }
-    // ---- per-thread pools -------------------------------------------------------------------------
-    size_t log_need = threads * (size_t)a.log_capacity;
-    if (c->log_entries < log_need) {
-        cudaFree(c->d_log);
-        c->d_log = nullptr; c->log_entries = 0;
-        RSB_CUDA(cudaMalloc(&c->d_log, log_need * sizeof(LogEntry)));
-        c->log_entries = log_need;
-    }
-    a.log_pool = c->d_log;
-    if (mt) {
-        if (c->mt_threads < threads) {
-            cudaFree(c->d_mt);
-            c->d_mt = nullptr; c->mt_threads = 0;
-            RSB_CUDA(cudaMalloc(&c->d_mt, threads * 2 * RSB_MT_NN * sizeof(unsigned long long)));
-            c->mt_threads = threads;
-        }
-        a.mt_state = c->d_mt;
-    }
+    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, &a.st);
     RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
+    RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-    if (mt) {
-        if (count) k_render<RNG_MT19937_64, true><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
-        else k_render<RNG_MT19937_64, false><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
-    } else {
-        if (count) k_render<RNG_PHILOX, true><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
-        else k_render<RNG_PHILOX, false><<<grid, RSB_RENDER_THREADS, smem, st>>>(a);
-    }
-    RSB_CUDA(cudaGetLastError());
-    if (count) {
-        int rc = read_counters(c, st);
-        if (rc) return rc;
+    int rc;
+    if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st)
+                       : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st);
+    else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st)
+                    : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st);
+    if (rc) return rc;
+    {
         int32_t overflow = 0;
         RSB_CUDA(cudaMemcpyAsync(&overflow, a.overflow_flag, 4, cudaMemcpyDeviceToHost, st));
         RSB_CUDA(cudaStreamSynchronize(st));
         if (overflow) return fail(RSB_ERR_OVERFLOW, "rsb_render: a path exceeded the per-path log capacity");
+    }
+    if (count) {
+        rc = read_counters(c, st);
+        if (rc) return rc;
     }
     return RSB_OK;
 }

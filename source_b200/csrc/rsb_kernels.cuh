@@ -217,176 +217,327 @@ __global__ void k_rng_uniform(unsigned long long seed, long long n, unsigned lon
 }
 
 // ---------------------------------------------------------------------------------------------
-struct RenderArgs {
+// Wavefront renderer.  Observer._render_pixel (observer.pyx:363-419) runs one path at a time per pixel
+// and the reference's RNG stream makes a pixel's samples inherently sequential, so the unit of
+// parallelism is the PIXEL STREAM: P slots, each owning one pixel at a time (dynamic assignment from a
+// work counter) and carrying exactly one path.  A "wave" advances every live path by one segment through
+// three small kernels, so that all warps of an SM execute the same few KB of code (the monolithic
+// per-thread path tracer measured 68 % instruction-fetch stalls and 6.7 of 32 lanes active, see
+// profiles/):
+//   k_wf_trace     roulette + World.hit                 1 thread = 1 slot
+//   k_wf_shade     geometry, material, volumes, spawn   1 thread = 1 slot
+//   k_wf_finalize  ended paths: log replay + Welford into the frame (1 warp = 1 path, lane = bin),
+//                  then the slot's next sample / next pixel is generated
+// Slot state is SoA in HBM; ended slots are handed to k_wf_finalize through a compacted list.
+// ---------------------------------------------------------------------------------------------
+enum SlotStatus : int32_t { SLOT_IDLE = 0, SLOT_ALIVE = 1, SLOT_HIT = 2, SLOT_ENDED_ZERO = 3, SLOT_ENDED_EMIT = 4 };
+
+struct WfSlots {
+    double* ray;            // [6][P] origin xyz, direction xyz
+    double* weight;         // [P] projection weight of the sample in flight
+    double* norm;           // [P] roulette normalisation of the segment in flight
+    double* hit_t;          // [P]
+    int4* hit_a;            // [P] prim, leaf, code, flip
+    float4* hit_uvw;        // [P] mesh barycentrics
+    int32_t* depth;         // [P]
+    uint32_t* rays;         // [P] reference ray counter of the path in flight
+    int32_t* sample;        // [P] index of the sample in flight
+    int32_t* px;            // [P]
+    int32_t* py;            // [P]
+    int32_t* status;        // [P]
+    int32_t* log_n;         // [P]
+    uint32_t* philox_idx;   // [P]
+    int32_t* mti;           // [2][P]  path stream, jitter stream cursors
+    unsigned long long* mt; // [P][2][312]
+    LogEntry* log;          // [P][log_capacity]
+    int32_t* ended;         // [2][P] compacted lists of ended slots (double buffered by wave parity)
+    unsigned int* n_ended;  // [2]
+};
+
+struct WfArgs {
     Scene sc;
     Spectral sp;
     RayConfig cfg;
     Camera cam;
+    WfSlots st;
     long long n_pixels;
-    const int32_t* pixels;          // [n][2] or null
+    const int32_t* pixels;
     double* mean;
     double* variance;
     unsigned long long* ray_count;
     unsigned long long* work_counter;
-    unsigned long long* mt_state;   // [2][312][T] word-interleaved across the T threads of the grid
-    LogEntry* log_pool;             // [capacity][T]
+    unsigned int* n_idle;
     int32_t* overflow_flag;
     DevCounters* counters;
     unsigned long long seed;
+    int32_t n_slots;
     int32_t log_capacity;
     int32_t n_items;
     int32_t staged;
     int32_t tables_staged;
+    int32_t wave;
 };
 
+template <int RNGMODE>
+__device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng) {
+    rng.mode = RNGMODE;
+    if (RNGMODE == RNG_MT19937_64) {
+        rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.mt) + (size_t)slot * (2 * RSB_MT_NN);
+        rng.mt.stride = 1;
+        rng.mt.mti = a.st.mti[slot];
+    } else {
+        long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
+        rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)a.st.sample[slot]);
+        rng.px.idx = a.st.philox_idx[slot];
+    }
+}
+
+template <int RNGMODE>
+__device__ __forceinline__ void wf_store_rng(const WfArgs& a, int slot, const Rng& rng) {
+    if (RNGMODE == RNG_MT19937_64) a.st.mti[slot] = rng.mt.mti;
+    else a.st.philox_idx[slot] = rng.px.idx;
+}
+
+__device__ __forceinline__ void wf_push_ended(const WfArgs& a, int slot) {
+    int par = a.wave & 1;
+    unsigned int k = atomicAdd(&a.st.n_ended[par], 1u);
+    a.st.ended[(size_t)par * a.n_slots + k] = slot;
+}
+
+// Next sample of the slot's pixel, or the next pixel from the work counter (FullFrameSampler2D task list);
+// PinholeCamera._generate_rays for that sample.  Runs on one thread.
+template <int RNGMODE>
+__device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
+    const int spp = a.cam.pixel_samples;
+    int s = a.st.sample[slot];
+    int px = a.st.px[slot], py = a.st.py[slot];
+    Rng jit;
+    jit.mode = RNGMODE;
+    jit.mt.mt = reinterpret_cast<uint64_t*>(a.st.mt) + (size_t)slot * (2 * RSB_MT_NN) + RSB_MT_NN;
+    jit.mt.stride = 1;
+    jit.mt.mti = a.st.mti[a.n_slots + slot];
+    if (s >= spp) {
+        unsigned long long w = atomicAdd(a.work_counter, 1ULL);
+        if (w >= (unsigned long long)a.n_pixels) {
+            a.st.status[slot] = SLOT_IDLE;
+            atomicAdd(a.n_idle, 1u);
+            return;
+        }
+        if (a.pixels) { px = a.pixels[2 * w]; py = a.pixels[2 * w + 1]; }
+        else { px = (int)(w / (unsigned long long)a.cam.ny); py = (int)(w % (unsigned long long)a.cam.ny); }
+        a.st.px[slot] = px;
+        a.st.py[slot] = py;
+        s = 0;
+        if (RNGMODE == RNG_MT19937_64) {
+            // seed(seed + pixel_id): the jitter cursor starts at draw 0, the path cursor after the 2*spp draws
+            // that RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
+            long long pixel_id = (long long)py * a.cam.nx + px;
+            jit.mt.seed(a.seed + (unsigned long long)pixel_id);
+            Mt19937_64 path;
+            path.mt = jit.mt.mt - RSB_MT_NN;
+            path.stride = 1;
+            for (int i = 0; i < RSB_MT_NN; ++i) path.w(i) = jit.mt.w(i);
+            path.mti = RSB_MT_NN;
+            for (int i = 0; i < 2 * spp; ++i) (void)path.next_u64();
+            a.st.mti[slot] = path.mti;
+        }
+    }
+    a.st.sample[slot] = s;
+    double u1, u2;
+    if (RNGMODE == RNG_MT19937_64) {
+        u1 = jit.uniform();
+        u2 = jit.uniform();
+        a.st.mti[a.n_slots + slot] = jit.mt.mti;
+    } else {
+        long long pixel_id = (long long)py * a.cam.nx + px;
+        jit.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)s);
+        u1 = jit.uniform();
+        u2 = jit.uniform();
+        a.st.philox_idx[slot] = jit.px.idx;
+    }
+    V3 o, d;
+    double weight;
+    pinhole_ray(a.cam, px, py, u1, u2, &o, &d, &weight);
+    const size_t P = (size_t)a.n_slots;
+    a.st.ray[0 * P + slot] = o.x; a.st.ray[1 * P + slot] = o.y; a.st.ray[2 * P + slot] = o.z;
+    a.st.ray[3 * P + slot] = d.x; a.st.ray[4 * P + slot] = d.y; a.st.ray[5 * P + slot] = d.z;
+    a.st.weight[slot] = weight;
+    a.st.depth[slot] = 0;
+    a.st.rays[slot] = 1;
+    a.st.log_n[slot] = 0;
+    a.st.status[slot] = SLOT_ALIVE;
+}
+
+template <int RNGMODE>
+__global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs a) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_slots) return;
+    a.st.sample[slot] = a.cam.pixel_samples;   // forces a pixel fetch
+    a.st.px[slot] = 0;
+    a.st.py[slot] = 0;
+    a.st.mti[slot] = RSB_MT_NN;
+    a.st.mti[a.n_slots + slot] = RSB_MT_NN;
+    wf_regenerate<RNGMODE>(a, slot);
+}
+
 template <int RNGMODE, bool COUNT>
-__global__ void __launch_bounds__(RSB_RENDER_THREADS)
-k_render(const __grid_constant__ RenderArgs a) {
+__global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Scene sc = a.sc;
+    stage_scene(sc, smem, a.n_items, a.staged);
+    typename StatsSel<COUNT>::type stats;
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = slot < a.n_slots && a.st.status[slot] == SLOT_ALIVE;
+    unsigned long long hits = 0;
+    if (active) {
+        const size_t P = (size_t)a.n_slots;
+        PathState ps;
+        ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
+        ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
+        ps.depth = a.st.depth[slot];
+        ps.rays = 0;
+        Rng rng;
+        wf_load_rng<RNGMODE>(a, slot, rng);
+        KdStackEntry stack[RSB_KD_STACK];
+        HitRec rec;
+        double normalisation;
+        int r = path_trace(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats);
+        wf_store_rng<RNGMODE>(a, slot, rng);
+        hits = 1;
+        if (r == PATH_CONTINUE) {
+            a.st.hit_t[slot] = rec.t;
+            a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
+            a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
+            a.st.norm[slot] = normalisation;
+            a.st.status[slot] = SLOT_HIT;
+        } else {
+            a.st.status[slot] = SLOT_ENDED_ZERO;
+            wf_push_ended(a, slot);
+        }
+    }
+    if (COUNT) {
+        __syncwarp();
+        hits = warp_sum(hits);
+        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&a.counters->rays, hits);
+        flush_stats(stats, a.counters);
+    }
+}
+
+template <int RNGMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     Spectral sp = a.sp;
     stage_scene(sc, smem, a.n_items, a.staged);
     if (a.tables_staged) {
-        // materials + per-slice spectral tables behind the scene data
         StageLayout l = stage_layout(a.staged ? a.sc.world.n_nodes : 0, a.staged ? a.n_items : 0, a.staged ? a.sc.n_prims : 0);
         unsigned char* base = smem + l.total;
         int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
-        int tab_bytes = ((sp.n_materials * sp.bins * 8 + 15) / 16) * 16;
         copy16(base, a.sp.mats, mat_bytes);
-        copy16(base + mat_bytes, a.sp.tables, tab_bytes);
         __syncthreads();
         sp.mats = reinterpret_cast<const Material*>(base);
-        sp.tables = reinterpret_cast<const double*>(base + mat_bytes);
     }
-
     typename StatsSel<COUNT>::type stats;
-    KdStackEntry stack[RSB_KD_STACK];
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = slot < a.n_slots && a.st.status[slot] == SLOT_HIT;
+    if (active) {
+        const size_t P = (size_t)a.n_slots;
+        PathState ps;
+        ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
+        ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
+        ps.depth = a.st.depth[slot];
+        ps.rays = a.st.rays[slot];
+        HitRec rec;
+        rec.t = a.st.hit_t[slot];
+        int4 h = a.st.hit_a[slot];
+        float4 uvw = a.st.hit_uvw[slot];
+        rec.prim = h.x; rec.leaf = h.y; rec.code = h.z; rec.flip = h.w;
+        rec.u = uvw.x; rec.v = uvw.y; rec.w = uvw.z;
+        rec.mesh_node = __float_as_int(uvw.w);
+        rec.node = -1;
+        Rng rng;
+        wf_load_rng<RNGMODE>(a, slot, rng);
+        PathLog log;
+        log.base = a.st.log + (size_t)slot * a.log_capacity;
+        log.stride = 1;
+        log.capacity = a.log_capacity;
+        log.n = a.st.log_n[slot];
+        log.overflow = 0;
+        KdStackEntry stack[RSB_KD_STACK];
+        int r = path_shade(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
+        wf_store_rng<RNGMODE>(a, slot, rng);
+        a.st.log_n[slot] = log.n;
+        if (log.overflow) atomicExch(a.overflow_flag, 1);
+        if (r == PATH_CONTINUE) {
+            a.st.ray[0 * P + slot] = ps.o.x; a.st.ray[1 * P + slot] = ps.o.y; a.st.ray[2 * P + slot] = ps.o.z;
+            a.st.ray[3 * P + slot] = ps.d.x; a.st.ray[4 * P + slot] = ps.d.y; a.st.ray[5 * P + slot] = ps.d.z;
+            a.st.depth[slot] = ps.depth;
+            a.st.rays[slot] = ps.rays;
+            a.st.status[slot] = SLOT_ALIVE;
+        } else {
+            a.st.status[slot] = (r == PATH_EMITTED) ? SLOT_ENDED_EMIT : SLOT_ENDED_ZERO;
+            wf_push_ended(a, slot);
+        }
+    }
+    if (COUNT) {
+        __syncwarp();
+        flush_stats(stats, a.counters);
+    }
+}
+
+// 1 warp = 1 ended path: the reference's unwind (per-bin multiplies), projection weight, sensitivity and
+// PixelProcessor.add_sample (Welford) for bins lane, lane+32, ...; then lane 0 starts the slot's next sample.
+template <int RNGMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Spectral sp = a.sp;
+    if (a.tables_staged) {
+        int tab_bytes = ((sp.n_materials * sp.bins * 8 + 15) / 16) * 16;
+        copy16(smem, a.sp.tables, tab_bytes);
+        __syncthreads();
+        sp.tables = reinterpret_cast<const double*>(smem);
+    }
+    const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
-    const size_t warp_tid0 = tid - lane;
+    const unsigned int n = a.st.n_ended[par];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.st.n_ended[par ^ 1] = 0;   // list of the next wave
+    const int warps = (gridDim.x * blockDim.x) >> 5;
     const int bins = sp.bins;
-    const int spp = a.cam.pixel_samples;
-
-    Rng rng;        // path stream
-    Rng jit;        // jitter stream (MT mode: the pixel's stream before the 2*spp jitter draws were consumed)
-    rng.mode = RNGMODE;
-    jit.mode = RNGMODE;
-    rng.mt.mt = a.mt_state ? reinterpret_cast<uint64_t*>(a.mt_state) + tid : nullptr;
-    rng.mt.stride = T;
-    rng.mt.mti = RSB_MT_NN;
-    jit.mt.mt = a.mt_state ? reinterpret_cast<uint64_t*>(a.mt_state) + (size_t)RSB_MT_NN * T + tid : nullptr;
-    jit.mt.stride = T;
-    jit.mt.mti = RSB_MT_NN;
-
-    PathLog log;
-    log.base = a.log_pool + tid;
-    log.stride = T;
-    log.capacity = a.log_capacity;
-    log.n = 0;
-    log.overflow = 0;
-
-    PathState ps;
-    ps.depth = 0; ps.rays = 0;
-    ps.o = v3(0, 0, 0); ps.d = v3(0, 0, 1);
-    long long frame_row = 0;     // (x*ny + y): row of the pixel in the frame arrays
-    long long pixel_id = 0;      // y*nx + x: RNG stream id
-    int px = 0, py = 0;
-    int s = spp;                 // next sample index of the current pixel; spp => need a pixel
-    bool have_path = false, exhausted = false;
-    double weight = 0.0;
-    unsigned long long my_rays = 0, my_paths = 0, my_hits = 0;
-
-    for (;;) {
-        // ---- regenerate: next sample of this lane's pixel, or a new pixel ---------------------------
-        if (!have_path && !exhausted) {
-            if (s >= spp) {
-                unsigned long long w = atomicAdd(a.work_counter, 1ULL);
-                if (w >= (unsigned long long)a.n_pixels) {
-                    exhausted = true;
-                } else {
-                    if (a.pixels) { px = a.pixels[2 * w]; py = a.pixels[2 * w + 1]; }
-                    else { px = (int)(w / (unsigned long long)a.cam.ny); py = (int)(w % (unsigned long long)a.cam.ny); }
-                    frame_row = (long long)px * a.cam.ny + py;
-                    pixel_id = (long long)py * a.cam.nx + px;
-                    s = 0;
-                    if (RNGMODE == RNG_MT19937_64) {
-                        // seed(seed + pixel_id); the jitter cursor starts at draw 0, the path cursor after the
-                        // 2*spp draws RectangleSampler3D.samples(spp) consumes up front (pinhole.pyx:183)
-                        jit.mt.seed(a.seed + (unsigned long long)pixel_id);
-                        for (int i = 0; i < RSB_MT_NN; ++i) rng.mt.w(i) = jit.mt.w(i);
-                        rng.mt.mti = RSB_MT_NN;
-                        for (int i = 0; i < 2 * spp; ++i) (void)rng.mt.next_u64();
-                    }
-                }
-            }
-            if (!exhausted) {
-                if (RNGMODE == RNG_PHILOX) {
-                    rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)s);
-                }
-                double u1, u2;
-                if (RNGMODE == RNG_MT19937_64) { u1 = jit.uniform(); u2 = jit.uniform(); }
-                else { u1 = rng.uniform(); u2 = rng.uniform(); }
-                V3 o, d;
-                pinhole_ray(a.cam, px, py, u1, u2, &o, &d, &weight);
-                path_begin(ps, log, o, d);
-                have_path = true;
-                my_paths += 1;
-            }
-        }
-        // ---- one segment --------------------------------------------------------------------------
-        int result = PATH_CONTINUE;
-        bool ended = false;
-        if (have_path) {
-            my_hits += 1;
-            result = path_step(sc, sp, a.cfg, ps, rng, stack, log, stats);
-            ended = (result != PATH_CONTINUE);
-        }
-        // ---- fold finished paths into their pixel's statistics, warp-cooperatively (lane = bin) -------
-        __syncwarp();
-        unsigned ended_mask = __ballot_sync(RSB_FULL_MASK, ended);
-        while (ended_mask) {
-            int src = __ffs(ended_mask) - 1;
-            ended_mask &= ended_mask - 1;
-            int e_n = __shfl_sync(RSB_FULL_MASK, log.n, src);
-            int e_res = __shfl_sync(RSB_FULL_MASK, result, src);
-            long long e_row = __shfl_sync(RSB_FULL_MASK, frame_row, src);
-            int e_s = __shfl_sync(RSB_FULL_MASK, s, src);
-            double e_w = __shfl_sync(RSB_FULL_MASK, weight, src);
-            PathLog elog;
-            elog.base = a.log_pool + warp_tid0 + src;
-            elog.stride = T;
-            elog.n = e_n;
-            elog.capacity = a.log_capacity;
-            elog.overflow = 0;
-            double* m = a.mean + e_row * bins;
-            double* v = a.variance + e_row * bins;
-            for (int b = lane; b < bins; b += 32) {
-                double x = 0.0;
-                if (e_res == PATH_EMITTED) x = replay_bin(elog, sp, b);
-                x = x * e_w;                    // spectrum.mul_scalar(projection_weight), observer.pyx:408
-                x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
-                welford_add(x, m + b, v + b, e_s);
-            }
+    unsigned long long rays = 0, paths = 0;
+    for (unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        int slot = a.st.ended[(size_t)par * a.n_slots + k];
+        int status = a.st.status[slot];
+        int s = a.st.sample[slot];
+        double w = a.st.weight[slot];
+        PathLog log;
+        log.base = a.st.log + (size_t)slot * a.log_capacity;
+        log.stride = 1;
+        log.capacity = a.log_capacity;
+        log.n = a.st.log_n[slot];
+        log.overflow = 0;
+        size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * bins;
+        double* m = a.mean + row;
+        double* v = a.variance + row;
+        for (int b = lane; b < bins; b += 32) {
+            double x = 0.0;
+            if (status == SLOT_ENDED_EMIT) x = replay_bin(log, sp, b);
+            x = x * w;                      // spectrum.mul_scalar(projection_weight), observer.pyx:408
+            x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
+            welford_add(x, m + b, v + b, s);
         }
         __syncwarp();
-        if (ended) {
-            my_rays += ps.rays;
-            s += 1;
-            have_path = false;
+        if (lane == 0) {
+            rays += a.st.rays[slot];
+            paths += 1;
+            a.st.sample[slot] = s + 1;
+            wf_regenerate<RNGMODE>(a, slot);
         }
-        if (__all_sync(RSB_FULL_MASK, exhausted && !have_path)) break;
+        __syncwarp();
     }
-    if (log.overflow) atomicExch(a.overflow_flag, 1);
-    // ray counter (observer.pyx:414) + roofline counters
-    unsigned long long r = warp_sum(my_rays);
-    unsigned long long p = warp_sum(my_paths);
-    unsigned long long h = warp_sum(my_hits);
-    if (lane == 0) {
-        atomicAdd(a.ray_count, r);
-        if (COUNT) { atomicAdd(&a.counters->paths, p); atomicAdd(&a.counters->rays, h); }
+    if (lane == 0 && rays) {
+        atomicAdd(a.ray_count, rays);
+        if (COUNT) atomicAdd(&a.counters->paths, paths);
     }
-    if (COUNT) flush_stats(stats, a.counters);
 }
 
 // StatsArray3D.combine_samples over the listed pixels of a slice (statsarray.pyx:780-857, power.pyx:424-437)

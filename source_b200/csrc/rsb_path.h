@@ -191,27 +191,34 @@ RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
     log.n = 0;
 }
 
-// One segment of the Ray.trace recursion (raysect/optical/ray.pyx:338-401): roulette, World.hit,
-// material.evaluate_surface up to the point where it would call daughter.trace(), volumes.
+// One segment of the Ray.trace recursion (raysect/optical/ray.pyx:338-401) in two stages, which the
+// wavefront kernels run as separate launches and the serial harness back to back:
+//   path_trace  roulette + World.hit                         (ray.pyx:380-393)
+//   path_shade  material.evaluate_surface up to the point where it would call daughter.trace(),
+//               then _sample_volumes and the roulette normalisation (ray.pyx:395-401)
 // PATH_CONTINUE: ps holds the daughter ray.  PATH_EMITTED: the log now ends with a LOG_EMIT entry.
 // PATH_ZERO: the path's spectrum is identically zero.
 template <class Stats>
-RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, Rng& rng,
-                     KdStackEntry* stack, PathLog& log, Stats& stats) {
+RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps, Rng& rng, KdStackEntry* stack,
+                      HitRec* rec, double* normalisation, Stats& stats) {
+    // -- Russian roulette (ray.pyx:380-388)
+    if (ps.depth < cfg.extinction_min_depth) {
+        *normalisation = 1.0;
+    } else {
+        if (ps.depth >= cfg.max_depth || rng.probability(cfg.extinction_prob)) return PATH_ZERO;
+        *normalisation = 1 / (1 - cfg.extinction_prob);
+    }
+    // -- closest hit (ray.pyx:391-393)
+    if (!world_hit(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
+    return PATH_CONTINUE;
+}
+
+template <class Stats>
+RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, const HitRec& rec,
+                      double normalisation, Rng& rng, KdStackEntry* stack, PathLog& log, Stats& stats) {
     const V3 o = ps.o, d = ps.d;
     const int depth = ps.depth;
     {
-        // -- Russian roulette (ray.pyx:380-388)
-        double normalisation;
-        if (depth < cfg.extinction_min_depth) {
-            normalisation = 1.0;
-        } else {
-            if (depth >= cfg.max_depth || rng.probability(cfg.extinction_prob)) return PATH_ZERO;
-            normalisation = 1 / (1 - cfg.extinction_prob);
-        }
-        // -- closest hit (ray.pyx:391-393)
-        HitRec rec;
-        if (!world_hit(sc, o, d, cfg.max_distance, stack, &rec, stats)) return PATH_ZERO;
         Isect is;
         world_hit_geometry(sc, o, d, rec, &is);
         const Prim& prim = sc.prims[rec.prim];
@@ -334,8 +341,17 @@ RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, 
     }
 }
 
-// A whole path (used by the serial harness; the render kernel steps segment by segment so that
-// a warp never waits for its longest path).
+template <class Stats>
+RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, Rng& rng,
+                     KdStackEntry* stack, PathLog& log, Stats& stats) {
+    HitRec rec;
+    double normalisation;
+    int r = path_trace(sc, cfg, ps, rng, stack, &rec, &normalisation, stats);
+    if (r != PATH_CONTINUE) return r;
+    return path_shade(sc, sp, cfg, ps, rec, normalisation, rng, stack, log, stats);
+}
+
+// A whole path (serial harness).
 template <class Stats>
 RSB_HD int trace_path(const Scene& sc, const Spectral& sp, const RayConfig& cfg, const V3& o, const V3& d, Rng& rng,
                       KdStackEntry* stack, PathLog& log, uint32_t* ray_count, Stats& stats) {

@@ -83,9 +83,8 @@ struct Mt19937_64 {
 
 struct Philox4x32 {
     uint32_t key[2];
-    uint32_t ctr[4];
-    uint32_t out[4];
-    int have;   // buffered 64-bit words available (0..2)
+    uint32_t ctr[3];    // (sub-stream, stream lo, stream hi); the block index is idx >> 1
+    uint32_t idx;       // 64-bit words drawn so far: the whole state besides the key and the stream id
 
     RSB_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
         uint64_t p = (uint64_t)a * (uint64_t)b;
@@ -96,15 +95,15 @@ struct Philox4x32 {
     RSB_HD void init(uint64_t seed, uint64_t stream, uint32_t sub) {
         key[0] = (uint32_t)seed;
         key[1] = (uint32_t)(seed >> 32);
-        ctr[0] = 0;
-        ctr[1] = sub;
-        ctr[2] = (uint32_t)stream;
-        ctr[3] = (uint32_t)(stream >> 32);
-        have = 0;
+        ctr[0] = sub;
+        ctr[1] = (uint32_t)stream;
+        ctr[2] = (uint32_t)(stream >> 32);
+        idx = 0;
     }
 
-    RSB_HD void block() {
-        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    // Philox4x32-10 (Salmon et al., SC'11) of counter (idx >> 1, ctr[0..2]); word idx & 1 of the block
+    RSB_HD uint64_t next_u64() {
+        uint32_t c0 = idx >> 1, c1 = ctr[0], c2 = ctr[1], c3 = ctr[2];
         uint32_t k0 = key[0], k1 = key[1];
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
@@ -117,15 +116,9 @@ struct Philox4x32 {
             k0 += 0x9E3779B9u;
             k1 += 0xBB67AE85u;
         }
-        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-        ctr[0] += 1;
-        have = 2;
-    }
-
-    RSB_HD uint64_t next_u64() {
-        if (have == 0) block();
-        --have;
-        return ((uint64_t)out[2 * have + 1] << 32) | (uint64_t)out[2 * have];
+        uint64_t w = (idx & 1u) ? (((uint64_t)c3 << 32) | (uint64_t)c2) : (((uint64_t)c1 << 32) | (uint64_t)c0);
+        idx += 1;
+        return w;
     }
 };
 
