@@ -533,6 +533,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int threads = 128;
     const int grid = (a.n_slots + threads - 1) / threads;
     const int fin_grid = std::max(1, std::min(grid, c->sm_count * 16));
+    const int regen_grid = std::max(1, std::min((grid + 3) / 4, c->sm_count * 8));
     if (smem_shade > 48 * 1024) {
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
@@ -550,6 +551,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
             k_wf_trace<RNGMODE, COUNT><<<grid, threads, smem_scene, st>>>(a);
             k_wf_shade<RNGMODE, COUNT><<<grid, threads, smem_shade, st>>>(a);
             k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, st>>>(a);
+            k_wf_regen<RNGMODE, COUNT><<<regen_grid, threads, 0, st>>>(a);
         }
         RSB_CUDA(cudaGetLastError());
         RSB_CUDA(cudaMemcpyAsync(h_idle, a.n_idle, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));

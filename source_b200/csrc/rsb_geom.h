@@ -409,37 +409,44 @@ RSB_HD bool kd_trace(const KdTree& tree, const V3& o, const V3& d, KdStackEntry*
     int node = 0;
     int sp = 0;
     for (;;) {
+        // "while-while" form: every lane of a warp first descends to its next leaf (cheap, uniform code),
+        // and only then are the leaves processed, so that the expensive item tests run with the warp
+        // converged instead of interleaved with other lanes' branch steps
         KdNode n = tree.nodes[node];
-        if (n.axis < 0) {
-            stats.leaf(n.leaf.item_count);
-            if (leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) { *hit_node = node; return true; }
-            if (sp == 0) return false;
-            --sp;
-            node = stack[sp].node;
-            min_range = max_range;
-            max_range = stack[sp].tmax;
-            continue;
+        while (n.axis >= 0) {
+            stats.branch();
+            double origin = v3_get(o, n.axis);
+            double direction = v3_get(d, n.axis);
+            int lower_id = node + 1;
+            int upper_id = n.upper;
+            if (direction == 0) {
+                node = (origin < n.split) ? lower_id : upper_id;
+            } else {
+                double plane_distance = (n.split - origin) / direction;
+                bool below_split = origin < n.split || (origin == n.split && direction < 0);
+                int near_id = below_split ? lower_id : upper_id;
+                int far_id = below_split ? upper_id : lower_id;
+                if (plane_distance > max_range || plane_distance <= 0) {
+                    node = near_id;
+                } else if (plane_distance < min_range) {
+                    node = far_id;
+                } else {
+                    stack[sp].node = far_id;
+                    stack[sp].tmax = max_range;
+                    ++sp;
+                    node = near_id;
+                    max_range = plane_distance;
+                }
+            }
+            n = tree.nodes[node];
         }
-        stats.branch();
-        double origin = v3_get(o, n.axis);
-        double direction = v3_get(d, n.axis);
-        int lower_id = node + 1;
-        int upper_id = n.upper;
-        if (direction == 0) {
-            node = (origin < n.split) ? lower_id : upper_id;
-            continue;
-        }
-        double plane_distance = (n.split - origin) / direction;
-        bool below_split = origin < n.split || (origin == n.split && direction < 0);
-        int near_id = below_split ? lower_id : upper_id;
-        int far_id = below_split ? upper_id : lower_id;
-        if (plane_distance > max_range || plane_distance <= 0) { node = near_id; continue; }
-        if (plane_distance < min_range) { node = far_id; continue; }
-        stack[sp].node = far_id;
-        stack[sp].tmax = max_range;
-        ++sp;
-        node = near_id;
-        max_range = plane_distance;
+        stats.leaf(n.leaf.item_count);
+        if (n.leaf.item_count > 0 && leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) { *hit_node = node; return true; }
+        if (sp == 0) return false;
+        --sp;
+        node = stack[sp].node;
+        min_range = max_range;
+        max_range = stack[sp].tmax;
     }
 }
 
@@ -852,46 +859,59 @@ struct WorldLeaf {
     HitRec* best;
     Stats* stats;
 
-    // _PrimitiveKDTree._trace_leaf (acceleration/kdtree.pyx:73-122): `<=` => last of equal-t items wins
+    // one candidate primitive that passed its AABB pre-test (BoundPrimitive.hit, boundprimitive.pyx:42-51)
+    RSB_HD void test(int id, double& distance, bool& found) {
+        const Prim& p = sc->prims[id];
+        if (p.type <= PRIM_CONE) {
+            V3 lo = xform_point(p.to_local, o);
+            V3 ld = xform_vector(p.to_local, d);
+            Crossing c[2];
+            if (analytic_crossings(p.type, p.params, lo, ld, max_distance, c) > 0 && c[0].t <= distance) {
+                distance = c[0].t;
+                best->t = c[0].t; best->prim = id; best->leaf = id; best->code = c[0].code; best->flip = 0;
+                best->mesh_node = -1;
+                found = true;
+            }
+        } else if (p.type == PRIM_MESH) {
+            V3 lo = xform_point(p.to_local, o);
+            V3 ld = xform_vector(p.to_local, d);
+            MeshHit mh;
+            if (mesh_trace(sc->meshes[p.mesh], lo, ld, max_distance, mesh_stack, &mh, *stats) && mh.t <= distance) {
+                distance = mh.t;
+                best->t = mh.t; best->prim = id; best->leaf = id; best->code = mh.tri; best->flip = 0;
+                best->mesh_node = mh.node;
+                best->u = mh.u; best->v = mh.v; best->w = mh.w;
+                found = true;
+            }
+        } else {
+            CsgEvent ev;
+            if (csg_first_hit(*sc, id, o, d, max_distance, &ev) && ev.t <= distance) {
+                distance = ev.t;
+                best->t = ev.t; best->prim = id; best->leaf = ev.leaf; best->code = ev.code;
+                best->flip = ev.flip | (ev.exiting << 1);
+                best->mesh_node = -1;
+                found = true;
+            }
+        }
+    }
+
+    // _PrimitiveKDTree._trace_leaf (acceleration/kdtree.pyx:73-122): `<=` => last of equal-t items wins.
+    // Two phases per chunk of items: the cheap AABB pre-tests first, collecting the survivors (in item
+    // order, which the tie rule depends on), then the primitive tests -- so lanes whose items were all
+    // rejected do not sit through other lanes' quadratic solves one item at a time.
     RSB_HD bool operator()(int offset, int count, double max_range) {
         double distance = max_distance < max_range ? max_distance : max_range;
         bool found = false;
-        for (int i = 0; i < count; ++i) {
-            int id = sc->world.items[offset + i];
-            const Prim& p = sc->prims[id];
-            stats->prim_test();
-            if (!box_hit(p.bbox, o, d)) continue;   // BoundPrimitive.hit, boundprimitive.pyx:42-51
-            if (p.type <= PRIM_CONE) {
-                V3 lo = xform_point(p.to_local, o);
-                V3 ld = xform_vector(p.to_local, d);
-                Crossing c[2];
-                if (analytic_crossings(p.type, p.params, lo, ld, max_distance, c) > 0 && c[0].t <= distance) {
-                    distance = c[0].t;
-                    best->t = c[0].t; best->prim = id; best->leaf = id; best->code = c[0].code; best->flip = 0;
-                    best->mesh_node = -1;
-                    found = true;
-                }
-            } else if (p.type == PRIM_MESH) {
-                V3 lo = xform_point(p.to_local, o);
-                V3 ld = xform_vector(p.to_local, d);
-                MeshHit mh;
-                if (mesh_trace(sc->meshes[p.mesh], lo, ld, max_distance, mesh_stack, &mh, *stats) && mh.t <= distance) {
-                    distance = mh.t;
-                    best->t = mh.t; best->prim = id; best->leaf = id; best->code = mh.tri; best->flip = 0;
-                    best->mesh_node = mh.node;
-                    best->u = mh.u; best->v = mh.v; best->w = mh.w;
-                    found = true;
-                }
-            } else {
-                CsgEvent ev;
-                if (csg_first_hit(*sc, id, o, d, max_distance, &ev) && ev.t <= distance) {
-                    distance = ev.t;
-                    best->t = ev.t; best->prim = id; best->leaf = ev.leaf; best->code = ev.code;
-                    best->flip = ev.flip | (ev.exiting << 1);
-                    best->mesh_node = -1;
-                    found = true;
-                }
+        for (int base = 0; base < count; base += 4) {
+            int cand[4];
+            int nc = 0;
+            int end = count - base < 4 ? count - base : 4;
+            for (int i = 0; i < end; ++i) {
+                int id = sc->world.items[offset + base + i];
+                stats->prim_test();
+                if (box_hit(sc->prims[id].bbox, o, d)) cand[nc++] = id;
             }
+            for (int i = 0; i < nc; ++i) test(cand[i], distance, found);
         }
         return found;
     }

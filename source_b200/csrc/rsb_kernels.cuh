@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs
 }
 
 // 1 warp = 1 ended path: the reference's unwind (per-bin multiplies), projection weight, sensitivity and
-// PixelProcessor.add_sample (Welford) for bins lane, lane+32, ...; then lane 0 starts the slot's next sample.
+// PixelProcessor.add_sample (Welford) for bins lane, lane+32, ...
 template <int RNGMODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -503,7 +503,6 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     if (blockIdx.x == 0 && threadIdx.x == 0) a.st.n_ended[par ^ 1] = 0;   // list of the next wave
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int bins = sp.bins;
-    unsigned long long rays = 0, paths = 0;
     for (unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
         int slot = a.st.ended[(size_t)par * a.n_slots + k];
         int status = a.st.status[slot];
@@ -525,16 +524,28 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
             welford_add(x, m + b, v + b, s);
         }
-        __syncwarp();
-        if (lane == 0) {
-            rays += a.st.rays[slot];
-            paths += 1;
-            a.st.sample[slot] = s + 1;
-            wf_regenerate<RNGMODE>(a, slot);
-        }
-        __syncwarp();
     }
-    if (lane == 0 && rays) {
+}
+
+// 1 thread = 1 ended slot: the ray counter of the finished path (observer.pyx:414), then the slot's next
+// sample or next pixel.  Separate from the accumulate kernel so that ray generation runs converged.
+template <int RNGMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_wf_regen(const __grid_constant__ WfArgs a) {
+    const int par = a.wave & 1;
+    const unsigned int n = a.st.n_ended[par];
+    const unsigned int stride = gridDim.x * blockDim.x;
+    unsigned long long rays = 0, paths = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int slot = a.st.ended[(size_t)par * a.n_slots + k];
+        rays += a.st.rays[slot];
+        paths += 1;
+        a.st.sample[slot] = a.st.sample[slot] + 1;
+        wf_regenerate<RNGMODE>(a, slot);
+    }
+    __syncwarp();
+    rays = warp_sum(rays);
+    paths = warp_sum(paths);
+    if ((threadIdx.x & 31) == 0 && paths) {
         atomicAdd(a.ray_count, rays);
         if (COUNT) atomicAdd(&a.counters->paths, paths);
     }
