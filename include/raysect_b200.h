@@ -139,15 +139,17 @@ typedef struct RsbRngDesc {
 /* traversal counters behind the algorithmic-bytes roofline model */
 typedef struct RsbCounters {
     uint64_t rays;        /* World.hit queries */
-    uint64_t branches;    /* kd branch nodes visited (world + mesh trees) */
-    uint64_t leaves;      /* kd leaves visited */
-    uint64_t items;       /* leaf item ids read */
+    uint64_t branches;    /* kd branch nodes visited by World.hit (world + mesh trees) */
+    uint64_t leaves;      /* kd leaves visited by World.hit */
+    uint64_t items;       /* leaf item ids read by World.hit */
     uint64_t prim_tests;  /* BoundPrimitive.hit calls on world-level primitives */
-    uint64_t tri_tests;   /* _hit_triangle calls */
+    uint64_t tri_tests;   /* _hit_triangle calls (World.hit and mesh contains rays) */
     uint64_t paths;       /* primary rays traced by rsb_render */
     uint64_t contains;    /* World.contains queries */
     uint64_t table_reads; /* per-bin spectral table rows consumed (surface + volume + emission interactions) */
-    uint64_t reserved[3];
+    uint64_t contains_nodes;      /* kd nodes visited by World.contains point location (+ mesh contains rays) */
+    uint64_t contains_items;      /* leaf item ids read by World.contains */
+    uint64_t contains_prim_tests; /* BoundPrimitive.contains calls */
 } RsbCounters;
 
 const char* rsb_last_error(void);
@@ -241,6 +243,20 @@ int rsb_frame_combine_dev(uint64_t ctx, void* cuda_stream, int64_t n_pixels_tota
                           int32_t slice_offset, int32_t slice_bins, int64_t n_pixels, const int32_t* pixels_dev,
                           int32_t ny, const double* mean_dev, const double* variance_dev, int32_t samples,
                           double* frame_mean_dev, double* frame_variance_dev, int32_t* frame_samples_dev);
+
+/* shape of the last rsb_render / rsb_render_dev call */
+typedef struct RsbRenderStats {
+    int64_t slots;            /* pixel streams in flight (wavefront width) */
+    int64_t waves;            /* trace -> shade -> finalize -> regen rounds */
+    int64_t launches;         /* kernels launched */
+    int64_t trace_launches;   /* launches of the dominant kernel (k_wf_trace) */
+    double trace_ms;          /* summed device time of k_wf_trace (CUDA events on the launch stream); 0 unless
+                                 the call was made with RSB_RENDER_TIME_TRACE */
+} RsbRenderStats;
+int rsb_render_stats(uint64_t ctx, RsbRenderStats* out);
+
+#define RSB_RENDER_COUNT 1        /* `count` argument of rsb_render_dev: collect traversal counters */
+#define RSB_RENDER_TIME_TRACE 2   /* bracket every k_wf_trace launch with CUDA events */
 
 /* counters of the last *_dev / host call made with count != 0 (host calls always count) */
 int rsb_counters(uint64_t ctx, RsbCounters* out);

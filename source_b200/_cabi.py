@@ -126,11 +126,21 @@ class RsbRngDesc(C.Structure):
 class RsbCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("rays", "branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "contains",
-                 "table_reads")] + [("reserved", C.c_uint64 * 3)]
+                 "table_reads", "contains_nodes", "contains_items", "contains_prim_tests")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
+
+class RsbRenderStats(C.Structure):
+    _fields_ = [("slots", C.c_int64), ("waves", C.c_int64), ("launches", C.c_int64), ("trace_launches", C.c_int64),
+                ("trace_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+RENDER_COUNT, RENDER_TIME_TRACE = 1, 2
 
 # every symbol include/raysect_b200.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
@@ -163,6 +173,7 @@ SIGNATURES = {
                                  C.c_int32]),
     "rsb_frame_combine_dev": (C.c_int, [_U64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _VP,
                                         C.c_int32, _VP, _VP, C.c_int32, _VP, _VP, _VP]),
+    "rsb_render_stats": (C.c_int, [_U64, C.POINTER(RsbRenderStats)]),
     "rsb_counters": (C.c_int, [_U64, C.POINTER(RsbCounters)]),
     "rsb_last_kernel_ms": (C.c_int, [_U64, C.POINTER(C.c_float)]),
 }

@@ -52,7 +52,8 @@ struct Context {
     unsigned char* d_slots = nullptr;   // wavefront slot state (rsb_kernels.cuh: WfSlots)
     size_t slot_bytes = 0;
     unsigned int* h_idle = nullptr;     // pinned
-    long long last_waves = 0;
+    RsbRenderStats render_stats{};
+    std::vector<cudaEvent_t> event_pool;
     Material* d_mats = nullptr;
     double* d_tables = nullptr;
     size_t mats_cap = 0, tables_cap = 0;
@@ -115,6 +116,9 @@ int read_counters(Context* c, cudaStream_t st) {
     c->last_counters.paths = h.paths;
     c->last_counters.contains = h.contains;
     c->last_counters.table_reads = h.table_reads;
+    c->last_counters.contains_nodes = h.contains_nodes;
+    c->last_counters.contains_items = h.contains_items;
+    c->last_counters.contains_prim_tests = h.contains_prim_tests;
     return RSB_OK;
 }
 
@@ -228,6 +232,7 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_scalars);
     cudaFree(c->d_slots);
     cudaFreeHost(c->h_idle);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_mats);
     cudaFree(c->d_tables);
     cudaEventDestroy(c->ev0);
@@ -523,17 +528,20 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, WfSlots* 
     st->mti = c.take<int32_t>(2 * P);
     st->ended = c.take<int32_t>(2 * P);
     st->n_ended = c.take<unsigned int>(2);
+    st->hit_list = c.take<int32_t>(4 * P);
+    st->n_hit = c.take<unsigned int>(4);
     st->mt = mt ? c.take<unsigned long long>(P * 2 * RSB_MT_NN) : nullptr;
     st->log = c.take<LogEntry>(P * cap);
     return (c.off + 255) & ~(size_t)255;
 }
 
 template <int RNGMODE, bool COUNT>
-int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st) {
+int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st, bool time_trace) {
     const int threads = 128;
     const int grid = (a.n_slots + threads - 1) / threads;
     const int fin_grid = std::max(1, std::min(grid, c->sm_count * 16));
     const int regen_grid = std::max(1, std::min((grid + 3) / 4, c->sm_count * 8));
+    const int shade_grid = grid;
     if (smem_shade > 48 * 1024) {
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
@@ -545,20 +553,42 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     RSB_CUDA(cudaGetLastError());
     unsigned int* h_idle = c->h_idle;
     const int kBatch = 32;
+    RsbRenderStats& rs = c->render_stats;
+    rs = RsbRenderStats{};
+    rs.slots = a.n_slots;
+    rs.launches = 1;
+    if (time_trace) {
+        while (c->event_pool.size() < 2 * kBatch) {
+            cudaEvent_t e;
+            RSB_CUDA(cudaEventCreate(&e));
+            c->event_pool.push_back(e);
+        }
+    }
     for (long long wave = 0;;) {
         for (int b = 0; b < kBatch; ++b, ++wave) {
             a.wave = (int32_t)(wave & 0x7fffffff);
+            if (time_trace) RSB_CUDA(cudaEventRecord(c->event_pool[2 * b], st));
             k_wf_trace<RNGMODE, COUNT><<<grid, threads, smem_scene, st>>>(a);
-            k_wf_shade<RNGMODE, COUNT><<<grid, threads, smem_shade, st>>>(a);
+            if (time_trace) RSB_CUDA(cudaEventRecord(c->event_pool[2 * b + 1], st));
+            k_wf_shade<RNGMODE, COUNT><<<shade_grid, threads, smem_shade, st>>>(a);
             k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, st>>>(a);
             k_wf_regen<RNGMODE, COUNT><<<regen_grid, threads, 0, st>>>(a);
         }
         RSB_CUDA(cudaGetLastError());
         RSB_CUDA(cudaMemcpyAsync(h_idle, a.n_idle, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         RSB_CUDA(cudaStreamSynchronize(st));
+        rs.waves += kBatch;
+        rs.launches += 4 * kBatch;
+        rs.trace_launches += kBatch;
+        if (time_trace) {
+            for (int b = 0; b < kBatch; ++b) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, c->event_pool[2 * b], c->event_pool[2 * b + 1]);
+                rs.trace_ms += ms;
+            }
+        }
         if (*h_idle >= (unsigned int)a.n_slots) break;
     }
-    c->last_waves = 0;
     return RSB_OK;
 }
 
@@ -680,12 +710,15 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, &a.st);
     RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
     RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
-    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+    RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
+    if (count & RSB_RENDER_COUNT) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     int rc;
-    if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st)
-                       : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st);
-    else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st)
-                    : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st);
+    const bool time_trace = (count & RSB_RENDER_TIME_TRACE) != 0;
+    count &= RSB_RENDER_COUNT;
+    if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+                       : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
+    else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+                    : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
     if (rc) return rc;
     {
         int32_t overflow = 0;
@@ -756,6 +789,13 @@ int rsb_frame_combine_dev(uint64_t ctx, void* cuda_stream, int64_t n_pixels_tota
     k_frame_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, ny, frame_bins, slice_offset, slice_bins, mean_dev,
                                                                  variance_dev, samples, frame_mean_dev, frame_variance_dev, frame_samples_dev);
     RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+int rsb_render_stats(uint64_t ctx, RsbRenderStats* out) {
+    Context* c = as_ctx(ctx);
+    if (!c || !out) return fail(RSB_ERR_ARG, "null argument");
+    *out = c->render_stats;
     return RSB_OK;
 }
 

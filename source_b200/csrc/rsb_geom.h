@@ -402,52 +402,80 @@ RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
 // min_range = plane_distance, which equals the max_range of the last leaf visited (front-to-back
 // order), so only (node, max_range) is stacked.
 // ---------------------------------------------------------------------------------------------
+struct KdCursor {
+    double min_range, max_range;
+    int32_t node, sp;
+};
+
+enum KdResult : int32_t { KD_MISS = 0, KD_HIT = 1, KD_MORE = 2 };
+
+// KDTree3DCore._trace (kdtree3d.pyx:589-607): clip the ray against the tree bounds
+RSB_HD bool kd_begin(const KdTree& tree, const V3& o, const V3& d, KdCursor& c) {
+    c.node = 0;
+    c.sp = 0;
+    return box_intersect(tree.bounds, o, d, &c.min_range, &c.max_range);
+}
+
+// One unit of traversal: descend from the cursor to the next leaf in front-to-back order
+// (_trace_branch, kdtree3d.pyx:626-700) and run the leaf test (_trace_leaf).  "While-while" form: every
+// lane of a warp first reaches its next leaf (cheap, uniform code) and only then are leaves processed,
+// so the expensive item tests run with the warp converged.  KD_MORE: no hit in that leaf, the cursor
+// points at the next subtree; callers loop (or interleave other rays' units, see k_wf_trace).
+template <class LeafFn, class Stats>
+RSB_HD int kd_advance(const KdTree& tree, const V3& o, const V3& d, KdStackEntry* stack, KdCursor& c, LeafFn& leaf,
+                      Stats& stats, int* hit_node) {
+    int node = c.node, sp = c.sp;
+    double min_range = c.min_range, max_range = c.max_range;
+    KdNode n = tree.nodes[node];
+    while (n.axis >= 0) {
+        stats.branch();
+        double origin = v3_get(o, n.axis);
+        double direction = v3_get(d, n.axis);
+        int lower_id = node + 1;
+        int upper_id = n.upper;
+        if (direction == 0) {
+            node = (origin < n.split) ? lower_id : upper_id;
+        } else {
+            double plane_distance = (n.split - origin) / direction;
+            bool below_split = origin < n.split || (origin == n.split && direction < 0);
+            int near_id = below_split ? lower_id : upper_id;
+            int far_id = below_split ? upper_id : lower_id;
+            if (plane_distance > max_range || plane_distance <= 0) {
+                node = near_id;
+            } else if (plane_distance < min_range) {
+                node = far_id;
+            } else {
+                stack[sp].node = far_id;
+                stack[sp].tmax = max_range;
+                ++sp;
+                node = near_id;
+                max_range = plane_distance;
+            }
+        }
+        n = tree.nodes[node];
+    }
+    stats.leaf(n.leaf.item_count);
+    if (n.leaf.item_count > 0 && leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) {
+        *hit_node = node;
+        return KD_HIT;
+    }
+    if (sp == 0) return KD_MISS;
+    --sp;
+    // the far child resumes with min_range = the plane distance = max_range of the leaf just left
+    c.node = stack[sp].node;
+    c.min_range = max_range;
+    c.max_range = stack[sp].tmax;
+    c.sp = sp;
+    return KD_MORE;
+}
+
 template <class LeafFn, class Stats>
 RSB_HD bool kd_trace(const KdTree& tree, const V3& o, const V3& d, KdStackEntry* stack, LeafFn& leaf, Stats& stats, int* hit_node) {
-    double min_range, max_range;
-    if (!box_intersect(tree.bounds, o, d, &min_range, &max_range)) return false;
-    int node = 0;
-    int sp = 0;
-    for (;;) {
-        // "while-while" form: every lane of a warp first descends to its next leaf (cheap, uniform code),
-        // and only then are the leaves processed, so that the expensive item tests run with the warp
-        // converged instead of interleaved with other lanes' branch steps
-        KdNode n = tree.nodes[node];
-        while (n.axis >= 0) {
-            stats.branch();
-            double origin = v3_get(o, n.axis);
-            double direction = v3_get(d, n.axis);
-            int lower_id = node + 1;
-            int upper_id = n.upper;
-            if (direction == 0) {
-                node = (origin < n.split) ? lower_id : upper_id;
-            } else {
-                double plane_distance = (n.split - origin) / direction;
-                bool below_split = origin < n.split || (origin == n.split && direction < 0);
-                int near_id = below_split ? lower_id : upper_id;
-                int far_id = below_split ? upper_id : lower_id;
-                if (plane_distance > max_range || plane_distance <= 0) {
-                    node = near_id;
-                } else if (plane_distance < min_range) {
-                    node = far_id;
-                } else {
-                    stack[sp].node = far_id;
-                    stack[sp].tmax = max_range;
-                    ++sp;
-                    node = near_id;
-                    max_range = plane_distance;
-                }
-            }
-            n = tree.nodes[node];
-        }
-        stats.leaf(n.leaf.item_count);
-        if (n.leaf.item_count > 0 && leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) { *hit_node = node; return true; }
-        if (sp == 0) return false;
-        --sp;
-        node = stack[sp].node;
-        min_range = max_range;
-        max_range = stack[sp].tmax;
-    }
+    KdCursor c;
+    if (!kd_begin(tree, o, d, c)) return false;
+    int r;
+    do { r = kd_advance(tree, o, d, stack, c, leaf, stats, hit_node); } while (r == KD_MORE);
+    return r == KD_HIT;
 }
 
 // raysect/core/math/spatial/kdtree3d.pyx:736-792 (_items_containing*): descend to the one leaf

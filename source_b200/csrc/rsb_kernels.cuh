@@ -20,7 +20,8 @@ namespace rsb {
 #define RSB_RENDER_THREADS 128
 
 struct DevCounters {   // mirrors RsbCounters
-    unsigned long long rays, branches, leaves, items, prim_tests, tri_tests, paths, contains, table_reads, reserved[3];
+    unsigned long long rays, branches, leaves, items, prim_tests, tri_tests, paths, contains, table_reads,
+        contains_nodes, contains_items, contains_prim_tests;
 };
 
 template <bool COUNT>
@@ -34,12 +35,22 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
-__device__ __forceinline__ void flush_stats(const NoStats&, DevCounters*) {}
-__device__ __forceinline__ void flush_stats(const CountStats& s, DevCounters* c) {
+__device__ __forceinline__ void flush_stats(const NoStats&, DevCounters*, bool = false) {}
+// shade: the traversal counters of this kernel belong to World.contains queries, not World.hit
+__device__ __forceinline__ void flush_stats(const CountStats& s, DevCounters* c, bool shade = false) {
     // all lanes of the warp reach here together (kernel epilogue)
     unsigned long long b = warp_sum(s.branches), l = warp_sum(s.leaves), i = warp_sum(s.items),
                        p = warp_sum(s.prim_tests), t = warp_sum(s.tri_tests), cq = warp_sum(s.contains),
                        tb = warp_sum(s.tables);
+    if ((threadIdx.x & 31) == 0 && shade) {
+        atomicAdd(&c->contains, cq);
+        atomicAdd(&c->table_reads, tb);
+        atomicAdd(&c->contains_nodes, b + l);
+        atomicAdd(&c->contains_items, i);
+        atomicAdd(&c->contains_prim_tests, p);
+        atomicAdd(&c->tri_tests, t);
+        return;
+    }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&c->contains, cq);
         atomicAdd(&c->table_reads, tb);
@@ -252,6 +263,8 @@ struct WfSlots {
     LogEntry* log;          // [P][log_capacity]
     int32_t* ended;         // [2][P] compacted lists of ended slots (double buffered by wave parity)
     unsigned int* n_ended;  // [2]
+    int32_t* hit_list;      // [4][P] slots with a hit, by material type of the hit primitive
+    unsigned int* n_hit;    // [4]
 };
 
 struct WfArgs {
@@ -380,20 +393,24 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
     wf_regenerate<RNGMODE>(a, slot);
 }
 
+// 1 thread = 1 slot.  (A persistent-lane variant, where a lane picks up its next slot as soon as its ray
+// finishes, was measured SLOWER on the Cornell scene -- 208 vs 129 us per 262k-ray wave, 9.1 vs 10.0 active
+// lanes per instruction: iteration counts per ray vary little here, and the refill path diverges.)
 template <int RNGMODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     stage_scene(sc, smem, a.n_items, a.staged);
     typename StatsSel<COUNT>::type stats;
+    const int P = a.n_slots;
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = slot < a.n_slots && a.st.status[slot] == SLOT_ALIVE;
+    bool active = slot < P && a.st.status[slot] == SLOT_ALIVE;
     unsigned long long hits = 0;
     if (active) {
-        const size_t P = (size_t)a.n_slots;
+        const size_t PP = (size_t)P;
         PathState ps;
-        ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
-        ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
+        ps.o = v3(a.st.ray[0 * PP + slot], a.st.ray[1 * PP + slot], a.st.ray[2 * PP + slot]);
+        ps.d = v3(a.st.ray[3 * PP + slot], a.st.ray[4 * PP + slot], a.st.ray[5 * PP + slot]);
         ps.depth = a.st.depth[slot];
         ps.rays = 0;
         Rng rng;
@@ -410,6 +427,9 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
             a.st.norm[slot] = normalisation;
             a.st.status[slot] = SLOT_HIT;
+            int mt = a.sp.mats[sc.prims[rec.prim].material].type;
+            unsigned int k = atomicAdd(&a.st.n_hit[mt], 1u);
+            a.st.hit_list[(size_t)mt * PP + k] = slot;
         } else {
             a.st.status[slot] = SLOT_ENDED_ZERO;
             wf_push_ended(a, slot);
@@ -423,25 +443,17 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs
     }
 }
 
-template <int RNGMODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    Scene sc = a.sc;
-    Spectral sp = a.sp;
-    stage_scene(sc, smem, a.n_items, a.staged);
-    if (a.tables_staged) {
-        StageLayout l = stage_layout(a.staged ? a.sc.world.n_nodes : 0, a.staged ? a.n_items : 0, a.staged ? a.sc.n_prims : 0);
-        unsigned char* base = smem + l.total;
-        int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
-        copy16(base, a.sp.mats, mat_bytes);
-        __syncthreads();
-        sp.mats = reinterpret_cast<const Material*>(base);
-    }
-    typename StatsSel<COUNT>::type stats;
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = slot < a.n_slots && a.st.status[slot] == SLOT_HIT;
-    if (active) {
-        const size_t P = (size_t)a.n_slots;
+// 1 thread = 1 hit slot.  The trace kernel compacts hit slots into one list per material family; every CTA
+// walks the lists in turn (Lambert, dielectric, emitter, absorber), so a warp executes ONE BSDF at a time
+// while the whole GPU stays busy (separate launches per family left the smaller lists under-occupied).
+template <int RNGMODE, bool COUNT, int MAT>
+__device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, const Spectral& sp, KdStackEntry* stack,
+                                              typename StatsSel<COUNT>::type& stats) {
+    const size_t P = (size_t)a.n_slots;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int n = a.st.n_hit[MAT];
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        int slot = a.st.hit_list[(size_t)MAT * P + k];
         PathState ps;
         ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
         ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
@@ -463,8 +475,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs
         log.capacity = a.log_capacity;
         log.n = a.st.log_n[slot];
         log.overflow = 0;
-        KdStackEntry stack[RSB_KD_STACK];
-        int r = path_shade(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
+        int r = path_shade<MAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
         wf_store_rng<RNGMODE>(a, slot, rng);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
@@ -479,9 +490,31 @@ __global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs
             wf_push_ended(a, slot);
         }
     }
+}
+
+template <int RNGMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    Scene sc = a.sc;
+    Spectral sp = a.sp;
+    stage_scene(sc, smem, a.n_items, a.staged);
+    if (a.tables_staged) {
+        StageLayout l = stage_layout(a.staged ? a.sc.world.n_nodes : 0, a.staged ? a.n_items : 0, a.staged ? a.sc.n_prims : 0);
+        unsigned char* base = smem + l.total;
+        int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
+        copy16(base, a.sp.mats, mat_bytes);
+        __syncthreads();
+        sp.mats = reinterpret_cast<const Material*>(base);
+    }
+    typename StatsSel<COUNT>::type stats;
+    KdStackEntry stack[RSB_KD_STACK];
+    wf_shade_list<RNGMODE, COUNT, MAT_LAMBERT>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_DIELECTRIC>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_EMITTER>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_ABSORBER>(a, sc, sp, stack, stats);
     if (COUNT) {
         __syncwarp();
-        flush_stats(stats, a.counters);
+        flush_stats(stats, a.counters, true);
     }
 }
 
@@ -534,6 +567,7 @@ __global__ void __launch_bounds__(128) k_wf_regen(const __grid_constant__ WfArgs
     const int par = a.wave & 1;
     const unsigned int n = a.st.n_ended[par];
     const unsigned int stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x < 4) a.st.n_hit[threadIdx.x] = 0;   // consumed by this wave's shade kernels
     unsigned long long rays = 0, paths = 0;
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         int slot = a.st.ended[(size_t)par * a.n_slots + k];

@@ -213,7 +213,10 @@ RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps
     return PATH_CONTINUE;
 }
 
-template <class Stats>
+// MATSEL: -1 = dispatch on the material at run time (serial harness); otherwise the caller guarantees the
+// hit primitive's material type (the wavefront shade kernels run one launch per material family, so the
+// other families' code is compiled out and the warp stays converged).
+template <int MATSEL, class Stats>
 RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, const HitRec& rec,
                       double normalisation, Rng& rng, KdStackEntry* stack, PathLog& log, Stats& stats) {
     const V3 o = ps.o, d = ps.d;
@@ -223,6 +226,7 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
         world_hit_geometry(sc, o, d, rec, &is);
         const Prim& prim = sc.prims[rec.prim];
         const Material& mat = sp.mats[prim.material];
+        const int mtype = MATSEL >= 0 ? MATSEL : mat.type;
         const double* w2p = prim.to_local;
         const double* p2w = prim.to_root;
 
@@ -231,15 +235,15 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
         V3 w_hit = xform_point(p2w, is.hit);
         log_volumes(sc, sp, o, w_hit, stack, log, stats);
 
-        if (mat.type == MAT_EMITTER) {
+        if (mtype == MAT_EMITTER) {
             log.push(LOG_EMIT, mat.table, mat.scale);
             stats.table_read();
             return PATH_EMITTED;
         }
-        if (mat.type == MAT_ABSORBER) return PATH_ZERO;
+        if (mtype == MAT_ABSORBER) return PATH_ZERO;
 
         V3 next_o, next_d;
-        if (mat.type == MAT_LAMBERT) {
+        if (mtype == MAT_LAMBERT) {
             // ContinuousBSDF.evaluate_surface (material.pyx:291-361) + Lambert (lambert.pyx:71-105)
             V3 normal = is.normal;
             V3 w_reflection_origin;
@@ -348,7 +352,7 @@ RSB_HD int path_step(const Scene& sc, const Spectral& sp, const RayConfig& cfg, 
     double normalisation;
     int r = path_trace(sc, cfg, ps, rng, stack, &rec, &normalisation, stats);
     if (r != PATH_CONTINUE) return r;
-    return path_shade(sc, sp, cfg, ps, rec, normalisation, rng, stack, log, stats);
+    return path_shade<-1>(sc, sp, cfg, ps, rec, normalisation, rng, stack, log, stats);
 }
 
 // A whole path (serial harness).

@@ -59,9 +59,9 @@ class FrameRenderer:
         self.d2h_bytes = 0
         self._reduce = backend_reduce
 
-    def _render(self, seed, pixels, count=False):
+    def _render(self, seed, pixels, count=False, time_trace=False):
         return self.accel.render_device(self.cam, self.cfg, self.spectral, self.camera.rng_mode, seed, pixels,
-                                        self.stats[0], self.stats[1], count=count)[2]
+                                        self.stats[0], self.stats[1], count=count, time_trace=time_trace)[2]
 
     def _assemble(self):
         """single reduce(sum) of the (mean, variance) frame to rank 0"""
@@ -75,13 +75,11 @@ class FrameRenderer:
         dist.reduce(self.stats, dst=0, op=dist.ReduceOp.SUM)
         return None
 
-    def step_device(self, seed, kernel_events=None):
-        """One frame with everything resident in HBM.  Returns this rank's ray counter (device tensor)."""
-        if kernel_events:
-            kernel_events[0].record()
-        rays = self._render(seed, self.dev_pixels)
-        if kernel_events:
-            kernel_events[1].record()
+    def step_device(self, seed, time_trace=False):
+        """One frame with everything resident in HBM.  Returns this rank's ray counter (device tensor).
+        With ``time_trace`` every launch of the dominant kernel is bracketed with CUDA events
+        (Device.render_stats()['trace_ms'])."""
+        rays = self._render(seed, self.dev_pixels, time_trace=time_trace)
         self._assemble()
         return rays
 

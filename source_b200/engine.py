@@ -53,6 +53,11 @@ class Device:
         cabi.check(self.lib.rsb_counters(self.ctx, C.byref(c)))
         return c.as_dict()
 
+    def render_stats(self):
+        r = cabi.RsbRenderStats()
+        cabi.check(self.lib.rsb_render_stats(self.ctx, C.byref(r)))
+        return r.as_dict()
+
     def last_kernel_ms(self):
         ms = C.c_float()
         cabi.check(self.lib.rsb_last_kernel_ms(self.ctx, C.byref(ms)))
@@ -143,7 +148,7 @@ class Accelerator:
 
     # ---- Observer._render_pixel over a pixel list ---------------------------------------------------------
     def render_device(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None,
-                      count=False, stream=None):
+                      count=False, stream=None, time_trace=False):
         """Device-resident form: ``mean``/``variance`` are torch CUDA float64 tensors of shape (nx, ny, bins)
         (allocated zero-filled when None), ``pixels`` an int32 CUDA tensor [n, 2] or None for the whole frame.
         Enqueues on torch's current stream and returns (mean, variance, ray_count_tensor) without synchronising
@@ -162,7 +167,8 @@ class Accelerator:
         cabi.check(self.lib.rsb_render_dev(
             self.device.ctx, self.scene, C.c_void_p(st.cuda_stream), C.byref(camera), C.byref(config), C.byref(spectral),
             C.byref(rng), n, C.c_void_p(0 if pixels is None else pixels.data_ptr()), C.c_void_p(mean.data_ptr()),
-            C.c_void_p(variance.data_ptr()), C.c_void_p(rays.data_ptr()), int(bool(count))))
+            C.c_void_p(variance.data_ptr()), C.c_void_p(rays.data_ptr()),
+            (cabi.RENDER_COUNT if count else 0) | (cabi.RENDER_TIME_TRACE if time_trace else 0)))
         return mean, variance, rays
 
     def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
