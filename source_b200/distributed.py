@@ -27,6 +27,20 @@ def tile_pixels(nx, ny, tile, rank, world_size):
     return np.ascontiguousarray(np.stack([x[keep], y[keep]], axis=1).astype(np.int32))
 
 
+def reduce_frame(stats, out, rank, world_size):
+    """The single collective of the path: reduce(sum) of the stacked (mean, variance) frame to rank 0.
+    Every rank's ``stats`` is zero outside its own tiles, so the sum only ever adds zeros and rank 0 ends up
+    with bit-identical values to what the owning ranks wrote.  The collective runs on the scratch copy ``out``
+    (a reduce may use non-root buffers as workspace), so every rank's ``stats`` keeps exact zeros in its
+    foreign tiles for the next frame."""
+    if world_size == 1:
+        return stats
+    import torch.distributed as dist
+    out.copy_(stats)
+    dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+    return out if rank == 0 else None
+
+
 class FrameRenderer:
     """Renders one spectral slice of a PinholeCamera frame on `world_size` GPUs (this process = `rank`)."""
 
@@ -53,7 +67,7 @@ class FrameRenderer:
             self.dev_pixels = self.host_pixels.to(self.dev)
         # [0] mean, [1] variance: one tensor so that the frame crosses NVLink in a single reduce
         self.stats = torch.zeros((2, nx, ny, self.bins), dtype=torch.float64, device=self.dev)
-        self.out = torch.zeros_like(self.stats) if (world_size > 1 and rank == 0) else None
+        self.out = torch.zeros_like(self.stats) if world_size > 1 else None
         self.host_stats = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -65,15 +79,7 @@ class FrameRenderer:
 
     def _assemble(self):
         """single reduce(sum) of the (mean, variance) frame to rank 0"""
-        if self.world_size == 1:
-            return self.stats
-        import torch.distributed as dist
-        if self.rank == 0:
-            self.out.copy_(self.stats)      # keep this rank's buffer zero outside its own tiles for the next step
-            dist.reduce(self.out, dst=0, op=dist.ReduceOp.SUM)
-            return self.out
-        dist.reduce(self.stats, dst=0, op=dist.ReduceOp.SUM)
-        return None
+        return reduce_frame(self.stats, self.out, self.rank, self.world_size)
 
     def step_device(self, seed, time_trace=False):
         """One frame with everything resident in HBM.  Returns this rank's ray counter (device tensor).

@@ -1,0 +1,210 @@
+"""Drop-in plugins for a real Raysect installation.
+
+    from source_b200.plugin import CudaAccelerator, CudaRenderEngine
+    world.accelerator = CudaAccelerator()          # World.hit / World.contains on the GPU
+    camera.render_engine = CudaRenderEngine()      # camera.observe() renders on the GPU
+
+``CudaAccelerator`` subclasses ``raysect.core.acceleration.Accelerator`` (accelerator.pxd:37-41; installed
+through the ``World.accelerator`` setter, world.pyx:67-70) and ``CudaRenderEngine`` subclasses
+``raysect.core.workflow.RenderEngine`` (workflow.py:35-97; installed through ``observer.render_engine``,
+observer.pyx:106).  Both flatten the live Raysect scenegraph with ``source_b200.flatten`` -- every AABB,
+bounding sphere, matrix and spectral table is obtained from Raysect's own objects -- and call
+``libraysect_b200.so``.  Anything outside the supported set raises ``NotImplementedError``: there is no
+CPU fallback.
+
+Importing this module requires ``raysect``; the rest of ``source_b200`` does not.
+"""
+import numpy as np
+
+from raysect.core import Normal3D, Point3D
+from raysect.core.acceleration.accelerator import Accelerator
+from raysect.core.intersection import Intersection
+from raysect.core.workflow import RenderEngine
+
+from . import _cabi as cabi
+from .engine import Accelerator as _DeviceAccelerator
+from .engine import camera_desc, default_device, ray_config
+from .flatten import flatten_world
+
+
+class _PrimitiveList:
+    """what flatten_world needs from a World: the ordered primitive list"""
+
+    def __init__(self, primitives):
+        self.primitives = list(primitives)
+
+
+class CudaAccelerator(Accelerator):
+    """Scene accelerator backed by the device kd-tree traversal + primitive kernels.
+
+    ``hit(ray)`` / ``contains(point)`` keep the reference's scalar contract (1-element batches; meant for
+    API parity and tests); ``hit_batch`` / ``contains_batch`` are the forms that use the GPU properly.
+    """
+
+    def __init__(self, device=None, backend=None):
+        self._device = device
+        self._backend_factory = backend     # test hook: callable(FlatScene) -> object with the Accelerator surface
+        self._accel = None
+        self._primitives = []
+
+    # -- Accelerator interface (accelerator.pyx:32-41) ---------------------------------------------------
+    def build(self, primitives):
+        if self._accel is not None:
+            self._accel.close()
+            self._accel = None
+        self._primitives = list(primitives)
+        if not self._primitives:
+            return
+        flat = flatten_world(_PrimitiveList(self._primitives))
+        if self._backend_factory is not None:
+            self._accel = self._backend_factory(flat)
+        else:
+            self._accel = _DeviceAccelerator(self._device or default_device(), flat)
+
+    def hit(self, ray):
+        if self._accel is None:
+            return None
+        o, d = ray.origin, ray.direction
+        r = self._accel.hit_batch([[o.x, o.y, o.z]], [[d.x, d.y, d.z]], [ray.max_distance], geometry=True)
+        i = int(r.primitive[0])
+        if i < 0:
+            return None
+        prim = self._primitives[i]
+        g = r.geometry[0]
+        return Intersection(ray, float(r.distance[0]), prim, Point3D(g[0], g[1], g[2]), Point3D(g[3], g[4], g[5]),
+                            Point3D(g[6], g[7], g[8]), Normal3D(g[9], g[10], g[11]), bool(r.exiting[0]),
+                            prim.to_local(), prim.to_root())
+
+    def contains(self, point):
+        if self._accel is None:
+            return []
+        cap = 8
+        while True:
+            count, prims = self._accel.contains_batch([[point.x, point.y, point.z]], cap)
+            if count[0] <= cap:
+                return [self._primitives[int(i)] for i in prims[0, :count[0]]]
+            cap = int(count[0])
+
+    # -- batched forms -----------------------------------------------------------------------------------
+    def hit_batch(self, origins, directions, max_distance=None, geometry=False):
+        """-> source_b200.engine.HitBatch (primitive = index into the list passed to build())"""
+        return self._accel.hit_batch(origins, directions, max_distance, geometry=geometry)
+
+    def contains_batch(self, points, cap=8):
+        return self._accel.contains_batch(points, cap)
+
+    @property
+    def device_accelerator(self):
+        return self._accel
+
+
+class CudaRenderEngine(RenderEngine):
+    """RenderEngine that renders every task of a spectral slice on the GPU(s).
+
+    Contract (workflow.py:78-91, observer.pyx:299-305): ``run(tasks, render, update, render_args=(slice_id,
+    template_ray), update_args=(slice_id,))`` is called once per spectral slice; ``render`` is the bound
+    ``observer._render_pixel``, so the observer, its world and its pipelines are reachable from it.
+    Supported: ``PinholeCamera`` observers feeding ``SpectralPowerPipeline2D`` pipelines (the spectral frame
+    every other 2-D pipeline is a post-processing of), worlds built from Sphere/Box/Cylinder/Cone/CSG/Mesh
+    with Lambert / UniformSurfaceEmitter / Dielectric / AbsorbingSurface materials.
+
+    Random streams: pixel (x, y) of slice k draws from the reference generator seeded with
+    ``seed + k*nx*ny + y*nx + x`` (``rng="mt"``), i.e. exactly what a SerialEngine would produce if
+    ``raysect.core.math.random.seed`` were called with that value before each pixel task; ``rng="philox"``
+    uses counter-based streams instead (faster, statistically equivalent).
+
+    ``bulk_update=True`` writes the slice straight into each pipeline's ``frame`` arrays (StatsArray3D)
+    with the reference's combine rule instead of calling ``update`` once per pixel.
+    """
+
+    def __init__(self, seed=1, rng="mt", device=None, bulk_update=True, backend=None):
+        if rng not in ("mt", "philox"):
+            raise ValueError("rng must be 'mt' or 'philox'")
+        if seed < 1:
+            raise ValueError("seed must be >= 1")
+        self.seed = int(seed)
+        self.rng_mode = cabi.RNG_MT19937_64 if rng == "mt" else cabi.RNG_PHILOX
+        self.bulk_update = bulk_update
+        self._device = device
+        self._backend_factory = backend
+        self._accel = None
+        self._accel_world = None
+        self.ray_count = 0
+
+    def worker_count(self):
+        return 1
+
+    def _accelerator_for(self, world, slice_id):
+        # a new observe() starts at slice 0: re-flatten there so scene edits between renders are picked up
+        if self._accel is None or self._accel_world is not world or slice_id == 0:
+            if self._accel is not None:
+                self._accel.close()
+            flat = flatten_world(world)
+            if self._backend_factory is not None:
+                self._accel = self._backend_factory(flat)
+            else:
+                self._accel = _DeviceAccelerator(self._device or default_device(), flat)
+            self._accel_world = world
+        return self._accel
+
+    def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
+        from raysect.optical.observer import PinholeCamera, SpectralPowerPipeline2D
+        observer = getattr(render, "__self__", None)
+        if not isinstance(observer, PinholeCamera):
+            raise NotImplementedError("CudaRenderEngine renders PinholeCamera observers; got %r (no CPU fallback)"
+                                      % type(observer).__name__)
+        pipelines = list(observer.pipelines)
+        for p in pipelines:
+            if not isinstance(p, SpectralPowerPipeline2D):
+                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D pipelines; %r is host-side "
+                                          "post-processing of that spectral frame" % type(p).__name__)
+        slice_id, template = render_args[0], render_args[1]
+        world = observer.root
+        accel = self._accelerator_for(world, slice_id)
+        nx, ny = observer.pixels
+        cam = camera_desc(nx, ny, observer.pixel_samples, observer.fov, observer.sensitivity, observer.to_root())
+        cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
+                         template.extinction_min_depth, template.max_depth, template.importance_sampling,
+                         template.important_path_weight, template.max_distance)
+        spectral = accel.flat.spectral(template.min_wavelength, template.max_wavelength, template.bins)
+        pix = np.asarray(tasks, dtype=np.int32).reshape(-1, 2)
+        mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix)
+        self.ray_count += rays
+        if self.bulk_update:
+            offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
+            self._bulk_update(pipelines, pix, offset, mean, variance, observer.pixel_samples)
+            # statistics hook of the observer: one update carrying the whole ray count
+            observer._update_statistics(rays)
+            return
+        share, extra = divmod(rays, len(pix))
+        for k, (x, y) in enumerate(pix):
+            result = ((int(x), int(y)), [(mean[x, y].copy(), variance[x, y].copy()) for _ in pipelines],
+                      share + (extra if k == 0 else 0))
+            update(result, *update_args, **update_kwargs)
+
+    @staticmethod
+    def _bulk_update(pipelines, pix, offset, mean, variance, samples):
+        """SpectralPowerPipeline2D.update for every pixel at once (power.pyx:424-437 ->
+        StatsArray3D.combine_samples, statsarray.pyx:623-667)."""
+        from .observer import combine_samples
+        xs, ys = pix[:, 0], pix[:, 1]
+        sl = slice(offset, offset + mean.shape[2])
+        for p in pipelines:
+            frame = p.frame
+            fm, fv, fs = np.asarray(frame.mean), np.asarray(frame.variance), np.asarray(frame.samples)
+            mt, vt, nt = combine_samples(fm[xs, ys, sl], fv[xs, ys, sl], fs[xs, ys, sl],
+                                         mean[xs, ys], np.maximum(variance[xs, ys], 0.0), samples)
+            fm[xs, ys, sl] = mt
+            fv[xs, ys, sl] = vt
+            fs[xs, ys, sl] = nt
+
+
+def slice_offsets(spectral_bins, spectral_rays):
+    """Bin offset of every spectral slice, cut as observer._slice_spectrum does (observer.pyx:311-340)."""
+    current, start, offsets = 0, 0, []
+    while start < spectral_bins:
+        current += spectral_bins / spectral_rays
+        end = round(current)
+        offsets.append(start)
+        start = end
+    return offsets

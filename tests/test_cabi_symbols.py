@@ -1,0 +1,122 @@
+"""The C-ABI shared library loads on a machine without a GPU and exports exactly the entry points that
+include/raysect_b200.h declares; host-only entry points work, device entry points fail loudly."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from source_b200 import _cabi as cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "raysect_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libraysect_b200.so does not export %s" % n
+    assert sorted(cabi.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
+    assert lib.rsb_version() >= 100
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    """product sources never reference oracle/ or the test-only host build"""
+    for root, _, files in os.walk(os.path.join(ROOT, "source_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "hostsim" not in text, f
+
+
+def test_device_entry_points_fail_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_uint64()
+    rc = lib.rsb_context_create(0, C.byref(h))
+    assert rc == cabi.ERR_CUDA
+    assert b"no CPU fallback" in lib.rsb_last_error()
+    with pytest.raises(cabi.RsbError):
+        from source_b200.engine import Device
+        Device(0)
+
+
+def test_kdtree_builder_stream_roundtrip_and_errors(lib):
+    from source_b200.flatten import kdtree_build
+    rng = np.random.default_rng(0)
+    lo = rng.uniform(-1, 1, (200, 3))
+    boxes = np.c_[lo, lo + rng.uniform(0.01, 0.2, (200, 3))]
+    stream = kdtree_build(boxes, 0, 1, 80.0, 0.2)
+    import struct
+    max_depth, min_items, hit_cost, bonus = struct.unpack_from("<iidd", stream, 0)
+    assert max_depth == int(np.ceil(8 + 1.3 * np.log(200))) and min_items == 1 and hit_cost == 80.0 and bonus == 0.2
+    bounds = struct.unpack_from("<6d", stream, 24)
+    np.testing.assert_array_equal(bounds[:3], boxes[:, :3].min(axis=0))
+    np.testing.assert_array_equal(bounds[3:], boxes[:, 3:].max(axis=0))
+    # every item appears in at least one leaf
+    n_nodes = struct.unpack_from("<i", stream, 72)[0]
+    off, seen = 76, set()
+    for _ in range(n_nodes):
+        t = struct.unpack_from("<i", stream, off)[0]
+        if t == -1:
+            cnt = struct.unpack_from("<i", stream, off + 4)[0]
+            seen.update(struct.unpack_from("<%di" % cnt, stream, off + 8))
+            off += 8 + 4 * cnt
+        else:
+            off += 16
+    assert off == len(stream) and seen == set(range(200))
+    with pytest.raises(cabi.RsbError):
+        kdtree_build(boxes, 0, 1, 80.0, 1.5)      # empty_bonus outside [0, 1]: the reference raises ValueError
+
+
+def test_object_model_matches_reference_golden():
+    """transforms, bounding boxes/spheres and spectral resampling of the mirror classes vs the reference"""
+    import parity
+    import scenes
+    import source_b200 as api
+    g = parity.golden("object_model")
+    world = scenes.primitive_zoo(api)
+    rows = []
+    for p in world.primitives:
+        b, s = p.bounding_box(), p.bounding_sphere()
+        rows.append([p.to_local()[i, j] for i in range(3) for j in range(4)] + [p.to_root()[i, j] for i in range(3) for j in range(4)]
+                    + [b.lower.x, b.lower.y, b.lower.z, b.upper.x, b.upper.y, b.upper.z, s.centre.x, s.centre.y, s.centre.z, s.radius])
+    np.testing.assert_array_equal(np.array(rows), g["zoo_rows"])
+    glass, sf11 = api.schott("N-BK7"), api.schott("SF11")
+    white = api.InterpolatedSF(scenes.CB_WAVELENGTHS, scenes.CB_WHITE)
+    light = api.InterpolatedSF(*scenes.CB_LIGHT)
+    for tag, (lo, hi, bins) in dict(a=(375.0, 740.0, 15), b=(400.0, 700.0, 64), c=(520.5, 530.25, 3), d=(300.0, 420.0, 7)).items():
+        np.testing.assert_array_equal(white.sample(lo, hi, bins), g["white_" + tag])
+        np.testing.assert_array_equal(light.sample(lo, hi, bins), g["light_" + tag])
+        np.testing.assert_array_equal(glass.transmission.sample(lo, hi, bins), g["bk7_t_" + tag])
+        assert glass.index.average(lo, hi) == float(g["bk7_n_" + tag])
+        np.testing.assert_array_equal(sf11.transmission.sample(lo, hi, bins), g["sf11_t_" + tag])
+        assert sf11.index.average(lo, hi) == float(g["sf11_n_" + tag])
+
+
+def test_combine_samples_matches_host_build_of_device_code():
+    """numpy StatsArray3D.combine (observer.py) vs stats_combine (rsb_path.h) incl. the n in {0, 1} branches"""
+    import hostsim_api
+    from source_b200.observer import combine_samples
+    rng = np.random.default_rng(3)
+    n_pix, fb, sb, off = 60, 7, 3, 2
+    fm = rng.normal(size=(n_pix, fb)); fv = rng.uniform(0, 2, (n_pix, fb)); fs = rng.integers(0, 4, (n_pix, fb)).astype(np.int32)
+    fm[fs == 0] = 0; fv[fs <= 1] = 0
+    for samples in (1, 2, 9):
+        m = rng.normal(size=(n_pix, sb)); v = rng.uniform(0, 2, (n_pix, sb))
+        if samples == 1:
+            v[...] = 0
+        gm, gv, gs = fm.copy(), fv.copy(), fs.copy()
+        hostsim_api.lib().hs_frame_combine(n_pix, fb, off, sb, m.ctypes.data, v.ctypes.data, samples, gm.ctypes.data, gv.ctypes.data, gs.ctypes.data)
+        mt, vt, nt = combine_samples(fm[:, off:off + sb], fv[:, off:off + sb], fs[:, off:off + sb], m, v, samples)
+        np.testing.assert_array_equal(nt, gs[:, off:off + sb])
+        np.testing.assert_array_equal(mt, gm[:, off:off + sb])
+        np.testing.assert_array_equal(vt, gv[:, off:off + sb])

@@ -1,0 +1,101 @@
+"""CPU suite, part 2: the Raysect plugin classes (CudaAccelerator / CudaRenderEngine) driven on REAL Raysect
+objects from the compiled reference, with the device replaced by the host build of the device code -- this
+pins the host-side logic (flattening of live Raysect scenegraphs, Intersection reconstruction, slice
+handling, pipeline updates) bit-for-bit against the reference's own KDTree accelerator / SerialEngine."""
+import numpy as np
+import pytest
+
+import hostsim_api
+import scenes
+
+pytestmark = pytest.mark.ref
+
+
+@pytest.fixture(scope="module")
+def api(reference, lib):
+    hostsim_api.build()
+    return reference.ref_api()
+
+
+def test_accelerator_scalar_api_matches_reference_kdtree(api, reference):
+    from raysect.core import Point3D, Vector3D
+    from source_b200.plugin import CudaAccelerator
+    world = scenes.primitive_zoo(api)
+    o, d = scenes.zoo_rays(300)
+    ref = reference.oracle_hit(world, o, d)
+    pts = np.random.default_rng(5).uniform([-2.8, -2.6, -0.6], [2.8, 2.2, 0.8], (200, 3))
+    c_ref, p_ref = reference.oracle_contains(world, pts)
+    world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)     # World.accelerator seam, world.pyx:67-70
+    index = {id(p): i for i, p in enumerate(world.primitives)}
+    for i in range(len(o)):
+        it = world.hit(api.Ray(Point3D(*o[i]), Vector3D(*d[i])))
+        if ref["primitive"][i] < 0:
+            assert it is None
+            continue
+        assert index[id(it.primitive)] == ref["primitive"][i]
+        assert it.ray_distance == ref["distance"][i]
+        assert bool(it.exiting) == bool(ref["exiting"][i])
+        g = ref["geometry"][i]
+        assert (it.hit_point.x, it.hit_point.y, it.hit_point.z) == tuple(g[0:3])
+        assert (it.inside_point.x, it.inside_point.y, it.inside_point.z) == tuple(g[3:6])
+        assert (it.outside_point.x, it.outside_point.y, it.outside_point.z) == tuple(g[6:9])
+        assert (it.normal.x, it.normal.y, it.normal.z) == tuple(g[9:12])
+        assert it.primitive_to_world is not None and it.world_to_primitive is not None
+    for i in range(len(pts)):
+        got = [index[id(p)] for p in world.contains(Point3D(*pts[i]))]
+        assert got == list(p_ref[i, :c_ref[i]])
+
+
+def test_accelerator_inside_optical_trace(api, reference):
+    """The reference's own Ray.trace recursion running on top of CudaAccelerator.hit/contains must reproduce the
+    reference render exactly (every World.hit / World.contains of the render goes through the plugin)."""
+    from source_b200.plugin import CudaAccelerator
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(8, 8), samples=2, bins=4)
+    m_ref, v_ref, _ = reference.oracle_render(cam, pipe, 321)
+    world2 = scenes.cornell_box(api)
+    world2.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, pixels=(8, 8), samples=2, bins=4)
+    m, v, _ = reference.oracle_render(cam2, pipe2, 321)
+    np.testing.assert_array_equal(m, m_ref)
+    np.testing.assert_array_equal(v, v_ref)
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_render_engine_matches_serial_reference(api, reference, bulk):
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(12, 10), samples=3, bins=9, spectral_rays=3)
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 555)
+    world2 = scenes.cornell_box(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
+    cam2.render_engine = CudaRenderEngine(seed=555, rng="mt", bulk_update=bulk, backend=hostsim_api.HostScene)
+    cam2.observe()                                          # observer.render_engine seam, observer.pyx:106
+    f = pipe2.frame
+    np.testing.assert_array_equal(np.array(f.samples), n_ref)
+    np.testing.assert_array_equal(np.array(f.mean), m_ref)
+    np.testing.assert_array_equal(np.array(f.variance), v_ref)
+    # accumulate=True: a second observe() merges into the frame with the reference's combine rule
+    cam.observe()
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.samples), np.array(pipe.frame.samples))
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), np.array(pipe.frame.mean))
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), np.array(pipe.frame.variance))
+
+
+def test_unsupported_objects_fail_loudly(api):
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    world = scenes.cornell_box(api)
+    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[RGBPipeline2D()], frame_sampler=api.FullFrameSampler2D())
+    cam.quiet = True
+    cam.render_engine = CudaRenderEngine(backend=hostsim_api.HostScene)
+    with pytest.raises(NotImplementedError):
+        cam.observe()
+    from raysect.primitive import Torus
+    from source_b200.plugin import CudaAccelerator
+    Torus(1.0, 0.2, world, material=api.AbsorbingSurface())
+    world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
+    with pytest.raises(NotImplementedError):
+        world.build_accelerator(force=True)
