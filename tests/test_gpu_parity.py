@@ -100,9 +100,9 @@ def test_errors_are_loud(device):
 def test_plugin_on_device_against_live_reference(device, reference):
     """Real Raysect objects + CudaAccelerator / CudaRenderEngine on the B200 vs Raysect's own KDTree + serial render"""
     import scenes
+    api = reference.ref_api()      # puts oracle/_ref on sys.path
     from raysect.core import Point3D, Vector3D
     from source_b200.plugin import CudaAccelerator, CudaRenderEngine
-    api = reference.ref_api()
     world = scenes.primitive_zoo(api)
     o, d = scenes.zoo_rays(400)
     ref = reference.oracle_hit(world, o, d)
