@@ -509,7 +509,7 @@ struct Carver {
     }
 };
 
-size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, WfSlots* st) {
+size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t chunk, WfSlots* st) {
     Carver c{base};
     st->ray = c.take<double>(6 * P);
     st->weight = c.take<double>(P);
@@ -525,12 +525,13 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, WfSlots* 
     st->status = c.take<int32_t>(P);
     st->log_n = c.take<int32_t>(P);
     st->philox_idx = c.take<uint32_t>(P);
-    st->mti = c.take<int32_t>(2 * P);
+    st->work = c.take<int32_t>(P);
     st->ended = c.take<int32_t>(2 * P);
     st->n_ended = c.take<unsigned int>(2);
     st->hit_list = c.take<int32_t>(4 * P);
     st->n_hit = c.take<unsigned int>(4);
-    st->mt = mt ? c.take<unsigned long long>(P * 2 * RSB_MT_NN) : nullptr;
+    st->pix_mti = mt ? c.take<int32_t>(2 * chunk) : nullptr;
+    st->pix_mt = mt ? c.take<unsigned long long>(chunk * 2 * RSB_MT_NN) : nullptr;
     st->log = c.take<LogEntry>(P * cap);
     return (c.off + 255) & ~(size_t)255;
 }
@@ -549,14 +550,17 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
     a.wave = 0;
+    RsbRenderStats& rs = c->render_stats;
+    rs.slots = std::max<int64_t>(rs.slots, a.n_slots);
+    if (RNGMODE == RNG_MT19937_64) {
+        k_wf_seed<<<(unsigned int)((a.n_pixels + threads - 1) / threads), threads, 0, st>>>(a);
+        rs.launches += 1;
+    }
     k_wf_init<RNGMODE><<<grid, threads, 0, st>>>(a);
     RSB_CUDA(cudaGetLastError());
     unsigned int* h_idle = c->h_idle;
     const int kBatch = 32;
-    RsbRenderStats& rs = c->render_stats;
-    rs = RsbRenderStats{};
-    rs.slots = a.n_slots;
-    rs.launches = 1;
+    rs.launches += 1;
     if (time_trace) {
         while (c->event_pool.size() < 2 * kBatch) {
             cudaEvent_t e;
@@ -671,14 +675,13 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     a.cam.image_start_y = camera->image_start_y;
     a.cam.sensitivity = camera->sensitivity;
     memcpy(a.cam.to_root, camera->to_root, sizeof(a.cam.to_root));
-    a.n_pixels = n_pixels;
-    a.pixels = pixels_dev;
     a.mean = mean_dev;
     a.variance = variance_dev;
     a.ray_count = (unsigned long long*)ray_count_dev;
     a.work_counter = c->d_scalars;
     a.n_idle = (unsigned int*)(c->d_scalars + 1);
     a.overflow_flag = (int32_t*)(c->d_scalars + 2);
+    RSB_CUDA(cudaMemsetAsync(c->d_scalars + 2, 0, sizeof(unsigned long long), st));
     a.counters = c->d_counters;
     a.seed = rng->seed;
     a.n_items = ds->n_world_items;
@@ -695,30 +698,41 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     a.log_capacity = (int32_t)std::min(cap, 1LL << 16);
 
     // ---- slot pool: one pixel stream per slot, two CTA waves of 1024 threads per SM ---------------------
+    // Pixels are processed in chunks so that the up-front MT19937-64 state of a chunk (5 KB per pixel) stays
+    // within a fixed HBM budget; a 1024 x 1024 frame is one chunk (5.2 GB).
     bool mt = rng->mode == RSB_RNG_MT19937_64;
-    long long P = std::min<long long>(n_pixels, (long long)c->sm_count * 2048);
+    const long long kChunkPixels = 2LL << 20;
+    long long chunk_cap = std::min<long long>(n_pixels, kChunkPixels);
+    long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * 2048);
     P = std::max<long long>(P, 1);
-    a.n_slots = (int32_t)P;
     WfSlots probe;
-    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, &probe);
+    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe);
     if (c->slot_bytes < need) {
         cudaFree(c->d_slots);
         c->d_slots = nullptr; c->slot_bytes = 0;
         RSB_CUDA(cudaMalloc(&c->d_slots, need));
         c->slot_bytes = need;
     }
-    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, &a.st);
-    RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 8 * sizeof(unsigned long long), st));
-    RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
-    RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
+    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &a.st);
     if (count & RSB_RENDER_COUNT) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-    int rc;
     const bool time_trace = (count & RSB_RENDER_TIME_TRACE) != 0;
     count &= RSB_RENDER_COUNT;
-    if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-                       : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
-    else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-                    : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
+    c->render_stats = RsbRenderStats{};
+    int rc = RSB_OK;
+    for (long long base = 0; base < n_pixels && rc == RSB_OK; base += chunk_cap) {
+        a.n_pixels = std::min<long long>(chunk_cap, n_pixels - base);
+        a.pixel_base = base;
+        a.pixels = pixels_dev ? pixels_dev + 2 * base : nullptr;
+        a.n_slots = (int32_t)std::min<long long>(P, a.n_pixels);
+        // scalars: [0] work counter, [1] idle slots, [2] overflow flag (sticky across chunks)
+        RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(unsigned long long), st));
+        RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
+        RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
+        if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+                           : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
+        else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+                        : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
+    }
     if (rc) return rc;
     {
         int32_t overflow = 0;

@@ -258,8 +258,9 @@ struct WfSlots {
     int32_t* status;        // [P]
     int32_t* log_n;         // [P]
     uint32_t* philox_idx;   // [P]
-    int32_t* mti;           // [2][P]  path stream, jitter stream cursors
-    unsigned long long* mt; // [P][2][312]
+    int32_t* work;          // [P] index (within the current pixel chunk) of the pixel the slot is rendering
+    int32_t* pix_mti;       // [n_chunk][2] MT19937-64 cursors of every pixel of the chunk: path stream, jitter stream
+    unsigned long long* pix_mt;   // [n_chunk][2][312] their state words (seeded up front by k_wf_seed)
     LogEntry* log;          // [P][log_capacity]
     int32_t* ended;         // [2][P] compacted lists of ended slots (double buffered by wave parity)
     unsigned int* n_ended;  // [2]
@@ -273,8 +274,9 @@ struct WfArgs {
     RayConfig cfg;
     Camera cam;
     WfSlots st;
-    long long n_pixels;
-    const int32_t* pixels;
+    long long n_pixels;         // pixels of the current chunk
+    long long pixel_base;       // first frame pixel of the chunk when `pixels` is null
+    const int32_t* pixels;      // chunk's slice of the task list, or null
     double* mean;
     double* variance;
     unsigned long long* ray_count;
@@ -295,9 +297,10 @@ template <int RNGMODE>
 __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng) {
     rng.mode = RNGMODE;
     if (RNGMODE == RNG_MT19937_64) {
-        rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.mt) + (size_t)slot * (2 * RSB_MT_NN);
+        size_t w = (size_t)a.st.work[slot];
+        rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN);
         rng.mt.stride = 1;
-        rng.mt.mti = a.st.mti[slot];
+        rng.mt.mti = a.st.pix_mti[2 * w];
     } else {
         long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
         rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)a.st.sample[slot]);
@@ -307,7 +310,7 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
 
 template <int RNGMODE>
 __device__ __forceinline__ void wf_store_rng(const WfArgs& a, int slot, const Rng& rng) {
-    if (RNGMODE == RNG_MT19937_64) a.st.mti[slot] = rng.mt.mti;
+    if (RNGMODE == RNG_MT19937_64) a.st.pix_mti[2 * (size_t)a.st.work[slot]] = rng.mt.mti;
     else a.st.philox_idx[slot] = rng.px.idx;
 }
 
@@ -317,18 +320,41 @@ __device__ __forceinline__ void wf_push_ended(const WfArgs& a, int slot) {
     a.st.ended[(size_t)par * a.n_slots + k] = slot;
 }
 
-// Next sample of the slot's pixel, or the next pixel from the work counter (FullFrameSampler2D task list);
-// PinholeCamera._generate_rays for that sample.  Runs on one thread.
+// Pixel (x, y) of work item w of the current chunk (FullFrameSampler2D task list, or the whole frame)
+__device__ __forceinline__ void wf_pixel_of(const WfArgs& a, unsigned long long w, int* px, int* py) {
+    if (a.pixels) { *px = a.pixels[2 * w]; *py = a.pixels[2 * w + 1]; }
+    else {
+        unsigned long long g = w + (unsigned long long)a.pixel_base;
+        *px = (int)(g / (unsigned long long)a.cam.ny);
+        *py = (int)(g % (unsigned long long)a.cam.ny);
+    }
+}
+
+// 1 thread = 1 pixel of the chunk: seed(seed + y*nx + x) for both cursors of the pixel's stream, all pixels in
+// parallel and ahead of time (seeding is a 935-step dependent chain; done lazily inside the wave loop it put
+// the latency of one chain on the critical path of every wave).
+__global__ void __launch_bounds__(128) k_wf_seed(const __grid_constant__ WfArgs a) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.n_pixels) return;
+    int px, py;
+    wf_pixel_of(a, (unsigned long long)w, &px, &py);
+    long long pixel_id = (long long)py * a.cam.nx + px;
+    uint64_t* base = reinterpret_cast<uint64_t*>(a.st.pix_mt) + (size_t)w * (2 * RSB_MT_NN);
+    int jm, pm;
+    // the jitter cursor starts at draw 0, the path cursor after the 2*spp draws that
+    // RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
+    mt_seed_pair(a.seed + (unsigned long long)pixel_id, 2 * a.cam.pixel_samples, base + RSB_MT_NN, &jm, base, &pm);
+    a.st.pix_mti[2 * w] = pm;
+    a.st.pix_mti[2 * w + 1] = jm;
+}
+
+// Next sample of the slot's pixel, or the next pixel from the work counter; PinholeCamera._generate_rays for
+// that sample.  Runs on one thread.
 template <int RNGMODE>
 __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     const int spp = a.cam.pixel_samples;
     int s = a.st.sample[slot];
     int px = a.st.px[slot], py = a.st.py[slot];
-    Rng jit;
-    jit.mode = RNGMODE;
-    jit.mt.mt = reinterpret_cast<uint64_t*>(a.st.mt) + (size_t)slot * (2 * RSB_MT_NN) + RSB_MT_NN;
-    jit.mt.stride = 1;
-    jit.mt.mti = a.st.mti[a.n_slots + slot];
     if (s >= spp) {
         unsigned long long w = atomicAdd(a.work_counter, 1ULL);
         if (w >= (unsigned long long)a.n_pixels) {
@@ -336,31 +362,24 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
             atomicAdd(a.n_idle, 1u);
             return;
         }
-        if (a.pixels) { px = a.pixels[2 * w]; py = a.pixels[2 * w + 1]; }
-        else { px = (int)(w / (unsigned long long)a.cam.ny); py = (int)(w % (unsigned long long)a.cam.ny); }
+        wf_pixel_of(a, w, &px, &py);
         a.st.px[slot] = px;
         a.st.py[slot] = py;
+        a.st.work[slot] = (int32_t)w;
         s = 0;
-        if (RNGMODE == RNG_MT19937_64) {
-            // seed(seed + pixel_id): the jitter cursor starts at draw 0, the path cursor after the 2*spp draws
-            // that RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
-            long long pixel_id = (long long)py * a.cam.nx + px;
-            jit.mt.seed(a.seed + (unsigned long long)pixel_id);
-            Mt19937_64 path;
-            path.mt = jit.mt.mt - RSB_MT_NN;
-            path.stride = 1;
-            for (int i = 0; i < RSB_MT_NN; ++i) path.w(i) = jit.mt.w(i);
-            path.mti = RSB_MT_NN;
-            for (int i = 0; i < 2 * spp; ++i) (void)path.next_u64();
-            a.st.mti[slot] = path.mti;
-        }
     }
     a.st.sample[slot] = s;
+    Rng jit;
+    jit.mode = RNGMODE;
     double u1, u2;
     if (RNGMODE == RNG_MT19937_64) {
+        size_t w = (size_t)a.st.work[slot];
+        jit.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN) + RSB_MT_NN;
+        jit.mt.stride = 1;
+        jit.mt.mti = a.st.pix_mti[2 * w + 1];
         u1 = jit.uniform();
         u2 = jit.uniform();
-        a.st.mti[a.n_slots + slot] = jit.mt.mti;
+        a.st.pix_mti[2 * w + 1] = jit.mt.mti;
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
         jit.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)s);
@@ -388,8 +407,7 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
     a.st.sample[slot] = a.cam.pixel_samples;   // forces a pixel fetch
     a.st.px[slot] = 0;
     a.st.py[slot] = 0;
-    a.st.mti[slot] = RSB_MT_NN;
-    a.st.mti[a.n_slots + slot] = RSB_MT_NN;
+    a.st.work[slot] = 0;
     wf_regenerate<RNGMODE>(a, slot);
 }
 

@@ -81,6 +81,23 @@ struct Mt19937_64 {
     }
 };
 
+// Seeds a pixel's two cursors in one pass over a thread-private scratch array (local memory, L1 resident)
+// instead of running the 935-step initialisation chain and the 2*spp-draw skip as dependent round trips to
+// the HBM-resident state: `jitter` receives the state right after seed(d) (cursor at draw 0), `path` the
+// same stream advanced by `skip` draws.  Sequence identical to Mt19937_64::seed + next_u64.
+RSB_HD void mt_seed_pair(uint64_t d, int skip, uint64_t* jitter, int* jitter_mti, uint64_t* path, int* path_mti) {
+    uint64_t m[RSB_MT_NN];
+    Mt19937_64 g;
+    g.mt = m;
+    g.stride = 1;
+    g.seed(d);
+    for (int i = 0; i < RSB_MT_NN; ++i) jitter[i] = m[i];
+    *jitter_mti = g.mti;
+    for (int i = 0; i < skip; ++i) (void)g.next_u64();
+    for (int i = 0; i < RSB_MT_NN; ++i) path[i] = m[i];
+    *path_mti = g.mti;
+}
+
 struct Philox4x32 {
     uint32_t key[2];
     uint32_t ctr[3];    // (sub-stream, stream lo, stream hi); the block index is idx >> 1

@@ -213,10 +213,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
         rng.mt.mt = st_path.data(); rng.mt.stride = 1; rng.mt.mti = RSB_MT_NN;
         jit.mt.mt = st_jit.data(); jit.mt.stride = 1; jit.mt.mti = RSB_MT_NN;
         if (rngd->mode == RNG_MT19937_64) {
-            jit.mt.seed(rngd->seed + (uint64_t)pixel_id);
-            for (int i = 0; i < RSB_MT_NN; ++i) rng.mt.w(i) = jit.mt.w(i);
-            rng.mt.mti = RSB_MT_NN;
-            for (int i = 0; i < 2 * spp; ++i) (void)rng.mt.next_u64();
+            mt_seed_pair(rngd->seed + (uint64_t)pixel_id, 2 * spp, st_jit.data(), &jit.mt.mti, st_path.data(), &rng.mt.mti);
         }
         double* m = mean + frame_row * bins;
         double* v = variance + frame_row * bins;
