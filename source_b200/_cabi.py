@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraysect_b200.so")
+LIB_PATH = os.environ.get("RSB_LIBRARY") or os.path.join(_HERE, "libraysect_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3, 4
 

@@ -4,7 +4,7 @@
 # that products and sums round separately.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libraysect_b200.so"
+OUT="${RSB_OUT:-$HERE/../libraysect_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo -fmad=false \
     -gencode arch=compute_100a,code=sm_100a \

@@ -17,6 +17,12 @@
 namespace rsb {
 
 #define RSB_FULL_MASK 0xffffffffu
+#ifndef RSB_TRACE_MIN_BLOCKS
+#define RSB_TRACE_MIN_BLOCKS 3      // k_wf_trace: CTAs of 128 threads per SM the register allocation must allow
+#endif
+#ifndef RSB_SHADE_MIN_BLOCKS
+#define RSB_SHADE_MIN_BLOCKS 4
+#endif
 #define RSB_RENDER_THREADS 128
 
 struct DevCounters {   // mirrors RsbCounters
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
 // finishes, was measured SLOWER on the Cornell scene -- 208 vs 129 us per 262k-ray wave, 9.1 vs 10.0 active
 // lanes per instruction: iteration counts per ray vary little here, and the refill path diverges.)
 template <int RNGMODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs a) {
+__global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     stage_scene(sc, smem, a.n_items, a.staged);
@@ -424,6 +430,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = slot < P && a.st.status[slot] == SLOT_ALIVE;
     unsigned long long hits = 0;
+    int list = -1;
     if (active) {
         const size_t PP = (size_t)P;
         PathState ps;
@@ -445,12 +452,29 @@ __global__ void __launch_bounds__(128) k_wf_trace(const __grid_constant__ WfArgs
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
             a.st.norm[slot] = normalisation;
             a.st.status[slot] = SLOT_HIT;
-            int mt = a.sp.mats[sc.prims[rec.prim].material].type;
-            unsigned int k = atomicAdd(&a.st.n_hit[mt], 1u);
-            a.st.hit_list[(size_t)mt * PP + k] = slot;
+            list = a.sp.mats[sc.prims[rec.prim].material].type;     // 0..3: per-material hit lists
         } else {
             a.st.status[slot] = SLOT_ENDED_ZERO;
-            wf_push_ended(a, slot);
+            list = 4;                                                // ended list
+        }
+    }
+    // compact into the five lists with one atomic per (warp, list) instead of one per lane
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        unsigned m = __ballot_sync(RSB_FULL_MASK, list == l);
+        if (m == 0) continue;
+        const int lane = threadIdx.x & 31;
+        unsigned int base = 0;
+        if (lane == __ffs(m) - 1) {
+            unsigned int* ctr = (l < 4) ? &a.st.n_hit[l] : &a.st.n_ended[a.wave & 1];
+            base = atomicAdd(ctr, (unsigned int)__popc(m));
+        }
+        base = __shfl_sync(RSB_FULL_MASK, base, __ffs(m) - 1);
+        if (list == l) {
+            unsigned int k = base + __popc(m & ((1u << lane) - 1));
+            if (l < 4) a.st.hit_list[(size_t)l * P + k] = slot;
+            else a.st.ended[(size_t)(a.wave & 1) * P + k] = slot;
         }
     }
     if (COUNT) {
@@ -511,7 +535,7 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
 }
 
 template <int RNGMODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_wf_shade(const __grid_constant__ WfArgs a) {
+__global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     Spectral sp = a.sp;
