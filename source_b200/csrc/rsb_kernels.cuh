@@ -592,12 +592,46 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * bins;
         double* m = a.mean + row;
         double* v = a.variance + row;
-        for (int b = lane; b < bins; b += 32) {
-            double x = 0.0;
-            if (status == SLOT_ENDED_EMIT) x = replay_bin(log, sp, b);
-            x = x * w;                      // spectrum.mul_scalar(projection_weight), observer.pyx:408
-            x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
-            welford_add(x, m + b, v + b, s);
+        const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
+        const bool emit = status == SLOT_ENDED_EMIT;
+        for (int b0 = 0; b0 < bins; b0 += 64) {
+            // two bins per lane per pass; the statistics rows are fetched before the replay so that their
+            // latency overlaps it
+            const int ba = b0 + lane, bb = b0 + 32 + lane;
+            const bool ha = ba < bins, hb = bb < bins;
+            double ma = 0, va = 0, mb = 0, vb = 0;
+            if (s > 0) {
+                if (ha) { ma = m[ba]; va = v[ba]; }
+                if (hb) { mb = m[bb]; vb = v[bb]; }
+            }
+            double xa = 0.0, xb = 0.0;
+            if (emit) {
+                // the log is read 32 entries at a time, one entry per lane (coalesced), and broadcast by shuffle:
+                // every lane applies every entry, newest first, to its own bins
+                for (int top = log.n; top > 0; top -= 32) {
+                    int cnt = top < 32 ? top : 32;
+                    LogEntry mine;
+                    mine.op = 0; mine.table = 0; mine.v = 0.0;
+                    if (lane < cnt) mine = log.get(top - 1 - lane);
+                    for (int j = 0; j < cnt; ++j) {
+                        int op = __shfl_sync(RSB_FULL_MASK, mine.op, j);
+                        int tb = __shfl_sync(RSB_FULL_MASK, mine.table, j);
+                        double ev = __shfl_sync(RSB_FULL_MASK, mine.v, j);
+                        if (ha) xa = apply_entry(xa, op, tb, ev, sp, ba);
+                        if (hb) xb = apply_entry(xb, op, tb, ev, sp, bb);
+                    }
+                }
+            }
+            if (ha) {
+                double x = xa * w;              // spectrum.mul_scalar(projection_weight), observer.pyx:408
+                x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
+                welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
+            }
+            if (hb) {
+                double x = xb * w;
+                x = x * a.cam.sensitivity;
+                welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
+            }
         }
     }
 }

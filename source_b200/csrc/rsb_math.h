@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RSB_HD __host__ __device__ __forceinline__
@@ -134,6 +135,75 @@ RSB_HD bool box_intersect(const double* box, const V3& o, const V3& d, double* f
     if (f > b) return false;
     if ((f < 0.0) && (b < 0.0)) return false;
     return true;
+}
+
+// Same slab test with the reciprocal `1.0 / direction` supplied by the caller: every world-space AABB test of
+// one ray divides by the same three direction components, so the quotients are computed once per ray and
+// reused -- bit-identical to recomputing them per box (boundingbox.pyx:208-209).
+RSB_HD void box_slab_inv(double origin, double direction, double reciprocal, double lower, double upper, double* front, double* back) {
+    double tmin, tmax;
+    if (direction != 0.0) {
+        if (direction > 0) {
+            tmin = (lower - origin) * reciprocal;
+            tmax = (upper - origin) * reciprocal;
+        } else {
+            tmin = (upper - origin) * reciprocal;
+            tmax = (lower - origin) * reciprocal;
+        }
+    } else {
+        if (origin < lower) { tmin = -RSB_INF; tmax = -RSB_INF; }
+        else if (origin > upper) { tmin = RSB_INF; tmax = RSB_INF; }
+        else { tmin = -RSB_INF; tmax = RSB_INF; }
+    }
+    if (tmin > *front) *front = tmin;
+    if (tmax < *back) *back = tmax;
+}
+
+RSB_HD V3 ray_reciprocals(const V3& d) { return v3(1.0 / d.x, 1.0 / d.y, 1.0 / d.z); }
+
+// ---- exact division through a precomputed reciprocal ------------------------------------------------------
+// For r = RN(1/d), q = x*r followed by the FMA residual correction q += r * fma(-d, q, x) yields the correctly
+// rounded x/d (Markstein 1990) -- i.e. the very bits of the IEEE division the reference executes -- unless d's
+// significand is all ones or an intermediate leaves the normal range.  The kd traversal divides by the same
+// three direction components at every branch node (kdtree3d.pyx:672), so the reciprocals are formed once per
+// ray; where exactness cannot be guaranteed the recipe falls back to a true division.
+RSB_HD double exact_recip(double d) {
+    double r = 1.0 / d;
+    unsigned long long bits;
+    memcpy(&bits, &d, 8);
+    double ar = fabs(r);
+    if ((bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL || !(ar > 1e-250 && ar < 1e250)) return 0.0;   // 0 = "divide"
+    return r;
+}
+
+RSB_HD double div_exact(double x, double d, double r) {
+    double ax = fabs(x);
+    if (r == 0.0 || !(ax > 1e-250 && ax < 1e250)) return x / d;
+    double q = x * r;
+    double e = fma(-d, q, x);
+    q = fma(e, r, q);
+    e = fma(-d, q, x);
+    q = fma(e, r, q);
+    return q;
+}
+
+RSB_HD V3 exact_reciprocals(const V3& d) { return v3(exact_recip(d.x), exact_recip(d.y), exact_recip(d.z)); }
+
+RSB_HD bool box_intersect_inv(const double* box, const V3& o, const V3& d, const V3& inv, double* front, double* back) {
+    double f = -RSB_INF, b = RSB_INF;
+    box_slab_inv(o.x, d.x, inv.x, box[0], box[3], &f, &b);
+    box_slab_inv(o.y, d.y, inv.y, box[1], box[4], &f, &b);
+    box_slab_inv(o.z, d.z, inv.z, box[2], box[5], &f, &b);
+    *front = f;
+    *back = b;
+    if (f > b) return false;
+    if ((f < 0.0) && (b < 0.0)) return false;
+    return true;
+}
+
+RSB_HD bool box_hit_inv(const double* box, const V3& o, const V3& d, const V3& inv) {
+    double f, b;
+    return box_intersect_inv(box, o, d, inv, &f, &b);
 }
 
 // raysect/core/boundingbox.pyx:146-158 (hit)

@@ -262,6 +262,16 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     return 0;
 }
 
+int hs_div_count(int64_t n, const double* x, const int32_t* d, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = div_count(x[i], (double)d[i], 1.0 / (double)d[i]);
+    return 0;
+}
+
+int hs_div_exact(int64_t n, const double* x, const double* d, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = div_exact(x[i], d[i], exact_recip(d[i]));
+    return 0;
+}
+
 int hs_frame_combine(int64_t n_pixels_total, int32_t frame_bins, int32_t slice_offset, int32_t slice_bins, const double* mean,
                      const double* variance, int32_t samples, double* fmean, double* fvar, int32_t* fsamples) {
     for (int64_t p = 0; p < n_pixels_total; ++p)

@@ -120,3 +120,47 @@ def test_combine_samples_matches_host_build_of_device_code():
         np.testing.assert_array_equal(nt, gs[:, off:off + sb])
         np.testing.assert_array_equal(mt, gm[:, off:off + sb])
         np.testing.assert_array_equal(vt, gv[:, off:off + sb])
+
+
+def test_reciprocal_division_is_exact_ieee_division():
+    """div_count (rsb_path.h): x / n via reciprocal + FMA residual correction == IEEE x / n, incl. edge values"""
+    import ctypes as C
+    import hostsim_api
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    x = rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n)
+    x[:8] = [0.0, -0.0, 1e-300, -1e-300, 1e300, np.inf, -np.inf, np.nan]
+    d = rng.integers(1, 5000, n).astype(np.int32)
+    d[n // 2:] = rng.integers(1, 2_000_000_000, n - n // 2)
+    out = np.zeros(n)
+    lib = hostsim_api.lib()
+    lib.hs_div_count.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_div_count(n, x.ctypes.data, d.ctypes.data, out.ctypes.data)
+    with np.errstate(all="ignore"):
+        ref = x / d
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)) or np.array_equal(
+        out[~np.isnan(ref)].view(np.uint64), ref[~np.isnan(ref)].view(np.uint64))
+
+
+def test_exact_reciprocal_division_general_divisors():
+    """div_exact/exact_recip (rsb_math.h), used for the kd plane distance: identical bits to x / d for arbitrary
+    doubles, including divisors with an all-ones significand, denormals, infinities and zeros (fallback path)"""
+    import ctypes as C
+    import hostsim_api
+    rng = np.random.default_rng(5)
+    n = 3_000_000
+    x = rng.standard_normal(n) * 10.0 ** rng.uniform(-40, 40, n)
+    d = rng.standard_normal(n) * 10.0 ** rng.uniform(-40, 40, n)
+    allones = np.array([0x3FFFFFFFFFFFFFFF, 0x400FFFFFFFFFFFFF, 0xBFEFFFFFFFFFFFFF], dtype=np.uint64).view(np.float64)
+    d[:3] = allones
+    d[3:9] = [5e-324, 1e-310, np.inf, -np.inf, 1e308, -1e-308]
+    x[9:15] = [0.0, -0.0, np.inf, 1e-320, 1e308, -1e300]
+    out = np.zeros(n)
+    lib = hostsim_api.lib()
+    lib.hs_div_exact.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_div_exact(n, x.ctypes.data, d.ctypes.data, out.ctypes.data)
+    with np.errstate(all="ignore"):
+        ref = x / d
+    ok = ~np.isnan(ref)
+    assert np.array_equal(out[ok].view(np.uint64), ref[ok].view(np.uint64))
+    assert np.all(np.isnan(out[~ok]))
