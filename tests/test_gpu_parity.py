@@ -180,3 +180,58 @@ def test_frame_combine_kernel_matches_numpy(device):
     np.testing.assert_array_equal(gs.cpu().numpy()[:, off:off + sb], nt)
     np.testing.assert_array_equal(gm.cpu().numpy()[:, off:off + sb], mt)
     np.testing.assert_array_equal(gv.cpu().numpy()[:, off:off + sb], vt)
+
+
+def test_million_triangle_mesh_properties(make_backend):
+    """config-4 geometry at full size: Cornell box + a 1.3M-triangle closed mesh (tree built by this package's SAH
+    builder).  The oracle cannot finish this size in seconds, so: (1) the CUDA traversal must equal the host build of
+    the same source on a sample of rays, bit for bit; (2) size-independent properties: every hit point lies on the mesh
+    surface shell, rays started inside the mesh report exiting hits, contains() agrees with the radial shell."""
+    import time
+    import hostsim_api
+    import scenes
+    import source_b200 as api
+    from source_b200.flatten import flatten_world
+    verts, tris, normals = scenes.icosphere(8, radius=0.45, bumps=0.1)      # 20 * 4^8 = 1,310,720 triangles
+    assert len(tris) > 1_000_000
+    t0 = time.time()
+
+    def extra(a, w):
+        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1),
+               material=a.Lambert(a.ConstantSF(0.7)))
+    world = scenes.cornell_box(api, glass=False, extra=extra)
+    flat = flatten_world(world)
+    print("1.3M-triangle kd build + flatten: %.1f s" % (time.time() - t0))
+    be = make_backend(flat)
+    rng = np.random.default_rng(12)
+    n = 60000
+    o = np.tile(np.array([0.0, 0.0, -3.3]), (n, 1))
+    tgt = np.array([0.1, -0.5, 0.1]) + rng.uniform(-0.6, 0.6, (n, 3))
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    r = be.hit_batch(o, d, geometry=True)
+    mesh_id = len(world.primitives) - 1
+    on_mesh = r.primitive == mesh_id
+    assert on_mesh.sum() > 10000
+    # hit points (mesh-local == translated world) lie in the radial shell of the bumpy sphere
+    rad = np.linalg.norm(r.geometry[on_mesh, 0:3], axis=1)
+    assert rad.min() > 0.45 * 0.88 and rad.max() < 0.45 * 1.12
+    assert np.all(r.exiting[on_mesh] == 0)
+    np.testing.assert_allclose(r.uvw[on_mesh].sum(axis=1), 1.0, atol=1e-5)
+    # same source compiled for the host: bit-exact on a sub-sample
+    k = 4000
+    h = hostsim_api.HostScene(flat).hit_batch(o[:k], d[:k])
+    for f in ("primitive", "distance", "sub", "exiting", "geometry", "uvw"):
+        np.testing.assert_array_equal(getattr(r, f)[:k], getattr(h, f))
+    # rays from the mesh centre leave through the surface: exiting hits at the shell radius
+    c = np.array([0.1, -0.5, 0.1])
+    dirs = rng.normal(size=(5000, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    r2 = be.hit_batch(np.tile(c, (5000, 1)), dirs, geometry=True)
+    assert np.all(r2.primitive == mesh_id) and np.all(r2.exiting == 1)
+    assert r2.distance.min() > 0.45 * 0.88 and r2.distance.max() < 0.45 * 1.12
+    # contains: centre region inside, far points outside
+    pts = np.r_[c + rng.uniform(-0.2, 0.2, (2000, 3)), c + np.array([0.0, 0.0, 0.7]) + rng.uniform(-0.1, 0.1, (2000, 3))]
+    cnt, prims = be.contains_batch(pts, 4)
+    assert np.all(cnt[:2000] == 1) and np.all(prims[:2000, 0] == mesh_id) and np.all(cnt[2000:] == 0)
+    be.close()
