@@ -38,6 +38,7 @@ struct DeviceScene {
     int32_t n_materials = 0;
     std::vector<int32_t> mat_type, mat_transmission_only;
     int32_t stage_bytes = 0;   // shared memory needed to stage world tree + prims (0 = do not stage)
+    bool has_mesh = false, has_csg = false;
 };
 
 struct Context {
@@ -273,6 +274,10 @@ int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
     int rc = upload(ds, ps.prims.data(), ps.prims.size(), &ds->sc.prims);
     if (rc) return bail(rc);
     ds->sc.n_prims = (int32_t)ps.prims.size();
+    for (const Prim& pr : ps.prims) {
+        if (pr.type == PRIM_MESH) ds->has_mesh = true;
+        if (pr.type >= PRIM_UNION) ds->has_csg = true;
+    }
     ds->sc.n_world = ps.n_world;
     rc = upload_tree(ds, ps.world, &ds->sc.world);
     if (rc) return bail(rc);
@@ -542,7 +547,7 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     return (c.off + 255) & ~(size_t)255;
 }
 
-template <int RNGMODE, bool COUNT>
+template <int RNGMODE, bool COUNT, int FEAT>
 int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st, bool time_trace) {
     const int threads = 128;
     const int grid = (a.n_slots + threads - 1) / threads;
@@ -550,8 +555,8 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int regen_grid = std::max(1, std::min((grid + 3) / 4, c->sm_count * 8));
     const int shade_grid = grid;
     if (smem_shade > 48 * 1024) {
-        RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
-        RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     }
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
@@ -584,12 +589,12 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b], s));
             }
-            k_wf_trace<RNGMODE, COUNT><<<grid, threads, smem_scene, s>>>(a);
+            k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
             if (time_trace) {
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b + 1], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b + 1], s));
             }
-            k_wf_shade<RNGMODE, COUNT><<<shade_grid, threads, smem_shade, s>>>(a);
+            k_wf_shade<RNGMODE, COUNT, FEAT><<<shade_grid, threads, smem_shade, s>>>(a);
             k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, s>>>(a);
             k_wf_regen<RNGMODE, COUNT><<<regen_grid, threads, 0, s>>>(a);
         }
@@ -778,10 +783,14 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
         RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(unsigned long long), st));
         RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
         RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
-        if (mt) rc = count ? run_wavefront<RNG_MT19937_64, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-                           : run_wavefront<RNG_MT19937_64, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
-        else rc = count ? run_wavefront<RNG_PHILOX, true>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-                        : run_wavefront<RNG_PHILOX, false>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace);
+        // kernels are instantiated for "analytic primitives only" and for "everything" (meshes and CSG)
+#define RSB_RUN(R, C, F) run_wavefront<R, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+        const bool plain = !ds->has_mesh && !ds->has_csg;
+        if (mt) rc = count ? (plain ? RSB_RUN(RNG_MT19937_64, true, 0) : RSB_RUN(RNG_MT19937_64, true, RSB_FEAT_ALL))
+                           : (plain ? RSB_RUN(RNG_MT19937_64, false, 0) : RSB_RUN(RNG_MT19937_64, false, RSB_FEAT_ALL));
+        else rc = count ? (plain ? RSB_RUN(RNG_PHILOX, true, 0) : RSB_RUN(RNG_PHILOX, true, RSB_FEAT_ALL))
+                        : (plain ? RSB_RUN(RNG_PHILOX, false, 0) : RSB_RUN(RNG_PHILOX, false, RSB_FEAT_ALL));
+#undef RSB_RUN
     }
     if (rc) return rc;
     {

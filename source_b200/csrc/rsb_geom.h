@@ -879,7 +879,14 @@ RSB_HD_NOINLINE void csg_geometry(const Scene& sc, int top, const CsgEvent& ev, 
 // ---------------------------------------------------------------------------------------------
 // World.hit  (raysect/core/scenegraph/world.pyx:125-146 -> acceleration/kdtree.pyx:73-175)
 // ---------------------------------------------------------------------------------------------
-template <class Stats>
+// FEAT: scene features the instantiation must handle (bit 0: Mesh primitives, bit 1: CSG primitives).  The
+// wavefront kernels are instantiated per feature set, so that a scene of analytic primitives does not pay the
+// registers and instruction footprint of the nested mesh traversal and the CSG evaluator.
+#define RSB_FEAT_MESH 1
+#define RSB_FEAT_CSG 2
+#define RSB_FEAT_ALL 3
+
+template <class Stats, int FEAT = RSB_FEAT_ALL>
 struct WorldLeaf {
     const Scene* sc;
     V3 o, d;
@@ -902,7 +909,7 @@ struct WorldLeaf {
                 best->mesh_node = -1;
                 found = true;
             }
-        } else if (p.type == PRIM_MESH) {
+        } else if ((FEAT & RSB_FEAT_MESH) && p.type == PRIM_MESH) {
             V3 lo = xform_point(p.to_local, o);
             V3 ld = xform_vector(p.to_local, d);
             MeshHit mh;
@@ -913,7 +920,7 @@ struct WorldLeaf {
                 best->u = mh.u; best->v = mh.v; best->w = mh.w;
                 found = true;
             }
-        } else {
+        } else if ((FEAT & RSB_FEAT_CSG) && p.type >= PRIM_UNION) {
             CsgEvent ev;
             if (csg_first_hit(*sc, id, o, d, max_distance, &ev) && ev.t <= distance) {
                 distance = ev.t;
@@ -948,9 +955,9 @@ struct WorldLeaf {
 };
 
 // Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries.
-template <class Stats>
+template <int FEAT = RSB_FEAT_ALL, class Stats>
 RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats) {
-    WorldLeaf<Stats> leaf;
+    WorldLeaf<Stats, FEAT> leaf;
     leaf.sc = &sc;
     leaf.o = o;
     leaf.d = d;
@@ -972,6 +979,7 @@ RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_dist
 }
 
 // Intersection geometry for a HitRec, in the world-level primitive's local space.
+template <int FEAT = RSB_FEAT_ALL>
 RSB_HD void world_hit_geometry(const Scene& sc, const V3& o, const V3& d, const HitRec& rec, Isect* is) {
     const Prim& p = sc.prims[rec.prim];
     is->t = rec.t;
@@ -983,13 +991,13 @@ RSB_HD void world_hit_geometry(const Scene& sc, const V3& o, const V3& d, const 
         V3 lo = xform_point(p.to_local, o);
         V3 ld = xform_vector(p.to_local, d);
         analytic_geometry(p.type, p.params, lo, ld, rec.t, rec.code, is);
-    } else if (p.type == PRIM_MESH) {
+    } else if ((FEAT & RSB_FEAT_MESH) && p.type == PRIM_MESH) {
         V3 lo = xform_point(p.to_local, o);
         V3 ld = xform_vector(p.to_local, d);
         MeshHit mh;
         mh.t = rec.t; mh.tri = rec.code; mh.node = rec.mesh_node; mh.u = rec.u; mh.v = rec.v; mh.w = rec.w;
         mesh_geometry(sc.meshes[p.mesh], lo, ld, mh, is);
-    } else {
+    } else if ((FEAT & RSB_FEAT_CSG) && p.type >= PRIM_UNION) {
         CsgEvent ev;
         ev.t = rec.t; ev.leaf = rec.leaf; ev.code = (int16_t)rec.code;
         ev.flip = (int8_t)(rec.flip & 1);
@@ -999,11 +1007,13 @@ RSB_HD void world_hit_geometry(const Scene& sc, const V3& o, const V3& d, const 
 }
 
 // Primitive.contains for a world-level row behind BoundPrimitive.contains (boundprimitive.pyx:62-66)
-template <class Stats>
+template <int FEAT = RSB_FEAT_ALL, class Stats>
 RSB_HD bool prim_contains(const Scene& sc, int id, const V3& pt, KdStackEntry* stack, Stats& stats) {
     const Prim& p = sc.prims[id];
     if (!box_contains(p.bbox, pt)) return false;
     if (p.type <= PRIM_CONE) return analytic_contains(p.type, p.params, xform_point(p.to_local, pt));
+    if (!(FEAT & RSB_FEAT_MESH) && p.type == PRIM_MESH) return false;
+    if (!(FEAT & RSB_FEAT_CSG) && p.type >= PRIM_UNION) return false;
     if (p.type == PRIM_MESH) {
         const Mesh& m = sc.meshes[p.mesh];
         if (!m.closed) return false;   // mesh.pyx:1290-1292

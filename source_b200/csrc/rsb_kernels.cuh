@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
 // 1 thread = 1 slot.  (A persistent-lane variant, where a lane picks up its next slot as soon as its ray
 // finishes, was measured SLOWER on the Cornell scene -- 208 vs 129 us per 262k-ray wave, 9.1 vs 10.0 active
 // lanes per instruction: iteration counts per ray vary little here, and the refill path diverges.)
-template <int RNGMODE, bool COUNT>
+template <int RNGMODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
         KdStackEntry stack[RSB_KD_STACK];
         HitRec rec;
         double normalisation;
-        int r = path_trace(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats);
+        int r = path_trace<FEAT>(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats);
         wf_store_rng<RNGMODE>(a, slot, rng);
         hits = 1;
         if (r == PATH_CONTINUE) {
@@ -458,22 +458,27 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
             list = 4;                                                // ended list
         }
     }
-    // compact into the five lists with one atomic per (warp, list) instead of one per lane
+    // compact into the five lists: ballots first, then lanes 0..4 issue the five atomics of the warp TOGETHER
+    // (one round trip instead of five back-to-back ones), then every lane takes its slot in its list
     __syncwarp();
-#pragma unroll
-    for (int l = 0; l < 5; ++l) {
-        unsigned m = __ballot_sync(RSB_FULL_MASK, list == l);
-        if (m == 0) continue;
+    {
         const int lane = threadIdx.x & 31;
+        unsigned masks[5];
+#pragma unroll
+        for (int l = 0; l < 5; ++l) masks[l] = __ballot_sync(RSB_FULL_MASK, list == l);
         unsigned int base = 0;
-        if (lane == __ffs(m) - 1) {
-            unsigned int* ctr = (l < 4) ? &a.st.n_hit[l] : &a.st.n_ended[a.wave & 1];
-            base = atomicAdd(ctr, (unsigned int)__popc(m));
+        if (lane < 5) {
+            unsigned mine = lane == 0 ? masks[0] : lane == 1 ? masks[1] : lane == 2 ? masks[2] : lane == 3 ? masks[3] : masks[4];
+            if (mine) {
+                unsigned int* ctr = (lane < 4) ? &a.st.n_hit[lane] : &a.st.n_ended[a.wave & 1];
+                base = atomicAdd(ctr, (unsigned int)__popc(mine));
+            }
         }
-        base = __shfl_sync(RSB_FULL_MASK, base, __ffs(m) - 1);
-        if (list == l) {
-            unsigned int k = base + __popc(m & ((1u << lane) - 1));
-            if (l < 4) a.st.hit_list[(size_t)l * P + k] = slot;
+        unsigned int b = __shfl_sync(RSB_FULL_MASK, base, list < 0 ? 0 : list);
+        if (list >= 0) {
+            unsigned m = list == 0 ? masks[0] : list == 1 ? masks[1] : list == 2 ? masks[2] : list == 3 ? masks[3] : masks[4];
+            unsigned int k = b + __popc(m & ((1u << lane) - 1));
+            if (list < 4) a.st.hit_list[(size_t)list * P + k] = slot;
             else a.st.ended[(size_t)(a.wave & 1) * P + k] = slot;
         }
     }
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
 // 1 thread = 1 hit slot.  The trace kernel compacts hit slots into one list per material family; every CTA
 // walks the lists in turn (Lambert, dielectric, emitter, absorber), so a warp executes ONE BSDF at a time
 // while the whole GPU stays busy (separate launches per family left the smaller lists under-occupied).
-template <int RNGMODE, bool COUNT, int MAT>
+template <int RNGMODE, bool COUNT, int MAT, int FEAT>
 __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, const Spectral& sp, KdStackEntry* stack,
                                               typename StatsSel<COUNT>::type& stats) {
     const size_t P = (size_t)a.n_slots;
@@ -517,7 +522,7 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         log.capacity = a.log_capacity;
         log.n = a.st.log_n[slot];
         log.overflow = 0;
-        int r = path_shade<MAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
+        int r = path_shade<MAT, FEAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
         wf_store_rng<RNGMODE>(a, slot, rng);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
@@ -534,7 +539,7 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
     }
 }
 
-template <int RNGMODE, bool COUNT>
+template <int RNGMODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
@@ -550,10 +555,10 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
     }
     typename StatsSel<COUNT>::type stats;
     KdStackEntry stack[RSB_KD_STACK];
-    wf_shade_list<RNGMODE, COUNT, MAT_LAMBERT>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_DIELECTRIC>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_EMITTER>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_ABSORBER>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_LAMBERT, FEAT>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_DIELECTRIC, FEAT>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_EMITTER, FEAT>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_ABSORBER, FEAT>(a, sc, sp, stack, stats);
     if (COUNT) {
         __syncwarp();
         flush_stats(stats, a.counters, true);

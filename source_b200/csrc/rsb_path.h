@@ -157,7 +157,7 @@ RSB_HD double important_direction_pdf(const Scene& sc, const V3& origin, const V
 // world.contains(ray.origin) -> the one world leaf holding the origin, items in leaf order; each
 // containing primitive's material.evaluate_volume(start = world hit point, end = ray origin).
 // Entries are pushed in REVERSE so that the backward replay applies them in forward order.
-template <class Stats>
+template <int FEAT = RSB_FEAT_ALL, class Stats>
 RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, const V3& w_hit,
                         KdStackEntry* stack, PathLog& log, Stats& stats) {
     int offset, count;
@@ -167,7 +167,7 @@ RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, c
         const Material& m = sp.mats[sc.prims[id].material];
         if (m.type != MAT_DIELECTRIC) continue;   // Lambert/emitter/absorber: evaluate_volume is the identity
         stats.prim_test();
-        if (!prim_contains(sc, id, origin, stack, stats)) continue;
+        if (!prim_contains<FEAT>(sc, id, origin, stack, stats)) continue;
         stats.table_read();
         // length = start_point.vector_to(end_point).get_length()
         V3 v = v3(origin.x - w_hit.x, origin.y - w_hit.y, origin.z - w_hit.z);
@@ -198,7 +198,7 @@ RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
 //               then _sample_volumes and the roulette normalisation (ray.pyx:395-401)
 // PATH_CONTINUE: ps holds the daughter ray.  PATH_EMITTED: the log now ends with a LOG_EMIT entry.
 // PATH_ZERO: the path's spectrum is identically zero.
-template <class Stats>
+template <int FEAT = RSB_FEAT_ALL, class Stats>
 RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps, Rng& rng, KdStackEntry* stack,
                       HitRec* rec, double* normalisation, Stats& stats) {
     // -- Russian roulette (ray.pyx:380-388)
@@ -209,21 +209,21 @@ RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps
         *normalisation = 1 / (1 - cfg.extinction_prob);
     }
     // -- closest hit (ray.pyx:391-393)
-    if (!world_hit(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
+    if (!world_hit<FEAT>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
     return PATH_CONTINUE;
 }
 
 // MATSEL: -1 = dispatch on the material at run time (serial harness); otherwise the caller guarantees the
 // hit primitive's material type (the wavefront shade kernels run one launch per material family, so the
 // other families' code is compiled out and the warp stays converged).
-template <int MATSEL, class Stats>
+template <int MATSEL, int FEAT = RSB_FEAT_ALL, class Stats>
 RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg, PathState& ps, const HitRec& rec,
                       double normalisation, Rng& rng, KdStackEntry* stack, PathLog& log, Stats& stats) {
     const V3 o = ps.o, d = ps.d;
     const int depth = ps.depth;
     {
         Isect is;
-        world_hit_geometry(sc, o, d, rec, &is);
+        world_hit_geometry<FEAT>(sc, o, d, rec, &is);
         const Prim& prim = sc.prims[rec.prim];
         const Material& mat = sp.mats[prim.material];
         const int mtype = MATSEL >= 0 ? MATSEL : mat.type;
@@ -233,7 +233,7 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
         // entries of this segment, pushed in reverse application order: normalisation, volumes, surface
         if (normalisation != 1.0) log.push(LOG_MULS, 0, normalisation);
         V3 w_hit = xform_point(p2w, is.hit);
-        log_volumes(sc, sp, o, w_hit, stack, log, stats);
+        log_volumes<FEAT>(sc, sp, o, w_hit, stack, log, stats);
 
         if (mtype == MAT_EMITTER) {
             log.push(LOG_EMIT, mat.table, mat.scale);
