@@ -689,20 +689,27 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     }
     size_t mat_bytes = (((size_t)nm * sizeof(Material) + 15) / 16) * 16;
     size_t tab_bytes = (((size_t)nm * spectral->bins * 8 + 15) / 16) * 16;
+    size_t tab_alloc = (size_t)nm * spectral->bins * 16 + 16;
     if (c->mats_cap < mat_bytes) {
         cudaFree(c->d_mats);
         c->d_mats = nullptr; c->mats_cap = 0;
         RSB_CUDA(cudaMalloc(&c->d_mats, mat_bytes));
         c->mats_cap = mat_bytes;
     }
-    if (c->tables_cap < tab_bytes) {
+    if (c->tables_cap < tab_alloc) {
         cudaFree(c->d_tables);
         c->d_tables = nullptr; c->tables_cap = 0;
-        RSB_CUDA(cudaMalloc(&c->d_tables, tab_bytes));
-        c->tables_cap = tab_bytes;
+        RSB_CUDA(cudaMalloc(&c->d_tables, tab_alloc));
+        c->tables_cap = tab_alloc;
     }
     RSB_CUDA(cudaMemcpyAsync(c->d_mats, mats.data(), (size_t)nm * sizeof(Material), cudaMemcpyHostToDevice, st));
-    RSB_CUDA(cudaMemcpyAsync(c->d_tables, spectral->tables, (size_t)nm * spectral->bins * 8, cudaMemcpyHostToDevice, st));
+    // tables, followed by their natural logs (exp(length * ln T) form of the Beer-Lambert pow in the replay)
+    std::vector<double> both((size_t)nm * spectral->bins * 2);
+    for (size_t i = 0; i < (size_t)nm * spectral->bins; ++i) {
+        both[i] = spectral->tables[i];
+        both[(size_t)nm * spectral->bins + i] = log(spectral->tables[i]);
+    }
+    RSB_CUDA(cudaMemcpyAsync(c->d_tables, both.data(), both.size() * 8, cudaMemcpyHostToDevice, st));
     // the two host staging buffers above are stack/heap temporaries: make the copies complete before returning
     RSB_CUDA(cudaStreamSynchronize(st));
 
@@ -711,6 +718,7 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     a.sc = ds->sc;
     a.sp.mats = c->d_mats;
     a.sp.tables = c->d_tables;
+    a.sp.tables_ln = c->d_tables + (size_t)nm * spectral->bins;
     a.sp.bins = spectral->bins;
     a.sp.n_materials = nm;
     a.cfg.bins = config->bins;
@@ -742,10 +750,10 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     a.n_items = ds->n_world_items;
     a.staged = ds->stage_bytes ? 1 : 0;
     size_t smem_scene = ds->stage_bytes, smem_shade = ds->stage_bytes, smem_tables = 0;
-    if (smem_shade + mat_bytes <= kMaxStageBytes && tab_bytes <= kMaxStageBytes) {
+    if (smem_shade + mat_bytes <= kMaxStageBytes && 2 * tab_bytes <= kMaxStageBytes) {
         a.tables_staged = 1;
         smem_shade += mat_bytes;
-        smem_tables = tab_bytes;
+        smem_tables = 2 * tab_bytes;
     }
     // a path of D segments logs at most 3 surface + 1 roulette entries per segment plus one per enclosing
     // dielectric; budget 6 per segment

@@ -572,10 +572,12 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     extern __shared__ __align__(16) unsigned char smem[];
     Spectral sp = a.sp;
     if (a.tables_staged) {
-        int tab_bytes = ((sp.n_materials * sp.bins * 8 + 15) / 16) * 16;
+        // tables and their logs are contiguous in HBM: [n_materials][bins] x 2
+        int tab_bytes = ((sp.n_materials * sp.bins * 16 + 15) / 16) * 16;
         copy16(smem, a.sp.tables, tab_bytes);
         __syncthreads();
         sp.tables = reinterpret_cast<const double*>(smem);
+        sp.tables_ln = sp.tables + (size_t)sp.n_materials * sp.bins;
     }
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;

@@ -176,6 +176,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     Spectral sp;
     sp.mats = mats.data();
     sp.tables = spectral->tables;
+    sp.tables_ln = nullptr;
     sp.bins = spectral->bins;
     sp.n_materials = nm;
     RayConfig cfg;
