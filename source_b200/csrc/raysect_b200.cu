@@ -352,16 +352,17 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 16);
     size_t smem = ds->stage_bytes;
-    if (count) {
-        RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hit_batch<true><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance,
-                                                  out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters);
-    } else {
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hit_batch<false><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance,
-                                                   out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters);
-    }
+    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+    const bool plain = !ds->has_mesh && !ds->has_csg;
+#define RSB_LAUNCH_HIT(C, F)                                                                                              \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_hit_batch<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance, \
+                                                   out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters); \
+    } while (0)
+    if (count) { if (plain) RSB_LAUNCH_HIT(true, 0); else RSB_LAUNCH_HIT(true, RSB_FEAT_ALL); }
+    else { if (plain) RSB_LAUNCH_HIT(false, 0); else RSB_LAUNCH_HIT(false, RSB_FEAT_ALL); }
+#undef RSB_LAUNCH_HIT
     RSB_CUDA(cudaGetLastError());
     if (count) {
         int rc = read_counters(c, st);
@@ -436,18 +437,18 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 8);
     size_t smem = ds->stage_bytes;
-    if (count) {
-        RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hit_sweep<true><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2],
-                                                  target[0], target[1], target[2], half_window,
-                                                  (unsigned long long*)out_hits_dev, out_sum_t_dev, (unsigned long long*)out_xor_prim_dev, c->d_counters);
-    } else {
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hit_sweep<false><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2],
-                                                   target[0], target[1], target[2], half_window,
-                                                   (unsigned long long*)out_hits_dev, out_sum_t_dev, (unsigned long long*)out_xor_prim_dev, c->d_counters);
-    }
+    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
+    const bool plain = !ds->has_mesh && !ds->has_csg;
+#define RSB_LAUNCH_SWEEP(C, F)                                                                                            \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_hit_sweep<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2], \
+                                                   target[0], target[1], target[2], half_window, (unsigned long long*)out_hits_dev, out_sum_t_dev, \
+                                                   (unsigned long long*)out_xor_prim_dev, c->d_counters);             \
+    } while (0)
+    if (count) { if (plain) RSB_LAUNCH_SWEEP(true, 0); else RSB_LAUNCH_SWEEP(true, RSB_FEAT_ALL); }
+    else { if (plain) RSB_LAUNCH_SWEEP(false, 0); else RSB_LAUNCH_SWEEP(false, RSB_FEAT_ALL); }
+#undef RSB_LAUNCH_SWEEP
     RSB_CUDA(cudaGetLastError());
     if (count) {
         int rc = read_counters(c, st);

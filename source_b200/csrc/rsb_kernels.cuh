@@ -108,7 +108,7 @@ __device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128)
 k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __restrict__ origins,
             const double* __restrict__ directions, const double* __restrict__ max_distance,
@@ -125,10 +125,10 @@ k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __rest
         V3 d = v3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
         double md = max_distance ? max_distance[i] : RSB_INF;
         HitRec rec;
-        bool hit = world_hit(sc, o, d, md, stack, &rec, stats);
+        bool hit = world_hit<FEAT>(sc, o, d, md, stack, &rec, stats);
         if (hit) {
             Isect is;
-            world_hit_geometry(sc, o, d, rec, &is);
+            world_hit_geometry<FEAT>(sc, o, d, rec, &is);
             out_prim[i] = rec.prim;
             out_t[i] = rec.t;
             out_sub[i] = rec.code;
@@ -159,7 +159,7 @@ k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __rest
 }
 
 // rays from `origin` toward target + (jx, jy, 0)*half_window, (jx, jy) uniform in [-1, 1) from Philox(seed, index)
-template <bool COUNT>
+template <bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128)
 k_hit_sweep(Scene sc, int n_items, int staged, long long n, long long first_index, unsigned long long seed,
             double ox, double oy, double oz, double tx, double ty, double tz, double half_window,
@@ -180,7 +180,7 @@ k_hit_sweep(Scene sc, int n_items, int staged, long long n, long long first_inde
         V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
         V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
         HitRec rec;
-        if (world_hit(sc, o, d, RSB_INF, stack, &rec, stats)) {
+        if (world_hit<FEAT>(sc, o, d, RSB_INF, stack, &rec, stats)) {
             hits += 1;
             sum_t += rec.t;
             xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + i);
