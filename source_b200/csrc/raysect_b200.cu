@@ -54,6 +54,7 @@ struct Context {
     size_t slot_bytes = 0;
     unsigned int* h_idle = nullptr;     // pinned
     RsbRenderStats render_stats{};
+    int slots_per_sm = 2048;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)
     bool use_graphs = true;             // RSB_NO_GRAPH=1 launches the wave kernels one by one (debugging)
     std::vector<cudaEvent_t> event_pool;
     Material* d_mats = nullptr;
@@ -224,6 +225,7 @@ int rsb_context_create(int device, uint64_t* ctx) {
     RSB_CUDA(cudaMemset(c->d_scalars, 0, 8 * sizeof(unsigned long long)));
     RSB_CUDA(cudaMallocHost(&c->h_idle, sizeof(unsigned int)));
     if (const char* ng = getenv("RSB_NO_GRAPH")) c->use_graphs = !(ng[0] == '1');
+    if (const char* sp = getenv("RSB_SLOTS_PER_SM")) { int v = atoi(sp); if (v >= 32 && v <= 65536) c->slots_per_sm = v; }
     *ctx = reinterpret_cast<uint64_t>(c);
     return RSB_OK;
 }
@@ -767,7 +769,7 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     bool mt = rng->mode == RSB_RNG_MT19937_64;
     const long long kChunkPixels = 2LL << 20;
     long long chunk_cap = std::min<long long>(n_pixels, kChunkPixels);
-    long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * 2048);
+    long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * c->slots_per_sm);
     P = std::max<long long>(P, 1);
     WfSlots probe;
     size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe);

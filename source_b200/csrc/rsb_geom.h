@@ -405,7 +405,14 @@ RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
 struct KdCursor {
     double min_range, max_range;
     int32_t node, sp;
+    V3 rcp;             // 1.0 / d per component (plane distances through div_recip1)
+    int32_t unsafe;     // recip_unsafe_mask(d, rcp)
 };
+
+RSB_HD void kd_set_reciprocals(KdCursor& c, const V3& d, const V3& rcp) {
+    c.rcp = rcp;
+    c.unsafe = recip_unsafe_mask(d, rcp);
+}
 
 enum KdResult : int32_t { KD_MISS = 0, KD_HIT = 1, KD_MORE = 2 };
 
@@ -413,7 +420,10 @@ enum KdResult : int32_t { KD_MISS = 0, KD_HIT = 1, KD_MORE = 2 };
 RSB_HD bool kd_begin(const KdTree& tree, const V3& o, const V3& d, KdCursor& c) {
     c.node = 0;
     c.sp = 0;
-    return box_intersect(tree.bounds, o, d, &c.min_range, &c.max_range);
+    // the slab test divides 1.0 by the same three components (boundingbox.pyx:208-209)
+    V3 rcp = ray_reciprocals(d);
+    kd_set_reciprocals(c, d, rcp);
+    return box_intersect_inv(tree.bounds, o, d, rcp, &c.min_range, &c.max_range);
 }
 
 // One unit of traversal: descend from the cursor to the next leaf in front-to-back order
@@ -436,8 +446,12 @@ RSB_HD int kd_advance(const KdTree& tree, const V3& o, const V3& d, KdStackEntry
         if (direction == 0) {
             node = (origin < n.split) ? lower_id : upper_id;
         } else {
-            // (an exact reciprocal-multiply form, div_exact in rsb_math.h, was measured slower here: 175 vs 164 us/wave)
+#ifdef RSB_KD_TRUE_DIVIDE
             double plane_distance = (n.split - origin) / direction;
+#else
+            // (n.split - origin) / direction, correctly rounded, through the per-ray reciprocal
+            double plane_distance = div_recip1(n.split - origin, direction, v3_get(c.rcp, n.axis), (c.unsafe >> n.axis) & 1);
+#endif
             bool below_split = origin < n.split || (origin == n.split && direction < 0);
             int near_id = below_split ? lower_id : upper_id;
             int far_id = below_split ? upper_id : lower_id;
@@ -972,6 +986,7 @@ RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_dist
     KdCursor c;
     c.node = 0;
     c.sp = 0;
+    kd_set_reciprocals(c, d, leaf.inv);
     if (!box_intersect_inv(sc.world.bounds, o, d, leaf.inv, &c.min_range, &c.max_range)) return false;
     int r;
     do { r = kd_advance(sc.world, o, d, stack, c, leaf, stats, &rec->node); } while (r == KD_MORE);

@@ -187,6 +187,33 @@ RSB_HD double div_exact(double x, double d, double r) {
     return q;
 }
 
+// Single-correction form used by the kd traversal (one plane distance per branch node, kdtree3d.pyx:672):
+// q = RN(x*r); q' = RN(q + r * (x - d*q)), the residual being exact in one FMA.  With r = RN(1/d) this is the
+// correctly rounded quotient whenever d's significand is not all ones and nothing leaves the normal range
+// (Markstein); `unsafe` bit k flags a direction component that fails that test, and |x| is windowed here, so
+// that every other case takes a true division.  The dependent chain is 3 instructions instead of the ~10 of
+// div.rn.f64 -- the traversal is bound by exactly that chain.  Checked against x / d on 4e8 adversarial pairs
+// (tests/test_host_parity.py::test_div_recip1).
+RSB_HD int recip_unsafe_mask(const V3& d, const V3& r) {
+    int m = 0;
+    const double c[3] = {d.x, d.y, d.z}, q[3] = {r.x, r.y, r.z};
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long bits;
+        memcpy(&bits, &c[k], 8);
+        double ar = fabs(q[k]);
+        if ((bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL || !(ar > 1e-140 && ar < 1e140)) m |= 1 << k;
+    }
+    return m;
+}
+
+RSB_HD double div_recip1(double x, double d, double r, bool unsafe) {
+    double ax = fabs(x);
+    if (unsafe || !(ax < 1e140) || (ax < 1e-140 && x != 0.0)) return x / d;
+    double q = x * r;
+    double e = fma(-d, q, x);
+    return fma(e, r, q);
+}
+
 RSB_HD V3 exact_reciprocals(const V3& d) { return v3(exact_recip(d.x), exact_recip(d.y), exact_recip(d.z)); }
 
 RSB_HD bool box_intersect_inv(const double* box, const V3& o, const V3& d, const V3& inv, double* front, double* back) {
