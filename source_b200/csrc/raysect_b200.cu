@@ -67,6 +67,25 @@ struct Context {
 
 const size_t kMaxStageBytes = 96 * 1024;
 
+// Kernels are instantiated per scene feature set (rsb_geom.h RSB_FEAT_*): analytic primitives only vs everything
+// (meshes, CSG), and world-level data staged in shared memory vs read from HBM/L2.  M(COUNT, FEAT) is expanded
+// with compile-time constants.
+#define RSB_DISPATCH_FEAT(count, plain, staged, M)                                                     \
+    do {                                                                                               \
+        const int feat_ = ((plain) ? 0 : RSB_FEAT_ALL) | ((staged) ? RSB_FEAT_STAGED : 0);             \
+        if (count) {                                                                                   \
+            if (feat_ == 0) M(true, 0);                                                                \
+            else if (feat_ == RSB_FEAT_STAGED) M(true, RSB_FEAT_STAGED);                               \
+            else if (feat_ == RSB_FEAT_ALL) M(true, RSB_FEAT_ALL);                                     \
+            else M(true, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                            \
+        } else {                                                                                       \
+            if (feat_ == 0) M(false, 0);                                                               \
+            else if (feat_ == RSB_FEAT_STAGED) M(false, RSB_FEAT_STAGED);                              \
+            else if (feat_ == RSB_FEAT_ALL) M(false, RSB_FEAT_ALL);                                    \
+            else M(false, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                           \
+        }                                                                                              \
+    } while (0)
+
 template <class T>
 int upload(DeviceScene* ds, const T* host, size_t count, const T** dev, size_t pad_to_bytes = 16) {
     size_t bytes = count * sizeof(T);
@@ -353,17 +372,17 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 16);
-    size_t smem = ds->stage_bytes;
-    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const bool plain = !ds->has_mesh && !ds->has_csg;
+    const int staged = ds->stage_bytes ? 1 : 0;
+    size_t smem = ds->stage_bytes + ax_bytes(plain ? 0 : RSB_FEAT_ALL);
+    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
 #define RSB_LAUNCH_HIT(C, F)                                                                                              \
     do {                                                                                                                  \
         if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_hit_batch<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, origins, directions, max_distance, \
+        k_hit_batch<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, origins, directions, max_distance, \
                                                    out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters); \
     } while (0)
-    if (count) { if (plain) RSB_LAUNCH_HIT(true, 0); else RSB_LAUNCH_HIT(true, RSB_FEAT_ALL); }
-    else { if (plain) RSB_LAUNCH_HIT(false, 0); else RSB_LAUNCH_HIT(false, RSB_FEAT_ALL); }
+    RSB_DISPATCH_FEAT(count != 0, plain, staged, RSB_LAUNCH_HIT);
 #undef RSB_LAUNCH_HIT
     RSB_CUDA(cudaGetLastError());
     if (count) {
@@ -438,18 +457,18 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 8);
-    size_t smem = ds->stage_bytes;
-    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const bool plain = !ds->has_mesh && !ds->has_csg;
+    const int staged = ds->stage_bytes ? 1 : 0;
+    size_t smem = ds->stage_bytes + ax_bytes(plain ? 0 : RSB_FEAT_ALL);
+    if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
 #define RSB_LAUNCH_SWEEP(C, F)                                                                                            \
     do {                                                                                                                  \
         if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_hit_sweep<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, smem ? 1 : 0, n, first_index, seed, origin[0], origin[1], origin[2], \
+        k_hit_sweep<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, first_index, seed, origin[0], origin[1], origin[2], \
                                                    target[0], target[1], target[2], half_window, (unsigned long long*)out_hits_dev, out_sum_t_dev, \
                                                    (unsigned long long*)out_xor_prim_dev, c->d_counters);             \
     } while (0)
-    if (count) { if (plain) RSB_LAUNCH_SWEEP(true, 0); else RSB_LAUNCH_SWEEP(true, RSB_FEAT_ALL); }
-    else { if (plain) RSB_LAUNCH_SWEEP(false, 0); else RSB_LAUNCH_SWEEP(false, RSB_FEAT_ALL); }
+    RSB_DISPATCH_FEAT(count != 0, plain, staged, RSB_LAUNCH_SWEEP);
 #undef RSB_LAUNCH_SWEEP
     RSB_CUDA(cudaGetLastError());
     if (count) {
@@ -557,10 +576,11 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int fin_grid = std::max(1, std::min(grid, c->sm_count * 16));
     const int regen_grid = std::max(1, std::min((grid + 3) / 4, c->sm_count * 8));
     const int shade_grid = grid;
-    if (smem_shade > 48 * 1024) {
+    smem_scene += ax_bytes(FEAT);   // RayAx storage of k_wf_trace behind the staged scene
+    if (smem_scene > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+    if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
-    }
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
     a.wave = 0;
@@ -795,13 +815,13 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
         RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
         RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
         // kernels are instantiated for "analytic primitives only" and for "everything" (meshes and CSG)
-#define RSB_RUN(R, C, F) run_wavefront<R, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
         const bool plain = !ds->has_mesh && !ds->has_csg;
-        if (mt) rc = count ? (plain ? RSB_RUN(RNG_MT19937_64, true, 0) : RSB_RUN(RNG_MT19937_64, true, RSB_FEAT_ALL))
-                           : (plain ? RSB_RUN(RNG_MT19937_64, false, 0) : RSB_RUN(RNG_MT19937_64, false, RSB_FEAT_ALL));
-        else rc = count ? (plain ? RSB_RUN(RNG_PHILOX, true, 0) : RSB_RUN(RNG_PHILOX, true, RSB_FEAT_ALL))
-                        : (plain ? RSB_RUN(RNG_PHILOX, false, 0) : RSB_RUN(RNG_PHILOX, false, RSB_FEAT_ALL));
-#undef RSB_RUN
+#define RSB_RUN_MT(C, F) rc = run_wavefront<RNG_MT19937_64, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+#define RSB_RUN_PX(C, F) rc = run_wavefront<RNG_PHILOX, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+        if (mt) RSB_DISPATCH_FEAT(count != 0, plain, a.staged, RSB_RUN_MT);
+        else RSB_DISPATCH_FEAT(count != 0, plain, a.staged, RSB_RUN_PX);
+#undef RSB_RUN_MT
+#undef RSB_RUN_PX
     }
     if (rc) return rc;
     {

@@ -405,69 +405,101 @@ RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
 struct KdCursor {
     double min_range, max_range;
     int32_t node, sp;
-    V3 rcp;             // 1.0 / d per component (plane distances through div_recip1)
-    int32_t unsafe;     // recip_unsafe_mask(d, rcp)
 };
 
-RSB_HD void kd_set_reciprocals(KdCursor& c, const V3& d, const V3& rcp) {
-    c.rcp = rcp;
-    c.unsafe = recip_unsafe_mask(d, rcp);
-}
+// Per-ray storage the traversal indexes by split axis: element k of {origin xyz, direction xyz, 1/direction xyz}
+// lives at p[k * S].  Selecting a component of a register-resident vector by a run-time axis costs a chain of
+// predicated moves per 64-bit value (14 % of k_wf_trace's instructions in the round-1 profile); one indexed load
+// replaces it.  On the device S = the CTA size and p points into shared memory at the thread's own column
+// (bank = thread index, whatever the axis: conflict free); host code and the slow paths use S = 1 over a local
+// array.  `unsafe` = recip_unsafe_mask: direction components whose plane distances must use a true division.
+template <int S>
+struct RayAx {
+    double* p;
+    int32_t unsafe;
+    RSB_HD double o(int a) const { return p[a * S]; }
+    RSB_HD double d(int a) const { return p[(3 + a) * S]; }
+    RSB_HD double r(int a) const { return p[(6 + a) * S]; }
+    RSB_HD V3 O() const { return v3(p[0], p[S], p[2 * S]); }
+    RSB_HD V3 D() const { return v3(p[3 * S], p[4 * S], p[5 * S]); }
+    RSB_HD V3 R() const { return v3(p[6 * S], p[7 * S], p[8 * S]); }
+    // the reciprocals are the very quotients BoundingBox3D._slab forms (boundingbox.pyx:208-209)
+    RSB_HD void set(double* storage, const V3& o, const V3& d) {
+        p = storage;
+        V3 rc = ray_reciprocals(d);
+        p[0] = o.x; p[S] = o.y; p[2 * S] = o.z;
+        p[3 * S] = d.x; p[4 * S] = d.y; p[5 * S] = d.z;
+        p[6 * S] = rc.x; p[7 * S] = rc.y; p[8 * S] = rc.z;
+        unsafe = recip_unsafe_mask(d, rc);
+    }
+};
+#define RSB_AX_WORDS 18   // doubles of RayAx storage per thread: the world-space ray + one nested mesh-local ray
 
 enum KdResult : int32_t { KD_MISS = 0, KD_HIT = 1, KD_MORE = 2 };
 
 // KDTree3DCore._trace (kdtree3d.pyx:589-607): clip the ray against the tree bounds
-RSB_HD bool kd_begin(const KdTree& tree, const V3& o, const V3& d, KdCursor& c) {
+template <int S>
+RSB_HD bool kd_begin(const KdTree& tree, const RayAx<S>& ax, KdCursor& c) {
     c.node = 0;
     c.sp = 0;
-    // the slab test divides 1.0 by the same three components (boundingbox.pyx:208-209)
-    V3 rcp = ray_reciprocals(d);
-    kd_set_reciprocals(c, d, rcp);
-    return box_intersect_inv(tree.bounds, o, d, rcp, &c.min_range, &c.max_range);
+    return box_intersect_inv(tree.bounds, ax.O(), ax.D(), ax.R(), &c.min_range, &c.max_range);
 }
 
 // One unit of traversal: descend from the cursor to the next leaf in front-to-back order
 // (_trace_branch, kdtree3d.pyx:626-700) and run the leaf test (_trace_leaf).  "While-while" form: every
 // lane of a warp first reaches its next leaf (cheap, uniform code) and only then are leaves processed,
 // so the expensive item tests run with the warp converged.  KD_MORE: no hit in that leaf, the cursor
-// points at the next subtree; callers loop (or interleave other rays' units, see k_wf_trace).
-template <class LeafFn, class Stats>
-RSB_HD int kd_advance(const KdTree& tree, const V3& o, const V3& d, KdStackEntry* stack, KdCursor& c, LeafFn& leaf,
+// points at the next subtree; callers loop.
+// The branch step is written without control flow: the three cases of _trace_branch (near only / far only /
+// both) become predicates, the plane distance (n.split - origin) / direction comes from the per-ray reciprocal
+// (div_recip1: correctly rounded, 3 dependent instructions).  A zero direction component gives a NaN or
+// infinite quotient that every comparison below rejects, which is the reference's `direction == 0` branch:
+// go to the child on the origin's side.
+// One 16-byte load per node visit (the address space -- shared for a staged world tree, global for mesh trees --
+// is inferred by the compiler from the kernel's template flags)
+RSB_HD KdNode kd_load_node(const KdNode* p) {
+#ifdef __CUDA_ARCH__
+    int4 v = *reinterpret_cast<const int4*>(p);
+    KdNode n;
+    n.split = __hiloint2double(v.y, v.x);
+    n.upper = v.z;
+    n.axis = v.w;
+    return n;
+#else
+    return *p;
+#endif
+}
+
+template <int S, class LeafFn, class Stats>
+RSB_HD int kd_advance(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stack, KdCursor& c, LeafFn& leaf,
                       Stats& stats, int* hit_node) {
     int node = c.node, sp = c.sp;
-    double min_range = c.min_range, max_range = c.max_range;
-    KdNode n = tree.nodes[node];
+    const double min_range = c.min_range;
+    double max_range = c.max_range;
+    KdNode n = kd_load_node(tree.nodes + node);
     while (n.axis >= 0) {
         stats.branch();
-        double origin = v3_get(o, n.axis);
-        double direction = v3_get(d, n.axis);
-        int lower_id = node + 1;
-        int upper_id = n.upper;
-        if (direction == 0) {
-            node = (origin < n.split) ? lower_id : upper_id;
-        } else {
+        const int axis = n.axis;
+        const double origin = ax.o(axis), direction = ax.d(axis);
 #ifdef RSB_KD_TRUE_DIVIDE
-            double plane_distance = (n.split - origin) / direction;
+        const double plane_distance = (n.split - origin) / direction;
 #else
-            // (n.split - origin) / direction, correctly rounded, through the per-ray reciprocal
-            double plane_distance = div_recip1(n.split - origin, direction, v3_get(c.rcp, n.axis), (c.unsafe >> n.axis) & 1);
+        const double plane_distance = div_recip1(n.split - origin, direction, ax.r(axis), (ax.unsafe >> axis) & 1);
 #endif
-            bool below_split = origin < n.split || (origin == n.split && direction < 0);
-            int near_id = below_split ? lower_id : upper_id;
-            int far_id = below_split ? upper_id : lower_id;
-            if (plane_distance > max_range || plane_distance <= 0) {
-                node = near_id;
-            } else if (plane_distance < min_range) {
-                node = far_id;
-            } else {
-                stack[sp].node = far_id;
-                stack[sp].tmax = max_range;
-                ++sp;
-                node = near_id;
-                max_range = plane_distance;
-            }
+        const bool below_split = origin < n.split || (origin == n.split && direction < 0);
+        const int lower_id = node + 1, upper_id = n.upper;
+        const int near_id = below_split ? lower_id : upper_id;
+        const int far_id = below_split ? upper_id : lower_id;
+        const bool only_near = direction == 0 || plane_distance > max_range || plane_distance <= 0;
+        const bool only_far = !only_near && plane_distance < min_range;
+        if (!only_near && !only_far) {
+            stack[sp].node = far_id;
+            stack[sp].tmax = max_range;
+            ++sp;
+            max_range = plane_distance;
         }
-        n = tree.nodes[node];
+        node = only_far ? far_id : near_id;
+        n = kd_load_node(tree.nodes + node);
     }
     stats.leaf(n.leaf.item_count);
     if (n.leaf.item_count > 0 && leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) {
@@ -484,12 +516,12 @@ RSB_HD int kd_advance(const KdTree& tree, const V3& o, const V3& d, KdStackEntry
     return KD_MORE;
 }
 
-template <class LeafFn, class Stats>
-RSB_HD bool kd_trace(const KdTree& tree, const V3& o, const V3& d, KdStackEntry* stack, LeafFn& leaf, Stats& stats, int* hit_node) {
+template <int S, class LeafFn, class Stats>
+RSB_HD bool kd_trace(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stack, LeafFn& leaf, Stats& stats, int* hit_node) {
     KdCursor c;
-    if (!kd_begin(tree, o, d, c)) return false;
+    if (!kd_begin(tree, ax, c)) return false;
     int r;
-    do { r = kd_advance(tree, o, d, stack, c, leaf, stats, hit_node); } while (r == KD_MORE);
+    do { r = kd_advance(tree, ax, stack, c, leaf, stats, hit_node); } while (r == KD_MORE);
     return r == KD_HIT;
 }
 
@@ -644,9 +676,12 @@ struct MeshLeaf {
     }
 };
 
-// mesh.pyx:506-518 (MeshData.trace) on a mesh-local ray
-template <class Stats>
-RSB_HD bool mesh_trace(const Mesh& mesh, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, MeshHit* out, Stats& stats) {
+// mesh.pyx:506-518 (MeshData.trace) on a mesh-local ray; `axbuf` = 9*S doubles of RayAx storage
+template <int S, class Stats>
+RSB_HD bool mesh_trace(const Mesh& mesh, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, MeshHit* out, Stats& stats,
+                       double* axbuf) {
+    RayAx<S> ax;
+    ax.set(axbuf, o, d);
     MeshLeaf<Stats> leaf;
     leaf.mesh = &mesh;
     leaf.o = o;
@@ -654,7 +689,7 @@ RSB_HD bool mesh_trace(const Mesh& mesh, const V3& o, const V3& d, double max_di
     leaf.rs = mesh_rayspace(d);
     leaf.result = out;
     leaf.stats = &stats;
-    return kd_trace(mesh.tree, o, d, stack, leaf, stats, &out->node);
+    return kd_trace(mesh.tree, ax, stack, leaf, stats, &out->node);
 }
 
 // mesh.pyx:718-800 (calc_intersection, _intersection_normal) in mesh-local space
@@ -691,7 +726,8 @@ RSB_HD void mesh_geometry(const Mesh& mesh, const V3& o, const V3& d, const Mesh
 template <class Stats>
 RSB_HD bool mesh_contains(const Mesh& mesh, const V3& p, KdStackEntry* stack, Stats& stats) {
     MeshHit h;
-    if (!mesh_trace(mesh, p, v3(0, 0, 1), RSB_INF, stack, &h, stats)) return false;
+    double axbuf[9];
+    if (!mesh_trace<1>(mesh, p, v3(0, 0, 1), RSB_INF, stack, &h, stats, axbuf)) return false;
     return mesh.tri[3 * (size_t)h.tri + 2].w > 0.0f;
 }
 
@@ -899,20 +935,22 @@ RSB_HD_NOINLINE void csg_geometry(const Scene& sc, int top, const CsgEvent& ev, 
 #define RSB_FEAT_MESH 1
 #define RSB_FEAT_CSG 2
 #define RSB_FEAT_ALL 3
+#define RSB_FEAT_STAGED 4   // kernels only: world tree, item list and primitive table are in shared memory
 
-template <class Stats, int FEAT = RSB_FEAT_ALL>
+template <class Stats, int FEAT = RSB_FEAT_ALL, int S = 1>
 struct WorldLeaf {
     const Scene* sc;
-    V3 o, d;
-    V3 inv;                     // 1.0 / d per component, shared by every world-space AABB test of this ray
+    RayAx<S> ax;                // world-space ray: origin, direction, 1.0 / direction (shared by every AABB test)
     double max_distance;
     KdStackEntry* mesh_stack;   // stack space above the world traversal's own entries
+    double* mesh_axbuf;         // RayAx storage of a nested mesh traversal
     HitRec* best;
     Stats* stats;
 
     // one candidate primitive that passed its AABB pre-test (BoundPrimitive.hit, boundprimitive.pyx:42-51)
     RSB_HD void test(int id, double& distance, bool& found) {
         const Prim& p = sc->prims[id];
+        const V3 o = ax.O(), d = ax.D();
         if (p.type <= PRIM_CONE) {
             V3 lo = xform_point(p.to_local, o);
             V3 ld = xform_vector(p.to_local, d);
@@ -927,7 +965,7 @@ struct WorldLeaf {
             V3 lo = xform_point(p.to_local, o);
             V3 ld = xform_vector(p.to_local, d);
             MeshHit mh;
-            if (mesh_trace(sc->meshes[p.mesh], lo, ld, max_distance, mesh_stack, &mh, *stats) && mh.t <= distance) {
+            if (mesh_trace<S>(sc->meshes[p.mesh], lo, ld, max_distance, mesh_stack, &mh, *stats, mesh_axbuf) && mh.t <= distance) {
                 distance = mh.t;
                 best->t = mh.t; best->prim = id; best->leaf = id; best->code = mh.tri; best->flip = 0;
                 best->mesh_node = mh.node;
@@ -957,10 +995,13 @@ struct WorldLeaf {
             int cand[4];
             int nc = 0;
             int end = count - base < 4 ? count - base : 4;
-            for (int i = 0; i < end; ++i) {
-                int id = sc->world.items[offset + base + i];
-                stats->prim_test();
-                if (box_hit_inv(sc->prims[id].bbox, o, d, inv)) cand[nc++] = id;
+            {
+                const V3 o = ax.O(), d = ax.D(), inv = ax.R();
+                for (int i = 0; i < end; ++i) {
+                    int id = sc->world.items[offset + base + i];
+                    stats->prim_test();
+                    if (box_hit_inv(sc->prims[id].bbox, o, d, inv)) cand[nc++] = id;
+                }
             }
             for (int i = 0; i < nc; ++i) test(cand[i], distance, found);
         }
@@ -968,29 +1009,34 @@ struct WorldLeaf {
     }
 };
 
-// Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries.
-template <int FEAT = RSB_FEAT_ALL, class Stats>
-RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats) {
-    WorldLeaf<Stats, FEAT> leaf;
+// Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries, `axbuf` RSB_AX_WORDS * S doubles
+// (element k of the calling thread at axbuf[k * S]).
+template <int FEAT, int S, class Stats>
+RSB_HD bool world_hit_ax(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats,
+                         double* axbuf) {
+    WorldLeaf<Stats, FEAT, S> leaf;
     leaf.sc = &sc;
-    leaf.o = o;
-    leaf.d = d;
-    leaf.inv = ray_reciprocals(d);
+    leaf.ax.set(axbuf, o, d);
     leaf.max_distance = max_distance;
     leaf.mesh_stack = stack + (RSB_KD_STACK / 2);
+    leaf.mesh_axbuf = axbuf + 9 * S;
     leaf.best = rec;
     leaf.stats = &stats;
     rec->u = rec->v = rec->w = 0.0f;
     rec->node = -1;
     rec->mesh_node = -1;
     KdCursor c;
-    c.node = 0;
-    c.sp = 0;
-    kd_set_reciprocals(c, d, leaf.inv);
-    if (!box_intersect_inv(sc.world.bounds, o, d, leaf.inv, &c.min_range, &c.max_range)) return false;
+    if (!kd_begin(sc.world, leaf.ax, c)) return false;
     int r;
-    do { r = kd_advance(sc.world, o, d, stack, c, leaf, stats, &rec->node); } while (r == KD_MORE);
+    do { r = kd_advance(sc.world, leaf.ax, stack, c, leaf, stats, &rec->node); } while (r == KD_MORE);
     return r == KD_HIT;
+}
+
+// The same over thread-local storage (host builds, and device code outside the traversal kernels)
+template <int FEAT = RSB_FEAT_ALL, class Stats>
+RSB_HD bool world_hit(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats) {
+    double axbuf[RSB_AX_WORDS];
+    return world_hit_ax<FEAT, 1>(sc, o, d, max_distance, stack, rec, stats, axbuf);
 }
 
 // Intersection geometry for a HitRec, in the world-level primitive's local space.

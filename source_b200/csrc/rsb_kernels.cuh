@@ -93,9 +93,11 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes) {
     for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
 }
 
-// n_items: number of leaf item ids of the world tree; staged == 0 leaves the scene untouched
-__device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int n_items, int staged) {
-    if (!staged) return;
+// n_items: number of leaf item ids of the world tree.  STAGED is a compile-time flag (RSB_FEAT_STAGED) so that
+// every load through the redirected pointers is compiled as a shared-memory load, not a generic one.
+template <bool STAGED>
+__device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int n_items) {
+    if (!STAGED) return;
     StageLayout l = stage_layout(sc.world.n_nodes, n_items, sc.n_prims);
     copy16(smem, sc.world.nodes, l.nodes_bytes);
     // item list: copy whole 16-B words (the allocation is padded to 16 B)
@@ -107,16 +109,27 @@ __device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int 
     sc.prims = reinterpret_cast<const Prim*>(smem + l.nodes_bytes + l.items_bytes);
 }
 
+// RayAx storage of the calling thread (rsb_geom.h): RSB_AX_WORDS columns of blockDim.x doubles behind the staged
+// scene.  Kernels that use it are launched with RSB_RENDER_THREADS threads and ax_bytes(FEAT) extra shared memory.
+__host__ __device__ inline int ax_bytes(int feat) { return ((feat & RSB_FEAT_MESH) ? RSB_AX_WORDS : 9) * 8 * RSB_RENDER_THREADS; }
+
+template <bool STAGED>
+__device__ __forceinline__ double* ax_storage(unsigned char* smem, const Scene& sc, int n_items) {
+    int off = STAGED ? stage_layout(sc.world.n_nodes, n_items, sc.n_prims).total : 0;
+    return reinterpret_cast<double*>(smem + off) + threadIdx.x;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128)
-k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __restrict__ origins,
+k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origins,
             const double* __restrict__ directions, const double* __restrict__ max_distance,
             int32_t* __restrict__ out_prim, double* __restrict__ out_t, int32_t* __restrict__ out_sub,
             uint8_t* __restrict__ out_flags, int32_t* __restrict__ out_node, double* __restrict__ out_geom,
             float* __restrict__ out_uvw, DevCounters* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_scene(sc, smem, n_items, staged);
+    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
+    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, n_items);
     typename StatsSel<COUNT>::type stats;
     KdStackEntry stack[RSB_KD_STACK];
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -125,7 +138,7 @@ k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __rest
         V3 d = v3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
         double md = max_distance ? max_distance[i] : RSB_INF;
         HitRec rec;
-        bool hit = world_hit<FEAT>(sc, o, d, md, stack, &rec, stats);
+        bool hit = world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, o, d, md, stack, &rec, stats, axbuf);
         if (hit) {
             Isect is;
             world_hit_geometry<FEAT>(sc, o, d, rec, &is);
@@ -161,11 +174,12 @@ k_hit_batch(Scene sc, int n_items, int staged, long long n, const double* __rest
 // rays from `origin` toward target + (jx, jy, 0)*half_window, (jx, jy) uniform in [-1, 1) from Philox(seed, index)
 template <bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128)
-k_hit_sweep(Scene sc, int n_items, int staged, long long n, long long first_index, unsigned long long seed,
+k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned long long seed,
             double ox, double oy, double oz, double tx, double ty, double tz, double half_window,
             unsigned long long* out_hits, double* out_sum_t, unsigned long long* out_xor_prim, DevCounters* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_scene(sc, smem, n_items, staged);
+    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
+    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, n_items);
     typename StatsSel<COUNT>::type stats;
     KdStackEntry stack[RSB_KD_STACK];
     unsigned long long hits = 0, xr = 0;
@@ -180,7 +194,7 @@ k_hit_sweep(Scene sc, int n_items, int staged, long long n, long long first_inde
         V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
         V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
         HitRec rec;
-        if (world_hit<FEAT>(sc, o, d, RSB_INF, stack, &rec, stats)) {
+        if (world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, o, d, RSB_INF, stack, &rec, stats, axbuf)) {
             hits += 1;
             sum_t += rec.t;
             xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + i);
@@ -424,7 +438,8 @@ template <int RNGMODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
-    stage_scene(sc, smem, a.n_items, a.staged);
+    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, a.n_items);
+    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, a.n_items);
     typename StatsSel<COUNT>::type stats;
     const int P = a.n_slots;
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -443,7 +458,7 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
         KdStackEntry stack[RSB_KD_STACK];
         HitRec rec;
         double normalisation;
-        int r = path_trace<FEAT>(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats);
+        int r = path_trace<FEAT, RSB_RENDER_THREADS>(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats, axbuf);
         wf_store_rng<RNGMODE>(a, slot, rng);
         hits = 1;
         if (r == PATH_CONTINUE) {
@@ -544,9 +559,10 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     Spectral sp = a.sp;
-    stage_scene(sc, smem, a.n_items, a.staged);
+    constexpr bool STAGED = (FEAT & RSB_FEAT_STAGED) != 0;
+    stage_scene<STAGED>(sc, smem, a.n_items);
     if (a.tables_staged) {
-        StageLayout l = stage_layout(a.staged ? a.sc.world.n_nodes : 0, a.staged ? a.n_items : 0, a.staged ? a.sc.n_prims : 0);
+        StageLayout l = stage_layout(STAGED ? a.sc.world.n_nodes : 0, STAGED ? a.n_items : 0, STAGED ? a.sc.n_prims : 0);
         unsigned char* base = smem + l.total;
         int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
         copy16(base, a.sp.mats, mat_bytes);

@@ -199,9 +199,9 @@ RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
 //               then _sample_volumes and the roulette normalisation (ray.pyx:395-401)
 // PATH_CONTINUE: ps holds the daughter ray.  PATH_EMITTED: the log now ends with a LOG_EMIT entry.
 // PATH_ZERO: the path's spectrum is identically zero.
-template <int FEAT = RSB_FEAT_ALL, class Stats>
+template <int FEAT = RSB_FEAT_ALL, int S = 1, class Stats>
 RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps, Rng& rng, KdStackEntry* stack,
-                      HitRec* rec, double* normalisation, Stats& stats) {
+                      HitRec* rec, double* normalisation, Stats& stats, double* axbuf = nullptr) {
     // -- Russian roulette (ray.pyx:380-388)
     if (ps.depth < cfg.extinction_min_depth) {
         *normalisation = 1.0;
@@ -210,7 +210,11 @@ RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps
         *normalisation = 1 / (1 - cfg.extinction_prob);
     }
     // -- closest hit (ray.pyx:391-393)
-    if (!world_hit<FEAT>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
+    if (S == 1) {
+        if (!world_hit<FEAT>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
+    } else {
+        if (!world_hit_ax<FEAT, S>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats, axbuf)) return PATH_ZERO;
+    }
     return PATH_CONTINUE;
 }
 
