@@ -54,7 +54,7 @@ struct Context {
     size_t slot_bytes = 0;
     unsigned int* h_idle = nullptr;     // pinned
     RsbRenderStats render_stats{};
-    int slots_per_sm = 2048;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)
+    int slots_per_sm = 8192;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)
     bool use_graphs = true;             // RSB_NO_GRAPH=1 launches the wave kernels one by one (debugging)
     std::vector<cudaEvent_t> event_pool;
     Material* d_mats = nullptr;
@@ -581,6 +581,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
+    smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
     a.wave = 0;

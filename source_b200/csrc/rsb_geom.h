@@ -470,12 +470,12 @@ RSB_HD KdNode kd_load_node(const KdNode* p) {
 #endif
 }
 
-template <int S, class LeafFn, class Stats>
-RSB_HD int kd_advance(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stack, KdCursor& c, LeafFn& leaf,
-                      Stats& stats, int* hit_node) {
-    int node = c.node, sp = c.sp;
-    const double min_range = c.min_range;
-    double max_range = c.max_range;
+// _trace_branch (kdtree3d.pyx:626-700) from `node` down to the next leaf in front-to-back order; far children
+// that must be visited later are stacked with the max_range they resume with.  Returns the leaf node.
+template <int S, class Stats>
+RSB_HD KdNode kd_descend(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stack, int& node, int& sp, double min_range,
+                         double& max_range, Stats& stats) {
+    const bool unsafe = ax.unsafe != 0;
     KdNode n = kd_load_node(tree.nodes + node);
     while (n.axis >= 0) {
         stats.branch();
@@ -484,7 +484,7 @@ RSB_HD int kd_advance(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stac
 #ifdef RSB_KD_TRUE_DIVIDE
         const double plane_distance = (n.split - origin) / direction;
 #else
-        const double plane_distance = div_recip1(n.split - origin, direction, ax.r(axis), (ax.unsafe >> axis) & 1);
+        const double plane_distance = div_recip1(n.split - origin, direction, ax.r(axis), unsafe);
 #endif
         const bool below_split = origin < n.split || (origin == n.split && direction < 0);
         const int lower_id = node + 1, upper_id = n.upper;
@@ -501,6 +501,15 @@ RSB_HD int kd_advance(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stac
         node = only_far ? far_id : near_id;
         n = kd_load_node(tree.nodes + node);
     }
+    return n;
+}
+
+template <int S, class LeafFn, class Stats>
+RSB_HD int kd_advance(const KdTree& tree, const RayAx<S>& ax, KdStackEntry* stack, KdCursor& c, LeafFn& leaf,
+                      Stats& stats, int* hit_node) {
+    int node = c.node, sp = c.sp;
+    double max_range = c.max_range;
+    KdNode n = kd_descend(tree, ax, stack, node, sp, c.min_range, max_range, stats);
     stats.leaf(n.leaf.item_count);
     if (n.leaf.item_count > 0 && leaf(n.leaf.item_offset, n.leaf.item_count, max_range)) {
         *hit_node = node;
@@ -1011,6 +1020,13 @@ struct WorldLeaf {
 
 // Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries, `axbuf` RSB_AX_WORDS * S doubles
 // (element k of the calling thread at axbuf[k * S]).
+//
+// Traversal with POSTPONED primitive tests: a lane keeps descending and running the cheap AABB pre-tests of the
+// leaves it passes (phase A) until it holds candidates or has finished; only then does the warp run the
+// primitive tests (phase B), so phase B executes with every lane that still has work instead of the fraction
+// whose current leaf happened to be occupied.  Per leaf the order of AABB tests, primitive tests and the
+// `<=` tie rule are exactly those of _PrimitiveKDTree._trace_leaf (acceleration/kdtree.pyx:73-122): items in
+// leaf order, chunks of four.
 template <int FEAT, int S, class Stats>
 RSB_HD bool world_hit_ax(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats,
                          double* axbuf) {
@@ -1027,9 +1043,53 @@ RSB_HD bool world_hit_ax(const Scene& sc, const V3& o, const V3& d, double max_d
     rec->mesh_node = -1;
     KdCursor c;
     if (!kd_begin(sc.world, leaf.ax, c)) return false;
-    int r;
-    do { r = kd_advance(sc.world, leaf.ax, stack, c, leaf, stats, &rec->node); } while (r == KD_MORE);
-    return r == KD_HIT;
+    int node = 0, sp = 0, leaf_node = -1;
+    double min_range = c.min_range, max_range = c.max_range;
+    int item_offset = 0, item_count = 0, item_base = 0;   // the leaf being processed, and how far
+    int cand[4];
+    int nc = 0;
+    double distance = 0.0;
+    bool found = false, done = false;
+    for (;;) {
+        while (!done && nc == 0) {
+            if (item_base >= item_count) {
+                KdNode n = kd_descend(sc.world, leaf.ax, stack, node, sp, min_range, max_range, stats);
+                stats.leaf(n.leaf.item_count);
+                leaf_node = node;
+                item_offset = n.leaf.item_offset;
+                item_count = n.leaf.item_count;
+                item_base = 0;
+                distance = max_distance < max_range ? max_distance : max_range;
+                found = false;
+            }
+            {
+                const V3 ro = leaf.ax.O(), rd = leaf.ax.D(), inv = leaf.ax.R();
+                int end = item_count - item_base < 4 ? item_count - item_base : 4;
+                for (int i = 0; i < end; ++i) {
+                    int id = sc.world.items[item_offset + item_base + i];
+                    stats.prim_test();
+                    if (box_hit_inv(sc.prims[id].bbox, ro, rd, inv)) cand[nc++] = id;
+                }
+                item_base += end;
+            }
+            if (nc == 0 && item_base >= item_count) {
+                // leaf finished with nothing pending: report, or resume at the nearest stacked far child with
+                // min_range = the plane distance = max_range of the leaf just left
+                if (found || sp == 0) done = true;
+                else { --sp; node = stack[sp].node; min_range = max_range; max_range = stack[sp].tmax; }
+            }
+        }
+        if (nc == 0) break;   // done
+        for (int i = 0; i < nc; ++i) leaf.test(cand[i], distance, found);
+        nc = 0;
+        if (item_base >= item_count) {
+            if (found || sp == 0) done = true;
+            else { --sp; node = stack[sp].node; min_range = max_range; max_range = stack[sp].tmax; }
+        }
+        if (done) break;
+    }
+    if (found) rec->node = leaf_node;
+    return found;
 }
 
 // The same over thread-local storage (host builds, and device code outside the traversal kernels)

@@ -121,7 +121,7 @@ __device__ __forceinline__ double* ax_storage(unsigned char* smem, const Scene& 
 
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_ALL) ? 3 : 5)
 k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origins,
             const double* __restrict__ directions, const double* __restrict__ max_distance,
             int32_t* __restrict__ out_prim, double* __restrict__ out_t, int32_t* __restrict__ out_sub,
@@ -173,7 +173,7 @@ k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origi
 
 // rays from `origin` toward target + (jx, jy, 0)*half_window, (jx, jy) uniform in [-1, 1) from Philox(seed, index)
 template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_ALL) ? 3 : 5)
 k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned long long seed,
             double ox, double oy, double oz, double tx, double ty, double tz, double half_window,
             unsigned long long* out_hits, double* out_sum_t, unsigned long long* out_xor_prim, DevCounters* counters) {
@@ -313,7 +313,13 @@ struct WfArgs {
     int32_t wave;
 };
 
-template <int RNGMODE>
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// PREFETCH: start fetching the state words the next few draws will read (words i.. and i+156.. of the 312-word
+// ring, rsb_rng.h next_u64).  A pixel's MT19937-64 state lives in HBM (2.5 KB per stream, ~0.8 GB in flight per
+// frame), each draw is a dependent round trip to it, and the shade kernel's first draw comes only after the
+// intersection geometry has been computed -- so the fetch overlaps that arithmetic.
+template <int RNGMODE, bool PREFETCH = false>
 __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng) {
     rng.mode = RNGMODE;
     if (RNGMODE == RNG_MT19937_64) {
@@ -321,6 +327,15 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
         rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN);
         rng.mt.stride = 1;
         rng.mt.mti = a.st.pix_mti[2 * w];
+        if (PREFETCH) {
+            int i = rng.mt.mti >= RSB_MT_NN ? 0 : rng.mt.mti;
+            int im = i + RSB_MT_MM >= RSB_MT_NN ? i + RSB_MT_MM - RSB_MT_NN : i + RSB_MT_MM;
+            int i4 = i + 4 < RSB_MT_NN ? i + 4 : 0, im4 = im + 4 < RSB_MT_NN ? im + 4 : 0;
+            prefetch_l1(rng.mt.mt + i);
+            prefetch_l1(rng.mt.mt + im);
+            prefetch_l1(rng.mt.mt + i4);
+            prefetch_l1(rng.mt.mt + im4);
+        }
     } else {
         long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
         rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)a.st.sample[slot]);
@@ -418,6 +433,15 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     a.st.rays[slot] = 1;
     a.st.log_n[slot] = 0;
     a.st.status[slot] = SLOT_ALIVE;
+    // roulette of the primary segment (see k_wf_trace); with the usual extinction_min_depth > 0 there is no draw
+    double normalisation = 1.0;
+    if (a.cfg.extinction_min_depth <= 0) {
+        Rng rng;
+        wf_load_rng<RNGMODE>(a, slot, rng);
+        if (!path_roulette(a.cfg, 0, rng, &normalisation)) normalisation = 0.0;
+        wf_store_rng<RNGMODE>(a, slot, rng);
+    }
+    a.st.norm[slot] = normalisation;
 }
 
 template <int RNGMODE>
@@ -439,33 +463,38 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, a.n_items);
-    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, a.n_items);
     typename StatsSel<COUNT>::type stats;
     const int P = a.n_slots;
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = slot < P && a.st.status[slot] == SLOT_ALIVE;
+    // The Russian roulette of this segment was already played by the kernel that produced the ray (k_wf_shade /
+    // k_wf_regen, right after their own draws -- the reference's draw order, ray.pyx:380-388): norm == 0 marks a
+    // path it ended.  The trace kernel therefore touches no RNG state: nothing but slot-indexed, coalesced loads
+    // stand before the traversal.
+    const size_t PP = (size_t)P;
+    const bool in_range = slot < P;
+    const int cs = in_range ? slot : 0;
+    const int status = a.st.status[cs];
+    const double normalisation = a.st.norm[cs];
+    PathState ps;
+    ps.o = v3(a.st.ray[0 * PP + cs], a.st.ray[1 * PP + cs], a.st.ray[2 * PP + cs]);
+    ps.d = v3(a.st.ray[3 * PP + cs], a.st.ray[4 * PP + cs], a.st.ray[5 * PP + cs]);
+    // (the slot loads above are in flight while the CTA stages the scene)
+    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, a.n_items);
+    const bool active = in_range && status == SLOT_ALIVE;
     unsigned long long hits = 0;
     int list = -1;
     if (active) {
-        const size_t PP = (size_t)P;
-        PathState ps;
-        ps.o = v3(a.st.ray[0 * PP + slot], a.st.ray[1 * PP + slot], a.st.ray[2 * PP + slot]);
-        ps.d = v3(a.st.ray[3 * PP + slot], a.st.ray[4 * PP + slot], a.st.ray[5 * PP + slot]);
-        ps.depth = a.st.depth[slot];
-        ps.rays = 0;
-        Rng rng;
-        wf_load_rng<RNGMODE>(a, slot, rng);
         KdStackEntry stack[RSB_KD_STACK];
         HitRec rec;
-        double normalisation;
-        int r = path_trace<FEAT, RSB_RENDER_THREADS>(sc, a.cfg, ps, rng, stack, &rec, &normalisation, stats, axbuf);
-        wf_store_rng<RNGMODE>(a, slot, rng);
-        hits = 1;
-        if (r == PATH_CONTINUE) {
+        bool hit = false;
+        if (normalisation != 0.0) {
+            hits = 1;
+            hit = world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, ps.o, ps.d, a.cfg.max_distance, stack, &rec, stats, axbuf);
+        }
+        if (hit) {
             a.st.hit_t[slot] = rec.t;
             a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
-            a.st.norm[slot] = normalisation;
             a.st.status[slot] = SLOT_HIT;
             list = a.sp.mats[sc.prims[rec.prim].material].type;     // 0..3: per-material hit lists
         } else {
@@ -516,6 +545,8 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
     const unsigned int n = a.st.n_hit[MAT];
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         int slot = a.st.hit_list[(size_t)MAT * P + k];
+        Rng rng;
+        wf_load_rng<RNGMODE, MAT == MAT_LAMBERT || MAT == MAT_DIELECTRIC>(a, slot, rng);
         PathState ps;
         ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
         ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
@@ -529,8 +560,6 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         rec.u = uvw.x; rec.v = uvw.y; rec.w = uvw.z;
         rec.mesh_node = __float_as_int(uvw.w);
         rec.node = -1;
-        Rng rng;
-        wf_load_rng<RNGMODE>(a, slot, rng);
         PathLog log;
         log.base = a.st.log + (size_t)slot * a.log_capacity;
         log.stride = 1;
@@ -542,6 +571,11 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
         if (r == PATH_CONTINUE) {
+            // the daughter's Russian roulette, played here so that k_wf_trace needs no RNG state: it is the next
+            // draw of the stream in the reference too (spawn_daughter -> daughter.trace -> roulette, ray.pyx:380-388)
+            double normalisation;
+            if (!path_roulette(a.cfg, ps.depth, rng, &normalisation)) normalisation = 0.0;
+            a.st.norm[slot] = normalisation;
             a.st.ray[0 * P + slot] = ps.o.x; a.st.ray[1 * P + slot] = ps.o.y; a.st.ray[2 * P + slot] = ps.o.z;
             a.st.ray[3 * P + slot] = ps.d.x; a.st.ray[4 * P + slot] = ps.d.y; a.st.ray[5 * P + slot] = ps.d.z;
             a.st.depth[slot] = ps.depth;
@@ -587,14 +621,17 @@ template <int RNGMODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Spectral sp = a.sp;
+    int tab_bytes = 0;
     if (a.tables_staged) {
         // tables and their logs are contiguous in HBM: [n_materials][bins] x 2
-        int tab_bytes = ((sp.n_materials * sp.bins * 16 + 15) / 16) * 16;
+        tab_bytes = ((sp.n_materials * sp.bins * 16 + 15) / 16) * 16;
         copy16(smem, a.sp.tables, tab_bytes);
         __syncthreads();
         sp.tables = reinterpret_cast<const double*>(smem);
         sp.tables_ln = sp.tables + (size_t)sp.n_materials * sp.bins;
     }
+    // 32 log entries per warp, staged in shared memory and read back as one broadcast LDS.128 per entry
+    LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
     const unsigned int n = a.st.n_ended[par];
@@ -629,19 +666,17 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             double xa = 0.0, xb = 0.0;
             if (emit) {
-                // the log is read 32 entries at a time, one entry per lane (coalesced), and broadcast by shuffle:
-                // every lane applies every entry, newest first, to its own bins
+                // the log is read 32 entries at a time, one entry per lane (coalesced), and handed round through
+                // shared memory: every lane applies every entry, newest first, to its own bins
                 for (int top = log.n; top > 0; top -= 32) {
                     int cnt = top < 32 ? top : 32;
-                    LogEntry mine;
-                    mine.op = 0; mine.table = 0; mine.v = 0.0;
-                    if (lane < cnt) mine = log.get(top - 1 - lane);
+                    __syncwarp();
+                    if (lane < cnt) wlog[lane] = log.get(top - 1 - lane);
+                    __syncwarp();
                     for (int j = 0; j < cnt; ++j) {
-                        int op = __shfl_sync(RSB_FULL_MASK, mine.op, j);
-                        int tb = __shfl_sync(RSB_FULL_MASK, mine.table, j);
-                        double ev = __shfl_sync(RSB_FULL_MASK, mine.v, j);
-                        if (ha) xa = apply_entry(xa, op, tb, ev, sp, ba);
-                        if (hb) xb = apply_entry(xb, op, tb, ev, sp, bb);
+                        const LogEntry e = wlog[j];
+                        if (ha) xa = apply_entry(xa, e.op, e.table, e.v, sp, ba);
+                        if (hb) xb = apply_entry(xb, e.op, e.table, e.v, sp, bb);
                     }
                 }
             }

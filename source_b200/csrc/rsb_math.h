@@ -194,6 +194,8 @@ RSB_HD double div_exact(double x, double d, double r) {
 // that every other case takes a true division.  The dependent chain is 3 instructions instead of the ~10 of
 // div.rn.f64 -- the traversal is bound by exactly that chain.  Checked against x / d on 4e8 adversarial pairs
 // (tests/test_host_parity.py::test_div_recip1).
+// Non-zero when some NON-ZERO direction component cannot take the reciprocal shortcut (all-ones significand, or a
+// reciprocal outside 1e-140 .. 1e140).  Zero components never reach the division (kdtree3d.pyx:660-668).
 RSB_HD int recip_unsafe_mask(const V3& d, const V3& r) {
     int m = 0;
     const double c[3] = {d.x, d.y, d.z}, q[3] = {r.x, r.y, r.z};
@@ -201,14 +203,19 @@ RSB_HD int recip_unsafe_mask(const V3& d, const V3& r) {
         unsigned long long bits;
         memcpy(&bits, &c[k], 8);
         double ar = fabs(q[k]);
-        if ((bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL || !(ar > 1e-140 && ar < 1e140)) m |= 1 << k;
+        if (c[k] != 0.0 && ((bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL || !(ar > 1e-140 && ar < 1e140))) m |= 1 << k;
     }
     return m;
 }
 
+// `unsafe`: the ray has a flagged direction component (then every plane distance of the ray is a true division).
+// The numerator's magnitude is windowed on its exponent field alone: biased exponent in [559, 1488], i.e.
+// 2^-464 <= |x| < 2^466 (about 2e-140 .. 2e140); zero, subnormal, infinite and NaN numerators divide.
 RSB_HD double div_recip1(double x, double d, double r, bool unsafe) {
-    double ax = fabs(x);
-    if (unsafe || !(ax < 1e140) || (ax < 1e-140 && x != 0.0)) return x / d;
+    unsigned long long bits;
+    memcpy(&bits, &x, 8);
+    unsigned int ex = ((unsigned int)(bits >> 52) & 0x7FFu) - 559u;
+    if (unsafe || ex > 929u) return x / d;
     double q = x * r;
     double e = fma(-d, q, x);
     return fma(e, r, q);

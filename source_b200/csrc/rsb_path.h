@@ -199,16 +199,22 @@ RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
 //               then _sample_volumes and the roulette normalisation (ray.pyx:395-401)
 // PATH_CONTINUE: ps holds the daughter ray.  PATH_EMITTED: the log now ends with a LOG_EMIT entry.
 // PATH_ZERO: the path's spectrum is identically zero.
+// Russian roulette of a segment that is about to be traced (ray.pyx:380-388).  false: the path ends here with an
+// all-zero spectrum (roulette, or ray.max_depth reached -- no draw in that case).
+RSB_HD bool path_roulette(const RayConfig& cfg, int depth, Rng& rng, double* normalisation) {
+    if (depth < cfg.extinction_min_depth) {
+        *normalisation = 1.0;
+        return true;
+    }
+    if (depth >= cfg.max_depth || rng.probability(cfg.extinction_prob)) return false;
+    *normalisation = 1 / (1 - cfg.extinction_prob);
+    return true;
+}
+
 template <int FEAT = RSB_FEAT_ALL, int S = 1, class Stats>
 RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps, Rng& rng, KdStackEntry* stack,
                       HitRec* rec, double* normalisation, Stats& stats, double* axbuf = nullptr) {
-    // -- Russian roulette (ray.pyx:380-388)
-    if (ps.depth < cfg.extinction_min_depth) {
-        *normalisation = 1.0;
-    } else {
-        if (ps.depth >= cfg.max_depth || rng.probability(cfg.extinction_prob)) return PATH_ZERO;
-        *normalisation = 1 / (1 - cfg.extinction_prob);
-    }
+    if (!path_roulette(cfg, ps.depth, rng, normalisation)) return PATH_ZERO;
     // -- closest hit (ray.pyx:391-393)
     if (S == 1) {
         if (!world_hit<FEAT>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
