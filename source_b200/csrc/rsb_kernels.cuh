@@ -567,7 +567,6 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         log.n = a.st.log_n[slot];
         log.overflow = 0;
         int r = path_shade<MAT, FEAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
-        wf_store_rng<RNGMODE>(a, slot, rng);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
         if (r == PATH_CONTINUE) {
@@ -575,6 +574,7 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
             // draw of the stream in the reference too (spawn_daughter -> daughter.trace -> roulette, ray.pyx:380-388)
             double normalisation;
             if (!path_roulette(a.cfg, ps.depth, rng, &normalisation)) normalisation = 0.0;
+            wf_store_rng<RNGMODE>(a, slot, rng);
             a.st.norm[slot] = normalisation;
             a.st.ray[0 * P + slot] = ps.o.x; a.st.ray[1 * P + slot] = ps.o.y; a.st.ray[2 * P + slot] = ps.o.z;
             a.st.ray[3 * P + slot] = ps.d.x; a.st.ray[4 * P + slot] = ps.d.y; a.st.ray[5 * P + slot] = ps.d.z;
@@ -582,6 +582,7 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
             a.st.rays[slot] = ps.rays;
             a.st.status[slot] = SLOT_ALIVE;
         } else {
+            wf_store_rng<RNGMODE>(a, slot, rng);
             a.st.status[slot] = (r == PATH_EMITTED) ? SLOT_ENDED_EMIT : SLOT_ENDED_ZERO;
             wf_push_ended(a, slot);
         }
