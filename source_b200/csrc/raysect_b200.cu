@@ -558,6 +558,7 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->status = c.take<int32_t>(P);
     st->log_n = c.take<int32_t>(P);
     st->philox_idx = c.take<uint32_t>(P);
+    st->jit_mti = c.take<int32_t>(P);
     st->work = c.take<int32_t>(P);
     st->ended = c.take<int32_t>(2 * P);
     st->n_ended = c.take<unsigned int>(2);
@@ -577,6 +578,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int regen_grid = std::max(1, std::min((grid + 3) / 4, c->sm_count * 8));
     const int shade_grid = grid;
     smem_scene += ax_bytes(FEAT);   // RayAx storage of k_wf_trace behind the staged scene
+    if (RNGMODE == RNG_MT19937_64) smem_shade += RSB_MT_WIN_WORDS * 8 * threads;   // k_wf_shade: MT state window per thread
     if (smem_scene > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
     if (smem_shade > 48 * 1024)

@@ -1020,13 +1020,9 @@ struct WorldLeaf {
 
 // Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries, `axbuf` RSB_AX_WORDS * S doubles
 // (element k of the calling thread at axbuf[k * S]).
-//
-// Traversal with POSTPONED primitive tests: a lane keeps descending and running the cheap AABB pre-tests of the
-// leaves it passes (phase A) until it holds candidates or has finished; only then does the warp run the
-// primitive tests (phase B), so phase B executes with every lane that still has work instead of the fraction
-// whose current leaf happened to be occupied.  Per leaf the order of AABB tests, primitive tests and the
-// `<=` tie rule are exactly those of _PrimitiveKDTree._trace_leaf (acceleration/kdtree.pyx:73-122): items in
-// leaf order, chunks of four.
+// (Postponing the primitive tests -- a lane keeps descending and pre-testing AABBs until it holds candidates, and
+// the warp runs the primitive tests only when every lane has some or has finished -- was measured SLOWER on the
+// Cornell scene: 176 vs 156 us per 1M-ray wave, 9.3 vs 11.2 active lanes per instruction; profiles/README.md.)
 template <int FEAT, int S, class Stats>
 RSB_HD bool world_hit_ax(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats,
                          double* axbuf) {
@@ -1043,53 +1039,9 @@ RSB_HD bool world_hit_ax(const Scene& sc, const V3& o, const V3& d, double max_d
     rec->mesh_node = -1;
     KdCursor c;
     if (!kd_begin(sc.world, leaf.ax, c)) return false;
-    int node = 0, sp = 0, leaf_node = -1;
-    double min_range = c.min_range, max_range = c.max_range;
-    int item_offset = 0, item_count = 0, item_base = 0;   // the leaf being processed, and how far
-    int cand[4];
-    int nc = 0;
-    double distance = 0.0;
-    bool found = false, done = false;
-    for (;;) {
-        while (!done && nc == 0) {
-            if (item_base >= item_count) {
-                KdNode n = kd_descend(sc.world, leaf.ax, stack, node, sp, min_range, max_range, stats);
-                stats.leaf(n.leaf.item_count);
-                leaf_node = node;
-                item_offset = n.leaf.item_offset;
-                item_count = n.leaf.item_count;
-                item_base = 0;
-                distance = max_distance < max_range ? max_distance : max_range;
-                found = false;
-            }
-            {
-                const V3 ro = leaf.ax.O(), rd = leaf.ax.D(), inv = leaf.ax.R();
-                int end = item_count - item_base < 4 ? item_count - item_base : 4;
-                for (int i = 0; i < end; ++i) {
-                    int id = sc.world.items[item_offset + item_base + i];
-                    stats.prim_test();
-                    if (box_hit_inv(sc.prims[id].bbox, ro, rd, inv)) cand[nc++] = id;
-                }
-                item_base += end;
-            }
-            if (nc == 0 && item_base >= item_count) {
-                // leaf finished with nothing pending: report, or resume at the nearest stacked far child with
-                // min_range = the plane distance = max_range of the leaf just left
-                if (found || sp == 0) done = true;
-                else { --sp; node = stack[sp].node; min_range = max_range; max_range = stack[sp].tmax; }
-            }
-        }
-        if (nc == 0) break;   // done
-        for (int i = 0; i < nc; ++i) leaf.test(cand[i], distance, found);
-        nc = 0;
-        if (item_base >= item_count) {
-            if (found || sp == 0) done = true;
-            else { --sp; node = stack[sp].node; min_range = max_range; max_range = stack[sp].tmax; }
-        }
-        if (done) break;
-    }
-    if (found) rec->node = leaf_node;
-    return found;
+    int r;
+    do { r = kd_advance(sc.world, leaf.ax, stack, c, leaf, stats, &rec->node); } while (r == KD_MORE);
+    return r == KD_HIT;
 }
 
 // The same over thread-local storage (host builds, and device code outside the traversal kernels)

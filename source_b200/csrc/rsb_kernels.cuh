@@ -277,7 +277,8 @@ struct WfSlots {
     int32_t* py;            // [P]
     int32_t* status;        // [P]
     int32_t* log_n;         // [P]
-    uint32_t* philox_idx;   // [P]
+    uint32_t* philox_idx;   // [P] draws so far (Philox) / cursor of the pixel's path stream (MT19937-64)
+    int32_t* jit_mti;       // [P] cursor of the pixel's jitter stream (MT19937-64)
     int32_t* work;          // [P] index (within the current pixel chunk) of the pixel the slot is rendering
     int32_t* pix_mti;       // [n_chunk][2] MT19937-64 cursors of every pixel of the chunk: path stream, jitter stream
     unsigned long long* pix_mt;   // [n_chunk][2][312] their state words (seeded up front by k_wf_seed)
@@ -313,29 +314,17 @@ struct WfArgs {
     int32_t wave;
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// PREFETCH: start fetching the state words the next few draws will read (words i.. and i+156.. of the 312-word
-// ring, rsb_rng.h next_u64).  A pixel's MT19937-64 state lives in HBM (2.5 KB per stream, ~0.8 GB in flight per
-// frame), each draw is a dependent round trip to it, and the shade kernel's first draw comes only after the
-// intersection geometry has been computed -- so the fetch overlaps that arithmetic.
-template <int RNGMODE, bool PREFETCH = false>
+// The cursors of the pixel stream a slot is rendering are kept per SLOT (copied from the pixel's seeded cursors
+// when the slot picks the pixel up), so that they arrive with the rest of the slot state instead of behind a
+// second dependent load through the pixel index.
+template <int RNGMODE>
 __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng) {
     rng.mode = RNGMODE;
     if (RNGMODE == RNG_MT19937_64) {
         size_t w = (size_t)a.st.work[slot];
         rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN);
         rng.mt.stride = 1;
-        rng.mt.mti = a.st.pix_mti[2 * w];
-        if (PREFETCH) {
-            int i = rng.mt.mti >= RSB_MT_NN ? 0 : rng.mt.mti;
-            int im = i + RSB_MT_MM >= RSB_MT_NN ? i + RSB_MT_MM - RSB_MT_NN : i + RSB_MT_MM;
-            int i4 = i + 4 < RSB_MT_NN ? i + 4 : 0, im4 = im + 4 < RSB_MT_NN ? im + 4 : 0;
-            prefetch_l1(rng.mt.mt + i);
-            prefetch_l1(rng.mt.mt + im);
-            prefetch_l1(rng.mt.mt + i4);
-            prefetch_l1(rng.mt.mt + im4);
-        }
+        rng.mt.mti = (int)a.st.philox_idx[slot];
     } else {
         long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
         rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)a.st.sample[slot]);
@@ -343,9 +332,33 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
     }
 }
 
+// Fetch the words the next RSB_MT_WIN_DRAWS draws of `g` will read into the thread's shared-memory column
+// (rsb_rng.h): 13 independent loads in flight at once.  (A prefetch.global.L1 of the same words made no
+// difference: the kernel is bound by the NUMBER of dependent round trips, and the prefetch sat behind the same
+// cursor load.)
+__device__ __forceinline__ void mt_preload(Mt19937_64& g, uint64_t* col) {
+    const int i = g.mti >= RSB_MT_NN ? 0 : g.mti;
+    uint64_t v[RSB_MT_WIN_WORDS];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        int j = i + k;
+        v[k] = g.mt[j < RSB_MT_NN ? j : j - RSB_MT_NN];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        int j = i + k + RSB_MT_MM;
+        v[7 + k] = g.mt[j < RSB_MT_NN ? j : j - RSB_MT_NN];
+    }
+#pragma unroll
+    for (int k = 0; k < RSB_MT_WIN_WORDS; ++k) col[k * RSB_MT_WIN_STRIDE] = v[k];
+    g.win = col;
+    g.win_i0 = i;
+    g.win_n = RSB_MT_WIN_DRAWS;
+}
+
 template <int RNGMODE>
 __device__ __forceinline__ void wf_store_rng(const WfArgs& a, int slot, const Rng& rng) {
-    if (RNGMODE == RNG_MT19937_64) a.st.pix_mti[2 * (size_t)a.st.work[slot]] = rng.mt.mti;
+    if (RNGMODE == RNG_MT19937_64) a.st.philox_idx[slot] = (uint32_t)rng.mt.mti;
     else a.st.philox_idx[slot] = rng.px.idx;
 }
 
@@ -401,6 +414,10 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
         a.st.px[slot] = px;
         a.st.py[slot] = py;
         a.st.work[slot] = (int32_t)w;
+        if (RNGMODE == RNG_MT19937_64) {
+            a.st.philox_idx[slot] = (uint32_t)a.st.pix_mti[2 * w];
+            a.st.jit_mti[slot] = a.st.pix_mti[2 * w + 1];
+        }
         s = 0;
     }
     a.st.sample[slot] = s;
@@ -411,10 +428,10 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
         size_t w = (size_t)a.st.work[slot];
         jit.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN) + RSB_MT_NN;
         jit.mt.stride = 1;
-        jit.mt.mti = a.st.pix_mti[2 * w + 1];
+        jit.mt.mti = a.st.jit_mti[slot];
         u1 = jit.uniform();
         u2 = jit.uniform();
-        a.st.pix_mti[2 * w + 1] = jit.mt.mti;
+        a.st.jit_mti[slot] = jit.mt.mti;
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
         jit.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)s);
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
 // finishes, was measured SLOWER on the Cornell scene -- 208 vs 129 us per 262k-ray wave, 9.1 vs 10.0 active
 // lanes per instruction: iteration counts per ray vary little here, and the refill path diverges.)
 template <int RNGMODE, bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __grid_constant__ WfArgs a) {
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_ALL) ? RSB_TRACE_MIN_BLOCKS : 5) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, a.n_items);
@@ -539,14 +556,14 @@ __global__ void __launch_bounds__(128, RSB_TRACE_MIN_BLOCKS) k_wf_trace(const __
 // while the whole GPU stays busy (separate launches per family left the smaller lists under-occupied).
 template <int RNGMODE, bool COUNT, int MAT, int FEAT>
 __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, const Spectral& sp, KdStackEntry* stack,
-                                              typename StatsSel<COUNT>::type& stats) {
+                                              typename StatsSel<COUNT>::type& stats, uint64_t* mt_col) {
     const size_t P = (size_t)a.n_slots;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int n = a.st.n_hit[MAT];
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
         int slot = a.st.hit_list[(size_t)MAT * P + k];
         Rng rng;
-        wf_load_rng<RNGMODE, MAT == MAT_LAMBERT || MAT == MAT_DIELECTRIC>(a, slot, rng);
+        wf_load_rng<RNGMODE>(a, slot, rng);
         PathState ps;
         ps.o = v3(a.st.ray[0 * P + slot], a.st.ray[1 * P + slot], a.st.ray[2 * P + slot]);
         ps.d = v3(a.st.ray[3 * P + slot], a.st.ray[4 * P + slot], a.st.ray[5 * P + slot]);
@@ -560,6 +577,8 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         rec.u = uvw.x; rec.v = uvw.y; rec.w = uvw.z;
         rec.mesh_node = __float_as_int(uvw.w);
         rec.node = -1;
+        // (after the slot-state loads above, so that those are already in flight)
+        if (RNGMODE == RNG_MT19937_64 && (MAT == MAT_LAMBERT || MAT == MAT_DIELECTRIC)) mt_preload(rng.mt, mt_col);
         PathLog log;
         log.base = a.st.log + (size_t)slot * a.log_capacity;
         log.stride = 1;
@@ -596,20 +615,23 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
     Spectral sp = a.sp;
     constexpr bool STAGED = (FEAT & RSB_FEAT_STAGED) != 0;
     stage_scene<STAGED>(sc, smem, a.n_items);
+    int smem_used = STAGED ? stage_layout(a.sc.world.n_nodes, a.n_items, a.sc.n_prims).total : 0;
     if (a.tables_staged) {
-        StageLayout l = stage_layout(STAGED ? a.sc.world.n_nodes : 0, STAGED ? a.n_items : 0, STAGED ? a.sc.n_prims : 0);
-        unsigned char* base = smem + l.total;
+        unsigned char* base = smem + smem_used;
         int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
         copy16(base, a.sp.mats, mat_bytes);
         __syncthreads();
         sp.mats = reinterpret_cast<const Material*>(base);
+        smem_used += mat_bytes;
     }
+    // the thread's column of the MT19937-64 state window (mt_preload)
+    uint64_t* mt_col = reinterpret_cast<uint64_t*>(smem + smem_used) + threadIdx.x;
     typename StatsSel<COUNT>::type stats;
     KdStackEntry stack[RSB_KD_STACK];
-    wf_shade_list<RNGMODE, COUNT, MAT_LAMBERT, FEAT>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_DIELECTRIC, FEAT>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_EMITTER, FEAT>(a, sc, sp, stack, stats);
-    wf_shade_list<RNGMODE, COUNT, MAT_ABSORBER, FEAT>(a, sc, sp, stack, stats);
+    wf_shade_list<RNGMODE, COUNT, MAT_LAMBERT, FEAT>(a, sc, sp, stack, stats, mt_col);
+    wf_shade_list<RNGMODE, COUNT, MAT_DIELECTRIC, FEAT>(a, sc, sp, stack, stats, mt_col);
+    wf_shade_list<RNGMODE, COUNT, MAT_EMITTER, FEAT>(a, sc, sp, stack, stats, mt_col);
+    wf_shade_list<RNGMODE, COUNT, MAT_ABSORBER, FEAT>(a, sc, sp, stack, stats, mt_col);
     if (COUNT) {
         __syncwarp();
         flush_stats(stats, a.counters, true);

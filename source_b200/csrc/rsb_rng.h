@@ -17,10 +17,21 @@ namespace rsb {
 #define RSB_MT_NN 312
 #define RSB_MT_MM 156
 
+#define RSB_MT_WIN_DRAWS 6      // draws covered by a preloaded window (a Lambert bounce + the next roulette take 5)
+#define RSB_MT_WIN_WORDS 13     // words i .. i+6 and i+156 .. i+161 of the ring
+#define RSB_MT_WIN_STRIDE 128   // window element k of a thread at win[k * 128] (shared memory, one column per thread)
+
 struct Mt19937_64 {
     uint64_t* mt;       // base of this stream's words
     size_t stride;      // distance (in words) between consecutive words of the stream
     int mti;
+    // Optional preloaded window (device kernels): the state words the next RSB_MT_WIN_DRAWS draws read, fetched
+    // from HBM in ONE batch of independent loads instead of one dependent round trip per draw.  The values are
+    // exactly what the draws would load themselves: draw k reads words i+k, i+k+1 (both still old) and i+k+156
+    // (mod 312; never a word this window regenerates), and writes only word i+k.
+    const uint64_t* win = nullptr;
+    int win_i0 = 0;
+    int win_n = 0;
 
     RSB_HD uint64_t& w(int i) { return mt[(size_t)i * stride]; }
 
@@ -69,8 +80,18 @@ struct Mt19937_64 {
         int i = (mti >= RSB_MT_NN) ? 0 : mti;
         int i1 = (i + 1 == RSB_MT_NN) ? 0 : i + 1;
         int im = (i + RSB_MT_MM >= RSB_MT_NN) ? i + RSB_MT_MM - RSB_MT_NN : i + RSB_MT_MM;
-        uint64_t x = (w(i) & UM) | (w(i1) & LM);
-        x = w(im) ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
+        uint64_t wi, wi1, wim;
+        int k = i - win_i0;
+        if (k < 0) k += RSB_MT_NN;
+        if (k < win_n) {
+            wi = win[k * RSB_MT_WIN_STRIDE];
+            wi1 = win[(k + 1) * RSB_MT_WIN_STRIDE];
+            wim = win[(k + 7) * RSB_MT_WIN_STRIDE];
+        } else {
+            wi = w(i); wi1 = w(i1); wim = w(im);
+        }
+        uint64_t x = (wi & UM) | (wi1 & LM);
+        x = wim ^ (x >> 1) ^ ((x & 1ULL) ? MAG : 0ULL);
         w(i) = x;
         mti = i + 1;
         x ^= (x >> 29) & 0x5555555555555555ULL;

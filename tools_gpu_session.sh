@@ -31,14 +31,15 @@ lib:*)
   RSB_LIBRARY=$PWD/build/$L.so timeout 300 python bench.py $B > $O/${TAG}_b_$L.json 2> $O/${TAG}_b_$L.err; show $O/${TAG}_b_$L.json ;;
 full)
   timeout 900 python bench.py > $O/${TAG}_bench_full.json 2> $O/${TAG}_bench_full.err; show $O/${TAG}_bench_full.json ;;
-list)
-  RSB_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none -s 800 -c 200 --csv \
-    --log-file $O/${TAG}_launches.csv python bench.py --pixels 1024 --spp 16 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_list.log 2>&1
-  python tools_kernel_summary.py $O/${TAG}_launches.csv > $O/${TAG}_launch_summary.txt 2>&1; cat $O/${TAG}_launch_summary.txt ;;
+list|list:*)
+  V=${S#list:}; [ "$V" = "list" ] && V=8192
+  RSB_SLOTS_PER_SM=$V RSB_NO_GRAPH=1 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum --clock-control none -s 800 -c 120 --csv \
+    --log-file $O/${TAG}_launches_$V.csv python bench.py --pixels 1024 --spp 64 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_list_$V.log 2>&1
+  python tools_kernel_summary.py $O/${TAG}_launches_$V.csv > $O/${TAG}_launch_summary_$V.txt 2>&1; echo "slots/SM $V"; cat $O/${TAG}_launch_summary_$V.txt ;;
 ncu:*)
   K=${S#ncu:}
-  RSB_NO_GRAPH=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:$K -s 300 -c 1 -f -o $O/${TAG}_full_$K \
-    python bench.py --pixels 1024 --spp 16 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_$K.log 2>&1 ;;
+  RSB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none -k regex:$K -s 200 -c 1 -f -o $O/${TAG}_full_$K \
+    python bench.py --pixels 1024 --spp 64 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_$K.log 2>&1 ;;
 sweep)
   timeout 900 python tools_sweep.py --n 1e6 1e7 1e8 --mesh-subdiv 8 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err; cut -c1-400 $O/${TAG}_sweep.jsonl ;;
 *) echo "unknown step $S" ;;
