@@ -210,12 +210,17 @@ RSB_HD int recip_unsafe_mask(const V3& d, const V3& r) {
 
 // `unsafe`: the ray has a flagged direction component (then every plane distance of the ray is a true division).
 // The numerator's magnitude is windowed on its exponent field alone: biased exponent in [559, 1488], i.e.
-// 2^-464 <= |x| < 2^466 (about 2e-140 .. 2e140); zero, subnormal, infinite and NaN numerators divide.
+// 2^-464 <= |x| < 2^466 (about 2e-140 .. 2e140); subnormal, infinite and NaN numerators divide.
 RSB_HD double div_recip1(double x, double d, double r, bool unsafe) {
     unsigned long long bits;
     memcpy(&bits, &x, 8);
     unsigned int ex = ((unsigned int)(bits >> 52) & 0x7FFu) - 559u;
-    if (unsafe || ex > 929u) return x / d;
+    // (a zero numerator -- an origin exactly on the split plane, 1.2 % of the Cornell box's branch visits -- stays on
+    // the shortcut: q = +-0 and both corrections keep it zero; only the SIGN of a zero quotient may differ from the
+    // division's, and the traversal compares plane distances, it never looks at the sign of a zero)
+    if (unsafe || ex > 929u) {
+        if (unsafe || x != 0.0) return x / d;
+    }
     double q = x * r;
     double e = fma(-d, q, x);
     return fma(e, r, q);
