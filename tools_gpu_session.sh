@@ -29,6 +29,8 @@ variants)
 lib:*)
   L=${S#lib:}
   RSB_LIBRARY=$PWD/build/$L.so timeout 300 python bench.py $B > $O/${TAG}_b_$L.json 2> $O/${TAG}_b_$L.err; show $O/${TAG}_b_$L.json ;;
+philox)
+  timeout 300 python bench.py $B --rng philox > $O/${TAG}_b_philox.json 2> $O/${TAG}_b_philox.err; show $O/${TAG}_b_philox.json ;;
 full)
   timeout 900 python bench.py > $O/${TAG}_bench_full.json 2> $O/${TAG}_bench_full.err; show $O/${TAG}_bench_full.json ;;
 list|list:*)
