@@ -42,6 +42,16 @@ ncu:*)
   K=${S#ncu:}
   RSB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none -k regex:$K -s 200 -c 1 -f -o $O/${TAG}_full_$K \
     python bench.py --pixels 1024 --spp 64 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_$K.log 2>&1 ;;
+sweeplib:*)
+  L=${S#sweeplib:}
+  RSB_LIBRARY=$PWD/build/$L.so timeout 900 python tools_sweep.py --n 1e7 --mesh-subdiv 8 > $O/${TAG}_sweep_$L.jsonl 2> $O/${TAG}_sweep_$L.err
+  echo "== $L"; python - $O/${TAG}_sweep_$L.jsonl <<'PY'
+import json,sys
+for l in open(sys.argv[1]):
+    d=json.loads(l)
+    if "rays" in d: print(d["scene"], "rays %g"%d["rays"], "Mrays/s %.1f"%d["Mrays_per_s"], "frac %.3f"%d["roofline_frac"], "KB/ray %.2f"%(d["algorithmic_bytes_per_ray"]/1e3))
+PY
+  ;;
 sweep)
   timeout 900 python tools_sweep.py --n 1e6 1e7 1e8 --mesh-subdiv 8 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err; cut -c1-400 $O/${TAG}_sweep.jsonl ;;
 *) echo "unknown step $S" ;;
