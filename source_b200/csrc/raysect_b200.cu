@@ -580,12 +580,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     smem_scene += ax_bytes(FEAT);   // RayAx storage of k_wf_trace behind the staged scene
     if (RNGMODE == RNG_MT19937_64) smem_shade += RSB_MT_WIN_WORDS * 8 * threads;   // k_wf_shade: MT state window per thread
     if (smem_scene > 48 * 1024)
-    {
-        if constexpr ((FEAT & RSB_FEAT_ALL) == 0)
-            RSB_CUDA(cudaFuncSetAttribute(k_wf_trace_persistent<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
-        else
-            RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
-    }
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
@@ -620,11 +615,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b], s));
             }
-            // analytic-only scenes: persistent lanes, one resident set of CTAs (5 per SM); meshes / CSG: one ray per thread
-            if constexpr ((FEAT & RSB_FEAT_ALL) == 0)
-                k_wf_trace_persistent<RNGMODE, COUNT, FEAT><<<std::min(grid, c->sm_count * 5), threads, smem_scene, s>>>(a);
-            else
-                k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
+            k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
             if (time_trace) {
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b + 1], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b + 1], s));

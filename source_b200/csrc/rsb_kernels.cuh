@@ -530,9 +530,38 @@ __global__ void __launch_bounds__(128) k_wf_init(const __grid_constant__ WfArgs 
     wf_regenerate<RNGMODE>(a, slot);
 }
 
-// 1 thread = 1 slot.  (A persistent-lane variant, where a lane picks up its next slot as soon as its ray
-// finishes, was measured SLOWER on the Cornell scene -- 208 vs 129 us per 262k-ray wave, 9.1 vs 10.0 active
-// lanes per instruction: iteration counts per ray vary little here, and the refill path diverges.)
+// Warp-aggregated append of every lane's slot to list `list` (0..3: per-material hit lists, 4: ended list, < 0:
+// nothing): ballots first, then lanes 0..4 issue the (up to) five atomics of the warp together, then every lane
+// takes its place.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void wf_append_lists(const WfArgs& a, int list, int slot) {
+    const int lane = threadIdx.x & 31;
+    const size_t P = (size_t)a.n_slots;
+    unsigned masks[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l) masks[l] = __ballot_sync(RSB_FULL_MASK, list == l);
+    unsigned int base = 0;
+    if (lane < 5) {
+        unsigned mine = lane == 0 ? masks[0] : lane == 1 ? masks[1] : lane == 2 ? masks[2] : lane == 3 ? masks[3] : masks[4];
+        if (mine) {
+            unsigned int* ctr = (lane < 4) ? &a.st.n_hit[lane] : &a.st.n_ended[a.wave & 1];
+            base = atomicAdd(ctr, (unsigned int)__popc(mine));
+        }
+    }
+    unsigned int b = __shfl_sync(RSB_FULL_MASK, base, list < 0 ? 0 : list);
+    if (list >= 0) {
+        unsigned m = list == 0 ? masks[0] : list == 1 ? masks[1] : list == 2 ? masks[2] : list == 3 ? masks[3] : masks[4];
+        unsigned int k = b + __popc(m & ((1u << lane) - 1));
+        if (list < 4) a.st.hit_list[(size_t)list * P + k] = slot;
+        else a.st.ended[(size_t)(a.wave & 1) * P + k] = slot;
+    }
+}
+
+// 1 thread = 1 slot.  (Persistent lanes with batched refill -- the form k_hit_sweep uses -- were tried here twice.
+// Round-1 first attempt: 208 vs 129 us per 262k-ray wave.  Second attempt, after the kernel had lost its RNG
+// state and most of its instructions: 14.4 instead of 10.9 active lanes per instruction and 18 % fewer warp
+// instructions, yet 143 vs 131 us per 1M-ray wave, and the lists it emits are less ordered, which cost
+// k_wf_shade / k_wf_regen another 15-30 %.  A Cornell ray is ~3 traversal units long: too short to amortise the
+// flush + refill.  See profiles/README.md.)
 template <int RNGMODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_ALL) ? RSB_TRACE_MIN_BLOCKS : 5) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -577,170 +606,13 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_ALL) ? RSB_TRACE_MIN_BLO
             list = 4;                                                // ended list
         }
     }
-    // compact into the five lists: ballots first, then lanes 0..4 issue the five atomics of the warp TOGETHER
-    // (one round trip instead of five back-to-back ones), then every lane takes its slot in its list
+    // compact into the five lists (one atomic per warp and list)
     __syncwarp();
-    {
-        const int lane = threadIdx.x & 31;
-        unsigned masks[5];
-#pragma unroll
-        for (int l = 0; l < 5; ++l) masks[l] = __ballot_sync(RSB_FULL_MASK, list == l);
-        unsigned int base = 0;
-        if (lane < 5) {
-            unsigned mine = lane == 0 ? masks[0] : lane == 1 ? masks[1] : lane == 2 ? masks[2] : lane == 3 ? masks[3] : masks[4];
-            if (mine) {
-                unsigned int* ctr = (lane < 4) ? &a.st.n_hit[lane] : &a.st.n_ended[a.wave & 1];
-                base = atomicAdd(ctr, (unsigned int)__popc(mine));
-            }
-        }
-        unsigned int b = __shfl_sync(RSB_FULL_MASK, base, list < 0 ? 0 : list);
-        if (list >= 0) {
-            unsigned m = list == 0 ? masks[0] : list == 1 ? masks[1] : list == 2 ? masks[2] : list == 3 ? masks[3] : masks[4];
-            unsigned int k = b + __popc(m & ((1u << lane) - 1));
-            if (list < 4) a.st.hit_list[(size_t)list * P + k] = slot;
-            else a.st.ended[(size_t)(a.wave & 1) * P + k] = slot;
-        }
-    }
+    wf_append_lists(a, list, slot);
     if (COUNT) {
         __syncwarp();
         hits = warp_sum(hits);
         if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&a.counters->rays, hits);
-        flush_stats(stats, a.counters);
-    }
-}
-
-// Warp-aggregated append of every lane's slot to list `list` (0..3: per-material hit lists, 4: ended list, < 0:
-// nothing): ballots first, then lanes 0..4 issue the (up to) five atomics of the warp together, then every lane
-// takes its place.  Must be reached by all 32 lanes.
-__device__ __forceinline__ void wf_append_lists(const WfArgs& a, int list, int slot) {
-    const int lane = threadIdx.x & 31;
-    const size_t P = (size_t)a.n_slots;
-    unsigned masks[5];
-#pragma unroll
-    for (int l = 0; l < 5; ++l) masks[l] = __ballot_sync(RSB_FULL_MASK, list == l);
-    unsigned int base = 0;
-    if (lane < 5) {
-        unsigned mine = lane == 0 ? masks[0] : lane == 1 ? masks[1] : lane == 2 ? masks[2] : lane == 3 ? masks[3] : masks[4];
-        if (mine) {
-            unsigned int* ctr = (lane < 4) ? &a.st.n_hit[lane] : &a.st.n_ended[a.wave & 1];
-            base = atomicAdd(ctr, (unsigned int)__popc(mine));
-        }
-    }
-    unsigned int b = __shfl_sync(RSB_FULL_MASK, base, list < 0 ? 0 : list);
-    if (list >= 0) {
-        unsigned m = list == 0 ? masks[0] : list == 1 ? masks[1] : list == 2 ? masks[2] : list == 3 ? masks[3] : masks[4];
-        unsigned int k = b + __popc(m & ((1u << lane) - 1));
-        if (list < 4) a.st.hit_list[(size_t)list * P + k] = slot;
-        else a.st.ended[(size_t)(a.wave & 1) * P + k] = slot;
-    }
-}
-
-// Persistent-lane form of k_wf_trace for scenes of analytic primitives (the variant k_hit_sweep measured +50 % with
-// on the 10,000-sphere field).  A warp owns a contiguous range of slots.  Every lane advances its ray by one
-// traversal unit (descend to the next leaf + that leaf's tests) per trip; when RSB_REFILL_LANES lanes have run out
-// of work, the warp (a) writes the finished lanes' hit records and appends them to the material / ended lists, and
-// (b) hands those lanes the next slots of the range -- consecutive slots, so the state loads stay coalesced.  The
-// warp no longer idles until its longest ray is done (10.9 of 32 lanes active per instruction in the one-ray-per-
-// thread form).  Results are per slot and do not depend on the order of processing.
-template <int RNGMODE, bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, 5) k_wf_trace_persistent(const __grid_constant__ WfArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    constexpr bool STAGED = (FEAT & RSB_FEAT_STAGED) != 0;
-    Scene sc = a.sc;
-    double* axbuf = ax_storage<STAGED>(smem, sc, a.n_items);
-    stage_scene<STAGED>(sc, smem, a.n_items);
-    typename StatsSel<COUNT>::type stats;
-    const int P = a.n_slots;
-    const size_t PP = (size_t)P;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int per = (P + n_warps - 1) / n_warps;
-    int wnext = warp * per;                                  // uniform across the warp
-    const int wend = wnext + per < P ? wnext + per : P;
-    KdStackEntry stack[RSB_KD_STACK];
-    HitRec rec;
-    WorldLeaf<typename StatsSel<COUNT>::type, FEAT, RSB_RENDER_THREADS> leaf;
-    leaf.sc = &sc;
-    leaf.max_distance = a.cfg.max_distance;
-    leaf.mesh_stack = stack + (RSB_KD_STACK / 2);
-    leaf.mesh_axbuf = axbuf + 9 * RSB_RENDER_THREADS;
-    leaf.best = &rec;
-    leaf.stats = &stats;
-    KdCursor c;
-    c.node = 0; c.sp = 0; c.min_range = 0; c.max_range = 0;
-    bool active = false;
-    int slot = -1, list = -1;        // list >= 0: `slot` has finished, its result waits for the next flush
-    unsigned long long traced = 0;
-    for (;;) {
-        const unsigned active_mask = __ballot_sync(RSB_FULL_MASK, active);
-        const int avail = wend - wnext;
-        if (active_mask == 0 && avail <= 0) break;
-        const int n_idle = 32 - __popc(active_mask);
-        if (avail > 0 && (n_idle >= RSB_REFILL_LANES || active_mask == 0)) {
-            // -- flush: hit records and list entries of the lanes that finished since the last refill
-            if (list >= 0) {
-                if (list < 4) {
-                    a.st.hit_t[slot] = rec.t;
-                    a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
-                    if (FEAT & RSB_FEAT_MESH) a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
-                    a.st.status[slot] = SLOT_HIT;
-                } else {
-                    a.st.status[slot] = SLOT_ENDED_ZERO;
-                }
-            }
-            wf_append_lists(a, list, slot);
-            list = -1;
-            // -- refill: idle lane of rank r takes slot wnext + r
-            if (!active) {
-                const int rank = __popc(~active_mask & ((1u << lane) - 1));
-                if (rank < avail) {
-                    slot = wnext + rank;
-                    const int status = a.st.status[slot];
-                    const double normalisation = a.st.norm[slot];
-                    V3 o = v3(a.st.ray[0 * PP + slot], a.st.ray[1 * PP + slot], a.st.ray[2 * PP + slot]);
-                    V3 d = v3(a.st.ray[3 * PP + slot], a.st.ray[4 * PP + slot], a.st.ray[5 * PP + slot]);
-                    if (status == SLOT_ALIVE) {
-                        if (normalisation == 0.0) {
-                            list = 4;                    // ended by the roulette played in k_wf_shade / k_wf_regen
-                        } else {
-                            traced += 1;
-                            leaf.ax.set(axbuf, o, d);
-                            rec.u = rec.v = rec.w = 0.0f;
-                            rec.node = -1;
-                            rec.mesh_node = -1;
-                            if (kd_begin(sc.world, leaf.ax, c)) active = true;
-                            else list = 4;               // misses the world
-                        }
-                    }
-                }
-            }
-            wnext += n_idle < avail ? n_idle : avail;
-        }
-        if (active) {
-            int r = kd_advance(sc.world, leaf.ax, stack, c, leaf, stats, &rec.node);
-            if (r != KD_MORE) {
-                active = false;
-                list = (r == KD_HIT) ? a.sp.mats[sc.prims[rec.prim].material].type : 4;
-            }
-        }
-    }
-    // -- final flush
-    if (list >= 0) {
-        if (list < 4) {
-            a.st.hit_t[slot] = rec.t;
-            a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
-            if (FEAT & RSB_FEAT_MESH) a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
-            a.st.status[slot] = SLOT_HIT;
-        } else {
-            a.st.status[slot] = SLOT_ENDED_ZERO;
-        }
-    }
-    wf_append_lists(a, list, slot);
-    if (COUNT) {
-        __syncwarp();
-        traced = warp_sum(traced);
-        if (lane == 0 && traced) atomicAdd(&a.counters->rays, traced);
         flush_stats(stats, a.counters);
     }
 }
