@@ -243,7 +243,8 @@ def run_ours(args):
     alg_step = algorithmic_bytes(counters, w["bins"], w["spp"])
     # the dominant kernel, k_wf_trace, owns the World.hit part of the model: ray in/out + kd nodes + leaf items +
     # primitive tests of the hit queries (the contains-query and table/frame terms belong to shade/finalize)
-    alg = trace_algorithmic_bytes(counters)
+    # rank 0's own share of the frame against rank 0's own kernel time: the roofline is a per-GPU figure
+    alg = trace_algorithmic_bytes(renderer.local_counters)
     peaks = {}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -255,9 +256,10 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "render_traffic.json")
     if os.path.exists(tp):
+        # ncu --set full of one mid-frame k_wf_trace launch: (dram__bytes_read.sum + dram__bytes_write.sum) / rays traced
         traffic = json.load(open(tp)).get("dram_bytes_per_ray")
         if traffic is not None:
-            traffic = traffic * counters["rays"]
+            traffic = traffic * renderer.local_counters["rays"] / max(1.0, trace_launches / args.steps)
 
     # ---- CPU baseline (rank 0, N = 1 only): the compiled reference in a clean subprocess --------------------
     cpu = None

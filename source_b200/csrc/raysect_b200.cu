@@ -67,20 +67,24 @@ struct Context {
 
 const size_t kMaxStageBytes = 96 * 1024;
 
-// Kernels are instantiated per scene feature set (rsb_geom.h RSB_FEAT_*): analytic primitives only vs everything
-// (meshes, CSG), and world-level data staged in shared memory vs read from HBM/L2.  M(COUNT, FEAT) is expanded
+// Kernels are instantiated per scene feature set (rsb_geom.h RSB_FEAT_*): analytic primitives only, + meshes, or
+// everything (meshes and CSG), and world-level data staged in shared memory vs read from HBM/L2.  M(COUNT, FEAT) is expanded
 // with compile-time constants.
-#define RSB_DISPATCH_FEAT(count, plain, staged, M)                                                     \
+#define RSB_DISPATCH_FEAT(count, feat, staged, M)                                                      \
     do {                                                                                               \
-        const int feat_ = ((plain) ? 0 : RSB_FEAT_ALL) | ((staged) ? RSB_FEAT_STAGED : 0);             \
+        const int feat_ = (feat) | ((staged) ? RSB_FEAT_STAGED : 0);                                   \
         if (count) {                                                                                   \
             if (feat_ == 0) M(true, 0);                                                                \
             else if (feat_ == RSB_FEAT_STAGED) M(true, RSB_FEAT_STAGED);                               \
+            else if (feat_ == RSB_FEAT_MESH) M(true, RSB_FEAT_MESH);                                   \
+            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(true, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
             else if (feat_ == RSB_FEAT_ALL) M(true, RSB_FEAT_ALL);                                     \
             else M(true, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                            \
         } else {                                                                                       \
             if (feat_ == 0) M(false, 0);                                                               \
             else if (feat_ == RSB_FEAT_STAGED) M(false, RSB_FEAT_STAGED);                              \
+            else if (feat_ == RSB_FEAT_MESH) M(false, RSB_FEAT_MESH);                                  \
+            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(false, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
             else if (feat_ == RSB_FEAT_ALL) M(false, RSB_FEAT_ALL);                                    \
             else M(false, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                           \
         }                                                                                              \
@@ -372,9 +376,9 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 16);
-    const bool plain = !ds->has_mesh && !ds->has_csg;
+    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
     const int staged = ds->stage_bytes ? 1 : 0;
-    size_t smem = ds->stage_bytes + ax_bytes(plain ? 0 : RSB_FEAT_ALL);
+    size_t smem = ds->stage_bytes + ax_bytes(feat);
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
 #define RSB_LAUNCH_HIT(C, F)                                                                                              \
     do {                                                                                                                  \
@@ -382,7 +386,7 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
         k_hit_batch<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, origins, directions, max_distance, \
                                                    out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters); \
     } while (0)
-    RSB_DISPATCH_FEAT(count != 0, plain, staged, RSB_LAUNCH_HIT);
+    RSB_DISPATCH_FEAT(count != 0, feat, staged, RSB_LAUNCH_HIT);
 #undef RSB_LAUNCH_HIT
     RSB_CUDA(cudaGetLastError());
     if (count) {
@@ -457,9 +461,9 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     int grid = grid_for(c, n, 128, 8);
-    const bool plain = !ds->has_mesh && !ds->has_csg;
+    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
     const int staged = ds->stage_bytes ? 1 : 0;
-    size_t smem = ds->stage_bytes + ax_bytes(plain ? 0 : RSB_FEAT_ALL);
+    size_t smem = ds->stage_bytes + ax_bytes(feat);
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
 #define RSB_LAUNCH_SWEEP(C, F)                                                                                            \
     do {                                                                                                                  \
@@ -468,7 +472,7 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
                                                    target[0], target[1], target[2], half_window, (unsigned long long*)out_hits_dev, out_sum_t_dev, \
                                                    (unsigned long long*)out_xor_prim_dev, c->d_counters);             \
     } while (0)
-    RSB_DISPATCH_FEAT(count != 0, plain, staged, RSB_LAUNCH_SWEEP);
+    RSB_DISPATCH_FEAT(count != 0, feat, staged, RSB_LAUNCH_SWEEP);
 #undef RSB_LAUNCH_SWEEP
     RSB_CUDA(cudaGetLastError());
     if (count) {
@@ -818,11 +822,11 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
         RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
         RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
         // kernels are instantiated for "analytic primitives only" and for "everything" (meshes and CSG)
-        const bool plain = !ds->has_mesh && !ds->has_csg;
+        const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
 #define RSB_RUN_MT(C, F) rc = run_wavefront<RNG_MT19937_64, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
 #define RSB_RUN_PX(C, F) rc = run_wavefront<RNG_PHILOX, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-        if (mt) RSB_DISPATCH_FEAT(count != 0, plain, a.staged, RSB_RUN_MT);
-        else RSB_DISPATCH_FEAT(count != 0, plain, a.staged, RSB_RUN_PX);
+        if (mt) RSB_DISPATCH_FEAT(count != 0, feat, a.staged, RSB_RUN_MT);
+        else RSB_DISPATCH_FEAT(count != 0, feat, a.staged, RSB_RUN_PX);
 #undef RSB_RUN_MT
 #undef RSB_RUN_PX
     }

@@ -131,6 +131,7 @@ class FrameRenderer:
         """Untimed pass with the traversal counters switched on (roofline model inputs)."""
         self._render(seed, self.dev_pixels, count=True)
         c = self.accel.device.counters()
+        self.local_counters = dict(c)      # this rank's share (per-GPU roofline)
         if self.world_size > 1:
             import torch.distributed as dist
             keys = sorted(c)

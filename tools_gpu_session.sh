@@ -52,8 +52,11 @@ for l in open(sys.argv[1]):
     if "rays" in d: print(d["scene"], "rays %g"%d["rays"], "Mrays/s %.1f"%d["Mrays_per_s"], "frac %.3f"%d["roofline_frac"], "KB/ray %.2f"%(d["algorithmic_bytes_per_ray"]/1e3))
 PY
   ;;
+ncusweep)
+  timeout 900 ncu --set full --clock-control none -k regex:k_hit_sweep -s 2 -c 1 -f -o $O/${TAG}_full_sweep_mesh \
+    python tools_sweep.py --n 4e6 --mesh-subdiv 8 --no-spheres > $O/${TAG}_ncusweep.log 2>&1; tail -n 3 $O/${TAG}_ncusweep.log ;;
 sweep)
-  timeout 900 python tools_sweep.py --n 1e6 1e7 1e8 --mesh-subdiv 8 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err; cut -c1-400 $O/${TAG}_sweep.jsonl ;;
+  timeout 900 python tools_sweep.py --n 1e7 --mesh-subdiv 8 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err; cut -c1-400 $O/${TAG}_sweep.jsonl ;;
 *) echo "unknown step $S" ;;
 esac
 done

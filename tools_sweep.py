@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--spheres", type=int, default=10000)
     ap.add_argument("--n", type=float, nargs="+", default=[1e5, 1e6, 1e7, 1e8])
     ap.add_argument("--mesh-subdiv", type=int, default=0, help="also sweep a Cornell box holding a 20*4^k-triangle mesh")
+    ap.add_argument("--no-spheres", action="store_true", help="skip the sphere field (profiling the mesh scene)")
     args = ap.parse_args()
     dev = Device(0)
     peak = 6554.2
@@ -67,12 +68,13 @@ def main():
                               "algorithmic_bytes_per_ray": per_ray, "achieved_GBps": achieved, "roofline_frac": achieved / peak,
                               "per_ray": {k: c[k] / c["rays"] for k in ("branches", "leaves", "items", "prim_tests", "tri_tests")}}), flush=True)
 
-    world = scenes.random_spheres(api, args.spheres, seed=7)
-    t0 = time.time()
-    acc = dev.build(world)
-    print(json.dumps({"scene": "%d spheres" % args.spheres, "flatten_build_upload_s": time.time() - t0}), flush=True)
-    sweep("%d spheres" % args.spheres, acc, (0, 0, -4.0), (0, 0, 0), 0.9, args.n)
-    acc.close()
+    if not args.no_spheres:
+        world = scenes.random_spheres(api, args.spheres, seed=7)
+        t0 = time.time()
+        acc = dev.build(world)
+        print(json.dumps({"scene": "%d spheres" % args.spheres, "flatten_build_upload_s": time.time() - t0}), flush=True)
+        sweep("%d spheres" % args.spheres, acc, (0, 0, -4.0), (0, 0, 0), 0.9, args.n)
+        acc.close()
 
     if args.mesh_subdiv:
         verts, tris, normals = scenes.icosphere(args.mesh_subdiv, radius=0.45, bumps=0.15)
