@@ -1030,55 +1030,73 @@ struct WorldLeaf {
 // per trip, whatever world-level path brought them there.  Per ray the sequence of AABB tests, primitive tests,
 // mesh leaf visits and triangle tests -- and therefore every comparison and tie rule -- is exactly that of
 // world_hit_ax / _PrimitiveKDTree._trace_leaf; only the interleaving BETWEEN rays changes.
+// The traversal is a resumable object so that kernels can interleave it with lane refill (k_hit_sweep):
+//   begin(o, d)  world-level work up to the first mesh unit; false: the ray is finished already
+//   step()       ONE mesh traversal unit (descend to the next mesh leaf + its triangle tests), then the world-level
+//                work that follows it; false: the ray is finished
+//   finish()     closest hit found?
 template <int FEAT, int S, class Stats>
-RSB_HD bool world_hit_nested(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats,
-                             double* axbuf) {
+struct NestedTraversal {
+    enum { ST_WORLD = 0, ST_MESH = 1, ST_DONE = 2 };
+    const Scene* sc;
+    Stats* stats;
+    KdStackEntry* stack;
+    HitRec* rec;
     WorldLeaf<Stats, FEAT, S> leaf;
-    leaf.sc = &sc;
-    leaf.ax.set(axbuf, o, d);
-    leaf.max_distance = max_distance;
-    leaf.mesh_stack = stack + (RSB_KD_STACK / 2);
-    leaf.mesh_axbuf = axbuf + 9 * S;
-    leaf.best = rec;
-    leaf.stats = &stats;
-    rec->u = rec->v = rec->w = 0.0f;
-    rec->node = -1;
-    rec->mesh_node = -1;
-    KdCursor c;
-    if (!kd_begin(sc.world, leaf.ax, c)) return false;
-    int node = 0, sp = 0, leaf_node = -1;
-    double min_range = c.min_range, max_range = c.max_range;
-    int item_offset = 0, item_count = 0, item_base = 0;   // the world leaf being processed, and how far
+    int node, sp, leaf_node;
+    double min_range, max_range;
+    int item_offset, item_count, item_base;   // the world leaf being processed, and how far
     int cand[4];
-    int nc = 0, ci = 0;
-    bool have_leaf = false, found = false;
-    double distance = 0.0;
+    int nc, ci;
+    bool have_leaf, found;
+    double distance;
+    int state;
     // nested mesh traversal of candidate cand[ci]
     RayAx<S> max;
-    max.p = leaf.mesh_axbuf;
-    max.unsafe = 0;
     KdCursor mc;
-    mc.node = 0; mc.sp = 0; mc.min_range = 0; mc.max_range = 0;
     MeshLeaf<Stats> mleaf;
     MeshHit mh;
-    mleaf.mesh = nullptr;
-    mleaf.max_distance = max_distance;
-    mleaf.result = &mh;
-    mleaf.stats = &stats;
-    mh.node = -1;
-    enum { ST_WORLD = 0, ST_MESH = 1, ST_DONE = 2 };
-    int state = ST_WORLD;
-    for (;;) {
+
+    RSB_HD void init(const Scene& scene, double max_distance, KdStackEntry* stack_, HitRec* rec_, Stats& stats_, double* axbuf) {
+        sc = &scene;
+        stats = &stats_;
+        stack = stack_;
+        rec = rec_;
+        leaf.sc = &scene;
+        leaf.ax.p = axbuf;
+        leaf.ax.unsafe = 0;
+        leaf.max_distance = max_distance;
+        leaf.mesh_stack = stack_ + (RSB_KD_STACK / 2);
+        leaf.mesh_axbuf = axbuf + 9 * S;
+        leaf.best = rec_;
+        leaf.stats = &stats_;
+        max.p = leaf.mesh_axbuf;
+        max.unsafe = 0;
+        mc.node = 0; mc.sp = 0; mc.min_range = 0; mc.max_range = 0;
+        mleaf.mesh = nullptr;
+        mleaf.max_distance = max_distance;
+        mleaf.result = &mh;
+        mleaf.stats = &stats_;
+        mh.node = -1;
+        state = ST_DONE;
+        found = false;
+        node = sp = 0; leaf_node = -1;
+        min_range = max_range = distance = 0.0;
+        item_offset = item_count = item_base = nc = ci = 0;
+        have_leaf = false;
+    }
+
+    RSB_HD void run_world() {
         while (state == ST_WORLD) {
             if (ci < nc) {
                 const int id = cand[ci];
-                const Prim& p = sc.prims[id];
+                const Prim& p = sc->prims[id];
                 if (p.type == PRIM_MESH) {
                     const V3 wo = leaf.ax.O(), wd = leaf.ax.D();
                     const V3 lo = xform_point(p.to_local, wo);
                     const V3 ld = xform_vector(p.to_local, wd);
                     max.set(leaf.mesh_axbuf, lo, ld);
-                    mleaf.mesh = &sc.meshes[p.mesh];
+                    mleaf.mesh = &sc->meshes[p.mesh];
                     mleaf.o = lo;
                     mleaf.rs = mesh_rayspace(ld);
                     if (kd_begin(mleaf.mesh->tree, max, mc)) state = ST_MESH;   // MeshData.trace, mesh.pyx:506-518
@@ -1094,9 +1112,9 @@ RSB_HD bool world_hit_nested(const Scene& sc, const V3& o, const V3& d, double m
                 nc = 0;
                 ci = 0;
                 for (int i = 0; i < end; ++i) {
-                    int id = sc.world.items[item_offset + item_base + i];
-                    stats.prim_test();
-                    if (box_hit_inv(sc.prims[id].bbox, ro, rd, inv)) cand[nc++] = id;
+                    int id = sc->world.items[item_offset + item_base + i];
+                    stats->prim_test();
+                    if (box_hit_inv(sc->prims[id].bbox, ro, rd, inv)) cand[nc++] = id;
                 }
                 item_base += end;
             } else if (have_leaf) {
@@ -1106,22 +1124,42 @@ RSB_HD bool world_hit_nested(const Scene& sc, const V3& o, const V3& d, double m
                 if (found || sp == 0) state = ST_DONE;
                 else { --sp; node = stack[sp].node; min_range = max_range; max_range = stack[sp].tmax; }
             } else {
-                KdNode n = kd_descend(sc.world, leaf.ax, stack, node, sp, min_range, max_range, stats);
-                stats.leaf(n.leaf.item_count);
+                KdNode n = kd_descend(sc->world, leaf.ax, stack, node, sp, min_range, max_range, *stats);
+                stats->leaf(n.leaf.item_count);
                 leaf_node = node;
                 item_offset = n.leaf.item_offset;
                 item_count = n.leaf.item_count;
                 item_base = 0;
                 nc = 0;
                 ci = 0;
-                distance = max_distance < max_range ? max_distance : max_range;
+                distance = leaf.max_distance < max_range ? leaf.max_distance : max_range;
                 found = false;
                 have_leaf = true;
             }
         }
-        if (state == ST_DONE) break;
-        // one unit of the nested mesh traversal: descend to the next mesh leaf + its triangle tests
-        const int r = kd_advance(mleaf.mesh->tree, max, leaf.mesh_stack, mc, mleaf, stats, &mh.node);
+    }
+
+    RSB_HD bool begin(const V3& o, const V3& d) {
+        leaf.ax.set(leaf.ax.p, o, d);
+        rec->u = rec->v = rec->w = 0.0f;
+        rec->node = -1;
+        rec->mesh_node = -1;
+        found = false;
+        have_leaf = false;
+        nc = ci = item_base = item_count = 0;
+        node = 0;
+        sp = 0;
+        KdCursor c;
+        if (!kd_begin(sc->world, leaf.ax, c)) { state = ST_DONE; return false; }
+        min_range = c.min_range;
+        max_range = c.max_range;
+        state = ST_WORLD;
+        run_world();
+        return state != ST_DONE;
+    }
+
+    RSB_HD bool step() {
+        const int r = kd_advance(mleaf.mesh->tree, max, leaf.mesh_stack, mc, mleaf, *stats, &mh.node);
         if (r != KD_MORE) {
             if (r == KD_HIT && mh.t <= distance) {
                 const int id = cand[ci];
@@ -1133,10 +1171,26 @@ RSB_HD bool world_hit_nested(const Scene& sc, const V3& o, const V3& d, double m
             }
             ++ci;
             state = ST_WORLD;
+            run_world();
         }
+        return state != ST_DONE;
     }
-    if (found) rec->node = leaf_node;
-    return found;
+
+    RSB_HD bool finish() {
+        if (found) rec->node = leaf_node;
+        return found;
+    }
+};
+
+template <int FEAT, int S, class Stats>
+RSB_HD bool world_hit_nested(const Scene& sc, const V3& o, const V3& d, double max_distance, KdStackEntry* stack, HitRec* rec, Stats& stats,
+                             double* axbuf) {
+    NestedTraversal<FEAT, S, Stats> t;
+    t.init(sc, max_distance, stack, rec, stats, axbuf);
+    if (t.begin(o, d)) {
+        while (t.step()) {}
+    }
+    return t.finish();
 }
 
 // Closest hit of a world-space ray.  `stack` must hold RSB_KD_STACK entries, `axbuf` RSB_AX_WORDS * S doubles

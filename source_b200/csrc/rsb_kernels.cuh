@@ -189,30 +189,45 @@ k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned 
     double sum_t = 0.0;
     long long stride = (long long)gridDim.x * blockDim.x;
     V3 o = v3(ox, oy, oz);
-    // scenes with meshes: one ray per thread at a time (a world-level traversal unit contains a whole nested mesh
-    // traversal, so world-level refill does not even out the lanes: measured 126 vs 156 Mrays/s on 1.3 M triangles)
-    if constexpr ((FEAT & RSB_FEAT_MESH) != 0) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Philox4x32 px;
-        px.init(seed, (unsigned long long)(first_index + i), 0u);
-        double u1 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-        double u2 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-        V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
-        V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
-        HitRec rec;
-        if (world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, o, d, RSB_INF, stack, &rec, stats, axbuf)) {
-            hits += 1;
-            sum_t += rec.t;
-            xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + i);
-        }
-    }
-    } else
     // Persistent lanes with batched refill (Aila & Laine): every lane owns the rays i, i + stride, ... and advances
-    // its current ray by ONE traversal unit (descend to the next leaf + that leaf's tests) per trip; lanes whose
-    // ray has ended pick up their next ray only when at least RSB_REFILL_LANES lanes are waiting (or nothing else
-    // is left to do), so the ray set-up code runs with a well filled warp instead of once per finished lane.  Rays
-    // of different lengths no longer hold a whole warp until the longest one is done.
-    {
+    // its current ray by ONE traversal unit per trip; lanes whose ray has ended pick up their next ray only when at
+    // least RSB_REFILL_LANES lanes are waiting (or nothing else is left to do), so the ray set-up code runs with a
+    // well filled warp instead of once per finished lane.  Rays of different lengths no longer hold a whole warp
+    // until the longest one is done.  Scenes with meshes: the unit is one MESH traversal unit (NestedTraversal).
+    if constexpr ((FEAT & RSB_FEAT_MESH) != 0) {
+        HitRec rec;
+        NestedTraversal<FEAT, RSB_RENDER_THREADS, typename StatsSel<COUNT>::type> t;
+        t.init(sc, RSB_INF, stack, &rec, stats, axbuf);
+        bool active = false;
+        long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
+        for (;;) {
+            const bool want = !active && next < n;
+            const unsigned want_mask = __ballot_sync(RSB_FULL_MASK, want);
+            const unsigned active_mask = __ballot_sync(RSB_FULL_MASK, active);
+            if (active_mask == 0 && want_mask == 0) break;
+            bool ended = false;
+            if (want && (__popc(want_mask) >= RSB_REFILL_LANES || active_mask == 0)) {
+                cur = next;
+                next += stride;
+                Philox4x32 px;
+                px.init(seed, (unsigned long long)(first_index + cur), 0u);
+                double u1 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
+                double u2 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
+                V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
+                V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
+                active = t.begin(o, d);
+                ended = !active;
+            } else if (active) {
+                active = t.step();
+                ended = !active;
+            }
+            if (ended && t.finish()) {
+                hits += 1;
+                sum_t += rec.t;
+                xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + cur);
+            }
+        }
+    } else {
         HitRec rec;
         WorldLeaf<typename StatsSel<COUNT>::type, FEAT, RSB_RENDER_THREADS> leaf;
         leaf.sc = &sc;
