@@ -1158,10 +1158,41 @@ struct NestedTraversal {
         return state != ST_DONE;
     }
 
-    RSB_HD bool step() {
-        const int r = kd_advance(mleaf.mesh->tree, max, leaf.mesh_stack, mc, mleaf, *stats, &mh.node);
-        if (r != KD_MORE) {
-            if (r == KD_HIT && mh.t <= distance) {
+    // step() in three parts, so that kernels can run the triangle tests of a whole warp's leaves cooperatively
+    // (rsb_kernels.cuh mesh_leaf_coop) between the first and the last:
+    //   step_descend()        _trace_branch down to the next mesh leaf: m_off / m_cnt / mc.max_range describe it
+    //   (leaf test)           MeshData._trace_leaf over the leaf's triangles -> mh, true on a hit
+    //   step_resolve(hit)     the rest of kd_advance, and the world-level work that follows
+    int m_off, m_cnt;
+    RSB_HD void step_descend() {
+        int mnode = mc.node, msp = mc.sp;
+        double mr = mc.max_range;
+        KdNode n = kd_descend(mleaf.mesh->tree, max, leaf.mesh_stack, mnode, msp, mc.min_range, mr, *stats);
+        stats->leaf(n.leaf.item_count);
+        mc.node = mnode;
+        mc.sp = msp;
+        mc.max_range = mr;
+        m_off = n.leaf.item_offset;
+        m_cnt = n.leaf.item_count;
+    }
+
+    RSB_HD bool step_resolve(bool leaf_hit) {
+        bool finished;
+        if (leaf_hit) {
+            mh.node = mc.node;
+            finished = true;
+        } else if (mc.sp == 0) {
+            finished = true;
+        } else {
+            // the far child resumes with min_range = the plane distance = max_range of the leaf just left
+            --mc.sp;
+            mc.node = leaf.mesh_stack[mc.sp].node;
+            mc.min_range = mc.max_range;
+            mc.max_range = leaf.mesh_stack[mc.sp].tmax;
+            finished = false;
+        }
+        if (finished) {
+            if (leaf_hit && mh.t <= distance) {
                 const int id = cand[ci];
                 distance = mh.t;
                 rec->t = mh.t; rec->prim = id; rec->leaf = id; rec->code = mh.tri; rec->flip = 0;
@@ -1174,6 +1205,12 @@ struct NestedTraversal {
             run_world();
         }
         return state != ST_DONE;
+    }
+
+    RSB_HD bool step() {
+        step_descend();
+        const bool leaf_hit = m_cnt > 0 && mleaf(m_off, m_cnt, mc.max_range);
+        return step_resolve(leaf_hit);
     }
 
     RSB_HD bool finish() {

@@ -114,12 +114,139 @@ __device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int 
 
 // RayAx storage of the calling thread (rsb_geom.h): RSB_AX_WORDS columns of blockDim.x doubles behind the staged
 // scene.  Kernels that use it are launched with RSB_RENDER_THREADS threads and ax_bytes(FEAT) extra shared memory.
-__host__ __device__ inline int ax_bytes(int feat) { return ((feat & RSB_FEAT_MESH) ? RSB_AX_WORDS : 9) * 8 * RSB_RENDER_THREADS; }
+#define RSB_COOP_CAP 64      // (ray, triangle) pairs a warp tests per cooperative round
+#define RSB_COOP_WARP_BYTES ((36 + 32 + RSB_COOP_CAP) * 4 + RSB_COOP_CAP * 16)
+#define RSB_COOP_BYTES (5 * 4 * RSB_RENDER_THREADS + (RSB_RENDER_THREADS / 32) * RSB_COOP_WARP_BYTES)
+__host__ __device__ inline int ax_bytes(int feat) {
+    return (feat & RSB_FEAT_MESH) ? RSB_AX_WORDS * 8 * RSB_RENDER_THREADS + RSB_COOP_BYTES : 9 * 8 * RSB_RENDER_THREADS;
+}
 
 template <bool STAGED>
 __device__ __forceinline__ double* ax_storage(unsigned char* smem, const Scene& sc, int n_items) {
     int off = STAGED ? stage_layout(sc.world.n_nodes, n_items, sc.n_prims).total : 0;
     return reinterpret_cast<double*>(smem + off) + threadIdx.x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative triangle tests.  In the mesh traversal every lane reaches a leaf with its own number of triangles
+// (0 for ~40 % of the leaves, a dozen for some); looping over them per lane ran the Woop test -- 45 % of the
+// kernel's instructions -- with 1.8 of 32 lanes active (round-1 profile of the 1.3 M-triangle sweep).  Here the
+// warp pools the (ray, triangle) pairs of all its lanes' current leaves and deals them out evenly: pair g belongs
+// to the lane whose exclusive prefix sum of leaf sizes brackets g, the testing lane reads that lane's mesh-local
+// origin and ray-space shear from shared memory, and the owner then replays MeshData._trace_leaf's comparison
+// (`t < distance`, first of equal-t triangles wins, mesh.pyx:520-563) over its own results in leaf order -- the
+// same values through the same comparisons as the sequential loop.
+struct CoopSmem {
+    int32_t* rs_pack;     // [T] ix | iy << 2 | iz << 4 of the thread's ray-space permutation
+    float* rs_s;          // [3][T] sx, sy, sz
+    int32_t* mesh_idx;    // [T]
+    int32_t* prefix;      // warp: [33]
+    int32_t* leaf_off;    // warp: [32]
+    int32_t* res_tri;     // warp: [CAP]
+    float4* res;          // warp: [CAP] (t, u, v, w); t = NaN: no hit
+    const double* ax_cta; // RayAx storage of thread 0 of the CTA
+};
+
+__device__ __forceinline__ CoopSmem coop_carve(double* axbuf_thread) {
+    CoopSmem cs;
+    double* ax0 = axbuf_thread - threadIdx.x;
+    cs.ax_cta = ax0;
+    unsigned char* base = reinterpret_cast<unsigned char*>(ax0 + RSB_AX_WORDS * RSB_RENDER_THREADS);
+    cs.rs_pack = reinterpret_cast<int32_t*>(base);
+    cs.rs_s = reinterpret_cast<float*>(base + 4 * RSB_RENDER_THREADS);
+    cs.mesh_idx = reinterpret_cast<int32_t*>(base + 16 * RSB_RENDER_THREADS);
+    unsigned char* w = base + 20 * RSB_RENDER_THREADS + (threadIdx.x >> 5) * RSB_COOP_WARP_BYTES;
+    cs.res = reinterpret_cast<float4*>(w);
+    cs.prefix = reinterpret_cast<int32_t*>(w + RSB_COOP_CAP * 16);
+    cs.leaf_off = cs.prefix + 36;
+    cs.res_tri = cs.leaf_off + 32;
+    return cs;
+}
+
+// publish the calling thread's ray-space transform and mesh for the lanes that will test its triangles
+__device__ __forceinline__ void coop_publish(const CoopSmem& cs, const RaySpace& rs, int mesh_index) {
+    const int t = threadIdx.x;
+    cs.rs_pack[t] = rs.ix | (rs.iy << 2) | (rs.iz << 4);
+    cs.rs_s[t] = rs.sx;
+    cs.rs_s[RSB_RENDER_THREADS + t] = rs.sy;
+    cs.rs_s[2 * RSB_RENDER_THREADS + t] = rs.sz;
+    cs.mesh_idx[t] = mesh_index;
+}
+
+// All 32 lanes.  in_leaf: this lane stands at a mesh leaf (off, cnt) and accepts hits closer than d0 =
+// min(ray.max_distance, leaf max_range).  true: *mh holds the leaf's closest triangle.
+template <class Stats>
+__device__ __forceinline__ bool mesh_leaf_coop(const Scene& sc, const CoopSmem& cs, bool in_leaf, int off, int cnt, double d0,
+                                               double max_distance, MeshHit* mh, Stats& stats) {
+    const int lane = threadIdx.x & 31;
+    const int tid0 = threadIdx.x & ~31;
+    const int c = in_leaf ? cnt : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(RSB_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - c;
+    const int total = __shfl_sync(RSB_FULL_MASK, incl, 31);
+    if (total == 0) return false;
+    __syncwarp();
+    cs.prefix[lane] = excl;
+    if (lane == 31) cs.prefix[32] = total;
+    cs.leaf_off[lane] = off;
+    double distance = d0;
+    int closest = -1;
+    float cu = 0, cv = 0, cw = 0;
+    for (int base = 0; base < total; base += RSB_COOP_CAP) {
+        __syncwarp();
+        const int lim = total - base < RSB_COOP_CAP ? total - base : RSB_COOP_CAP;
+        for (int p = lane; p < lim; p += 32) {
+            const int g = base + p;
+            int lo = 0, hi = 32;           // prefix[lo] <= g < prefix[hi]
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int mid = (lo + hi) >> 1;
+                if (cs.prefix[mid] <= g) lo = mid; else hi = mid;
+            }
+            const int ot = tid0 + lo;      // the owner's thread index within the CTA
+            const Mesh& m = sc.meshes[cs.mesh_idx[ot]];
+            const int tri = m.tree.items[cs.leaf_off[lo] + (g - cs.prefix[lo])];
+            const double* ax = cs.ax_cta + ot;
+            V3 o = v3(ax[9 * RSB_RENDER_THREADS], ax[10 * RSB_RENDER_THREADS], ax[11 * RSB_RENDER_THREADS]);
+            RaySpace rs;
+            const int pk = cs.rs_pack[ot];
+            rs.ix = pk & 3; rs.iy = (pk >> 2) & 3; rs.iz = (pk >> 4) & 3;
+            rs.sx = cs.rs_s[ot]; rs.sy = cs.rs_s[RSB_RENDER_THREADS + ot]; rs.sz = cs.rs_s[2 * RSB_RENDER_THREADS + ot];
+            float h[4];
+            stats.tri_test();
+            const bool hit = mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, max_distance, rs, h);
+            cs.res_tri[p] = tri;
+            cs.res[p] = hit ? make_float4(h[3], h[0], h[1], h[2]) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (c > 0) {
+            const int j0 = base > excl ? base - excl : 0;
+            const int j1 = base + RSB_COOP_CAP - excl < c ? base + RSB_COOP_CAP - excl : c;
+            for (int j = j0; j < j1; ++j) {
+                const int p = excl + j - base;
+                const float4 r = cs.res[p];
+                if (r.x == r.x) {
+                    const double t = (double)r.x;
+                    if (t < distance) {
+                        distance = t;
+                        closest = cs.res_tri[p];
+                        cu = r.y; cv = r.z; cw = r.w;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (closest < 0) return false;
+    mh->t = (double)(float)distance;
+    mh->tri = closest;
+    mh->u = cu; mh->v = cv; mh->w = cw;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,6 +325,7 @@ k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned 
         HitRec rec;
         NestedTraversal<FEAT, RSB_RENDER_THREADS, typename StatsSel<COUNT>::type> t;
         t.init(sc, RSB_INF, stack, &rec, stats, axbuf);
+        const CoopSmem cs = coop_carve(axbuf);
         bool active = false;
         long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
         for (;;) {
@@ -217,8 +345,16 @@ k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned 
                 V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
                 active = t.begin(o, d);
                 ended = !active;
-            } else if (active) {
-                active = t.step();
+            }
+            // one mesh traversal unit for every lane that is inside a mesh: descend, pooled triangle tests, resolve
+            if (active) {
+                t.step_descend();
+                coop_publish(cs, t.mleaf.rs, (int)(t.mleaf.mesh - sc.meshes));
+            }
+            const double d0 = RSB_INF < t.mc.max_range ? RSB_INF : t.mc.max_range;
+            const bool leaf_hit = mesh_leaf_coop(sc, cs, active, t.m_off, t.m_cnt, d0, RSB_INF, &t.mh, stats);
+            if (active) {
+                active = t.step_resolve(leaf_hit);
                 ended = !active;
             }
             if (ended && t.finish()) {
@@ -602,14 +738,38 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
     const bool active = in_range && status == SLOT_ALIVE;
     unsigned long long hits = 0;
     int list = -1;
-    if (active) {
-        KdStackEntry stack[RSB_KD_STACK];
-        HitRec rec;
-        bool hit = false;
-        if (normalisation != 0.0) {
+    KdStackEntry stack[RSB_KD_STACK];
+    HitRec rec;
+    bool hit = false;
+    if constexpr ((FEAT & RSB_FEAT_MESH) != 0) {
+        // scenes with meshes: the two-level traversal advances in warp-wide trips, one mesh traversal unit per trip,
+        // with the triangle tests of all lanes' leaves pooled (mesh_leaf_coop); every lane of the warp takes part
+        // in the pooled tests, whether or not it still has a ray of its own
+        NestedTraversal<FEAT, RSB_RENDER_THREADS, typename StatsSel<COUNT>::type> t;
+        t.init(sc, a.cfg.max_distance, stack, &rec, stats, axbuf);
+        const CoopSmem cs = coop_carve(axbuf);
+        bool tracing = false;
+        if (active && normalisation != 0.0) {
+            hits = 1;
+            tracing = t.begin(ps.o, ps.d);
+        }
+        while (__any_sync(RSB_FULL_MASK, tracing)) {
+            if (tracing) {
+                t.step_descend();
+                coop_publish(cs, t.mleaf.rs, (int)(t.mleaf.mesh - sc.meshes));
+            }
+            const double d0 = a.cfg.max_distance < t.mc.max_range ? a.cfg.max_distance : t.mc.max_range;
+            const bool leaf_hit = mesh_leaf_coop(sc, cs, tracing, t.m_off, t.m_cnt, d0, a.cfg.max_distance, &t.mh, stats);
+            if (tracing) tracing = t.step_resolve(leaf_hit);
+        }
+        if (hits) hit = t.finish();
+    } else {
+        if (active && normalisation != 0.0) {
             hits = 1;
             hit = world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, ps.o, ps.d, a.cfg.max_distance, stack, &rec, stats, axbuf);
         }
+    }
+    if (active) {
         if (hit) {
             a.st.hit_t[slot] = rec.t;
             a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);

@@ -235,3 +235,96 @@ def test_million_triangle_mesh_properties(make_backend):
     cnt, prims = be.contains_batch(pts, 4)
     assert np.all(cnt[:2000] == 1) and np.all(prims[:2000, 0] == mesh_id) and np.all(cnt[2000:] == 0)
     be.close()
+
+
+def _philox_pair(seed, index):
+    """Philox4x32-10 words 0 and 1 of block 0 of stream `index` (csrc/rsb_rng.h Philox4x32: key = seed,
+    counter = (0, 0, index lo, index hi)) -> two uniform() values, as k_hit_sweep draws them."""
+    index = np.asarray(index, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    c0 = np.zeros_like(index); c1 = np.zeros_like(index)
+    c2 = index & m32; c3 = index >> np.uint64(32)
+    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64(seed >> 32)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    w0 = (c1 << np.uint64(32)) | c0
+    w1 = (c3 << np.uint64(32)) | c2
+    scale = 1.0 / 9007199254740992.0
+    return (w0 >> np.uint64(11)).astype(np.float64) * scale, (w1 >> np.uint64(11)).astype(np.float64) * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["spheres", "mesh"])
+def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind):
+    """The sweep kernels (persistent lanes with refill; for meshes the two-level loop with pooled triangle tests) must
+    report exactly the hits the one-ray-per-thread batch kernel reports for the rays they generate on the device."""
+    import ctypes as C
+    import torch
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    if kind == "spheres":
+        world = scenes.random_spheres(api, 3000, seed=7)
+        origin, target, half = (0.0, 0.0, -4.0), (0.0, 0.0, 0.0), 0.9
+    else:
+        verts, tris, normals = scenes.icosphere(5, radius=0.45, bumps=0.1)     # 20,480 triangles
+
+        def extra(a, w):
+            a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+                   material=a.Lambert(a.ConstantSF(0.7)))
+        world = scenes.cornell_box(api, glass=False, extra=extra)
+        origin, target, half = (0.0, 0.0, -3.3), (0.1, -0.5, 0.1), 0.6
+    acc = device.build(world)
+    n, first, seed = 150000, 1000, 2024
+    hits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sum_t = torch.zeros(1, dtype=torch.float64, device="cuda")
+    xr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), n, first, seed, (C.c_double * 3)(*origin),
+                                            (C.c_double * 3)(*target), half, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
+                                            C.c_void_p(xr.data_ptr()), 0))
+    torch.cuda.synchronize()
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    u1, u2 = _philox_pair(seed, idx)
+    px = target[0] + (2.0 * u1 - 1.0) * half
+    py = target[1] + (2.0 * u2 - 1.0) * half
+    pz = np.full(n, target[2])
+    dx, dy, dz = px - origin[0], py - origin[1], pz - origin[2]
+    t = dx * dx + dy * dy + dz * dz
+    t = 1.0 / np.sqrt(t)
+    d = np.stack([dx * t, dy * t, dz * t], axis=1)
+    o = np.tile(np.array(origin), (n, 1))
+    r = acc.hit_batch(o, d)
+    hit = r.primitive >= 0
+    assert hit.sum() > n // 2
+    assert hits.item() == int(hit.sum())
+    key = (r.primitive[hit].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + idx[hit])
+    assert np.uint64(xr.item() & 0xFFFFFFFFFFFFFFFF) == np.bitwise_xor.reduce(key)
+    assert abs(sum_t.item() - r.distance[hit].sum()) <= 1e-9 * r.distance[hit].sum()
+    acc.close()
+
+
+@pytest.mark.gpu
+def test_mesh_frame_gpu_matches_host_build(make_backend):
+    """Cornell box holding a 20k-triangle mesh, rendered by the wavefront kernels (two-level traversal loop with pooled
+    triangle tests in k_wf_trace) against the host build of the same source running the sequential traversal."""
+    import hostsim_api
+    import scenes
+    import source_b200 as api
+    verts, tris, normals = scenes.icosphere(5, radius=0.45, bumps=0.1)
+
+    def extra(a, w):
+        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+               material=a.Lambert(a.ConstantSF(0.7)))
+    world = scenes.cornell_box(api, glass=True, extra=extra)
+    kw = dict(pixels=(40, 36), samples=6, bins=16)
+    _, f_gpu = parity.observe(make_backend, world, 31, **kw)
+    _, f_cpu = parity.observe(hostsim_api.HostScene, world, 31, **kw)
+    g = dict(mean=f_cpu.mean, variance=f_cpu.variance, samples=f_cpu.samples)
+    fr = parity.compare_frame(f_gpu, g, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+    print("mesh frame: divergent pixel fraction vs host build:", fr)
