@@ -23,6 +23,9 @@ namespace rsb {
 #ifndef RSB_SHADE_MIN_BLOCKS
 #define RSB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef RSB_MESH_MIN_BLOCKS
+#define RSB_MESH_MIN_BLOCKS 4       // traversal kernels of scenes with meshes: resident CTAs per SM the registers must allow
+#endif
 #define RSB_RENDER_THREADS 128
 #ifndef RSB_REFILL_LANES
 #define RSB_REFILL_LANES 8          // persistent-lane kernels: idle lanes that trigger a refill
@@ -251,7 +254,7 @@ __device__ __forceinline__ bool mesh_leaf_coop(const Scene& sc, const CoopSmem& 
 
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? 4 : 5))
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? RSB_MESH_MIN_BLOCKS : 5))
 k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origins,
             const double* __restrict__ directions, const double* __restrict__ max_distance,
             int32_t* __restrict__ out_prim, double* __restrict__ out_t, int32_t* __restrict__ out_sub,
@@ -303,7 +306,7 @@ k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origi
 
 // rays from `origin` toward target + (jx, jy, 0)*half_window, (jx, jy) uniform in [-1, 1) from Philox(seed, index)
 template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? 4 : 5))
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? RSB_MESH_MIN_BLOCKS : 5))
 k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned long long seed,
             double ox, double oy, double oz, double tx, double ty, double tz, double half_window,
             unsigned long long* out_hits, double* out_sum_t, unsigned long long* out_xor_prim, DevCounters* counters) {
@@ -714,7 +717,7 @@ __device__ __forceinline__ void wf_append_lists(const WfArgs& a, int list, int s
 // k_wf_shade / k_wf_regen another 15-30 %.  A Cornell ray is ~3 traversal units long: too short to amortise the
 // flush + refill.  See profiles/README.md.)
 template <int RNGMODE, bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLOCKS : ((FEAT & RSB_FEAT_MESH) ? 4 : 5)) k_wf_trace(const __grid_constant__ WfArgs a) {
+__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLOCKS : ((FEAT & RSB_FEAT_MESH) ? RSB_MESH_MIN_BLOCKS : 5)) k_wf_trace(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scene sc = a.sc;
     double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, a.n_items);

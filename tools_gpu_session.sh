@@ -42,6 +42,11 @@ ncu:*)
   K=${S#ncu:}
   RSB_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none -k regex:$K -s 200 -c 1 -f -o $O/${TAG}_full_$K \
     python bench.py --pixels 1024 --spp 64 --steps 1 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_ncu_$K.log 2>&1 ;;
+rendermesh|rendermesh:*)
+  L=${S#rendermesh:}; [ "$L" = "rendermesh" ] && L=""
+  if [ -n "$L" ]; then export RSB_LIBRARY=$PWD/build/$L.so; fi
+  timeout 900 python tools_render_mesh.py --pixels 1024 --spp 16 > $O/${TAG}_rendermesh_$L.json 2> $O/${TAG}_rendermesh_$L.err; echo "rendermesh $L"; cut -c1-400 $O/${TAG}_rendermesh_$L.json; tail -n 2 $O/${TAG}_rendermesh_$L.err
+  unset RSB_LIBRARY ;;
 sweeplib:*)
   L=${S#sweeplib:}
   RSB_LIBRARY=$PWD/build/$L.so timeout 900 python tools_sweep.py --n 1e7 --mesh-subdiv 8 > $O/${TAG}_sweep_$L.jsonl 2> $O/${TAG}_sweep_$L.err
