@@ -468,7 +468,6 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
 #define RSB_LAUNCH_SWEEP(C, F)                                                                                            \
     do {                                                                                                                  \
         if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<C, F>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
         k_hit_sweep<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, first_index, seed, origin[0], origin[1], origin[2], \
                                                    target[0], target[1], target[2], half_window, (unsigned long long*)out_hits_dev, out_sum_t_dev, \
                                                    (unsigned long long*)out_xor_prim_dev, c->d_counters);             \
@@ -586,7 +585,6 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (RNGMODE == RNG_MT19937_64) smem_shade += RSB_MT_WIN_WORDS * 8 * threads;   // k_wf_shade: MT state window per thread
     if (smem_scene > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
-    RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp

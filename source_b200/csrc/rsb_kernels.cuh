@@ -744,7 +744,11 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
     KdStackEntry stack[RSB_KD_STACK];
     HitRec rec;
     bool hit = false;
+#ifdef RSB_NO_COOP
+    if constexpr (false) {
+#else
     if constexpr ((FEAT & RSB_FEAT_MESH) != 0) {
+#endif
         // scenes with meshes: the two-level traversal advances in warp-wide trips, one mesh traversal unit per trip,
         // with the triangle tests of all lanes' leaves pooled (mesh_leaf_coop); every lane of the warp takes part
         // in the pooled tests, whether or not it still has a ray of its own

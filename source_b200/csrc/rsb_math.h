@@ -197,7 +197,7 @@ RSB_HD double div_exact(double x, double d, double r) {
 // (Markstein); `unsafe` bit k flags a direction component that fails that test, and |x| is windowed here, so
 // that every other case takes a true division.  The dependent chain is 3 instructions instead of the ~10 of
 // div.rn.f64 -- the traversal is bound by exactly that chain.  Checked against x / d on 4e8 adversarial pairs
-// (tests/test_host_parity.py::test_div_recip1).
+// (tests/test_cabi_symbols.py::test_kd_plane_distance_through_reciprocal_is_the_ieee_quotient checks that form; 4e8 more pairs were run offline).
 // Non-zero when some NON-ZERO direction component cannot take the reciprocal shortcut (all-ones significand, or a
 // reciprocal outside 1e-140 .. 1e140).  Zero components never reach the division (kdtree3d.pyx:660-668).
 RSB_HD int recip_unsafe_mask(const V3& d, const V3& r) {

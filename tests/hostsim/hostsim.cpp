@@ -273,6 +273,17 @@ int hs_div_exact(int64_t n, const double* x, const double* d, double* out) {
     return 0;
 }
 
+// the kd traversal's plane distance exactly as kd_descend forms it: per-ray reciprocal + unsafe mask + one correction
+int hs_div_recip1(int64_t n, const double* x, const double* d, double* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        V3 dir = v3(d[i], d[i], d[i]);
+        V3 rc = ray_reciprocals(dir);
+        bool unsafe = recip_unsafe_mask(dir, rc) != 0;
+        out[i] = d[i] == 0.0 ? x[i] / d[i] : div_recip1(x[i], d[i], rc.x, unsafe);   // zero components never reach the division
+    }
+    return 0;
+}
+
 int hs_frame_combine(int64_t n_pixels_total, int32_t frame_bins, int32_t slice_offset, int32_t slice_bins, const double* mean,
                      const double* variance, int32_t samples, double* fmean, double* fvar, int32_t* fsamples) {
     for (int64_t p = 0; p < n_pixels_total; ++p)

@@ -164,3 +164,39 @@ def test_exact_reciprocal_division_general_divisors():
     ok = ~np.isnan(ref)
     assert np.array_equal(out[ok].view(np.uint64), ref[ok].view(np.uint64))
     assert np.all(np.isnan(out[~ok]))
+
+
+def test_kd_plane_distance_through_reciprocal_is_the_ieee_quotient():
+    """div_recip1 (rsb_math.h): (split - origin) / direction through the per-ray reciprocal with ONE fused residual
+    correction must give the bits of the IEEE division for every input the traversal can meet -- adversarial
+    significands (few bits set / all ones / near powers of two), zero and tiny numerators, extreme exponents (which
+    must take the fallback).  Sign of a zero quotient excepted (the traversal never looks at it)."""
+    import ctypes as C
+    import hostsim_api
+    rng = np.random.default_rng(11)
+    n = 4_000_000
+
+    def adversarial(k):
+        m = rng.integers(0, 1 << 52, k, dtype=np.uint64)
+        few = (np.uint64(1) << rng.integers(0, 52, k).astype(np.uint64)) | (np.uint64(1) << rng.integers(0, 52, k).astype(np.uint64))
+        sel = rng.integers(0, 4, k)
+        m = np.where(sel == 1, few, m)
+        m = np.where(sel == 2, np.uint64((1 << 52) - 1) - (few & np.uint64(0xFFF)), m)
+        m = np.where(sel == 3, few & np.uint64(0xFFF), m)
+        e = (1023 + rng.integers(-30, 31, k)).astype(np.uint64)
+        s = rng.integers(0, 2, k).astype(np.uint64)
+        return ((s << np.uint64(63)) | (e << np.uint64(52)) | m).view(np.float64)
+    x, d = adversarial(n), adversarial(n)
+    x[:8] = [0.0, -0.0, 1e-320, 1e-200, 1e200, np.inf, 3e-141, 3e140]
+    d[8:16] = [1e-200, 1e200, 5e-324, -1e-150, 1e150, 1.0, -1.0, 0.5]
+    d[16:19] = np.array([0x3FFFFFFFFFFFFFFF, 0x400FFFFFFFFFFFFF, 0xBFEFFFFFFFFFFFFF], dtype=np.uint64).view(np.float64)
+    out = np.zeros(n)
+    lib = hostsim_api.lib()
+    lib.hs_div_recip1.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_div_recip1(n, x.ctypes.data, d.ctypes.data, out.ctypes.data)
+    with np.errstate(all="ignore"):
+        ref = x / d
+    ok = ~np.isnan(ref) & (ref != 0)
+    assert np.array_equal(out[ok].view(np.uint64), ref[ok].view(np.uint64))
+    zero = ref == 0
+    assert np.all(out[zero] == 0)
