@@ -34,6 +34,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 WORKLOAD = dict(name="cornell_box 1024x1024 x 256 spp x 64 bins (BASELINE configs[1])", pixels=1024, spp=256, bins=64)
 CPU_SAMPLE = dict(pixels=192, spp=8, bins=64)
+DEFAULT_PASSES = 4   # 256 spp = 4 accumulated observe() passes of 64 spp (the reference's progressive-render loop)
 RAY_CFG = dict(extinction_prob=0.01, extinction_min_depth=3, max_depth=500, importance_sampling=True,
                important_path_weight=0.25)   # demos/cornell_box.py:147-156
 MIN_WL, MAX_WL = 375.0, 740.0               # observer defaults, observer.pyx:116-117
@@ -70,6 +71,9 @@ def run_reference(args):
     cam.render_engine = Counting(processes=cores)
     world.build_accelerator()
     times, rays = [], []
+    # The reference renders its sample in ONE observe() call whatever --passes says: that is its faster mode
+    # (MulticoreEngine forks its workers on every observe(); measured here, 4 passes of the bounded sample run at
+    # half the rays/s of one pass), and the frame is statistically the same.
     for i in range(args.warmup + args.steps):
         Counting.rays = 0
         pipe.accumulate = False
@@ -81,7 +85,8 @@ def run_reference(args):
             rays.append(Counting.rays)
     total_t, total_r = sum(times), sum(rays)
     value = total_r / total_t / 1e6
-    sample = "cornell_box %dx%d x %d spp x %d bins, MulticoreEngine(%d)" % (s["pixels"], s["pixels"], s["spp"], s["bins"], cores)
+    sample = "cornell_box %dx%d x %d spp (one observe() pass) x %d bins, MulticoreEngine(%d)" % (
+        s["pixels"], s["pixels"], s["spp"], s["bins"], cores)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": 0, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, len(times)), "higher_is_better": True,
@@ -183,7 +188,9 @@ def run_ours(args):
     pipe.accumulate = False
     world._device = device
     accel = world.build_accelerator()
-    renderer = FrameRenderer(cam, accel, rank, world_size, tile=16)
+    if w["spp"] % args.passes:
+        raise SystemExit("bench.py: --passes must divide the samples per pixel")
+    renderer = FrameRenderer(cam, accel, rank, world_size, tile=16, passes=args.passes)
 
     def barrier():
         if world_size > 1:
@@ -278,7 +285,10 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"] if not (args.pixels or args.spp) else "cornell_box %dx%d x %d spp x %d bins" % (w["pixels"], w["pixels"], w["spp"], w["bins"]),
-                       "rng": "mt19937_64 per pixel" if args.rng == "mt" else "philox4x32-10 per (pixel, sample)",
+                       "passes": "%d spp accumulated as %d observe() passes of %d spp (streams keyed on (pass, pixel)), merged with "
+                                 "StatsArray3D.combine_samples" % (w["spp"], args.passes, w["spp"] // args.passes)
+                                 if args.passes > 1 else "one observe() pass of %d spp" % w["spp"],
+                       "rng": "mt19937_64 per (pass, pixel)" if args.rng == "mt" else "philox4x32-10 per (pass, pixel, sample)",
                        "partition": "16x16 px tiles interleaved over ranks, one NCCL reduce(sum) of the frame" if world_size > 1 else "single GPU",
                        "l2": "frame buffers 1.07 GB per step exceed the 126 MB L2; scene (4.5 KB) is shared-memory resident by design"},
             "frames_per_s": 1e3 * args.steps / total_ms, "rays_per_step": total_rays / args.steps,
@@ -311,6 +321,8 @@ def main():
     ap.add_argument("--rng", default="mt", choices=["mt", "philox"])
     ap.add_argument("--pixels", type=int, default=0, help="override frame size (development only)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only)")
+    ap.add_argument("--passes", type=int, default=DEFAULT_PASSES,
+                    help="render the frame's samples as this many accumulated observe() passes, concurrently")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

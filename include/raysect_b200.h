@@ -235,6 +235,25 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
                    uint64_t* ray_count_dev, int32_t count);
 
 /*
+ * n_passes accumulated observe() calls of the same camera rendered CONCURRENTLY (the reference's usage pattern
+ * for progressive renders, demos/cornell_box.py:166-174: observe() in a loop with pipeline.accumulate = True):
+ * pass p renders camera->pixel_samples samples per listed pixel from the streams seeded
+ * rng->seed + p*seed_stride + y*nx + x, and the passes are merged in order p = 0, 1, ... with
+ * SpectralPowerPipeline2D.update -> StatsArray3D.combine_samples (power.pyx:424-437, statsarray.pyx:612-670,
+ * 780-857), starting from an EMPTY frame.  mean/variance of the listed pixels come back holding
+ * n_passes*pixel_samples samples.  A pixel's samples within one pass are sequential (they share a stream);
+ * passes are independent streams, so they multiply the number of pixel streams in flight by n_passes.
+ * n_passes = 1, seed_stride = 0 is rsb_render / rsb_render_dev (no merge step: the frame is the pass).
+ */
+int rsb_render_passes(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+                      const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride,
+                      int64_t n_pixels, const int32_t* pixels, double* mean, double* variance, uint64_t* ray_count);
+int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera,
+                          const RsbRayConfig* config, const RsbSpectral* spectral, const RsbRngDesc* rng,
+                          int32_t n_passes, uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels_dev,
+                          double* mean_dev, double* variance_dev, uint64_t* ray_count_dev, int32_t count);
+
+/*
  * SpectralPowerPipeline2D.update -> StatsArray3D.combine_samples (power.pyx:424-437, statsarray.pyx:780-857):
  * merges a freshly rendered slice (mean, variance, samples_per_pixel; [n_pixels_total][slice_bins]) into an
  * accumulating frame (frame_* [n_pixels_total][frame_bins]) at bin offset slice_offset, for the listed pixels.

@@ -67,10 +67,29 @@ class OracleScene:
         lib().ro_contains(C.byref(self.flat.desc), C.c_int64(n), _p(p), C.c_int32(cap), _p(count), _p(prims))
         return count, prims
 
-    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
+    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None, passes=1,
+               seed_stride=0):
         if rng_mode != 0:
             raise NotImplementedError("the C oracle implements the reference generator (MT19937-64) only")
         nx, ny, bins = camera.nx, camera.ny, config.bins
+        if passes > 1:
+            # `passes` observe() calls into an accumulating pipeline, starting from an empty frame
+            fm, fv = np.zeros((nx, ny, bins)), np.zeros((nx, ny, bins))
+            fs = np.zeros((nx, ny, bins), dtype=np.int32)
+            total = 0
+            for p in range(passes):
+                m, v, r = self.render(camera, config, spectral, rng_mode, seed + p * seed_stride, pixels)
+                total += r
+                lib().ro_combine(C.c_int64(fm.size), _p(m), _p(v), C.c_int32(camera.pixel_samples), _p(fm), _p(fv), _p(fs))
+            mean = np.zeros((nx, ny, bins)) if mean is None else mean
+            variance = np.zeros((nx, ny, bins)) if variance is None else variance
+            listed = np.ones((nx, ny), dtype=bool)
+            if pixels is not None:
+                pix = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1, 2)
+                listed[:] = False
+                listed[pix[:, 0], pix[:, 1]] = True
+            mean[listed], variance[listed] = fm[listed], fv[listed]
+            return mean, variance, total
         if mean is None:
             mean = np.zeros((nx, ny, bins))
         if variance is None:

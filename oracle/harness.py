@@ -127,12 +127,15 @@ def make_reseeding_engine(seed_base, nx):
     return ReseedingEngine()
 
 
-def oracle_render(camera, pipeline, seed_base):
+def oracle_render(camera, pipeline, seed_base, passes=1):
     """camera.observe() with per-pixel re-seeding.  One pass per spectral slice; slice k uses
-    seed_base + k*nx*ny, matching source_b200.observer.PinholeCamera.observe."""
+    seed_base + k*nx*ny, matching source_b200.observer.PinholeCamera.observe.  ``passes`` > 1 calls observe()
+    that many times into the accumulating pipeline (the reference's progressive-render loop,
+    demos/cornell_box.py:160-174); call p offsets the seed by p*n_slices*nx*ny."""
     _activate()
     nx, ny = camera.pixels
     slices = camera.spectral_rays
+    state = {"pass": 0}
 
     class SliceAwareEngine(type(make_reseeding_engine(seed_base, nx))):
         def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
@@ -140,10 +143,14 @@ def oracle_render(camera, pipeline, seed_base):
             slice_id = render_args[0] if render_args else 0
             for task in tasks:
                 x, y = task
-                seed(seed_base + slice_id * nx * ny + y * nx + x)
+                seed(seed_base + (state["pass"] * slices + slice_id) * nx * ny + y * nx + x)
                 update(render(task, *render_args, **render_kwargs), *update_args, **update_kwargs)
 
     camera.render_engine = SliceAwareEngine()
-    camera.observe()
+    if passes > 1:
+        pipeline.accumulate = True
+    for p in range(passes):
+        state["pass"] = p
+        camera.observe()
     f = pipeline.frame
     return np.array(f.mean), np.array(f.variance), np.array(f.samples)

@@ -921,6 +921,57 @@ int ro_contains(const RsbSceneDesc* d, int64_t n, const double* p, int32_t cap, 
 
 /* Observer._render_pixel (observer.pyx:363-419) for the listed pixels (NULL = all), MT19937-64 streams seeded
  * per pixel with seed + y*nx + x; PinholeCamera._generate_rays (pinhole.pyx:169-204); Welford (statsarray.pyx:743-777) */
+/* StatsArray3D.combine_samples (raysect/core/math/statsarray.pyx:612-670) over a whole frame: merges n_new samples
+ * with statistics (mean, variance) into the stored (fmean, fvar, fsamples), element by element, through
+ * _combine_samples (:780-857): larger set first, Chan's pooled formula when both sets hold more than one sample,
+ * else the special cases; a single new sample goes through _add_sample (:743-777).  This is what
+ * SpectralPowerPipeline2D.update does with every pixel of an observe() pass (power.pyx:424-437). */
+static void add_one(double sample, double* m, double* v, int* n) {
+    if (*n == 0) { *n = 1; *m = sample; *v = 0; return; }
+    double pm = *m, pv = *v;
+    int pn = *n > 1 ? *n : 2;
+    *n += 1;
+    *m = pm + (sample - pm) / *n;
+    *v = (pv * (pn - 1) + (sample - pm) * (sample - *m)) / (*n - 1);
+}
+
+int ro_combine(int64_t n, const double* mean, const double* variance, int32_t n_new, double* fmean, double* fvar, int32_t* fsamples) {
+    if (n_new < 1) return 1;
+    for (int64_t i = 0; i < n; ++i) {
+        double mb = mean[i], vb = variance[i] < 0 ? 0 : variance[i];
+        double mx = fmean[i], vx = fvar[i], my = mb, vy = vb, mt = 0, vt = 0;
+        int nx = fsamples[i], ny = n_new, nt = 0;
+        if (nx < ny) {
+            int ti = nx; nx = ny; ny = ti;
+            double td = mx; mx = my; my = td;
+            td = vx; vx = vy; vy = td;
+        }
+        if (nx > 1 && ny > 1) {
+            nt = nx + ny;
+            mt = (nx * mx + ny * my) / (double)nt;
+            vx = (nx - 1) * vx / (double)nx;
+            vy = (ny - 1) * vy / (double)ny;
+            vt = (nx * (mx * mx + vx) + ny * (my * my + vy)) / (double)nt - mt * mt;
+            vt = nt * vt / (double)(nt - 1);
+        } else if (nx == 0 && ny == 0) {
+            nt = 0; mt = 0; vt = 0;
+        } else if (nx == 1) {
+            if (ny == 0) { nt = 1; mt = mx; vt = 0; }
+            else {
+                nt = 2;
+                mt = 0.5 * (mx + my);
+                double temp = mx - mt;
+                vt = 2 * temp * temp;
+            }
+        } else if (nx > 1) {
+            nt = nx; mt = mx; vt = vx;
+            if (ny == 1) add_one(my, &mt, &vt, &nt);
+        }
+        fmean[i] = mt; fvar[i] = vt; fsamples[i] = nt;
+    }
+    return 0;
+}
+
 int ro_render(const RsbSceneDesc* d, const RsbCamera* cam, const RsbRayConfig* cfg, const RsbSpectral* sp, uint64_t seed,
               int64_t n_pixels, const int32_t* pixels, double* mean, double* variance, uint64_t* ray_count) {
     scene_t* s = scene_new(d);

@@ -171,6 +171,12 @@ SIGNATURES = {
     "rsb_render_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),
                                  C.POINTER(RsbSpectral), C.POINTER(RsbRngDesc), C.c_int64, _VP, _VP, _VP, _VP,
                                  C.c_int32]),
+    "rsb_render_passes": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
+                                    C.POINTER(RsbRngDesc), C.c_int32, C.c_uint64, C.c_int64, c_int32_p, c_double_p,
+                                    c_double_p, c_uint64_p]),
+    "rsb_render_passes_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),
+                                        C.POINTER(RsbSpectral), C.POINTER(RsbRngDesc), C.c_int32, C.c_uint64, C.c_int64,
+                                        _VP, _VP, _VP, _VP, C.c_int32]),
     "rsb_frame_combine_dev": (C.c_int, [_U64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _VP,
                                         C.c_int32, _VP, _VP, C.c_int32, _VP, _VP, _VP]),
     "rsb_render_stats": (C.c_int, [_U64, C.POINTER(RsbRenderStats)]),

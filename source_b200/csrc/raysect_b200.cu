@@ -52,6 +52,9 @@ struct Context {
     unsigned long long* d_scalars = nullptr;   // [0] work counter, [1] ray count, [2] overflow flag (as int)
     unsigned char* d_slots = nullptr;   // wavefront slot state (rsb_kernels.cuh: WfSlots)
     size_t slot_bytes = 0;
+    double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
+    size_t pass_bytes = 0;
+    long long chunk_items = 4LL << 20;  // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (5 KB each)
     unsigned int* h_idle = nullptr;     // pinned
     RsbRenderStats render_stats{};
     int slots_per_sm = 8192;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)
@@ -248,6 +251,7 @@ int rsb_context_create(int device, uint64_t* ctx) {
     RSB_CUDA(cudaMemset(c->d_scalars, 0, 8 * sizeof(unsigned long long)));
     RSB_CUDA(cudaMallocHost(&c->h_idle, sizeof(unsigned int)));
     if (const char* ng = getenv("RSB_NO_GRAPH")) c->use_graphs = !(ng[0] == '1');
+    if (const char* sp = getenv("RSB_CHUNK_ITEMS")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->chunk_items = v; }
     if (const char* sp = getenv("RSB_SLOTS_PER_SM")) { int v = atoi(sp); if (v >= 32 && v <= 65536) c->slots_per_sm = v; }
     *ctx = reinterpret_cast<uint64_t>(c);
     return RSB_OK;
@@ -261,6 +265,7 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_counters);
     cudaFree(c->d_scalars);
     cudaFree(c->d_slots);
+    cudaFree(c->d_pass);
     cudaFreeHost(c->h_idle);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_mats);
@@ -681,6 +686,14 @@ extern "C" {
 int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
                    const RsbSpectral* spectral, const RsbRngDesc* rng, int64_t n_pixels, const int32_t* pixels_dev,
                    double* mean_dev, double* variance_dev, uint64_t* ray_count_dev, int32_t count) {
+    return rsb_render_passes_dev(ctx, scene, cuda_stream, camera, config, spectral, rng, 1, 0, n_pixels, pixels_dev, mean_dev,
+                                 variance_dev, ray_count_dev, count);
+}
+
+int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
+                          const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride,
+                          int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
+                          uint64_t* ray_count_dev, int32_t count) {
     Context* c = as_ctx(ctx);
     DeviceScene* ds = as_scene(scene);
     if (!c || !ds || !camera || !config || !spectral || !rng || !mean_dev || !variance_dev || !ray_count_dev)
@@ -693,6 +706,8 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
         return fail(RSB_ERR_ARG, "Important path weight must be in the range [0, 1].");
     if (rng->seed == 0) return fail(RSB_ERR_ARG, "rng seed must be >= 1");
     if (rng->mode != RSB_RNG_MT19937_64 && rng->mode != RSB_RNG_PHILOX) return fail(RSB_ERR_ARG, "unknown rng mode");
+    if (n_passes < 1 || n_passes > 1024) return fail(RSB_ERR_ARG, "rsb_render_passes: the number of passes must be in [1, 1024]");
+    if (!pixels_dev) n_pixels = (int64_t)camera->nx * camera->ny;
     if (n_pixels <= 0) return RSB_OK;
     cudaStream_t caller = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
@@ -777,6 +792,22 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     RSB_CUDA(cudaMemsetAsync(c->d_scalars + 2, 0, sizeof(unsigned long long), st));
     a.counters = c->d_counters;
     a.seed = rng->seed;
+    a.seed_stride = seed_stride;
+    a.n_passes = n_passes;
+    a.n_pix_pass = n_pixels;
+    a.pixels = pixels_dev;
+    a.frame_elems = (long long)camera->nx * camera->ny * config->bins;
+    if (n_passes > 1) {
+        size_t need_pass = (size_t)2 * (size_t)(n_passes - 1) * (size_t)a.frame_elems * sizeof(double);
+        if (c->pass_bytes < need_pass) {
+            cudaFree(c->d_pass);
+            c->d_pass = nullptr; c->pass_bytes = 0;
+            RSB_CUDA(cudaMalloc(&c->d_pass, need_pass));
+            c->pass_bytes = need_pass;
+        }
+        a.pass_mean = c->d_pass;
+        a.pass_variance = c->d_pass + (size_t)(n_passes - 1) * (size_t)a.frame_elems;
+    }
     a.n_items = ds->n_world_items;
     a.staged = ds->stage_bytes ? 1 : 0;
     size_t smem_scene = ds->stage_bytes, smem_shade = ds->stage_bytes, smem_tables = 0;
@@ -794,8 +825,8 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     // Pixels are processed in chunks so that the up-front MT19937-64 state of a chunk (5 KB per pixel) stays
     // within a fixed HBM budget; a 1024 x 1024 frame is one chunk (5.2 GB).
     bool mt = rng->mode == RSB_RNG_MT19937_64;
-    const long long kChunkPixels = 2LL << 20;
-    long long chunk_cap = std::min<long long>(n_pixels, kChunkPixels);
+    const long long n_work = (long long)n_pixels * n_passes;   // work items: (pass, pixel task)
+    long long chunk_cap = std::min<long long>(n_work, c->chunk_items);
     long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * c->slots_per_sm);
     P = std::max<long long>(P, 1);
     WfSlots probe;
@@ -812,10 +843,9 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
     count &= RSB_RENDER_COUNT;
     c->render_stats = RsbRenderStats{};
     int rc = RSB_OK;
-    for (long long base = 0; base < n_pixels && rc == RSB_OK; base += chunk_cap) {
-        a.n_pixels = std::min<long long>(chunk_cap, n_pixels - base);
-        a.pixel_base = base;
-        a.pixels = pixels_dev ? pixels_dev + 2 * base : nullptr;
+    for (long long base = 0; base < n_work && rc == RSB_OK; base += chunk_cap) {
+        a.n_pixels = std::min<long long>(chunk_cap, n_work - base);
+        a.item_base = base;
         a.n_slots = (int32_t)std::min<long long>(P, a.n_pixels);
         // scalars: [0] work counter, [1] idle slots, [2] overflow flag (sticky across chunks)
         RSB_CUDA(cudaMemsetAsync(c->d_scalars, 0, 2 * sizeof(unsigned long long), st));
@@ -831,6 +861,14 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
 #undef RSB_RUN_PX
     }
     if (rc) return rc;
+    if (n_passes > 1) {
+        long long total = (long long)n_pixels * config->bins;
+        k_pass_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, camera->ny, config->bins, n_passes,
+                                                                    camera->pixel_samples, a.frame_elems, a.pass_mean, a.pass_variance,
+                                                                    mean_dev, variance_dev);
+        RSB_CUDA(cudaGetLastError());
+        c->render_stats.launches += 1;
+    }
     {
         int32_t overflow = 0;
         RSB_CUDA(cudaMemcpyAsync(&overflow, a.overflow_flag, 4, cudaMemcpyDeviceToHost, st));
@@ -850,6 +888,12 @@ int rsb_render_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCam
 
 int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                const RsbRngDesc* rng, int64_t n_pixels, const int32_t* pixels, double* mean, double* variance, uint64_t* ray_count) {
+    return rsb_render_passes(ctx, scene, camera, config, spectral, rng, 1, 0, n_pixels, pixels, mean, variance, ray_count);
+}
+
+int rsb_render_passes(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                      const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels,
+                      double* mean, double* variance, uint64_t* ray_count) {
     Context* c = as_ctx(ctx);
     if (!c || !as_scene(scene) || !camera || !config || !mean || !variance || !ray_count) return fail(RSB_ERR_ARG, "rsb_render: null argument");
     RSB_CUDA(cudaSetDevice(c->device));
@@ -873,7 +917,8 @@ int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbR
         RSB_TRY(cudaMemcpyAsync(d_pix, pixels, n_pixels * 8, cudaMemcpyHostToDevice, st));
     }
     RSB_TRY(cudaEventRecord(c->ev0, st));
-    int rc = rsb_render_dev(ctx, scene, st, camera, config, spectral, rng, n_pixels, d_pix, d_mean, d_var, (uint64_t*)d_rc, 1);
+    int rc = rsb_render_passes_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, seed_stride, n_pixels, d_pix, d_mean,
+                                   d_var, (uint64_t*)d_rc, 1);
     if (rc) { cleanup(); return rc; }
     RSB_TRY(cudaEventRecord(c->ev1, st));
     unsigned long long rays = 0;

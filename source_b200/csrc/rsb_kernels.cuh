@@ -507,11 +507,17 @@ struct WfArgs {
     RayConfig cfg;
     Camera cam;
     WfSlots st;
-    long long n_pixels;         // pixels of the current chunk
-    long long pixel_base;       // first frame pixel of the chunk when `pixels` is null
-    const int32_t* pixels;      // chunk's slice of the task list, or null
-    double* mean;
+    long long n_pixels;         // work items (pass, pixel) of the current chunk
+    long long item_base;        // global index of the chunk's first work item; item g = pass * n_pix_pass + task
+    long long n_pix_pass;       // pixel tasks per pass (length of `pixels`, or nx * ny)
+    const int32_t* pixels;      // the task list [n_pix_pass][2], or null = the whole frame
+    double* mean;               // pass 0 accumulates straight into the caller's frame
     double* variance;
+    double* pass_mean;          // [n_passes - 1][frame_elems] frames of passes 1.., merged by k_pass_combine
+    double* pass_variance;
+    long long frame_elems;      // nx * ny * bins
+    unsigned long long seed_stride;   // pass p draws from streams seeded seed + p * seed_stride + y * nx + x
+    int32_t n_passes;
     unsigned long long* ray_count;
     unsigned long long* work_counter;
     unsigned int* n_idle;
@@ -526,6 +532,12 @@ struct WfArgs {
     int32_t wave;
 };
 
+// Pass (accumulated observe() call) of the work item a slot is rendering
+__device__ __forceinline__ int wf_pass_of(const WfArgs& a, int slot) {
+    if (a.n_passes <= 1) return 0;
+    return (int)((unsigned long long)(a.item_base + a.st.work[slot]) / (unsigned long long)a.n_pix_pass);
+}
+
 // The cursors of the pixel stream a slot is rendering are kept per SLOT (copied from the pixel's seeded cursors
 // when the slot picks the pixel up), so that they arrive with the rest of the slot state instead of behind a
 // second dependent load through the pixel index.
@@ -539,7 +551,8 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
         rng.mt.mti = (int)a.st.philox_idx[slot];
     } else {
         long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
-        rng.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)a.st.sample[slot]);
+        rng.px.init(a.seed + (unsigned long long)wf_pass_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id,
+                    (uint32_t)a.st.sample[slot]);
         rng.px.idx = a.st.philox_idx[slot];
     }
 }
@@ -580,14 +593,21 @@ __device__ __forceinline__ void wf_push_ended(const WfArgs& a, int slot) {
     a.st.ended[(size_t)par * a.n_slots + k] = slot;
 }
 
-// Pixel (x, y) of work item w of the current chunk (FullFrameSampler2D task list, or the whole frame)
-__device__ __forceinline__ void wf_pixel_of(const WfArgs& a, unsigned long long w, int* px, int* py) {
-    if (a.pixels) { *px = a.pixels[2 * w]; *py = a.pixels[2 * w + 1]; }
+// Pixel (x, y) of work item w of the current chunk (FullFrameSampler2D task list, or the whole frame); returns
+// the pass the item belongs to
+__device__ __forceinline__ int wf_pixel_of(const WfArgs& a, unsigned long long w, int* px, int* py) {
+    unsigned long long g = w + (unsigned long long)a.item_base;
+    int pass = 0;
+    if (a.n_passes > 1) {
+        pass = (int)(g / (unsigned long long)a.n_pix_pass);
+        g -= (unsigned long long)pass * (unsigned long long)a.n_pix_pass;
+    }
+    if (a.pixels) { *px = a.pixels[2 * g]; *py = a.pixels[2 * g + 1]; }
     else {
-        unsigned long long g = w + (unsigned long long)a.pixel_base;
         *px = (int)(g / (unsigned long long)a.cam.ny);
         *py = (int)(g % (unsigned long long)a.cam.ny);
     }
+    return pass;
 }
 
 // 1 thread = 1 pixel of the chunk: seed(seed + y*nx + x) for both cursors of the pixel's stream, all pixels in
@@ -597,13 +617,13 @@ __global__ void __launch_bounds__(128) k_wf_seed(const __grid_constant__ WfArgs 
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.n_pixels) return;
     int px, py;
-    wf_pixel_of(a, (unsigned long long)w, &px, &py);
+    const int pass = wf_pixel_of(a, (unsigned long long)w, &px, &py);
     long long pixel_id = (long long)py * a.cam.nx + px;
     uint64_t* base = reinterpret_cast<uint64_t*>(a.st.pix_mt) + (size_t)w * (2 * RSB_MT_NN);
     int jm, pm;
     // the jitter cursor starts at draw 0, the path cursor after the 2*spp draws that
     // RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
-    mt_seed_pair(a.seed + (unsigned long long)pixel_id, 2 * a.cam.pixel_samples, base + RSB_MT_NN, &jm, base, &pm);
+    mt_seed_pair(a.seed + (unsigned long long)pass * a.seed_stride + (unsigned long long)pixel_id, 2 * a.cam.pixel_samples, base + RSB_MT_NN, &jm, base, &pm);
     a.st.pix_mti[2 * w] = pm;
     a.st.pix_mti[2 * w + 1] = jm;
 }
@@ -646,7 +666,7 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
         a.st.jit_mti[slot] = jit.mt.mti;
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
-        jit.px.init(a.seed, (unsigned long long)pixel_id, (uint32_t)s);
+        jit.px.init(a.seed + (unsigned long long)wf_pass_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);
         u1 = jit.uniform();
         u2 = jit.uniform();
         a.st.philox_idx[slot] = jit.px.idx;
@@ -921,8 +941,9 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         log.n = a.st.log_n[slot];
         log.overflow = 0;
         size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * bins;
-        double* m = a.mean + row;
-        double* v = a.variance + row;
+        const int pass = wf_pass_of(a, slot);
+        double* m = (pass ? a.pass_mean + (size_t)(pass - 1) * a.frame_elems : a.mean) + row;
+        double* v = (pass ? a.pass_variance + (size_t)(pass - 1) * a.frame_elems : a.variance) + row;
         const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
         const bool emit = status == SLOT_ENDED_EMIT;
         for (int b0 = 0; b0 < bins; b0 += 64) {
@@ -1011,6 +1032,37 @@ __global__ void k_frame_combine(long long n_pixels, const int32_t* __restrict__ 
         fmean[dst] = mt;
         fvar[dst] = vt;
         fsamples[dst] = nt;
+    }
+}
+
+// P accumulated observe() calls rendered concurrently: pass p (p >= 1) of every listed pixel is merged into the
+// caller's frame, which holds passes 0..p-1 (n_acc samples), exactly as SpectralPowerPipeline2D.update does
+// between observe() calls (power.pyx:424-437 -> statsarray.pyx:780-857).  The passes of one pixel are merged
+// in order by the same thread.
+__global__ void k_pass_combine(long long n_pixels, const int32_t* __restrict__ pixels, int ny, int bins, int n_passes, int samples,
+                               long long frame_elems, const double* __restrict__ pass_mean, const double* __restrict__ pass_variance,
+                               double* __restrict__ fmean, double* __restrict__ fvar) {
+    long long total = n_pixels * bins;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long p = i / bins;
+        int b = (int)(i % bins);
+        long long row = pixels ? ((long long)pixels[2 * p] * ny + pixels[2 * p + 1]) : p;
+        long long e = row * bins + b;
+        // the first update merges pass 0 into the empty frame (n = 0), like every later one
+        double m = 0.0, v = 0.0;
+        int n = 0;
+        for (int q = 0; q < n_passes; ++q) {
+            double mb = q ? pass_mean[(long long)(q - 1) * frame_elems + e] : fmean[e];
+            double vb = q ? pass_variance[(long long)(q - 1) * frame_elems + e] : fvar[e];
+            if (vb < 0) vb = 0;   // statsarray.pyx:647-650
+            double mt, vt;
+            int nt;
+            stats_combine(m, v, n, mb, vb, samples, &mt, &vt, &nt);
+            m = mt; v = vt; n = nt;
+        }
+        fmean[e] = m;
+        fvar[e] = v;
     }
 }
 

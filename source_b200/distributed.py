@@ -44,7 +44,7 @@ def reduce_frame(stats, out, rank, world_size):
 class FrameRenderer:
     """Renders one spectral slice of a PinholeCamera frame on `world_size` GPUs (this process = `rank`)."""
 
-    def __init__(self, camera, accel, rank=0, world_size=1, tile=16, backend_reduce=None):
+    def __init__(self, camera, accel, rank=0, world_size=1, tile=16, backend_reduce=None, passes=1):
         import torch
         self.torch = torch
         self.camera, self.accel = camera, accel
@@ -53,8 +53,13 @@ class FrameRenderer:
         self.nx, self.ny, self.bins = nx, ny, camera.spectral_bins
         if camera.spectral_rays != 1:
             raise NotImplementedError("FrameRenderer handles one spectral slice per call")
+        # ``passes`` accumulated observe() calls of pixel_samples / passes samples each, rendered concurrently
+        # (rsb_render_passes_dev): the frame holds camera.pixel_samples samples per pixel either way
+        self.passes = int(passes)
+        if self.passes < 1 or camera.pixel_samples % self.passes:
+            raise ValueError("pixel_samples must be a multiple of the number of passes")
         self.dev = torch.device("cuda", accel.device.index)
-        self.cam = camera_desc(nx, ny, camera.pixel_samples, camera.fov, camera.sensitivity, camera.to_root())
+        self.cam = camera_desc(nx, ny, camera.pixel_samples // self.passes, camera.fov, camera.sensitivity, camera.to_root())
         self.cfg = ray_config(self.bins, camera.min_wavelength, camera.max_wavelength, camera.ray_extinction_prob,
                               camera.ray_extinction_min_depth, camera.ray_max_depth, camera.ray_importance_sampling,
                               camera.ray_important_path_weight)
@@ -75,7 +80,8 @@ class FrameRenderer:
 
     def _render(self, seed, pixels, count=False, time_trace=False):
         return self.accel.render_device(self.cam, self.cfg, self.spectral, self.camera.rng_mode, seed, pixels,
-                                        self.stats[0], self.stats[1], count=count, time_trace=time_trace)[2]
+                                        self.stats[0], self.stats[1], count=count, time_trace=time_trace,
+                                        passes=self.passes, seed_stride=self.nx * self.ny)[2]
 
     def _assemble(self):
         """single reduce(sum) of the (mean, variance) frame to rank 0"""

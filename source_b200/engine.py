@@ -148,11 +148,13 @@ class Accelerator:
 
     # ---- Observer._render_pixel over a pixel list ---------------------------------------------------------
     def render_device(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None,
-                      count=False, stream=None, time_trace=False):
+                      count=False, stream=None, time_trace=False, passes=1, seed_stride=0):
         """Device-resident form: ``mean``/``variance`` are torch CUDA float64 tensors of shape (nx, ny, bins)
         (allocated zero-filled when None), ``pixels`` an int32 CUDA tensor [n, 2] or None for the whole frame.
         Enqueues on torch's current stream and returns (mean, variance, ray_count_tensor) without synchronising
-        (unless ``count``, which reads the traversal counters back)."""
+        (unless ``count``, which reads the traversal counters back).  ``passes`` > 1 renders that many accumulated
+        observe() calls of ``camera.pixel_samples`` samples each concurrently (rsb_render_passes_dev): pass p
+        draws from the streams seeded ``seed + p*seed_stride + y*nx + x``."""
         import torch
         dev = torch.device("cuda", self.device.index)
         nx, ny, bins = camera.nx, camera.ny, config.bins
@@ -164,17 +166,18 @@ class Accelerator:
         n = nx * ny if pixels is None else int(pixels.shape[0])
         rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        cabi.check(self.lib.rsb_render_dev(
+        cabi.check(self.lib.rsb_render_passes_dev(
             self.device.ctx, self.scene, C.c_void_p(st.cuda_stream), C.byref(camera), C.byref(config), C.byref(spectral),
-            C.byref(rng), n, C.c_void_p(0 if pixels is None else pixels.data_ptr()), C.c_void_p(mean.data_ptr()),
+            C.byref(rng), int(passes), int(seed_stride), n, C.c_void_p(0 if pixels is None else pixels.data_ptr()), C.c_void_p(mean.data_ptr()),
             C.c_void_p(variance.data_ptr()), C.c_void_p(rays.data_ptr()),
             (cabi.RENDER_COUNT if count else 0) | (cabi.RENDER_TIME_TRACE if time_trace else 0)))
         return mean, variance, rays
 
-    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
+    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None, passes=1,
+               seed_stride=0):
         """Host-buffer form (the call the observer makes): camera: RsbCamera, config: RsbRayConfig, spectral:
         RsbSpectral (from FlatScene.spectral()).  Returns (mean, variance, ray_count); mean/variance are
-        (nx, ny, bins) float64 numpy arrays; only the listed pixels are written."""
+        (nx, ny, bins) float64 numpy arrays; only the listed pixels are written.  ``passes``: see render_device."""
         nx, ny, bins = camera.nx, camera.ny, config.bins
         if mean is None:
             mean = np.zeros((nx, ny, bins), dtype=np.float64)
@@ -187,9 +190,10 @@ class Accelerator:
         if pixels is not None:
             pix = cabi.as_i32(pixels).reshape(-1, 2)
             n = pix.shape[0]
-        cabi.check(self.lib.rsb_render(self.device.ctx, self.scene, C.byref(camera), C.byref(config), C.byref(spectral),
-                                       C.byref(rng), n, cabi.ptr(pix, C.c_int32), cabi.ptr(mean, C.c_double),
-                                       cabi.ptr(variance, C.c_double), C.byref(rays)))
+        cabi.check(self.lib.rsb_render_passes(self.device.ctx, self.scene, C.byref(camera), C.byref(config),
+                                              C.byref(spectral), C.byref(rng), int(passes), int(seed_stride), n,
+                                              cabi.ptr(pix, C.c_int32), cabi.ptr(mean, C.c_double),
+                                              cabi.ptr(variance, C.c_double), C.byref(rays)))
         return mean, variance, rays.value
 
 

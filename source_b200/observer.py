@@ -267,16 +267,26 @@ class PinholeCamera(Observer):
         return [SpectralSlice(self.min_wavelength, self.max_wavelength, self.spectral_bins, end - start, start)
                 for start, end in ranges]
 
-    def observe(self):
-        """observer.pyx:265-309"""
+    def observe(self, passes=1):
+        """observer.pyx:265-309.  ``passes`` > 1 is ``passes`` consecutive observe() calls into accumulating
+        pipelines (the progressive-render loop of demos/cornell_box.py) rendered CONCURRENTLY: pass p draws from
+        the pixel streams seeded ``seed + (p*n_slices + slice)*nx*ny + y*nx + x`` and the passes are merged in
+        order with StatsArray3D.combine_samples, starting from an empty frame (include/raysect_b200.h,
+        rsb_render_passes)."""
         from .scenegraph import World
+        passes = int(passes)
+        if passes < 1:
+            raise ValueError("The number of passes must be at least 1.")
         self.render_complete = False
         world = self.root
         if not isinstance(world, World):
             raise TypeError("Observer is not connected to a scene graph containing a World object.")
         slices = self._slice_spectrum()
         for p in self.pipelines:
-            p.initialise(self._pixels, self.pixel_samples, self.min_wavelength, self.max_wavelength,
+            if passes > 1 and p.accumulate and p.frame is not None and np.any(p.frame.samples):
+                raise NotImplementedError("concurrent passes merge into an empty frame: clear the pipeline's frame "
+                                          "or call observe() once per pass")
+            p.initialise(self._pixels, self.pixel_samples * passes, self.min_wavelength, self.max_wavelength,
                          self.spectral_bins, slices, self.quiet)
         tasks = self.frame_sampler.generate_tasks(self._pixels)
         if tasks is not None and len(tasks) == 0:
@@ -294,7 +304,8 @@ class PinholeCamera(Observer):
             # each slice is an independent pass with its own streams (the reference's single global stream
             # simply keeps running): offset the seed by the slice so passes are not correlated
             mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode,
-                                                self.seed + slice_id * nx * ny, tasks)
+                                                self.seed + slice_id * nx * ny, tasks, passes=passes,
+                                                seed_stride=len(slices) * nx * ny)
             self.ray_count += rays
             for p in self.pipelines:
                 p.update_slice(tasks, slice_id, mean, variance)

@@ -45,7 +45,22 @@ def render(world, camera_kwargs, seed):
     return cam, dict(mean=mean, variance=var, samples=n)
 
 
+def passes_goldens():
+    """Accumulated observe() passes (the reference's progressive-render loop, demos/cornell_box.py:160-174):
+    the reference merges each pass into the frame with StatsArray3D.combine_samples."""
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(16, 12), samples=2, bins=16, spectral_rays=4, path_weight=0.5)
+    mean, var, n = harness.oracle_render(cam, pipe, 999, passes=3)
+    save("cornell_16x12_s2_p3_b16_r4", mean=mean, variance=var, samples=n)
+    # one sample per pass walks the n in {0, 1} special cases of _combine_samples (statsarray.pyx:822-857)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(12, 12), samples=1, bins=8)
+    mean, var, n = harness.oracle_render(cam, pipe, 555, passes=4)
+    save("cornell_12x12_s1_p4_b8", mean=mean, variance=var, samples=n)
+
+
 def main():
+    if "--passes-only" in sys.argv:
+        return passes_goldens()
     # 1. RNG known answers: the reference's own test vector (raysect/core/math/tests/test_random.py:37-253)
     from raysect.core.math.tests.test_random import _random_reference
     kat = np.array(_random_reference)
@@ -97,6 +112,8 @@ def main():
     world = scenes.cornell_box(api, glass=False)
     cam, r = render(world, dict(pixels=(24, 24), samples=2, bins=8, importance=False, min_depth=2, max_depth=6, extinction=0.2), 77)
     save("cornell_noglass_noimp_24", **r)
+
+    passes_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

@@ -90,7 +90,10 @@ class HostScene:
         lib().hs_contains_batch(self.scene, n, _p(p), cap, _p(count), _p(prims))
         return count, prims
 
-    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None):
+    def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None, passes=1,
+               seed_stride=0):
+        if passes > 1:
+            return self._render_passes(camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride)
         nx, ny, bins = camera.nx, camera.ny, config.bins
         if mean is None:
             mean = np.zeros((nx, ny, bins))
@@ -110,6 +113,31 @@ class HostScene:
         self.counters = dict(zip(("branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "segments"),
                                  (int(c) for c in counters)))
         return mean, variance, rays.value
+
+
+    def _render_passes(self, camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride):
+        """rsb_render_passes restated with the sequential pieces: one render per pass, merged in pass order into an
+        empty frame with StatsArray3D.combine_samples (hs_frame_combine)."""
+        nx, ny, bins = camera.nx, camera.ny, config.bins
+        fm, fv = np.zeros((nx, ny, bins)), np.zeros((nx, ny, bins))
+        fs = np.zeros((nx, ny, bins), dtype=np.int32)
+        total = 0
+        for p in range(passes):
+            m, v, rays = self.render(camera, config, spectral, rng_mode, seed + p * seed_stride, pixels)
+            total += rays
+            lib().hs_frame_combine(nx * ny, bins, 0, bins, _p(m), _p(v), camera.pixel_samples, _p(fm), _p(fv), _p(fs))
+        if mean is None:
+            mean = np.zeros((nx, ny, bins))
+        if variance is None:
+            variance = np.zeros((nx, ny, bins))
+        listed = np.ones((nx, ny), dtype=bool)
+        if pixels is not None:
+            pix = cabi.as_i32(pixels).reshape(-1, 2)
+            listed[:] = False
+            listed[pix[:, 0], pix[:, 1]] = True
+        mean[listed] = fm[listed]
+        variance[listed] = fv[listed]
+        return mean, variance, total
 
 
 def rng_uniform(seed, n):

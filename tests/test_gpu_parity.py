@@ -44,6 +44,50 @@ def test_cornell_frames(make_backend):
     print("divergent pixel fractions:", fr)
 
 
+def test_accumulated_passes_vs_reference(make_backend):
+    """rsb_render_passes: P observe() passes rendered concurrently vs the reference calling observe() P times"""
+    fr = parity.cornell_passes(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+    print("divergent pixel fractions:", fr)
+
+
+def test_concurrent_passes_equal_sequential_passes_bit_for_bit(device, make_backend, monkeypatch):
+    """Concurrent passes (one wavefront over (pass, pixel) streams, several chunks, a masked task list) must equal
+    the same passes rendered one rsb_render call at a time and merged on the host with combine_samples -- exactly:
+    both sides run the same device code, so no libm tolerance is involved."""
+    import scenes
+    import source_b200 as api
+    from source_b200.engine import Accelerator, Device, camera_desc, ray_config
+    from source_b200.observer import StatsArray3D
+    monkeypatch.setenv("RSB_CHUNK_ITEMS", "5500")   # 5 passes x 40 x 30 pixels = 6000 work items -> 2 chunks, split inside pass 4
+    monkeypatch.setenv("RSB_SLOTS_PER_SM", "32")    # 4,736 slots < 5,500 items: slots pick up items of later passes
+    dev = Device(device.index)
+    world = scenes.cornell_box(api)
+    accel = Accelerator(dev, parity.flatten_world(world))
+    nx, ny, bins, spp, passes, seed = 40, 30, 12, 3, 5, 4321
+    cam_t = api.translate(0, 0, -3.3)
+    cam = camera_desc(nx, ny, spp, 45.0, 1.0, cam_t)
+    cfg = ray_config(bins, 375.0, 740.0, 0.01, 3, 500, True, 0.25)
+    spectral = accel.flat.spectral(375.0, 740.0, bins)
+    from source_b200 import _cabi as cabi
+    for pixels in (None, np.argwhere(np.random.default_rng(0).random((nx, ny)) < 0.4).astype(np.int32)):
+        m, v, rays = accel.render(cam, cfg, spectral, cabi.RNG_MT19937_64, seed, pixels, passes=passes, seed_stride=nx * ny)
+        frame = StatsArray3D(nx, ny, bins)
+        total = 0
+        for p in range(passes):
+            mp, vp, rp = accel.render(cam, cfg, spectral, cabi.RNG_MT19937_64, seed + p * nx * ny, pixels)
+            frame.combine_slice(pixels, 0, mp, vp, spp)
+            total += rp
+        assert rays == total
+        np.testing.assert_array_equal(m, frame.mean)
+        np.testing.assert_array_equal(v, frame.variance)
+        if pixels is not None:
+            untouched = np.ones((nx, ny), dtype=bool)
+            untouched[pixels[:, 0], pixels[:, 1]] = False
+            assert np.all(m[untouched] == 0) and np.all(v[untouched] == 0)
+    accel.close()
+    dev.close()
+
+
 def test_prism_csg_dispersion(make_backend):
     fr = parity.prism(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
     print("divergent pixel fraction:", fr)

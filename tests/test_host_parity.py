@@ -38,6 +38,10 @@ def test_cornell_frames_bit_exact(make_backend):
     parity.cornell(make_backend, exact=True)
 
 
+def test_accumulated_passes_bit_exact(make_backend):
+    parity.cornell_passes(make_backend, exact=True)
+
+
 def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 

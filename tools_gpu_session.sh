@@ -29,6 +29,10 @@ variants)
 lib:*)
   L=${S#lib:}
   RSB_LIBRARY=$PWD/build/$L.so timeout 300 python bench.py $B > $O/${TAG}_b_$L.json 2> $O/${TAG}_b_$L.err; show $O/${TAG}_b_$L.json ;;
+passes)
+  for V in ${RSB_VARIANT_PASSES:-1 2 4 8}; do
+    timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 --passes $V > $O/${TAG}_b_passes$V.json 2> $O/${TAG}_b_passes$V.err; show $O/${TAG}_b_passes$V.json
+  done ;;
 philox)
   timeout 300 python bench.py $B --rng philox > $O/${TAG}_b_philox.json 2> $O/${TAG}_b_philox.err; show $O/${TAG}_b_philox.json ;;
 full)
