@@ -34,7 +34,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 WORKLOAD = dict(name="cornell_box 1024x1024 x 256 spp x 64 bins (BASELINE configs[1])", pixels=1024, spp=256, bins=64)
 CPU_SAMPLE = dict(pixels=192, spp=8, bins=64)
-DEFAULT_PASSES = 4   # 256 spp = 4 accumulated observe() passes of 64 spp (the reference's progressive-render loop)
+DEFAULT_PASSES = 8   # 256 spp = 8 accumulated observe() passes of 32 spp (the reference's progressive-render loop)
 RAY_CFG = dict(extinction_prob=0.01, extinction_min_depth=3, max_depth=500, importance_sampling=True,
                important_path_weight=0.25)   # demos/cornell_box.py:147-156
 MIN_WL, MAX_WL = 375.0, 740.0               # observer defaults, observer.pyx:116-117

@@ -54,7 +54,7 @@ struct Context {
     size_t slot_bytes = 0;
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
-    long long chunk_items = 4LL << 20;  // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (5 KB each)
+    long long chunk_items = 8LL << 20;  // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (5 KB each)
     unsigned int* h_idle = nullptr;     // pinned
     RsbRenderStats render_stats{};
     int slots_per_sm = 8192;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)

@@ -879,6 +879,12 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
 template <int RNGMODE, bool COUNT, int FEAT>
 __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    {
+        // sparse waves (the tail of a frame, small per-rank shares): a CTA whose first index lies past the end of
+        // all four lists has nothing to shade -- leave before staging the scene (uniform across the CTA)
+        const unsigned int first = blockIdx.x * blockDim.x;
+        if (first >= a.st.n_hit[0] && first >= a.st.n_hit[1] && first >= a.st.n_hit[2] && first >= a.st.n_hit[3]) return;
+    }
     Scene sc = a.sc;
     Spectral sp = a.sp;
     constexpr bool STAGED = (FEAT & RSB_FEAT_STAGED) != 0;

@@ -115,9 +115,16 @@ class CudaRenderEngine(RenderEngine):
 
     ``bulk_update=True`` writes the slice straight into each pipeline's ``frame`` arrays (StatsArray3D)
     with the reference's combine rule instead of calling ``update`` once per pixel.
+
+    ``passes`` > 1 renders the observer's ``pixel_samples`` as that many CONCURRENT passes of
+    ``pixel_samples / passes`` samples (rsb_render_passes): pass p of slice k draws from the streams seeded
+    ``seed + (p*n_slices + k)*nx*ny + y*nx + x`` and the passes are merged in order with
+    StatsArray3D.combine_samples -- bit for bit what ``passes`` observe() calls of ``pixel_samples / passes``
+    samples into an empty accumulating pipeline give on the reference (its progressive-render loop,
+    demos/cornell_box.py:160-174), with ``passes`` times as many independent pixel streams in flight.
     """
 
-    def __init__(self, seed=1, rng="mt", device=None, bulk_update=True, backend=None):
+    def __init__(self, seed=1, rng="mt", device=None, bulk_update=True, backend=None, passes=1):
         if rng not in ("mt", "philox"):
             raise ValueError("rng must be 'mt' or 'philox'")
         if seed < 1:
@@ -125,6 +132,9 @@ class CudaRenderEngine(RenderEngine):
         self.seed = int(seed)
         self.rng_mode = cabi.RNG_MT19937_64 if rng == "mt" else cabi.RNG_PHILOX
         self.bulk_update = bulk_update
+        self.passes = int(passes)
+        if self.passes < 1:
+            raise ValueError("passes must be >= 1")
         self._device = device
         self._backend_factory = backend
         self._accel = None
@@ -162,13 +172,21 @@ class CudaRenderEngine(RenderEngine):
         world = observer.root
         accel = self._accelerator_for(world, slice_id)
         nx, ny = observer.pixels
-        cam = camera_desc(nx, ny, observer.pixel_samples, observer.fov, observer.sensitivity, observer.to_root())
+        if observer.pixel_samples % self.passes:
+            raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
+                             % (observer.pixel_samples, self.passes))
+        cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, observer.fov, observer.sensitivity,
+                          observer.to_root())
         cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
                          template.extinction_min_depth, template.max_depth, template.importance_sampling,
                          template.important_path_weight, template.max_distance)
         spectral = accel.flat.spectral(template.min_wavelength, template.max_wavelength, template.bins)
         pix = np.asarray(tasks, dtype=np.int32).reshape(-1, 2)
-        mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix)
+        if self.passes > 1:
+            mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix,
+                                                passes=self.passes, seed_stride=observer.spectral_rays * nx * ny)
+        else:
+            mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix)
         self.ray_count += rays
         if self.bulk_update:
             offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]

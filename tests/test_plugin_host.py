@@ -84,6 +84,27 @@ def test_render_engine_matches_serial_reference(api, reference, bulk):
     np.testing.assert_array_equal(np.array(pipe2.frame.variance), np.array(pipe.frame.variance))
 
 
+def test_render_engine_concurrent_passes_match_repeated_observe(api, reference):
+    """CudaRenderEngine(passes=3) rendering pixel_samples=6 in one observe() == the reference calling observe()
+    three times with pixel_samples=2 into an accumulating pipeline (re-seeded per pass, slice and pixel)."""
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(10, 8), bins=8, spectral_rays=2)
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, samples=2, **kw)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 808, passes=3)
+    world2 = scenes.cornell_box(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, samples=6, **kw)
+    cam2.render_engine = CudaRenderEngine(seed=808, rng="mt", backend=hostsim_api.HostScene, passes=3)
+    cam2.observe()
+    f = pipe2.frame
+    np.testing.assert_array_equal(np.array(f.samples), n_ref)
+    np.testing.assert_array_equal(np.array(f.mean), m_ref)
+    np.testing.assert_array_equal(np.array(f.variance), v_ref)
+    cam2.pixel_samples = 7
+    with pytest.raises(ValueError):
+        cam2.observe()
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import RGBPipeline2D
     from source_b200.plugin import CudaRenderEngine
