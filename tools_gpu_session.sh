@@ -33,6 +33,11 @@ passes)
   for V in ${RSB_VARIANT_PASSES:-1 2 4 8}; do
     timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 --passes $V > $O/${TAG}_b_passes$V.json 2> $O/${TAG}_b_passes$V.err; show $O/${TAG}_b_passes$V.json
   done ;;
+fulllib:*)
+  L=${S#fulllib:}
+  if [ "$L" != "main" ]; then export RSB_LIBRARY=$PWD/build/$L.so; fi
+  timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu --e2e-steps 1 > $O/${TAG}_bfull_$L.json 2> $O/${TAG}_bfull_$L.err; show $O/${TAG}_bfull_$L.json
+  unset RSB_LIBRARY ;;
 philox)
   timeout 300 python bench.py $B --rng philox > $O/${TAG}_b_philox.json 2> $O/${TAG}_b_philox.err; show $O/${TAG}_b_philox.json ;;
 full)

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""BASELINE config 4 geometry on one GPU: Cornell box + a 20*4^k-triangle closed mesh (k = 8: 1,310,720 triangles, SAH
+"""BASELINE config 4 geometry: Cornell box + a 20*4^k-triangle closed mesh (k = 8: 1,310,720 triangles, SAH
 tree built by this package), PinholeCamera, 64 spectral bins.  Prints one JSON line with Mrays/s and frames/s.
 
-    python tools_render_mesh.py [--subdiv 8] [--pixels 1024] [--spp 64] [--rng mt|philox]
+    python tools_render_mesh.py [--subdiv 8] [--pixels 1024] [--spp 64] [--rng mt|philox] [--passes P]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools_render_mesh.py --passes 8
+                                     (tiles interleaved over ranks, one NCCL reduce of the frame: FrameRenderer)
 """
 import argparse
 import json
@@ -28,7 +30,11 @@ def main():
     ap.add_argument("--bins", type=int, default=64)
     ap.add_argument("--rng", default="mt", choices=["mt", "philox"])
     ap.add_argument("--glass", action="store_true", help="keep the glass box and sphere of the Cornell scene")
+    ap.add_argument("--passes", type=int, default=1, help="render spp as this many concurrent accumulated passes")
     args = ap.parse_args()
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size > 1 or args.passes > 1:
+        return main_distributed(args)
     dev = Device(0)
     verts, tris, normals = scenes.icosphere(args.subdiv, radius=0.45, bumps=0.15)
     t0 = time.time()
@@ -62,6 +68,67 @@ def main():
     print(json.dumps({"scene": "cornell + %d-triangle mesh" % len(tris), "pixels": N, "spp": args.spp, "bins": args.bins, "rng": args.rng,
                       "mesh_kdtree_build_s": build_s, "ms": best[0], "rays": best[1], "Mrays_per_s": best[1] / best[0] / 1e3,
                       "frames_per_s": 1e3 / best[0], "waves": rs["waves"], "mean_sum": float(m.sum())}))
+
+
+def main_distributed(args):
+    """the same scene through distributed.FrameRenderer: one process per GPU, optional concurrent passes"""
+    import torch
+    import torch.distributed as dist
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    from source_b200.distributed import FrameRenderer
+    from source_b200.engine import Device
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev_t = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev_t)
+    device = Device(local_rank)
+    verts, tris, normals = scenes.icosphere(args.subdiv, radius=0.45, bumps=0.15)
+    t0 = time.time()
+
+    def extra(a, w):
+        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+               material=a.Lambert(a.ConstantSF(0.7)))
+    world = scenes.cornell_box(api, glass=args.glass, extra=extra)
+    build_s = time.time() - t0
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(args.pixels, args.pixels), samples=args.spp, bins=args.bins, path_weight=0.25)
+    cam.rng_mode = cabi.RNG_MT19937_64 if args.rng == "mt" else cabi.RNG_PHILOX
+    world._device = device
+    accel = world.build_accelerator()
+    renderer = FrameRenderer(cam, accel, rank, world_size, tile=16, passes=args.passes)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    renderer.step_device(seed=1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 2
+    rays_t = torch.zeros(1, dtype=torch.int64, device=dev_t)
+    e0.record()
+    for i in range(steps):
+        rays_t += renderer.step_device(seed=10 + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev_t)
+    if world_size > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    rs = device.render_stats()
+    if rank == 0:
+        total_ms, rays = float(ms.item()) / steps, int(rays_t.item()) / steps
+        print(json.dumps({"scene": "cornell + %d-triangle mesh" % len(tris), "n_gpus": world_size, "passes": args.passes,
+                          "pixels": args.pixels, "spp": args.spp, "bins": args.bins, "rng": args.rng,
+                          "mesh_kdtree_build_s": build_s, "ms": total_ms, "rays": rays, "Mrays_per_s": rays / total_ms / 1e3,
+                          "frames_per_s": 1e3 / total_ms, "waves": rs["waves"],
+                          "mean_sum": float(renderer.stats[0].sum()) if world_size == 1 else float(renderer.out[0].sum())}))
+    if world_size > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
