@@ -242,7 +242,8 @@ void kd_build(const double* boxes, int64_t n_items, int32_t max_depth, int32_t m
     out->max_depth = std::max(0, max_depth);
     out->min_items = std::max(1, min_items);
     out->hit_cost = std::max(1.0, hit_cost);
-    if (out->max_depth == 0) out->max_depth = (int32_t)ceil(8 + 1.3 * log((double)n_items));
+    // no items: log(0) = -inf, and the reference's <int32_t> cast of -inf is x86's cvttsd2si "integer indefinite"
+    if (out->max_depth == 0) out->max_depth = n_items > 0 ? (int32_t)ceil(8 + 1.3 * log((double)n_items)) : INT32_MIN;
     // BoundingBox3D() default is the empty box (lower=+inf... no: see note) then union of item boxes
     double b[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int64_t i = 0; i < n_items; ++i) {

@@ -161,7 +161,8 @@ void rsb_free(void* p) { free(p); }
 
 int rsb_kdtree_build(const double* boxes, int64_t n_items, int32_t max_depth, int32_t min_items, double hit_cost,
                      double empty_bonus, uint8_t** stream, int64_t* stream_bytes) {
-    if (!boxes || n_items <= 0 || !stream || !stream_bytes) return fail(RSB_ERR_ARG, "rsb_kdtree_build: bad arguments");
+    // n_items == 0 is legal: the reference builds a single empty leaf inside inverted (+inf, -inf) bounds
+    if ((!boxes && n_items > 0) || n_items < 0 || !stream || !stream_bytes) return fail(RSB_ERR_ARG, "rsb_kdtree_build: bad arguments");
     if (empty_bonus < 0.0 || empty_bonus > 1.0)
         return fail(RSB_ERR_ARG, "The empty_bonus cost modifier must lie in the range [0.0, 1.0].");
     HostKdTree t;

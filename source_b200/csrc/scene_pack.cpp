@@ -38,8 +38,9 @@ int csg_depth_and_leaves(const RsbSceneDesc* d, int id, int depth, int* leaves, 
 }  // namespace
 
 int pack_scene(const RsbSceneDesc* d, PackedScene* out, std::string* err) {
-    if (d->n_primitives <= 0 || d->n_world <= 0 || d->n_world > d->n_primitives) {
-        *err = "a scene needs at least one world-level primitive";
+    // an EMPTY world is legal (the reference builds a one-leaf tree and every query misses)
+    if (d->n_primitives < 0 || d->n_world < 0 || d->n_world > d->n_primitives || (d->n_primitives > 0 && d->n_world == 0)) {
+        *err = "bad primitive counts";
         return RSB_ERR_ARG;
     }
     for (int i = 0; i < d->n_primitives; ++i) {

@@ -58,9 +58,30 @@ def passes_goldens():
     save("cornell_12x12_s1_p4_b8", mean=mean, variance=var, samples=n)
 
 
+def edge_goldens():
+    """hand-placed rays and points on faces, edges, corners, tips, tangents, shared faces; empty and one-primitive worlds"""
+    world = scenes.edge_scene(api)
+    o, d, md = scenes.edge_rays()
+    g = hits(world, o, d, md)
+    cc, cp = harness.oracle_contains(world, scenes.edge_points())
+    empty = api.World()
+    ge = harness.oracle_hit(empty, o[:40], d[:40])
+    ce, pe = harness.oracle_contains(empty, scenes.edge_points())
+    one = api.World()
+    api.Sphere(0.5, one, api.translate(3, 0, 0), api.AbsorbingSurface())
+    g1 = harness.oracle_hit(one, o, d, md)
+    c1, p1 = harness.oracle_contains(one, scenes.edge_points())
+    save("edge_hits", **g, contains_count=cc, contains_prims=cp, empty_primitive=ge["primitive"], empty_contains=ce,
+         one_primitive=g1["primitive"], one_distance=g1["distance"], one_contains=c1,
+         empty_tree_sha256=digest(harness.world_kdtree_stream(empty)), one_tree_sha256=digest(harness.world_kdtree_stream(one)))
+    print("edge rays: %d, hits %d; one-sphere hits %d" % (len(o), (g["primitive"] >= 0).sum(), (g1["primitive"] >= 0).sum()))
+
+
 def main():
     if "--passes-only" in sys.argv:
         return passes_goldens()
+    if "--edge-only" in sys.argv:
+        return edge_goldens()
     # 1. RNG known answers: the reference's own test vector (raysect/core/math/tests/test_random.py:37-253)
     from raysect.core.math.tests.test_random import _random_reference
     kat = np.array(_random_reference)
@@ -114,6 +135,7 @@ def main():
     save("cornell_noglass_noimp_24", **r)
 
     passes_goldens()
+    edge_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

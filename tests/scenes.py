@@ -126,6 +126,80 @@ def primitive_zoo(api):
     return world
 
 
+def edge_scene(api):
+    """UNROTATED primitives at integer positions, so that rays can be aimed exactly at faces, edges, corners, tips,
+    tangent lines and shared faces: every `==`, `<=` and zero-discriminant branch of the hit code sees exact input."""
+    a = api
+    world = a.World()
+    m = a.AbsorbingSurface()
+    a.Box(a.Point3D(-1, -1, -1), a.Point3D(1, 1, 1), world, a.translate(0, 0, 0), m)
+    a.Sphere(0.5, world, a.translate(3, 0, 0), m)
+    a.Cylinder(0.5, 1.0, world, a.translate(0, 3, 0), m)
+    a.Cone(0.5, 1.0, world, a.translate(0, -3, 0), m)
+    a.Box(a.Point3D(5, -0.5, -0.5), a.Point3D(6, 0.5, 0.5), world, a.translate(0, 0, 0), m)      # shares the face x = 6 ...
+    a.Box(a.Point3D(6, -0.5, -0.5), a.Point3D(7, 0.5, 0.5), world, a.translate(0, 0, 0), m)      # ... with this one
+    a.Box(a.Point3D(-4, -1, 0), a.Point3D(-3, 1, 0), world, a.translate(0, 0, 0), m)              # zero thickness
+    a.Subtract(a.Box(a.Point3D(-0.5, -0.5, -0.5), a.Point3D(0.5, 0.5, 0.5)), a.Sphere(0.5), world, a.translate(0, 0, 4), m)
+    a.Union(a.Box(a.Point3D(-0.5, -0.5, -0.5), a.Point3D(0.5, 0.5, 0.5)),
+            a.Box(a.Point3D(0.5, -0.5, -0.5), a.Point3D(1.5, 0.5, 0.5)), world, a.translate(3, 0, 4), m)     # coplanar operands
+    return world
+
+
+def edge_rays():
+    """(origins, directions, max_distance) of hand-placed rays: see edge_scene"""
+    inf = np.inf
+    rows = []
+
+    def add(o, d, md=inf):
+        rows.append((o, d, md))
+    for s in (1.0, 1e-3, 1e3, 7.0):                          # directions need not be unit length (core/ray.pxd)
+        add((-3, 0, 0), (s, 0, 0)); add((0, 0, -3), (0, 0, s)); add((3, 0, -3), (0, 0, s)); add((0, 3, -3), (0, 0, s))
+        add((0, -3, -3), (0, 0, s)); add((-3, 0.25, 0.125), (s, 0, 0)); add((4, 0.1, 0.2), (s * 0.6, 0, s * 0.8))
+    # origins exactly ON a box face, pointing out / in / along it; edges and corners
+    for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, 0, 1), (0.6, 0.8, 0), (-0.6, 0.8, 0)):
+        add((1, 0, 0), d); add((1, 1, 0), d); add((1, 1, 1), d); add((-1, 0.5, -1), d)
+    add((-3, 1, 1), (1, 0, 0)); add((-3, 1, 0), (1, 0, 0)); add((-3, -1, -1), (1, 0, 0)); add((-2, -2, -2), (1, 1, 1))
+    add((2, 2, 2), (-1, -1, -1)); add((-3, 1, 0.5), (1, 0, 0)); add((0, 0, 0), (1, 0, 0)); add((0, 0, 0), (0, -1, 0))
+    # sphere: tangent lines (zero discriminant), centre, surface origins
+    add((3, 0.5, -3), (0, 0, 1)); add((3.5, 0, -3), (0, 0, 1)); add((3, -0.5, 3), (0, 0, -1)); add((3, 0, 0), (0, 1, 0))
+    add((3.5, 0, 0), (1, 0, 0)); add((3.5, 0, 0), (-1, 0, 0)); add((3, 0, 0.5), (0, 0, 1)); add((3, 0.5, 0), (1, 0, 0))
+    # cylinder: parallel to the axis at r, inside, outside; in the cap planes; tangent to the barrel
+    for x in (0.5, 0.25, 0.0, 0.75, -0.5):
+        add((x, 3, -2), (0, 0, 1)); add((x, 3, 3), (0, 0, -1)); add((x, 3, 0.5), (0, 0, 1))
+    add((-2, 3, 0), (1, 0, 0)); add((-2, 3, 1), (1, 0, 0)); add((-2, 3.5, 0.5), (1, 0, 0)); add((-2, 2.5, 0.25), (1, 0, 0))
+    add((0, 3, 0), (0, 0, 1)); add((0, 3, 1), (0, 0, -1)); add((0.5, 3, 0), (1, 0, 0)); add((0, 3, 0.5), (1, 0, 0))
+    # cone: through the tip, along the axis, in the base plane, along the slant
+    add((0, -3, -2), (0, 0, 1)); add((0, -3, 3), (0, 0, -1)); add((-2, -3, 1), (1, 0, 0)); add((-2, -3, 0), (1, 0, 0))
+    add((0.5, -3, 0), (-0.5, 0, 1)); add((-0.5, -3, 0), (0.5, 0, 1)); add((0.25, -3, -2), (0, 0, 1)); add((0, -3, 0.5), (1, 0, 0))
+    add((0, -3, 1), (0, 0, 1)); add((0, -3, 1), (0, 0, -1)); add((0, -3, 1), (1, 0, 0))
+    # shared face of two boxes: ties between the exit of one and the entry of the other
+    add((4, 0, 0), (1, 0, 0)); add((8, 0, 0), (-1, 0, 0)); add((6, 0, 0), (1, 0, 0)); add((6, 0, 0), (-1, 0, 0))
+    add((6, 0, -2), (0, 0, 1)); add((6, 0.5, -2), (0, 0, 1)); add((5.5, 0, 0), (1, 0, 0)); add((6, 0, 0), (0, 1, 0))
+    # zero-thickness box: through it, in its plane, from a point on it
+    add((-3.5, 0, -1), (0, 0, 1)); add((-3.5, 0, 1), (0, 0, -1)); add((-5, 0, 0), (1, 0, 0)); add((-3.5, 0, 0), (0, 0, 1))
+    add((-3.5, 0, 0), (1, 0, 0)); add((-3.5, -2, 0), (0, 1, 0))
+    # CSG: tangent operands, coplanar faces of a union
+    add((0, 0, 2), (0, 0, 1)); add((0.5, 0.5, 2), (0, 0, 1)); add((-2, 0, 4), (1, 0, 0)); add((0, 0, 4), (1, 0, 0))
+    add((0.45, 0.45, 4), (-1, 0, 0)); add((1, 0, 4), (1, 0, 0)); add((3.5, 0, 2), (0, 0, 1)); add((3.5, 0, 4), (1, 0, 0))
+    add((3.5, 0, 4), (-1, 0, 0)); add((6, 0, 4), (-1, 0, 0)); add((3.5, -2, 4), (0, 1, 0))
+    # max_distance: zero, exactly the hit distance, one ulp below and above it, huge
+    for md in (0.0, 2.0, np.nextafter(2.0, 0.0), np.nextafter(2.0, 3.0), 1e300, 5e-324):
+        add((-3, 0, 0), (1, 0, 0), md); add((3, 0, -2.5), (0, 0, 1), md); add((0, 0, 0), (1, 0, 0), md)
+    o = np.array([r[0] for r in rows], dtype=np.float64)
+    d = np.array([r[1] for r in rows], dtype=np.float64)
+    md = np.array([r[2] for r in rows], dtype=np.float64)
+    return np.ascontiguousarray(o), np.ascontiguousarray(d), np.ascontiguousarray(md)
+
+
+def edge_points():
+    """points exactly on surfaces, edges, corners, tips and shared faces (Primitive.contains boundary rules)"""
+    pts = [(1, 0, 0), (1, 1, 1), (-1, -1, -1), (0, 0, 0), (1.0000000001, 0, 0), (3.5, 0, 0), (3, 0.5, 0), (3, 0, 0),
+           (0.5, 3, 0.5), (0, 3, 0), (0, 3, 1), (0, 3, 1.0000001), (0.5, 3, 0), (0, -3, 1), (0, -3, 0), (0.5, -3, 0),
+           (0.25, -3, 0.5), (6, 0, 0), (5, 0, 0), (7, 0.5, 0.5), (-3.5, 0, 0), (-3.5, 0, 1e-12), (0, 0, 4), (0.5, 0, 4),
+           (0.45, 0.45, 4.45), (3.5, 0, 4), (4.5, 0, 4), (2.5, 0, 4), (100, 100, 100), (0, 0, 4.5)]
+    return np.ascontiguousarray(np.array(pts, dtype=np.float64))
+
+
 def zoo_rays(n, seed=3):
     """Rays aimed from a shell of random origins at random points inside the zoo's extent, plus rays
     started INSIDE primitives (so exiting hits and t0 < 0 branches are exercised)."""

@@ -30,6 +30,10 @@ def test_zoo_hits_contains(make_backend):
     parity.zoo(make_backend)
 
 
+def test_edge_cases(make_backend):
+    parity.edge(make_backend)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 
