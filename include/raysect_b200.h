@@ -40,11 +40,12 @@ extern "C" {
 #define RSB_PRIM_INTERSECT 6
 #define RSB_PRIM_SUBTRACT 7
 
-/* materials: raysect/optical/material/{absorber,lambert,dielectric}.pyx, emitter/uniform.pyx */
+/* materials: raysect/optical/material/{absorber,lambert,dielectric,conductor}.pyx, emitter/{uniform,unity}.pyx */
 #define RSB_MAT_ABSORBER 0
 #define RSB_MAT_EMITTER 1
 #define RSB_MAT_LAMBERT 2
 #define RSB_MAT_DIELECTRIC 3
+#define RSB_MAT_CONDUCTOR 4 /* raysect/optical/material/conductor.pyx:39-147 (specular Fresnel conductor) */
 
 #define RSB_RNG_MT19937_64 0 /* raysect/core/math/random.pyx:99-265, one stream per pixel = seed(seed + y*nx + x) */
 #define RSB_RNG_PHILOX 1     /* counter based, keyed on (seed, pixel, sample) */
@@ -124,10 +125,16 @@ typedef struct RsbRayConfig {
 typedef struct RsbSpectral {
     int32_t bins;
     int32_t n_materials;
-    const double* tables;     /* [n_materials][bins] reflectivity | emission | transmission */
+    const double* tables;     /* [n_materials][bins] reflectivity | emission | transmission | conductor index n */
     const double* scale;      /* [n_materials] emitter scale */
     const double* index_in;   /* [n_materials] dielectric index.average() */
     const double* index_out;  /* [n_materials] dielectric external_index.average() */
+    /* materials that sample TWO spectral functions (Conductor: index n -> row i, extinction k -> row table2[i]):
+     * `tables` then holds n_tables >= n_materials rows, the extra rows after the per-material ones.
+     * n_tables == 0 means n_materials rows and no second tables (table2 may be NULL). */
+    int32_t n_tables;
+    int32_t pad;
+    const int32_t* table2;    /* [n_materials] row of the material's second table, or -1 */
 } RsbSpectral;
 
 typedef struct RsbRngDesc {

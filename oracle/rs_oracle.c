@@ -820,6 +820,23 @@ static void trace(tracer* T, ray_t ray, int depth, double* spectrum) {
             trace(T, dr, depth + 1, spectrum);
         }
     }
+    else if (mtype == RSB_MAT_CONDUCTOR) {                                 /* conductor.pyx:75-147 */
+        v3 inc = norm3(xvec(it.w2p, ray.d)), n = norm3(it.n);
+        double ci = dot3(n, inc), tmp = 2 * ci;
+        ray_t dr;
+        dr.maxd = ray.maxd;
+        dr.d = xvec(it.p2w, V(inc.x - tmp * n.x, inc.y - tmp * n.y, inc.z - tmp * n.z));
+        dr.o = (ci > 0.0) ? xpoint(it.p2w, it.pin) : xpoint(it.p2w, it.pout);   /* the side comes from ci, not from `exiting` */
+        T->rays += 1;
+        trace(T, dr, depth + 1, spectrum);
+        ci = fabs(ci);
+        const double* kk = T->sp->tables + (size_t)T->sp->table2[mat] * bins;     /* extinction k; `table` is the index n */
+        for (int i = 0; i < bins; ++i) {                                          /* _fresnel, conductor.pyx:132-145 */
+            double nn = table[i], k = kk[i];
+            double ci2 = ci * ci, k0 = nn * nn + k * k, k1 = k0 * ci2 + 1, k2 = 2 * nn * ci, k3 = k0 + ci2;
+            spectrum[i] *= 0.5 * ((k1 - k2) / (k1 + k2) + (k3 - k2) / (k3 + k2));
+        }
+    }
     /* _sample_volumes, ray.pyx:422-455 */
     int32_t inside[16];
     int n_in = world_contains(T->c, ray.o, inside, 16);

@@ -13,7 +13,8 @@ __version__ = "0.1.0"
 from .math3d import (AffineMatrix3D, BoundingBox3D, BoundingSphere3D, Normal3D, Point3D, Vector3D, rotate, rotate_x,
                      rotate_y, rotate_z, translate)
 from .spectral import ConstantSF, InterpolatedSF, NumericallyIntegratedSF, Sellmeier, SpectralFunction
-from .material import AbsorbingSurface, Dielectric, Lambert, Material, UniformSurfaceEmitter, schott
+from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Material, UniformSurfaceEmitter,
+                       UnitySurfaceEmitter, schott)
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Primitive, Ray, Sphere,
                          Subtract, Union, World)
 from .observer import FullFrameSampler2D, Observer, PinholeCamera, SpectralPowerPipeline2D, SpectralSlice, StatsArray3D

@@ -703,6 +703,12 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");
     if (spectral->n_materials != ds->n_materials) return fail(RSB_ERR_ARG, "rsb_render: spectral tables do not match the scene's materials");
+    const int n_tables = spectral->n_tables > 0 ? spectral->n_tables : spectral->n_materials;
+    if (n_tables < spectral->n_materials) return fail(RSB_ERR_ARG, "rsb_render: n_tables is smaller than the number of materials");
+    for (int i = 0; i < ds->n_materials; ++i)
+        if (ds->mat_type[i] == RSB_MAT_CONDUCTOR &&
+            (!spectral->table2 || spectral->table2[i] < 0 || spectral->table2[i] >= n_tables))
+            return fail(RSB_ERR_ARG, "rsb_render: a Conductor needs its extinction table (RsbSpectral.table2)");
     if (config->important_path_weight < 0 || config->important_path_weight > 1.0)
         return fail(RSB_ERR_ARG, "Important path weight must be in the range [0, 1].");
     if (rng->seed == 0) return fail(RSB_ERR_ARG, "rng seed must be >= 1");
@@ -729,13 +735,14 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         m.type = ds->mat_type[i];
         m.transmission_only = ds->mat_transmission_only[i];
         m.table = i;
+        m.table2 = spectral->table2 ? spectral->table2[i] : -1;
         m.scale = spectral->scale ? spectral->scale[i] : 1.0;
         m.index_in = spectral->index_in ? spectral->index_in[i] : 1.0;
         m.index_out = spectral->index_out ? spectral->index_out[i] : 1.0;
     }
     size_t mat_bytes = (((size_t)nm * sizeof(Material) + 15) / 16) * 16;
-    size_t tab_bytes = (((size_t)nm * spectral->bins * 8 + 15) / 16) * 16;
-    size_t tab_alloc = (size_t)nm * spectral->bins * 16 + 16;
+    size_t tab_bytes = (((size_t)n_tables * spectral->bins * 8 + 15) / 16) * 16;
+    size_t tab_alloc = (size_t)n_tables * spectral->bins * 16 + 16;
     if (c->mats_cap < mat_bytes) {
         cudaFree(c->d_mats);
         c->d_mats = nullptr; c->mats_cap = 0;
@@ -750,10 +757,10 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     }
     RSB_CUDA(cudaMemcpyAsync(c->d_mats, mats.data(), (size_t)nm * sizeof(Material), cudaMemcpyHostToDevice, st));
     // tables, followed by their natural logs (exp(length * ln T) form of the Beer-Lambert pow in the replay)
-    std::vector<double> both((size_t)nm * spectral->bins * 2);
-    for (size_t i = 0; i < (size_t)nm * spectral->bins; ++i) {
+    std::vector<double> both((size_t)n_tables * spectral->bins * 2);
+    for (size_t i = 0; i < (size_t)n_tables * spectral->bins; ++i) {
         both[i] = spectral->tables[i];
-        both[(size_t)nm * spectral->bins + i] = log(spectral->tables[i]);
+        both[(size_t)n_tables * spectral->bins + i] = log(spectral->tables[i]);
     }
     RSB_CUDA(cudaMemcpyAsync(c->d_tables, both.data(), both.size() * 8, cudaMemcpyHostToDevice, st));
     // the two host staging buffers above are stack/heap temporaries: make the copies complete before returning
@@ -764,9 +771,10 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.sc = ds->sc;
     a.sp.mats = c->d_mats;
     a.sp.tables = c->d_tables;
-    a.sp.tables_ln = c->d_tables + (size_t)nm * spectral->bins;
+    a.sp.tables_ln = c->d_tables + (size_t)n_tables * spectral->bins;
     a.sp.bins = spectral->bins;
     a.sp.n_materials = nm;
+    a.sp.n_tables = n_tables;
     a.cfg.bins = config->bins;
     a.cfg.extinction_min_depth = config->extinction_min_depth;
     a.cfg.max_depth = config->max_depth;

@@ -803,6 +803,7 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
             a.st.status[slot] = SLOT_HIT;
             list = a.sp.mats[sc.prims[rec.prim].material].type;     // 0..3: per-material hit lists
+            if (list == MAT_CONDUCTOR) list = MAT_DIELECTRIC;        // the specular family shares one list
         } else {
             a.st.status[slot] = SLOT_ENDED_ZERO;
             list = 4;                                                // ended list
@@ -920,12 +921,12 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     Spectral sp = a.sp;
     int tab_bytes = 0;
     if (a.tables_staged) {
-        // tables and their logs are contiguous in HBM: [n_materials][bins] x 2
-        tab_bytes = ((sp.n_materials * sp.bins * 16 + 15) / 16) * 16;
+        // tables and their logs are contiguous in HBM: [n_tables][bins] x 2
+        tab_bytes = ((sp.n_tables * sp.bins * 16 + 15) / 16) * 16;
         copy16(smem, a.sp.tables, tab_bytes);
         __syncthreads();
         sp.tables = reinterpret_cast<const double*>(smem);
-        sp.tables_ln = sp.tables + (size_t)sp.n_materials * sp.bins;
+        sp.tables_ln = sp.tables + (size_t)sp.n_tables * sp.bins;
     }
     // 32 log entries per warp, staged in shared memory and read back as one broadcast LDS.128 per entry
     LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;

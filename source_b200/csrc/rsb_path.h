@@ -30,10 +30,11 @@ struct RayConfig {   // optical Ray template fields, raysect/optical/ray.pyx:85-
 
 struct Spectral {    // per spectral slice: what SpectralFunction.sample()/average() cache on the host
     const Material* mats;
-    const double* tables;   // [n_materials][bins]
-    const double* tables_ln;   // [n_materials][bins] natural log of `tables` (device replay only), or null
+    const double* tables;   // [n_tables][bins]: one row per material, then the second tables (conductor extinction)
+    const double* tables_ln;   // [n_tables][bins] natural log of `tables` (device replay only), or null
     int32_t bins;
     int32_t n_materials;
+    int32_t n_tables;
 };
 
 struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207
@@ -50,6 +51,8 @@ enum LogOp : int32_t {
     LOG_MULA = 1,   // s *= table[i]               Spectrum.mul_array (spectrum.pyx:491)
     LOG_POWA = 2,   // s *= pow(table[i], v)       Dielectric.evaluate_volume (dielectric.pyx:313-330)
     LOG_EMIT = 3,   // s  = table[i] * v           UniformSurfaceEmitter.evaluate_surface (uniform.pyx:67-81)
+    LOG_FRESNEL = 4,   // s *= fresnel(v, n[i], k[i])  Conductor.evaluate_surface (conductor.pyx:122-128); n = table,
+                       //                              k = the row in bits 8.. of the op word
 };
 
 struct __attribute__((aligned(16))) LogEntry {
@@ -307,6 +310,20 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
             log.push(LOG_MULS, 0, pdf_cos);
             log.push(LOG_MULA, mat.table, 0.0);
             stats.table_read();
+        } else if (mat.type == MAT_CONDUCTOR) {
+            // Conductor.evaluate_surface (conductor.pyx:75-130): mirror reflection, no random draws; the per-bin
+            // Fresnel reflectance of the complex index n + ik is applied on the way back up
+            V3 incident = normalise(xform_vector(w2p, d));
+            V3 normal = normalise(is.normal);
+            double ci = dot(normal, incident);
+            double temp = 2 * ci;
+            V3 reflected = v3(incident.x - temp * normal.x, incident.y - temp * normal.y, incident.z - temp * normal.z);
+            next_d = xform_vector(p2w, reflected);
+            // "we do not use the supplied exiting parameter" (conductor.pyx:108-118): the side comes from ci
+            next_o = (ci > 0.0) ? xform_point(p2w, is.inside) : xform_point(p2w, is.outside);
+            log.push(LOG_FRESNEL | (mat.table2 << 8), mat.table, fabs(ci));
+            stats.table_read();
+            stats.table_read();
         } else {
             // Dielectric.evaluate_surface (dielectric.pyx:153-303)
             V3 incident = normalise(xform_vector(w2p, d));
@@ -405,9 +422,20 @@ RSB_HD void welford_add(double sample, double* m, double* v, int n) {
 }
 
 // One log entry applied to one bin's running value (the reference's unwind, one Spectrum op at a time)
+// Conductor._fresnel (conductor.pyx:132-145)
+RSB_HD double conductor_fresnel(double ci, double n, double k) {
+    double ci2 = ci * ci;
+    double k0 = n * n + k * k;
+    double k1 = k0 * ci2 + 1;
+    double k2 = 2 * n * ci;
+    double k3 = k0 + ci2;
+    return 0.5 * ((k1 - k2) / (k1 + k2) + (k3 - k2) / (k3 + k2));
+}
+
 RSB_HD double apply_entry(double s, int op, int table, double v, const Spectral& sp, int bin) {
     if (op == LOG_MULS) return s * v;
     double t = sp.tables[(size_t)table * sp.bins + bin];
+    if ((op & 0xff) == LOG_FRESNEL) return s * conductor_fresnel(v, t, sp.tables[(size_t)(op >> 8) * sp.bins + bin]);
     if (op == LOG_MULA) return s * t;
     if (op == LOG_POWA) {
 #ifdef __CUDA_ARCH__

@@ -29,6 +29,7 @@ enum MatType : int32_t {
     MAT_EMITTER = 1,    // raysect/optical/material/emitter/uniform.pyx:67-81
     MAT_LAMBERT = 2,    // raysect/optical/material/lambert.pyx:77-105
     MAT_DIELECTRIC = 3, // raysect/optical/material/dielectric.pyx:153-330
+    MAT_CONDUCTOR = 4,  // raysect/optical/material/conductor.pyx:75-147 (shaded with the dielectric family)
 };
 
 // 16-byte kd-tree node.  Branch: split, upper child id, axis 0..2 (lower child is id+1).
@@ -86,8 +87,8 @@ struct Mesh {
 struct Material {
     int32_t type;
     int32_t transmission_only;
-    int32_t table;      // row of the per-slice spectral table (reflectivity | emission | transmission)
-    int32_t pad;
+    int32_t table;      // row of the per-slice spectral table (reflectivity | emission | transmission | conductor n)
+    int32_t table2;     // conductor: row of the extinction table k; else -1
     double scale;       // emitter scale
     double index_in;    // dielectric: index.average(min,max) for the slice
     double index_out;   // dielectric: external_index.average(min,max)

@@ -26,7 +26,9 @@ _SHAPES = {
 }
 _MATERIALS = {
     "AbsorbingSurface": cabi.MAT_ABSORBER, "UniformSurfaceEmitter": cabi.MAT_EMITTER,
+    "UnitySurfaceEmitter": cabi.MAT_EMITTER,     # emitter/unity.pyx:65-76: every bin 1.0 = a constant table, scale 1
     "Lambert": cabi.MAT_LAMBERT, "Dielectric": cabi.MAT_DIELECTRIC,
+    "Conductor": cabi.MAT_CONDUCTOR,             # conductor.pyx:39-147 (RoughConductor is a different class: unsupported)
 }
 
 # world tree parameters of _PrimitiveKDTree (raysect/core/acceleration/kdtree.pyx:43)
@@ -98,13 +100,20 @@ class FlatScene:
         """What SpectralFunction.sample()/average() return for every material on this slice
         (raysect/optical/spectralfunction.pyx:140-216); evaluated by the object model itself."""
         n = len(self.materials)
-        tables = np.zeros((n, bins), dtype=np.float64)
+        # materials that sample two spectral functions (Conductor: index, extinction) get an extra table row each
+        second = [i for i, t in enumerate(self.mat_type) if t == cabi.MAT_CONDUCTOR]
+        table2 = np.full(n, -1, dtype=np.int32)
+        for j, i in enumerate(second):
+            table2[i] = n + j
+        tables = np.zeros((n + len(second), bins), dtype=np.float64)
         scale = np.ones(n, dtype=np.float64)
         index_in = np.ones(n, dtype=np.float64)
         index_out = np.ones(n, dtype=np.float64)
         for i, (m, t) in enumerate(zip(self.materials, self.mat_type)):
             if t == cabi.MAT_LAMBERT:
                 tables[i] = np.asarray(lambert_reflectivity(m).sample(min_wavelength, max_wavelength, bins))
+            elif t == cabi.MAT_EMITTER and not hasattr(m, "emission_spectrum"):
+                tables[i] = 1.0     # UnitySurfaceEmitter (emitter/unity.pyx:73-75): samples[:] = 1.0; 1.0 * 1.0 is exact
             elif t == cabi.MAT_EMITTER:
                 tables[i] = np.asarray(m.emission_spectrum.sample(min_wavelength, max_wavelength, bins))
                 scale[i] = m.scale
@@ -112,6 +121,10 @@ class FlatScene:
                 tables[i] = np.asarray(m.transmission.sample(min_wavelength, max_wavelength, bins))
                 index_in[i] = m.index.average(min_wavelength, max_wavelength)
                 index_out[i] = m.external_index.average(min_wavelength, max_wavelength)
+            elif t == cabi.MAT_CONDUCTOR:
+                # conductor.pyx:101-102: n and k resampled onto the ray's bins
+                tables[i] = np.asarray(m.index.sample(min_wavelength, max_wavelength, bins))
+                tables[table2[i]] = np.asarray(m.extinction.sample(min_wavelength, max_wavelength, bins))
         s = cabi.RsbSpectral()
         s.bins = bins
         s.n_materials = n
@@ -119,7 +132,9 @@ class FlatScene:
         s.scale = cabi.ptr(scale, C.c_double)
         s.index_in = cabi.ptr(index_in, C.c_double)
         s.index_out = cabi.ptr(index_out, C.c_double)
-        s._keep = (tables, scale, index_in, index_out)
+        s.n_tables = tables.shape[0]
+        s.table2 = cabi.ptr(table2, C.c_int32)
+        s._keep = (tables, scale, index_in, index_out, table2)
         return s
 
 

@@ -50,6 +50,21 @@ class UniformSurfaceEmitter(Material):
         self.importance = 1.0
 
 
+class Conductor(Material):
+    """conductor.pyx:39-147: specular reflection off a metal with complex refractive index n + ik (Fresnel)"""
+
+    def __init__(self, index, extinction):
+        super().__init__()
+        if not isinstance(index, SpectralFunction) or not isinstance(extinction, SpectralFunction):
+            raise TypeError("index and extinction must be SpectralFunction objects")
+        self.index = index
+        self.extinction = extinction
+
+
+class UnitySurfaceEmitter(Material):
+    """emitter/unity.pyx:37-76: 1 W/m^2/str/nm in every bin, whatever the direction (importance stays 0)"""
+
+
 class Dielectric(Material):
     """dielectric.pyx:120-330: Fresnel reflect/transmit with Beer-Lambert volume attenuation, importance 1"""
 

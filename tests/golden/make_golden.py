@@ -77,7 +77,18 @@ def edge_goldens():
     print("edge rays: %d, hits %d; one-sphere hits %d" % (len(o), (g["primitive"] >= 0).sum(), (g1["primitive"] >= 0).sum()))
 
 
+def metal_goldens():
+    """Conductor (specular, complex index) on an analytic sphere and on a smooth-shaded mesh, UnitySurfaceEmitter"""
+    world = scenes.metal_scene(api)
+    cam, r = render(world, dict(pixels=(28, 24), samples=4, bins=12, path_weight=0.3), 2024)
+    save("metal_28x24_s4_b12", **r)
+    cam, r = render(world, dict(pixels=(16, 16), samples=3, bins=8, spectral_rays=4, importance=False), 77)
+    save("metal_16x16_s3_b8_r4_noimp", **r)
+
+
 def main():
+    if "--metal-only" in sys.argv:
+        return metal_goldens()
     if "--passes-only" in sys.argv:
         return passes_goldens()
     if "--edge-only" in sys.argv:
@@ -136,6 +147,7 @@ def main():
 
     passes_goldens()
     edge_goldens()
+    metal_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

@@ -169,6 +169,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
         mats[i].type = h->ps.mat_type[i];
         mats[i].transmission_only = h->ps.mat_transmission_only[i];
         mats[i].table = i;
+        mats[i].table2 = spectral->table2 ? spectral->table2[i] : -1;
         mats[i].scale = spectral->scale ? spectral->scale[i] : 1.0;
         mats[i].index_in = spectral->index_in ? spectral->index_in[i] : 1.0;
         mats[i].index_out = spectral->index_out ? spectral->index_out[i] : 1.0;
@@ -179,6 +180,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     sp.tables_ln = nullptr;
     sp.bins = spectral->bins;
     sp.n_materials = nm;
+    sp.n_tables = spectral->n_tables > 0 ? spectral->n_tables : nm;
     RayConfig cfg;
     cfg.bins = config->bins;
     cfg.extinction_min_depth = config->extinction_min_depth;

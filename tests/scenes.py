@@ -53,6 +53,29 @@ def cornell_box(api, glass=True, extra=None):
     return world
 
 
+GOLD_WAVELENGTHS = [300.0, 400.0, 450.0, 500.0, 550.0, 600.0, 700.0, 800.0]
+GOLD_N = [1.53, 1.47, 1.38, 0.97, 0.43, 0.25, 0.16, 0.15]      # gold-like complex index n + ik
+GOLD_K = [1.89, 1.95, 1.92, 1.87, 2.46, 2.99, 3.95, 4.85]
+
+
+def metal_scene(api):
+    """Cornell box with metal: a Conductor sphere and a smooth-shaded Conductor mesh (interpolated normals: the side
+    of the reflection is chosen from n.d, conductor.pyx:108-118), the glass box kept, and a UnitySurfaceEmitter."""
+    a = api
+    gold = a.Conductor(a.InterpolatedSF(GOLD_WAVELENGTHS, GOLD_N), a.InterpolatedSF(GOLD_WAVELENGTHS, GOLD_K))
+    verts, tris, normals = icosphere(2, radius=0.3, bumps=0.2)
+
+    def extra(a, w):
+        a.Sphere(0.35, parent=w, transform=a.translate(-0.45, -0.65, -0.3), material=gold)
+        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w,
+               transform=a.translate(0.3, 0.35, -0.2) * a.rotate(15, 25, 5), material=gold)
+        a.Sphere(0.12, parent=w, transform=a.translate(-0.6, 0.6, 0.2), material=a.UnitySurfaceEmitter())
+    world = cornell_box(a, glass=False, extra=extra)
+    a.Box(a.Point3D(-0.4, 0, -0.4), a.Point3D(0.3, 1.0, 0.3), parent=world,
+          transform=a.translate(0.45, -1 + 1e-6, 0.45) * a.rotate(30, 0, 0), material=a.schott("N-BK7"))
+    return world
+
+
 def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_rays=1, min_depth=3, max_depth=500,
                    extinction=0.01, path_weight=0.25, importance=True):
     """Camera of demos/cornell_box.py:147-156 with a SpectralPowerPipeline2D and a full-frame sampler."""

@@ -92,6 +92,11 @@ def test_concurrent_passes_equal_sequential_passes_bit_for_bit(device, make_back
     dev.close()
 
 
+def test_conductor_and_unity_emitter(make_backend):
+    fr = parity.metal(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+    print("divergent pixel fractions:", fr)
+
+
 def test_prism_csg_dispersion(make_backend):
     fr = parity.prism(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
     print("divergent pixel fraction:", fr)

@@ -46,6 +46,10 @@ def test_accumulated_passes_bit_exact(make_backend):
     parity.cornell_passes(make_backend, exact=True)
 
 
+def test_conductor_and_unity_emitter_bit_exact(make_backend):
+    parity.metal(make_backend, exact=True)
+
+
 def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 

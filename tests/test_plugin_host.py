@@ -105,6 +105,22 @@ def test_render_engine_concurrent_passes_match_repeated_observe(api, reference):
         cam2.observe()
 
 
+def test_render_engine_on_real_conductor_and_unity_emitter_objects(api, reference):
+    """raysect.optical.material.Conductor / UnitySurfaceEmitter objects flattened from a live Raysect scenegraph"""
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(12, 10), samples=3, bins=6)
+    world = scenes.metal_scene(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 4711)
+    world2 = scenes.metal_scene(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
+    cam2.render_engine = CudaRenderEngine(seed=4711, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert m_ref.sum() > 0
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import RGBPipeline2D
     from source_b200.plugin import CudaRenderEngine
