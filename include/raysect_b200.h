@@ -46,6 +46,8 @@ extern "C" {
 #define RSB_MAT_LAMBERT 2
 #define RSB_MAT_DIELECTRIC 3
 #define RSB_MAT_CONDUCTOR 4 /* raysect/optical/material/conductor.pyx:39-147 (specular Fresnel conductor) */
+#define RSB_MAT_VOLUME_EMITTER 5 /* emitter/uniform.pyx:91-133, emitter/unity.pyx:79-99 on emitter/homogeneous.pyx:40-93
+                                    (HomogeneousVolumeEmitter: NullSurface + emission * path length) */
 
 #define RSB_RNG_MT19937_64 0 /* raysect/core/math/random.pyx:99-265, one stream per pixel = seed(seed + y*nx + x) */
 #define RSB_RNG_PHILOX 1     /* counter based, keyed on (seed, pixel, sample) */
@@ -125,7 +127,7 @@ typedef struct RsbRayConfig {
 typedef struct RsbSpectral {
     int32_t bins;
     int32_t n_materials;
-    const double* tables;     /* [n_materials][bins] reflectivity | emission | transmission | conductor index n */
+    const double* tables;     /* [n_materials][bins] reflectivity | (surface or volume) emission | transmission | conductor index n */
     const double* scale;      /* [n_materials] emitter scale */
     const double* index_in;   /* [n_materials] dielectric index.average() */
     const double* index_out;  /* [n_materials] dielectric external_index.average() */

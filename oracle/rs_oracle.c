@@ -727,13 +727,16 @@ static double important_pdf(tracer* T, v3 origin, v3 direction) {           /* w
 }
 
 /* Ray.trace, optical/ray.pyx:338-401: fills spectrum[bins]; recursion through the material */
-static void trace(tracer* T, ray_t ray, int depth, double* spectrum) {
+static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep_alive);
+static void trace(tracer* T, ray_t ray, int depth, double* spectrum) { trace_ka(T, ray, depth, spectrum, 0); }
+
+static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep_alive) {
     const RsbRayConfig* cfg = T->cfg;
     const RsbSceneDesc* d = T->c->s->d;
     int bins = cfg->bins;
     memset(spectrum, 0, sizeof(double) * (size_t)bins);
     double normalisation;
-    if (depth < cfg->extinction_min_depth) normalisation = 1.0;
+    if (keep_alive || depth < cfg->extinction_min_depth) normalisation = 1.0;     /* ray.pyx:382 */
     else {
         if (depth >= cfg->max_depth || uniform(T->rng) < cfg->extinction_prob) return;
         normalisation = 1 / (1 - cfg->extinction_prob);
@@ -820,6 +823,14 @@ static void trace(tracer* T, ray_t ray, int depth, double* spectrum) {
             trace(T, dr, depth + 1, spectrum);
         }
     }
+    else if (mtype == RSB_MAT_VOLUME_EMITTER) {                            /* NullSurface.evaluate_surface, material.pyx:126-147 */
+        ray_t dr;
+        dr.maxd = ray.maxd;
+        dr.d = ray.d;
+        dr.o = it.exiting ? xpoint(it.p2w, it.pout) : xpoint(it.p2w, it.pin);
+        T->rays += 1;
+        trace_ka(T, dr, depth, spectrum, 1);                                 /* daughter.depth -= 1; keep_alive=True */
+    }
     else if (mtype == RSB_MAT_CONDUCTOR) {                                 /* conductor.pyx:75-147 */
         v3 inc = norm3(xvec(it.w2p, ray.d)), n = norm3(it.n);
         double ci = dot3(n, inc), tmp = 2 * ci;
@@ -844,6 +855,18 @@ static void trace(tracer* T, ray_t ray, int depth, double* spectrum) {
         v3 start = xpoint(it.p2w, it.p);
         for (int k = 0; k < n_in && k < 16; ++k) {
             int m2 = d->prim_material[inside[k]];
+            if (d->mat_type[m2] == RSB_MAT_VOLUME_EMITTER) {                  /* homogeneous.pyx:66-91, uniform.pyx:129-131 */
+                const double* w2p = d->prim_to_local + 12 * (size_t)inside[k];
+                v3 ls = xpoint(w2p, start), le = xpoint(w2p, ray.o);
+                double len = len3(V(ls.x - le.x, ls.y - le.y, ls.z - le.z));   /* end.vector_to(start).get_length() */
+                if (len == 0) continue;
+                const double* em = T->sp->tables + (size_t)m2 * bins;
+                for (int i = 0; i < bins; ++i) {
+                    double e = 0.0 + em[i] * T->sp->scale[m2];
+                    spectrum[i] += e * len;
+                }
+                continue;
+            }
             if (d->mat_type[m2] != RSB_MAT_DIELECTRIC) continue;
             double length = len3(V(ray.o.x - start.x, ray.o.y - start.y, ray.o.z - start.z));
             const double* tt = T->sp->tables + (size_t)m2 * bins;

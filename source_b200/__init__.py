@@ -14,7 +14,7 @@ from .math3d import (AffineMatrix3D, BoundingBox3D, BoundingSphere3D, Normal3D, 
                      rotate_y, rotate_z, translate)
 from .spectral import ConstantSF, InterpolatedSF, NumericallyIntegratedSF, Sellmeier, SpectralFunction
 from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Material, UniformSurfaceEmitter,
-                       UnitySurfaceEmitter, schott)
+                       UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter, schott)
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Primitive, Ray, Sphere,
                          Subtract, Union, World)
 from .observer import FullFrameSampler2D, Observer, PinholeCamera, SpectralPowerPipeline2D, SpectralSlice, StatsArray3D

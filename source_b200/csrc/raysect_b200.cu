@@ -570,6 +570,7 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->philox_idx = c.take<uint32_t>(P);
     st->jit_mti = c.take<int32_t>(P);
     st->work = c.take<int32_t>(P);
+    st->additive = c.take<int32_t>(P);
     st->ended = c.take<int32_t>(2 * P);
     st->n_ended = c.take<unsigned int>(2);
     st->hit_list = c.take<int32_t>(4 * P);
@@ -803,6 +804,8 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.seed = rng->seed;
     a.seed_stride = seed_stride;
     a.n_passes = n_passes;
+    for (int i = 0; i < ds->n_materials; ++i)
+        if (ds->mat_type[i] == RSB_MAT_VOLUME_EMITTER) a.has_additive = 1;
     a.n_pix_pass = n_pixels;
     a.pixels = pixels_dev;
     a.frame_elems = (long long)camera->nx * camera->ny * config->bins;

@@ -492,6 +492,7 @@ struct WfSlots {
     uint32_t* philox_idx;   // [P] draws so far (Philox) / cursor of the pixel's path stream (MT19937-64)
     int32_t* jit_mti;       // [P] cursor of the pixel's jitter stream (MT19937-64)
     int32_t* work;          // [P] index (within the current pixel chunk) of the pixel the slot is rendering
+    int32_t* additive;      // [P] the path in flight has logged an emitting volume (only touched when has_additive)
     int32_t* pix_mti;       // [n_chunk][2] MT19937-64 cursors of every pixel of the chunk: path stream, jitter stream
     unsigned long long* pix_mt;   // [n_chunk][2][312] their state words (seeded up front by k_wf_seed)
     LogEntry* log;          // [P][log_capacity]
@@ -518,6 +519,7 @@ struct WfArgs {
     long long frame_elems;      // nx * ny * bins
     unsigned long long seed_stride;   // pass p draws from streams seeded seed + p * seed_stride + y * nx + x
     int32_t n_passes;
+    int32_t has_additive;       // the scene has volume emitters: dark path ends may still have to be replayed
     unsigned long long* ray_count;
     unsigned long long* work_counter;
     unsigned int* n_idle;
@@ -681,6 +683,7 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     a.st.depth[slot] = 0;
     a.st.rays[slot] = 1;
     a.st.log_n[slot] = 0;
+    if (a.has_additive) a.st.additive[slot] = 0;
     a.st.status[slot] = SLOT_ALIVE;
     // roulette of the primary segment (see k_wf_trace); with the usual extinction_min_depth > 0 there is no draw
     double normalisation = 1.0;
@@ -803,7 +806,7 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
             a.st.status[slot] = SLOT_HIT;
             list = a.sp.mats[sc.prims[rec.prim].material].type;     // 0..3: per-material hit lists
-            if (list == MAT_CONDUCTOR) list = MAT_DIELECTRIC;        // the specular family shares one list
+            if (list >= MAT_CONDUCTOR) list = MAT_DIELECTRIC;        // conductors and null surfaces share the specular list
         } else {
             a.st.status[slot] = SLOT_ENDED_ZERO;
             list = 4;                                                // ended list
@@ -854,14 +857,18 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         log.capacity = a.log_capacity;
         log.n = a.st.log_n[slot];
         log.overflow = 0;
+        log.additive = 0;
         int r = path_shade<MAT, FEAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
+        if (log.additive) a.st.additive[slot] = 1;
         if (r == PATH_CONTINUE) {
             // the daughter's Russian roulette, played here so that k_wf_trace needs no RNG state: it is the next
-            // draw of the stream in the reference too (spawn_daughter -> daughter.trace -> roulette, ray.pyx:380-388)
+            // draw of the stream in the reference too (spawn_daughter -> daughter.trace -> roulette, ray.pyx:380-388);
+            // a daughter spawned by a NullSurface is traced with keep_alive=True: no roulette (material.pyx:147)
             double normalisation;
-            if (!path_roulette(a.cfg, ps.depth, rng, &normalisation)) normalisation = 0.0;
+            if (ps.keep_alive) normalisation = 1.0;
+            else if (!path_roulette(a.cfg, ps.depth, rng, &normalisation)) normalisation = 0.0;
             wf_store_rng<RNGMODE>(a, slot, rng);
             a.st.norm[slot] = normalisation;
             a.st.ray[0 * P + slot] = ps.o.x; a.st.ray[1 * P + slot] = ps.o.y; a.st.ray[2 * P + slot] = ps.o.z;
@@ -952,7 +959,8 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         double* m = (pass ? a.pass_mean + (size_t)(pass - 1) * a.frame_elems : a.mean) + row;
         double* v = (pass ? a.pass_variance + (size_t)(pass - 1) * a.frame_elems : a.variance) + row;
         const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
-        const bool emit = status == SLOT_ENDED_EMIT;
+        // (with emitting volumes in the scene a path that ended dark may still carry what they added on the way)
+        const bool emit = status == SLOT_ENDED_EMIT || (a.has_additive && a.st.additive[slot] != 0);
         for (int b0 = 0; b0 < bins; b0 += 64) {
             // two bins per lane per pass; the statistics rows are fetched before the replay so that their
             // latency overlaps it

@@ -51,6 +51,8 @@ enum LogOp : int32_t {
     LOG_MULA = 1,   // s *= table[i]               Spectrum.mul_array (spectrum.pyx:491)
     LOG_POWA = 2,   // s *= pow(table[i], v)       Dielectric.evaluate_volume (dielectric.pyx:313-330)
     LOG_EMIT = 3,   // s  = table[i] * v           UniformSurfaceEmitter.evaluate_surface (uniform.pyx:67-81)
+    LOG_ADDA = 5,   // s += (0 + table[i] * scale) * v   HomogeneousVolumeEmitter.evaluate_volume (homogeneous.pyx:78-91) with
+                    //                              UniformVolumeEmitter.emission_function (uniform.pyx:129-131); v = length
     LOG_FRESNEL = 4,   // s *= fresnel(v, n[i], k[i])  Conductor.evaluate_surface (conductor.pyx:122-128); n = table,
                        //                              k = the row in bits 8.. of the op word
 };
@@ -67,7 +69,9 @@ struct PathLog {
     int32_t n;
     int32_t capacity;
     int32_t overflow;
+    int32_t additive;   // a LOG_ADDA entry was pushed: the path's spectrum is not identically zero even if it ends dark
     RSB_HD void push(int op, int table, double v) {
+        if (op == LOG_ADDA) additive = 1;
         if (n < capacity) {
             LogEntry e; e.op = op; e.table = table; e.v = v;
             base[(size_t)n * stride] = e;
@@ -169,10 +173,20 @@ RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, c
     for (int i = count - 1; i >= 0; --i) {
         int id = sc.world.items[offset + i];
         const Material& m = sp.mats[sc.prims[id].material];
-        if (m.type != MAT_DIELECTRIC) continue;   // Lambert/emitter/absorber: evaluate_volume is the identity
+        if (m.type != MAT_DIELECTRIC && m.type != MAT_VOLUME_EMITTER) continue;   // the others: evaluate_volume is the identity
         stats.prim_test();
         if (!prim_contains<FEAT>(sc, id, origin, stack, stats)) continue;
         stats.table_read();
+        if (m.type == MAT_VOLUME_EMITTER) {
+            // HomogeneousVolumeEmitter.evaluate_volume (homogeneous.pyx:66-91): the integration length is measured in
+            // the CONTAINING primitive's local space, end -> start; a zero length contributes nothing
+            const double* w2p = sc.prims[id].to_local;
+            V3 s = xform_point(w2p, w_hit), e = xform_point(w2p, origin);
+            double len = length(v3(s.x - e.x, s.y - e.y, s.z - e.z));
+            if (len == 0) continue;
+            log.push(LOG_ADDA, m.table, len);
+            continue;
+        }
         // length = start_point.vector_to(end_point).get_length()
         V3 v = v3(origin.x - w_hit.x, origin.y - w_hit.y, origin.z - w_hit.z);
         log.push(LOG_POWA, m.table, length(v));
@@ -185,6 +199,7 @@ struct PathState {
     V3 o, d;            // world-space ray of the current segment
     int32_t depth;
     uint32_t rays;      // the reference's ray counter for this primary ray (1 + daughters spawned)
+    int32_t keep_alive; // the segment was spawned by a NullSurface: trace(world, keep_alive=True), no roulette (material.pyx:147)
 };
 
 RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
@@ -192,7 +207,9 @@ RSB_HD void path_begin(PathState& ps, PathLog& log, const V3& o, const V3& d) {
     ps.d = d;
     ps.depth = 0;
     ps.rays = 1;
+    ps.keep_alive = 0;
     log.n = 0;
+    log.additive = 0;
 }
 
 // One segment of the Ray.trace recursion (raysect/optical/ray.pyx:338-401) in two stages, which the
@@ -217,7 +234,8 @@ RSB_HD bool path_roulette(const RayConfig& cfg, int depth, Rng& rng, double* nor
 template <int FEAT = RSB_FEAT_ALL, int S = 1, class Stats>
 RSB_HD int path_trace(const Scene& sc, const RayConfig& cfg, const PathState& ps, Rng& rng, KdStackEntry* stack,
                       HitRec* rec, double* normalisation, Stats& stats, double* axbuf = nullptr) {
-    if (!path_roulette(cfg, ps.depth, rng, normalisation)) return PATH_ZERO;
+    if (ps.keep_alive) *normalisation = 1.0;     // ray.pyx:382: "if keep_alive or self.depth < self._extinction_min_depth"
+    else if (!path_roulette(cfg, ps.depth, rng, normalisation)) return PATH_ZERO;
     // -- closest hit (ray.pyx:391-393)
     if (S == 1) {
         if (!world_hit<FEAT>(sc, ps.o, ps.d, cfg.max_distance, stack, rec, stats)) return PATH_ZERO;
@@ -235,6 +253,7 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
                       double normalisation, Rng& rng, KdStackEntry* stack, PathLog& log, Stats& stats) {
     const V3 o = ps.o, d = ps.d;
     const int depth = ps.depth;
+    ps.keep_alive = 0;
     {
         Isect is;
         world_hit_geometry<FEAT>(sc, o, d, rec, &is);
@@ -310,6 +329,14 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
             log.push(LOG_MULS, 0, pdf_cos);
             log.push(LOG_MULA, mat.table, 0.0);
             stats.table_read();
+        } else if (mat.type == MAT_VOLUME_EMITTER) {
+            // NullSurface.evaluate_surface (material.pyx:126-147): the ray carries on through the surface in the same
+            // direction; the transit is not counted in the depth and the daughter cannot be extinguished
+            next_o = is.exiting ? xform_point(p2w, is.outside) : xform_point(p2w, is.inside);
+            ps.o = next_o;
+            ps.rays += 1;
+            ps.keep_alive = 1;
+            return PATH_CONTINUE;
         } else if (mat.type == MAT_CONDUCTOR) {
             // Conductor.evaluate_surface (conductor.pyx:75-130): mirror reflection, no random draws; the per-bin
             // Fresnel reflectance of the complex index n + ik is applied on the way back up
@@ -392,6 +419,8 @@ RSB_HD int trace_path(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
     int r;
     do { r = path_step(sc, sp, cfg, ps, rng, stack, log, stats); } while (r == PATH_CONTINUE);
     *ray_count = ps.rays;
+    // a path that ends dark still carries what emitting volumes added along the way: it must be replayed
+    if (r == PATH_ZERO && log.additive) r = PATH_EMITTED;
     return r;
 }
 
@@ -437,6 +466,7 @@ RSB_HD double apply_entry(double s, int op, int table, double v, const Spectral&
     double t = sp.tables[(size_t)table * sp.bins + bin];
     if ((op & 0xff) == LOG_FRESNEL) return s * conductor_fresnel(v, t, sp.tables[(size_t)(op >> 8) * sp.bins + bin]);
     if (op == LOG_MULA) return s * t;
+    if (op == LOG_ADDA) return s + (0.0 + t * sp.mats[table].scale) * v;
     if (op == LOG_POWA) {
 #ifdef __CUDA_ARCH__
         // Dielectric.evaluate_volume's pow(transmission, length) (dielectric.pyx:326) as exp(length * ln T) with ln T

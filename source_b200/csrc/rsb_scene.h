@@ -30,6 +30,7 @@ enum MatType : int32_t {
     MAT_LAMBERT = 2,    // raysect/optical/material/lambert.pyx:77-105
     MAT_DIELECTRIC = 3, // raysect/optical/material/dielectric.pyx:153-330
     MAT_CONDUCTOR = 4,  // raysect/optical/material/conductor.pyx:75-147 (shaded with the dielectric family)
+    MAT_VOLUME_EMITTER = 5,   // emitter/homogeneous.pyx:40-93 with uniform.pyx:91-133 / unity.pyx:79-99 (same family)
 };
 
 // 16-byte kd-tree node.  Branch: split, upper child id, axis 0..2 (lower child is id+1).

@@ -28,6 +28,8 @@ _MATERIALS = {
     "AbsorbingSurface": cabi.MAT_ABSORBER, "UniformSurfaceEmitter": cabi.MAT_EMITTER,
     "UnitySurfaceEmitter": cabi.MAT_EMITTER,     # emitter/unity.pyx:65-76: every bin 1.0 = a constant table, scale 1
     "Lambert": cabi.MAT_LAMBERT, "Dielectric": cabi.MAT_DIELECTRIC,
+    # HomogeneousVolumeEmitter subclasses with a direction-independent emission_function (homogeneous.pyx:40-93)
+    "UniformVolumeEmitter": cabi.MAT_VOLUME_EMITTER, "UnityVolumeEmitter": cabi.MAT_VOLUME_EMITTER,
     "Conductor": cabi.MAT_CONDUCTOR,             # conductor.pyx:39-147 (RoughConductor is a different class: unsupported)
 }
 
@@ -112,9 +114,9 @@ class FlatScene:
         for i, (m, t) in enumerate(zip(self.materials, self.mat_type)):
             if t == cabi.MAT_LAMBERT:
                 tables[i] = np.asarray(lambert_reflectivity(m).sample(min_wavelength, max_wavelength, bins))
-            elif t == cabi.MAT_EMITTER and not hasattr(m, "emission_spectrum"):
-                tables[i] = 1.0     # UnitySurfaceEmitter (emitter/unity.pyx:73-75): samples[:] = 1.0; 1.0 * 1.0 is exact
-            elif t == cabi.MAT_EMITTER:
+            elif t in (cabi.MAT_EMITTER, cabi.MAT_VOLUME_EMITTER) and not hasattr(m, "emission_spectrum"):
+                tables[i] = 1.0     # Unity{Surface,Volume}Emitter (emitter/unity.pyx:73-75, 98): samples[:] = 1.0; 1.0 * 1.0 is exact
+            elif t in (cabi.MAT_EMITTER, cabi.MAT_VOLUME_EMITTER):
                 tables[i] = np.asarray(m.emission_spectrum.sample(min_wavelength, max_wavelength, bins))
                 scale[i] = m.scale
             elif t == cabi.MAT_DIELECTRIC:

@@ -61,6 +61,25 @@ class Conductor(Material):
         self.extinction = extinction
 
 
+class UniformVolumeEmitter(Material):
+    """emitter/uniform.pyx:91-133 on emitter/homogeneous.pyx:40-93: transparent surface, emission_spectrum * scale
+    (W/m^3/str/nm) integrated along the path inside the primitive; importance 1 (homogeneous.pyx:48)"""
+
+    def __init__(self, emission_spectrum, scale=1.0):
+        super().__init__()
+        self.emission_spectrum = emission_spectrum
+        self.scale = float(scale)
+        self.importance = 1.0
+
+
+class UnityVolumeEmitter(Material):
+    """emitter/unity.pyx:79-99: 1 W/m^3/str/nm in every bin"""
+
+    def __init__(self):
+        super().__init__()
+        self.importance = 1.0
+
+
 class UnitySurfaceEmitter(Material):
     """emitter/unity.pyx:37-76: 1 W/m^2/str/nm in every bin, whatever the direction (importance stays 0)"""
 

@@ -86,7 +86,19 @@ def metal_goldens():
     save("metal_16x16_s3_b8_r4_noimp", **r)
 
 
+def volume_goldens():
+    """UniformVolumeEmitter / UnityVolumeEmitter: NullSurface transits (keep_alive, depth not counted) + emission * length"""
+    world = scenes.volume_scene(api, fog=True)
+    cam, r = render(world, dict(pixels=(24, 20), samples=4, bins=10, path_weight=0.3), 31)
+    save("volume_fog_24x20_s4_b10", **r)
+    world = scenes.volume_scene(api, fog=False)
+    cam, r = render(world, dict(pixels=(16, 16), samples=3, bins=8, spectral_rays=2, min_depth=1, extinction=0.3, max_depth=4), 32)
+    save("volume_16x16_s3_b8_r2_shallow", **r)
+
+
 def main():
+    if "--volume-only" in sys.argv:
+        return volume_goldens()
     if "--metal-only" in sys.argv:
         return metal_goldens()
     if "--passes-only" in sys.argv:
@@ -148,6 +160,7 @@ def main():
     passes_goldens()
     edge_goldens()
     metal_goldens()
+    volume_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

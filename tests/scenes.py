@@ -76,6 +76,23 @@ def metal_scene(api):
     return world
 
 
+def volume_scene(api, fog=True):
+    """Cornell box with emitting volumes (HomogeneousVolumeEmitter on a NullSurface): a glowing sphere overlapped by
+    a glass sphere, a unity-emission cylinder, and (fog) a faint emitting box that contains the whole room AND the
+    camera, so that every segment of every path integrates emission and paths that end dark still carry light."""
+    a = api
+    glow = a.UniformVolumeEmitter(a.InterpolatedSF(*CB_LIGHT), 0.8)
+
+    def extra(a, w):
+        a.Sphere(0.3, parent=w, transform=a.translate(-0.4, -0.5, -0.2), material=glow)
+        a.Sphere(0.25, parent=w, transform=a.translate(-0.15, -0.6, -0.35), material=a.schott("N-BK7"))
+        a.Cylinder(0.15, 0.7, parent=w, transform=a.translate(0.45, -0.2, 0.1) * a.rotate(20, 70, 0), material=a.UnityVolumeEmitter())
+        if fog:
+            a.Box(a.Point3D(-1.5, -1.5, -4.0), a.Point3D(1.5, 1.5, 1.5), parent=w,
+                  material=a.UniformVolumeEmitter(a.ConstantSF(1.0), 0.01))
+    return cornell_box(a, glass=False, extra=extra)
+
+
 def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_rays=1, min_depth=3, max_depth=500,
                    extinction=0.01, path_weight=0.25, importance=True):
     """Camera of demos/cornell_box.py:147-156 with a SpectralPowerPipeline2D and a full-frame sampler."""

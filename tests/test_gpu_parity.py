@@ -97,6 +97,11 @@ def test_conductor_and_unity_emitter(make_backend):
     print("divergent pixel fractions:", fr)
 
 
+def test_volume_emitters(make_backend):
+    fr = parity.volumes(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+    print("divergent pixel fractions:", fr)
+
+
 def test_prism_csg_dispersion(make_backend):
     fr = parity.prism(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
     print("divergent pixel fraction:", fr)

@@ -50,6 +50,10 @@ def test_conductor_and_unity_emitter_bit_exact(make_backend):
     parity.metal(make_backend, exact=True)
 
 
+def test_volume_emitters_bit_exact(make_backend):
+    parity.volumes(make_backend, exact=True)
+
+
 def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 

@@ -121,6 +121,22 @@ def test_render_engine_on_real_conductor_and_unity_emitter_objects(api, referenc
     assert m_ref.sum() > 0
 
 
+def test_render_engine_on_real_volume_emitter_objects(api, reference):
+    """raysect UniformVolumeEmitter / UnityVolumeEmitter objects (NullSurface + homogeneous emission) from a live scenegraph"""
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(10, 10), samples=3, bins=5)
+    world = scenes.volume_scene(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 99)
+    world2 = scenes.volume_scene(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
+    cam2.render_engine = CudaRenderEngine(seed=99, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert np.all(m_ref > 0)       # the fog box contains the camera: every pixel sees emission
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import RGBPipeline2D
     from source_b200.plugin import CudaRenderEngine
