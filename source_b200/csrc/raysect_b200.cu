@@ -864,7 +864,10 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         RSB_CUDA(cudaMemsetAsync(a.st.n_ended, 0, 2 * sizeof(unsigned int), st));
         RSB_CUDA(cudaMemsetAsync(a.st.n_hit, 0, 4 * sizeof(unsigned int), st));
         // kernels are instantiated for "analytic primitives only" and for "everything" (meshes and CSG)
-        const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
+        // conductors and volume emitters are compiled into the full-featured instantiation only (RSB_FEAT_RARE_MATERIALS)
+        bool rare = false;
+        for (int i = 0; i < ds->n_materials; ++i) rare = rare || ds->mat_type[i] >= RSB_MAT_CONDUCTOR;
+        const int feat = (ds->has_csg || rare) ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
 #define RSB_RUN_MT(C, F) rc = run_wavefront<RNG_MT19937_64, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
 #define RSB_RUN_PX(C, F) rc = run_wavefront<RNG_PHILOX, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
         if (mt) RSB_DISPATCH_FEAT(count != 0, feat, a.staged, RSB_RUN_MT);

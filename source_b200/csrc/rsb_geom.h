@@ -944,6 +944,10 @@ RSB_HD_NOINLINE void csg_geometry(const Scene& sc, int top, const CsgEvent& ev, 
 #define RSB_FEAT_MESH 1
 #define RSB_FEAT_CSG 2
 #define RSB_FEAT_ALL 3
+// Conductor and the volume emitters ride in the full-featured instantiation (the one that also carries the CSG
+// evaluator): scenes that use them are dispatched to RSB_FEAT_ALL, and the lean analytic-only / mesh-only kernels
+// do not pay their registers (measured: 3 % of the Cornell bench when compiled in unconditionally).
+#define RSB_FEAT_RARE_MATERIALS RSB_FEAT_CSG
 #define RSB_FEAT_STAGED 4   // kernels only: world tree, item list and primitive table are in shared memory
 
 template <class Stats, int FEAT = RSB_FEAT_ALL, int S = 1>

@@ -861,13 +861,13 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         int r = path_shade<MAT, FEAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
-        if (log.additive) a.st.additive[slot] = 1;
+        if ((FEAT & RSB_FEAT_RARE_MATERIALS) && log.additive) a.st.additive[slot] = 1;
         if (r == PATH_CONTINUE) {
             // the daughter's Russian roulette, played here so that k_wf_trace needs no RNG state: it is the next
             // draw of the stream in the reference too (spawn_daughter -> daughter.trace -> roulette, ray.pyx:380-388);
             // a daughter spawned by a NullSurface is traced with keep_alive=True: no roulette (material.pyx:147)
             double normalisation;
-            if (ps.keep_alive) normalisation = 1.0;
+            if ((FEAT & RSB_FEAT_RARE_MATERIALS) && ps.keep_alive) normalisation = 1.0;
             else if (!path_roulette(a.cfg, ps.depth, rng, &normalisation)) normalisation = 0.0;
             wf_store_rng<RNGMODE>(a, slot, rng);
             a.st.norm[slot] = normalisation;

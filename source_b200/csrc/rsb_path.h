@@ -173,11 +173,13 @@ RSB_HD void log_volumes(const Scene& sc, const Spectral& sp, const V3& origin, c
     for (int i = count - 1; i >= 0; --i) {
         int id = sc.world.items[offset + i];
         const Material& m = sp.mats[sc.prims[id].material];
-        if (m.type != MAT_DIELECTRIC && m.type != MAT_VOLUME_EMITTER) continue;   // the others: evaluate_volume is the identity
+        // (conductors, volume emitters: only in the full-featured instantiation, see RSB_FEAT_RARE_MATERIALS)
+        const bool emitter = (FEAT & RSB_FEAT_RARE_MATERIALS) && m.type == MAT_VOLUME_EMITTER;
+        if (m.type != MAT_DIELECTRIC && !emitter) continue;   // the others: evaluate_volume is the identity
         stats.prim_test();
         if (!prim_contains<FEAT>(sc, id, origin, stack, stats)) continue;
         stats.table_read();
-        if (m.type == MAT_VOLUME_EMITTER) {
+        if (emitter) {
             // HomogeneousVolumeEmitter.evaluate_volume (homogeneous.pyx:66-91): the integration length is measured in
             // the CONTAINING primitive's local space, end -> start; a zero length contributes nothing
             const double* w2p = sc.prims[id].to_local;
@@ -329,7 +331,7 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
             log.push(LOG_MULS, 0, pdf_cos);
             log.push(LOG_MULA, mat.table, 0.0);
             stats.table_read();
-        } else if (mat.type == MAT_VOLUME_EMITTER) {
+        } else if ((FEAT & RSB_FEAT_RARE_MATERIALS) && mat.type == MAT_VOLUME_EMITTER) {
             // NullSurface.evaluate_surface (material.pyx:126-147): the ray carries on through the surface in the same
             // direction; the transit is not counted in the depth and the daughter cannot be extinguished
             next_o = is.exiting ? xform_point(p2w, is.outside) : xform_point(p2w, is.inside);
@@ -337,7 +339,7 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
             ps.rays += 1;
             ps.keep_alive = 1;
             return PATH_CONTINUE;
-        } else if (mat.type == MAT_CONDUCTOR) {
+        } else if ((FEAT & RSB_FEAT_RARE_MATERIALS) && mat.type == MAT_CONDUCTOR) {
             // Conductor.evaluate_surface (conductor.pyx:75-130): mirror reflection, no random draws; the per-bin
             // Fresnel reflectance of the complex index n + ik is applied on the way back up
             V3 incident = normalise(xform_vector(w2p, d));
