@@ -61,3 +61,61 @@ def test_reduce_assembles_frame_bit_exactly_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def _render_worker(rank, world_size, port, q):
+    """each rank renders ITS tiles of a Cornell frame (host build of the device code, 2 accumulated passes) into an
+    otherwise-zero frame; rank 0 checks the reduced frame against the single-process render of the whole frame"""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [os.path.dirname(here), here]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        import hostsim_api
+        import scenes
+        import source_b200 as api
+        from source_b200 import _cabi as cabi
+        from source_b200.engine import camera_desc, ray_config
+        from source_b200.flatten import flatten_world
+        nx, ny, bins, spp, passes, seed = 24, 20, 4, 2, 2, 77
+        flat = flatten_world(scenes.cornell_box(api))
+        be = hostsim_api.HostScene(flat)
+        cam = camera_desc(nx, ny, spp, 45.0, 1.0, api.translate(0, 0, -3.3))
+        cfg = ray_config(bins, 375.0, 740.0, 0.01, 3, 500, True, 0.25)
+        sp = flat.spectral(375.0, 740.0, bins)
+        px = tile_pixels(nx, ny, 8, rank, world_size)
+        m, v, rays = be.render(cam, cfg, sp, cabi.RNG_MT19937_64, seed, px, passes=passes, seed_stride=nx * ny)
+        stats = torch.from_numpy(np.stack([m, v]))
+        out = torch.zeros_like(stats)
+        frame = reduce_frame(stats, out, rank, world_size)
+        total = torch.tensor([rays], dtype=torch.int64)
+        dist.all_reduce(total)
+        if rank == 0:
+            m1, v1, rays1 = be.render(cam, cfg, sp, cabi.RNG_MT19937_64, seed, None, passes=passes, seed_stride=nx * ny)
+            q.put(bool(np.array_equal(frame[0].numpy(), m1) and np.array_equal(frame[1].numpy(), v1)
+                       and int(total.item()) == rays1 and m1.sum() > 0))
+        be.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tile_partitioned_render_equals_single_process_render_world_size_2(lib):
+    """pixel streams are keyed on (pass, pixel): the frame must not depend on how tiles are dealt to ranks"""
+    import hostsim_api
+    hostsim_api.build()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_render_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok
