@@ -101,11 +101,15 @@ typedef struct RsbSceneDesc {
     const double* imp_weight;       /* [n_important] */
 } RsbSceneDesc;
 
-/* PinholeCamera state after _update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-167) */
+/* PinholeCamera state after _update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-167), or
+ * OrthographicCamera state (imaging/orthographic.pyx:132-137): image_delta = width / nx, rays leave the pixel's
+ * jittered position on the z = 0 plane along +z with projection weight 1 (orthographic.pyx:139-167). */
+#define RSB_CAMERA_PINHOLE 0
+#define RSB_CAMERA_ORTHOGRAPHIC 1
 typedef struct RsbCamera {
     int32_t nx, ny;
     int32_t pixel_samples;
-    int32_t pad;
+    int32_t kind;
     double image_delta, image_start_x, image_start_y;
     double sensitivity;
     double to_root[12];

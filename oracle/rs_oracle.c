@@ -1040,6 +1040,12 @@ int ro_render(const RsbSceneDesc* d, const RsbCamera* cam, const RsbRayConfig* c
             v3 dir = norm3(V(jx + pixel_x, jy + pixel_y, 0.0 + 1.0));
             ray_t r;
             r.o = xpoint(cam->to_root, V(0, 0, 0)); r.d = xvec(cam->to_root, dir); r.maxd = cfg->max_distance;
+            if (cam->kind == RSB_CAMERA_ORTHOGRAPHIC) {                     /* orthographic.pyx:139-167 */
+                const double p2l[12] = {1, 0, 0, pixel_x, 0, 1, 0, pixel_y, 0, 0, 1, 0};   /* translate(pixel_x, pixel_y, 0) */
+                dir = V(0, 0, 1);                                           /* dir.z = 1: projection weight 1 */
+                r.o = xpoint(cam->to_root, xpoint(p2l, V(jx, jy, 0)));
+                r.d = xvec(cam->to_root, dir);
+            }
             T.rays += 1;
             trace(&T, r, 0, spectrum);
             for (int i = 0; i < bins; ++i) {

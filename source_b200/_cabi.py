@@ -17,6 +17,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3, 4
 
 PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INTERSECT, PRIM_SUBTRACT = range(8)
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER = range(6)
+CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC = 0, 1
 RNG_MT19937_64, RNG_PHILOX = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -85,7 +86,7 @@ class RsbCamera(C.Structure):
         ("nx", C.c_int32),
         ("ny", C.c_int32),
         ("pixel_samples", C.c_int32),
-        ("pad", C.c_int32),
+        ("kind", C.c_int32),
         ("image_delta", C.c_double),
         ("image_start_x", C.c_double),
         ("image_start_y", C.c_double),

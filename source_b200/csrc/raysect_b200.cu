@@ -701,6 +701,8 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     if (!c || !ds || !camera || !config || !spectral || !rng || !mean_dev || !variance_dev || !ray_count_dev)
         return fail(RSB_ERR_ARG, "rsb_render: null argument");
     if (camera->nx < 1 || camera->ny < 1 || camera->pixel_samples < 1) return fail(RSB_ERR_ARG, "rsb_render: bad camera");
+    if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC)
+        return fail(RSB_ERR_UNSUPPORTED, "rsb_render: unknown camera kind");
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");
     if (spectral->n_materials != ds->n_materials) return fail(RSB_ERR_ARG, "rsb_render: spectral tables do not match the scene's materials");
@@ -788,6 +790,7 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.cam.nx = camera->nx;
     a.cam.ny = camera->ny;
     a.cam.pixel_samples = camera->pixel_samples;
+    a.cam.kind = camera->kind;
     a.cam.image_delta = camera->image_delta;
     a.cam.image_start_x = camera->image_start_x;
     a.cam.image_start_y = camera->image_start_y;

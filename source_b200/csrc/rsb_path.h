@@ -37,10 +37,10 @@ struct Spectral {    // per spectral slice: what SpectralFunction.sample()/avera
     int32_t n_tables;
 };
 
-struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207
+struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1)
     int32_t nx, ny;
     int32_t pixel_samples;
-    int32_t pad;
+    int32_t kind;
     double image_delta, image_start_x, image_start_y;
     double sensitivity;
     double to_root[12];
@@ -534,6 +534,17 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
     double half = 0.5 * cam.image_delta;
     double jy = u1 * cam.image_delta - half;
     double jx = u2 * cam.image_delta - half;
+    if (cam.kind == 1) {
+        // OrthographicCamera._generate_rays (orthographic.pyx:139-167): the sample point is moved to the pixel with
+        // Point3D.transform(translate(pixel_x, pixel_y, 0)) and the ray leaves it along +z; "non-physical camera
+        // samples radiance directly": projection weight 1
+        const double pixel_to_local[12] = {1.0, 0.0, 0.0, pixel_x, 0.0, 1.0, 0.0, pixel_y, 0.0, 0.0, 1.0, 0.0};
+        V3 origin = xform_point(pixel_to_local, v3(jx, jy, 0.0));
+        *weight = 1.0;
+        *o = xform_point(cam.to_root, origin);
+        *d = xform_vector(cam.to_root, v3(0.0, 0.0, 1.0));
+        return;
+    }
     V3 dir = normalise(v3(jx + pixel_x, jy + pixel_y, 0.0 + 1.0));
     *weight = dir.z;
     *o = xform_point(cam.to_root, v3(0, 0, 0));

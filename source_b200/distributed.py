@@ -59,7 +59,7 @@ class FrameRenderer:
         if self.passes < 1 or camera.pixel_samples % self.passes:
             raise ValueError("pixel_samples must be a multiple of the number of passes")
         self.dev = torch.device("cuda", accel.device.index)
-        self.cam = camera_desc(nx, ny, camera.pixel_samples // self.passes, camera.fov, camera.sensitivity, camera.to_root())
+        self.cam = camera._camera_desc(camera.pixel_samples // self.passes)
         self.cfg = ray_config(self.bins, camera.min_wavelength, camera.max_wavelength, camera.ray_extinction_prob,
                               camera.ray_extinction_min_depth, camera.ray_max_depth, camera.ray_importance_sampling,
                               camera.ray_important_path_weight)

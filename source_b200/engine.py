@@ -197,14 +197,22 @@ class Accelerator:
         return mean, variance, rays.value
 
 
-def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root):
-    """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160)"""
-    max_pixels = max(nx, ny)
-    if max_pixels <= 1:
-        raise RuntimeError("Number of Pinhole camera Pixels must be > 1.")
-    image_max_width = 2 * math.tan(math.pi / 180 * 0.5 * fov)
-    image_delta = image_max_width / max_pixels
+def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None):
+    """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160), or, with
+    ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137)"""
     cam = cabi.RsbCamera()
+    if width is not None:
+        if width <= 0:
+            raise ValueError("width can not be less than or equal to 0 meters.")
+        image_delta = width / nx
+        cam.kind = cabi.CAMERA_ORTHOGRAPHIC
+    else:
+        max_pixels = max(nx, ny)
+        if max_pixels <= 1:
+            raise RuntimeError("Number of Pinhole camera Pixels must be > 1.")
+        image_max_width = 2 * math.tan(math.pi / 180 * 0.5 * fov)
+        image_delta = image_max_width / max_pixels
+        cam.kind = cabi.CAMERA_PINHOLE
     cam.nx, cam.ny, cam.pixel_samples = int(nx), int(ny), int(pixel_samples)
     cam.image_delta = image_delta
     cam.image_start_x = 0.5 * nx * image_delta

@@ -252,6 +252,11 @@ class PinholeCamera(Observer):
             raise ValueError("The field-of-view angle must lie in the range (0, 180).")
         self._fov = value
 
+    def _camera_desc(self, pixel_samples):
+        """the RsbCamera of this observer for one render call (``pixel_samples`` samples per pixel)"""
+        nx, ny = self._pixels
+        return camera_desc(nx, ny, pixel_samples, self._fov, self.sensitivity, self.to_root())
+
     def _slice_spectrum(self):
         """observer.pyx:311-340"""
         if self.spectral_rays < 1 or self.spectral_rays > self.spectral_bins:
@@ -294,7 +299,7 @@ class PinholeCamera(Observer):
             return
         accel = world.build_accelerator()
         nx, ny = self._pixels
-        cam = camera_desc(nx, ny, self.pixel_samples, self._fov, self.sensitivity, self.to_root())
+        cam = self._camera_desc(self.pixel_samples)
         self.ray_count = 0
         for slice_id, s in enumerate(slices):
             cfg = ray_config(s.bins, s.min_wavelength, s.max_wavelength, self.ray_extinction_prob,
@@ -312,3 +317,28 @@ class PinholeCamera(Observer):
         for p in self.pipelines:
             p.finalise()
         self.render_complete = True
+
+
+class OrthographicCamera(PinholeCamera):
+    """raysect/optical/observer/imaging/orthographic.pyx:37-170: parallel rays along the camera's +z axis from a
+    ``width`` metres wide image plane (height follows the pixel aspect ratio); samples radiance directly
+    (projection weight 1).  Everything else -- spectral slicing, pipelines, ray settings -- is Observer2D's."""
+
+    def __init__(self, pixels, width, sensitivity=None, frame_sampler=None, pipelines=None, parent=None, transform=None,
+                 name=None):
+        super().__init__(pixels, None, sensitivity, frame_sampler, pipelines, parent, transform, name)
+        self.width = width
+
+    @property
+    def width(self):
+        return self._width
+
+    @width.setter
+    def width(self, width):
+        if width <= 0:
+            raise ValueError("width can not be less than or equal to 0 meters.")
+        self._width = float(width)
+
+    def _camera_desc(self, pixel_samples):
+        nx, ny = self._pixels
+        return camera_desc(nx, ny, pixel_samples, None, self.sensitivity, self.to_root(), width=self._width)

@@ -104,7 +104,7 @@ class CudaRenderEngine(RenderEngine):
     Contract (workflow.py:78-91, observer.pyx:299-305): ``run(tasks, render, update, render_args=(slice_id,
     template_ray), update_args=(slice_id,))`` is called once per spectral slice; ``render`` is the bound
     ``observer._render_pixel``, so the observer, its world and its pipelines are reachable from it.
-    Supported: ``PinholeCamera`` observers feeding ``SpectralPowerPipeline2D`` pipelines (the spectral frame
+    Supported: ``PinholeCamera`` and ``OrthographicCamera`` observers feeding ``SpectralPowerPipeline2D`` pipelines (the spectral frame
     every other 2-D pipeline is a post-processing of), worlds built from Sphere/Box/Cylinder/Cone/CSG/Mesh
     with Lambert / UniformSurfaceEmitter / UnitySurfaceEmitter / Dielectric / Conductor / AbsorbingSurface /
     UniformVolumeEmitter / UnityVolumeEmitter materials.
@@ -159,11 +159,11 @@ class CudaRenderEngine(RenderEngine):
         return self._accel
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import PinholeCamera, SpectralPowerPipeline2D
+        from raysect.optical.observer import OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D
         observer = getattr(render, "__self__", None)
-        if not isinstance(observer, PinholeCamera):
-            raise NotImplementedError("CudaRenderEngine renders PinholeCamera observers; got %r (no CPU fallback)"
-                                      % type(observer).__name__)
+        if not isinstance(observer, (PinholeCamera, OrthographicCamera)):
+            raise NotImplementedError("CudaRenderEngine renders PinholeCamera and OrthographicCamera observers; got %r "
+                                      "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
             if not isinstance(p, SpectralPowerPipeline2D):
@@ -176,8 +176,12 @@ class CudaRenderEngine(RenderEngine):
         if observer.pixel_samples % self.passes:
             raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
                              % (observer.pixel_samples, self.passes))
-        cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, observer.fov, observer.sensitivity,
-                          observer.to_root())
+        if isinstance(observer, OrthographicCamera):
+            cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, None, observer.sensitivity,
+                              observer.to_root(), width=observer.width)
+        else:
+            cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, observer.fov, observer.sensitivity,
+                              observer.to_root())
         cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
                          template.extinction_min_depth, template.max_depth, template.importance_sampling,
                          template.important_path_weight, template.max_distance)

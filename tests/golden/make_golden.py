@@ -96,7 +96,17 @@ def volume_goldens():
     save("volume_16x16_s3_b8_r2_shallow", **r)
 
 
+def ortho_goldens():
+    """OrthographicCamera observer (parallel rays from the image plane, projection weight 1)"""
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.orthographic_camera(api, world, pixels=(20, 16), width=2.4, samples=3, bins=8, spectral_rays=2)
+    mean, var, n = harness.oracle_render(cam, pipe, 808)
+    save("ortho_20x16_s3_b8_r2", mean=mean, variance=var, samples=n)
+
+
 def main():
+    if "--ortho-only" in sys.argv:
+        return ortho_goldens()
     if "--volume-only" in sys.argv:
         return volume_goldens()
     if "--metal-only" in sys.argv:
@@ -161,6 +171,7 @@ def main():
     edge_goldens()
     metal_goldens()
     volume_goldens()
+    ortho_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

@@ -192,7 +192,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     cfg.important_path_weight = config->important_path_weight;
     cfg.max_distance = config->max_distance;
     Camera cam;
-    cam.nx = camera->nx; cam.ny = camera->ny; cam.pixel_samples = camera->pixel_samples;
+    cam.nx = camera->nx; cam.ny = camera->ny; cam.pixel_samples = camera->pixel_samples; cam.kind = camera->kind;
     cam.image_delta = camera->image_delta; cam.image_start_x = camera->image_start_x; cam.image_start_y = camera->image_start_y;
     cam.sensitivity = camera->sensitivity;
     memcpy(cam.to_root, camera->to_root, sizeof(cam.to_root));

@@ -112,6 +112,24 @@ def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_r
     return camera, pipeline
 
 
+def orthographic_camera(api, world, pixels=(20, 16), width=2.4, samples=3, bins=8, spectral_rays=1, transform=None):
+    """OrthographicCamera (imaging/orthographic.pyx) looking into the Cornell box: parallel rays, weight 1"""
+    a = api
+    pipeline = a.SpectralPowerPipeline2D()
+    camera = a.OrthographicCamera(pixels, width, parent=world, pipelines=[pipeline], frame_sampler=a.FullFrameSampler2D(),
+                                  transform=transform if transform is not None else a.translate(0.05, -0.1, -3.3) * a.rotate(4, -3, 2))
+    camera.spectral_rays = spectral_rays
+    camera.spectral_bins = bins
+    camera.pixel_samples = samples
+    camera.ray_importance_sampling = True
+    camera.ray_important_path_weight = 0.25
+    camera.ray_max_depth = 500
+    camera.ray_extinction_min_depth = 3
+    camera.ray_extinction_prob = 0.01
+    camera.quiet = True
+    return camera, pipeline
+
+
 def random_spheres(api, n, seed=7, uniform=None):
     """BASELINE config 5: n spheres, centres uniform in [-1,1]^3, radii uniform in [0.01,0.03]; the draws
     come from ``uniform`` (the reference RNG after seed(7) when generating goldens) or numpy."""

@@ -53,6 +53,10 @@ def test_volume_emitters_bit_exact(make_backend):
     parity.volumes(make_backend, exact=True)
 
 
+def test_orthographic_camera_bit_exact(make_backend):
+    parity.orthographic(make_backend, exact=True)
+
+
 def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 

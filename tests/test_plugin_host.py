@@ -137,6 +137,20 @@ def test_render_engine_on_real_volume_emitter_objects(api, reference):
     assert np.all(m_ref > 0)       # the fog box contains the camera: every pixel sees emission
 
 
+def test_render_engine_with_real_orthographic_camera(api, reference):
+    from source_b200.plugin import CudaRenderEngine
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.orthographic_camera(api, world, pixels=(10, 8), samples=2, bins=4)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 15)
+    world2 = scenes.cornell_box(api)
+    cam2, pipe2 = scenes.orthographic_camera(api, world2, pixels=(10, 8), samples=2, bins=4)
+    cam2.render_engine = CudaRenderEngine(seed=15, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert m_ref.sum() > 0
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import RGBPipeline2D
     from source_b200.plugin import CudaRenderEngine
