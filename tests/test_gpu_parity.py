@@ -54,7 +54,8 @@ def test_accumulated_passes_vs_reference(make_backend):
     print("divergent pixel fractions:", fr)
 
 
-def test_concurrent_passes_equal_sequential_passes_bit_for_bit(device, make_backend, monkeypatch):
+@pytest.mark.parametrize("rng", ["mt", "philox"])
+def test_concurrent_passes_equal_sequential_passes_bit_for_bit(device, make_backend, monkeypatch, rng):
     """Concurrent passes (one wavefront over (pass, pixel) streams, several chunks, a masked task list) must equal
     the same passes rendered one rsb_render call at a time and merged on the host with combine_samples -- exactly:
     both sides run the same device code, so no libm tolerance is involved."""
@@ -73,12 +74,13 @@ def test_concurrent_passes_equal_sequential_passes_bit_for_bit(device, make_back
     cfg = ray_config(bins, 375.0, 740.0, 0.01, 3, 500, True, 0.25)
     spectral = accel.flat.spectral(375.0, 740.0, bins)
     from source_b200 import _cabi as cabi
+    mode = cabi.RNG_MT19937_64 if rng == "mt" else cabi.RNG_PHILOX
     for pixels in (None, np.argwhere(np.random.default_rng(0).random((nx, ny)) < 0.4).astype(np.int32)):
-        m, v, rays = accel.render(cam, cfg, spectral, cabi.RNG_MT19937_64, seed, pixels, passes=passes, seed_stride=nx * ny)
+        m, v, rays = accel.render(cam, cfg, spectral, mode, seed, pixels, passes=passes, seed_stride=nx * ny)
         frame = StatsArray3D(nx, ny, bins)
         total = 0
         for p in range(passes):
-            mp, vp, rp = accel.render(cam, cfg, spectral, cabi.RNG_MT19937_64, seed + p * nx * ny, pixels)
+            mp, vp, rp = accel.render(cam, cfg, spectral, mode, seed + p * nx * ny, pixels)
             frame.combine_slice(pixels, 0, mp, vp, spp)
             total += rp
         assert rays == total
