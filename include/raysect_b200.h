@@ -46,6 +46,8 @@ extern "C" {
 #define RSB_MAT_LAMBERT 2
 #define RSB_MAT_DIELECTRIC 3
 #define RSB_MAT_CONDUCTOR 4 /* raysect/optical/material/conductor.pyx:39-147 (specular Fresnel conductor) */
+#define RSB_MAT_ROUGH_CONDUCTOR 6 /* raysect/optical/material/conductor.pyx:157-344 (GGX microfacets, Smith shadowing,
+                                    conductor Fresnel; roughness in RsbSpectral.scale[]) */
 #define RSB_MAT_VOLUME_EMITTER 5 /* emitter/uniform.pyx:91-133, emitter/unity.pyx:79-99 on emitter/homogeneous.pyx:40-93
                                     (HomogeneousVolumeEmitter: NullSurface + emission * path length) */
 
@@ -132,7 +134,7 @@ typedef struct RsbSpectral {
     int32_t bins;
     int32_t n_materials;
     const double* tables;     /* [n_materials][bins] reflectivity | (surface or volume) emission | transmission | conductor index n */
-    const double* scale;      /* [n_materials] emitter scale */
+    const double* scale;      /* [n_materials] emitter scale | RoughConductor roughness */
     const double* index_in;   /* [n_materials] dielectric index.average() */
     const double* index_out;  /* [n_materials] dielectric external_index.average() */
     /* materials that sample TWO spectral functions (Conductor: index n -> row i, extinction k -> row table2[i]):

@@ -35,8 +35,8 @@ def ref_api():
     from raysect.core.ray import Ray as CoreRay
     from raysect.optical import ConstantSF, InterpolatedSF, Node, World
     from raysect.optical.library import schott
-    from raysect.optical.material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Sellmeier, UniformSurfaceEmitter,
-                                          UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter)
+    from raysect.optical.material import (AbsorbingSurface, Conductor, Dielectric, Lambert, RoughConductor, Sellmeier,
+                                          UniformSurfaceEmitter, UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter)
     from raysect.optical.observer import FullFrameSampler2D, OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D
     from raysect.primitive import Box, Cone, Cylinder, Intersect, Mesh, Sphere, Subtract, Union
     ns = types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "ns"})

@@ -726,6 +726,23 @@ static double important_pdf(tracer* T, v3 origin, v3 direction) {           /* w
     return pdf_all;
 }
 
+/* RoughConductor helpers, optical/material/conductor.pyx:203-247, 292-310 */
+static double rough_d(v3 h, double r) { double r2 = r * r, h2 = h.z * h.z, k = h2 * (r2 - 1) + 1; return r2 / (M_PI * k * k); }
+static double rough_g1(v3 v, double r) { double r2 = r * r; return 2 * v.z / (v.z + sqrt(r2 + (1 - r2) * (v.z * v.z))); }
+static double rough_pdf(v3 si, v3 so, double r) {
+    v3 h = V(si.x + so.x, si.y + so.y, si.z + so.z);
+    if (len3(h) == 0.0) return 0.0;
+    h = norm3(h);
+    return 0.25 * rough_d(h, r) * fabs(h.z / dot3(so, h));
+}
+static v3 rough_sample(mt_t* g, v3 si, double r) {
+    double e1 = uniform(g), e2 = uniform(g);
+    double theta = atan(r * sqrt(e1) / sqrt(1 - e1)), phi = 2 * M_PI * e2;
+    v3 f = V(cos(phi) * sin(theta), sin(phi) * sin(theta), cos(theta));
+    double t = 2 * dot3(si, f);
+    return V(t * f.x - si.x, t * f.y - si.y, t * f.z - si.z);
+}
+
 /* Ray.trace, optical/ray.pyx:338-401: fills spectrum[bins]; recursion through the material */
 static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep_alive);
 static void trace(tracer* T, ray_t ray, int depth, double* spectrum) { trace_ka(T, ray, depth, spectrum, 0); }
@@ -747,7 +764,9 @@ static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep
     const double* table = T->sp->tables + (size_t)mat * bins;
     if (mtype == RSB_MAT_EMITTER) {                                          /* emitter/uniform.pyx:67-81 */
         for (int i = 0; i < bins; ++i) spectrum[i] = table[i] * T->sp->scale[mat];
-    } else if (mtype == RSB_MAT_LAMBERT) {                                   /* material.pyx:291-361, lambert.pyx:77-105 */
+    } else if (mtype == RSB_MAT_LAMBERT || mtype == RSB_MAT_ROUGH_CONDUCTOR) {  /* ContinuousBSDF: material.pyx:291-361; lambert.pyx:77-105 | conductor.pyx:157-344 */
+        const int rough = mtype == RSB_MAT_ROUGH_CONDUCTOR;
+        const double rgh = T->sp->scale[mat];
         v3 n = it.n, refl_o;
         if (it.exiting) { refl_o = xpoint(it.p2w, it.pin); n = V(-n.x, -n.y, -n.z); } else refl_o = xpoint(it.p2w, it.pout);
         v3 tg = orthogonal3(n), bt = cross3(n, tg);
@@ -761,6 +780,12 @@ static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep
             }
         v3 so, wo;
         double pdf;
+        v3 si = V(0, 0, 0);                                                   /* s_incoming = (world_to_surface . d).neg() */
+        if (rough) {
+            v3 t = V(w2s[0][0] * ray.d.x + w2s[0][1] * ray.d.y + w2s[0][2] * ray.d.z, w2s[1][0] * ray.d.x + w2s[1][1] * ray.d.y + w2s[1][2] * ray.d.z,
+                     w2s[2][0] * ray.d.x + w2s[2][1] * ray.d.y + w2s[2][2] * ray.d.z);
+            si = V(-t.x, -t.y, -t.z);
+        }
         if (cfg->importance_sampling && T->c->s->imp_total > 0) {
             v3 wh = xpoint(it.p2w, it.p);
             if (uniform(T->rng) < cfg->important_path_weight) {
@@ -768,18 +793,38 @@ static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep
                 so = V(w2s[0][0] * wo.x + w2s[0][1] * wo.y + w2s[0][2] * wo.z, w2s[1][0] * wo.x + w2s[1][1] * wo.y + w2s[1][2] * wo.z,
                        w2s[2][0] * wo.x + w2s[2][1] * wo.y + w2s[2][2] * wo.z);
             } else {
-                so = hemisphere_cosine(T->rng);
+                so = rough ? rough_sample(T->rng, si, rgh) : hemisphere_cosine(T->rng);
                 wo = V(s2w[0][0] * so.x + s2w[0][1] * so.y + s2w[0][2] * so.z, s2w[1][0] * so.x + s2w[1][1] * so.y + s2w[1][2] * so.z,
                        s2w[2][0] * so.x + s2w[2][1] * so.y + s2w[2][2] * so.z);
             }
-            double pi = important_pdf(T, wh, wo), pb = so.z >= 0.0 ? M_1_PI * so.z : 0.0;
+            double pi = important_pdf(T, wh, wo), pb = rough ? rough_pdf(si, so, rgh) : (so.z >= 0.0 ? M_1_PI * so.z : 0.0);
             pdf = cfg->important_path_weight * pi + (1 - cfg->important_path_weight) * pb;
         } else {
-            so = hemisphere_cosine(T->rng);
-            pdf = so.z >= 0.0 ? M_1_PI * so.z : 0.0;
+            so = rough ? rough_sample(T->rng, si, rgh) : hemisphere_cosine(T->rng);
+            pdf = rough ? rough_pdf(si, so, rgh) : (so.z >= 0.0 ? M_1_PI * so.z : 0.0);
         }
         double pc = so.z >= 0.0 ? M_1_PI * so.z : 0.0;
-        if (pc != 0.0) {
+        if (rough) {                                                          /* evaluate_shading, conductor.pyx:249-289 */
+            if (so.z > 0 && si.z != 0) {
+                v3 h = norm3(V(si.x + so.x, si.y + so.y, si.z + so.z));
+                ray_t dr;
+                dr.o = refl_o;
+                dr.d = V(s2w[0][0] * so.x + s2w[0][1] * so.y + s2w[0][2] * so.z, s2w[1][0] * so.x + s2w[1][1] * so.y + s2w[1][2] * so.z,
+                         s2w[2][0] * so.x + s2w[2][1] * so.y + s2w[2][2] * so.z);
+                dr.maxd = ray.maxd;
+                T->rays += 1;
+                trace(T, dr, depth + 1, spectrum);
+                double f = rough_d(h, rgh) * (rough_g1(si, rgh) * rough_g1(so, rgh)) / (4 * si.z);
+                for (int i = 0; i < bins; ++i) spectrum[i] *= f;
+                double ci = dot3(h, so);                                      /* _f, conductor.pyx:312-328 */
+                const double* kk = T->sp->tables + (size_t)T->sp->table2[mat] * bins;
+                for (int i = 0; i < bins; ++i) {
+                    double nn = table[i], k = kk[i];
+                    double ci2 = ci * ci, k0 = nn * nn + k * k, k1 = k0 * ci2 + 1, k2 = 2 * nn * ci, k3 = k0 + ci2;
+                    spectrum[i] *= 0.5 * ((k1 - k2) / (k1 + k2) + (k3 - k2) / (k3 + k2));
+                }
+            }
+        } else if (pc != 0.0) {
             ray_t dr;
             dr.o = refl_o;
             dr.d = V(s2w[0][0] * so.x + s2w[0][1] * so.y + s2w[0][2] * so.z, s2w[1][0] * so.x + s2w[1][1] * so.y + s2w[1][2] * so.z,

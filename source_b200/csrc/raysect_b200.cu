@@ -709,7 +709,7 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     const int n_tables = spectral->n_tables > 0 ? spectral->n_tables : spectral->n_materials;
     if (n_tables < spectral->n_materials) return fail(RSB_ERR_ARG, "rsb_render: n_tables is smaller than the number of materials");
     for (int i = 0; i < ds->n_materials; ++i)
-        if (ds->mat_type[i] == RSB_MAT_CONDUCTOR &&
+        if ((ds->mat_type[i] == RSB_MAT_CONDUCTOR || ds->mat_type[i] == RSB_MAT_ROUGH_CONDUCTOR) &&
             (!spectral->table2 || spectral->table2[i] < 0 || spectral->table2[i] >= n_tables))
             return fail(RSB_ERR_ARG, "rsb_render: a Conductor needs its extinction table (RsbSpectral.table2)");
     if (config->important_path_weight < 0 || config->important_path_weight > 1.0)

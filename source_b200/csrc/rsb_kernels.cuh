@@ -806,7 +806,8 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
             a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
             a.st.status[slot] = SLOT_HIT;
             list = a.sp.mats[sc.prims[rec.prim].material].type;     // 0..3: per-material hit lists
-            if (list >= MAT_CONDUCTOR) list = MAT_DIELECTRIC;        // conductors and null surfaces share the specular list
+            // conductors and null surfaces share the specular list, the rough conductor (a ContinuousBSDF) Lambert's
+            if (list >= MAT_CONDUCTOR) list = (list == MAT_ROUGH_CONDUCTOR) ? MAT_LAMBERT : MAT_DIELECTRIC;
         } else {
             a.st.status[slot] = SLOT_ENDED_ZERO;
             list = 4;                                                // ended list

@@ -110,6 +110,36 @@ RSB_HD V3 hemisphere_cosine_sample(Rng& rng) {
     return v3(x, y, sqrt(max0(1.0 - x * x - y * y)));
 }
 
+// ----- RoughConductor (raysect/optical/material/conductor.pyx:157-344): GGX facet distribution, Smith shadowing
+RSB_HD double ggx_d(const V3& s_half, double roughness) {          // _d, conductor.pyx:292-300
+    double r2 = roughness * roughness;
+    double h2 = s_half.z * s_half.z;
+    double k = h2 * (r2 - 1) + 1;
+    return r2 / (RSB_PI * k * k);
+}
+
+RSB_HD double ggx_g1(const V3& v, double roughness) {              // _g1, conductor.pyx:307-310
+    double r2 = roughness * roughness;
+    return 2 * v.z / (v.z + sqrt(r2 + (1 - r2) * (v.z * v.z)));
+}
+
+RSB_HD double ggx_pdf(const V3& s_incoming, const V3& s_outgoing, double roughness) {   // pdf, conductor.pyx:203-220
+    V3 s_half = v3(s_incoming.x + s_outgoing.x, s_incoming.y + s_outgoing.y, s_incoming.z + s_outgoing.z);
+    if (length(s_half) == 0.0) return 0.0;
+    s_half = normalise(s_half);
+    return 0.25 * ggx_d(s_half, roughness) * fabs(s_half.z / dot(s_outgoing, s_half));
+}
+
+RSB_HD V3 ggx_sample(Rng& rng, const V3& s_incoming, double roughness) {               // sample, conductor.pyx:222-247
+    double e1 = rng.uniform();
+    double e2 = rng.uniform();
+    double theta = atan(roughness * sqrt(e1) / sqrt(1 - e1));
+    double phi = 2 * RSB_PI * e2;
+    V3 facet_normal = v3(cos(phi) * sin(theta), sin(phi) * sin(theta), cos(theta));
+    double temp = 2 * dot(s_incoming, facet_normal);
+    return v3(temp * facet_normal.x - s_incoming.x, temp * facet_normal.y - s_incoming.y, temp * facet_normal.z - s_incoming.z);
+}
+
 RSB_HD double hemisphere_cosine_pdf(const V3& s) {
     if (s.z >= 0.0) return RSB_1_PI * s.z;
     return 0.0;
@@ -278,7 +308,10 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
         if (mtype == MAT_ABSORBER) return PATH_ZERO;
 
         V3 next_o, next_d;
-        if (mtype == MAT_LAMBERT) {
+        // RoughConductor is a ContinuousBSDF like Lambert: same surface frame and multiple importance sampling, its own
+        // sample / pdf / evaluate_shading (full-featured instantiation only; it is dealt to the Lambert shade list)
+        const bool rough = (FEAT & RSB_FEAT_RARE_MATERIALS) && mat.type == MAT_ROUGH_CONDUCTOR;
+        if (mtype == MAT_LAMBERT || rough) {
             // ContinuousBSDF.evaluate_surface (material.pyx:291-361) + Lambert (lambert.pyx:71-105)
             V3 normal = is.normal;
             V3 w_reflection_origin;
@@ -302,24 +335,48 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
                 }
             V3 s_outgoing, w_outgoing;
             double pdf;
+            // s_incoming = ray.direction.transform(world_to_surface).neg() (material.pyx:326); Lambert never looks at it
+            V3 s_incoming = v3(0, 0, 0);
+            const double roughness = mat.scale;
+            if (rough) {
+                V3 t = xform_vector33(w2s, d);
+                s_incoming = v3(-t.x, -t.y, -t.z);
+            }
             bool mis = cfg.importance_sampling && sc.imp_total > 0;
             if (mis) {
                 if (rng.probability(cfg.important_path_weight)) {
                     w_outgoing = important_direction_sample(sc, rng, w_hit);
                     s_outgoing = xform_vector33(w2s, w_outgoing);
                 } else {
-                    s_outgoing = hemisphere_cosine_sample(rng);
+                    s_outgoing = rough ? ggx_sample(rng, s_incoming, roughness) : hemisphere_cosine_sample(rng);
                     w_outgoing = xform_vector33(s2w, s_outgoing);
                 }
                 double pdf_important = important_direction_pdf(sc, w_hit, w_outgoing);
-                double pdf_bsdf = hemisphere_cosine_pdf(s_outgoing);
+                double pdf_bsdf = rough ? ggx_pdf(s_incoming, s_outgoing, roughness) : hemisphere_cosine_pdf(s_outgoing);
                 pdf = cfg.important_path_weight * pdf_important + (1 - cfg.important_path_weight) * pdf_bsdf;
 #ifdef RSB_DEBUG_MIS
                 fprintf(stderr, "MIS w_hit=(%.17g, %.17g, %.17g) w_out=(%.17g, %.17g, %.17g) pdf_imp=%.17g pdf_bsdf=%.17g pdf=%.17g\n", w_hit.x, w_hit.y, w_hit.z, w_outgoing.x, w_outgoing.y, w_outgoing.z, pdf_important, pdf_bsdf, pdf);
 #endif
             } else {
-                s_outgoing = hemisphere_cosine_sample(rng);
-                pdf = hemisphere_cosine_pdf(s_outgoing);
+                s_outgoing = rough ? ggx_sample(rng, s_incoming, roughness) : hemisphere_cosine_sample(rng);
+                pdf = rough ? ggx_pdf(s_incoming, s_outgoing, roughness) : hemisphere_cosine_pdf(s_outgoing);
+            }
+            if (rough) {
+                // RoughConductor.evaluate_shading (conductor.pyx:249-289): no transmission, no grazing incidence
+                if (s_outgoing.z <= 0) return PATH_ZERO;
+                if (s_incoming.z == 0) return PATH_ZERO;
+                V3 s_half = normalise(v3(s_incoming.x + s_outgoing.x, s_incoming.y + s_outgoing.y, s_incoming.z + s_outgoing.z));
+                // unwind order: mul_scalar(D * G / (4 cos_i)), per-bin Fresnel (_f, conductor.pyx:312-328), div_scalar(pdf)
+                log.push(LOG_MULS, 0, 1.0 / pdf);
+                log.push(LOG_FRESNEL | (mat.table2 << 8), mat.table, dot(s_half, s_outgoing));
+                log.push(LOG_MULS, 0, ggx_d(s_half, roughness) * (ggx_g1(s_incoming, roughness) * ggx_g1(s_outgoing, roughness)) / (4 * s_incoming.z));
+                stats.table_read();
+                stats.table_read();
+                ps.o = w_reflection_origin;
+                ps.d = xform_vector33(s2w, s_outgoing);
+                ps.depth = depth + 1;
+                ps.rays += 1;
+                return PATH_CONTINUE;
             }
             // Lambert.evaluate_shading (lambert.pyx:77-105)
             double pdf_cos = hemisphere_cosine_pdf(s_outgoing);

@@ -30,6 +30,7 @@ enum MatType : int32_t {
     MAT_LAMBERT = 2,    // raysect/optical/material/lambert.pyx:77-105
     MAT_DIELECTRIC = 3, // raysect/optical/material/dielectric.pyx:153-330
     MAT_CONDUCTOR = 4,  // raysect/optical/material/conductor.pyx:75-147 (shaded with the dielectric family)
+    MAT_ROUGH_CONDUCTOR = 6,  // raysect/optical/material/conductor.pyx:157-344 (a ContinuousBSDF: shaded with the Lambert family)
     MAT_VOLUME_EMITTER = 5,   // emitter/homogeneous.pyx:40-93 with uniform.pyx:91-133 / unity.pyx:79-99 (same family)
 };
 
@@ -90,7 +91,7 @@ struct Material {
     int32_t transmission_only;
     int32_t table;      // row of the per-slice spectral table (reflectivity | emission | transmission | conductor n)
     int32_t table2;     // conductor: row of the extinction table k; else -1
-    double scale;       // emitter scale
+    double scale;       // emitter scale | rough conductor: roughness
     double index_in;    // dielectric: index.average(min,max) for the slice
     double index_out;   // dielectric: external_index.average(min,max)
 };

@@ -60,7 +60,7 @@ int pack_scene(const RsbSceneDesc* d, PackedScene* out, std::string* err) {
         }
     }
     for (int i = 0; i < d->n_materials; ++i)
-        if (d->mat_type[i] < RSB_MAT_ABSORBER || d->mat_type[i] > RSB_MAT_VOLUME_EMITTER) {
+        if (d->mat_type[i] < RSB_MAT_ABSORBER || d->mat_type[i] > RSB_MAT_ROUGH_CONDUCTOR) {
             *err = "unsupported material type in row " + std::to_string(i);
             return RSB_ERR_UNSUPPORTED;
         }

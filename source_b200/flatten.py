@@ -30,7 +30,8 @@ _MATERIALS = {
     "Lambert": cabi.MAT_LAMBERT, "Dielectric": cabi.MAT_DIELECTRIC,
     # HomogeneousVolumeEmitter subclasses with a direction-independent emission_function (homogeneous.pyx:40-93)
     "UniformVolumeEmitter": cabi.MAT_VOLUME_EMITTER, "UnityVolumeEmitter": cabi.MAT_VOLUME_EMITTER,
-    "Conductor": cabi.MAT_CONDUCTOR,             # conductor.pyx:39-147 (RoughConductor is a different class: unsupported)
+    "Conductor": cabi.MAT_CONDUCTOR,             # conductor.pyx:39-147
+    "RoughConductor": cabi.MAT_ROUGH_CONDUCTOR,  # conductor.pyx:157-344 (a ContinuousBSDF, not a Conductor subclass)
 }
 
 # world tree parameters of _PrimitiveKDTree (raysect/core/acceleration/kdtree.pyx:43)
@@ -103,7 +104,7 @@ class FlatScene:
         (raysect/optical/spectralfunction.pyx:140-216); evaluated by the object model itself."""
         n = len(self.materials)
         # materials that sample two spectral functions (Conductor: index, extinction) get an extra table row each
-        second = [i for i, t in enumerate(self.mat_type) if t == cabi.MAT_CONDUCTOR]
+        second = [i for i, t in enumerate(self.mat_type) if t in (cabi.MAT_CONDUCTOR, cabi.MAT_ROUGH_CONDUCTOR)]
         table2 = np.full(n, -1, dtype=np.int32)
         for j, i in enumerate(second):
             table2[i] = n + j
@@ -123,10 +124,12 @@ class FlatScene:
                 tables[i] = np.asarray(m.transmission.sample(min_wavelength, max_wavelength, bins))
                 index_in[i] = m.index.average(min_wavelength, max_wavelength)
                 index_out[i] = m.external_index.average(min_wavelength, max_wavelength)
-            elif t == cabi.MAT_CONDUCTOR:
-                # conductor.pyx:101-102: n and k resampled onto the ray's bins
+            elif t in (cabi.MAT_CONDUCTOR, cabi.MAT_ROUGH_CONDUCTOR):
+                # conductor.pyx:101-102, 321-322: n and k resampled onto the ray's bins
                 tables[i] = np.asarray(m.index.sample(min_wavelength, max_wavelength, bins))
                 tables[table2[i]] = np.asarray(m.extinction.sample(min_wavelength, max_wavelength, bins))
+                if t == cabi.MAT_ROUGH_CONDUCTOR:
+                    scale[i] = m.roughness
         s = cabi.RsbSpectral()
         s.bins = bins
         s.n_materials = n

@@ -61,6 +61,29 @@ class Conductor(Material):
         self.extinction = extinction
 
 
+class RoughConductor(Material):
+    """conductor.pyx:157-344: Cook-Torrance metal -- GGX facet distribution, Smith shadowing, conductor Fresnel;
+    roughness in (0, 1]"""
+
+    def __init__(self, index, extinction, roughness):
+        super().__init__()
+        if not isinstance(index, SpectralFunction) or not isinstance(extinction, SpectralFunction):
+            raise TypeError("index and extinction must be SpectralFunction objects")
+        self.index = index
+        self.extinction = extinction
+        self.roughness = roughness
+
+    @property
+    def roughness(self):
+        return self._roughness
+
+    @roughness.setter
+    def roughness(self, value):
+        if value <= 0 or value > 1:
+            raise ValueError("Surface roughness must lie in the range (0, 1].")
+        self._roughness = float(value)
+
+
 class UniformVolumeEmitter(Material):
     """emitter/uniform.pyx:91-133 on emitter/homogeneous.pyx:40-93: transparent surface, emission_spectrum * scale
     (W/m^3/str/nm) integrated along the path inside the primitive; importance 1 (homogeneous.pyx:48)"""

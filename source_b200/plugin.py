@@ -106,7 +106,7 @@ class CudaRenderEngine(RenderEngine):
     ``observer._render_pixel``, so the observer, its world and its pipelines are reachable from it.
     Supported: ``PinholeCamera`` and ``OrthographicCamera`` observers feeding ``SpectralPowerPipeline2D`` pipelines (the spectral frame
     every other 2-D pipeline is a post-processing of), worlds built from Sphere/Box/Cylinder/Cone/CSG/Mesh
-    with Lambert / UniformSurfaceEmitter / UnitySurfaceEmitter / Dielectric / Conductor / AbsorbingSurface /
+    with Lambert / UniformSurfaceEmitter / UnitySurfaceEmitter / Dielectric / Conductor / RoughConductor / AbsorbingSurface /
     UniformVolumeEmitter / UnityVolumeEmitter materials.
 
     Random streams: pixel (x, y) of slice k draws from the reference generator seeded with

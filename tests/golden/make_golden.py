@@ -104,7 +104,18 @@ def ortho_goldens():
     save("ortho_20x16_s3_b8_r2", mean=mean, variance=var, samples=n)
 
 
+def rough_goldens():
+    """RoughConductor (GGX / Smith / conductor Fresnel) under multiple importance sampling and without it"""
+    world = scenes.rough_metal_scene(api)
+    cam, r = render(world, dict(pixels=(24, 24), samples=4, bins=10, path_weight=0.3), 606)
+    save("rough_24x24_s4_b10", **r)
+    cam, r = render(world, dict(pixels=(16, 12), samples=3, bins=6, spectral_rays=2, importance=False), 607)
+    save("rough_16x12_s3_b6_r2_noimp", **r)
+
+
 def main():
+    if "--rough-only" in sys.argv:
+        return rough_goldens()
     if "--ortho-only" in sys.argv:
         return ortho_goldens()
     if "--volume-only" in sys.argv:
@@ -172,6 +183,7 @@ def main():
     metal_goldens()
     volume_goldens()
     ortho_goldens()
+    rough_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

@@ -76,6 +76,21 @@ def metal_scene(api):
     return world
 
 
+def rough_metal_scene(api):
+    """Cornell box with RoughConductor objects (GGX microfacet metal) of three roughnesses: sphere, box, smooth-shaded mesh"""
+    a = api
+    n, k = a.InterpolatedSF(GOLD_WAVELENGTHS, GOLD_N), a.InterpolatedSF(GOLD_WAVELENGTHS, GOLD_K)
+    verts, tris, normals = icosphere(2, radius=0.3, bumps=0.2)
+
+    def extra(a, w):
+        a.Sphere(0.35, parent=w, transform=a.translate(-0.45, -0.65, -0.3), material=a.RoughConductor(n, k, 0.25))
+        a.Box(a.Point3D(-0.3, 0, -0.3), a.Point3D(0.3, 0.9, 0.3), parent=w,
+              transform=a.translate(0.45, -1 + 1e-6, 0.4) * a.rotate(25, 0, 0), material=a.RoughConductor(n, k, 0.8))
+        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w,
+               transform=a.translate(0.2, 0.4, -0.3) * a.rotate(15, 25, 5), material=a.RoughConductor(n, k, 0.1))
+    return cornell_box(a, glass=False, extra=extra)
+
+
 def volume_scene(api, fog=True):
     """Cornell box with emitting volumes (HomogeneousVolumeEmitter on a NullSurface): a glowing sphere overlapped by
     a glass sphere, a unity-emission cylinder, and (fog) a faint emitting box that contains the whole room AND the

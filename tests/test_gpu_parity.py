@@ -109,6 +109,11 @@ def test_orthographic_camera(make_backend):
     print("divergent pixel fraction:", fr)
 
 
+def test_rough_conductor(make_backend):
+    fr = parity.rough_metal(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.03)
+    print("divergent pixel fractions:", fr)
+
+
 def test_prism_csg_dispersion(make_backend):
     fr = parity.prism(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
     print("divergent pixel fraction:", fr)

@@ -58,6 +58,10 @@ def test_orthographic_camera_bit_exact(make_backend):
     parity.orthographic(make_backend, exact=True)
 
 
+def test_rough_conductor_bit_exact(make_backend):
+    parity.rough_metal(make_backend, exact=True)
+
+
 def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 

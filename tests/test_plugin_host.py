@@ -137,6 +137,21 @@ def test_render_engine_on_real_volume_emitter_objects(api, reference):
     assert np.all(m_ref > 0)       # the fog box contains the camera: every pixel sees emission
 
 
+def test_render_engine_on_real_rough_conductor_objects(api, reference):
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(10, 10), samples=3, bins=5)
+    world = scenes.rough_metal_scene(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 12)
+    world2 = scenes.rough_metal_scene(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
+    cam2.render_engine = CudaRenderEngine(seed=12, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert m_ref.sum() > 0
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
