@@ -152,6 +152,39 @@ def test_render_engine_on_real_rough_conductor_objects(api, reference):
     assert m_ref.sum() > 0
 
 
+def test_adaptive_sampling_loop_with_cuda_render_engine(api, reference):
+    """The reference's progressive / adaptive loop (demos/cornell_box.py:145-174 with the spectral variant of the
+    sampler): Raysect's own SpectralAdaptiveSampler2D reads the pipeline's frame (mean / variance / samples, written by
+    CudaRenderEngine's bulk update) and hands back a PARTIAL task list for the next observe(); the engine renders just
+    those pixels and merges them with combine_samples.  Three passes must leave exactly the frame the reference leaves."""
+    from raysect.optical.observer import SpectralAdaptiveSampler2D
+    from source_b200.plugin import CudaRenderEngine
+
+    def run(engine_factory):
+        world = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, world, pixels=(14, 14), samples=12, bins=4)
+        cam.frame_sampler = SpectralAdaptiveSampler2D(pipe, fraction=0.3, ratio=4.0, min_samples=12, cutoff=0.0)
+        pipe.accumulate = True
+        engine_factory(cam, pipe)
+        return np.array(pipe.frame.mean), np.array(pipe.frame.variance), np.array(pipe.frame.samples)
+
+    def reference_loop(cam, pipe):
+        for p in range(3):
+            reference.oracle_render(cam, pipe, 900 + 1000 * p)      # per-pixel re-seeding engine, one observe()
+
+    def cuda_loop(cam, pipe):
+        for p in range(3):
+            cam.render_engine = CudaRenderEngine(seed=900 + 1000 * p, rng="mt", backend=hostsim_api.HostScene)
+            cam.observe()
+
+    m_ref, v_ref, n_ref = run(reference_loop)
+    m, v, n = run(cuda_loop)
+    assert n_ref.min() == 12 and n_ref.max() == 36      # the sampler really did refine a subset of the pixels
+    np.testing.assert_array_equal(n, n_ref)
+    np.testing.assert_array_equal(m, m_ref)
+    np.testing.assert_array_equal(v, v_ref)
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
