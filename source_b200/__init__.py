@@ -17,7 +17,7 @@ from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Materia
                        UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter, schott)
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Primitive, Ray, Sphere,
                          Subtract, Union, World)
-from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D,
-                       SpectralSlice, StatsArray3D)
+from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
+                       SpectralPowerPipeline2D, SpectralSlice, StatsArray3D)
 from .engine import Accelerator, Device, default_device
 from ._cabi import RNG_MT19937_64, RNG_PHILOX, RsbError

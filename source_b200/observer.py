@@ -196,6 +196,93 @@ class FullFrameSampler2D:
         return np.stack([ix, iy], axis=1).astype(np.int32)
 
 
+class SpectralAdaptiveSampler2D:
+    """raysect/optical/observer/sampler2d.pyx:325-700: frame sampler that re-samples the noisiest fraction of the
+    frame.  Reads the pipeline's frame statistics (mean, variance, samples -- the arrays the device render fills) and
+    returns the pixels whose normalised standard error exceeds the (1 - fraction) percentile (or ``cutoff``), plus
+    every pixel that has fewer than max(min_samples, max_samples / ratio) samples.  Task order does not matter here
+    (pixel streams are keyed on the pixel), so tasks come back in scan order instead of shuffled."""
+
+    def __init__(self, pipeline, fraction=0.2, ratio=10.0, min_samples=1000, cutoff=0.0, reduction_method='percentile',
+                 percentile=100., mask=None):
+        if not isinstance(pipeline, SpectralPowerPipeline2D):
+            raise TypeError('Sampler only compatible with SpectralPowerPipeline2D or SpectralRadiancePipeline2D pipelines.')
+        if fraction <= 0 or fraction > 1.:
+            raise ValueError("Attribute 'fraction' must be in the range (0, 1].")
+        if ratio < 1.:
+            raise ValueError("Attribute 'ratio' must be >= 1.")
+        if min_samples < 1:
+            raise ValueError("Attribute 'min_samples' must be >= 1.")
+        if cutoff < 0 or cutoff > 1.:
+            raise ValueError("Attribute 'cutoff' must be in the range [0, 1].")
+        if reduction_method not in {'weighted', 'mean', 'percentile', 'power_percentile'}:
+            raise ValueError("Attribute 'reduction_method' must be 'weighted', 'mean', 'percentile' or 'power_percentile'.")
+        if percentile < 0 or percentile > 100.:
+            raise ValueError("Percentiles must be in the range [0, 100].")
+        self.pipeline, self.fraction, self.ratio, self.min_samples = pipeline, fraction, ratio, int(min_samples)
+        self.cutoff, self.reduction_method, self.percentile = cutoff, reduction_method, percentile
+        self.mask = None if mask is None else np.asarray(mask).astype(bool)
+        if self.mask is not None and self.mask.ndim != 2:
+            raise ValueError("Mask must be a 2D array.")
+
+    def _normalised(self, frame, mask):
+        """_reduce_weighted / _reduce_mean / _reduce_percentile / _reduce_power_percentile (sampler2d.pyx:545-668);
+        per-pixel sums run over the bins in order, as the reference's loops do"""
+        mean = frame.mean
+        samples = frame.samples
+        # StatsArray3D.errors -> _std_error (statsarray.pyx:728-739)
+        ok = (samples > 0) & (frame.variance > 0)
+        error = np.zeros_like(mean)
+        error[ok] = np.sqrt(frame.variance[ok] / samples[ok])
+        normalised = np.zeros((frame.nx, frame.ny))
+        for x in range(frame.nx):
+            for y in range(frame.ny):
+                if not mask[x, y]:
+                    continue
+                pos = mean[x, y] > 0
+                if not pos.any():
+                    continue
+                e, m = error[x, y][pos], mean[x, y][pos]
+                if self.reduction_method == 'weighted':
+                    acc, power = 0.0, 0.0
+                    for ei, mi in zip(e, m):
+                        acc += ei
+                        power += mi
+                    normalised[x, y] = acc / power if power else acc
+                elif self.reduction_method == 'mean':
+                    acc = 0.0
+                    for ei, mi in zip(e, m):
+                        acc += ei / mi
+                    normalised[x, y] = acc / len(e)
+                elif self.reduction_method == 'percentile':
+                    normalised[x, y] = np.percentile(e / m, self.percentile)
+                else:
+                    threshold = np.percentile(m, 100. - self.percentile)
+                    sel = mean[x, y] >= threshold
+                    normalised[x, y] = max(0.0, np.max(error[x, y][sel] / mean[x, y][sel]))
+        return normalised
+
+    def generate_tasks(self, pixels):
+        nx, ny = pixels
+        if self.mask is None or (self.mask.shape != (nx, ny) and np.all(self.mask)):
+            self.mask = np.ones((nx, ny), dtype=bool)
+        if self.mask.shape != (nx, ny):
+            raise ValueError('The pixel geometry passed to the frame sampler is inconsistent with the mask shape.')
+        frame = self.pipeline.frame
+        full = np.argwhere(self.mask).astype(np.int32)
+        if frame is None:
+            return full
+        if (nx, ny) != (frame.nx, frame.ny):
+            raise ValueError('The pixel geometry passed to the frame sampler is inconsistent with the pipeline frame size.')
+        min_samples = max(self.min_samples, int(frame.samples.max(2)[self.mask].max() / self.ratio))
+        normalised = self._normalised(frame, self.mask)
+        percentile_error = np.percentile(normalised[self.mask], (1 - self.fraction) * 100)
+        cutoff = max(self.cutoff, percentile_error)
+        frame_min_samples = frame.samples.min(2)
+        todo = self.mask & ((frame_min_samples < min_samples) | (normalised > cutoff))
+        return np.argwhere(todo).astype(np.int32)
+
+
 class PinholeCamera(Observer):
     """raysect/optical/observer/imaging/pinhole.pyx + base/observer.pyx (Observer2D, _ObserverBase).
 

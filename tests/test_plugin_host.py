@@ -185,6 +185,66 @@ def test_adaptive_sampling_loop_with_cuda_render_engine(api, reference):
     np.testing.assert_array_equal(v, v_ref)
 
 
+@pytest.mark.parametrize("method", ["weighted", "mean", "percentile", "power_percentile"])
+def test_mirror_adaptive_sampler_picks_the_reference_task_set(api, reference, method):
+    """source_b200.SpectralAdaptiveSampler2D (stand-alone mirror) against Raysect's sampler on the same frame statistics"""
+    import source_b200 as mirror
+    from raysect.optical.observer import SpectralAdaptiveSampler2D
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(14, 12), samples=10, bins=5)
+    pipe.accumulate = True
+    mask = np.ones((14, 12), dtype=bool)
+    mask[:2, :] = False
+    kw = dict(fraction=0.35, ratio=3.0, min_samples=10, cutoff=0.0, reduction_method=method, percentile=80.0)
+    ref_sampler = SpectralAdaptiveSampler2D(pipe, mask=mask.copy(), **kw)
+    cam.frame_sampler = ref_sampler
+    mpipe = mirror.SpectralPowerPipeline2D()
+    msampler = mirror.SpectralAdaptiveSampler2D(mpipe, mask=mask.copy(), **kw)
+    assert sorted(map(tuple, msampler.generate_tasks((14, 12)))) == sorted(ref_sampler.generate_tasks((14, 12)))   # no frame yet
+    sizes = []
+    for p in range(3):
+        reference.oracle_render(cam, pipe, 50 + 500 * p)
+        f = mirror.StatsArray3D(14, 12, 5)
+        f.mean[...], f.variance[...], f.samples[...] = np.array(pipe.frame.mean), np.array(pipe.frame.variance), np.array(pipe.frame.samples)
+        mpipe.frame = f
+        got = sorted(map(tuple, msampler.generate_tasks((14, 12))))
+        want = sorted(ref_sampler.generate_tasks((14, 12)))
+        assert got == want
+        sizes.append(len(want))
+    assert 0 < sizes[-1] < mask.sum()
+
+
+def test_standalone_mirror_adaptive_loop_matches_reference_loop(api, reference):
+    """the same progressive loop without Raysect installed: mirror World / PinholeCamera / SpectralAdaptiveSampler2D over
+    the host build of the device code, against Raysect running its own loop"""
+    import parity
+    import source_b200 as mirror
+    from raysect.optical.observer import SpectralAdaptiveSampler2D
+    kw = dict(pixels=(14, 14), samples=12, bins=4)
+    skw = dict(fraction=0.3, ratio=4.0, min_samples=12, cutoff=0.0, reduction_method="weighted")
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    cam.frame_sampler = SpectralAdaptiveSampler2D(pipe, **skw)
+    pipe.accumulate = True
+    for p in range(3):
+        reference.oracle_render(cam, pipe, 900 + 1000 * p)
+    mworld = scenes.cornell_box(mirror)
+    mcam, mpipe = scenes.cornell_camera(mirror, mworld, **kw)
+    mcam.frame_sampler = mirror.SpectralAdaptiveSampler2D(mpipe, **skw)
+    mpipe.accumulate = True
+    mworld._accel = parity._Accel(hostsim_api.HostScene(parity.flatten_world(mworld)))
+    mworld._rebuild = False
+    for p in range(3):
+        mcam.seed = 900 + 1000 * p
+        mcam.observe()
+    mworld._accel.close()
+    n_ref = np.array(pipe.frame.samples)
+    assert n_ref.min() == 12 and n_ref.max() == 36
+    np.testing.assert_array_equal(mpipe.frame.samples, n_ref)
+    np.testing.assert_array_equal(mpipe.frame.mean, np.array(pipe.frame.mean))
+    np.testing.assert_array_equal(mpipe.frame.variance, np.array(pipe.frame.variance))
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
