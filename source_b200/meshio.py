@@ -1,0 +1,117 @@
+"""Mesh file importers with the reference's call signatures (raysect/primitive/mesh/obj.py, stl.py).
+
+``import_obj(filename, scaling=1.0, **mesh_kwargs)`` and ``import_stl(filename, scaling=1.0, mode=..., **mesh_kwargs)``
+return a ``source_b200.Mesh``; its kd-tree is built by this package's bit-exact SAH builder and the triangles go to
+the device as pre-gathered 48-byte rows.
+"""
+import struct
+
+import numpy as np
+
+from .math3d import Normal3D
+from .scenegraph import Mesh
+
+
+def _parse_face_token(token):
+    """obj.py:128-142: ``v``, ``v/vt`` or ``v/vt/vn`` (1-based)"""
+    indices = token.split("/")
+    if len(indices) in (1, 2):
+        return int(indices[0]) - 1, None
+    if len(indices) == 3:
+        return int(indices[0]) - 1, int(indices[2]) - 1
+    raise ValueError("The .obj contains an invalid face definition.")
+
+
+def import_obj(filename, scaling=1.0, **kwargs):
+    """OBJHandler.import_obj (raysect/primitive/mesh/obj.py:38-95): vertices scaled by ``scaling``, vertex normals
+    normalised in double precision, triangular faces only, texture coordinates ignored."""
+    vertices, normals, triangles = [], [], []
+    with open(filename) as f:
+        for line in f:
+            if line[0] == "#":
+                continue
+            tokens = line.strip().split(" ")
+            cmd, tokens = tokens[0], tokens[1:]
+            if cmd == "v":
+                x, y, z = tokens
+                vertices.append([scaling * float(x), scaling * float(y), scaling * float(z)])
+            elif cmd == "vn":
+                x, y, z = tokens
+                n = Normal3D(float(x), float(y), float(z)).normalise()
+                normals.append([n.x, n.y, n.z])
+            elif cmd == "f":
+                if len(tokens) != 3:
+                    raise ValueError("The .obj importer only support meshes containing 3 sided faces (triangles).")
+                (v1, n1), (v2, n2), (v3, n3) = (_parse_face_token(t) for t in tokens)
+                if n1 is None or n2 is None or n3 is None:
+                    triangles.append([v1, v2, v3])
+                else:
+                    triangles.append([v1, v2, v3, n1, n2, n3])
+    if normals:
+        return Mesh(vertices, triangles, normals, **kwargs)
+    return Mesh(vertices, triangles, **kwargs)
+
+
+STL_AUTOMATIC, STL_ASCII, STL_BINARY = "auto", "ascii", "binary"
+
+
+def import_stl(filename, scaling=1.0, mode=STL_AUTOMATIC, **kwargs):
+    """STLHandler.import_stl (raysect/primitive/mesh/stl.py:46-180): every facet contributes three new vertices
+    (no welding), facet normals are ignored (the mesh computes its own face normals), smoothing is off."""
+    mode = mode.lower()
+    if mode == STL_ASCII:
+        vertices, triangles = _load_stl_ascii(filename, scaling)
+    elif mode == STL_BINARY:
+        vertices, triangles = _load_stl_binary(filename, scaling)
+    elif mode == STL_AUTOMATIC:
+        try:
+            vertices, triangles = _load_stl_ascii(filename, scaling)
+        except ValueError:
+            vertices, triangles = _load_stl_binary(filename, scaling)
+    else:
+        raise ValueError("Unrecognised import mode specified: {}".format(mode))
+    kwargs.setdefault("smoothing", False)
+    return Mesh(vertices, triangles, **kwargs)
+
+
+def _load_stl_ascii(filename, scaling):
+    with open(filename, "r") as f:
+        try:
+            if not f.readline().startswith("solid"):
+                raise ValueError("ASCII STL data does not start with 'solid'.")
+        except UnicodeDecodeError:
+            raise ValueError("File does not contain valid ascii data.")
+        vertices, triangles = [], []
+        facet = []
+        try:
+            for line in f:
+                tokens = line.strip().split()
+                if not tokens:
+                    continue
+                if tokens[0] == "vertex":
+                    facet.append([scaling * float(tokens[1]), scaling * float(tokens[2]), scaling * float(tokens[3])])
+                elif tokens[0] == "endfacet":
+                    if len(facet) != 3:
+                        raise ValueError("ASCII STL facet does not have three vertices.")
+                    base = len(vertices)
+                    vertices.extend(facet)
+                    triangles.append([base, base + 1, base + 2])
+                    facet = []
+        except UnicodeDecodeError:
+            raise ValueError("File does not contain valid ascii data.")
+    if not triangles:
+        raise ValueError("ASCII STL file contains no facets.")
+    return vertices, triangles
+
+
+def _load_stl_binary(filename, scaling):
+    with open(filename, "rb") as f:
+        f.seek(80)                                            # header
+        count = struct.unpack("<I", f.read(4))[0]
+        data = np.frombuffer(f.read(50 * count), dtype=np.uint8)
+    if data.size != 50 * count:
+        raise ValueError("Binary STL file is truncated.")
+    rec = data.reshape(count, 50)[:, 12:48].copy().view("<f4").reshape(count, 3, 3)   # skip the facet normal
+    vertices = (scaling * rec.astype(np.float64)).reshape(-1, 3)
+    triangles = np.arange(3 * count, dtype=np.int32).reshape(count, 3)
+    return vertices, triangles

@@ -245,6 +245,85 @@ def test_standalone_mirror_adaptive_loop_matches_reference_loop(api, reference):
     np.testing.assert_array_equal(mpipe.frame.variance, np.array(pipe.frame.variance))
 
 
+def _write_mesh_files(tmp_path):
+    """the bumpy icosphere as .obj (with and without normals, with v/vt/vn tokens and comments), ascii and binary .stl"""
+    import struct
+    verts, tris, normals = scenes.icosphere(2, radius=0.4, bumps=0.15)
+    obj_n, obj_p = tmp_path / "with_normals.obj", tmp_path / "plain.obj"
+    with open(obj_n, "w") as f:
+        f.write("# test mesh\n")
+        for v in verts:
+            f.write("v %.9g %.9g %.9g\n" % tuple(v))
+        f.write("vt 0.5 0.5\n")
+        for n in normals:
+            f.write("vn %.9g %.9g %.9g\n" % tuple(1.7 * n))          # not unit length: the importer normalises
+        for t in tris:
+            f.write("f %d/1/%d %d/1/%d %d/1/%d\n" % (t[0] + 1, t[3] + 1, t[1] + 1, t[4] + 1, t[2] + 1, t[5] + 1))
+    with open(obj_p, "w") as f:
+        for v in verts:
+            f.write("v %.9g %.9g %.9g\n" % tuple(v))
+        for k, t in enumerate(tris):
+            f.write(("f %d %d %d\n" if k % 2 else "f %d/1 %d/1 %d/1\n") % (t[0] + 1, t[1] + 1, t[2] + 1))
+    stl_a, stl_b = tmp_path / "ascii.stl", tmp_path / "binary.stl"
+    with open(stl_a, "w") as f:
+        f.write("solid test\n")
+        for t in tris:
+            f.write("facet normal 0 0 1\nouter loop\n")
+            for k in t[:3]:
+                f.write("vertex %.9g %.9g %.9g\n" % tuple(verts[k]))
+            f.write("endloop\nendfacet\n")
+        f.write("endsolid test\n")
+    with open(stl_b, "wb") as f:
+        f.write(b"binary stl".ljust(80, b" "))
+        f.write(struct.pack("<i", len(tris)))
+        for t in tris:
+            f.write(struct.pack("<3f", 0, 0, 1))
+            for k in t[:3]:
+                f.write(struct.pack("<3f", *[float(c) for c in verts[k]]))
+            f.write(struct.pack("<H", 0))
+    return obj_n, obj_p, stl_a, stl_b
+
+
+def test_mesh_importers_match_reference_importers(api, reference, tmp_path):
+    """source_b200.import_obj / import_stl against raysect.primitive.import_obj / import_stl: identical MeshData arrays,
+    identical kd-tree stream (built by this package's SAH builder), identical hits through the host build"""
+    import io
+    import source_b200 as mirror
+    from raysect.primitive import import_obj, import_stl
+    from source_b200.flatten import flatten_world, rsm_kdtree_stream
+    files = _write_mesh_files(tmp_path)
+    for path, ref_imp, our_imp, kw in [(files[0], import_obj, mirror.import_obj, dict(scaling=1.5)),
+                                        (files[1], import_obj, mirror.import_obj, dict(scaling=0.7)),
+                                        (files[2], import_stl, mirror.import_stl, dict(scaling=2.0, mode="ascii")),
+                                        (files[3], import_stl, mirror.import_stl, dict(scaling=2.0)),
+                                        (files[2], import_stl, mirror.import_stl, dict(scaling=1.0, mode="auto"))]:
+        rworld, mworld = api.World(), mirror.World()
+        rm = ref_imp(str(path), parent=rworld, material=api.AbsorbingSurface(), **kw)
+        mm = our_imp(str(path), parent=mworld, material=mirror.AbsorbingSurface(), **kw)
+        np.testing.assert_array_equal(mm.data.vertices, np.array(rm.data.vertices))
+        np.testing.assert_array_equal(mm.data.triangles, np.array(rm.data.triangles))
+        if rm.data.vertex_normals is not None:
+            np.testing.assert_array_equal(mm.data.vertex_normals, np.array(rm.data.vertex_normals))
+        else:
+            assert mm.data.vertex_normals is None
+        assert bool(mm.data.smoothing) == bool(rm.data.smoothing)
+        buf = io.BytesIO()
+        rm.data.save(buf)
+        blob = buf.getvalue()
+        assert bytes(mm.data.kdtree_stream) == blob[rsm_kdtree_stream(blob):]
+        rng = np.random.default_rng(1)
+        o = np.c_[rng.uniform(-0.5, 0.5, 300), rng.uniform(-0.5, 0.5, 300), np.full(300, -3.0)]
+        d = np.c_[rng.uniform(-0.05, 0.05, 300), rng.uniform(-0.05, 0.05, 300), np.ones(300)]
+        ref = reference.oracle_hit(rworld, o, d)
+        be = hostsim_api.HostScene(flatten_world(mworld))
+        r = be.hit_batch(o, d, geometry=True)
+        be.close()
+        np.testing.assert_array_equal(r.primitive, ref["primitive"])
+        np.testing.assert_array_equal(r.distance, ref["distance"])
+        np.testing.assert_array_equal(r.sub[ref["triangle"] >= 0], ref["triangle"][ref["triangle"] >= 0])
+        assert (ref["primitive"] >= 0).sum() > 60
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
