@@ -113,7 +113,21 @@ def rough_goldens():
     save("rough_16x12_s3_b6_r2_noimp", **r)
 
 
+def scaled_goldens():
+    """anisotropic scale + shear on every primitive type, a CSG tree and a mesh: hits, contains, a rendered frame"""
+    world = scenes.scaled_scene(api)
+    o, d = scenes.zoo_rays(4000, seed=21)
+    g = hits(world, o, d)
+    pts = np.random.default_rng(8).uniform([-2.6, -1.5, -1.2], [2.6, 2.9, 1.2], (3000, 3))
+    cc, cp = harness.oracle_contains(world, pts)
+    cam, r = render(world, dict(pixels=(20, 16), samples=3, bins=6, path_weight=0.3), 5150)
+    save("scaled_hits_and_frame", **g, contains_count=cc, contains_prims=cp, **r)
+    print("scaled scene: hits %d of %d, points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (cc > 0).sum()))
+
+
 def main():
+    if "--scaled-only" in sys.argv:
+        return scaled_goldens()
     if "--rough-only" in sys.argv:
         return rough_goldens()
     if "--ortho-only" in sys.argv:
@@ -184,6 +198,7 @@ def main():
     volume_goldens()
     ortho_goldens()
     rough_goldens()
+    scaled_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

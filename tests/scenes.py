@@ -218,6 +218,31 @@ def edge_scene(api):
     return world
 
 
+def scaled_scene(api):
+    """Non-rigid transforms (anisotropic scale and shear): ray directions are transformed without renormalisation
+    (core/ray.pxd), normals through the inverse transpose (normal.pyx:222-248), bounding boxes from the 8 transformed
+    corners -- every primitive type, a CSG tree and a mesh under AffineMatrix3D matrices that are not rotations."""
+    a = api
+    world = a.World()
+    lam = a.Lambert(a.ConstantSF(0.6))
+
+    def M(sx, sy, sz, shear=0.0):
+        return a.AffineMatrix3D([[sx, shear, 0, 0], [0, sy, 0.5 * shear, 0], [0, 0, sz, 0], [0, 0, 0, 1]])
+    a.Sphere(0.5, world, a.translate(-1.6, 0.4, 0.2) * a.rotate(10, 20, 30) * M(1.6, 0.5, 1.0, 0.3), lam)
+    a.Box(a.Point3D(-0.4, -0.3, -0.2), a.Point3D(0.5, 0.6, 0.7), world, a.translate(-0.4, -0.3, 0.1) * M(0.7, 1.4, 0.9, -0.4) * a.rotate(25, -15, 40), lam)
+    a.Cylinder(0.35, 1.1, world, a.translate(0.8, -0.6, 0.0) * a.rotate(-35, 60, 5) * M(1.3, 0.6, 0.8), lam)
+    a.Cone(0.45, 0.9, world, a.translate(1.9, -0.4, 0.3) * M(0.5, 1.5, 1.2, 0.2) * a.rotate(15, -70, 0), lam)
+    a.Subtract(a.Box(a.Point3D(-0.4, -0.4, -0.4), a.Point3D(0.4, 0.4, 0.4), transform=M(1.2, 0.8, 1.0, 0.1)),
+               a.Sphere(0.5, transform=a.translate(0.1, 0, 0) * M(0.9, 1.1, 0.7)),
+               world, a.translate(0.5, 1.3, 0.0) * a.rotate(40, 20, -10) * M(1.4, 0.7, 1.1, 0.25), lam)
+    verts, tris, normals = icosphere(2, radius=0.4, bumps=0.15)
+    a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=world,
+           transform=a.translate(-1.2, 1.4, 0.1) * M(1.5, 0.6, 1.0, -0.3) * a.rotate(20, 35, 10), material=lam)
+    a.Box(a.Point3D(-3, -0.05, -3), a.Point3D(3, 0, 3), world, a.translate(0, -1.4, 0), lam)
+    a.Sphere(0.3, world, a.translate(0.2, 2.6, -1.0) * M(2.0, 0.4, 2.0), a.UniformSurfaceEmitter(a.ConstantSF(1.0), 3.0))
+    return world
+
+
 def edge_rays():
     """(origins, directions, max_distance) of hand-placed rays: see edge_scene"""
     inf = np.inf

@@ -28,6 +28,10 @@ def test_edge_cases(make_backend):
     parity.edge(make_backend)
 
 
+def test_non_rigid_transforms(make_backend):
+    parity.scaled(make_backend, exact=True)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 

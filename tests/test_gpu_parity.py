@@ -34,6 +34,10 @@ def test_edge_cases(make_backend):
     parity.edge(make_backend)
 
 
+def test_non_rigid_transforms(make_backend):
+    parity.scaled(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 
