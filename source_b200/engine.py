@@ -234,13 +234,18 @@ def ray_config(bins, min_wavelength, max_wavelength, extinction_prob=0.1, extinc
         raise ValueError("Minimum wavelength must be less than the maximum wavelength.")
     if important_path_weight < 0 or important_path_weight > 1.0:
         raise ValueError("Important path weight must be in the range [0, 1].")
+    # optical Ray property setters, ray.pyx:274-292
+    if extinction_min_depth < 1:
+        raise ValueError("The minimum extinction depth cannot be less than 1.")
+    if max_depth < extinction_min_depth:
+        raise ValueError("The maximum depth cannot be less than the minimum depth.")
     c = cabi.RsbRayConfig()
     c.bins = int(bins)
     c.extinction_min_depth = int(extinction_min_depth)
     c.max_depth = int(max_depth)
     c.importance_sampling = int(bool(importance_sampling))
     c.min_wavelength, c.max_wavelength = float(min_wavelength), float(max_wavelength)
-    c.extinction_prob = float(extinction_prob)
+    c.extinction_prob = min(max(float(extinction_prob), 0.0), 1.0)    # clamp(extinction_prob, 0, 1), ray.pyx:262
     c.important_path_weight = float(important_path_weight)
     c.max_distance = float(max_distance)
     return c

@@ -125,7 +125,34 @@ def scaled_goldens():
     print("scaled scene: hits %d of %d, points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (cc > 0).sum()))
 
 
+def extremes_goldens():
+    """corners of the ray / camera configuration space"""
+    out = {}
+    # A: roulette from the first daughter on (min depth 1, the smallest legal value), hard depth limit 3, wide fov,
+    #    sensitivity != 1, tall frame
+    world = scenes.cornell_box(api)
+    cam, r = render(world, dict(pixels=(10, 14), samples=4, bins=5, min_depth=1, max_depth=3, extinction=0.3, fov=70.0,
+                                sensitivity=2.5), 1)
+    out.update({"a_" + k: v for k, v in r.items()})
+    # B: only important paths (weight 1.0) with unequal importances (light 5, glass box 2, glass sphere 0)
+    world = scenes.cornell_box(api)
+    for p, imp in zip(world.primitives[-3:], (5.0, 2.0, 0.0)):
+        p.material.importance = imp
+    cam, r = render(world, dict(pixels=(12, 10), samples=4, bins=5, path_weight=1.0), 2)
+    out.update({"b_" + k: v for k, v in r.items()})
+    # C: never the important path (weight 0.0, MIS pdf still evaluated), camera INSIDE the glass sphere
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(10, 10), samples=4, bins=5, path_weight=0.0)
+    cam.transform = api.translate(-0.4, -0.6, -0.45) * api.rotate(20, 10, 0)
+    mean, var, n = harness.oracle_render(cam, pipe, 3)
+    out.update(c_mean=mean, c_variance=var, c_samples=n)
+    save("cornell_extremes", **out)
+    print("light is primitive", [type(p.material).__name__ for p in world.primitives[-3:]])
+
+
 def main():
+    if "--extremes-only" in sys.argv:
+        return extremes_goldens()
     if "--scaled-only" in sys.argv:
         return scaled_goldens()
     if "--rough-only" in sys.argv:
@@ -199,6 +226,7 @@ def main():
     ortho_goldens()
     rough_goldens()
     scaled_goldens()
+    extremes_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

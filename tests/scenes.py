@@ -109,7 +109,7 @@ def volume_scene(api, fog=True):
 
 
 def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_rays=1, min_depth=3, max_depth=500,
-                   extinction=0.01, path_weight=0.25, importance=True):
+                   extinction=0.01, path_weight=0.25, importance=True, fov=None, sensitivity=None):
     """Camera of demos/cornell_box.py:147-156 with a SpectralPowerPipeline2D and a full-frame sampler."""
     a = api
     pipeline = a.SpectralPowerPipeline2D()
@@ -124,6 +124,10 @@ def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_r
     camera.ray_extinction_min_depth = min_depth
     camera.ray_extinction_prob = extinction
     camera.quiet = True
+    if fov is not None:
+        camera.fov = fov
+    if sensitivity is not None:
+        camera.sensitivity = sensitivity
     return camera, pipeline
 
 

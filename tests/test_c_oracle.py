@@ -32,6 +32,10 @@ def test_non_rigid_transforms(make_backend):
     parity.scaled(make_backend, exact=True)
 
 
+def test_configuration_extremes(make_backend):
+    parity.extremes(make_backend, exact=True)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 
