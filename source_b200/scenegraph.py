@@ -352,6 +352,30 @@ class MeshData:
         length = np.sqrt(cx * cx + cy * cy + cz * cz)
         return triangles[length != 0.0]
 
+    def save(self, file):
+        """mesh.pyx:864-931 (MeshData.save): the Raysect mesh file (.rsm) -- "RSM", version 1.0, smoothing / closed /
+        has-kdtree flags, counts, vertices f32, vertex normals f32, triangles i32, then the kd-tree stream
+        (kdtree3d.pyx:864-912).  ``file`` is a binary stream or a file name.  Byte-identical to what Raysect writes
+        for the same mesh (tests/test_plugin_host.py)."""
+        import io
+        import struct
+        close = False
+        if not isinstance(file, io.IOBase):
+            file = open(file, mode="wb")
+            close = True
+        nn = 0 if self.vertex_normals is None else self.vertex_normals.shape[0]
+        file.write(b"RSM")
+        file.write(struct.pack("<BB", 1, 0))
+        file.write(struct.pack("<???", self.smoothing, self.closed, True))
+        file.write(struct.pack("<iii", self.vertices.shape[0], nn, self.triangles.shape[0]))
+        file.write(np.ascontiguousarray(self.vertices, dtype="<f4").tobytes())
+        if nn:
+            file.write(np.ascontiguousarray(self.vertex_normals, dtype="<f4").tobytes())
+        file.write(np.ascontiguousarray(self.triangles, dtype="<i4").tobytes())
+        file.write(bytes(self.kdtree_stream))
+        if close:
+            file.close()
+
     @classmethod
     def from_rsm(cls, blob):
         """mesh.pyx:933-1024: load arrays + kd-tree from a Raysect mesh (.rsm) blob"""
@@ -389,6 +413,21 @@ class Mesh(Primitive):
 
     def instance(self, parent=None, transform=None, material=None, name=None):
         return Mesh(data=self.data, parent=parent, transform=transform, material=material, name=name)
+
+    def save(self, file):
+        """Mesh.save (mesh.pyx:1310-1327): write the mesh and its kd-tree as a .rsm file"""
+        self.data.save(file)
+
+    @classmethod
+    def from_file(cls, file, parent=None, transform=None, material=None, name=None):
+        """Mesh.from_file (mesh.pyx:1343-1370): a mesh from a .rsm file or stream -- the kd-tree comes with it, nothing
+        is rebuilt"""
+        if hasattr(file, "read"):
+            blob = file.read()
+        else:
+            with open(file, "rb") as f:
+                blob = f.read()
+        return cls(data=MeshData.from_rsm(blob), parent=parent, transform=transform, material=material, name=name)
 
     def bounding_box(self):
         """mesh.pyx:835-858: every vertex -> world (float32 -> float64), padded extend"""

@@ -311,6 +311,13 @@ def test_mesh_importers_match_reference_importers(api, reference, tmp_path):
         rm.data.save(buf)
         blob = buf.getvalue()
         assert bytes(mm.data.kdtree_stream) == blob[rsm_kdtree_stream(blob):]
+        # .rsm writer: the whole file byte for byte, and the mirror reads back what Raysect wrote
+        out = io.BytesIO()
+        mm.save(out)
+        assert out.getvalue() == blob
+        back = mirror.Mesh.from_file(io.BytesIO(blob), parent=None)
+        np.testing.assert_array_equal(back.data.triangles, mm.data.triangles)
+        assert bytes(back.data.kdtree_stream) == bytes(mm.data.kdtree_stream)
         rng = np.random.default_rng(1)
         o = np.c_[rng.uniform(-0.5, 0.5, 300), rng.uniform(-0.5, 0.5, 300), np.full(300, -3.0)]
         d = np.c_[rng.uniform(-0.05, 0.05, 300), rng.uniform(-0.05, 0.05, 300), np.ones(300)]
