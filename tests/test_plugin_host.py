@@ -360,3 +360,56 @@ def test_unsupported_objects_fail_loudly(api):
     world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
     with pytest.raises(NotImplementedError):
         world.build_accelerator(force=True)
+
+
+def test_mirror_object_model_against_live_reference_on_random_inputs(api, reference):
+    """The stand-alone mirror (math3d, scenegraph bounding volumes, spectral functions) against Raysect's own classes on
+    seeded random inputs -- everything the flattener feeds to the device must be bit-identical on both object models."""
+    import source_b200 as mirror
+    rng = np.random.default_rng(2025)
+
+    def mat(m):
+        return np.array([[m[i, j] for j in range(4)] for i in range(4)])
+    for _ in range(40):
+        yaw, pitch, roll = rng.uniform(-180, 180, 3)
+        t = rng.uniform(-3, 3, 3)
+        sc = rng.uniform(0.3, 2.0, 3)
+        sh = rng.uniform(-0.4, 0.4)
+
+        def build(a):
+            m = a.AffineMatrix3D([[sc[0], sh, 0, 0], [0, sc[1], 0.5 * sh, 0], [0, 0, sc[2], 0], [0, 0, 0, 1]])
+            return a.translate(*t) * a.rotate(yaw, pitch, roll) * m * a.rotate_x(roll) * a.rotate_y(yaw) * a.rotate_z(pitch)
+        mr, mm = build(api), build(mirror)
+        np.testing.assert_array_equal(mat(mm), mat(mr))
+        np.testing.assert_array_equal(mat(mm.inverse()), mat(mr.inverse()))
+        world_r, world_m = api.World(), mirror.World()
+        node_r = api.Node(world_r, api.translate(*rng.uniform(-1, 1, 3)) * api.rotate(*rng.uniform(-90, 90, 3)))
+        node_m = mirror.Node(world_m, mirror.AffineMatrix3D(mat(node_r.transform).tolist()))
+        r, h = rng.uniform(0.1, 1.5, 2)
+        lo, hi = rng.uniform(-1, 0, 3), rng.uniform(0, 1, 3)
+        shapes = []
+        for a, node, m in ((api, node_r, mr), (mirror, node_m, mm)):
+            shapes.append([a.Sphere(r, node, m), a.Box(a.Point3D(*lo), a.Point3D(*hi), node, m), a.Cylinder(r, h, node, m),
+                           a.Cone(r, h, node, m),
+                           a.Intersect(a.Sphere(r, transform=a.translate(0.1, 0, 0)), a.Box(a.Point3D(*lo), a.Point3D(*hi)), node, m)])
+        for pr, pm in zip(*shapes):
+            np.testing.assert_array_equal(mat(pm.to_root()), mat(pr.to_root()))
+            np.testing.assert_array_equal(mat(pm.to_local()), mat(pr.to_local()))
+            br, bm = pr.bounding_box(), pm.bounding_box()
+            assert (bm.lower.x, bm.lower.y, bm.lower.z, bm.upper.x, bm.upper.y, bm.upper.z) == \
+                   (br.lower.x, br.lower.y, br.lower.z, br.upper.x, br.upper.y, br.upper.z)
+            sr, sm = pr.bounding_sphere(), pm.bounding_sphere()
+            assert (sm.centre.x, sm.centre.y, sm.centre.z, sm.radius) == (sr.centre.x, sr.centre.y, sr.centre.z, sr.radius)
+    # spectral functions: bin averages over random ranges, inside / across / outside the tabulated range
+    w = np.sort(rng.uniform(300, 800, 25))
+    v = rng.uniform(0, 2, 25)
+    fr, fm = api.InterpolatedSF(w, v), mirror.InterpolatedSF(w, v)
+    gr, gm = api.schott("N-BK7"), mirror.schott("N-BK7")
+    for _ in range(60):
+        a0 = rng.uniform(250, 820)
+        a1 = a0 + rng.uniform(0.01, 400)
+        bins = int(rng.integers(1, 40))
+        np.testing.assert_array_equal(np.asarray(fm.sample(a0, a1, bins)), np.asarray(fr.sample(a0, a1, bins)))
+        assert fm.average(a0, a1) == fr.average(a0, a1)
+        np.testing.assert_array_equal(np.asarray(gm.transmission.sample(a0, a1, bins)), np.asarray(gr.transmission.sample(a0, a1, bins)))
+        assert gm.index.average(a0, a1) == gr.index.average(a0, a1)
