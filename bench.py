@@ -88,7 +88,7 @@ def run_reference(args):
     sample = "cornell_box %dx%d x %d spp (one observe() pass) x %d bins, MulticoreEngine(%d)" % (
         s["pixels"], s["pixels"], s["spp"], s["bins"], cores)
     line = {
-        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": 0, "steps": args.steps,
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, len(times)), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], "sample": sample},
