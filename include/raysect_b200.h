@@ -30,7 +30,7 @@ extern "C" {
 #define RSB_ERR_UNSUPPORTED 3
 #define RSB_ERR_OVERFLOW 4
 
-/* primitive rows: raysect/primitive/{sphere,box,cylinder,cone,csg}.pyx, raysect/primitive/mesh/mesh.pyx */
+/* primitive rows: raysect/primitive/{sphere,box,cylinder,cone,parabola,csg}.pyx, raysect/primitive/mesh/mesh.pyx */
 #define RSB_PRIM_SPHERE 0
 #define RSB_PRIM_BOX 1
 #define RSB_PRIM_CYLINDER 2
@@ -39,6 +39,8 @@ extern "C" {
 #define RSB_PRIM_UNION 5
 #define RSB_PRIM_INTERSECT 6
 #define RSB_PRIM_SUBTRACT 7
+#define RSB_PRIM_PARABOLA (-1) /* raysect/primitive/parabola.pyx; params: radius, height.  (Analytic primitives are the
+                                  types <= RSB_PRIM_CONE, meshes 4, CSG operators >= 5: the new analytic type takes -1.) */
 
 /* materials: raysect/optical/material/{absorber,lambert,dielectric,conductor}.pyx, emitter/{uniform,unity}.pyx */
 #define RSB_MAT_ABSORBER 0
@@ -84,7 +86,7 @@ typedef struct RsbSceneDesc {
     const int32_t* prim_child_b;
     const int32_t* prim_mesh;       /* mesh row, else -1 */
     const int32_t* prim_parent;     /* enclosing CSG row, -1 for world-level primitives */
-    const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone r,h */
+    const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone/parabola r,h */
     const double* prim_to_local;    /* [n][12] rows 0..2 of Node.to_local() (parent space -> local) */
     const double* prim_to_root;     /* [n][12] rows 0..2 of Node.to_root() */
     const double* prim_root_inv;    /* [n][12] rows 0..2 of to_root().inverse() (Normal3D.transform, normal.pyx:241) */

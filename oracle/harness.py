@@ -38,7 +38,7 @@ def ref_api():
     from raysect.optical.material import (AbsorbingSurface, Conductor, Dielectric, Lambert, RoughConductor, Sellmeier,
                                           UniformSurfaceEmitter, UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter)
     from raysect.optical.observer import FullFrameSampler2D, OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D
-    from raysect.primitive import Box, Cone, Cylinder, Intersect, Mesh, Sphere, Subtract, Union
+    from raysect.primitive import Box, Cone, Cylinder, Intersect, Mesh, Parabola, Sphere, Subtract, Union
     ns = types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "ns"})
     ns.Ray = CoreRay
     return ns

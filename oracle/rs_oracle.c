@@ -273,8 +273,22 @@ static void cone_gen(scene_t* s, int id, v3 o, v3 d, double t, int code, isect* 
     } else in = V(x, y, z);
     finish(it, s, id, t, d, h, in, V(h.x + 1e-9 * n.x, h.y + 1e-9 * n.y, h.z + 1e-9 * n.z), n, dot3(d, n) >= 0.0);
 }
+/* parabola.pyx:270-342; code 0 parabola, 1 base */
+static void parabola_gen(scene_t* s, int id, v3 o, v3 d, double t, int code, isect* it) {
+    const double* q = P_params(s, id);
+    double radius = q[0], height = q[1];
+    v3 h = V(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z), n;
+    if (code == 1) n = V(0, 0, -1);
+    else { double k = 2 * height / (radius * radius); n = norm3(V(k * h.x, k * h.y, 1)); }
+    double x = h.x, y = h.y, z = h.z, inner_r = radius - 1e-9, hr2 = h.x * h.x + h.y * h.y;   /* _interior_point */
+    if (hr2 > inner_r * inner_r) { double sc = inner_r / sqrt(hr2); x = sc * h.x; y = sc * h.y; }
+    if (h.z < 1e-9) z = 1e-9;
+    else { x = h.x - n.x * 1e-9; y = h.y - n.y * 1e-9; z = h.z - n.z * 1e-9; }
+    finish(it, s, id, t, d, h, V(x, y, z), V(h.x + 1e-9 * n.x, h.y + 1e-9 * n.y, h.z + 1e-9 * n.z), n, dot3(d, n) >= 0.0);
+}
 static void analytic_gen(scene_t* s, int id, v3 o, v3 d, double t, int code, isect* it) {
     switch (s->d->prim_type[id]) {
+        case RSB_PRIM_PARABOLA: parabola_gen(s, id, o, d, t, code, it); break;
         case RSB_PRIM_SPHERE: sphere_gen(s, id, o, d, t, it); break;
         case RSB_PRIM_BOX: box_gen(s, id, o, d, t, code, it); break;
         case RSB_PRIM_CYLINDER: cyl_gen(s, id, o, d, t, code, it); break;
@@ -359,6 +373,28 @@ static int analytic_hit(ctx_t* c, int id, const ray_t* ray, isect* it) {
             }
             if (nt > ft) return 0;
             return select_hit(c, id, o, d, ray->maxd, nt, nc, ft, fc, it);
+        }
+        case RSB_PRIM_PARABOLA: {                               /* parabola.pyx:141-257 */
+            double radius = q[0], height = q[1], k = height / (radius * radius); int y0, y1;
+            double a = k * (d.x * d.x + d.y * d.y);
+            double b = 2 * k * (d.x * o.x + d.y * o.y) + d.z;
+            double cc = k * (o.x * o.x + o.y * o.y) - (height - o.z);
+            if (!solve_quadratic(a, b, cc, &t0, &t1)) return 0;
+            if (t0 == t1) {
+                t0 = -b / (2.0 * a); y0 = 0;
+                k = -o.z / d.z;
+                double ex = o.x + k * d.x;
+                double r2 = ex * ex + (o.y + k * (d.y * d.y));       /* parabola.pyx:184, `**2` placement as written */
+                if (r2 <= radius * radius) { t1 = k; y1 = 1; } else { t1 = t0; y1 = y0; }
+            } else {
+                int o0 = (o.z + t0 * d.z) < 0, o1 = (o.z + t1 * d.z) < 0;
+                if (o0 && o1) return 0;
+                else if (!o0 && o1) { y0 = 0; t1 = -o.z / d.z; y1 = 1; }
+                else if (o0 && !o1) { y0 = 1; t0 = -o.z / d.z; y1 = 0; }
+                else { y0 = 0; y1 = 0; }
+            }
+            if (t0 > t1) { double tmp = t0; t0 = t1; t1 = tmp; int ti = y0; y0 = y1; y1 = ti; }
+            return select_hit(c, id, o, d, ray->maxd, t0, y0, t1, y1, it);
         }
         default: {                                              /* cone.pyx:142-262 */
             double radius = q[0], height = q[1], k = radius / height; int y0, y1;
@@ -641,6 +677,9 @@ static int prim_contains(ctx_t* c, int id, v3 p) {
             if (l.z < q[2] || l.z > q[5]) return 0;
             return 1;
         case RSB_PRIM_CYLINDER: return (0.0 <= l.z && l.z <= q[1]) && ((l.x * l.x + l.y * l.y) <= (q[0] * q[0]));
+        case RSB_PRIM_PARABOLA:                                                 /* parabola.pyx:344-363 */
+            if (l.z < 0 || l.z > q[1]) return 0;
+            return sqrt(l.x * l.x + l.y * l.y) <= q[0] * sqrt((q[1] - l.z) / q[1]);
         case RSB_PRIM_CONE: {
             if (l.z < 0 || l.z > q[1]) return 0;
             double pr = l.x * l.x + l.y * l.y, cr = (q[1] - l.z) * q[0] / q[1];

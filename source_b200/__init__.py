@@ -15,8 +15,8 @@ from .math3d import (AffineMatrix3D, BoundingBox3D, BoundingSphere3D, Normal3D, 
 from .spectral import ConstantSF, InterpolatedSF, NumericallyIntegratedSF, Sellmeier, SpectralFunction
 from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Material, RoughConductor, UniformSurfaceEmitter,
                        UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter, schott)
-from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Primitive, Ray, Sphere,
-                         Subtract, Union, World)
+from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Parabola, Primitive, Ray,
+                         Sphere, Subtract, Union, World)
 from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
                        SpectralPowerPipeline2D, SpectralSlice, StatsArray3D)
 from .meshio import import_obj, import_stl

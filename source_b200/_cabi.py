@@ -15,7 +15,9 @@ LIB_PATH = os.environ.get("RSB_LIBRARY") or os.path.join(_HERE, "libraysect_b200
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3, 4
 
+PRIM_PARABOLA = -1
 PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INTERSECT, PRIM_SUBTRACT = range(8)
+PRIM_PARABOLA = -1   # analytic primitives are the types <= PRIM_CONE (include/raysect_b200.h)
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER, MAT_ROUGH_CONDUCTOR = range(7)
 CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC = 0, 1
 RNG_MT19937_64, RNG_PHILOX = 0, 1

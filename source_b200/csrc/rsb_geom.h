@@ -346,8 +346,89 @@ RSB_HD void cone_geometry(const double* params, const V3& o, const V3& d, double
     is->exiting = dot(d, n) >= 0.0;
 }
 
+// raysect/primitive/parabola.pyx:141-257.  Codes: 0 PARABOLA, 1 BASE.  The paraboloid z = height - k (x^2 + y^2),
+// k = height / radius^2, tip at z = height, closed by the base disc at z = 0.
+RSB_HD int parabola_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    double radius = params[0], height = params[1];
+    double k = height / (radius * radius);
+    double a = k * (d.x * d.x + d.y * d.y);
+    double b = 2 * k * (d.x * o.x + d.y * o.y) + d.z;
+    double c = k * (o.x * o.x + o.y * o.y) - (height - o.z);
+    double t0, t1;
+    int t0_type, t1_type;
+    if (!solve_quadratic(a, b, c, &t0, &t1)) return 0;
+    if (t0 == t1) {
+        // parabola.pyx:176-190, with the same `direction.y**2` placement as the cone (:184), reproduced verbatim
+        t0 = -b / (2.0 * a);
+        t0_type = 0;
+        k = -o.z / d.z;
+        double ex = o.x + k * d.x;
+        double r2 = ex * ex + (o.y + k * (d.y * d.y));
+        if (r2 <= (radius * radius)) { t1 = k; t1_type = 1; }
+        else { t1 = t0; t1_type = t0_type; }
+    } else {
+        double t0_z = o.z + t0 * d.z;
+        double t1_z = o.z + t1 * d.z;
+        bool t0_outside = t0_z < 0;
+        bool t1_outside = t1_z < 0;
+        if (t0_outside && t1_outside) return 0;
+        else if (!t0_outside && t1_outside) { t0_type = 0; t1 = -o.z / d.z; t1_type = 1; }
+        else if (t0_outside && !t1_outside) { t0_type = 1; t0 = -o.z / d.z; t1_type = 0; }
+        else { t0_type = 0; t1_type = 0; }
+    }
+    if (t0 > t1) {
+        double tmp = t0; t0 = t1; t1 = tmp;
+        int ti = t0_type; t0_type = t1_type; t1_type = ti;
+    }
+    if (t0 > max_distance || t1 < 0.0) return 0;
+    if (t0 >= 0.0) {
+        out[0].t = t0; out[0].code = t0_type;
+        if (t1 <= max_distance) { out[1].t = t1; out[1].code = t1_type; return 2; }
+        return 1;
+    } else if (t1 <= max_distance) {
+        out[0].t = t1; out[0].code = t1_type;
+        return 1;
+    }
+    return 0;
+}
+
+// raysect/primitive/parabola.pyx:270-342 (_generate_intersection, _interior_point)
+RSB_HD void parabola_geometry(const double* params, const V3& o, const V3& d, double t, int code, Isect* is) {
+    const double EPSILON = 1e-9;
+    double radius = params[0], height = params[1];
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    V3 n;
+    if (code == 1) {
+        n = v3(0, 0, -1);
+    } else {
+        double k = 2 * height / (radius * radius);
+        n = normalise(v3(k * hit.x, k * hit.y, 1));
+    }
+    double x = hit.x, y = hit.y, z = hit.z;
+    double inner_radius = radius - EPSILON;
+    double hit_radius_sqr = hit.x * hit.x + hit.y * hit.y;
+    if (hit_radius_sqr > (inner_radius * inner_radius)) {
+        double scale = inner_radius / sqrt(hit_radius_sqr);
+        x = scale * hit.x;
+        y = scale * hit.y;
+    }
+    if (hit.z < EPSILON) {
+        z = EPSILON;
+    } else {
+        x = hit.x - n.x * EPSILON;
+        y = hit.y - n.y * EPSILON;
+        z = hit.z - n.z * EPSILON;
+    }
+    is->hit = hit;
+    is->normal = n;
+    is->inside = v3(x, y, z);
+    is->outside = v3(hit.x + EPSILON * n.x, hit.y + EPSILON * n.y, hit.z + EPSILON * n.z);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
 RSB_HD int analytic_crossings(int type, const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
     switch (type) {
+        case PRIM_PARABOLA: return parabola_crossings(params, o, d, max_distance, out);
         case PRIM_SPHERE: return sphere_crossings(params, o, d, max_distance, out);
         case PRIM_BOX: return box_crossings(params, o, d, max_distance, out);
         case PRIM_CYLINDER: return cylinder_crossings(params, o, d, max_distance, out);
@@ -361,6 +442,7 @@ RSB_HD void analytic_geometry(int type, const double* params, const V3& o, const
         case PRIM_SPHERE: sphere_geometry(o, d, t, is); break;
         case PRIM_BOX: box_geometry(params, o, d, t, code, is); break;
         case PRIM_CYLINDER: cylinder_geometry(params, o, d, t, code, is); break;
+        case PRIM_PARABOLA: parabola_geometry(params, o, d, t, code, is); break;
         default: cone_geometry(params, o, d, t, code, is); break;
     }
 }
@@ -382,6 +464,13 @@ RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
         case PRIM_CYLINDER: {
             bool slab = (0.0 <= p.z) && (p.z <= params[1]);
             return slab && ((p.x * p.x + p.y * p.y) <= (params[0] * params[0]));
+        }
+        case PRIM_PARABOLA: {   // parabola.pyx:344-363
+            double radius = params[0], height = params[1];
+            if (p.z < 0 || p.z > height) return false;
+            double parabola_radius = radius * sqrt((height - p.z) / height);
+            double point_radius = sqrt(p.x * p.x + p.y * p.y);
+            return point_radius <= parabola_radius;
         }
         case PRIM_CONE: {
             double radius = params[0], height = params[1];

@@ -17,6 +17,7 @@ enum PrimType : int32_t {
     PRIM_SPHERE = 0,
     PRIM_BOX = 1,
     PRIM_CYLINDER = 2,
+    PRIM_PARABOLA = -1,   // raysect/primitive/parabola.pyx (analytic primitives are the types <= PRIM_CONE)
     PRIM_CONE = 3,
     PRIM_MESH = 4,
     PRIM_UNION = 5,

@@ -45,7 +45,7 @@ int pack_scene(const RsbSceneDesc* d, PackedScene* out, std::string* err) {
     }
     for (int i = 0; i < d->n_primitives; ++i) {
         int t = d->prim_type[i];
-        if (t < RSB_PRIM_SPHERE || t > RSB_PRIM_SUBTRACT) { *err = "unsupported primitive type in row " + std::to_string(i); return RSB_ERR_UNSUPPORTED; }
+        if (t < RSB_PRIM_PARABOLA || t > RSB_PRIM_SUBTRACT) { *err = "unsupported primitive type in row " + std::to_string(i); return RSB_ERR_UNSUPPORTED; }
         if (t == RSB_PRIM_MESH && (d->prim_mesh[i] < 0 || d->prim_mesh[i] >= d->n_meshes)) { *err = "mesh row out of range"; return RSB_ERR_ARG; }
         if (i < d->n_world && (d->prim_material[i] < 0 || d->prim_material[i] >= d->n_materials)) {
             *err = "material row out of range for primitive " + std::to_string(i);

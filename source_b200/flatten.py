@@ -22,6 +22,7 @@ from . import _cabi as cabi
 
 _SHAPES = {
     "Sphere": cabi.PRIM_SPHERE, "Box": cabi.PRIM_BOX, "Cylinder": cabi.PRIM_CYLINDER, "Cone": cabi.PRIM_CONE,
+    "Parabola": cabi.PRIM_PARABOLA,
     "Mesh": cabi.PRIM_MESH, "Union": cabi.PRIM_UNION, "Intersect": cabi.PRIM_INTERSECT, "Subtract": cabi.PRIM_SUBTRACT,
 }
 _MATERIALS = {
@@ -47,7 +48,20 @@ def _classify(obj, table, what):
         % (what, type(obj).__name__, ", ".join(sorted(table))))
 
 
+_warned_w = [False]
+
+
 def mat34(m):
+    """Rows 0..2 of an AffineMatrix3D.  The device transforms points with these rows only; Raysect's Point3D.transform
+    also divides by w = m30 x + m31 y + m32 z + m33 (point.pyx:272-281).  For an affine matrix w is exactly 1, but
+    AffineMatrix3D.inverse() of a non-rigid transform can leave m33 one ulp off 1.0: hit distances then deviate from
+    Raysect's by a few ulp (primitive ids do not).  Warn once; see DESIGN.md section 8."""
+    bottom = [float(m[3, j]) for j in range(4)]
+    if bottom != [0.0, 0.0, 0.0, 1.0] and not _warned_w[0]:
+        import warnings
+        _warned_w[0] = True
+        warnings.warn("a primitive transform is not exactly affine (bottom row %r): the B200 path ignores the homogeneous "
+                      "divide, so intersection distances may differ from Raysect's in the last few ulp" % (bottom,))
     return [float(m[i, j]) for i in range(3) for j in range(4)]
 
 
@@ -211,7 +225,7 @@ def flatten_world(world, world_kdtree=None):
             row["params"][0] = p.radius
         elif t == cabi.PRIM_BOX:
             row["params"] = [p.lower.x, p.lower.y, p.lower.z, p.upper.x, p.upper.y, p.upper.z]
-        elif t in (cabi.PRIM_CYLINDER, cabi.PRIM_CONE):
+        elif t in (cabi.PRIM_CYLINDER, cabi.PRIM_CONE, cabi.PRIM_PARABOLA):
             row["params"][0] = p.radius
             row["params"][1] = p.height
         elif t == cabi.PRIM_MESH:

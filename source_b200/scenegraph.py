@@ -218,6 +218,11 @@ class Cone(_RadiusHeight):
     _what = "Cone"
 
 
+class Parabola(_RadiusHeight):
+    """raysect/primitive/parabola.pyx: paraboloid of revolution, tip at z = height, base disc of ``radius`` at z = 0"""
+    _what = "Parabola"
+
+
 class CSGRoot(Node):
     """raysect/primitive/csg.pyx:258-287: root of the operand sub-graph; operands live in CSG-local space"""
 

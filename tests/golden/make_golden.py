@@ -32,7 +32,17 @@ def save(name, **arrays):
     print("%-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
 
 
+def assert_affine(world):
+    """The device path carries rows 0..2 of every transform (RsbSceneDesc): AffineMatrix3D.inverse() can leave m33 one
+    ulp off 1.0, and Point3D.transform then divides by w (point.pyx:272-281) -- a documented limitation (DESIGN.md
+    section 8: t deviates by a few ulp, ids do not); the golden scenes stay on exactly affine matrices."""
+    for p in world.primitives:
+        for m in (p.to_local(), p.to_root()):
+            assert [m[3, j] for j in range(4)] == [0.0, 0.0, 0.0, 1.0], (type(p).__name__, [m[3, j] for j in range(4)])
+
+
 def hits(world, o, d, md=None):
+    assert_affine(world)
     r = harness.oracle_hit(world, o, d, md)
     stream = harness.world_kdtree_stream(world)
     return dict(primitive=r["primitive"], distance=r["distance"], exiting=r["exiting"], geometry=r["geometry"],
@@ -150,7 +160,20 @@ def extremes_goldens():
     print("light is primitive", [type(p.material).__name__ for p in world.primitives[-3:]])
 
 
+def parabola_goldens():
+    world = scenes.parabola_scene(api)
+    o, d = scenes.parabola_rays()
+    g = hits(world, o, d)
+    pts = np.random.default_rng(9).uniform([-2.0, -1.3, -1.0], [2.0, 1.9, 1.0], (3000, 3))
+    cc, cp = harness.oracle_contains(world, pts)
+    cam, r = render(world, dict(pixels=(20, 16), samples=3, bins=5, path_weight=0.3), 8080)
+    save("parabola_hits_and_frame", **g, contains_count=cc, contains_prims=cp, **r)
+    print("parabola scene: hits %d of %d, points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (cc > 0).sum()))
+
+
 def main():
+    if "--parabola-only" in sys.argv:
+        return parabola_goldens()
     if "--extremes-only" in sys.argv:
         return extremes_goldens()
     if "--scaled-only" in sys.argv:
@@ -227,6 +250,7 @@ def main():
     rough_goldens()
     scaled_goldens()
     extremes_goldens()
+    parabola_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

@@ -247,6 +247,35 @@ def scaled_scene(api):
     return world
 
 
+def parabola_scene(api):
+    """Parabola primitives: rotated, non-rigidly scaled, as CSG operands, next to a lit Lambert floor"""
+    a = api
+    world = a.World()
+    lam = a.Lambert(a.ConstantSF(0.7))
+    a.Parabola(0.5, 1.0, world, a.translate(-1.2, -0.4, 0.1) * a.rotate(20, -60, 10), lam)
+    a.Parabola(0.3, 0.6, world, a.translate(0.0, -0.5, 0.0) * a.rotate(0, -90, 0)
+               * a.AffineMatrix3D([[1.25, 0.25, 0, 0], [0, 0.75, 0, 0], [0, 0, 1.5, 0], [0, 0, 0, 1]]), lam)
+    a.Subtract(a.Parabola(0.5, 0.9), a.Parabola(0.4, 0.7, transform=a.translate(0, 0, -0.05)),
+               world, a.translate(1.2, -0.5, 0.2) * a.rotate(-30, -75, 0), lam)                      # a parabolic dish
+    a.Intersect(a.Parabola(0.6, 1.2), a.Box(a.Point3D(-0.3, -1, 0.1), a.Point3D(0.3, 1, 1.0)),
+                world, a.translate(0.0, 0.9, 0.0) * a.rotate(40, -100, 20), lam)
+    a.Parabola(0.5, 1.0, world, a.translate(-1.2, 1.0, 0.0), lam)                                    # unrotated: exact axis rays
+    a.Box(a.Point3D(-3, -0.05, -3), a.Point3D(3, 0, 3), world, a.translate(0, -1.2, 0), lam)
+    a.Sphere(0.3, world, a.translate(0.3, 2.4, -1.2), a.UniformSurfaceEmitter(a.ConstantSF(1.0), 4.0))
+    return world
+
+
+def parabola_rays(n=3000):
+    o, d = zoo_rays(n, seed=33)
+    # exact rays for the unrotated parabola at (-1.2, 1.0, 0): along the axis through the tip (t0 == t1 branch), in the
+    # base plane, tangent to the rim, from inside
+    extra_o = np.array([[-1.2, 1.0, -3], [-1.2, 1.0, 3], [-1.2, 1.0, 0.5], [-3, 1.0, 0.0], [-3, 1.5, 0.0], [-1.2, 1.0, 1.0],
+                        [-0.95, 1.0, -2], [-1.2, 1.0, 0.0], [-3, 1.0, 1.0], [-1.2, 1.25, 0.75]], dtype=float)
+    extra_d = np.array([[0, 0, 1], [0, 0, -1], [0, 0, 1], [1, 0, 0], [1, 0, 0], [0, 0, 1],
+                        [0, 0, 1], [1, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=float)
+    return np.ascontiguousarray(np.r_[o, extra_o]), np.ascontiguousarray(np.r_[d, extra_d])
+
+
 def edge_rays():
     """(origins, directions, max_distance) of hand-placed rays: see edge_scene"""
     inf = np.inf

@@ -36,6 +36,10 @@ def test_configuration_extremes(make_backend):
     parity.extremes(make_backend, exact=True)
 
 
+def test_parabola_primitive(make_backend):
+    parity.parabola(make_backend, exact=True)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 

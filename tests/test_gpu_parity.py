@@ -42,6 +42,10 @@ def test_configuration_extremes(make_backend):
     parity.extremes(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.03)
 
 
+def test_parabola_primitive(make_backend):
+    parity.parabola(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.02)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 
