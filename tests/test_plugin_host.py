@@ -413,3 +413,13 @@ def test_mirror_object_model_against_live_reference_on_random_inputs(api, refere
         assert fm.average(a0, a1) == fr.average(a0, a1)
         np.testing.assert_array_equal(np.asarray(gm.transmission.sample(a0, a1, bins)), np.asarray(gr.transmission.sample(a0, a1, bins)))
         assert gm.index.average(a0, a1) == gr.index.average(a0, a1)
+
+
+def test_accelerator_on_an_empty_world(api):
+    """World() without primitives: Raysect's own accelerator answers None / []; so does the plugin"""
+    from raysect.core import Point3D, Vector3D
+    from source_b200.plugin import CudaAccelerator
+    world = api.World()
+    world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
+    assert world.hit(api.Ray(Point3D(0, 0, -3), Vector3D(0, 0, 1))) is None
+    assert world.contains(Point3D(0, 0, 0)) == []
