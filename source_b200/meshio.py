@@ -12,41 +12,38 @@ from .math3d import Normal3D
 from .scenegraph import Mesh
 
 
-def _parse_face_token(token):
-    """obj.py:128-142: ``v``, ``v/vt`` or ``v/vt/vn`` (1-based)"""
-    indices = token.split("/")
-    if len(indices) in (1, 2):
-        return int(indices[0]) - 1, None
-    if len(indices) == 3:
-        return int(indices[0]) - 1, int(indices[2]) - 1
-    raise ValueError("The .obj contains an invalid face definition.")
+def _face_indices(token):
+    """one corner of an OBJ face, ``v``, ``v/vt`` or ``v/vt/vn`` (1-based in the file): (vertex, normal or None)"""
+    parts = token.split("/")
+    if not 1 <= len(parts) <= 3:
+        raise ValueError("The .obj contains an invalid face definition.")
+    return int(parts[0]) - 1, (int(parts[2]) - 1 if len(parts) == 3 else None)
 
 
 def import_obj(filename, scaling=1.0, **kwargs):
-    """OBJHandler.import_obj (raysect/primitive/mesh/obj.py:38-95): vertices scaled by ``scaling``, vertex normals
-    normalised in double precision, triangular faces only, texture coordinates ignored."""
-    vertices, normals, triangles = [], [], []
+    """Wavefront OBJ -> Mesh with the semantics of the reference importer (raysect/primitive/mesh/obj.py:38-142):
+    ``v`` records scaled by ``scaling``, ``vn`` records normalised in double precision, ``vt`` ignored, triangular
+    ``f`` records only; a face carries normal indices only when all three corners name one."""
+    records = {"v": [], "vn": [], "f": []}
     with open(filename) as f:
         for line in f:
-            if line[0] == "#":
-                continue
-            tokens = line.strip().split(" ")
-            cmd, tokens = tokens[0], tokens[1:]
-            if cmd == "v":
-                x, y, z = tokens
-                vertices.append([scaling * float(x), scaling * float(y), scaling * float(z)])
-            elif cmd == "vn":
-                x, y, z = tokens
-                n = Normal3D(float(x), float(y), float(z)).normalise()
-                normals.append([n.x, n.y, n.z])
-            elif cmd == "f":
-                if len(tokens) != 3:
-                    raise ValueError("The .obj importer only support meshes containing 3 sided faces (triangles).")
-                (v1, n1), (v2, n2), (v3, n3) = (_parse_face_token(t) for t in tokens)
-                if n1 is None or n2 is None or n3 is None:
-                    triangles.append([v1, v2, v3])
-                else:
-                    triangles.append([v1, v2, v3, n1, n2, n3])
+            fields = line.split()
+            if fields and fields[0] in records:
+                records[fields[0]].append(fields[1:])
+    vertices = scaling * np.array(records["v"], dtype=np.float64).reshape(-1, 3)
+    normals = []
+    for x, y, z in records["vn"]:
+        n = Normal3D(float(x), float(y), float(z)).normalise()
+        normals.append([n.x, n.y, n.z])
+    triangles = []
+    for corners in records["f"]:
+        if len(corners) != 3:
+            raise ValueError("The .obj importer only support meshes containing 3 sided faces (triangles).")
+        idx = [_face_indices(c) for c in corners]
+        row = [v for v, _ in idx]
+        if all(n is not None for _, n in idx):
+            row += [n for _, n in idx]
+        triangles.append(row)
     if normals:
         return Mesh(vertices, triangles, normals, **kwargs)
     return Mesh(vertices, triangles, **kwargs)
