@@ -423,3 +423,28 @@ def test_accelerator_on_an_empty_world(api):
     world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
     assert world.hit(api.Ray(Point3D(0, 0, -3), Vector3D(0, 0, 1))) is None
     assert world.contains(Point3D(0, 0, 0)) == []
+
+
+def test_accelerator_with_real_parabola_objects(api, reference):
+    """raysect.primitive.Parabola objects (world-level and CSG operands) flattened from a live scenegraph"""
+    from raysect.core import Point3D, Vector3D
+    from source_b200.plugin import CudaAccelerator
+    world = scenes.parabola_scene(api)
+    o, d = scenes.parabola_rays(400)
+    ref = reference.oracle_hit(world, o, d)
+    world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
+    index = {id(p): i for i, p in enumerate(world.primitives)}
+    hits = 0
+    for i in range(len(o)):
+        it = world.hit(api.Ray(Point3D(*o[i]), Vector3D(*d[i])))
+        if ref["primitive"][i] < 0:
+            assert it is None
+            continue
+        hits += 1
+        assert index[id(it.primitive)] == ref["primitive"][i]
+        assert it.ray_distance == ref["distance"][i]
+        assert bool(it.exiting) == bool(ref["exiting"][i])
+        g = ref["geometry"][i]
+        assert (it.hit_point.x, it.hit_point.y, it.hit_point.z) == tuple(g[0:3])
+        assert (it.normal.x, it.normal.y, it.normal.z) == tuple(g[9:12])
+    assert hits > 150
