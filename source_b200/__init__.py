@@ -18,7 +18,7 @@ from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Materia
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Parabola, Primitive, Ray,
                          Sphere, Subtract, Union, World)
 from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
-                       SpectralPowerPipeline2D, SpectralSlice, StatsArray3D)
+                       SpectralPowerPipeline2D, SpectralRadiancePipeline2D, SpectralSlice, StatsArray3D)
 from .meshio import import_obj, import_stl
 from .engine import Accelerator, Device, default_device
 from ._cabi import RNG_MT19937_64, RNG_PHILOX, RsbError

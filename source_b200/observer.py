@@ -174,6 +174,15 @@ class SpectralPowerPipeline2D:
         pass
 
 
+class SpectralRadiancePipeline2D(SpectralPowerPipeline2D):
+    """raysect/optical/observer/pipeline/spectral/radiance.pyx: the same frame statistics, of the spectral RADIANCE:
+    its pixel processor does not apply the pixel sensitivity (radiance.pyx:256-260)"""
+    radiance = True
+
+    def __init__(self, accumulate=True, name=None):
+        super().__init__(accumulate, name or "SpectralRadiancePipeline2D")
+
+
 class FullFrameSampler2D:
     """raysect/optical/observer/sampler2d.pyx:38-102.  The reference shuffles the task list so the image
     assembles randomly on screen; pixel streams here are keyed on the pixel, so order does not matter and
@@ -386,7 +395,15 @@ class PinholeCamera(Observer):
             return
         accel = world.build_accelerator()
         nx, ny = self._pixels
-        cam = self._camera_desc(self.pixel_samples)
+        # power pipelines see samples scaled by the pixel sensitivity, radiance pipelines unscaled ones (= sensitivity
+        # exactly 1.0): one render per distinct sensitivity, over the very same pixel streams
+        cams = {}
+        for p in self.pipelines:
+            sens = 1.0 if getattr(p, "radiance", False) else float(self.sensitivity)
+            if sens not in cams:
+                cam = self._camera_desc(self.pixel_samples)
+                cam.sensitivity = sens
+                cams[sens] = cam
         self.ray_count = 0
         for slice_id, s in enumerate(slices):
             cfg = ray_config(s.bins, s.min_wavelength, s.max_wavelength, self.ray_extinction_prob,
@@ -395,11 +412,15 @@ class PinholeCamera(Observer):
             spectral = accel.flat.spectral(s.min_wavelength, s.max_wavelength, s.bins)
             # each slice is an independent pass with its own streams (the reference's single global stream
             # simply keeps running): offset the seed by the slice so passes are not correlated
-            mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode,
-                                                self.seed + slice_id * nx * ny, tasks, passes=passes,
-                                                seed_stride=len(slices) * nx * ny)
+            frames, rays = {}, 0
+            for sens, cam in cams.items():
+                mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode,
+                                                    self.seed + slice_id * nx * ny, tasks, passes=passes,
+                                                    seed_stride=len(slices) * nx * ny)
+                frames[sens] = (mean, variance)
             self.ray_count += rays
             for p in self.pipelines:
+                mean, variance = frames[1.0 if getattr(p, "radiance", False) else float(self.sensitivity)]
                 p.update_slice(tasks, slice_id, mean, variance)
         for p in self.pipelines:
             p.finalise()

@@ -104,7 +104,7 @@ class CudaRenderEngine(RenderEngine):
     Contract (workflow.py:78-91, observer.pyx:299-305): ``run(tasks, render, update, render_args=(slice_id,
     template_ray), update_args=(slice_id,))`` is called once per spectral slice; ``render`` is the bound
     ``observer._render_pixel``, so the observer, its world and its pipelines are reachable from it.
-    Supported: ``PinholeCamera`` and ``OrthographicCamera`` observers feeding ``SpectralPowerPipeline2D`` pipelines (the spectral frame
+    Supported: ``PinholeCamera`` and ``OrthographicCamera`` observers feeding ``SpectralPowerPipeline2D`` / ``SpectralRadiancePipeline2D`` pipelines (the spectral frame
     every other 2-D pipeline is a post-processing of), worlds built from Sphere/Box/Cylinder/Cone/CSG/Mesh
     with Lambert / UniformSurfaceEmitter / UnitySurfaceEmitter / Dielectric / Conductor / RoughConductor / AbsorbingSurface /
     UniformVolumeEmitter / UnityVolumeEmitter materials.
@@ -159,16 +159,18 @@ class CudaRenderEngine(RenderEngine):
         return self._accel
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D
+        from raysect.optical.observer import (OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D,
+                                              SpectralRadiancePipeline2D)
         observer = getattr(render, "__self__", None)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera)):
             raise NotImplementedError("CudaRenderEngine renders PinholeCamera and OrthographicCamera observers; got %r "
                                       "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
-            if not isinstance(p, SpectralPowerPipeline2D):
-                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D pipelines; %r is host-side "
-                                          "post-processing of that spectral frame" % type(p).__name__)
+            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D)):
+                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D "
+                                          "pipelines; %r is host-side post-processing of that spectral frame"
+                                          % type(p).__name__)
         slice_id, template = render_args[0], render_args[1]
         world = observer.root
         accel = self._accelerator_for(world, slice_id)
@@ -176,32 +178,41 @@ class CudaRenderEngine(RenderEngine):
         if observer.pixel_samples % self.passes:
             raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
                              % (observer.pixel_samples, self.passes))
-        if isinstance(observer, OrthographicCamera):
-            cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, None, observer.sensitivity,
-                              observer.to_root(), width=observer.width)
-        else:
-            cam = camera_desc(nx, ny, observer.pixel_samples // self.passes, observer.fov, observer.sensitivity,
-                              observer.to_root())
+        def camera_for(sensitivity):
+            if isinstance(observer, OrthographicCamera):
+                return camera_desc(nx, ny, observer.pixel_samples // self.passes, None, sensitivity,
+                                   observer.to_root(), width=observer.width)
+            return camera_desc(nx, ny, observer.pixel_samples // self.passes, observer.fov, sensitivity,
+                               observer.to_root())
         cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
                          template.extinction_min_depth, template.max_depth, template.importance_sampling,
                          template.important_path_weight, template.max_distance)
         spectral = accel.flat.spectral(template.min_wavelength, template.max_wavelength, template.bins)
         pix = np.asarray(tasks, dtype=np.int32).reshape(-1, 2)
-        if self.passes > 1:
-            mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix,
-                                                passes=self.passes, seed_stride=observer.spectral_rays * nx * ny)
-        else:
-            mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, self.seed + slice_id * nx * ny, pix)
+        # The power pipeline's pixel processor scales every sample by the pixel sensitivity (power.pyx:478-481), the
+        # radiance pipeline's does not (radiance.pyx:256-260) -- the same as a sensitivity of exactly 1.0.  One render
+        # per distinct sensitivity; the pixel streams are keyed on the pixel, so both see the very same paths.
+        frames, rays = {}, 0
+        for p in pipelines:
+            sensitivity = 1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)
+            if sensitivity not in frames:
+                kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
+                mean, variance, rays = accel.render(camera_for(sensitivity), cfg, spectral, self.rng_mode,
+                                                    self.seed + slice_id * nx * ny, pix, **kw)
+                frames[sensitivity] = (mean, variance)
+        per_pipeline = [frames[1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)]
+                        for p in pipelines]
         self.ray_count += rays
         if self.bulk_update:
             offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
-            self._bulk_update(pipelines, pix, offset, mean, variance, observer.pixel_samples)
+            for p, (mean, variance) in zip(pipelines, per_pipeline):
+                self._bulk_update([p], pix, offset, mean, variance, observer.pixel_samples)
             # statistics hook of the observer: one update carrying the whole ray count
             observer._update_statistics(rays)
             return
         share, extra = divmod(rays, len(pix))
         for k, (x, y) in enumerate(pix):
-            result = ((int(x), int(y)), [(mean[x, y].copy(), variance[x, y].copy()) for _ in pipelines],
+            result = ((int(x), int(y)), [(m[x, y].copy(), v[x, y].copy()) for m, v in per_pipeline],
                       share + (extra if k == 0 else 0))
             update(result, *update_args, **update_kwargs)
 

@@ -448,3 +448,43 @@ def test_accelerator_with_real_parabola_objects(api, reference):
         assert (it.hit_point.x, it.hit_point.y, it.hit_point.z) == tuple(g[0:3])
         assert (it.normal.x, it.normal.y, it.normal.z) == tuple(g[9:12])
     assert hits > 150
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_power_and_radiance_pipelines_side_by_side(api, reference, bulk):
+    """one camera feeding a SpectralPowerPipeline2D AND a SpectralRadiancePipeline2D (sensitivity 2.5): the power
+    frame carries the sensitivity, the radiance frame does not; both bit-exact against the reference's processors"""
+    from raysect.optical.observer import SpectralRadiancePipeline2D
+    from source_b200.plugin import CudaRenderEngine
+
+    def make():
+        world = scenes.cornell_box(api)
+        cam, power = scenes.cornell_camera(api, world, pixels=(10, 8), samples=3, bins=6, spectral_rays=2, sensitivity=2.5)
+        radiance = SpectralRadiancePipeline2D()
+        cam.pipelines = [radiance, power]
+        return cam, power, radiance
+    cam, power, radiance = make()
+    reference.oracle_render(cam, power, 77)
+    cam2, power2, radiance2 = make()
+    cam2.render_engine = CudaRenderEngine(seed=77, rng="mt", bulk_update=bulk, backend=hostsim_api.HostScene)
+    cam2.observe()
+    for a, b in ((power2, power), (radiance2, radiance)):
+        np.testing.assert_array_equal(np.array(a.frame.samples), np.array(b.frame.samples))
+        np.testing.assert_array_equal(np.array(a.frame.mean), np.array(b.frame.mean))
+        np.testing.assert_array_equal(np.array(a.frame.variance), np.array(b.frame.variance))
+    assert np.array(power.frame.mean).sum() > 2.0 * np.array(radiance.frame.mean).sum() > 0
+    # the stand-alone mirror: same two pipelines
+    import parity
+    import source_b200 as mirror
+    mworld = scenes.cornell_box(mirror)
+    mcam, mpower = scenes.cornell_camera(mirror, mworld, pixels=(10, 8), samples=3, bins=6, spectral_rays=2, sensitivity=2.5)
+    mrad = mirror.SpectralRadiancePipeline2D()
+    mcam.pipelines = [mrad, mpower]
+    mcam.seed = 77
+    mworld._accel = parity._Accel(hostsim_api.HostScene(parity.flatten_world(mworld)))
+    mworld._rebuild = False
+    mcam.observe()
+    mworld._accel.close()
+    np.testing.assert_array_equal(mpower.frame.mean, np.array(power.frame.mean))
+    np.testing.assert_array_equal(mrad.frame.mean, np.array(radiance.frame.mean))
+    np.testing.assert_array_equal(mrad.frame.variance, np.array(radiance.frame.variance))
