@@ -395,6 +395,74 @@ def icosphere(subdivisions=3, radius=0.5, bumps=0.08, seed=5):
     return verts, np.ascontiguousarray(np.c_[tris, tris]), vn.astype(np.float32)
 
 
+def refine_mesh(vertices, triangles, target):
+    """Deterministic refinement of a closed triangle mesh to EXACTLY ``target`` triangles (the
+    144,046-triangle Stanford bunny -> 1,000,000): 1 -> 4 midpoint subdivision (shared edge midpoints, so the surface
+    stays closed) while 4 x count <= target, then longest-edge bisection in triangle index order -- an edge split
+    replaces BOTH triangles on that edge by two each (+2, no T-junctions) -- until the count is reached; if one
+    triangle is missing at the end (odd remainder) the target is not reachable this way and ValueError is raised.
+    Positions are float32, like MeshData's.  Returns (vertices f32 [n,3], triangles i32 [m,3])."""
+    v = [tuple(float(c) for c in p) for p in np.asarray(vertices, dtype=np.float32)]
+    t = [tuple(int(i) for i in tri[:3]) for tri in np.asarray(triangles)]
+
+    def midpoint(a, b, cache):
+        key = (a, b) if a < b else (b, a)
+        if key not in cache:
+            pa, pb = v[a], v[b]
+            m = tuple(float(np.float32(0.5) * (np.float32(pa[k]) + np.float32(pb[k]))) for k in range(3))
+            cache[key] = len(v)
+            v.append(m)
+        return cache[key]
+    while 4 * len(t) <= target:
+        cache, out = {}, []
+        for a, b, c in t:
+            ab, bc, ca = midpoint(a, b, cache), midpoint(b, c, cache), midpoint(c, a, cache)
+            out += [(a, ab, ca), (ab, b, bc), (ca, bc, c), (ab, bc, ca)]
+        t = out
+    if (target - len(t)) % 2:
+        raise ValueError("target not reachable: longest-edge bisection of a closed mesh adds two triangles per split")
+    # edge -> the (up to two) triangles using it, kept current while triangles are replaced
+    edge_tris = {}
+
+    def edges_of(tri):
+        a, b, c = tri
+        return [tuple(sorted(e)) for e in ((a, b), (b, c), (c, a))]
+
+    def link(i):
+        for e in edges_of(t[i]):
+            edge_tris.setdefault(e, set()).add(i)
+
+    def unlink(i):
+        for e in edges_of(t[i]):
+            edge_tris[e].discard(i)
+    for i in range(len(t)):
+        link(i)
+
+    def length2(e):
+        pa, pb = np.array(v[e[0]], dtype=np.float64), np.array(v[e[1]], dtype=np.float64)
+        return float(((pa - pb) ** 2).sum())
+
+    def split(i, e, m):
+        """replace triangle i (which has edge e = (p, q)) by (.., p, m) and (.., m, q), keeping its orientation"""
+        tri = t[i]
+        k = [j for j in range(3) if tuple(sorted((tri[j], tri[(j + 1) % 3]))) == e][0]
+        p, q, r = tri[k], tri[(k + 1) % 3], tri[(k + 2) % 3]
+        unlink(i)
+        t[i] = (p, m, r)
+        t.append((m, q, r))
+        link(i)
+        link(len(t) - 1)
+    i = 0
+    cache = {}
+    while len(t) < target:
+        e = max(edges_of(t[i]), key=lambda ed: (length2(ed), ed))      # ties broken by the vertex ids: deterministic
+        m = midpoint(e[0], e[1], cache)
+        for j in sorted(edge_tris[e]):
+            split(j, e, m)
+        i += 1
+    return np.array(v, dtype=np.float32), np.array(t, dtype=np.int32)
+
+
 def mesh_scene(api, smoothing=True):
     """Two instances of the bumpy icosphere (one via Mesh.instance) plus a floor box."""
     a = api

@@ -200,3 +200,24 @@ def test_kd_plane_distance_through_reciprocal_is_the_ieee_quotient():
     assert np.array_equal(out[ok].view(np.uint64), ref[ok].view(np.uint64))
     zero = ref == 0
     assert np.all(out[zero] == 0)
+
+
+def test_refine_mesh_is_exact_closed_and_deterministic():
+    """tests/scenes.refine_mesh (SURVEY config 4 recipe: bunny -> exactly 1,000,000 triangles): exact count, every edge
+    shared by two triangles with opposite directions (closed, consistently oriented), same output twice"""
+    from collections import Counter
+    import scenes
+    v, t, _ = scenes.icosphere(1)
+    for target in (320, 322, 1000, 1282):
+        V, T = scenes.refine_mesh(v, t[:, :3], target)
+        assert len(T) == target and V.dtype == np.float32
+        und, dire = Counter(), Counter()
+        for a, b, c in T:
+            for e in ((a, b), (b, c), (c, a)):
+                und[tuple(sorted(e))] += 1
+                dire[e] += 1
+        assert set(und.values()) == {2} and max(dire.values()) == 1
+        V2, T2 = scenes.refine_mesh(v, t[:, :3], target)
+        assert np.array_equal(V, V2) and np.array_equal(T, T2)
+    with pytest.raises(ValueError):
+        scenes.refine_mesh(v, t[:, :3], 321)

@@ -31,16 +31,21 @@ def main():
     ap.add_argument("--rng", default="mt", choices=["mt", "philox"])
     ap.add_argument("--glass", action="store_true", help="keep the glass box and sphere of the Cornell scene")
     ap.add_argument("--passes", type=int, default=1, help="render spp as this many concurrent accumulated passes")
+    ap.add_argument("--obj", default="", help="Wavefront OBJ to use instead of the icosphere (SURVEY config 4: the Stanford "
+                    "bunny, demos/resources/stanford_bunny.obj), refined deterministically to --triangles, scaled to "
+                    "stand 1 m tall on the floor of the box")
+    ap.add_argument("--triangles", type=int, default=1000000)
     args = ap.parse_args()
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if world_size > 1 or args.passes > 1:
         return main_distributed(args)
     dev = Device(0)
-    verts, tris, normals = scenes.icosphere(args.subdiv, radius=0.45, bumps=0.15)
+    verts, tris, normals = load_mesh(args, scenes)
     t0 = time.time()
 
     def extra(a, w):
-        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+        a.Mesh(verts, tris, normals, smoothing=normals is not None, closed=True, parent=w,
+               transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 0 if args.obj else 10, 0),
                material=a.Lambert(a.ConstantSF(0.7)))
     world = scenes.cornell_box(api, glass=args.glass, extra=extra)
     build_s = time.time() - t0
@@ -70,6 +75,21 @@ def main():
                       "frames_per_s": 1e3 / best[0], "waves": rs["waves"], "mean_sum": float(m.sum())}))
 
 
+def load_mesh(args, scenes):
+    """(vertices, triangles, normals-or-None) of the mesh the run uses"""
+    if not args.obj:
+        return scenes.icosphere(args.subdiv, radius=0.45, bumps=0.15)
+    import numpy as np
+    import source_b200 as api
+    base = api.import_obj(args.obj)
+    v, t = scenes.refine_mesh(base.data.vertices, base.data.triangles, args.triangles)
+    v = v.astype(np.float64)
+    lo, hi = v.min(0), v.max(0)
+    s = 1.0 / (hi[1] - lo[1])
+    v = (v - [0.5 * (lo[0] + hi[0]), lo[1], 0.5 * (lo[2] + hi[2])]) * s + [0.0, -1.0 + 1e-6 + 0.5, 0.0]
+    return v.astype(np.float32), t, None
+
+
 def main_distributed(args):
     """the same scene through distributed.FrameRenderer: one process per GPU, optional concurrent passes"""
     import torch
@@ -87,11 +107,12 @@ def main_distributed(args):
     if world_size > 1:
         dist.init_process_group("nccl", device_id=dev_t)
     device = Device(local_rank)
-    verts, tris, normals = scenes.icosphere(args.subdiv, radius=0.45, bumps=0.15)
+    verts, tris, normals = load_mesh(args, scenes)
     t0 = time.time()
 
     def extra(a, w):
-        a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+        a.Mesh(verts, tris, normals, smoothing=normals is not None, closed=True, parent=w,
+               transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 0 if args.obj else 10, 0),
                material=a.Lambert(a.ConstantSF(0.7)))
     world = scenes.cornell_box(api, glass=args.glass, extra=extra)
     build_s = time.time() - t0
