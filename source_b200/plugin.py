@@ -123,9 +123,17 @@ class CudaRenderEngine(RenderEngine):
     StatsArray3D.combine_samples -- bit for bit what ``passes`` observe() calls of ``pixel_samples / passes``
     samples into an empty accumulating pipeline give on the reference (its progressive-render loop,
     demos/cornell_box.py:160-174), with ``passes`` times as many independent pixel streams in flight.
+
+    ``devices=[0, 1, ...]`` (CUDA device indices or ``source_b200.Device`` objects) spreads the tasks of every
+    ``run`` over several GPUs from this one process: 16 x 16 pixel tiles are dealt round-robin to the devices, one
+    host thread per device drives its own context (ctypes releases the GIL), every device renders into an otherwise
+    zero frame and the frames are summed on the host -- exact, because the sum only ever adds zeros, and independent
+    of the number of devices, because pixel streams are keyed on the pixel.  (One process per GPU with a single NCCL
+    reduce -- ``source_b200.distributed.FrameRenderer`` under torchrun -- is the faster route; this one needs no
+    launcher.)
     """
 
-    def __init__(self, seed=1, rng="mt", device=None, bulk_update=True, backend=None, passes=1):
+    def __init__(self, seed=1, rng="mt", device=None, bulk_update=True, backend=None, passes=1, devices=None):
         if rng not in ("mt", "philox"):
             raise ValueError("rng must be 'mt' or 'philox'")
         if seed < 1:
@@ -137,26 +145,53 @@ class CudaRenderEngine(RenderEngine):
         if self.passes < 1:
             raise ValueError("passes must be >= 1")
         self._device = device
+        self._devices = list(devices) if devices else None
+        if self._devices is not None and device is not None:
+            raise ValueError("give either device or devices")
         self._backend_factory = backend
         self._accel = None
         self._accel_world = None
         self.ray_count = 0
 
     def worker_count(self):
-        return 1
+        return len(self._devices) if self._devices else 1
 
     def _accelerator_for(self, world, slice_id):
         # a new observe() starts at slice 0: re-flatten there so scene edits between renders are picked up
         if self._accel is None or self._accel_world is not world or slice_id == 0:
-            if self._accel is not None:
-                self._accel.close()
+            for a in (self._accel if isinstance(self._accel, list) else [self._accel] if self._accel else []):
+                a.close()
             flat = flatten_world(world)
-            if self._backend_factory is not None:
+            if self._devices:
+                from .engine import Device
+                self._devices = [d if hasattr(d, "ctx") or self._backend_factory else Device(int(d)) for d in self._devices]
+                self._accel = [self._backend_factory(flat) if self._backend_factory is not None else _DeviceAccelerator(d, flat)
+                               for d in self._devices]
+            elif self._backend_factory is not None:
                 self._accel = self._backend_factory(flat)
             else:
                 self._accel = _DeviceAccelerator(self._device or default_device(), flat)
             self._accel_world = world
         return self._accel
+
+    @staticmethod
+    def _render_on_devices(accels, pix, tile, render_one):
+        """tiles of 16 x 16 pixels dealt round-robin to the devices; one thread per device; frames summed on the host"""
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(accels)
+        tile_id = (pix[:, 0] // tile) * 65536 + (pix[:, 1] // tile)
+        order = {t: k for k, t in enumerate(sorted(set(tile_id.tolist())))}
+        owner = np.array([order[t] % n for t in tile_id.tolist()], dtype=np.int64)
+        jobs = [(a, np.ascontiguousarray(pix[owner == k])) for k, a in enumerate(accels)]
+        jobs = [(a, p) for a, p in jobs if len(p)]
+        with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as pool:
+            parts = list(pool.map(lambda job: render_one(job[0], job[1]), jobs))
+        mean, variance, rays = parts[0]
+        for m, v, r in parts[1:]:
+            mean += m           # exact: every frame is zero outside its own tiles
+            variance += v
+            rays += r
+        return mean, variance, rays
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
         from raysect.optical.observer import (OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D,
@@ -187,7 +222,8 @@ class CudaRenderEngine(RenderEngine):
         cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
                          template.extinction_min_depth, template.max_depth, template.importance_sampling,
                          template.important_path_weight, template.max_distance)
-        spectral = accel.flat.spectral(template.min_wavelength, template.max_wavelength, template.bins)
+        spectral = (accel[0] if isinstance(accel, list) else accel).flat.spectral(
+            template.min_wavelength, template.max_wavelength, template.bins)
         pix = np.asarray(tasks, dtype=np.int32).reshape(-1, 2)
         # The power pipeline's pixel processor scales every sample by the pixel sensitivity (power.pyx:478-481), the
         # radiance pipeline's does not (radiance.pyx:256-260) -- the same as a sensitivity of exactly 1.0.  One render
@@ -197,8 +233,15 @@ class CudaRenderEngine(RenderEngine):
             sensitivity = 1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)
             if sensitivity not in frames:
                 kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
-                mean, variance, rays = accel.render(camera_for(sensitivity), cfg, spectral, self.rng_mode,
-                                                    self.seed + slice_id * nx * ny, pix, **kw)
+                cam = camera_for(sensitivity)
+                if isinstance(accel, list):
+                    mean, variance, rays = self._render_on_devices(
+                        accel, pix, 16, lambda a, p: a.render(cam, cfg, a.flat.spectral(
+                            template.min_wavelength, template.max_wavelength, template.bins), self.rng_mode,
+                            self.seed + slice_id * nx * ny, p, **kw))
+                else:
+                    mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode,
+                                                        self.seed + slice_id * nx * ny, pix, **kw)
                 frames[sensitivity] = (mean, variance)
         per_pipeline = [frames[1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)]
                         for p in pipelines]

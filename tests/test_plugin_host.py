@@ -488,3 +488,28 @@ def test_power_and_radiance_pipelines_side_by_side(api, reference, bulk):
     np.testing.assert_array_equal(mpower.frame.mean, np.array(power.frame.mean))
     np.testing.assert_array_equal(mrad.frame.mean, np.array(radiance.frame.mean))
     np.testing.assert_array_equal(mrad.frame.variance, np.array(radiance.frame.variance))
+
+
+def test_render_engine_over_several_devices_equals_one_device(api, reference):
+    """CudaRenderEngine(devices=[...]): tiles dealt to three "devices" (three host-build scenes, one thread each), frames
+    summed on the host -- bit-identical to the reference / to a single device, with passes and a partial task mask"""
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(40, 36), samples=4, bins=4, spectral_rays=2)
+    mask = np.ones((40, 36), dtype=bool)
+    mask[5:9, :] = False
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, **kw)
+    cam.pixel_samples = 2
+    cam.frame_sampler = api.FullFrameSampler2D(mask)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 31, passes=2)
+    world2 = scenes.cornell_box(api)
+    cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
+    cam2.frame_sampler = api.FullFrameSampler2D(mask)
+    engine = CudaRenderEngine(seed=31, rng="mt", backend=hostsim_api.HostScene, passes=2, devices=[0, 1, 2])
+    assert engine.worker_count() == 3
+    cam2.render_engine = engine
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.samples), n_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert engine.ray_count > 0 and m_ref[mask].sum() > 0 and not np.array(pipe2.frame.mean)[~mask].any()
