@@ -12,7 +12,7 @@ OBJDIR="${RSB_OBJDIR:-$HERE/../../build/obj}"
 mkdir -p "$OBJDIR"
 TAG="$(printf '%s' "${RSB_NVCC_EXTRA}" | cksum | cut -d' ' -f1)"
 CUOBJ="$OBJDIR/raysect_b200_$TAG.o"
-FLAGS="-std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-ffp-contract=off ${RSB_NVCC_EXTRA}"
+FLAGS="-std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-ffp-contract=off,-pthread ${RSB_NVCC_EXTRA}"
 stale=0
 [ -f "$CUOBJ" ] || stale=1
 for f in "$HERE"/*.cu "$HERE"/*.cuh "$HERE"/*.h "$HERE"/../../include/*.h "$HERE/build.sh"; do
@@ -25,6 +25,6 @@ if [ "$stale" = 1 ]; then
 fi
 "$NVCC" $FLAGS -c -o "$OBJDIR/kdtree_host_$TAG.o" "$HERE/kdtree_host.cpp"
 "$NVCC" $FLAGS -c -o "$OBJDIR/scene_pack_$TAG.o" "$HERE/scene_pack.cpp"
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT.tmp" "$CUOBJ" "$OBJDIR/kdtree_host_$TAG.o" "$OBJDIR/scene_pack_$TAG.o"
+"$NVCC" -shared -Xcompiler -pthread -gencode arch=compute_100a,code=sm_100a -o "$OUT.tmp" "$CUOBJ" "$OBJDIR/kdtree_host_$TAG.o" "$OBJDIR/scene_pack_$TAG.o"
 mv "$OUT.tmp" "$OUT"
 echo "built $OUT"

@@ -2,9 +2,11 @@
 #include "kdtree_host.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 
 namespace rsb {
 
@@ -132,11 +134,19 @@ inline int largest_axis(const double* b) {
     return axis;
 }
 
+// A subtree under construction: node ids and item offsets are LOCAL to the subtree (its root is node 0), so that
+// independent subtrees can be built by different threads and spliced into the pre-order layout afterwards.
+struct Sub {
+    std::vector<KdNode> nodes;
+    std::vector<int32_t> items;
+    int32_t depth = 0;
+};
+
 struct Builder {
     const double* boxes;
     int32_t max_depth, min_items;
     double hit_cost, empty_bonus;
-    HostKdTree* out;
+    Sub* out;
     std::vector<Edge> edges;
 
     int32_t new_leaf(const std::vector<int32_t>& items) {
@@ -151,8 +161,23 @@ struct Builder {
         return (int32_t)out->nodes.size() - 1;
     }
 
-    // kdtree3d.pyx:166-188 (_build) + :193-308 (_split) + :422-459 (_new_branch)
-    int32_t build(std::vector<int32_t>& items, const double* bounds, int32_t depth) {
+    // appends a finished subtree behind the nodes already present, shifting its local ids / offsets
+    int32_t splice(const Sub& sub) {
+        const int32_t node_base = (int32_t)out->nodes.size(), item_base = (int32_t)out->items.size();
+        for (KdNode n : sub.nodes) {
+            if (n.axis < 0) n.leaf.item_offset += item_base;
+            else n.upper += node_base;
+            out->nodes.push_back(n);
+        }
+        out->items.insert(out->items.end(), sub.items.begin(), sub.items.end());
+        out->depth = std::max(out->depth, sub.depth);
+        return node_base;
+    }
+
+    // kdtree3d.pyx:166-188 (_build) + :193-308 (_split) + :422-459 (_new_branch).  `fork` > 0: the two children of
+    // this node are built concurrently (the lower one on a new thread) while enough items are left to pay for it;
+    // the layout -- and therefore the serialised stream -- is the same as the serial build's.
+    int32_t build(std::vector<int32_t>& items, const double* bounds, int32_t depth, int fork) {
         out->depth = std::max(out->depth, depth);
         if (depth == max_depth || (int32_t)items.size() <= min_items) return new_leaf(items);
 
@@ -222,8 +247,20 @@ struct Builder {
 
         int32_t id = (int32_t)out->nodes.size();
         out->nodes.push_back(KdNode{});
-        build(lower_items, lb, depth + 1);
-        int32_t upper_id = build(upper_items, ub, depth + 1);
+        int32_t upper_id;
+        if (fork > 0 && lower_items.size() + upper_items.size() >= 20000) {
+            Sub lower_sub, upper_sub;
+            Builder lower_builder{boxes, max_depth, min_items, hit_cost, empty_bonus, &lower_sub, {}};
+            Builder upper_builder{boxes, max_depth, min_items, hit_cost, empty_bonus, &upper_sub, {}};
+            std::thread worker([&]() { lower_builder.build(lower_items, lb, depth + 1, fork - 1); });
+            upper_builder.build(upper_items, ub, depth + 1, fork - 1);
+            worker.join();
+            splice(lower_sub);
+            upper_id = splice(upper_sub);
+        } else {
+            build(lower_items, lb, depth + 1, 0);
+            upper_id = build(upper_items, ub, depth + 1, 0);
+        }
         KdNode n;
         memset(&n, 0, sizeof(n));
         n.split = best_split;
@@ -254,13 +291,19 @@ void kd_build(const double* boxes, int64_t n_items, int32_t max_depth, int32_t m
         }
     }
     memcpy(out->bounds, b, sizeof(b));
-    out->nodes.clear();
-    out->items.clear();
-    out->depth = 0;
-    Builder bd{boxes, out->max_depth, out->min_items, out->hit_cost, out->empty_bonus, out, {}};
+    // RSB_KD_THREADS (default: hardware threads, at most 16): the top log2(threads) levels fork; 1 = serial
+    int threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("RSB_KD_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 256) threads = v; }
+    int fork = 0;
+    while ((1 << (fork + 1)) <= threads) ++fork;
+    Sub root;
+    Builder bd{boxes, out->max_depth, out->min_items, out->hit_cost, out->empty_bonus, &root, {}};
     std::vector<int32_t> items((size_t)n_items);
     for (int64_t i = 0; i < n_items; ++i) items[(size_t)i] = (int32_t)i;
-    bd.build(items, out->bounds, 0);
+    bd.build(items, out->bounds, 0, fork);
+    out->nodes.swap(root.nodes);
+    out->items.swap(root.items);
+    out->depth = root.depth;
 }
 
 }  // namespace rsb

@@ -23,7 +23,7 @@ def build(force=False):
     newest = max(os.path.getmtime(p) for p in SOURCES + HEADERS)
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO] + SOURCES)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-pthread", "-fPIC", "-shared", "-o", SO] + SOURCES)
     return SO
 
 
