@@ -221,3 +221,22 @@ def test_refine_mesh_is_exact_closed_and_deterministic():
         assert np.array_equal(V, V2) and np.array_equal(T, T2)
     with pytest.raises(ValueError):
         scenes.refine_mesh(v, t[:, :3], 321)
+
+
+def test_threaded_kdtree_build_writes_the_serial_stream(monkeypatch):
+    """rsb_kdtree_build forks its top levels onto threads (RSB_KD_THREADS) and splices the subtrees: the stream must be
+    the serial build's byte for byte (81,920 triangle boxes, mesh tree parameters)"""
+    import scenes
+    from source_b200.flatten import kdtree_build
+    v, t, _ = scenes.icosphere(6, radius=0.45, bumps=0.15)
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    t = np.ascontiguousarray(t, dtype=np.int32)
+    boxes = np.zeros((len(t), 6))
+    lib = cabi.load()
+    cabi.check(lib.rsb_mesh_triangle_boxes(cabi.ptr(v, C.c_float), len(v), cabi.ptr(t, C.c_int32), len(t), t.shape[1],
+                                           cabi.ptr(boxes, C.c_double)))
+    streams = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RSB_KD_THREADS", threads)
+        streams.append(kdtree_build(boxes, 0, 1, 5.0, 0.25))
+    assert streams[0] == streams[1] == streams[2] and len(streams[0]) > 1_000_000
