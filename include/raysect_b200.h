@@ -219,10 +219,15 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
 /*
  * Ray-batch sweep (BASELINE config 5): n primary rays generated ON DEVICE from (seed, index), from
  * `origin` toward a jittered window centred on `target` (half-width `half_window` in x and y),
- * hit results reduced to (hits, sum of t, xor of primitive ids) so that 1e9 rays need no ray arrays.
+ * hit results reduced to (hits, sum of t, xor of primitive ids) so that 1e9 rays need no host ray arrays
+ * (the rays live in a device-side chunk buffer of RSB_RQ_CHUNK queries).
+ * order_log2 = 0: ray `index` aims at a point drawn uniformly over the whole window (consecutive rays are
+ * unrelated: the incoherent case).  order_log2 = g > 0: the window is a 2^g x 2^g grid of cells walked along
+ * the Morton curve and ray `index` jitters inside cell (index mod 4^g) -- consecutive rays are neighbouring
+ * cells, the way an observer hands out the pixels of an image (the coherent, primary-ray case).
  */
 int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, int64_t first_index, uint64_t seed,
-                      const double* origin, const double* target, double half_window,
+                      const double* origin, const double* target, double half_window, int32_t order_log2,
                       uint64_t* out_hits_dev, double* out_sum_t_dev, uint64_t* out_xor_prim_dev, int32_t count);
 
 /*

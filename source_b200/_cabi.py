@@ -169,7 +169,7 @@ SIGNATURES = {
     "rsb_hit_batch_dev": (C.c_int, [_U64, _U64, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                     C.c_int32]),
     "rsb_hit_sweep_dev": (C.c_int, [_U64, _U64, _VP, C.c_int64, C.c_int64, _U64, c_double_p, c_double_p, C.c_double,
-                                    _VP, _VP, _VP, C.c_int32]),
+                                    C.c_int32, _VP, _VP, _VP, C.c_int32]),
     "rsb_contains_batch": (C.c_int, [_U64, _U64, C.c_int64, c_double_p, C.c_int32, c_int32_p, c_int32_p]),
     "rsb_rng_uniform": (C.c_int, [_U64, _U64, C.c_int64, c_double_p]),
     "rsb_render": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),

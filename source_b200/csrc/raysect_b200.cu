@@ -11,6 +11,7 @@
 
 #include "kdtree_host.h"
 #include "rsb_kernels.cuh"
+#include "rsb_trav.cuh"
 #include "scene_pack.h"
 
 using namespace rsb;
@@ -39,6 +40,7 @@ struct DeviceScene {
     std::vector<int32_t> mat_type, mat_transmission_only;
     int32_t stage_bytes = 0;   // shared memory needed to stage world tree + prims (0 = do not stage)
     bool has_mesh = false, has_csg = false;
+    int32_t n_mesh_prims = 0;  // world-level Mesh primitives (Mesh.hit rounds of the query pipeline)
 };
 
 struct Context {
@@ -52,6 +54,9 @@ struct Context {
     unsigned long long* d_scalars = nullptr;   // [0] work counter, [1] ray count, [2] overflow flag (as int)
     unsigned char* d_slots = nullptr;   // wavefront slot state (rsb_kernels.cuh: WfSlots)
     size_t slot_bytes = 0;
+    unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
+    size_t rq_bytes = 0;
+    long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
     long long chunk_items = 8LL << 20;  // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (5 KB each)
@@ -90,6 +95,39 @@ const size_t kMaxStageBytes = 96 * 1024;
             else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(false, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
             else if (feat_ == RSB_FEAT_ALL) M(false, RSB_FEAT_ALL);                                    \
             else M(false, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                           \
+        }                                                                                              \
+    } while (0)
+
+// the query pipeline's kernels exist for the feature sets that can reach them: k_rq_walk for scenes with meshes,
+// k_rq_world for scenes without
+#define RSB_DISPATCH_FEAT_MESH(count, feat, staged, M)                                                 \
+    do {                                                                                               \
+        const int feat_ = (feat) | ((staged) ? RSB_FEAT_STAGED : 0);                                   \
+        if (count) {                                                                                   \
+            if (feat_ == RSB_FEAT_MESH) M(true, RSB_FEAT_MESH);                                        \
+            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(true, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
+            else if (feat_ == RSB_FEAT_ALL) M(true, RSB_FEAT_ALL);                                     \
+            else M(true, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                            \
+        } else {                                                                                       \
+            if (feat_ == RSB_FEAT_MESH) M(false, RSB_FEAT_MESH);                                       \
+            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(false, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
+            else if (feat_ == RSB_FEAT_ALL) M(false, RSB_FEAT_ALL);                                    \
+            else M(false, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                           \
+        }                                                                                              \
+    } while (0)
+#define RSB_DISPATCH_FEAT_NOMESH(count, feat, staged, M)                                               \
+    do {                                                                                               \
+        const int feat_ = ((feat) & RSB_FEAT_CSG) | ((staged) ? RSB_FEAT_STAGED : 0);                  \
+        if (count) {                                                                                   \
+            if (feat_ == 0) M(true, 0);                                                                \
+            else if (feat_ == RSB_FEAT_STAGED) M(true, RSB_FEAT_STAGED);                               \
+            else if (feat_ == RSB_FEAT_CSG) M(true, RSB_FEAT_CSG);                                     \
+            else M(true, (RSB_FEAT_CSG | RSB_FEAT_STAGED));                                            \
+        } else {                                                                                       \
+            if (feat_ == 0) M(false, 0);                                                               \
+            else if (feat_ == RSB_FEAT_STAGED) M(false, RSB_FEAT_STAGED);                              \
+            else if (feat_ == RSB_FEAT_CSG) M(false, RSB_FEAT_CSG);                                    \
+            else M(false, (RSB_FEAT_CSG | RSB_FEAT_STAGED));                                           \
         }                                                                                              \
     } while (0)
 
@@ -253,6 +291,7 @@ int rsb_context_create(int device, uint64_t* ctx) {
     RSB_CUDA(cudaMallocHost(&c->h_idle, sizeof(unsigned int)));
     if (const char* ng = getenv("RSB_NO_GRAPH")) c->use_graphs = !(ng[0] == '1');
     if (const char* sp = getenv("RSB_CHUNK_ITEMS")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->chunk_items = v; }
+    if (const char* sp = getenv("RSB_RQ_CHUNK")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->rq_chunk = v; }
     if (const char* sp = getenv("RSB_SLOTS_PER_SM")) { int v = atoi(sp); if (v >= 32 && v <= 65536) c->slots_per_sm = v; }
     *ctx = reinterpret_cast<uint64_t>(c);
     return RSB_OK;
@@ -267,6 +306,7 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_scalars);
     cudaFree(c->d_slots);
     cudaFree(c->d_pass);
+    cudaFree(c->d_rq);
     cudaFreeHost(c->h_idle);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_mats);
@@ -309,6 +349,8 @@ int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
         if (pr.type == PRIM_MESH) ds->has_mesh = true;
         if (pr.type >= PRIM_UNION) ds->has_csg = true;
     }
+    for (int32_t i = 0; i < ps.n_world; ++i)
+        if (ps.prims[i].type == PRIM_MESH) ds->n_mesh_prims += 1;
     ds->sc.n_world = ps.n_world;
     rc = upload_tree(ds, ps.world, &ds->sc.world);
     if (rc) return bail(rc);
@@ -371,6 +413,113 @@ int rsb_scene_destroy(uint64_t ctx, uint64_t scene) {
     return RSB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// carve the arrays of the query pipeline (rsb_trav.cuh) out of one allocation
+struct RqHost {
+    RqBuf b;
+    double* ray;     // [6][cap]
+    double* md;      // [cap]
+};
+
+size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> unsigned char* {
+        off = (off + 255) & ~(size_t)255;
+        unsigned char* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    };
+    memset(&out->b, 0, sizeof(out->b));
+    out->b.ctr = reinterpret_cast<unsigned int*>(take(16 * sizeof(unsigned int)));
+    out->ray = reinterpret_cast<double*>(take(6 * cap * sizeof(double)));
+    out->md = reinterpret_cast<double*>(take(cap * sizeof(double)));
+    out->b.hit_t = reinterpret_cast<double*>(take(cap * sizeof(double)));
+    out->b.hit_a = reinterpret_cast<int4*>(take(cap * sizeof(int4)));
+    out->b.hit_uvw = reinterpret_cast<float4*>(take(cap * sizeof(float4)));
+    out->b.hit_node = reinterpret_cast<int32_t*>(take(cap * sizeof(int32_t)));
+    if (park) {
+        out->b.susp = reinterpret_cast<RqSusp*>(take(cap * sizeof(RqSusp)));
+        out->b.susp_stack = reinterpret_cast<KdStackEntry*>(take(cap * RQ_WORLD_STACK * sizeof(KdStackEntry)));
+        out->b.queue = reinterpret_cast<int2*>(take((size_t)(RQ_MAX_ROUNDS + 1) * cap * sizeof(int2)));
+    }
+    out->b.ray = out->ray;
+    out->b.ray_stride = (long long)cap;
+    out->b.md = out->md;
+    out->b.md_all = RSB_INF;
+    out->b.cap = (long long)cap;
+    return (off + 255) & ~(size_t)255;
+}
+
+int rq_reserve(Context* c, long long cap, bool park, RqHost* out) {
+    size_t need = rq_carve(nullptr, (size_t)cap, park, out);
+    if (c->rq_bytes < need) {
+        cudaFree(c->d_rq);
+        c->d_rq = nullptr; c->rq_bytes = 0;
+        RSB_CUDA(cudaMalloc(&c->d_rq, need));
+        c->rq_bytes = need;
+    }
+    rq_carve(c->d_rq, (size_t)cap, park, out);
+    return RSB_OK;
+}
+
+// World.hit for queries [0, n) of `b` (rays in b.ray / b.md, answers in b.hit_*): one kernel for mesh-free scenes,
+// world walk / Mesh.hit / resume rounds for scenes with meshes.
+int rq_trace(Context* c, DeviceScene* ds, const RqBuf& b, long long n, cudaStream_t st, bool count) {
+    RSB_CUDA(cudaMemsetAsync(b.ctr, 0, 16 * sizeof(unsigned int), st));
+    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
+    const int staged = ds->stage_bytes ? 1 : 0;
+    RqArrayClient cl;
+    cl.b = b;
+    if (!ds->has_mesh) {
+        const size_t smem = ds->stage_bytes + RQ_WORLD_SMEM;
+        const int grid = grid_for(c, n, RQ_THREADS, (feat & RSB_FEAT_CSG) ? 3 : RQ_WORLD_BLOCKS);
+#define RSB_LAUNCH_RQ_WORLD(C, F)                                                                                         \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_rq_world<C, F, RqArrayClient>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_rq_world<C, F, RqArrayClient><<<grid, RQ_THREADS, smem, st>>>(ds->sc, ds->n_world_items, cl, b, n, c->d_counters); \
+    } while (0)
+        RSB_DISPATCH_FEAT_NOMESH(count, feat, staged, RSB_LAUNCH_RQ_WORLD);
+#undef RSB_LAUNCH_RQ_WORLD
+        RSB_CUDA(cudaGetLastError());
+        return RSB_OK;
+    }
+    const size_t smem_walk = ds->stage_bytes + ax_bytes(feat);
+    const int grid_walk = grid_for(c, n, RQ_THREADS, 16);
+    const int grid_mesh = c->sm_count * RQ_MESH_BLOCKS;
+    const int rounds = std::min<int>(ds->n_mesh_prims, RQ_MAX_ROUNDS);
+    RSB_CUDA(cudaFuncSetAttribute(k_rq_mesh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_MESH_SMEM));
+    RSB_CUDA(cudaFuncSetAttribute(k_rq_mesh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_MESH_SMEM));
+#define RSB_LAUNCH_RQ_WALK(C, F, RES, LAST, ROUND)                                                                        \
+    do {                                                                                                                  \
+        if (smem_walk > 48 * 1024)                                                                                        \
+            RSB_CUDA(cudaFuncSetAttribute(k_rq_walk<C, F, RqArrayClient, RES, LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_walk)); \
+        k_rq_walk<C, F, RqArrayClient, RES, LAST><<<grid_walk, RQ_THREADS, smem_walk, st>>>(ds->sc, ds->n_world_items, cl, b, n, ROUND, c->d_counters); \
+    } while (0)
+#define RSB_LAUNCH_RQ_BEGIN(C, F) RSB_LAUNCH_RQ_WALK(C, F, false, false, 0)
+#define RSB_LAUNCH_RQ_RESUME(C, F) RSB_LAUNCH_RQ_WALK(C, F, true, false, r)
+#define RSB_LAUNCH_RQ_LAST(C, F) RSB_LAUNCH_RQ_WALK(C, F, true, true, r)
+    RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_BEGIN);
+    for (int r = 0; r < rounds; ++r) {
+        if (count) k_rq_mesh<true><<<grid_mesh, RQ_THREADS, RQ_MESH_SMEM, st>>>(ds->sc, b, r, c->d_counters);
+        else k_rq_mesh<false><<<grid_mesh, RQ_THREADS, RQ_MESH_SMEM, st>>>(ds->sc, b, r, c->d_counters);
+        if (r == rounds - 1) RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_LAST);
+        else RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_RESUME);
+    }
+#undef RSB_LAUNCH_RQ_BEGIN
+#undef RSB_LAUNCH_RQ_RESUME
+#undef RSB_LAUNCH_RQ_LAST
+#undef RSB_LAUNCH_RQ_WALK
+    RSB_CUDA(cudaGetLastError());
+    return RSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, const double* origins,
                       const double* directions, const double* max_distance, int32_t* out_prim, double* out_t,
                       int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom, float* out_uvw,
@@ -381,22 +530,32 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     if (n <= 0) return RSB_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
-    int grid = grid_for(c, n, 128, 16);
-    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
-    const int staged = ds->stage_bytes ? 1 : 0;
-    size_t smem = ds->stage_bytes + ax_bytes(feat);
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-#define RSB_LAUNCH_HIT(C, F)                                                                                              \
-    do {                                                                                                                  \
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_batch<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_hit_batch<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, origins, directions, max_distance, \
-                                                   out_prim, out_t, out_sub, out_flags, out_node, out_geom, out_uvw, c->d_counters); \
-    } while (0)
-    RSB_DISPATCH_FEAT(count != 0, feat, staged, RSB_LAUNCH_HIT);
-#undef RSB_LAUNCH_HIT
+    const long long chunk = std::min<long long>(n, c->rq_chunk);
+    RqHost rq;
+    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq);
+    if (rc) return rc;
+    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
+    for (long long off = 0; off < n; off += chunk) {
+        const long long m = std::min<long long>(chunk, n - off);
+        const int grid = grid_for(c, m, 256, 8);
+        k_rq_batch_in<<<grid, 256, 0, st>>>(m, origins + 3 * off, directions + 3 * off, max_distance ? max_distance + off : nullptr, rq.ray,
+                                            rq.b.ray_stride, rq.md);
+        rc = rq_trace(c, ds, rq.b, m, st, count != 0);
+        if (rc) return rc;
+        const int ogrid = grid_for(c, m, 128, 16);
+#define RSB_LAUNCH_OUT(F)                                                                                                     \
+    k_rq_batch_out<F><<<ogrid, 128, 0, st>>>(ds->sc, rq.b, m, out_prim + off, out_t + off, out_sub + off, out_flags + off,         \
+                                             out_node ? out_node + 2 * off : nullptr, out_geom ? out_geom + 12 * off : nullptr,   \
+                                             out_uvw ? out_uvw + 3 * off : nullptr)
+        if (feat == 0) RSB_LAUNCH_OUT(0);
+        else if (feat == RSB_FEAT_MESH) RSB_LAUNCH_OUT(RSB_FEAT_MESH);
+        else RSB_LAUNCH_OUT(RSB_FEAT_ALL);
+#undef RSB_LAUNCH_OUT
+    }
     RSB_CUDA(cudaGetLastError());
     if (count) {
-        int rc = read_counters(c, st);
+        rc = read_counters(c, st);
         if (rc) return rc;
         c->last_counters.rays = (uint64_t)n;
     }
@@ -458,31 +617,35 @@ int rsb_hit_batch(uint64_t ctx, uint64_t scene, int64_t n, const double* origins
 }
 
 int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, int64_t first_index, uint64_t seed,
-                      const double* origin, const double* target, double half_window, uint64_t* out_hits_dev,
+                      const double* origin, const double* target, double half_window, int32_t order_log2, uint64_t* out_hits_dev,
                       double* out_sum_t_dev, uint64_t* out_xor_prim_dev, int32_t count) {
     Context* c = as_ctx(ctx);
     DeviceScene* ds = as_scene(scene);
     if (!c || !ds || !origin || !target || !out_hits_dev || !out_sum_t_dev || !out_xor_prim_dev) return fail(RSB_ERR_ARG, "null argument");
+    if (order_log2 < 0 || order_log2 > 31) return fail(RSB_ERR_ARG, "rsb_hit_sweep: order_log2 must be in [0, 31]");
     if (n <= 0) return RSB_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
-    int grid = grid_for(c, n, 128, 8);
-    const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
-    const int staged = ds->stage_bytes ? 1 : 0;
-    size_t smem = ds->stage_bytes + ax_bytes(feat);
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-#define RSB_LAUNCH_SWEEP(C, F)                                                                                            \
-    do {                                                                                                                  \
-        if (smem > 48 * 1024) RSB_CUDA(cudaFuncSetAttribute(k_hit_sweep<C, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_hit_sweep<C, F><<<grid, 128, smem, st>>>(ds->sc, ds->n_world_items, n, first_index, seed, origin[0], origin[1], origin[2], \
-                                                   target[0], target[1], target[2], half_window, (unsigned long long*)out_hits_dev, out_sum_t_dev, \
-                                                   (unsigned long long*)out_xor_prim_dev, c->d_counters);             \
-    } while (0)
-    RSB_DISPATCH_FEAT(count != 0, feat, staged, RSB_LAUNCH_SWEEP);
-#undef RSB_LAUNCH_SWEEP
+    const long long chunk = std::min<long long>(n, c->rq_chunk);
+    RqHost rq;
+    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq);
+    if (rc) return rc;
+    rq.b.md = nullptr;          // every ray of a sweep is unbounded
+    rq.b.md_all = RSB_INF;
+    for (long long off = 0; off < n; off += chunk) {
+        const long long m = std::min<long long>(chunk, n - off);
+        const int grid = grid_for(c, m, 256, 8);
+        k_rq_sweep_gen<<<grid, 256, 0, st>>>(m, first_index + off, seed, origin[0], origin[1], origin[2], target[0], target[1], target[2],
+                                             half_window, order_log2, rq.ray, rq.b.ray_stride);
+        rc = rq_trace(c, ds, rq.b, m, st, count != 0);
+        if (rc) return rc;
+        k_rq_sweep_reduce<<<grid, 256, 0, st>>>(rq.b, m, first_index + off, (unsigned long long*)out_hits_dev, out_sum_t_dev,
+                                                (unsigned long long*)out_xor_prim_dev);
+    }
     RSB_CUDA(cudaGetLastError());
     if (count) {
-        int rc = read_counters(c, st);
+        rc = read_counters(c, st);
         if (rc) return rc;
         c->last_counters.rays = (uint64_t)n;
     }

@@ -1149,6 +1149,12 @@ struct NestedTraversal {
     KdCursor mc;
     MeshLeaf<Stats> mleaf;
     MeshHit mh;
+    // split pipeline (rsb_trav.cuh): the last Mesh.hit answer of this ray.  Mesh.hit(ray) depends on the ray and its
+    // max_distance only (mesh.pyx:506-518), and the reference calls it again from every world leaf that lists the mesh
+    // until a hit is accepted; the repeated calls return the very same intersection, so it is kept instead.
+    int memo_prim;
+    bool memo_hit;
+    MeshHit memo;
 
     RSB_HD void init(const Scene& scene, double max_distance, KdStackEntry* stack_, HitRec* rec_, Stats& stats_, double* axbuf) {
         sc = &scene;
@@ -1173,18 +1179,42 @@ struct NestedTraversal {
         mh.node = -1;
         state = ST_DONE;
         found = false;
+        memo_prim = -1;
+        memo_hit = false;
+        memo.t = 0.0; memo.tri = -1; memo.node = -1; memo.u = memo.v = memo.w = 0.0f;
         node = sp = 0; leaf_node = -1;
         min_range = max_range = distance = 0.0;
         item_offset = item_count = item_base = nc = ci = 0;
         have_leaf = false;
     }
 
-    RSB_HD void run_world() {
+    // Mesh.hit's answer for candidate cand[ci] against the running closest distance of the world leaf
+    // (_PrimitiveKDTree._trace_leaf, acceleration/kdtree.pyx:103-122: `<=`)
+    RSB_HD void accept_mesh(bool hit, const MeshHit& m) {
+        if (hit && m.t <= distance) {
+            const int id = cand[ci];
+            distance = m.t;
+            rec->t = m.t; rec->prim = id; rec->leaf = id; rec->code = m.tri; rec->flip = 0;
+            rec->mesh_node = m.node;
+            rec->u = m.u; rec->v = m.v; rec->w = m.w;
+            found = true;
+        }
+    }
+
+    RSB_HD void run_world() { run_world_t<false>(); }
+
+    // SPLIT: the world-level walk stops in front of every Mesh.hit call (state ST_MESH, nothing of the mesh touched yet);
+    // a separate kernel answers it and resume_split() carries on.
+    template <bool SPLIT>
+    RSB_HD void run_world_t() {
         while (state == ST_WORLD) {
             if (ci < nc) {
                 const int id = cand[ci];
                 const Prim& p = sc->prims[id];
-                if (p.type == PRIM_MESH) {
+                if (SPLIT && p.type == PRIM_MESH) {
+                    if (id == memo_prim) { accept_mesh(memo_hit, memo); ++ci; }
+                    else state = ST_MESH;
+                } else if (p.type == PRIM_MESH) {
                     const V3 wo = leaf.ax.O(), wd = leaf.ax.D();
                     const V3 lo = xform_point(p.to_local, wo);
                     const V3 ld = xform_vector(p.to_local, wd);
@@ -1232,8 +1262,12 @@ struct NestedTraversal {
         }
     }
 
-    RSB_HD bool begin(const V3& o, const V3& d) {
+    RSB_HD bool begin(const V3& o, const V3& d) { return begin_t<false>(o, d); }
+
+    template <bool SPLIT>
+    RSB_HD bool begin_t(const V3& o, const V3& d) {
         leaf.ax.set(leaf.ax.p, o, d);
+        memo_prim = -1;
         rec->u = rec->v = rec->w = 0.0f;
         rec->node = -1;
         rec->mesh_node = -1;
@@ -1247,7 +1281,35 @@ struct NestedTraversal {
         min_range = c.min_range;
         max_range = c.max_range;
         state = ST_WORLD;
-        run_world();
+        run_world_t<SPLIT>();
+        return state != ST_DONE;
+    }
+
+    // split pipeline: Mesh.hit of candidate cand[ci] was answered elsewhere
+    RSB_HD bool resume_split(bool hit, const MeshHit& m) {
+        memo_prim = cand[ci];
+        memo_hit = hit;
+        memo = m;
+        accept_mesh(hit, m);
+        ++ci;
+        state = ST_WORLD;
+        run_world_t<true>();
+        return state != ST_DONE;
+    }
+
+    // a walk suspended by the split pipeline in front of Mesh.hit, carried on by the nested loop (step()): MeshData.trace's
+    // preamble for candidate cand[ci] (mesh.pyx:506-518)
+    RSB_HD bool enter_mesh() {
+        const Prim& p = sc->prims[cand[ci]];
+        const V3 wo = leaf.ax.O(), wd = leaf.ax.D();
+        const V3 lo = xform_point(p.to_local, wo);
+        const V3 ld = xform_vector(p.to_local, wd);
+        max.set(leaf.mesh_axbuf, lo, ld);
+        mleaf.mesh = &sc->meshes[p.mesh];
+        mleaf.o = lo;
+        mleaf.rs = mesh_rayspace(ld);
+        if (kd_begin(mleaf.mesh->tree, max, mc)) state = ST_MESH;
+        else { ++ci; state = ST_WORLD; run_world(); }
         return state != ST_DONE;
     }
 
@@ -1285,14 +1347,7 @@ struct NestedTraversal {
             finished = false;
         }
         if (finished) {
-            if (leaf_hit && mh.t <= distance) {
-                const int id = cand[ci];
-                distance = mh.t;
-                rec->t = mh.t; rec->prim = id; rec->leaf = id; rec->code = mh.tri; rec->flip = 0;
-                rec->mesh_node = mh.node;
-                rec->u = mh.u; rec->v = mh.v; rec->w = mh.w;
-                found = true;
-            }
+            accept_mesh(leaf_hit, mh);
             ++ci;
             state = ST_WORLD;
             run_world();

@@ -1,7 +1,6 @@
 // rsb_kernels.cuh -- sm_100a kernels of the hot path.
 //
-//  k_hit_batch      World.hit over a ray batch (1 thread = 1 ray, grid-stride)
-//  k_hit_sweep      same, rays generated on device from (seed, index), results reduced on device
+//  (World.hit over ray batches: rsb_trav.cuh)
 //  k_contains_batch World.contains over a point batch
 //  k_render         Observer._render_pixel for a pinhole camera: persistent threads, 1 thread = 1 pixel
 //                   stream, one path SEGMENT per loop trip (no lane waits for a long path), finished
@@ -93,26 +92,79 @@ __host__ __device__ inline StageLayout stage_layout(int n_nodes, int n_items, in
     return l;
 }
 
-__device__ __forceinline__ void copy16(void* dst, const void* src, int bytes) {
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
-}
+// 1-D bulk copies global -> shared through the TMA engine (cp.async.bulk, completion counted on an mbarrier in bytes):
+// one elected thread issues up to a few descriptors-free copies and the CTA waits on the barrier's phase, while the
+// loads the threads issued before (slot state, queue entries) stay in flight.  Sizes and addresses are multiples of 16.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct BulkStage {
+    uint64_t* bar;
+    // all threads of the CTA; `bar` is 8 bytes of shared memory
+    __device__ __forceinline__ void init(uint64_t* b) {
+        bar = b;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // thread 0: announce the total, then issue the copies
+    __device__ __forceinline__ void expect(uint32_t total_bytes) const {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(total_bytes) : "memory");
+    }
+    __device__ __forceinline__ void copy(void* dst, const void* src, uint32_t bytes) const {
+        if (bytes == 0) return;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                     "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                     : "memory");
+    }
+    // all threads: until phase `parity` of the barrier has completed
+    __device__ __forceinline__ void wait(uint32_t parity) const {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "RSB_BULK_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra RSB_BULK_DONE;\n"
+            "bra RSB_BULK_WAIT;\n"
+            "RSB_BULK_DONE:\n"
+            "}\n" ::"r"(smem_addr(bar)),
+            "r"(parity)
+            : "memory");
+    }
+};
 
 // n_items: number of leaf item ids of the world tree.  STAGED is a compile-time flag (RSB_FEAT_STAGED) so that
 // every load through the redirected pointers is compiled as a shared-memory load, not a generic one.
 template <bool STAGED>
 __device__ __forceinline__ void stage_scene(Scene& sc, unsigned char* smem, int n_items) {
     if (!STAGED) return;
+    __shared__ __align__(8) uint64_t stage_bar;
     StageLayout l = stage_layout(sc.world.n_nodes, n_items, sc.n_prims);
-    copy16(smem, sc.world.nodes, l.nodes_bytes);
-    // item list: copy whole 16-B words (the allocation is padded to 16 B)
-    copy16(smem + l.nodes_bytes, sc.world.items, l.items_bytes);
-    copy16(smem + l.nodes_bytes + l.items_bytes, sc.prims, l.prims_bytes);
-    __syncthreads();
+    BulkStage bs;
+    bs.init(&stage_bar);
+    if (threadIdx.x == 0) {
+        bs.expect((uint32_t)l.total);
+        bs.copy(smem, sc.world.nodes, (uint32_t)l.nodes_bytes);
+        // item list: whole 16-B words (the allocation is padded to 16 B)
+        bs.copy(smem + l.nodes_bytes, sc.world.items, (uint32_t)l.items_bytes);
+        bs.copy(smem + l.nodes_bytes + l.items_bytes, sc.prims, (uint32_t)l.prims_bytes);
+    }
+    bs.wait(0);
     sc.world.nodes = reinterpret_cast<const KdNode*>(smem);
     sc.world.items = reinterpret_cast<const int32_t*>(smem + l.nodes_bytes);
     sc.prims = reinterpret_cast<const Prim*>(smem + l.nodes_bytes + l.items_bytes);
+}
+
+// one region, staged the same way (material rows of k_wf_shade, spectral tables of k_wf_finalize)
+__device__ __forceinline__ void stage_region(uint64_t* bar, void* dst, const void* src, int bytes) {
+    BulkStage bs;
+    bs.init(bar);
+    if (threadIdx.x == 0) {
+        bs.expect((uint32_t)bytes);
+        bs.copy(dst, src, (uint32_t)bytes);
+    }
+    bs.wait(0);
 }
 
 // RayAx storage of the calling thread (rsb_geom.h): RSB_AX_WORDS columns of blockDim.x doubles behind the staged
@@ -252,180 +304,7 @@ __device__ __forceinline__ bool mesh_leaf_coop(const Scene& sc, const CoopSmem& 
     return true;
 }
 
-// ---------------------------------------------------------------------------------------------
-template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? RSB_MESH_MIN_BLOCKS : 5))
-k_hit_batch(Scene sc, int n_items, long long n, const double* __restrict__ origins,
-            const double* __restrict__ directions, const double* __restrict__ max_distance,
-            int32_t* __restrict__ out_prim, double* __restrict__ out_t, int32_t* __restrict__ out_sub,
-            uint8_t* __restrict__ out_flags, int32_t* __restrict__ out_node, double* __restrict__ out_geom,
-            float* __restrict__ out_uvw, DevCounters* counters) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
-    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, n_items);
-    typename StatsSel<COUNT>::type stats;
-    KdStackEntry stack[RSB_KD_STACK];
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
-        V3 d = v3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
-        double md = max_distance ? max_distance[i] : RSB_INF;
-        HitRec rec;
-        bool hit = world_hit_ax<FEAT, RSB_RENDER_THREADS>(sc, o, d, md, stack, &rec, stats, axbuf);
-        if (hit) {
-            Isect is;
-            world_hit_geometry<FEAT>(sc, o, d, rec, &is);
-            out_prim[i] = rec.prim;
-            out_t[i] = rec.t;
-            out_sub[i] = rec.code;
-            out_flags[i] = (uint8_t)(is.exiting ? 1 : 0);
-            if (out_node) { out_node[2 * i] = rec.node; out_node[2 * i + 1] = rec.mesh_node; }
-            if (out_geom) {
-                double* g = out_geom + 12 * i;
-                g[0] = is.hit.x; g[1] = is.hit.y; g[2] = is.hit.z;
-                g[3] = is.inside.x; g[4] = is.inside.y; g[5] = is.inside.z;
-                g[6] = is.outside.x; g[7] = is.outside.y; g[8] = is.outside.z;
-                g[9] = is.normal.x; g[10] = is.normal.y; g[11] = is.normal.z;
-            }
-            if (out_uvw) { out_uvw[3 * i] = rec.u; out_uvw[3 * i + 1] = rec.v; out_uvw[3 * i + 2] = rec.w; }
-        } else {
-            out_prim[i] = -1;
-            out_t[i] = RSB_INF;
-            out_sub[i] = -1;
-            out_flags[i] = 0;
-            if (out_node) { out_node[2 * i] = -1; out_node[2 * i + 1] = -1; }
-            if (out_geom) { double* g = out_geom + 12 * i; for (int k = 0; k < 12; ++k) g[k] = 0.0; }
-            if (out_uvw) { out_uvw[3 * i] = 0; out_uvw[3 * i + 1] = 0; out_uvw[3 * i + 2] = 0; }
-        }
-    }
-    if (COUNT) {
-        __syncwarp();
-        flush_stats(stats, counters);
-    }
-}
-
-// rays from `origin` toward target + (jx, jy, 0)*half_window, (jx, jy) uniform in [-1, 1) from Philox(seed, index)
-template <bool COUNT, int FEAT>
-__global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? 3 : ((FEAT & RSB_FEAT_MESH) ? RSB_MESH_MIN_BLOCKS : 5))
-k_hit_sweep(Scene sc, int n_items, long long n, long long first_index, unsigned long long seed,
-            double ox, double oy, double oz, double tx, double ty, double tz, double half_window,
-            unsigned long long* out_hits, double* out_sum_t, unsigned long long* out_xor_prim, DevCounters* counters) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
-    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, n_items);
-    typename StatsSel<COUNT>::type stats;
-    KdStackEntry stack[RSB_KD_STACK];
-    unsigned long long hits = 0, xr = 0;
-    double sum_t = 0.0;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    V3 o = v3(ox, oy, oz);
-    // Persistent lanes with batched refill (Aila & Laine): every lane owns the rays i, i + stride, ... and advances
-    // its current ray by ONE traversal unit per trip; lanes whose ray has ended pick up their next ray only when at
-    // least RSB_REFILL_LANES lanes are waiting (or nothing else is left to do), so the ray set-up code runs with a
-    // well filled warp instead of once per finished lane.  Rays of different lengths no longer hold a whole warp
-    // until the longest one is done.  Scenes with meshes: the unit is one MESH traversal unit (NestedTraversal).
-    if constexpr ((FEAT & RSB_FEAT_MESH) != 0) {
-        HitRec rec;
-        NestedTraversal<FEAT, RSB_RENDER_THREADS, typename StatsSel<COUNT>::type> t;
-        t.init(sc, RSB_INF, stack, &rec, stats, axbuf);
-        const CoopSmem cs = coop_carve(axbuf);
-        bool active = false;
-        long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
-        for (;;) {
-            const bool want = !active && next < n;
-            const unsigned want_mask = __ballot_sync(RSB_FULL_MASK, want);
-            const unsigned active_mask = __ballot_sync(RSB_FULL_MASK, active);
-            if (active_mask == 0 && want_mask == 0) break;
-            bool ended = false;
-            if (want && (__popc(want_mask) >= RSB_REFILL_LANES || active_mask == 0)) {
-                cur = next;
-                next += stride;
-                Philox4x32 px;
-                px.init(seed, (unsigned long long)(first_index + cur), 0u);
-                double u1 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-                double u2 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-                V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
-                V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
-                active = t.begin(o, d);
-                ended = !active;
-            }
-            // one mesh traversal unit for every lane that is inside a mesh: descend, pooled triangle tests, resolve
-            if (active) {
-                t.step_descend();
-                coop_publish(cs, t.mleaf.rs, (int)(t.mleaf.mesh - sc.meshes));
-            }
-            const double d0 = RSB_INF < t.mc.max_range ? RSB_INF : t.mc.max_range;
-            const bool leaf_hit = mesh_leaf_coop(sc, cs, active, t.m_off, t.m_cnt, d0, RSB_INF, &t.mh, stats);
-            if (active) {
-                active = t.step_resolve(leaf_hit);
-                ended = !active;
-            }
-            if (ended && t.finish()) {
-                hits += 1;
-                sum_t += rec.t;
-                xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + cur);
-            }
-        }
-    } else {
-        HitRec rec;
-        WorldLeaf<typename StatsSel<COUNT>::type, FEAT, RSB_RENDER_THREADS> leaf;
-        leaf.sc = &sc;
-        leaf.max_distance = RSB_INF;
-        leaf.mesh_stack = stack + (RSB_KD_STACK / 2);
-        leaf.mesh_axbuf = axbuf + 9 * RSB_RENDER_THREADS;
-        leaf.best = &rec;
-        leaf.stats = &stats;
-        KdCursor c;
-        c.node = 0; c.sp = 0; c.min_range = 0; c.max_range = 0;
-        bool active = false;
-        long long next = (long long)blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
-        for (;;) {
-            const bool want = !active && next < n;
-            const unsigned want_mask = __ballot_sync(RSB_FULL_MASK, want);
-            const unsigned active_mask = __ballot_sync(RSB_FULL_MASK, active);
-            if (active_mask == 0 && want_mask == 0) break;
-            if (want && (__popc(want_mask) >= RSB_REFILL_LANES || active_mask == 0)) {
-                cur = next;
-                next += stride;
-                Philox4x32 px;
-                px.init(seed, (unsigned long long)(first_index + cur), 0u);
-                double u1 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-                double u2 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
-                V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
-                V3 d = normalise(v3(p.x - o.x, p.y - o.y, p.z - o.z));
-                leaf.ax.set(axbuf, o, d);
-                rec.u = rec.v = rec.w = 0.0f;
-                rec.node = -1;
-                rec.mesh_node = -1;
-                active = kd_begin(sc.world, leaf.ax, c);
-            }
-            if (active) {
-                int r = kd_advance(sc.world, leaf.ax, stack, c, leaf, stats, &rec.node);
-                if (r != KD_MORE) {
-                    active = false;
-                    if (r == KD_HIT) {
-                        hits += 1;
-                        sum_t += rec.t;
-                        xr ^= (unsigned long long)(unsigned)rec.prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + cur);
-                    }
-                }
-            }
-        }
-    }
-    __syncwarp();
-    hits = warp_sum(hits);
-#pragma unroll
-    for (int k = 16; k > 0; k >>= 1) {
-        sum_t += __shfl_down_sync(RSB_FULL_MASK, sum_t, k);
-        xr ^= __shfl_down_sync(RSB_FULL_MASK, xr, k);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(out_hits, hits);
-        atomicAdd(out_sum_t, sum_t);
-        atomicXor(out_xor_prim, xr);
-    }
-    if (COUNT) flush_stats(stats, counters);
-}
+// (World.hit over ray batches -- rsb_hit_batch, rsb_hit_sweep -- is the kernel pipeline of rsb_trav.cuh)
 
 __global__ void __launch_bounds__(128)
 k_contains_batch(Scene sc, long long n, const double* __restrict__ points, int cap, int32_t* __restrict__ out_count,
@@ -902,8 +781,8 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
     if (a.tables_staged) {
         unsigned char* base = smem + smem_used;
         int mat_bytes = ((sp.n_materials * (int)sizeof(Material) + 15) / 16) * 16;
-        copy16(base, a.sp.mats, mat_bytes);
-        __syncthreads();
+        __shared__ __align__(8) uint64_t mat_bar;
+        stage_region(&mat_bar, base, a.sp.mats, mat_bytes);
         sp.mats = reinterpret_cast<const Material*>(base);
         smem_used += mat_bytes;
     }
@@ -931,8 +810,8 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     if (a.tables_staged) {
         // tables and their logs are contiguous in HBM: [n_tables][bins] x 2
         tab_bytes = ((sp.n_tables * sp.bins * 16 + 15) / 16) * 16;
-        copy16(smem, a.sp.tables, tab_bytes);
-        __syncthreads();
+        __shared__ __align__(8) uint64_t tab_bar;
+        stage_region(&tab_bar, smem, a.sp.tables, tab_bytes);
         sp.tables = reinterpret_cast<const double*>(smem);
         sp.tables_ln = sp.tables + (size_t)sp.n_tables * sp.bins;
     }

@@ -1,0 +1,700 @@
+// rsb_trav.cuh -- World.hit over ray arrays as a pipeline of small kernels (sm_100a).
+//
+// Round 1 ran the whole two-level query (world kd-tree -> BoundPrimitive -> Mesh.hit -> mesh kd-tree -> triangles) in
+// one kernel: 118 registers (4 CTAs of 128 threads per SM), a 1 KB per-thread stack in local memory, and every lane of
+// a warp at a different point of the hierarchy (profiles/r1b_ncu_full_k_hit_sweep_mesh.txt: 8.7 of 32 lanes active,
+// 23 % of the warps an SM can hold, long-scoreboard stalls 54 %).  Here the query is cut where the reference's call
+// graph is cut:
+//
+//   k_rq_begin    the world-level walk (world tree, AABB pre-tests, analytic / CSG primitives) up to the first
+//                 Mesh.hit call; rays that meet none finish here, the others are PARKED (walk state -> HBM) and queued
+//   k_rq_mesh     Mesh.hit for the queue: nothing but the mesh kd-tree walk and the triangle tests, persistent lanes
+//                 refilled from the queue, far-child stack in shared memory, a bounded number of node visits per trip
+//                 (rsb_trav.h kd_visit), triangle tests of all lanes standing at a leaf pooled over the warp
+//   k_rq_resume   parked walks carry on with Mesh.hit's answer (kept as the ray's memo: the reference repeats the very
+//                 same Mesh.hit call from every world leaf that lists the mesh)
+//   k_rq_world    mesh-free scenes: the world walk in the same visit-per-trip form, one kernel
+//
+// Per ray the sequence of node visits, AABB tests, primitive tests and triangle tests is the reference's
+// (kdtree3d.pyx:589-700, acceleration/kdtree.pyx:73-122, mesh.pyx:506-713); rsb_trav.h holds the serial statement of
+// the same pipeline, which the CPU suite pins against the reference's goldens.
+#pragma once
+#include "rsb_kernels.cuh"
+#include "rsb_trav.h"
+
+namespace rsb {
+
+#define RQ_THREADS RSB_RENDER_THREADS
+#ifndef RQ_SCAP
+#define RQ_SCAP 8            // far-child stack entries kept in shared memory (deeper ones spill to local memory)
+#endif
+#ifndef RQ_VISITS
+#define RQ_VISITS 6          // node visits per lane per trip
+#endif
+#ifndef RQ_LEAF_MIN
+#define RQ_LEAF_MIN 8        // lanes standing at a leaf that trigger the leaf phase while other lanes still descend
+#endif
+#ifndef RQ_REFILL
+#define RQ_REFILL 8          // idle lanes that trigger a refill from the queue
+#endif
+#ifndef RQ_MESH_BLOCKS
+#define RQ_MESH_BLOCKS 7     // resident CTAs per SM the register allocation of k_rq_mesh must allow
+#endif
+#ifndef RQ_WORLD_BLOCKS
+#define RQ_WORLD_BLOCKS 5
+#endif
+#ifndef RQ_POOL_CAP
+#define RQ_POOL_CAP 64       // (ray, triangle) pairs a warp tests per pooled round
+#endif
+#define RQ_WORLD_STACK (RSB_KD_STACK / 2)   // world-level far-child entries a parked walk carries: the world half of the stack
+#define RQ_MAX_ROUNDS 2      // Mesh.hit rounds before the last resume finishes whatever is left in place
+
+// A parked world-level walk (NestedTraversal in state ST_MESH, nothing of the mesh touched yet) + the Mesh.hit answer
+struct __align__(16) RqSusp {
+    double min_range, max_range;
+    double distance, best_t;
+    int32_t node, sp, leaf_node, item_offset;
+    int32_t item_count, item_base, nc, ci;
+    int32_t cand[4];
+    int32_t flags, best_prim, best_leaf, best_code;         // flags: 1 have_leaf, 2 found
+    int32_t best_flip, best_mesh_node, memo_prim, memo_hit;
+    float best_u, best_v, best_w;
+    int32_t pad0;
+    double memo_t;                                          // written by k_rq_mesh from here on
+    int32_t memo_tri, memo_node;
+    float memo_u, memo_v, memo_w;
+    int32_t pad1;
+};
+
+// Device arrays of one batch of queries (capacity `cap`)
+struct RqBuf {
+    const double* ray;        // [6][ray_stride] origin xyz, direction xyz
+    const double* md;         // [n] ray.max_distance, or null: md_all
+    double md_all;
+    long long ray_stride;
+    double* hit_t;            // [cap]
+    int4* hit_a;              // [cap] primitive (-1: miss), leaf row, code, flip
+    float4* hit_uvw;          // [cap] u, v, w, mesh kd leaf (int bits)
+    int32_t* hit_node;        // [cap] world kd leaf, or null
+    RqSusp* susp;             // [cap]
+    KdStackEntry* susp_stack; // [cap][RQ_WORLD_STACK]
+    int2* queue;              // [RQ_MAX_ROUNDS + 1][cap] (query, mesh primitive row)
+    unsigned int* ctr;        // [0 .. RQ_MAX_ROUNDS] queue lengths, [4 ..] fetch cursors of the mesh rounds, [8] of k_rq_world
+    long long cap;
+};
+
+template <int CAP, int T>
+struct SmemKdStack {
+    double* t;             // the thread's column: entry k at t[k * T]
+    int32_t* n;
+    KdStackEntry* spill;   // entries CAP.. (local memory; touched by the rare deep walk only)
+    __device__ __forceinline__ void push(int sp, int node, double tmax) {
+        if (sp < CAP) { t[sp * T] = tmax; n[sp * T] = node; }
+        else { spill[sp - CAP].tmax = tmax; spill[sp - CAP].node = node; }
+    }
+    __device__ __forceinline__ int node(int sp) const { return sp < CAP ? n[sp * T] : spill[sp - CAP].node; }
+    __device__ __forceinline__ double tmax(int sp) const { return sp < CAP ? t[sp * T] : spill[sp - CAP].tmax; }
+};
+
+// ---- clients: where a query's ray comes from and where its answer goes -------------------------------------
+struct RqArrayClient {
+    RqBuf b;
+    __device__ __forceinline__ bool fetch(long long i, V3& o, V3& d, double& md) const {
+        const long long s = b.ray_stride;
+        o = v3(b.ray[i], b.ray[s + i], b.ray[2 * s + i]);
+        d = v3(b.ray[3 * s + i], b.ray[4 * s + i], b.ray[5 * s + i]);
+        md = b.md ? b.md[i] : b.md_all;
+        return true;
+    }
+    // reached by all 32 lanes together
+    __device__ __forceinline__ void commit(long long i, bool finished, bool hit, const HitRec& rec) const {
+        if (!finished) return;
+        if (hit) {
+            b.hit_t[i] = rec.t;
+            b.hit_a[i] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
+            b.hit_uvw[i] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
+            if (b.hit_node) b.hit_node[i] = rec.node;
+        } else {
+            b.hit_a[i] = make_int4(-1, -1, -1, 0);
+        }
+    }
+    __device__ __forceinline__ void count_rays(DevCounters*, unsigned long long) const {}
+};
+
+// ---- parking ----------------------------------------------------------------------------------------------
+template <class NT>
+__device__ __forceinline__ void rq_park(const NT& t, const HitRec& rec, const KdStackEntry* stack, RqSusp* out, KdStackEntry* out_stack) {
+    RqSusp s;
+    s.min_range = t.min_range; s.max_range = t.max_range;
+    s.distance = t.distance; s.best_t = rec.t;
+    s.node = t.node; s.sp = t.sp; s.leaf_node = t.leaf_node; s.item_offset = t.item_offset;
+    s.item_count = t.item_count; s.item_base = t.item_base; s.nc = t.nc; s.ci = t.ci;
+    s.cand[0] = t.cand[0]; s.cand[1] = t.cand[1]; s.cand[2] = t.cand[2]; s.cand[3] = t.cand[3];
+    s.flags = (t.have_leaf ? 1 : 0) | (t.found ? 2 : 0);
+    s.best_prim = rec.prim; s.best_leaf = rec.leaf; s.best_code = rec.code;
+    s.best_flip = rec.flip; s.best_mesh_node = rec.mesh_node;
+    s.memo_prim = t.cand[t.ci];      // the primitive k_rq_mesh answers for; the answer becomes the memo
+    s.memo_hit = 0;
+    s.best_u = rec.u; s.best_v = rec.v; s.best_w = rec.w;
+    s.pad0 = 0;
+    int4* dst = reinterpret_cast<int4*>(out);
+    const int4* src = reinterpret_cast<const int4*>(&s);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = src[k];
+    for (int k = 0; k < t.sp; ++k) reinterpret_cast<int4*>(out_stack)[k] = reinterpret_cast<const int4*>(stack)[k];
+}
+
+template <class NT>
+__device__ __forceinline__ void rq_unpark(NT& t, HitRec& rec, KdStackEntry* stack, const RqSusp* in, const KdStackEntry* in_stack, bool* memo_hit,
+                                          MeshHit* memo) {
+    RqSusp s;
+    int4* dst = reinterpret_cast<int4*>(&s);
+    const int4* src = reinterpret_cast<const int4*>(in);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(RqSusp) / 16); ++k) dst[k] = src[k];
+    t.min_range = s.min_range; t.max_range = s.max_range;
+    t.distance = s.distance; rec.t = s.best_t;
+    t.node = s.node; t.sp = s.sp; t.leaf_node = s.leaf_node; t.item_offset = s.item_offset;
+    t.item_count = s.item_count; t.item_base = s.item_base; t.nc = s.nc; t.ci = s.ci;
+    t.cand[0] = s.cand[0]; t.cand[1] = s.cand[1]; t.cand[2] = s.cand[2]; t.cand[3] = s.cand[3];
+    t.have_leaf = (s.flags & 1) != 0;
+    t.found = (s.flags & 2) != 0;
+    rec.prim = s.best_prim; rec.leaf = s.best_leaf; rec.code = s.best_code;
+    rec.flip = s.best_flip; rec.mesh_node = s.best_mesh_node; rec.node = -1;
+    rec.u = s.best_u; rec.v = s.best_v; rec.w = s.best_w;
+    t.state = NT::ST_MESH;
+    *memo_hit = s.memo_hit != 0;
+    memo->t = s.memo_t; memo->tri = s.memo_tri; memo->node = s.memo_node;
+    memo->u = s.memo_u; memo->v = s.memo_v; memo->w = s.memo_w;
+    for (int k = 0; k < s.sp; ++k) reinterpret_cast<int4*>(stack)[k] = reinterpret_cast<const int4*>(in_stack)[k];
+}
+
+// Warp-aggregated append of the lanes with `want` to a queue: returns the lane's position (valid where want)
+__device__ __forceinline__ unsigned int rq_queue_slot(unsigned int* counter, bool want) {
+    const unsigned m = __ballot_sync(RSB_FULL_MASK, want);
+    if (m == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(RSB_FULL_MASK, base, 0);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+// ---- k_rq_begin / k_rq_resume ---------------------------------------------------------------------------
+// RESUME: walks parked by the previous round carry on with Mesh.hit's answer; LAST: a walk that meets yet another
+// mesh is finished in place by the nested loop instead of being parked again.
+template <bool COUNT, int FEAT, class Client, bool RESUME, bool LAST>
+__global__ void __launch_bounds__(RQ_THREADS, (FEAT & RSB_FEAT_CSG) ? 3 : 4)
+k_rq_walk(Scene sc, int n_items, Client cl, RqBuf b, long long n, int round, DevCounters* counters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
+    stage_scene<(FEAT & RSB_FEAT_STAGED) != 0>(sc, smem, n_items);
+    typedef typename StatsSel<COUNT>::type Stats;
+    Stats stats;
+    KdStackEntry stack[RSB_KD_STACK];
+    HitRec rec;
+    NestedTraversal<FEAT, RQ_THREADS, Stats> t;
+    const long long total = RESUME ? (long long)b.ctr[round] : n;
+    const int2* queue_in = b.queue + (size_t)round * b.cap;
+    int2* queue_out = b.queue + (size_t)(RESUME ? round + 1 : 0) * b.cap;
+    unsigned int* ctr_out = b.ctr + (RESUME ? round + 1 : 0);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long traced = 0;
+    for (long long k0 = (long long)blockIdx.x * blockDim.x; k0 < total; k0 += stride) {
+        const long long k = k0 + threadIdx.x;
+        long long i = k;
+        bool valid = k < total;
+        if (RESUME && valid) i = queue_in[k].x;
+        V3 o, d;
+        double md = RSB_INF;
+        if (valid) valid = cl.fetch(i, o, d, md);
+        bool alive = false, hit = false;
+        if (valid) {
+            t.init(sc, md, stack, &rec, stats, axbuf);
+            if (RESUME) {
+                bool mhit;
+                MeshHit memo;
+                rq_unpark(t, rec, stack, b.susp + i, b.susp_stack + (size_t)i * RQ_WORLD_STACK, &mhit, &memo);
+                t.leaf.ax.set(axbuf, o, d);
+                alive = t.resume_split(mhit, memo);
+            } else {
+                traced = traced + 1;
+                alive = t.template begin_t<true>(o, d);
+            }
+            if (LAST && alive) {
+                alive = t.enter_mesh();
+                while (alive) alive = t.step();
+            }
+            if (!alive) hit = t.finish();
+        }
+        const unsigned int q = rq_queue_slot(ctr_out, alive);
+        if (alive) {
+            rq_park(t, rec, stack, b.susp + i, b.susp_stack + (size_t)i * RQ_WORLD_STACK);
+            queue_out[q] = make_int2((int)i, t.cand[t.ci]);
+        }
+        cl.commit(i, valid && !alive, hit, rec);
+    }
+    if (COUNT) {
+        __syncwarp();
+        traced = warp_sum(traced);
+        if ((threadIdx.x & 31) == 0 && traced) atomicAdd(&counters->rays, traced);
+        flush_stats(stats, counters);
+    }
+}
+
+// ---- k_rq_mesh --------------------------------------------------------------------------------------------
+struct MeshPool {
+    int32_t* rs_pack;     // [T] ix | iy << 2 | iz << 4 of the lane's ray-space permutation (mesh.pyx:566-610)
+    float* rs_s;          // [3][T] sx, sy, sz
+    int32_t* mesh_idx;    // [T]
+    float4* res;          // warp: [CAP] (t, u, v, w); t = NaN: no hit
+    int32_t* prefix;      // warp: [33 (+3)]
+    int32_t* leaf_off;    // warp: [32]
+    int32_t* res_tri;     // warp: [CAP]
+    const double* ax0;    // RayAx storage of thread 0: rows 0..2 mesh-local origin, row 9 ray.max_distance
+};
+
+#define RQ_AX_ROWS 10
+#define RQ_POOL_WARP_BYTES (RQ_POOL_CAP * 16 + (36 + 32 + RQ_POOL_CAP) * 4)
+#define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 20 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
+
+// MeshData._trace_leaf (mesh.pyx:520-563) for every lane with `in_leaf`, the (ray, triangle) pairs dealt out evenly
+// over the warp.  Same scheme as mesh_leaf_coop (rsb_kernels.cuh); here a lane's ray-space transform is published once
+// per ray, not once per trip.  All 32 lanes.
+template <class Stats>
+__device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& cs, bool in_leaf, int off, int cnt, double d0, MeshHit* mh,
+                                               Stats& stats) {
+    constexpr int T = RQ_THREADS;
+    const int lane = threadIdx.x & 31;
+    const int tid0 = threadIdx.x & ~31;
+    const int c = in_leaf ? cnt : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(RSB_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - c;
+    const int total = __shfl_sync(RSB_FULL_MASK, incl, 31);
+    if (total == 0) return false;
+    __syncwarp();
+    cs.prefix[lane] = excl;
+    if (lane == 31) cs.prefix[32] = total;
+    cs.leaf_off[lane] = off;
+    double distance = d0;
+    int closest = -1;
+    float cu = 0, cv = 0, cw = 0;
+    for (int base = 0; base < total; base += RQ_POOL_CAP) {
+        __syncwarp();
+        const int lim = total - base < RQ_POOL_CAP ? total - base : RQ_POOL_CAP;
+        for (int p = lane; p < lim; p += 32) {
+            const int g = base + p;
+            int lo = 0, hi = 32;           // prefix[lo] <= g < prefix[hi]
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int mid = (lo + hi) >> 1;
+                if (cs.prefix[mid] <= g) lo = mid; else hi = mid;
+            }
+            const int ot = tid0 + lo;      // the owner's thread index within the CTA
+            const Mesh& m = sc.meshes[cs.mesh_idx[ot]];
+            const int tri = m.tree.items[cs.leaf_off[lo] + (g - cs.prefix[lo])];
+            const double* ax = cs.ax0 + ot;
+            const V3 o = v3(ax[0], ax[T], ax[2 * T]);
+            const double md = ax[9 * T];
+            RaySpace rs;
+            const int pk = cs.rs_pack[ot];
+            rs.ix = pk & 3; rs.iy = (pk >> 2) & 3; rs.iz = (pk >> 4) & 3;
+            rs.sx = cs.rs_s[ot]; rs.sy = cs.rs_s[T + ot]; rs.sz = cs.rs_s[2 * T + ot];
+            float h[4];
+            stats.tri_test();
+            const bool hit = mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, md, rs, h);
+            cs.res_tri[p] = tri;
+            cs.res[p] = hit ? make_float4(h[3], h[0], h[1], h[2]) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (c > 0) {
+            // the owner replays `t < distance`, first of equal-t triangles wins, over its own results in leaf order
+            const int j0 = base > excl ? base - excl : 0;
+            const int j1 = base + RQ_POOL_CAP - excl < c ? base + RQ_POOL_CAP - excl : c;
+            for (int j = j0; j < j1; ++j) {
+                const int p = excl + j - base;
+                const float4 r = cs.res[p];
+                if (r.x == r.x) {
+                    const double t = (double)r.x;
+                    if (t < distance) {
+                        distance = t;
+                        closest = cs.res_tri[p];
+                        cu = r.y; cv = r.z; cw = r.w;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (closest < 0) return false;
+    mh->t = (double)(float)distance;
+    mh->tri = closest;
+    mh->u = cu; mh->v = cv; mh->w = cw;
+    return true;
+}
+
+__device__ __forceinline__ void rq_answer(RqSusp* s, bool hit, const MeshHit& mh) {
+    if (hit) {
+        int4 a;
+        a.x = __double2loint(mh.t); a.y = __double2hiint(mh.t); a.z = mh.tri; a.w = mh.node;
+        reinterpret_cast<int4*>(&s->memo_t)[0] = a;
+        reinterpret_cast<float4*>(&s->memo_u)[0] = make_float4(mh.u, mh.v, mh.w, 0.f);
+        s->memo_hit = 1;
+    } else {
+        s->memo_hit = 0;
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RQ_THREADS, RQ_MESH_BLOCKS)
+k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int T = RQ_THREADS;
+    typedef typename StatsSel<COUNT>::type Stats;
+    Stats stats;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double* ax0 = reinterpret_cast<double*>(smem);
+    RayAx<T> ax;
+    ax.p = ax0 + tid;
+    ax.unsafe = 0;
+    KdStackEntry spill[RSB_KD_STACK - RQ_SCAP];
+    SmemKdStack<RQ_SCAP, T> stk;
+    stk.t = ax0 + RQ_AX_ROWS * T + tid;
+    stk.n = reinterpret_cast<int32_t*>(ax0 + (RQ_AX_ROWS + RQ_SCAP) * T) + tid;
+    stk.spill = spill;
+    MeshPool cs;
+    {
+        unsigned char* base = smem + RQ_AX_ROWS * 8 * T + RQ_SCAP * 12 * T;
+        cs.rs_pack = reinterpret_cast<int32_t*>(base);
+        cs.rs_s = reinterpret_cast<float*>(base + 4 * T);
+        cs.mesh_idx = reinterpret_cast<int32_t*>(base + 16 * T);
+        unsigned char* w = base + 20 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
+        cs.res = reinterpret_cast<float4*>(w);
+        cs.prefix = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
+        cs.leaf_off = cs.prefix + 36;
+        cs.res_tri = cs.leaf_off + 32;
+        cs.ax0 = ax0;
+    }
+    const unsigned int n_q = b.ctr[round];
+    const int2* queue = b.queue + (size_t)round * b.cap;
+    unsigned int* cursor = b.ctr + 4 + round;
+    enum { IDLE = 0, DESCEND = 1, LEAF = 2 };
+    int st = IDLE, q = 0, node = 0, sp = 0, off = 0, cnt = 0;
+    double tmin = 0.0, tmax = 0.0, md = 0.0;
+    const KdNode* nodes = nullptr;
+    bool exhausted = n_q == 0;
+    for (;;) {
+        // ---- refill: idle lanes take the next queries, a batch at a time so that the set-up runs with a filled warp
+        const unsigned idle = __ballot_sync(RSB_FULL_MASK, st == IDLE);
+        if (idle == RSB_FULL_MASK && exhausted) break;
+        if (!exhausted && (idle == RSB_FULL_MASK || __popc(idle) >= RQ_REFILL)) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(idle));
+            base = __shfl_sync(RSB_FULL_MASK, base, 0);
+            if (base + (unsigned int)__popc(idle) >= n_q) exhausted = true;
+            const unsigned int k = base + __popc(idle & ((1u << lane) - 1));
+            if (st == IDLE && k < n_q) {
+                const int2 e = queue[k];
+                q = e.x;
+                const Prim& P = sc.prims[e.y];
+                const long long s = b.ray_stride;
+                const V3 o = v3(b.ray[q], b.ray[s + q], b.ray[2 * s + q]);
+                const V3 d = v3(b.ray[3 * s + q], b.ray[4 * s + q], b.ray[5 * s + q]);
+                md = b.md ? b.md[q] : b.md_all;
+                // Mesh.hit: ray into mesh space, MeshData.trace's ray-space shear and bounds clip (mesh.pyx:506-518, 566-610)
+                const V3 lo = xform_point(P.to_local, o);
+                const V3 ld = xform_vector(P.to_local, d);
+                ax.set(ax.p, lo, ld);
+                ax.p[9 * T] = md;
+                const Mesh& m = sc.meshes[P.mesh];
+                const RaySpace rs = mesh_rayspace(ld);
+                cs.rs_pack[tid] = rs.ix | (rs.iy << 2) | (rs.iz << 4);
+                cs.rs_s[tid] = rs.sx; cs.rs_s[T + tid] = rs.sy; cs.rs_s[2 * T + tid] = rs.sz;
+                cs.mesh_idx[tid] = P.mesh;
+                KdCursor c;
+                if (kd_begin(m.tree, ax, c)) {
+                    nodes = m.tree.nodes;
+                    node = 0; sp = 0;
+                    tmin = c.min_range; tmax = c.max_range;
+                    st = DESCEND;
+                } else {
+                    MeshHit none;
+                    rq_answer(b.susp + q, false, none);
+                }
+            }
+        }
+        // ---- visit phase: a bounded number of node visits for every lane that is on its way down
+#pragma unroll 1
+        for (int v = 0; v < RQ_VISITS; ++v) {
+            if (st == DESCEND) {
+                const int r = kd_visit(nodes, ax, stk, node, sp, tmin, tmax, off, cnt, stats);
+                if (r == VISIT_LEAF) st = LEAF;
+                else if (r == VISIT_DONE) {
+                    MeshHit none;
+                    rq_answer(b.susp + q, false, none);
+                    st = IDLE;
+                }
+            }
+            if (!__any_sync(RSB_FULL_MASK, st == DESCEND)) break;
+        }
+        // ---- leaf phase: pooled triangle tests once enough lanes stand at a leaf (or nobody can move)
+        const unsigned at_leaf = __ballot_sync(RSB_FULL_MASK, st == LEAF);
+        const unsigned moving = __ballot_sync(RSB_FULL_MASK, st == DESCEND);
+        if (at_leaf != 0 && (__popc(at_leaf) >= RQ_LEAF_MIN || moving == 0)) {
+            MeshHit mh;
+            const double d0 = md < tmax ? md : tmax;     // min(ray.max_distance, max_range), mesh.pyx:535
+            const bool leaf_hit = mesh_leaf_pool(sc, cs, st == LEAF, off, cnt, d0, &mh, stats);
+            if (st == LEAF) {
+                if (leaf_hit) {
+                    mh.node = node;
+                    rq_answer(b.susp + q, true, mh);
+                    st = IDLE;
+                } else if (kd_pop(stk, node, sp, tmin, tmax)) {
+                    st = DESCEND;
+                } else {
+                    rq_answer(b.susp + q, false, mh);
+                    st = IDLE;
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        __syncwarp();
+        flush_stats(stats, counters);
+    }
+}
+
+// ---- k_rq_world -------------------------------------------------------------------------------------------
+// Mesh-free scenes: World.hit as visits per trip + a leaf phase (WorldLeaf: AABB pre-tests, then the primitive tests).
+#define RQ_WORLD_SMEM (9 * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS)
+template <bool COUNT, int FEAT, class Client>
+__global__ void __launch_bounds__(RQ_THREADS, (FEAT & RSB_FEAT_CSG) ? 3 : RQ_WORLD_BLOCKS)
+k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* counters) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int T = RQ_THREADS;
+    constexpr bool STAGED = (FEAT & RSB_FEAT_STAGED) != 0;
+    typedef typename StatsSel<COUNT>::type Stats;
+    Stats stats;
+    const int tid = threadIdx.x, lane = tid & 31;
+    double* axbuf = ax_storage<STAGED>(smem, sc, n_items);
+    stage_scene<STAGED>(sc, smem, n_items);
+    KdStackEntry spill[RSB_KD_STACK - RQ_SCAP];
+    SmemKdStack<RQ_SCAP, T> stk;
+    stk.t = axbuf + 9 * T;
+    stk.n = reinterpret_cast<int32_t*>(axbuf - tid + (9 + RQ_SCAP) * T) + tid;
+    stk.spill = spill;
+    HitRec rec;
+    WorldLeaf<Stats, FEAT & ~RSB_FEAT_MESH, T> leaf;
+    leaf.sc = &sc;
+    leaf.ax.p = axbuf;
+    leaf.ax.unsafe = 0;
+    leaf.max_distance = RSB_INF;
+    leaf.mesh_stack = nullptr;
+    leaf.mesh_axbuf = nullptr;
+    leaf.best = &rec;
+    leaf.stats = &stats;
+    unsigned int* cursor = b.ctr + 8;
+    enum { IDLE = 0, DESCEND = 1, LEAF = 2 };
+    int st = IDLE, node = 0, sp = 0, off = 0, cnt = 0;
+    long long q = 0;
+    double tmin = 0.0, tmax = 0.0;
+    bool exhausted = n <= 0;
+    unsigned long long traced = 0;
+    for (;;) {
+        const unsigned idle = __ballot_sync(RSB_FULL_MASK, st == IDLE);
+        if (idle == RSB_FULL_MASK && exhausted) break;
+        if (!exhausted && (idle == RSB_FULL_MASK || __popc(idle) >= RQ_REFILL)) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(idle));
+            base = __shfl_sync(RSB_FULL_MASK, base, 0);
+            if ((long long)base + __popc(idle) >= n) exhausted = true;
+            const long long k = (long long)base + __popc(idle & ((1u << lane) - 1));
+            bool done = false;
+            if (st == IDLE && k < n) {
+                q = k;
+                V3 o, d;
+                double md;
+                if (cl.fetch(q, o, d, md)) {
+                    traced = traced + 1;
+                    leaf.ax.set(axbuf, o, d);
+                    leaf.max_distance = md;
+                    rec.u = rec.v = rec.w = 0.0f;
+                    rec.node = -1;
+                    rec.mesh_node = -1;
+                    KdCursor c;
+                    if (kd_begin(sc.world, leaf.ax, c)) {
+                        node = 0; sp = 0;
+                        tmin = c.min_range; tmax = c.max_range;
+                        st = DESCEND;
+                    } else {
+                        done = true;
+                    }
+                }
+            }
+            cl.commit(q, done, false, rec);
+        }
+#pragma unroll 1
+        for (int v = 0; v < RQ_VISITS; ++v) {
+            bool done = false;
+            if (st == DESCEND) {
+                const int r = kd_visit(sc.world.nodes, leaf.ax, stk, node, sp, tmin, tmax, off, cnt, stats);
+                if (r == VISIT_LEAF) st = LEAF;
+                else if (r == VISIT_DONE) { done = true; st = IDLE; }
+            }
+            if (__any_sync(RSB_FULL_MASK, done)) cl.commit(q, done, false, rec);
+            if (!__any_sync(RSB_FULL_MASK, st == DESCEND)) break;
+        }
+        const unsigned at_leaf = __ballot_sync(RSB_FULL_MASK, st == LEAF);
+        const unsigned moving = __ballot_sync(RSB_FULL_MASK, st == DESCEND);
+        if (at_leaf != 0 && (__popc(at_leaf) >= RQ_LEAF_MIN || moving == 0)) {
+            bool done = false, hit = false;
+            if (st == LEAF) {
+                if (leaf(off, cnt, tmax)) {
+                    rec.node = node;
+                    done = hit = true;
+                    st = IDLE;
+                } else if (kd_pop(stk, node, sp, tmin, tmax)) {
+                    st = DESCEND;
+                } else {
+                    done = true;
+                    st = IDLE;
+                }
+            }
+            cl.commit(q, done, hit, rec);
+        }
+    }
+    if (COUNT) {
+        __syncwarp();
+        traced = warp_sum(traced);
+        if ((threadIdx.x & 31) == 0 && traced) atomicAdd(&counters->rays, traced);
+        flush_stats(stats, counters);
+    }
+}
+
+// ---- ray sources / sinks of the batch and sweep entry points ------------------------------------------------
+// [n][3] origins, directions (+ max_distance) -> the pipeline's SoA rows
+__global__ void k_rq_batch_in(long long n, const double* __restrict__ origins, const double* __restrict__ directions,
+                              const double* __restrict__ max_distance, double* __restrict__ ray, long long stride, double* __restrict__ md) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        ray[i] = origins[3 * i]; ray[stride + i] = origins[3 * i + 1]; ray[2 * stride + i] = origins[3 * i + 2];
+        ray[3 * stride + i] = directions[3 * i]; ray[4 * stride + i] = directions[3 * i + 1]; ray[5 * stride + i] = directions[3 * i + 2];
+        md[i] = max_distance ? max_distance[i] : RSB_INF;
+    }
+}
+
+// the pipeline's hit records -> the arrays of rsb_hit_batch (intersection geometry generated once, for the winner)
+template <int FEAT>
+__global__ void __launch_bounds__(128)
+k_rq_batch_out(Scene sc, RqBuf b, long long n, int32_t* __restrict__ out_prim, double* __restrict__ out_t, int32_t* __restrict__ out_sub,
+               uint8_t* __restrict__ out_flags, int32_t* __restrict__ out_node, double* __restrict__ out_geom, float* __restrict__ out_uvw) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int4 a = b.hit_a[i];
+        if (a.x >= 0) {
+            const long long s = b.ray_stride;
+            const V3 o = v3(b.ray[i], b.ray[s + i], b.ray[2 * s + i]);
+            const V3 d = v3(b.ray[3 * s + i], b.ray[4 * s + i], b.ray[5 * s + i]);
+            const float4 uvw = b.hit_uvw[i];
+            HitRec rec;
+            rec.t = b.hit_t[i];
+            rec.prim = a.x; rec.leaf = a.y; rec.code = a.z; rec.flip = a.w;
+            rec.u = uvw.x; rec.v = uvw.y; rec.w = uvw.z;
+            rec.mesh_node = __float_as_int(uvw.w);
+            rec.node = b.hit_node ? b.hit_node[i] : -1;
+            Isect is;
+            world_hit_geometry<FEAT>(sc, o, d, rec, &is);
+            out_prim[i] = rec.prim;
+            out_t[i] = rec.t;
+            out_sub[i] = rec.code;
+            out_flags[i] = (uint8_t)(is.exiting ? 1 : 0);
+            if (out_node) { out_node[2 * i] = rec.node; out_node[2 * i + 1] = rec.mesh_node; }
+            if (out_geom) {
+                double* g = out_geom + 12 * i;
+                g[0] = is.hit.x; g[1] = is.hit.y; g[2] = is.hit.z;
+                g[3] = is.inside.x; g[4] = is.inside.y; g[5] = is.inside.z;
+                g[6] = is.outside.x; g[7] = is.outside.y; g[8] = is.outside.z;
+                g[9] = is.normal.x; g[10] = is.normal.y; g[11] = is.normal.z;
+            }
+            if (out_uvw) { out_uvw[3 * i] = rec.u; out_uvw[3 * i + 1] = rec.v; out_uvw[3 * i + 2] = rec.w; }
+        } else {
+            out_prim[i] = -1;
+            out_t[i] = RSB_INF;
+            out_sub[i] = -1;
+            out_flags[i] = 0;
+            if (out_node) { out_node[2 * i] = -1; out_node[2 * i + 1] = -1; }
+            if (out_geom) { double* g = out_geom + 12 * i; for (int k = 0; k < 12; ++k) g[k] = 0.0; }
+            if (out_uvw) { out_uvw[3 * i] = 0; out_uvw[3 * i + 1] = 0; out_uvw[3 * i + 2] = 0; }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned int morton_compact(unsigned long long x) {
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFULL;
+    return (unsigned int)x;
+}
+
+// Ray `index` of a sweep: from `origin` toward target + (jx, jy, 0) * half_window.  order_log2 = 0: (jx, jy) uniform
+// over the whole window, independently per ray (incoherent, like rays after a diffuse bounce).  order_log2 = g > 0: the
+// window is a 2^g x 2^g grid of cells walked along the Morton curve, ray `index` jitters inside cell index mod 4^g --
+// neighbouring indices are neighbouring cells, the way an observer hands out the pixels of an image (primary rays).
+__global__ void k_rq_sweep_gen(long long n, long long first_index, unsigned long long seed, double ox, double oy, double oz, double tx,
+                               double ty, double tz, double half_window, int order_log2, double* __restrict__ ray, long long stride) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long index = (unsigned long long)(first_index + i);
+        Philox4x32 px;
+        px.init(seed, index, 0u);
+        double u1 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
+        double u2 = (double)(px.next_u64() >> 11) * (1.0 / 9007199254740992.0);
+        if (order_log2 > 0) {
+            const unsigned long long cell = index & ((1ULL << (2 * order_log2)) - 1ULL);
+            const double inv = 1.0 / (double)(1ULL << order_log2);
+            u1 = ((double)morton_compact(cell) + u1) * inv;
+            u2 = ((double)morton_compact(cell >> 1) + u2) * inv;
+        }
+        const V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
+        const V3 d = normalise(v3(p.x - ox, p.y - oy, p.z - oz));
+        ray[i] = ox; ray[stride + i] = oy; ray[2 * stride + i] = oz;
+        ray[3 * stride + i] = d.x; ray[4 * stride + i] = d.y; ray[5 * stride + i] = d.z;
+    }
+}
+
+__global__ void k_rq_sweep_reduce(RqBuf b, long long n, long long first_index, unsigned long long* out_hits, double* out_sum_t,
+                                  unsigned long long* out_xor_prim) {
+    unsigned long long hits = 0, xr = 0;
+    double sum_t = 0.0;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int prim = b.hit_a[i].x;
+        if (prim >= 0) {
+            hits += 1;
+            sum_t += b.hit_t[i];
+            xr ^= (unsigned long long)(unsigned)prim * 0x9E3779B97F4A7C15ULL + (unsigned long long)(first_index + i);
+        }
+    }
+    __syncwarp();
+    hits = warp_sum(hits);
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+        sum_t += __shfl_down_sync(RSB_FULL_MASK, sum_t, k);
+        xr ^= __shfl_down_sync(RSB_FULL_MASK, xr, k);
+    }
+    if ((threadIdx.x & 31) == 0 && hits) {
+        atomicAdd(out_hits, hits);
+        atomicAdd(out_sum_t, sum_t);
+        atomicXor(out_xor_prim, xr);
+    }
+}
+
+}  // namespace rsb

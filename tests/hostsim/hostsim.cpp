@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../source_b200/csrc/rsb_path.h"
+#include "../../source_b200/csrc/rsb_trav.h"
 #include "../../source_b200/csrc/scene_pack.h"
 
 using namespace rsb;
@@ -79,9 +80,22 @@ int hs_scene_destroy(uint64_t s) {
     return 0;
 }
 
+// mode 0: world_hit (the nested two-level loop); 1: the split pipeline run serially (world walk suspended in front of
+// every Mesh.hit, mesh_query over kd_visit, resume with the per-ray memo); 2: the single-visit walk of mesh-free scenes
+int hs_hit_batch_mode(uint64_t scene, int32_t mode, int64_t n, const double* origins, const double* directions, const double* max_distance,
+                      int32_t* out_prim, double* out_t, int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom,
+                      float* out_uvw, uint64_t* counters /* branches, leaves, items, prim_tests, tri_tests */);
+
 int hs_hit_batch(uint64_t scene, int64_t n, const double* origins, const double* directions, const double* max_distance,
                  int32_t* out_prim, double* out_t, int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom,
-                 float* out_uvw, uint64_t* counters /* branches, leaves, items, prim_tests, tri_tests */) {
+                 float* out_uvw, uint64_t* counters) {
+    return hs_hit_batch_mode(scene, 0, n, origins, directions, max_distance, out_prim, out_t, out_sub, out_flags, out_node, out_geom,
+                             out_uvw, counters);
+}
+
+int hs_hit_batch_mode(uint64_t scene, int32_t mode, int64_t n, const double* origins, const double* directions, const double* max_distance,
+                      int32_t* out_prim, double* out_t, int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom,
+                      float* out_uvw, uint64_t* counters) {
     HostScene* h = reinterpret_cast<HostScene*>(scene);
     CountStats stats;
     KdStackEntry stack[RSB_KD_STACK];
@@ -90,7 +104,11 @@ int hs_hit_batch(uint64_t scene, int64_t n, const double* origins, const double*
         V3 d = v3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
         double md = max_distance ? max_distance[i] : RSB_INF;
         HitRec rec;
-        if (world_hit(h->sc, o, d, md, stack, &rec, stats)) {
+        bool hit;
+        if (mode == 1) hit = world_hit_split<RSB_FEAT_ALL>(h->sc, o, d, md, stack, &rec, stats);
+        else if (mode == 2) hit = world_hit_visits<RSB_FEAT_ALL>(h->sc, o, d, md, stack, &rec, stats);
+        else hit = world_hit(h->sc, o, d, md, stack, &rec, stats);
+        if (hit) {
             Isect is;
             world_hit_geometry(h->sc, o, d, rec, &is);
             out_prim[i] = rec.prim;

@@ -16,7 +16,7 @@ SOURCES = [os.path.join(HERE, "hostsim", "hostsim.cpp"),
            os.path.join(ROOT, "source_b200", "csrc", "scene_pack.cpp"),
            os.path.join(ROOT, "source_b200", "csrc", "kdtree_host.cpp")]
 HEADERS = [os.path.join(ROOT, "source_b200", "csrc", h) for h in
-           ("rsb_math.h", "rsb_scene.h", "rsb_geom.h", "rsb_rng.h", "rsb_path.h", "scene_pack.h", "kdtree_host.h")]
+           ("rsb_math.h", "rsb_scene.h", "rsb_geom.h", "rsb_trav.h", "rsb_rng.h", "rsb_path.h", "scene_pack.h", "kdtree_host.h")]
 
 
 def build(force=False):
@@ -38,6 +38,7 @@ def lib():
         _lib.hs_scene_create.argtypes = [C.POINTER(cabi.RsbSceneDesc), C.POINTER(C.c_uint64)]
         _lib.hs_scene_destroy.argtypes = [C.c_uint64]
         _lib.hs_hit_batch.argtypes = [C.c_uint64, C.c_int64] + [C.c_void_p] * 11
+        _lib.hs_hit_batch_mode.argtypes = [C.c_uint64, C.c_int32, C.c_int64] + [C.c_void_p] * 11
         _lib.hs_contains_batch.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib.hs_rng_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_uint64, C.POINTER(cabi.RsbCamera), C.POINTER(cabi.RsbRayConfig),
@@ -54,6 +55,8 @@ def _p(a):
 
 class HostScene:
     """Same surface as source_b200.engine.Accelerator, evaluated by the host build of the device code."""
+
+    hit_mode = 0    # 0: nested loop, 1: split pipeline (serial), 2: single-visit walk (mesh-free scenes)
 
     def __init__(self, flat):
         self.flat = flat
@@ -77,8 +80,8 @@ class HostScene:
         md = None if max_distance is None else cabi.as_f64(np.broadcast_to(max_distance, (n,)))
         out = HitBatch(n, True)
         counters = np.zeros(5, dtype=np.uint64)
-        lib().hs_hit_batch(self.scene, n, _p(o), _p(d), _p(md), _p(out.primitive), _p(out.distance), _p(out.sub),
-                           _p(out.exiting), _p(out.node), _p(out.geometry), _p(out.uvw), _p(counters))
+        lib().hs_hit_batch_mode(self.scene, int(self.hit_mode), n, _p(o), _p(d), _p(md), _p(out.primitive), _p(out.distance),
+                                _p(out.sub), _p(out.exiting), _p(out.node), _p(out.geometry), _p(out.uvw), _p(counters))
         self.counters = dict(zip(("branches", "leaves", "items", "prim_tests", "tri_tests"), (int(c) for c in counters)))
         return out
 

@@ -225,7 +225,7 @@ def test_hit_sweep_device_generated_rays(device):
     origin = (C.c_double * 3)(0, 0, -4.0)
     target = (C.c_double * 3)(0, 0, 0)
     st = torch.cuda.current_stream().cuda_stream
-    cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), n, 0, 12345, origin, target, 0.9,
+    cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), n, 0, 12345, origin, target, 0.9, 0,
                                             C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()), 1))
     torch.cuda.synchronize()
     c = device.counters()
@@ -235,7 +235,7 @@ def test_hit_sweep_device_generated_rays(device):
     # same answer when the sweep is split in two halves (index-keyed rays => order independent)
     h2 = torch.zeros(1, dtype=torch.int64, device="cuda"); s2 = torch.zeros(1, dtype=torch.float64, device="cuda"); x2 = torch.zeros(1, dtype=torch.int64, device="cuda")
     for first, cnt in ((0, n // 2), (n // 2, n - n // 2)):
-        cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), cnt, first, 12345, origin, target, 0.9,
+        cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), cnt, first, 12345, origin, target, 0.9, 0,
                                                 C.c_void_p(h2.data_ptr()), C.c_void_p(s2.data_ptr()), C.c_void_p(x2.data_ptr()), 0))
     torch.cuda.synchronize()
     assert h2.item() == hits.item() and x2.item() == xr.item()
@@ -368,7 +368,7 @@ def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind):
     xr = torch.zeros(1, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), n, first, seed, (C.c_double * 3)(*origin),
-                                            (C.c_double * 3)(*target), half, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
+                                            (C.c_double * 3)(*target), half, 0, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
                                             C.c_void_p(xr.data_ptr()), 0))
     torch.cuda.synchronize()
     idx = np.arange(first, first + n, dtype=np.uint64)

@@ -91,3 +91,38 @@ def test_philox_mode_statistics(make_backend):
     sigma = np.sqrt((g["variance"] / 4).sum())
     assert abs(total - total_ref) < 5 * np.sqrt(2) * sigma
     assert not np.array_equal(frame.mean, g["mean"])
+
+
+class _Mode:
+    """HostScene factory that evaluates World.hit through one of the new walk forms (rsb_trav.h)"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __call__(self, flat):
+        s = hostsim_api.HostScene(flat)
+        s.hit_mode = self.mode
+        return s
+
+
+@pytest.mark.parametrize("smoothing", [True, False])
+def test_split_pipeline_mesh_hits(lib, smoothing):
+    """world walk suspended in front of Mesh.hit + stand-alone mesh query over single node visits + resume with the
+    per-ray memo == the reference (ids, t, triangle, u v w, instanced meshes)"""
+    hostsim_api.build()
+    parity.mesh(_Mode(1), smoothing)
+
+
+def test_split_pipeline_on_every_primitive_type(lib):
+    hostsim_api.build()
+    parity.zoo(_Mode(1))
+    parity.edge(_Mode(1))
+    parity.scaled(_Mode(1), exact=True)
+
+
+def test_single_visit_walk_on_mesh_free_scenes(lib):
+    hostsim_api.build()
+    parity.zoo(_Mode(2))
+    parity.edge(_Mode(2))
+    parity.spheres(_Mode(2))
+    parity.parabola(_Mode(2), exact=True)

@@ -8,6 +8,7 @@ roofline of the traversal kernel; optionally the same for the Corn
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import sys
 import time
@@ -28,6 +29,9 @@ def main():
     ap.add_argument("--n", type=float, nargs="+", default=[1e5, 1e6, 1e7, 1e8])
     ap.add_argument("--mesh-subdiv", type=int, default=0, help="also sweep a Cornell box holding a 20*4^k-triangle mesh")
     ap.add_argument("--no-spheres", action="store_true", help="skip the sphere field (profiling the mesh scene)")
+    ap.add_argument("--order", nargs="+", default=["random", "morton"], choices=["random", "morton"],
+                    help="random: every ray aims anywhere in the window (incoherent); morton: rays walk a grid of cells along the "
+                         "Morton curve (coherent, like the pixels of an observer)")
     args = ap.parse_args()
     dev = Device(0)
     peak = 6554.2
@@ -36,6 +40,10 @@ def main():
         peak = float(json.load(open(pk))["hbm_gbs"])
 
     def sweep(name, acc, origin, target, half, ns):
+        for order_name in args.order:
+            sweep_order(name, acc, origin, target, half, ns, order_name)
+
+    def sweep_order(name, acc, origin, target, half, ns, order_name):
         hits = torch.zeros(1, dtype=torch.int64, device="cuda")
         sum_t = torch.zeros(1, dtype=torch.float64, device="cuda")
         xr = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -43,8 +51,10 @@ def main():
         st = torch.cuda.current_stream().cuda_stream
 
         def run(n, count):
+            # "morton": a 2^g x 2^g grid of cells along the Morton curve with about one ray per cell (primary rays of an image)
+            order = 0 if order_name == "random" else max(1, int(math.log(max(n, 4), 4)))
             hits.zero_(); sum_t.zero_(); xr.zero_()
-            cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), int(n), 0, 2024, o3, t3, half,
+            cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), int(n), 0, 2024, o3, t3, half, order,
                                                  C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()), count))
         for n in ns:
             n = int(n)
@@ -64,7 +74,7 @@ def main():
             c = dev.counters()
             per_ray = (72 * c["rays"] + 16 * c["branches"] + 8 * c["leaves"] + 4 * c["items"] + 128 * c["prim_tests"] + 48 * c["tri_tests"]) / c["rays"]
             achieved = per_ray * n / (ms * 1e-3) / 1e9
-            print(json.dumps({"scene": name, "rays": n, "ms": ms, "Mrays_per_s": n / ms / 1e3, "hit_fraction": h / n,
+            print(json.dumps({"scene": name, "order": order_name, "rays": n, "ms": ms, "Mrays_per_s": n / ms / 1e3, "hit_fraction": h / n,
                               "algorithmic_bytes_per_ray": per_ray, "achieved_GBps": achieved, "roofline_frac": achieved / peak,
                               "per_ray": {k: c[k] / c["rays"] for k in ("branches", "leaves", "items", "prim_tests", "tri_tests")}}), flush=True)
 
