@@ -56,7 +56,7 @@ class OracleScene:
         md = None if max_distance is None else np.ascontiguousarray(np.broadcast_to(max_distance, (n,)), dtype=np.float64)
         out = HitBatch(n, True)
         lib().ro_hit(C.byref(self.flat.desc), C.c_int64(n), _p(o), _p(d), _p(md), _p(out.primitive), _p(out.distance), _p(out.sub),
-                     _p(out.exiting), _p(out.geometry), _p(out.uvw))
+                     _p(out.exiting), _p(out.geometry), _p(out.uvw), _p(out.node))
         return out
 
     def contains_batch(self, points, cap=8):

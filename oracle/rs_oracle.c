@@ -116,6 +116,7 @@ typedef struct {
     kdtree tree;
     /* last-hit state of MeshData (mesh.pxd:56-60) */
     int ix, iy, iz; float sx, sy, sz; float u, v, w, t; int i;
+    int leaf;           /* node id of the leaf that produced the last hit (kd-node parity; not reference state) */
 } mesh_t;
 typedef struct {
     const RsbSceneDesc* d;
@@ -156,6 +157,7 @@ typedef struct {
     int hit; double t; int prim; int exiting; v3 p, pin, pout, n;
     const double* w2p; const double* p2w;
     int tri; float u, v, w;
+    int mesh_leaf;      /* mesh kd leaf of a mesh hit, else -1 */
 } isect;
 
 typedef struct { v3 o, d; double maxd; } ray_t;
@@ -206,7 +208,7 @@ typedef struct prim_state {
     int tested;                                              /* BoundPrimitive._primitive_tested */
 } prim_state;
 
-typedef struct { scene_t* s; prim_state* st; } ctx_t;
+typedef struct { scene_t* s; prim_state* st; int hit_leaf; /* world kd leaf in which the last World.hit accepted its hit */ } ctx_t;
 
 static const double* P_params(scene_t* s, int id) { return s->d->prim_params + 6 * (size_t)id; }
 static const double* P_tl(scene_t* s, int id) { return s->d->prim_to_local + 12 * (size_t)id; }
@@ -563,7 +565,11 @@ static int mesh_leaf(mesh_t* m, const kdnode* n, const ray_t* ray, double max_ra
 static int world_leaf(ctx_t* c, const kdnode* n, const ray_t* ray, double max_range, isect* best);
 static int trace_node(ctx_t* c, const kdtree* t, mesh_t* mesh, int id, const ray_t* ray, double min_range, double max_range, isect* best) {
     const kdnode* n = &t->nodes[id];
-    if (n->type == -1) return mesh ? mesh_leaf(mesh, n, ray, max_range) : world_leaf(c, n, ray, max_range, best);
+    if (n->type == -1) {
+        int found = mesh ? mesh_leaf(mesh, n, ray, max_range) : world_leaf(c, n, ray, max_range, best);
+        if (found) { if (mesh) mesh->leaf = id; else c->hit_leaf = id; }
+        return found;
+    }
     int axis = n->type;
     double split = n->split, origin = comp(ray->o, axis), direction = comp(ray->d, axis);
     int lower_id = id + 1, upper_id = n->count;
@@ -619,6 +625,7 @@ static int mesh_hit(ctx_t* c, int id, const ray_t* ray, isect* it) {        /* :
     finish(it, s, id, t, lr.d, h, V(h.x - fn.x * 1e-6, h.y - fn.y * 1e-6, h.z - fn.z * 1e-6),
            V(h.x + fn.x * 1e-6, h.y + fn.y * 1e-6, h.z + fn.z * 1e-6), n, dot3(lr.d, fn) > 0.0);
     it->tri = m->i; it->u = m->u; it->v = m->v; it->w = m->w;
+    it->mesh_leaf = m->leaf;
     return 1;
 }
 
@@ -1003,7 +1010,7 @@ int ro_uniform(uint64_t seed, int64_t n, double* out) {
 }
 
 int ro_hit(const RsbSceneDesc* d, int64_t n, const double* o, const double* dir, const double* maxd, int32_t* prim, double* t,
-           int32_t* sub, uint8_t* exiting, double* geom, float* uvw) {
+           int32_t* sub, uint8_t* exiting, double* geom, float* uvw, int32_t* node /* [n][2] world leaf, mesh leaf; or NULL */) {
     scene_t* s = scene_new(d);
     ctx_t c;
     c.s = s;
@@ -1019,7 +1026,9 @@ int ro_hit(const RsbSceneDesc* d, int64_t n, const double* o, const double* dir,
             g[0] = it.p.x; g[1] = it.p.y; g[2] = it.p.z; g[3] = it.pin.x; g[4] = it.pin.y; g[5] = it.pin.z;
             g[6] = it.pout.x; g[7] = it.pout.y; g[8] = it.pout.z; g[9] = it.n.x; g[10] = it.n.y; g[11] = it.n.z;
             uvw[3 * i] = it.u; uvw[3 * i + 1] = it.v; uvw[3 * i + 2] = it.w;
+            if (node) { node[2 * i] = c.hit_leaf; node[2 * i + 1] = d->prim_type[it.prim] == RSB_PRIM_MESH ? it.mesh_leaf : -1; }
         } else {
+            if (node) { node[2 * i] = -1; node[2 * i + 1] = -1; }
             prim[i] = -1; t[i] = INFINITY; sub[i] = -1; exiting[i] = 0;
             memset(geom + 12 * i, 0, 96); uvw[3 * i] = uvw[3 * i + 1] = uvw[3 * i + 2] = 0;
         }

@@ -82,19 +82,27 @@ const size_t kMaxStageBytes = 96 * 1024;
     do {                                                                                               \
         const int feat_ = (feat) | ((staged) ? RSB_FEAT_STAGED : 0);                                   \
         if (count) {                                                                                   \
-            if (feat_ == 0) M(true, 0);                                                                \
-            else if (feat_ == RSB_FEAT_STAGED) M(true, RSB_FEAT_STAGED);                               \
-            else if (feat_ == RSB_FEAT_MESH) M(true, RSB_FEAT_MESH);                                   \
-            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(true, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
-            else if (feat_ == RSB_FEAT_ALL) M(true, RSB_FEAT_ALL);                                     \
-            else M(true, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                            \
+            switch (feat_) {                                                                           \
+                case 0: M(true, 0); break;                                                             \
+                case 1: M(true, 1); break;                                                             \
+                case 2: M(true, 2); break;                                                             \
+                case 3: M(true, 3); break;                                                             \
+                case 4: M(true, 4); break;                                                             \
+                case 5: M(true, 5); break;                                                             \
+                case 6: M(true, 6); break;                                                             \
+                default: M(true, 7); break;                                                            \
+            }                                                                                          \
         } else {                                                                                       \
-            if (feat_ == 0) M(false, 0);                                                               \
-            else if (feat_ == RSB_FEAT_STAGED) M(false, RSB_FEAT_STAGED);                              \
-            else if (feat_ == RSB_FEAT_MESH) M(false, RSB_FEAT_MESH);                                  \
-            else if (feat_ == (RSB_FEAT_MESH | RSB_FEAT_STAGED)) M(false, (RSB_FEAT_MESH | RSB_FEAT_STAGED)); \
-            else if (feat_ == RSB_FEAT_ALL) M(false, RSB_FEAT_ALL);                                    \
-            else M(false, (RSB_FEAT_ALL | RSB_FEAT_STAGED));                                           \
+            switch (feat_) {                                                                           \
+                case 0: M(false, 0); break;                                                            \
+                case 1: M(false, 1); break;                                                            \
+                case 2: M(false, 2); break;                                                            \
+                case 3: M(false, 3); break;                                                            \
+                case 4: M(false, 4); break;                                                            \
+                case 5: M(false, 5); break;                                                            \
+                case 6: M(false, 6); break;                                                            \
+                default: M(false, 7); break;                                                           \
+            }                                                                                          \
         }                                                                                              \
     } while (0)
 
@@ -356,6 +364,19 @@ int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
     if (rc) return bail(rc);
     ds->n_world_items = (int32_t)ps.world.items.size();
     {
+        // leaf-ordered item rows with their AABBs (worlds that are not staged in shared memory read these)
+        std::vector<LeafRow> rows(ps.world.items.size());
+        for (size_t k = 0; k < rows.size(); ++k) {
+            const Prim& pr = ps.prims[ps.world.items[k]];
+            memcpy(rows[k].bbox, pr.bbox, sizeof(pr.bbox));
+            rows[k].id = ps.world.items[k];
+            rows[k].type = pr.type;
+            rows[k].pad[0] = rows[k].pad[1] = 0;
+        }
+        rc = upload(ds, rows.data(), rows.size(), &ds->sc.world_rows, 64);
+        if (rc) return bail(rc);
+    }
+    {
         StageLayout l = stage_layout((int)ps.world.nodes.size(), (int)ps.world.items.size(), (int)ps.prims.size());
         ds->stage_bytes = (size_t)l.total <= kMaxStageBytes ? l.total : 0;
     }
@@ -505,7 +526,8 @@ int rq_trace(Context* c, DeviceScene* ds, const RqBuf& b, long long n, cudaStrea
     for (int r = 0; r < rounds; ++r) {
         if (count) k_rq_mesh<true><<<grid_mesh, RQ_THREADS, RQ_MESH_SMEM, st>>>(ds->sc, b, r, c->d_counters);
         else k_rq_mesh<false><<<grid_mesh, RQ_THREADS, RQ_MESH_SMEM, st>>>(ds->sc, b, r, c->d_counters);
-        if (r == rounds - 1) RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_LAST);
+        // one mesh primitive: its answer is the ray's memo from now on, no walk can stop a second time
+        if (r == rounds - 1 && ds->n_mesh_prims > 1) RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_LAST);
         else RSB_DISPATCH_FEAT_MESH(count, feat, staged, RSB_LAUNCH_RQ_RESUME);
     }
 #undef RSB_LAUNCH_RQ_BEGIN
@@ -715,8 +737,17 @@ struct Carver {
     }
 };
 
-size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t chunk, WfSlots* st) {
+size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t chunk, WfSlots* st, bool mesh, RqBuf* rq) {
     Carver c{base};
+    memset(rq, 0, sizeof(*rq));
+    if (mesh) {
+        // scenes with meshes trace through the World.hit kernel pipeline (rsb_trav.cuh): parked walks and queues per slot
+        rq->ctr = c.take<unsigned int>(16);
+        rq->susp = c.take<RqSusp>(P);
+        rq->susp_stack = c.take<KdStackEntry>(P * RQ_WORLD_STACK);
+        rq->queue = c.take<int2>((size_t)(RQ_MAX_ROUNDS + 1) * P);
+        rq->cap = (long long)P;
+    }
     st->ray = c.take<double>(6 * P);
     st->weight = c.take<double>(P);
     st->norm = c.take<double>(P);
@@ -741,11 +772,17 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->pix_mti = mt ? c.take<int32_t>(2 * chunk) : nullptr;
     st->pix_mt = mt ? c.take<unsigned long long>(chunk * 2 * RSB_MT_NN) : nullptr;
     st->log = c.take<LogEntry>(P * cap);
+    if (mesh) {
+        rq->ray = st->ray;
+        rq->ray_stride = (long long)P;
+        rq->md = nullptr;
+    }
     return (c.off + 255) & ~(size_t)255;
 }
 
 template <int RNGMODE, bool COUNT, int FEAT>
-int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st, bool time_trace) {
+int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, size_t smem_tables, cudaStream_t st, bool time_trace,
+                  RqBuf rq, int n_mesh_prims) {
     const int threads = 128;
     const int grid = (a.n_slots + threads - 1) / threads;
     const int fin_grid = std::max(1, std::min(grid, c->sm_count * 16));
@@ -753,8 +790,22 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int shade_grid = grid;
     smem_scene += ax_bytes(FEAT);   // RayAx storage of k_wf_trace behind the staged scene
     if (RNGMODE == RNG_MT19937_64) smem_shade += RSB_MT_WIN_WORDS * 8 * threads;   // k_wf_shade: MT state window per thread
-    if (smem_scene > 48 * 1024)
-        RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+    constexpr bool PIPELINE = (FEAT & RSB_FEAT_MESH) != 0;   // scenes with meshes: World.hit = walk / Mesh.hit / resume kernels
+    const int mesh_rounds = std::min<int>(std::max(n_mesh_prims, 1), RQ_MAX_ROUNDS);
+    const int grid_mesh = c->sm_count * RQ_MESH_BLOCKS;
+    if constexpr (PIPELINE) {
+        rq.md_all = a.cfg.max_distance;
+        rq.ray_stride = a.n_slots;      // the slot arrays of this chunk are [..][n_slots]
+        if (smem_scene > 48 * 1024) {
+            RSB_CUDA(cudaFuncSetAttribute(k_rq_walk<COUNT, FEAT, RqWfClient, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+            RSB_CUDA(cudaFuncSetAttribute(k_rq_walk<COUNT, FEAT, RqWfClient, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+            RSB_CUDA(cudaFuncSetAttribute(k_rq_walk<COUNT, FEAT, RqWfClient, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+        }
+        RSB_CUDA(cudaFuncSetAttribute(k_rq_mesh<COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RQ_MESH_SMEM));
+    } else {
+        if (smem_scene > 48 * 1024)
+            RSB_CUDA(cudaFuncSetAttribute(k_wf_trace<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scene));
+    }
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
@@ -789,7 +840,21 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b], s));
             }
-            k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
+            if constexpr (PIPELINE) {
+                RqWfClient cl;
+                cl.a = a;
+                RSB_CUDA(cudaMemsetAsync(rq.ctr, 0, 16 * sizeof(unsigned int), s));
+                k_rq_walk<COUNT, FEAT, RqWfClient, false, false><<<grid, threads, smem_scene, s>>>(a.sc, a.n_items, cl, rq, a.n_slots, 0, a.counters);
+                for (int r = 0; r < mesh_rounds; ++r) {
+                    k_rq_mesh<COUNT><<<grid_mesh, RQ_THREADS, RQ_MESH_SMEM, s>>>(a.sc, rq, r, a.counters);
+                    if (r == mesh_rounds - 1 && n_mesh_prims > 1)
+                        k_rq_walk<COUNT, FEAT, RqWfClient, true, true><<<grid, threads, smem_scene, s>>>(a.sc, a.n_items, cl, rq, a.n_slots, r, a.counters);
+                    else
+                        k_rq_walk<COUNT, FEAT, RqWfClient, true, false><<<grid, threads, smem_scene, s>>>(a.sc, a.n_items, cl, rq, a.n_slots, r, a.counters);
+                }
+            } else {
+                k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
+            }
             if (time_trace) {
                 if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b + 1], s, cudaEventRecordExternal));
                 else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b + 1], s));
@@ -827,7 +892,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
         if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
         if (e1 != cudaSuccess) { rc_loop = fail(RSB_ERR_CUDA, std::string("wave batch: ") + cudaGetErrorString(e1)); break; }
         rs.waves += kBatch;
-        rs.launches += 4 * kBatch;
+        rs.launches += (4 + (PIPELINE ? 2 * mesh_rounds : 0)) * kBatch;
         rs.trace_launches += kBatch;
         if (time_trace) {
             for (int b = 0; b < kBatch; ++b) {
@@ -1008,14 +1073,15 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * c->slots_per_sm);
     P = std::max<long long>(P, 1);
     WfSlots probe;
-    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe);
+    RqBuf rq;
+    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe, ds->has_mesh, &rq);
     if (c->slot_bytes < need) {
         cudaFree(c->d_slots);
         c->d_slots = nullptr; c->slot_bytes = 0;
         RSB_CUDA(cudaMalloc(&c->d_slots, need));
         c->slot_bytes = need;
     }
-    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &a.st);
+    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &a.st, ds->has_mesh, &rq);
     if (count & RSB_RENDER_COUNT) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const bool time_trace = (count & RSB_RENDER_TIME_TRACE) != 0;
     count &= RSB_RENDER_COUNT;
@@ -1033,9 +1099,10 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         // conductors and volume emitters are compiled into the full-featured instantiation only (RSB_FEAT_RARE_MATERIALS)
         bool rare = false;
         for (int i = 0; i < ds->n_materials; ++i) rare = rare || ds->mat_type[i] >= RSB_MAT_CONDUCTOR;
-        const int feat = (ds->has_csg || rare) ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
-#define RSB_RUN_MT(C, F) rc = run_wavefront<RNG_MT19937_64, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
-#define RSB_RUN_PX(C, F) rc = run_wavefront<RNG_PHILOX, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace)
+        // the MESH bit is set exactly when the scene holds a mesh: those instantiations trace through the kernel pipeline
+        const int feat = ((ds->has_csg || rare) ? RSB_FEAT_CSG : 0) | (ds->has_mesh ? RSB_FEAT_MESH : 0);
+#define RSB_RUN_MT(C, F) rc = run_wavefront<RNG_MT19937_64, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace, rq, ds->n_mesh_prims)
+#define RSB_RUN_PX(C, F) rc = run_wavefront<RNG_PHILOX, C, F>(c, a, smem_scene, smem_shade, smem_tables, st, time_trace, rq, ds->n_mesh_prims)
         if (mt) RSB_DISPATCH_FEAT(count != 0, feat, a.staged, RSB_RUN_MT);
         else RSB_DISPATCH_FEAT(count != 0, feat, a.staged, RSB_RUN_PX);
 #undef RSB_RUN_MT

@@ -1039,6 +1039,18 @@ RSB_HD_NOINLINE void csg_geometry(const Scene& sc, int top, const CsgEvent& ev, 
 #define RSB_FEAT_RARE_MATERIALS RSB_FEAT_CSG
 #define RSB_FEAT_STAGED 4   // kernels only: world tree, item list and primitive table are in shared memory
 
+// AABB pre-test of world leaf item k (BoundPrimitive.hit, boundprimitive.pyx:42-51): id of the primitive, true when its box is hit
+template <int FEAT>
+RSB_HD bool world_item_pretest(const Scene& sc, int k, const V3& o, const V3& d, const V3& inv, int* id) {
+    if (!(FEAT & RSB_FEAT_STAGED) && sc.world_rows != nullptr) {
+        const LeafRow& r = sc.world_rows[k];
+        *id = r.id;
+        return box_hit_inv(r.bbox, o, d, inv);
+    }
+    *id = sc.world.items[k];
+    return box_hit_inv(sc.prims[*id].bbox, o, d, inv);
+}
+
 template <class Stats, int FEAT = RSB_FEAT_ALL, int S = 1>
 struct WorldLeaf {
     const Scene* sc;
@@ -1100,9 +1112,9 @@ struct WorldLeaf {
             {
                 const V3 o = ax.O(), d = ax.D(), inv = ax.R();
                 for (int i = 0; i < end; ++i) {
-                    int id = sc->world.items[offset + base + i];
+                    int id;
                     stats->prim_test();
-                    if (box_hit_inv(sc->prims[id].bbox, o, d, inv)) cand[nc++] = id;
+                    if (world_item_pretest<FEAT>(*sc, offset + base + i, o, d, inv, &id)) cand[nc++] = id;
                 }
             }
             for (int i = 0; i < nc; ++i) test(cand[i], distance, found);
@@ -1235,9 +1247,9 @@ struct NestedTraversal {
                 nc = 0;
                 ci = 0;
                 for (int i = 0; i < end; ++i) {
-                    int id = sc->world.items[item_offset + item_base + i];
+                    int id;
                     stats->prim_test();
-                    if (box_hit_inv(sc->prims[id].bbox, ro, rd, inv)) cand[nc++] = id;
+                    if (world_item_pretest<FEAT>(*sc, item_offset + item_base + i, ro, rd, inv, &id)) cand[nc++] = id;
                 }
                 item_base += end;
             } else if (have_leaf) {

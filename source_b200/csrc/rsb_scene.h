@@ -97,8 +97,18 @@ struct Material {
     double index_out;   // dielectric: external_index.average(min,max)
 };
 
+// One leaf item of the world tree with the AABB the leaf test starts with (BoundPrimitive.hit, boundprimitive.pyx:42-51),
+// in leaf order: the pre-test of a leaf reads consecutive 64-B rows instead of chasing item id -> primitive row.
+struct __attribute__((aligned(64))) LeafRow {
+    double bbox[6];
+    int32_t id;
+    int32_t type;
+    int32_t pad[2];
+};
+
 struct Scene {
     const Prim* prims;
+    const LeafRow* world_rows;  // [world items] or null (worlds staged in shared memory keep items + primitive table there)
     KdTree world;
     const Mesh* meshes;
     int32_t n_prims;    // all rows

@@ -43,6 +43,9 @@ namespace rsb {
 #ifndef RQ_WORLD_BLOCKS
 #define RQ_WORLD_BLOCKS 5
 #endif
+#ifndef RQ_WALK_BLOCKS
+#define RQ_WALK_BLOCKS 4     // k_rq_walk (world-level walk of scenes with meshes)
+#endif
 #ifndef RQ_POOL_CAP
 #define RQ_POOL_CAP 64       // (ray, triangle) pairs a warp tests per pooled round
 #endif
@@ -97,14 +100,17 @@ struct SmemKdStack {
 };
 
 // ---- clients: where a query's ray comes from and where its answer goes -------------------------------------
+// fetch: RQ_SKIP no query in this place, RQ_TRACE trace it, RQ_MISS report a miss without tracing
+enum RqFetch : int32_t { RQ_SKIP = 0, RQ_TRACE = 1, RQ_MISS = 2 };
+
 struct RqArrayClient {
     RqBuf b;
-    __device__ __forceinline__ bool fetch(long long i, V3& o, V3& d, double& md) const {
+    __device__ __forceinline__ int fetch(long long i, V3& o, V3& d, double& md) const {
         const long long s = b.ray_stride;
         o = v3(b.ray[i], b.ray[s + i], b.ray[2 * s + i]);
         d = v3(b.ray[3 * s + i], b.ray[4 * s + i], b.ray[5 * s + i]);
         md = b.md ? b.md[i] : b.md_all;
-        return true;
+        return RQ_TRACE;
     }
     // reached by all 32 lanes together
     __device__ __forceinline__ void commit(long long i, bool finished, bool hit, const HitRec& rec) const {
@@ -118,7 +124,42 @@ struct RqArrayClient {
             b.hit_a[i] = make_int4(-1, -1, -1, 0);
         }
     }
-    __device__ __forceinline__ void count_rays(DevCounters*, unsigned long long) const {}
+};
+
+// The wavefront renderer's slots as queries (k_wf_trace's prologue and epilogue, rsb_kernels.cuh): query i = slot i;
+// live paths whose Russian roulette ended them (norm == 0) go straight to the ended list, hits are filed under the
+// material family of the primitive they hit.
+struct RqWfClient {
+    WfArgs a;
+    __device__ __forceinline__ int fetch(long long i, V3& o, V3& d, double& md) const {
+        if (i >= a.n_slots || a.st.status[i] != SLOT_ALIVE) return RQ_SKIP;
+        if (a.st.norm[i] == 0.0) return RQ_MISS;
+        const size_t P = (size_t)a.n_slots;
+        o = v3(a.st.ray[i], a.st.ray[P + i], a.st.ray[2 * P + i]);
+        d = v3(a.st.ray[3 * P + i], a.st.ray[4 * P + i], a.st.ray[5 * P + i]);
+        md = a.cfg.max_distance;
+        return RQ_TRACE;
+    }
+    // reached by all 32 lanes together
+    __device__ __forceinline__ void commit(long long i, bool finished, bool hit, const HitRec& rec) const {
+        int list = -1;
+        const int slot = (int)i;
+        if (finished) {
+            if (hit) {
+                a.st.hit_t[slot] = rec.t;
+                a.st.hit_a[slot] = make_int4(rec.prim, rec.leaf, rec.code, rec.flip);
+                a.st.hit_uvw[slot] = make_float4(rec.u, rec.v, rec.w, __int_as_float(rec.mesh_node));
+                a.st.status[slot] = SLOT_HIT;
+                list = a.sp.mats[a.sc.prims[rec.prim].material].type;
+                if (list >= MAT_CONDUCTOR) list = (list == MAT_ROUGH_CONDUCTOR) ? MAT_LAMBERT : MAT_DIELECTRIC;
+            } else {
+                a.st.status[slot] = SLOT_ENDED_ZERO;
+                list = 4;
+            }
+        }
+        __syncwarp();
+        wf_append_lists(a, list, slot);
+    }
 };
 
 // ---- parking ----------------------------------------------------------------------------------------------
@@ -184,7 +225,7 @@ __device__ __forceinline__ unsigned int rq_queue_slot(unsigned int* counter, boo
 // RESUME: walks parked by the previous round carry on with Mesh.hit's answer; LAST: a walk that meets yet another
 // mesh is finished in place by the nested loop instead of being parked again.
 template <bool COUNT, int FEAT, class Client, bool RESUME, bool LAST>
-__global__ void __launch_bounds__(RQ_THREADS, (FEAT & RSB_FEAT_CSG) ? 3 : 4)
+__global__ void __launch_bounds__(RQ_THREADS, (FEAT & RSB_FEAT_CSG) ? 3 : RQ_WALK_BLOCKS)
 k_rq_walk(Scene sc, int n_items, Client cl, RqBuf b, long long n, int round, DevCounters* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* axbuf = ax_storage<(FEAT & RSB_FEAT_STAGED) != 0>(smem, sc, n_items);
@@ -207,9 +248,11 @@ k_rq_walk(Scene sc, int n_items, Client cl, RqBuf b, long long n, int round, Dev
         if (RESUME && valid) i = queue_in[k].x;
         V3 o, d;
         double md = RSB_INF;
-        if (valid) valid = cl.fetch(i, o, d, md);
+        int what = RQ_SKIP;
+        if (valid) what = cl.fetch(i, o, d, md);
+        valid = what != RQ_SKIP;
         bool alive = false, hit = false;
-        if (valid) {
+        if (what == RQ_TRACE) {
             t.init(sc, md, stack, &rec, stats, axbuf);
             if (RESUME) {
                 bool mhit;
@@ -247,20 +290,23 @@ struct MeshPool {
     int32_t* rs_pack;     // [T] ix | iy << 2 | iz << 4 of the lane's ray-space permutation (mesh.pyx:566-610)
     float* rs_s;          // [3][T] sx, sy, sz
     int32_t* mesh_idx;    // [T]
+    const F4** tri_base;  // [T] triangle rows of the lane's mesh
     float4* res;          // warp: [CAP] (t, u, v, w); t = NaN: no hit
-    int32_t* prefix;      // warp: [33 (+3)]
-    int32_t* leaf_off;    // warp: [32]
-    int32_t* res_tri;     // warp: [CAP]
+    int32_t* tri;         // warp: [CAP] triangle id of the pair
+    int32_t* own;         // warp: [CAP] lane that owns the pair
     const double* ax0;    // RayAx storage of thread 0: rows 0..2 mesh-local origin, row 9 ray.max_distance
 };
 
 #define RQ_AX_ROWS 10
-#define RQ_POOL_WARP_BYTES (RQ_POOL_CAP * 16 + (36 + 32 + RQ_POOL_CAP) * 4)
-#define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 20 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
+#define RQ_POOL_WARP_BYTES (RQ_POOL_CAP * 24)
+#define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 28 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
 
 // MeshData._trace_leaf (mesh.pyx:520-563) for every lane with `in_leaf`, the (ray, triangle) pairs dealt out evenly
-// over the warp.  Same scheme as mesh_leaf_coop (rsb_kernels.cuh); here a lane's ray-space transform is published once
-// per ray, not once per trip.  All 32 lanes.
+// over the warp: the lanes that stand at a leaf publish (owner lane, triangle id) for each of their triangles in one
+// list, every lane of the warp then tests the pairs p = lane, lane + 32, ... with the OWNER's mesh-local origin and
+// ray-space shear (read from shared memory, where the owner left them when it picked the ray up), and the owner
+// replays _trace_leaf's comparison -- `t < distance`, first of equal-t triangles wins -- over its own results in leaf
+// order: the same values through the same comparisons as the sequential loop.  All 32 lanes.
 template <class Stats>
 __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& cs, bool in_leaf, int off, int cnt, double d0, MeshHit* mh,
                                                Stats& stats) {
@@ -277,27 +323,25 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
     const int excl = incl - c;
     const int total = __shfl_sync(RSB_FULL_MASK, incl, 31);
     if (total == 0) return false;
-    __syncwarp();
-    cs.prefix[lane] = excl;
-    if (lane == 31) cs.prefix[32] = total;
-    cs.leaf_off[lane] = off;
+    const int32_t* items = c > 0 ? sc.meshes[cs.mesh_idx[threadIdx.x]].tree.items + off : nullptr;
     double distance = d0;
     int closest = -1;
     float cu = 0, cv = 0, cw = 0;
     for (int base = 0; base < total; base += RQ_POOL_CAP) {
+        const int j0 = base > excl ? base - excl : 0;
+        const int j1 = base + RQ_POOL_CAP - excl < c ? base + RQ_POOL_CAP - excl : c;
+        __syncwarp();
+        for (int j = j0; j < j1; ++j) {
+            const int p = excl + j - base;
+            cs.tri[p] = items[j];
+            cs.own[p] = lane;
+        }
         __syncwarp();
         const int lim = total - base < RQ_POOL_CAP ? total - base : RQ_POOL_CAP;
         for (int p = lane; p < lim; p += 32) {
-            const int g = base + p;
-            int lo = 0, hi = 32;           // prefix[lo] <= g < prefix[hi]
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                int mid = (lo + hi) >> 1;
-                if (cs.prefix[mid] <= g) lo = mid; else hi = mid;
-            }
-            const int ot = tid0 + lo;      // the owner's thread index within the CTA
-            const Mesh& m = sc.meshes[cs.mesh_idx[ot]];
-            const int tri = m.tree.items[cs.leaf_off[lo] + (g - cs.prefix[lo])];
+            const int ot = tid0 + cs.own[p];      // the owner's thread index within the CTA
+            const int tri = cs.tri[p];
+            const F4* rows = cs.tri_base[ot] + 3 * (size_t)tri;
             const double* ax = cs.ax0 + ot;
             const V3 o = v3(ax[0], ax[T], ax[2 * T]);
             const double md = ax[9 * T];
@@ -307,25 +351,19 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
             rs.sx = cs.rs_s[ot]; rs.sy = cs.rs_s[T + ot]; rs.sz = cs.rs_s[2 * T + ot];
             float h[4];
             stats.tri_test();
-            const bool hit = mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, md, rs, h);
-            cs.res_tri[p] = tri;
+            const bool hit = mesh_hit_triangle(rows, o, md, rs, h);
             cs.res[p] = hit ? make_float4(h[3], h[0], h[1], h[2]) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         }
         __syncwarp();
-        if (c > 0) {
-            // the owner replays `t < distance`, first of equal-t triangles wins, over its own results in leaf order
-            const int j0 = base > excl ? base - excl : 0;
-            const int j1 = base + RQ_POOL_CAP - excl < c ? base + RQ_POOL_CAP - excl : c;
-            for (int j = j0; j < j1; ++j) {
-                const int p = excl + j - base;
-                const float4 r = cs.res[p];
-                if (r.x == r.x) {
-                    const double t = (double)r.x;
-                    if (t < distance) {
-                        distance = t;
-                        closest = cs.res_tri[p];
-                        cu = r.y; cv = r.z; cw = r.w;
-                    }
+        for (int j = j0; j < j1; ++j) {
+            const int p = excl + j - base;
+            const float4 r = cs.res[p];
+            if (r.x == r.x) {
+                const double t = (double)r.x;
+                if (t < distance) {
+                    distance = t;
+                    closest = cs.tri[p];
+                    cu = r.y; cv = r.z; cw = r.w;
                 }
             }
         }
@@ -370,14 +408,14 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
     MeshPool cs;
     {
         unsigned char* base = smem + RQ_AX_ROWS * 8 * T + RQ_SCAP * 12 * T;
-        cs.rs_pack = reinterpret_cast<int32_t*>(base);
-        cs.rs_s = reinterpret_cast<float*>(base + 4 * T);
-        cs.mesh_idx = reinterpret_cast<int32_t*>(base + 16 * T);
-        unsigned char* w = base + 20 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
+        cs.tri_base = reinterpret_cast<const F4**>(base);
+        cs.rs_pack = reinterpret_cast<int32_t*>(base + 8 * T);
+        cs.rs_s = reinterpret_cast<float*>(base + 12 * T);
+        cs.mesh_idx = reinterpret_cast<int32_t*>(base + 24 * T);
+        unsigned char* w = base + 28 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
         cs.res = reinterpret_cast<float4*>(w);
-        cs.prefix = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
-        cs.leaf_off = cs.prefix + 36;
-        cs.res_tri = cs.leaf_off + 32;
+        cs.tri = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
+        cs.own = cs.tri + RQ_POOL_CAP;
         cs.ax0 = ax0;
     }
     const unsigned int n_q = b.ctr[round];
@@ -416,6 +454,7 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
                 cs.rs_pack[tid] = rs.ix | (rs.iy << 2) | (rs.iz << 4);
                 cs.rs_s[tid] = rs.sx; cs.rs_s[T + tid] = rs.sy; cs.rs_s[2 * T + tid] = rs.sz;
                 cs.mesh_idx[tid] = P.mesh;
+                cs.tri_base[tid] = m.tri;
                 KdCursor c;
                 if (kd_begin(m.tree, ax, c)) {
                     nodes = m.tree.nodes;
@@ -519,7 +558,9 @@ k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* 
                 q = k;
                 V3 o, d;
                 double md;
-                if (cl.fetch(q, o, d, md)) {
+                const int what = cl.fetch(q, o, d, md);
+                if (what == RQ_MISS) done = true;
+                if (what == RQ_TRACE) {
                     traced = traced + 1;
                     leaf.ax.set(axbuf, o, d);
                     leaf.max_distance = md;

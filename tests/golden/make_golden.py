@@ -171,7 +171,93 @@ def parabola_goldens():
     print("parabola scene: hits %d of %d, points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (cc > 0).sum()))
 
 
+def nodes_goldens():
+    """kd-node indices (north-star "kd-node indices bit-exact"): for every hit golden above, the world kd leaf in which
+    the reference accepted the hit and the mesh kd leaf that produced the triangle (oracle/harness.oracle_hit_nodes:
+    the reference's own leaf-visit sequence through the Python-subclassable KDTree3D, kdtree3d.pyx:993-1098)."""
+    out = {}
+
+    def add(tag, world, o, d, md=None):
+        h = harness.oracle_hit(world, o, d, md)
+        leaf, mesh_leaf, visits = harness.oracle_hit_nodes(world, o, d, md, hits=h)
+        out[tag + "_leaf"], out[tag + "_mesh_leaf"] = leaf, mesh_leaf
+        print("%-10s rays %5d hits %5d mesh hits %5d leaf visits %6d" % (tag, len(o), (leaf >= 0).sum(), (mesh_leaf >= 0).sum(), visits))
+    o, d = scenes.zoo_rays(6000)
+    add("zoo", scenes.primitive_zoo(api), o, d)
+    add("zoo_md", scenes.primitive_zoo(api), o, d, np.random.default_rng(4).uniform(0.5, 7.0, len(o)))
+    o, d, md = scenes.edge_rays()
+    add("edge", scenes.edge_scene(api), o, d, md)
+    rng = np.random.default_rng(1)
+    o = np.tile(np.array([0, 0, -4.0]), (5000, 1))
+    tgt = np.c_[rng.uniform(-1, 1, 5000), rng.uniform(-1, 1, 5000), np.zeros(5000)]
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    add("spheres", scenes.random_spheres(api, 2000, seed=7), np.ascontiguousarray(o), np.ascontiguousarray(d))
+    o, d = scenes.mesh_rays(5000)
+    add("mesh_smooth", scenes.mesh_scene(api, True), o, d)
+    add("mesh_flat", scenes.mesh_scene(api, False), o, d)
+    o, d = scenes.zoo_rays(4000, seed=21)
+    add("scaled", scenes.scaled_scene(api), o, d)
+    o, d = scenes.parabola_rays()
+    add("parabola", scenes.parabola_scene(api), o, d)
+    save("kd_nodes", **out)
+
+
+def with_nodes(world, o, d, md=None):
+    g = hits(world, o, d, md)
+    leaf, mesh_leaf, visits = harness.oracle_hit_nodes(world, o, d, md, hits=g)
+    g.update(leaf=leaf, mesh_leaf=mesh_leaf)
+    return g
+
+
+def bunny_goldens():
+    """(1) the reference's own mesh fixture demos/resources/stanford_bunny.rsm (144,046 triangles, the depth-24 tree stored
+    in the file); (2) BASELINE config 4: Cornell box + the bunny refined to 1,000,000 triangles -- mesh and tree written
+    by the mirror's .rsm writer, LOADED BY THE REFERENCE (Mesh.from_file), hit by the reference"""
+    import time
+    t0 = time.time()
+    world = scenes.bunny_rsm_scene(api)
+    print("reference loaded stanford_bunny.rsm in %.1f s" % (time.time() - t0))
+    o, d = scenes.bunny_rsm_rays()
+    g = with_nodes(world, o, d)
+    cc, cp = harness.oracle_contains(world, scenes.bunny_rsm_points())
+    save("bunny_rsm_hits", **g, contains_count=cc, contains_prims=cp)
+    print("bunny.rsm: hits %d of %d (mesh %d), points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (g["triangle"] >= 0).sum(), (cc > 0).sum()))
+    path = scenes.refined_bunny_rsm(1000000)
+    t0 = time.time()
+    world = scenes.cornell_mesh_scene(api, path)
+    print("reference loaded %s in %.1f s" % (os.path.basename(path), time.time() - t0))
+    o, d = scenes.cornell_mesh_rays()
+    g = with_nodes(world, o, d)
+    pts = np.random.default_rng(15).uniform([-0.5, -1.0, -0.4], [0.7, 0.05, 0.6], (1500, 3))
+    cc, cp = harness.oracle_contains(world, pts)
+    save("cornell_bunny_1m_hits", **g, contains_count=cc, contains_prims=cp, rsm_sha256=digest(open(path, "rb").read()))
+    print("cornell + 1M bunny: hits %d of %d (mesh %d), points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (g["triangle"] >= 0).sum(), (cc > 0).sum()))
+
+
+def sweep_goldens():
+    """BASELINE config 5 at size: 10,000 spheres drawn from the reference generator after seed(7); the first 20,000 rays
+    of the device sweep (seed 2024; incoherent order and Morton order) restated in numpy, hit by the reference"""
+    from raysect.core.math.random import seed, uniform
+    seed(7)
+    world = scenes.sweep_spheres(api, uniform)
+    out = {}
+    for tag, order in (("random", 0), ("morton", 7)):
+        o, d, idx = scenes.sweep_rays(2024, 0, 20000, scenes.SWEEP_ORIGIN, scenes.SWEEP_TARGET, scenes.SWEEP_HALF, order)
+        g = with_nodes(world, o, d)
+        out.update({tag + "_" + k: g[k] for k in ("primitive", "distance", "leaf")})
+        out["tree_sha256"], out["tree_bytes"] = g["tree_sha256"], g["tree_bytes"]
+        print("sweep %s: hits %d of %d" % (tag, (g["primitive"] >= 0).sum(), len(o)))
+    save("spheres10k_sweep", **out)
+
+
 def main():
+    if "--bunny-only" in sys.argv:
+        return bunny_goldens()
+    if "--sweep-only" in sys.argv:
+        return sweep_goldens()
+    if "--nodes-only" in sys.argv:
+        return nodes_goldens()
     if "--parabola-only" in sys.argv:
         return parabola_goldens()
     if "--extremes-only" in sys.argv:
@@ -251,6 +337,9 @@ def main():
     scaled_goldens()
     extremes_goldens()
     parabola_goldens()
+    nodes_goldens()
+    bunny_goldens()
+    sweep_goldens()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

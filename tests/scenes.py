@@ -511,3 +511,151 @@ def prism_scene(api):
           a.UniformSurfaceEmitter(a.InterpolatedSF(*CB_LIGHT), 5.0))
     a.Box(a.Point3D(-3, -3, 0), a.Point3D(3, 3, 0.1), world, a.translate(0, 0, 3), a.AbsorbingSurface())
     return world
+
+
+# ---- rays of rsb_hit_sweep_dev, restated in numpy (csrc/rsb_trav.cuh k_rq_sweep_gen) -----------------------------------
+def philox_pair(seed, index):
+    """Philox4x32-10 words 0 and 1 of block 0 of stream `index` (csrc/rsb_rng.h Philox4x32: key = seed,
+    counter = (0, 0, index lo, index hi)) -> two uniform() values, as the sweep draws them."""
+    index = np.asarray(index, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    c0 = np.zeros_like(index); c1 = np.zeros_like(index)
+    c2 = index & m32; c3 = index >> np.uint64(32)
+    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64(seed >> 32)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    w0 = (c1 << np.uint64(32)) | c0
+    w1 = (c3 << np.uint64(32)) | c2
+    scale = 1.0 / 9007199254740992.0
+    return (w0 >> np.uint64(11)).astype(np.float64) * scale, (w1 >> np.uint64(11)).astype(np.float64) * scale
+
+
+def _morton_compact(x):
+    x = x & np.uint64(0x5555555555555555)
+    for shift, mask in ((1, 0x3333333333333333), (2, 0x0F0F0F0F0F0F0F0F), (4, 0x00FF00FF00FF00FF), (8, 0x0000FFFF0000FFFF),
+                        (16, 0x00000000FFFFFFFF)):
+        x = (x | (x >> np.uint64(shift))) & np.uint64(mask)
+    return x
+
+
+def sweep_rays(seed, first, n, origin, target, half_window, order_log2=0):
+    """origins, directions [n][3] of rays first .. first + n - 1 of a sweep: toward target + (jx, jy, 0) * half_window;
+    order_log2 = 0: (jx, jy) uniform over the window per ray; g > 0: jittered inside cell (index mod 4^g) of a
+    2^g x 2^g grid walked along the Morton curve."""
+    idx = np.arange(first, first + n, dtype=np.uint64)
+    u1, u2 = philox_pair(seed, idx)
+    if order_log2 > 0:
+        cell = idx & np.uint64((1 << (2 * order_log2)) - 1)
+        inv = 1.0 / float(1 << order_log2)
+        u1 = (_morton_compact(cell).astype(np.float64) + u1) * inv
+        u2 = (_morton_compact(cell >> np.uint64(1)).astype(np.float64) + u2) * inv
+    px = target[0] + (2.0 * u1 - 1.0) * half_window
+    py = target[1] + (2.0 * u2 - 1.0) * half_window
+    pz = np.full(n, float(target[2]))
+    dx, dy, dz = px - origin[0], py - origin[1], pz - origin[2]
+    t = dx * dx + dy * dy + dz * dz
+    t = 1.0 / np.sqrt(t)
+    d = np.stack([dx * t, dy * t, dz * t], axis=1)
+    o = np.tile(np.array(origin, dtype=np.float64), (n, 1))
+    return np.ascontiguousarray(o), np.ascontiguousarray(d), idx
+
+
+SWEEP_ORIGIN, SWEEP_TARGET, SWEEP_HALF = (0.0, 0.0, -4.0), (0.0, 0.0, 0.0), 0.9    # BASELINE config 5 (tools_sweep.py, bench.py)
+
+
+def sweep_spheres(api, uniform, n=10000):
+    """BASELINE config 5 scene: n spheres drawn from the REFERENCE generator after seed(7); `uniform` is a
+    callable yielding that stream: raysect.core.math.random.uniform on the reference, the device's / the host build's
+    restatement of MT19937-64 elsewhere (rng_uniform(7, 4 n))."""
+    return random_spheres(api, n, seed=7, uniform=uniform)
+
+
+# ---- the reference's own mesh fixture and BASELINE config 4 (Cornell box + Stanford bunny refined to 1,000,000 triangles) ---
+import os as _os
+
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+BUNNY_RSM = _os.path.join(_ROOT, "oracle", "_ref", "resources", "stanford_bunny.rsm")   # demos/resources/stanford_bunny.rsm
+BUNNY_OBJ = _os.path.join(_ROOT, "oracle", "_ref", "resources", "stanford_bunny.obj")   # demos/resources/stanford_bunny.obj
+MESH_CACHE = _os.path.join(_ROOT, "build", "cache")
+
+
+def bunny_rsm_scene(api, path=BUNNY_RSM):
+    """The 144,046-triangle bunny with the kd-tree the reference shipped inside the file (Mesh.from_file: nothing is
+    rebuilt), as demos/bunny.py places it, plus a ground box."""
+    a = api
+    world = a.World()
+    m = a.AbsorbingSurface()
+    a.Mesh.from_file(path, parent=world, transform=a.translate(0.0, 0.0, 0.0) * a.rotate(165, 0, 0), material=m)
+    a.Box(a.Point3D(-1, -0.05, -1), a.Point3D(1, 0.033, 1), world, a.translate(0, 0, 0), m)
+    return world
+
+
+def bunny_rsm_rays(n=4000, seed=12):
+    """rays from a shell around the bunny into its bounding region; a tenth start inside the region"""
+    rng = np.random.default_rng(seed)
+    centre = np.array([-0.017, 0.11, 0.0])
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    u[:, 1] = np.abs(u[:, 1]) * 0.8 + 0.05
+    o = centre + 0.45 * u
+    tgt = centre + rng.uniform([-0.09, -0.08, -0.07], [0.09, 0.08, 0.07], (n, 3))
+    k = n // 10
+    o[:k] = centre + rng.uniform([-0.08, -0.07, -0.06], [0.08, 0.07, 0.06], (k, 3))
+    d = tgt - o
+    d[:k] = rng.normal(size=(k, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+def bunny_rsm_points(n=1500, seed=13):
+    rng = np.random.default_rng(seed)
+    return np.array([-0.017, 0.11, 0.0]) + rng.uniform([-0.1, -0.09, -0.08], [0.1, 0.09, 0.08], (n, 3))
+
+
+def refined_bunny_rsm(triangles=1000000, obj=BUNNY_OBJ, cache_dir=MESH_CACHE):
+    """BASELINE config 4 mesh as SURVEY 8(d) specifies it: demos/resources/stanford_bunny.obj refined deterministically to
+    exactly `triangles` triangles (refine_mesh), scaled to stand 1 m tall on the floor of the Cornell box, its SAH
+    kd-tree built by this package (byte-identical to the reference builder's, tests/test_cabi_symbols.py), written as a
+    Raysect mesh file with the mirror's byte-identical .rsm writer and cached: both the reference (Mesh.from_file) and
+    this package load mesh AND tree from the very same bytes.  Returns the file name."""
+    path = _os.path.join(cache_dir, "bunny_%d.rsm" % triangles)
+    if _os.path.exists(path):
+        return path
+    import source_b200 as mirror
+    base = mirror.import_obj(obj)
+    v, t = refine_mesh(base.data.vertices, base.data.triangles, triangles)
+    v = v.astype(np.float64)
+    lo, hi = v.min(0), v.max(0)
+    s = 1.0 / (hi[1] - lo[1])
+    v = (v - [0.5 * (lo[0] + hi[0]), lo[1], 0.5 * (lo[2] + hi[2])]) * s + [0.0, -1.0 + 1e-6 + 0.5, 0.0]
+    mesh = mirror.Mesh(v.astype(np.float32), t, None, smoothing=False, closed=True)
+    _os.makedirs(cache_dir, exist_ok=True)
+    tmp = path + ".tmp.%d" % _os.getpid()
+    mesh.save(tmp)
+    _os.replace(tmp, path)
+    return path
+
+
+def cornell_mesh_scene(api, rsm_path, glass=False):
+    """BASELINE config 4: the Cornell box with a Lambert mesh (from a .rsm file) standing in it"""
+    def extra(a, w):
+        a.Mesh.from_file(rsm_path, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 0, 0),
+                         material=a.Lambert(a.ConstantSF(0.7)))
+    return cornell_box(api, glass=glass, extra=extra)
+
+
+def cornell_mesh_rays(n=4000, seed=14):
+    """camera-like rays toward the mesh plus rays scattered from points inside the box (bounce-like)"""
+    rng = np.random.default_rng(seed)
+    o = np.tile(np.array([0.0, 0.0, -3.3]), (n, 1))
+    tgt = np.array([0.1, -0.5, 0.1]) + rng.uniform([-0.6, -0.5, -0.5], [0.6, 0.55, 0.5], (n, 3))
+    k = n // 2
+    o[:k] = rng.uniform([-0.95, -0.95, -0.95], [0.95, 0.95, 0.95], (k, 3))
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)

@@ -319,32 +319,12 @@ def test_million_triangle_mesh_properties(make_backend):
     be.close()
 
 
-def _philox_pair(seed, index):
-    """Philox4x32-10 words 0 and 1 of block 0 of stream `index` (csrc/rsb_rng.h Philox4x32: key = seed,
-    counter = (0, 0, index lo, index hi)) -> two uniform() values, as k_hit_sweep draws them."""
-    index = np.asarray(index, dtype=np.uint64)
-    m32 = np.uint64(0xFFFFFFFF)
-    c0 = np.zeros_like(index); c1 = np.zeros_like(index)
-    c2 = index & m32; c3 = index >> np.uint64(32)
-    k0 = np.uint64(seed & 0xFFFFFFFF); k1 = np.uint64(seed >> 32)
-    for _ in range(10):
-        p0 = np.uint64(0xD2511F53) * c0
-        p1 = np.uint64(0xCD9E8D57) * c2
-        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
-        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
-        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
-        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
-    w0 = (c1 << np.uint64(32)) | c0
-    w1 = (c3 << np.uint64(32)) | c2
-    scale = 1.0 / 9007199254740992.0
-    return (w0 >> np.uint64(11)).astype(np.float64) * scale, (w1 >> np.uint64(11)).astype(np.float64) * scale
-
-
 @pytest.mark.gpu
+@pytest.mark.parametrize("order", [0, 7])
 @pytest.mark.parametrize("kind", ["spheres", "mesh"])
-def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind):
-    """The sweep kernels (persistent lanes with refill; for meshes the two-level loop with pooled triangle tests) must
-    report exactly the hits the one-ray-per-thread batch kernel reports for the rays they generate on the device."""
+def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind, order):
+    """The sweep (rays generated on the device, incoherent or along the Morton curve, several pipeline chunks) must report
+    exactly the hits rsb_hit_batch reports for the same rays restated in numpy (scenes.sweep_rays)."""
     import ctypes as C
     import torch
     import scenes
@@ -368,19 +348,10 @@ def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind):
     xr = torch.zeros(1, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     cabi.check(device.lib.rsb_hit_sweep_dev(device.ctx, acc.scene, C.c_void_p(st), n, first, seed, (C.c_double * 3)(*origin),
-                                            (C.c_double * 3)(*target), half, 0, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
+                                            (C.c_double * 3)(*target), half, order, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
                                             C.c_void_p(xr.data_ptr()), 0))
     torch.cuda.synchronize()
-    idx = np.arange(first, first + n, dtype=np.uint64)
-    u1, u2 = _philox_pair(seed, idx)
-    px = target[0] + (2.0 * u1 - 1.0) * half
-    py = target[1] + (2.0 * u2 - 1.0) * half
-    pz = np.full(n, target[2])
-    dx, dy, dz = px - origin[0], py - origin[1], pz - origin[2]
-    t = dx * dx + dy * dy + dz * dz
-    t = 1.0 / np.sqrt(t)
-    d = np.stack([dx * t, dy * t, dz * t], axis=1)
-    o = np.tile(np.array(origin), (n, 1))
+    o, d, idx = scenes.sweep_rays(seed, first, n, origin, target, half, order)
     r = acc.hit_batch(o, d)
     hit = r.primitive >= 0
     assert hit.sum() > n // 2
