@@ -1,27 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- headline measurement of the B200 hot path (contract: see the task brief / DESIGN.md).
+"""bench.py -- measurement of the B200 hot path (contract: the task brief / DESIGN.md section 9).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rng mt|philox]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rng mt|philox] [--configs C3,C4,C5|none]
 
-Workload (BASELINE.json configs[1]): Cornell box (demos/cornell_box.py scene), PinholeCamera 1024x1024,
-256 samples/pixel, 64 spectral bins, one spectral ray.  One STEP = one full frame (one observe() pass).
-Metric: Mrays/s, "ray" = the reference's ray counter (primary rays + daughters spawned,
-raysect/optical/ray.pyx:375-378,537-547).  frames/s = 1000 / ms_per_step.
+Headline workload (BASELINE.json configs[1], "C2"): Cornell box (demos/cornell_box.py scene), PinholeCamera 1024x1024,
+256 samples/pixel, 64 spectral bins, one spectral ray.  One STEP = one full frame.  Metric: Mrays/s, "ray" = the
+reference's ray counter (primary rays + daughters spawned, raysect/optical/ray.pyx:375-378,537-547).
 
-  value     device-resident: scene, tables and frame buffers live in HBM; timed with CUDA events around
-            K x rsb_render_dev (+ the NCCL reduce of the frame when N > 1), max over ranks.
-  e2e       through the public API with HOST buffers: per step the pixel lists and spectral tables go
-            host->device from pinned memory and the reduced frame (mean, variance) comes device->host into
-            pinned memory, inside the timed region.
-  roofline  algorithmic bytes of the render kernel (SURVEY 8(d) model, from the kernel's own traversal
-            counters in an untimed counting pass) / mean kernel time, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the compiled reference (oracle/_ref) on the box's host cores, bounded sample.
+  value     device-resident: scene, tables and frame buffers live in HBM; CUDA events around K x rsb_render_passes_dev
+            (+ the NCCL collective that assembles the frame when N > 1), max over ranks.
+  e2e       the same frame through the reference-facing seam with HOST buffers: at N = 1 the real drop-in plugin -- a
+            raysect PinholeCamera + SpectralPowerPipeline2D with camera.render_engine = CudaRenderEngine(passes=8),
+            wall clock around camera.observe() (task list in, pipeline.frame numpy arrays out) -- when the compiled
+            reference travelled with the snapshot; else, and at N > 1, FrameRenderer.step_host (pinned host buffers).
+  roofline  algorithmic bytes of the traversal kernel (SURVEY 8(d) model, from the kernels' own counters in an
+            untimed counting pass) / its device time (CUDA events around every trace phase), against
+            MEASURED_PEAKS.json hbm_gbs; `phases` lists the measured share of every kernel of the wave.
+  configs   the rest of BASELINE.json's metric under the same clock: C4 = Cornell box + Stanford bunny refined to
+            1,000,000 triangles (1024^2, 64 spp; tiles over the N ranks), C5 = ray-batch sweep over the 10,000-sphere
+            field (1e7 and 1e9 device-generated rays, incoherent and Morton order; ray ranges over the N ranks),
+            C3 = dispersive CSG prism 512^2 x 512 spectral bins / rays (N = 1) -- each with Mrays/s, frames/s and a
+            live roofline.
+  cpu_baseline  the compiled reference (oracle/_ref) on the box's host cores, bounded samples.
 
---impl reference times the reference's own Cython path (MulticoreEngine, all host cores) on a bounded sample
-of the same workload and prints the same JSON line with "impl": "reference".
+--impl reference times the reference's own Cython path (MulticoreEngine, all host cores) on bounded samples of the
+same workloads and prints the same JSON line with "impl": "reference".
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -33,14 +40,122 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 WORKLOAD = dict(name="cornell_box 1024x1024 x 256 spp x 64 bins (BASELINE configs[1])", pixels=1024, spp=256, bins=64)
-CPU_SAMPLE = dict(pixels=192, spp=8, bins=64)
+CPU_SAMPLE = dict(pixels=512, spp=16, bins=64)      # >= 5 s per observe(): MulticoreEngine's per-call fork is amortised
+CPU_SERIAL_SAMPLE = dict(pixels=128, spp=8, bins=64)
 DEFAULT_PASSES = 8   # 256 spp = 8 accumulated observe() passes of 32 spp (the reference's progressive-render loop)
 RAY_CFG = dict(extinction_prob=0.01, extinction_min_depth=3, max_depth=500, importance_sampling=True,
                important_path_weight=0.25)   # demos/cornell_box.py:147-156
 MIN_WL, MAX_WL = 375.0, 740.0               # observer defaults, observer.pyx:116-117
+C4 = dict(name="cornell_box + stanford_bunny refined to 1,000,000 triangles, 1024x1024 x 64 spp x 64 bins (BASELINE configs[3])",
+          pixels=1024, spp=64, bins=64, triangles=1000000)
+C4_CPU = dict(pixels=256, spp=4)
+C5 = dict(name="ray-batch sweep over 10,000 spheres from the reference generator after seed(7) (BASELINE configs[4])",
+          spheres=10000, rays=(10**7, 10**9), seed=2024)
+C5_CPU_RAYS = 200000
+C3 = dict(name="dispersive CSG prism 512x512, 512 spectral bins = 512 spectral rays (BASELINE configs[2])",
+          pixels=512, bins=512, rays=512, spp=2)
+C3_CPU = dict(pixels=64, bins=64, rays=64, spp=2)      # 64 slices: the reference forks its workers once per slice (512 forks take ~40 s whatever the frame)
+
+
+def trace_algorithmic_bytes(c):
+    """World.hit share of the SURVEY 8(d) model = what the traversal kernels touch: 56 B ray in + 16 B hit out, 16 B per
+    kd branch, 8 B per leaf header, 4 B per item id, 128 B per analytic primitive test, 48 B per triangle test."""
+    return 72 * c["rays"] + 16 * c["branches"] + 8 * c["leaves"] + 4 * c["items"] + 128 * c["prim_tests"] + 48 * c["tri_tests"]
+
+
+def algorithmic_bytes(c, bins, spp):
+    """whole step: + World.contains (24 B point in, 12 B per kd node descended, 4 B per item id, 128 B per containment
+    test), the spectral table reads (bins * 8 B per interaction) and the pixel's share of the frame write"""
+    contains = 24 * c["contains"] + 12 * c["contains_nodes"] + 4 * c["contains_items"] + 128 * c["contains_prim_tests"]
+    return trace_algorithmic_bytes(c) + contains + 8 * bins * c.get("table_reads", 0) + c["paths"] * bins * 20.0 / spp
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
 # ----------------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------------
+def _counting_engine(cores):
+    from raysect.core.workflow import MulticoreEngine, SerialEngine
+
+    class Counting(MulticoreEngine if cores > 1 else SerialEngine):
+        rays = 0
+
+        def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
+            def counted(result, *a, **k):
+                Counting.rays += result[2]
+                update(result, *a, **k)
+            super().run(tasks, render, counted, render_args, render_kwargs, update_args, update_kwargs)
+    return Counting(processes=cores) if cores > 1 else Counting(), Counting
+
+
+def _ref_observe(cam, pipe, cores, steps, warmup):
+    eng, cls = _counting_engine(cores)
+    cam.render_engine = eng
+    times, rays = [], []
+    for i in range(warmup + steps):
+        cls.rays = 0
+        pipe.accumulate = False
+        t0 = time.perf_counter()
+        cam.observe()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            rays.append(cls.rays)
+    return sum(rays) / sum(times) / 1e6, sum(times) / len(times), sum(rays) / len(rays)
+
+
+def reference_configs(api, harness, scenes, cores, which):
+    """bounded samples of C4 / C5 / C3 on the reference's own code path"""
+    import numpy as np
+    out = {}
+    if "C4" in which:
+        try:
+            path = scenes.refined_bunny_rsm(C4["triangles"])
+            world = scenes.cornell_mesh_scene(api, path)       # Mesh.from_file: the reference loads mesh + tree from the .rsm
+            s = C4_CPU
+            cam, pipe = scenes.cornell_camera(api, world, pixels=(s["pixels"], s["pixels"]), samples=s["spp"], bins=C4["bins"],
+                                              path_weight=RAY_CFG["important_path_weight"])
+            world.build_accelerator()
+            v, sec, rays = _ref_observe(cam, pipe, cores, 1, 0)
+            out["C4"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                         "sample": "%dx%d x %d spp (one observe()), MulticoreEngine(%d)" % (s["pixels"], s["pixels"], s["spp"], cores)}
+        except Exception as exc:   # noqa: BLE001
+            out["C4"] = {"unavailable": repr(exc)}
+    if "C5" in which:
+        from raysect.core import Point3D, Vector3D
+        from raysect.core.math.random import seed, uniform
+        from raysect.core.ray import Ray as CoreRay
+        seed(7)
+        world = scenes.sweep_spheres(api, uniform, C5["spheres"])
+        world.build_accelerator()
+        o, d, _ = scenes.sweep_rays(C5["seed"], 0, C5_CPU_RAYS, scenes.SWEEP_ORIGIN, scenes.SWEEP_TARGET, scenes.SWEEP_HALF, 0)
+        rays = [CoreRay(Point3D(*o[i]), Vector3D(*d[i])) for i in range(len(o))]
+        t0 = time.perf_counter()
+        hits = sum(1 for r in rays if world.hit(r) is not None)
+        dt = time.perf_counter() - t0
+        out["C5"] = {"value": len(rays) / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "reference", "hit_fraction": hits / len(rays),
+                     "sample": "%d rays of the sweep (incoherent order) through the Python world.hit loop of "
+                               "demos/core/ray_intersection_hitpoints.py, 1 core" % len(rays)}
+    if "C3" in which:
+        s = C3_CPU
+        world = scenes.prism_scene(api)
+        cam, pipe = scenes.cornell_camera(api, world, pixels=(s["pixels"], s["pixels"]), samples=s["spp"], bins=s["bins"],
+                                          spectral_rays=s["rays"], path_weight=0.75)
+        cam.transform = api.translate(0.3, 0.2, -2.2) * api.rotate(5, -3, 0)
+        world.build_accelerator()
+        v, sec, rays = _ref_observe(cam, pipe, cores, 1, 0)
+        out["C3"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                     "sample": "%dx%d x %d spp x %d spectral rays (one observe() = %d slices, a worker fork per slice), "
+                               "MulticoreEngine(%d)" % (s["pixels"], s["pixels"], s["spp"], s["rays"], s["rays"], cores)}
+    return out
+
+
 def run_reference(args):
     """The reference's own CPU path (oracle/_ref = the unmodified compiled reference) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -52,49 +167,35 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) not present in this snapshot"}))
         return 0
     api = harness.ref_api()
-    from raysect.core.workflow import MulticoreEngine
     cores = os.cpu_count() or 1
-
-    class Counting(MulticoreEngine):
-        rays = 0
-
-        def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-            def counted(result, *a, **k):
-                Counting.rays += result[2]
-                update(result, *a, **k)
-            super().run(tasks, render, counted, render_args, render_kwargs, update_args, update_kwargs)
-
     s = CPU_SAMPLE
     world = scenes.cornell_box(api)
     cam, pipe = scenes.cornell_camera(api, world, pixels=(s["pixels"], s["pixels"]), samples=s["spp"], bins=s["bins"],
                                       path_weight=RAY_CFG["important_path_weight"])
-    cam.render_engine = Counting(processes=cores)
     world.build_accelerator()
-    times, rays = [], []
     # The reference renders its sample in ONE observe() call whatever --passes says: that is its faster mode
-    # (MulticoreEngine forks its workers on every observe(); measured here, 4 passes of the bounded sample run at
-    # half the rays/s of one pass), and the frame is statistically the same.
-    for i in range(args.warmup + args.steps):
-        Counting.rays = 0
-        pipe.accumulate = False
-        t0 = time.perf_counter()
-        cam.observe()
-        dt = time.perf_counter() - t0
-        if i >= args.warmup:
-            times.append(dt)
-            rays.append(Counting.rays)
-    total_t, total_r = sum(times), sum(rays)
-    value = total_r / total_t / 1e6
+    # (MulticoreEngine forks its workers on every observe()), and the frame is statistically the same.
+    value, sec, rays = _ref_observe(cam, pipe, cores, args.steps, args.warmup)
     sample = "cornell_box %dx%d x %d spp (one observe() pass) x %d bins, MulticoreEngine(%d)" % (
         s["pixels"], s["pixels"], s["spp"], s["bins"], cores)
+    # one core: SerialEngine on a smaller sample of the same workload
+    q = CPU_SERIAL_SAMPLE
+    cam1, pipe1 = scenes.cornell_camera(api, world, pixels=(q["pixels"], q["pixels"]), samples=q["spp"], bins=q["bins"],
+                                        path_weight=RAY_CFG["important_path_weight"])
+    v1, _, _ = _ref_observe(cam1, pipe1, 1, 1, 0)
+    which = [] if args.configs == "none" else args.configs.split(",")
+    cfgs = reference_configs(api, harness, scenes, cores, which)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, len(times)), "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample,
+                         "serial_1core": {"value": v1, "unit": "Mrays/s", "cores": 1,
+                                          "sample": "cornell_box %dx%d x %d spp, SerialEngine" % (q["pixels"], q["pixels"], q["spp"])},
+                         "configs": cfgs},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rays_per_step": total_r / max(1, len(rays)),
+        "rays_per_step": rays,
     }
     print(json.dumps(line))
     return 0
@@ -133,181 +234,349 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def algorithmic_bytes(c, bins, spp):
-    """per ray 72 B (56 in + 16 out) + 16 B per kd branch + 8 B per leaf + 4 B per item id
-    + 128 B per analytic primitive test + 48 B per triangle test; per path the spectral table reads
-    (surface + volume interactions, bins*8 B each) and the pixel's share of the frame write (bins*20/spp)."""
-    ray = trace_algorithmic_bytes(c)
-    # World.contains: 24 B point in, 12 B per kd node descended (split + child), 4 B per item id, 128 B per
-    # primitive containment test
-    contains = 24 * c["contains"] + 12 * c["contains_nodes"] + 4 * c["contains_items"] + 128 * c["contains_prim_tests"]
-    spectral = 8 * bins * c.get("table_reads", 0)
-    frame = c["paths"] * bins * 20.0 / spp
-    return ray + contains + spectral + frame
+class Ctx:
+    """what every workload needs: ranks, device, barrier, max-over-ranks timing"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; source_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world_size > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from source_b200.engine import Device
+        self.device = Device(self.local_rank)
+        self.peak, self.peak_source = peak_hbm()
+
+    def barrier(self):
+        if self.world_size > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value, op="max", dtype=None):
+        torch = self.torch
+        t = torch.tensor([value], dtype=dtype or torch.float64, device=self.dev)
+        if self.world_size > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.item()
 
 
-def trace_algorithmic_bytes(c):
-    """World.hit share of the model = what k_wf_trace touches: 56 B ray in + 16 B hit out, 16 B per kd branch,
-    8 B per leaf header, 4 B per item id, 128 B per analytic primitive test, 48 B per triangle test."""
-    return 72 * c["rays"] + 16 * c["branches"] + 8 * c["leaves"] + 4 * c["items"] + 128 * c["prim_tests"] + 48 * c["tri_tests"]
+def phase_shares(stats_sum, total_ms):
+    ph = {k: stats_sum[k + "_ms"] for k in ("trace", "shade", "finalize", "regen")}
+    tot = sum(ph.values())
+    return {"ms_per_step": ph, "share_of_wave_kernels": {k: (v / tot if tot else None) for k, v in ph.items()},
+            "largest": max(ph, key=ph.get) if tot else None, "kernels_share_of_step": tot / total_ms if total_ms else None}
 
 
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+def timed_frames(cx, renderer, steps, warmup, seed0):
+    """K frames device-resident: (total_ms max over ranks, rays summed over ranks, per-step phase times of rank 0, launches, waves)"""
+    torch = cx.torch
+    for i in range(warmup):
+        renderer.step_device(seed=seed0 + i)
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays_t = torch.zeros(1, dtype=torch.int64, device=cx.dev)
+    acc = dict(trace_ms=0.0, shade_ms=0.0, finalize_ms=0.0, regen_ms=0.0, trace_launches=0, launches=0, waves=0)
+    cx.barrier()
+    e0.record()
+    for i in range(steps):
+        rays_t += renderer.step_device(seed=seed0 + 100 + i, time_trace=True)
+        rs = cx.device.render_stats()
+        for k in acc:
+            acc[k] += rs[k]
+    e1.record()
+    cx.barrier()
+    total_ms = cx.reduce(e0.elapsed_time(e1), "max")
+    if cx.world_size > 1:
+        cx.dist.all_reduce(rays_t, op=cx.dist.ReduceOp.SUM)
+    return total_ms, int(rays_t.item()), {k: v / steps for k, v in acc.items()}
 
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; source_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
+def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kernel):
+    counters = renderer.count_pass(seed=seed)
+    alg_step = algorithmic_bytes(counters, bins, spp)
+    alg = trace_algorithmic_bytes(renderer.local_counters)     # rank 0's own share against rank 0's own kernel time
+    trace_ms = per_step["trace_ms"]
+    achieved = alg / (trace_ms * 1e-3) / 1e9 if trace_ms else None
+    launches = max(1.0, per_step["trace_launches"])
+    return {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak if achieved else None,
+            "traffic": None, "kernel": kernel, "kernel_ms": trace_ms / launches, "launches_per_step": per_step["trace_launches"],
+            "kernel_ms_per_step": trace_ms, "kernel_share_of_step": trace_ms / total_ms_step,
+            "algorithmic_bytes_per_launch": alg / launches, "algorithmic_bytes_per_step": alg,
+            "whole_step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (total_ms_step * 1e-3) / 1e9,
+                           "frac": alg_step / (total_ms_step * 1e-3) / 1e9 / cx.peak},
+            "phases": phase_shares(per_step, total_ms_step), "peak_source": cx.peak_source, "counters": counters}
+
+
+# ----------------------------------------------------------------------------------------------------
+def plugin_e2e(cx, w, args, steps):
+    """N = 1: the real drop-in seam.  raysect objects, camera.render_engine = CudaRenderEngine(passes), wall clock around
+    camera.observe(): flatten + upload + render + Pipeline.update into pipeline.frame's numpy arrays."""
+    from oracle import harness
+    if not harness.available():
+        return None
+    import scenes
+    api_ref = harness.ref_api()
+    from source_b200.plugin import CudaRenderEngine
+    world = scenes.cornell_box(api_ref)
+    cam, pipe = scenes.cornell_camera(api_ref, world, pixels=(w["pixels"], w["pixels"]), samples=w["spp"], bins=w["bins"],
+                                      path_weight=RAY_CFG["important_path_weight"])
+    pipe.accumulate = False
+    eng = CudaRenderEngine(seed=1, rng=args.rng, device=cx.device, passes=args.passes)
+    cam.render_engine = eng
+    cam.observe()                       # warm-up: allocations, kernel loading
+    cx.torch.cuda.synchronize()
+    eng.ray_count = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cam.observe()
+    dt = time.perf_counter() - t0
+    frame_bytes = w["pixels"] * w["pixels"] * w["bins"] * 20
+    return {"value": eng.ray_count / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": w["pixels"] * w["pixels"] * 8 + 8 * w["bins"] * 16,
+            "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": dt / steps,
+            "path": "raysect PinholeCamera.observe() -> CudaRenderEngine.run (rsb_render_slice + rsb_slice_update_frame) -> "
+                    "SpectralPowerPipeline2D.frame numpy arrays; wall clock"}
+
+
+def run_c4(cx, args):
     import scenes
     import source_b200 as api
     from source_b200 import _cabi as cabi
     from source_b200.distributed import FrameRenderer
-    from source_b200.engine import Device
+    torch = cx.torch
+    t0 = time.time()
+    note = None
+    have_obj = os.path.exists(scenes.BUNNY_OBJ) or os.path.exists(os.path.join(scenes.MESH_CACHE, "bunny_%d.rsm" % C4["triangles"]))
+    if have_obj:
+        if cx.rank == 0:
+            scenes.refined_bunny_rsm(C4["triangles"])          # cached .rsm (mesh + tree); the other ranks read it
+        cx.barrier()
+        world = scenes.cornell_mesh_scene(api, scenes.refined_bunny_rsm(C4["triangles"]))
+        name = C4["name"]
+    else:
+        note = "demos/resources/stanford_bunny.obj did not travel with this snapshot: bumpy icosphere (1,310,720 triangles) instead"
+        verts, tris, normals = scenes.icosphere(8, radius=0.45, bumps=0.15)
+
+        def extra(a, wd):
+            a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=wd, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+                   material=a.Lambert(a.ConstantSF(0.7)))
+        world = scenes.cornell_box(api, glass=False, extra=extra)
+        name = "cornell_box + 1,310,720-triangle icosphere, 1024x1024 x 64 spp x 64 bins"
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(C4["pixels"], C4["pixels"]), samples=C4["spp"], bins=C4["bins"],
+                                      path_weight=RAY_CFG["important_path_weight"])
+    cam.rng_mode = cabi.RNG_MT19937_64 if args.rng == "mt" else cabi.RNG_PHILOX
+    pipe.accumulate = False
+    world._device = cx.device
+    accel = world.build_accelerator()
+    setup_s = time.time() - t0
+    renderer = FrameRenderer(cam, accel, cx.rank, cx.world_size, tile=16, passes=args.passes)
+    steps = max(1, min(args.steps, 3))
+    total_ms, rays, per_step = timed_frames(cx, renderer, steps, 1, 1000)
+    ms_step = total_ms / steps
+    roof = frame_roofline(cx, renderer, ms_step, per_step, C4["bins"], C4["spp"], 1100,
+                          "trace phase = k_rq_walk (world walk) + k_rq_mesh (Mesh.hit) + k_rq_walk (resume)")
+    out = {"workload": name, "Mrays_per_s": rays / total_ms / 1e3, "frames_per_s": 1e3 / ms_step, "ms_per_step": ms_step,
+           "rays_per_step": rays / steps, "steps": steps, "n_gpus": cx.world_size, "scaling": "strong", "setup_s": setup_s,
+           "waves_per_step": per_step["waves"], "roofline": roof}
+    if note:
+        out["note"] = note
+    accel.close()
+    del renderer
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_c5(cx, args):
+    import ctypes as C
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    torch, dev = cx.torch, cx.device
+    it = iter(dev.rng_uniform(7, 4 * C5["spheres"]))           # the reference generator's stream after seed(7), on the device
+    world = scenes.sweep_spheres(api, lambda: float(next(it)), C5["spheres"])
+    acc = dev.build(world)
+    hits = torch.zeros(1, dtype=torch.int64, device=cx.dev)
+    sum_t = torch.zeros(1, dtype=torch.float64, device=cx.dev)
+    xr = torch.zeros(1, dtype=torch.int64, device=cx.dev)
+    o3, t3 = (C.c_double * 3)(*scenes.SWEEP_ORIGIN), (C.c_double * 3)(*scenes.SWEEP_TARGET)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def sweep(first, n, order, count=0):
+        cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), int(n), int(first), C5["seed"], o3, t3, scenes.SWEEP_HALF,
+                                             int(order), C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()),
+                                             count))
+    sweep(0, 8 * 10**6, 0)                                      # warm-up: chunk buffers, kernel loading
+    out = {"workload": C5["name"], "n_gpus": cx.world_size, "scaling": "strong",
+           "partition": "contiguous ray ranges per rank, no data-path collective" if cx.world_size > 1 else "single GPU", "sweeps": []}
+    for order_name in ("random", "morton"):
+        for n in C5["rays"]:
+            order = 0 if order_name == "random" else max(1, int(math.log(n, 4)))
+            lo = n * cx.rank // cx.world_size
+            hi = n * (cx.rank + 1) // cx.world_size
+            hits.zero_()
+            cx.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sweep(lo, hi - lo, order)
+            e1.record()
+            cx.barrier()
+            ms = cx.reduce(e0.elapsed_time(e1), "max")
+            h = cx.reduce(int(hits.item()), "sum", torch.int64)
+            sweep(lo, min(hi - lo, 10**7), order, 1)            # counting pass on (a prefix of) this rank's rays
+            torch.cuda.synchronize()
+            c = dev.counters()
+            per_ray = trace_algorithmic_bytes(c) / c["rays"]
+            achieved = per_ray * (hi - lo) / (ms * 1e-3) / 1e9   # this rank's rays against the slowest rank's time: per-GPU figure
+            out["sweeps"].append({"order": order_name, "rays": n, "ms": ms, "Mrays_per_s": n / ms / 1e3, "hit_fraction": h / n,
+                                  "roofline": {"bound": "hbm", "kernel": "k_rq_world", "achieved": achieved, "peak": cx.peak, "unit": "GB/s",
+                                               "frac": achieved / cx.peak, "algorithmic_bytes_per_ray": per_ray,
+                                               "per_ray": {k: c[k] / c["rays"] for k in ("branches", "leaves", "items", "prim_tests")}}})
+    acc.close()
+    return out
+
+
+def run_c3(cx, args):
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    torch = cx.torch
+    world = scenes.prism_scene(api)
+    world._device = cx.device
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(C3["pixels"], C3["pixels"]), samples=C3["spp"], bins=C3["bins"],
+                                      spectral_rays=C3["rays"], path_weight=0.75)
+    cam.transform = api.translate(0.3, 0.2, -2.2) * api.rotate(5, -3, 0)
+    cam.rng_mode = cabi.RNG_MT19937_64 if args.rng == "mt" else cabi.RNG_PHILOX
+    pipe.accumulate = False
+    world.build_accelerator()
+    best = None
+    for it in range(2):                                          # first frame warms up; the second is reported
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cam.observe()
+        torch.cuda.synchronize()
+        best = (time.perf_counter() - t0, cam.ray_count)
+    return {"workload": C3["name"] + ", %d samples per pixel and slice" % C3["spp"], "Mrays_per_s": best[1] / best[0] / 1e6,
+            "frames_per_s": 1.0 / best[0], "ms_per_step": 1e3 * best[0], "rays_per_step": best[1], "n_gpus": 1,
+            "path": "mirror PinholeCamera.observe(): %d spectral slices, host frame assembled per slice; wall clock" % C3["rays"]}
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    torch, dist = cx.torch, cx.dist
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    from source_b200.distributed import FrameRenderer
 
     w = dict(WORKLOAD)
     if args.pixels:
         w["pixels"] = args.pixels
     if args.spp:
         w["spp"] = args.spp
-    mode = cabi.RNG_MT19937_64 if args.rng == "mt" else cabi.RNG_PHILOX
-
-    device = Device(local_rank)
+    if w["spp"] % args.passes:
+        raise SystemExit("bench.py: --passes must divide the samples per pixel")
     world = scenes.cornell_box(api)
     cam, pipe = scenes.cornell_camera(api, world, pixels=(w["pixels"], w["pixels"]), samples=w["spp"], bins=w["bins"],
                                       path_weight=RAY_CFG["important_path_weight"])
-    cam.rng_mode = mode
+    cam.rng_mode = cabi.RNG_MT19937_64 if args.rng == "mt" else cabi.RNG_PHILOX
     pipe.accumulate = False
-    world._device = device
+    world._device = cx.device
     accel = world.build_accelerator()
-    if w["spp"] % args.passes:
-        raise SystemExit("bench.py: --passes must divide the samples per pixel")
-    renderer = FrameRenderer(cam, accel, rank, world_size, tile=16, passes=args.passes)
-
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    renderer = FrameRenderer(cam, accel, cx.rank, cx.world_size, tile=16, passes=args.passes)
 
     # ---- device-resident timing -------------------------------------------------------------------
-    for i in range(args.warmup):
-        renderer.step_device(seed=1 + i)
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    clocks = ClockSampler(cx.local_rank)
+    if cx.rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rays_t = torch.zeros(1, dtype=torch.int64, device=dev)
-    trace_ms = trace_launches = launches = waves = 0
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        rays_t += renderer.step_device(seed=100 + i, time_trace=True)
-        rs = device.render_stats()
-        trace_ms += rs["trace_ms"]
-        trace_launches += rs["trace_launches"]
-        launches += rs["launches"]
-        waves += rs["waves"]
-    e1.record()
-    barrier()
-    if rank == 0:
+    total_ms, total_rays, per_step = timed_frames(cx, renderer, args.steps, args.warmup, 1)
+    if cx.rank == 0:
         clocks.stop_flag.set()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    kernel_ms = trace_ms / max(1, trace_launches)
-    if world_size > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
-    total_ms, total_rays = float(ms.item()), int(rays_t.item())
     value = total_rays / total_ms / 1e3   # Mrays/s
+    ms_step = total_ms / args.steps
 
-    # ---- end to end through the public API (host buffers, pinned) ---------------------------------------
+    # ---- end to end with host buffers through the C ABI (every N) ---------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     renderer.step_host(seed=7)   # warm-up (allocates pinned buffers)
-    barrier()
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_rays = 0
     e0.record()
     for i in range(e2e_steps):
         t_rays += renderer.step_host(seed=200 + i)
     e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    r2 = torch.tensor([t_rays], dtype=torch.int64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r2, op=dist.ReduceOp.SUM)
-    e2e_value = int(r2.item()) / float(ms2.item()) / 1e3
+    cx.barrier()
+    ms2 = cx.reduce(e0.elapsed_time(e1), "max")
+    r2 = cx.reduce(t_rays, "sum", torch.int64)
+    e2e_cabi = {"value": r2 / ms2 / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": renderer.h2d_bytes, "d2h_bytes_per_step": renderer.d2h_bytes,
+                "steps": e2e_steps, "path": "FrameRenderer.step_host: rsb_render_passes_dev + frame assembly + pinned device->host copy; CUDA events"}
 
     # ---- roofline: counting pass (untimed) -----------------------------------------------------------
-    counters = renderer.count_pass(seed=100)
-    alg_step = algorithmic_bytes(counters, w["bins"], w["spp"])
-    # the dominant kernel, k_wf_trace, owns the World.hit part of the model: ray in/out + kd nodes + leaf items +
-    # primitive tests of the hit queries (the contains-query and table/frame terms belong to shade/finalize)
-    # rank 0's own share of the frame against rank 0's own kernel time: the roofline is a per-GPU figure
-    alg = trace_algorithmic_bytes(renderer.local_counters)
-    peaks = {}
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    trace_ms_step = trace_ms / args.steps
-    achieved = alg / (trace_ms_step * 1e-3) / 1e9
-    achieved_step = alg_step / (total_ms / args.steps * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "render_traffic.json")
-    if os.path.exists(tp):
-        # ncu --set full of one mid-frame k_wf_trace launch: (dram__bytes_read.sum + dram__bytes_write.sum) / rays traced
-        traffic = json.load(open(tp)).get("dram_bytes_per_ray")
-        if traffic is not None:
-            traffic = traffic * renderer.local_counters["rays"] / max(1.0, trace_launches / args.steps)
+    roof = frame_roofline(cx, renderer, ms_step, per_step, w["bins"], w["spp"], 100, "k_wf_trace")
+    del renderer
+    torch.cuda.empty_cache()
+
+    # ---- the drop-in plugin seam (N = 1) ---------------------------------------------------------------
+    e2e = None
+    if cx.world_size == 1 and not args.no_plugin:
+        try:
+            e2e = plugin_e2e(cx, w, args, e2e_steps)
+        except Exception as exc:   # noqa: BLE001
+            e2e_cabi["plugin_unavailable"] = repr(exc)
+    if e2e is None:
+        e2e = e2e_cabi
+
+    # ---- the other configurations of the metric --------------------------------------------------------
+    configs = {}
+    which = [] if args.configs == "none" else args.configs.split(",")
+    for key, fn in (("C4", run_c4), ("C5", run_c5), ("C3", run_c3)):
+        if key not in which or (key == "C3" and cx.world_size > 1):
+            continue
+        try:
+            configs[key] = fn(cx, args)
+        except Exception as exc:   # noqa: BLE001
+            configs[key] = {"failed": repr(exc)}
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1 only): the compiled reference in a clean subprocess --------------------
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu:
+    if cx.rank == 0 and cx.world_size == 1 and not args.no_cpu:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                                 capture_output=True, text=True, timeout=900).stdout.strip().splitlines()
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                  "--configs", args.configs],
+                                 capture_output=True, text=True, timeout=1200).stdout.strip().splitlines()
             ref = json.loads(out[-1])
             cpu = ref.get("cpu_baseline", {"unavailable": ref.get("unavailable")})
+            for key, val in (cpu.pop("configs", None) or {}).items():
+                if key in configs:
+                    configs[key]["cpu_reference"] = val
         except Exception as exc:   # noqa: BLE001
             cpu = {"unavailable": repr(exc)}
 
-    if rank == 0:
+    if cx.rank == 0:
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": cx.world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"] if not (args.pixels or args.spp) else "cornell_box %dx%d x %d spp x %d bins" % (w["pixels"], w["pixels"], w["spp"], w["bins"]),
                        "passes": "%d spp accumulated as %d observe() passes of %d spp (streams keyed on (pass, pixel)), merged with "
                                  "StatsArray3D.combine_samples" % (w["spp"], args.passes, w["spp"] // args.passes)
                                  if args.passes > 1 else "one observe() pass of %d spp" % w["spp"],
                        "rng": "mt19937_64 per (pass, pixel)" if args.rng == "mt" else "philox4x32-10 per (pass, pixel, sample)",
-                       "partition": "16x16 px tiles interleaved over ranks, one NCCL reduce(sum) of the frame" if world_size > 1 else "single GPU",
+                       "partition": "16x16 px tiles interleaved over ranks; owned tiles gathered on rank 0 over NCCL" if cx.world_size > 1 else "single GPU",
                        "l2": "frame buffers 1.07 GB per step exceed the 126 MB L2; scene (4.5 KB) is shared-memory resident by design"},
-            "frames_per_s": 1e3 * args.steps / total_ms, "rays_per_step": total_rays / args.steps,
-            "gpu_launches": launches, "waves_per_step": waves / args.steps,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": renderer.h2d_bytes, "d2h_bytes_per_step": renderer.d2h_bytes,
-                    "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_wf_trace", "kernel_ms": kernel_ms,
-                         "launches_per_step": trace_launches / args.steps, "kernel_ms_per_step": trace_ms_step,
-                         "kernel_share_of_step": trace_ms_step / (total_ms / args.steps),
-                         "algorithmic_bytes_per_launch": alg / max(1.0, trace_launches / args.steps),
-                         "algorithmic_bytes_per_step": alg, "whole_step": {"algorithmic_bytes": alg_step, "achieved": achieved_step,
-                                                                           "frac": achieved_step / peak},
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650", "counters": counters},
-            "cpu_baseline": cpu,
+            "frames_per_s": 1e3 / ms_step, "rays_per_step": total_rays / args.steps,
+            "gpu_launches": int(per_step["launches"] * args.steps), "waves_per_step": per_step["waves"],
+            "e2e": e2e, "e2e_cabi": e2e_cabi, "roofline": roof, "configs": configs, "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line))
-    if world_size > 1:
+    if cx.world_size > 1:
         dist.destroy_process_group()
     return 0
 
@@ -324,7 +593,9 @@ def main():
     ap.add_argument("--passes", type=int, default=DEFAULT_PASSES,
                     help="render the frame's samples as this many accumulated observe() passes, concurrently")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--configs", default="C4,C5,C3", help="comma list of the extra configurations to measure, or 'none'")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

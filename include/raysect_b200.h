@@ -276,6 +276,24 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
                           double* mean_dev, double* variance_dev, uint64_t* ray_count_dev, int32_t count);
 
 /*
+ * RenderEngine.run + Pipeline.update for a whole slice, the form the drop-in engine uses (workflow.py:78-91,
+ * observer.pyx:299-305, power.pyx:424-437): rsb_render_slice renders the listed pixels like rsb_render_passes but
+ * KEEPS the result on the device; rsb_slice_update_frame then merges it into a pipeline's HOST frame arrays
+ * ((nx, ny, frame_bins) mean / variance f64, samples i32 -- StatsArray3D's own buffers) at bin offset slice_offset with
+ * StatsArray3D.combine_samples (samples = n_passes * pixel_samples), for the listed pixels only: the slice's bin range of
+ * the frame goes host -> device (skipped when frame_is_empty: a freshly initialised frame), is combined on the device
+ * and comes back.  Several pipelines can be updated from one rendered slice.  rsb_slice_read copies the raw slice
+ * (mean, variance; (nx, ny, slice_bins); unlisted pixels zero) to the host.  All buffers are owned by the context and
+ * reused from call to call.
+ */
+int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+                     const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride,
+                     int64_t n_pixels, const int32_t* pixels, uint64_t* ray_count);
+int rsb_slice_read(uint64_t ctx, double* mean, double* variance);
+int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offset, int32_t frame_is_empty,
+                           double* frame_mean, double* frame_variance, int32_t* frame_samples);
+
+/*
  * SpectralPowerPipeline2D.update -> StatsArray3D.combine_samples (power.pyx:424-437, statsarray.pyx:780-857):
  * merges a freshly rendered slice (mean, variance, samples_per_pixel; [n_pixels_total][slice_bins]) into an
  * accumulating frame (frame_* [n_pixels_total][frame_bins]) at bin offset slice_offset, for the listed pixels.
@@ -290,14 +308,17 @@ typedef struct RsbRenderStats {
     int64_t slots;            /* pixel streams in flight (wavefront width) */
     int64_t waves;            /* trace -> shade -> finalize -> regen rounds */
     int64_t launches;         /* kernels launched */
-    int64_t trace_launches;   /* launches of the dominant kernel (k_wf_trace) */
-    double trace_ms;          /* summed device time of k_wf_trace (CUDA events on the launch stream); 0 unless
+    int64_t trace_launches;   /* trace phases run (k_wf_trace, or walk / Mesh.hit / resume kernels for scenes with meshes) */
+    double trace_ms;          /* summed device time of the trace phase (CUDA events on the launch stream); 0 unless
                                  the call was made with RSB_RENDER_TIME_TRACE */
+    double shade_ms;          /* the same for k_wf_shade, k_wf_finalize and k_wf_regen */
+    double finalize_ms;
+    double regen_ms;
 } RsbRenderStats;
 int rsb_render_stats(uint64_t ctx, RsbRenderStats* out);
 
 #define RSB_RENDER_COUNT 1        /* `count` argument of rsb_render_dev: collect traversal counters */
-#define RSB_RENDER_TIME_TRACE 2   /* bracket every k_wf_trace launch with CUDA events */
+#define RSB_RENDER_TIME_TRACE 2   /* bracket the four phases of every wave with CUDA events */
 
 /* counters of the last *_dev / host call made with count != 0 (host calls always count) */
 int rsb_counters(uint64_t ctx, RsbCounters* out);

@@ -140,7 +140,7 @@ class RsbCounters(C.Structure):
 
 class RsbRenderStats(C.Structure):
     _fields_ = [("slots", C.c_int64), ("waves", C.c_int64), ("launches", C.c_int64), ("trace_launches", C.c_int64),
-                ("trace_ms", C.c_double)]
+                ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("finalize_ms", C.c_double), ("regen_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -174,6 +174,10 @@ SIGNATURES = {
     "rsb_rng_uniform": (C.c_int, [_U64, _U64, C.c_int64, c_double_p]),
     "rsb_render": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
                              C.POINTER(RsbRngDesc), C.c_int64, c_int32_p, c_double_p, c_double_p, c_uint64_p]),
+    "rsb_render_slice": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
+                                   C.POINTER(RsbRngDesc), C.c_int32, _U64, C.c_int64, c_int32_p, c_uint64_p]),
+    "rsb_slice_read": (C.c_int, [_U64, c_double_p, c_double_p]),
+    "rsb_slice_update_frame": (C.c_int, [_U64, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "rsb_render_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),
                                  C.POINTER(RsbSpectral), C.POINTER(RsbRngDesc), C.c_int64, _VP, _VP, _VP, _VP,
                                  C.c_int32]),

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 #include <thread>
 
 namespace rsb {
@@ -61,6 +62,7 @@ int64_t kd_parse_stream(const uint8_t* data, int64_t size, HostKdTree* out, std:
     for (int i = 0; i < 6; ++i) out->bounds[i] = r.get<double>();
     int32_t n = r.get<int32_t>();
     if (!r.ok || n <= 0) { *err = "kd-tree stream: truncated header or no nodes"; return -1; }
+    if ((int64_t)n > r.left / 8) { *err = "kd-tree stream: node count exceeds the stream"; return -1; }   // a node is >= 8 bytes
     out->nodes.resize(n);
     out->items.clear();
     for (int32_t id = 0; id < n; ++id) {
@@ -69,7 +71,7 @@ int64_t kd_parse_stream(const uint8_t* data, int64_t size, HostKdTree* out, std:
         memset(&node, 0, sizeof(node));
         if (type == -1) {
             int32_t count = r.get<int32_t>();
-            if (!r.ok || count < 0) { *err = "kd-tree stream: bad leaf"; return -1; }
+            if (!r.ok || count < 0 || (int64_t)count > r.left / 4) { *err = "kd-tree stream: bad leaf"; return -1; }
             node.axis = -1;
             node.upper = -1;
             node.leaf.item_offset = (int32_t)out->items.size();
@@ -252,9 +254,20 @@ struct Builder {
             Sub lower_sub, upper_sub;
             Builder lower_builder{boxes, max_depth, min_items, hit_cost, empty_bonus, &lower_sub, {}};
             Builder upper_builder{boxes, max_depth, min_items, hit_cost, empty_bonus, &upper_sub, {}};
-            std::thread worker([&]() { lower_builder.build(lower_items, lb, depth + 1, fork - 1); });
-            upper_builder.build(upper_items, ub, depth + 1, fork - 1);
+            // the worker is joined on every path out of this scope, and an exception on either side is re-thrown in
+            // the forking thread (a joinable std::thread destroyed during unwinding would call std::terminate)
+            std::exception_ptr worker_error;
+            std::thread worker([&]() {
+                try { lower_builder.build(lower_items, lb, depth + 1, fork - 1); } catch (...) { worker_error = std::current_exception(); }
+            });
+            try {
+                upper_builder.build(upper_items, ub, depth + 1, fork - 1);
+            } catch (...) {
+                worker.join();
+                throw;
+            }
             worker.join();
+            if (worker_error) std::rethrow_exception(worker_error);
             splice(lower_sub);
             upper_id = splice(upper_sub);
         } else {

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,17 @@ struct Context {
     unsigned long long* d_scalars = nullptr;   // [0] work counter, [1] ray count, [2] overflow flag (as int)
     unsigned char* d_slots = nullptr;   // wavefront slot state (rsb_kernels.cuh: WfSlots)
     size_t slot_bytes = 0;
+    // rsb_render_slice: the last rendered slice stays on the device (mean | variance, [n_pix_frame][slice_bins]) with its
+    // task list, until rsb_slice_update_frame / rsb_slice_read consumed it; grow-only buffers
+    double* d_slice = nullptr;
+    size_t slice_cap = 0;               // doubles
+    int32_t* d_slice_pix = nullptr;
+    size_t slice_pix_cap = 0;           // int32 pairs
+    double* d_frame = nullptr;          // host frames pass through here: mean | variance, [n_pix_frame][frame_bins]
+    int32_t* d_frame_samples = nullptr;
+    size_t frame_cap = 0;               // elements
+    unsigned long long* d_slice_rays = nullptr;
+    struct { int32_t nx = 0, ny = 0, bins = 0, samples = 0; int64_t n_pixels = 0; bool listed = false, valid = false; } slice;
     unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
     size_t rq_bytes = 0;
     long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
@@ -211,16 +223,21 @@ int rsb_kdtree_build(const double* boxes, int64_t n_items, int32_t max_depth, in
     if ((!boxes && n_items > 0) || n_items < 0 || !stream || !stream_bytes) return fail(RSB_ERR_ARG, "rsb_kdtree_build: bad arguments");
     if (empty_bonus < 0.0 || empty_bonus > 1.0)
         return fail(RSB_ERR_ARG, "The empty_bonus cost modifier must lie in the range [0.0, 1.0].");
-    HostKdTree t;
-    kd_build(boxes, n_items, max_depth, min_items, hit_cost, empty_bonus, &t);
-    std::vector<uint8_t> bytes;
-    kd_write_stream(t, &bytes);
-    uint8_t* out = (uint8_t*)malloc(bytes.size());
-    if (!out) return fail(RSB_ERR_ARG, "rsb_kdtree_build: out of memory");
-    memcpy(out, bytes.data(), bytes.size());
-    *stream = out;
-    *stream_bytes = (int64_t)bytes.size();
-    return RSB_OK;
+    // nothing may unwind through the C ABI: allocation or thread-creation failures become an error code
+    try {
+        HostKdTree t;
+        kd_build(boxes, n_items, max_depth, min_items, hit_cost, empty_bonus, &t);
+        std::vector<uint8_t> bytes;
+        kd_write_stream(t, &bytes);
+        uint8_t* out = (uint8_t*)malloc(bytes.size());
+        if (!out) return fail(RSB_ERR_ARG, "rsb_kdtree_build: out of memory");
+        memcpy(out, bytes.data(), bytes.size());
+        *stream = out;
+        *stream_bytes = (int64_t)bytes.size();
+        return RSB_OK;
+    } catch (const std::exception& e) {
+        return fail(RSB_ERR_ARG, std::string("rsb_kdtree_build: ") + e.what());
+    }
 }
 
 int rsb_mesh_face_normals(const float* vertices, int32_t n_vertices, const int32_t* triangles, int32_t n_triangles,
@@ -315,6 +332,11 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_slots);
     cudaFree(c->d_pass);
     cudaFree(c->d_rq);
+    cudaFree(c->d_slice);
+    cudaFree(c->d_slice_pix);
+    cudaFree(c->d_frame);
+    cudaFree(c->d_frame_samples);
+    cudaFree(c->d_slice_rays);
     cudaFreeHost(c->h_idle);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_mats);
@@ -344,7 +366,12 @@ int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
     RSB_CUDA(cudaSetDevice(c->device));
     PackedScene ps;
     std::string err;
-    int prc = pack_scene(d, &ps, &err);
+    int prc;
+    try {
+        prc = pack_scene(d, &ps, &err);
+    } catch (const std::exception& e) {
+        return fail(RSB_ERR_ARG, std::string("rsb_scene_create: ") + e.what());
+    }
     if (prc) return fail(prc, err);
 
     DeviceScene* ds = new DeviceScene();
@@ -824,7 +851,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     const int kBatch = 32;
     rs.launches += 1;
     if (time_trace) {
-        while (c->event_pool.size() < 2 * kBatch) {
+        while (c->event_pool.size() < 5 * kBatch) {
             cudaEvent_t e;
             RSB_CUDA(cudaEventCreate(&e));
             c->event_pool.push_back(e);
@@ -834,12 +861,16 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     // arguments only differ in the wave parity) and replayed until every slot is idle: ~115k dependent
     // launches per 1024^2 x 256 spp frame otherwise cost ~5 us of launch gap each.
     auto enqueue_batch = [&](cudaStream_t s, bool external_events) -> int {
+        // (time_trace) five events per wave bracket its four phases: trace | shade | finalize | regen
+        auto mark = [&](int b, int k) -> int {
+            if (!time_trace) return RSB_OK;
+            if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[5 * b + k], s, cudaEventRecordExternal));
+            else RSB_CUDA(cudaEventRecord(c->event_pool[5 * b + k], s));
+            return RSB_OK;
+        };
         for (int b = 0; b < kBatch; ++b) {
             a.wave = b;
-            if (time_trace) {
-                if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b], s, cudaEventRecordExternal));
-                else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b], s));
-            }
+            if (mark(b, 0)) return RSB_ERR_CUDA;
             if constexpr (PIPELINE) {
                 RqWfClient cl;
                 cl.a = a;
@@ -855,13 +886,13 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
             } else {
                 k_wf_trace<RNGMODE, COUNT, FEAT><<<grid, threads, smem_scene, s>>>(a);
             }
-            if (time_trace) {
-                if (external_events) RSB_CUDA(cudaEventRecordWithFlags(c->event_pool[2 * b + 1], s, cudaEventRecordExternal));
-                else RSB_CUDA(cudaEventRecord(c->event_pool[2 * b + 1], s));
-            }
+            if (mark(b, 1)) return RSB_ERR_CUDA;
             k_wf_shade<RNGMODE, COUNT, FEAT><<<shade_grid, threads, smem_shade, s>>>(a);
+            if (mark(b, 2)) return RSB_ERR_CUDA;
             k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, s>>>(a);
+            if (mark(b, 3)) return RSB_ERR_CUDA;
             k_wf_regen<RNGMODE, COUNT><<<regen_grid, threads, 0, s>>>(a);
+            if (mark(b, 4)) return RSB_ERR_CUDA;
         }
         return RSB_OK;
     };
@@ -896,9 +927,12 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
         rs.trace_launches += kBatch;
         if (time_trace) {
             for (int b = 0; b < kBatch; ++b) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, c->event_pool[2 * b], c->event_pool[2 * b + 1]);
-                rs.trace_ms += ms;
+                float ms[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], c->event_pool[5 * b + k], c->event_pool[5 * b + k + 1]);
+                rs.trace_ms += ms[0];
+                rs.shade_ms += ms[1];
+                rs.finalize_ms += ms[2];
+                rs.regen_ms += ms[3];
             }
         }
         if (*h_idle >= (unsigned int)a.n_slots) break;
@@ -1076,6 +1110,18 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     RqBuf rq;
     size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe, ds->has_mesh, &rq);
     if (c->slot_bytes < need) {
+        // the per-slot path log grows with ray_max_depth (48 KB per slot at Raysect's default 500): narrow the wavefront
+        // and the seeded chunk until the pool fits what the device has left (another context, another process, ...)
+        size_t free_b = 0, total_b = 0;
+        RSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        free_b += c->slot_bytes;
+        while (need > free_b - free_b / 8 && (P > (long long)c->sm_count * 128 || chunk_cap > P)) {
+            if (chunk_cap > P) chunk_cap = std::max<long long>(P, chunk_cap / 2);
+            else { P = std::max<long long>((long long)c->sm_count * 128, P * 3 / 4); chunk_cap = std::min(chunk_cap, P); }
+            need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe, ds->has_mesh, &rq);
+        }
+    }
+    if (c->slot_bytes < need) {
         cudaFree(c->d_slots);
         c->d_slots = nullptr; c->slot_bytes = 0;
         RSB_CUDA(cudaMalloc(&c->d_slots, need));
@@ -1139,44 +1185,134 @@ int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbR
     return rsb_render_passes(ctx, scene, camera, config, spectral, rng, 1, 0, n_pixels, pixels, mean, variance, ray_count);
 }
 
+int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                     const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels,
+                     uint64_t* ray_count) {
+    Context* c = as_ctx(ctx);
+    if (!c || !as_scene(scene) || !camera || !config || !ray_count) return fail(RSB_ERR_ARG, "rsb_render_slice: null argument");
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->slice.valid = false;
+    const size_t frame = (size_t)camera->nx * camera->ny * config->bins;
+    if (!pixels) n_pixels = (int64_t)camera->nx * camera->ny;
+    if (n_pixels < 0) return fail(RSB_ERR_ARG, "rsb_render_slice: negative pixel count");
+    if (c->slice_cap < 2 * frame) {
+        cudaFree(c->d_slice);
+        c->d_slice = nullptr; c->slice_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_slice, 2 * frame * sizeof(double)));
+        c->slice_cap = 2 * frame;
+    }
+    if (!c->d_slice_rays) RSB_CUDA(cudaMalloc(&c->d_slice_rays, 8));
+    if (pixels && c->slice_pix_cap < (size_t)n_pixels) {
+        cudaFree(c->d_slice_pix);
+        c->d_slice_pix = nullptr; c->slice_pix_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_slice_pix, std::max<size_t>(1, (size_t)n_pixels) * 8));
+        c->slice_pix_cap = (size_t)n_pixels;
+    }
+    RSB_CUDA(cudaMemsetAsync(c->d_slice_rays, 0, 8, st));
+    // unlisted pixels of the slice read as zero
+    RSB_CUDA(cudaMemsetAsync(c->d_slice, 0, 2 * frame * sizeof(double), st));
+    if (pixels && n_pixels > 0) RSB_CUDA(cudaMemcpyAsync(c->d_slice_pix, pixels, (size_t)n_pixels * 8, cudaMemcpyHostToDevice, st));
+    RSB_CUDA(cudaEventRecord(c->ev0, st));
+    if (n_pixels > 0) {
+        int rc = rsb_render_passes_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, seed_stride, n_pixels,
+                                       pixels ? c->d_slice_pix : nullptr, c->d_slice, c->d_slice + frame, (uint64_t*)c->d_slice_rays, 1);
+        if (rc) return rc;
+    }
+    RSB_CUDA(cudaEventRecord(c->ev1, st));
+    unsigned long long rays = 0;
+    RSB_CUDA(cudaMemcpyAsync(&rays, c->d_slice_rays, 8, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    *ray_count += rays;
+    c->slice.nx = camera->nx; c->slice.ny = camera->ny; c->slice.bins = config->bins;
+    c->slice.samples = camera->pixel_samples * n_passes;
+    c->slice.n_pixels = n_pixels;
+    c->slice.listed = pixels != nullptr;
+    c->slice.valid = true;
+    return RSB_OK;
+}
+
+int rsb_slice_read(uint64_t ctx, double* mean, double* variance) {
+    Context* c = as_ctx(ctx);
+    if (!c || !mean || !variance) return fail(RSB_ERR_ARG, "rsb_slice_read: null argument");
+    if (!c->slice.valid) return fail(RSB_ERR_ARG, "rsb_slice_read: no rendered slice is held (call rsb_render_slice first)");
+    RSB_CUDA(cudaSetDevice(c->device));
+    const size_t frame = (size_t)c->slice.nx * c->slice.ny * c->slice.bins;
+    RSB_CUDA(cudaMemcpyAsync(mean, c->d_slice, frame * 8, cudaMemcpyDeviceToHost, c->stream));
+    RSB_CUDA(cudaMemcpyAsync(variance, c->d_slice + frame, frame * 8, cudaMemcpyDeviceToHost, c->stream));
+    RSB_CUDA(cudaStreamSynchronize(c->stream));
+    return RSB_OK;
+}
+
+int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offset, int32_t frame_is_empty, double* frame_mean,
+                           double* frame_variance, int32_t* frame_samples) {
+    Context* c = as_ctx(ctx);
+    if (!c || !frame_mean || !frame_variance || !frame_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_frame: null argument");
+    if (!c->slice.valid) return fail(RSB_ERR_ARG, "rsb_slice_update_frame: no rendered slice is held (call rsb_render_slice first)");
+    const int nx = c->slice.nx, ny = c->slice.ny, sb = c->slice.bins;
+    if (slice_offset < 0 || slice_offset + sb > frame_bins)
+        return fail(RSB_ERR_ARG, "The slice offset plus the bin count extends beyond the full bin count.");
+    if (c->slice.n_pixels == 0) return RSB_OK;
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t npix = (size_t)nx * ny, elems = npix * (size_t)frame_bins;
+    if (c->frame_cap < elems) {
+        cudaFree(c->d_frame); cudaFree(c->d_frame_samples);
+        c->d_frame = nullptr; c->d_frame_samples = nullptr; c->frame_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_frame, 2 * elems * sizeof(double)));
+        RSB_CUDA(cudaMalloc(&c->d_frame_samples, elems * sizeof(int32_t)));
+        c->frame_cap = elems;
+    }
+    double* d_fm = c->d_frame;
+    double* d_fv = c->d_frame + elems;
+    // only the slice's bin range of the frame travels: rows of frame_bins elements, slice_bins wide at slice_offset
+    const size_t pitch8 = (size_t)frame_bins * 8, width8 = (size_t)sb * 8, off8 = (size_t)slice_offset * 8;
+    const size_t pitch4 = (size_t)frame_bins * 4, width4 = (size_t)sb * 4, off4 = (size_t)slice_offset * 4;
+    if (frame_is_empty) {
+        RSB_CUDA(cudaMemsetAsync(d_fm, 0, 2 * elems * sizeof(double), st));
+        RSB_CUDA(cudaMemsetAsync(c->d_frame_samples, 0, elems * sizeof(int32_t), st));
+    } else {
+        RSB_CUDA(cudaMemcpy2DAsync((char*)d_fm + off8, pitch8, (char*)frame_mean + off8, pitch8, width8, npix, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpy2DAsync((char*)d_fv + off8, pitch8, (char*)frame_variance + off8, pitch8, width8, npix, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpy2DAsync((char*)c->d_frame_samples + off4, pitch4, (char*)frame_samples + off4, pitch4, width4, npix,
+                                   cudaMemcpyHostToDevice, st));
+    }
+    int rc = rsb_frame_combine_dev(ctx, st, (int64_t)npix, frame_bins, slice_offset, sb, c->slice.n_pixels,
+                                   c->slice.listed ? c->d_slice_pix : nullptr, ny, c->d_slice, c->d_slice + npix * sb, c->slice.samples, d_fm,
+                                   d_fv, c->d_frame_samples);
+    if (rc) return rc;
+    RSB_CUDA(cudaMemcpy2DAsync((char*)frame_mean + off8, pitch8, (char*)d_fm + off8, pitch8, width8, npix, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpy2DAsync((char*)frame_variance + off8, pitch8, (char*)d_fv + off8, pitch8, width8, npix, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpy2DAsync((char*)frame_samples + off4, pitch4, (char*)c->d_frame_samples + off4, pitch4, width4, npix,
+                               cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaStreamSynchronize(st));
+    return RSB_OK;
+}
+
 int rsb_render_passes(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                       const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels,
                       double* mean, double* variance, uint64_t* ray_count) {
     Context* c = as_ctx(ctx);
     if (!c || !as_scene(scene) || !camera || !config || !mean || !variance || !ray_count) return fail(RSB_ERR_ARG, "rsb_render: null argument");
-    RSB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    size_t frame = (size_t)camera->nx * camera->ny * config->bins;
     if (!pixels) n_pixels = (int64_t)camera->nx * camera->ny;
     if (n_pixels <= 0) return RSB_OK;
-    double *d_mean = nullptr, *d_var = nullptr;
-    int32_t* d_pix = nullptr;
-    unsigned long long* d_rc = nullptr;
-    auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_pix); cudaFree(d_rc); };
-    RSB_TRY(cudaMalloc(&d_mean, frame * 8));
-    RSB_TRY(cudaMalloc(&d_var, frame * 8));
-    RSB_TRY(cudaMalloc(&d_rc, 8));
-    RSB_TRY(cudaMemsetAsync(d_rc, 0, 8, st));
-    if (pixels) {
-        // unlisted pixels must come back untouched: start from the caller's arrays
-        RSB_TRY(cudaMemcpyAsync(d_mean, mean, frame * 8, cudaMemcpyHostToDevice, st));
-        RSB_TRY(cudaMemcpyAsync(d_var, variance, frame * 8, cudaMemcpyHostToDevice, st));
-        RSB_TRY(cudaMalloc(&d_pix, n_pixels * 8));
-        RSB_TRY(cudaMemcpyAsync(d_pix, pixels, n_pixels * 8, cudaMemcpyHostToDevice, st));
+    int rc = rsb_render_slice(ctx, scene, camera, config, spectral, rng, n_passes, seed_stride, n_pixels, pixels, ray_count);
+    if (rc) return rc;
+    const size_t frame = (size_t)camera->nx * camera->ny * config->bins;
+    if (!pixels) return rsb_slice_read(ctx, mean, variance);
+    // unlisted pixels must come back untouched: scatter the listed rows into the caller's arrays
+    std::vector<double> m(frame), v(frame);
+    rc = rsb_slice_read(ctx, m.data(), v.data());
+    if (rc) return rc;
+    const size_t bins = (size_t)config->bins;
+    for (int64_t k = 0; k < n_pixels; ++k) {
+        const int x = pixels[2 * k], y = pixels[2 * k + 1];
+        if (x < 0 || y < 0 || x >= camera->nx || y >= camera->ny) return fail(RSB_ERR_ARG, "rsb_render: pixel outside the frame");
+        const size_t row = ((size_t)x * camera->ny + y) * bins;
+        memcpy(mean + row, m.data() + row, bins * 8);
+        memcpy(variance + row, v.data() + row, bins * 8);
     }
-    RSB_TRY(cudaEventRecord(c->ev0, st));
-    int rc = rsb_render_passes_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, seed_stride, n_pixels, d_pix, d_mean,
-                                   d_var, (uint64_t*)d_rc, 1);
-    if (rc) { cleanup(); return rc; }
-    RSB_TRY(cudaEventRecord(c->ev1, st));
-    unsigned long long rays = 0;
-    RSB_TRY(cudaMemcpyAsync(mean, d_mean, frame * 8, cudaMemcpyDeviceToHost, st));
-    RSB_TRY(cudaMemcpyAsync(variance, d_var, frame * 8, cudaMemcpyDeviceToHost, st));
-    RSB_TRY(cudaMemcpyAsync(&rays, d_rc, 8, cudaMemcpyDeviceToHost, st));
-    RSB_TRY(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
-    *ray_count += rays;
-    cleanup();
     return RSB_OK;
 }
 

@@ -1,6 +1,5 @@
 """One process per GPU: image tiles are partitioned across ranks, each rank renders every sample of its
-own tiles into an otherwise-zero frame, and ONE NCCL reduce(sum) over NVLink assembles the spectral frame
-on rank 0 (exact: non-owned entries are zero, so the sum only ever adds zeros).
+own tiles, and ONE NCCL gather over NVLink assembles the spectral frame on rank 0 (exact: rows are copied).
 
 The reference's only parallelism is the same pixel-task data parallelism over forked processes with
 pickled (mean, variance) tuples (raysect/core/workflow.py:123-327); pixel random streams are keyed on the
@@ -27,18 +26,47 @@ def tile_pixels(nx, ny, tile, rank, world_size):
     return np.ascontiguousarray(np.stack([x[keep], y[keep]], axis=1).astype(np.int32))
 
 
-def reduce_frame(stats, out, rank, world_size):
-    """The single collective of the path: reduce(sum) of the stacked (mean, variance) frame to rank 0.
-    Every rank's ``stats`` is zero outside its own tiles, so the sum only ever adds zeros and rank 0 ends up
-    with bit-identical values to what the owning ranks wrote.  The collective runs on the scratch copy ``out``
-    (a reduce may use non-root buffers as workspace), so every rank's ``stats`` keeps exact zeros in its
-    foreign tiles for the next frame."""
-    if world_size == 1:
+class TileGather:
+    """The single collective of the path.  Every rank packs the frame rows of ITS tiles (1/N of the frame) and rank 0
+    gathers them over NCCL / NVLink and drops them into place in its own frame -- copies only, so the assembled frame
+    holds bit for bit what the owning ranks wrote.  (Round 1 summed whole frames with reduce(sum): exact as well,
+    because foreign entries were zero, but every rank shipped the full 2 x 1.07 GB frame, 7/8 of it zeros, after a
+    2.15 GB scratch copy.)  ``stats`` is (2, nx, ny, bins): mean, variance."""
+
+    def __init__(self, nx, ny, bins, tile, rank, world_size, device):
+        import torch
+        self.torch = torch
+        self.rank, self.world_size = rank, world_size
+        self.shape = (nx, ny, bins)
+        self.index, self.counts = [], []
+        for r in range(world_size):
+            px = tile_pixels(nx, ny, tile, r, world_size)
+            self.index.append(torch.from_numpy(px[:, 0].astype(np.int64) * ny + px[:, 1].astype(np.int64)).to(device))
+            self.counts.append(len(px))
+        n_max = max(self.counts)
+        self.send = torch.zeros((2, n_max, bins), dtype=torch.float64, device=device)
+        self.recv = [torch.zeros_like(self.send) for _ in range(world_size)] if rank == 0 else None
+        self.bytes_sent = 0 if rank == 0 else 2 * self.counts[rank] * bins * 8
+
+    def __call__(self, stats):
+        """-> the assembled frame on rank 0 (assembled in place in rank 0's ``stats``: a render only ever touches the
+        rows of its own pixels, so foreign rows left over from the previous frame are harmless), None elsewhere"""
+        if self.world_size == 1:
+            return stats
+        import torch.distributed as dist
+        torch = self.torch
+        nx, ny, bins = self.shape
+        flat = stats.view(2, nx * ny, bins)
+        n_own = self.counts[self.rank]
+        if self.rank != 0:
+            torch.index_select(flat, 1, self.index[self.rank], out=self.send[:, :n_own]) if n_own == self.send.shape[1] \
+                else self.send[:, :n_own].copy_(flat.index_select(1, self.index[self.rank]))
+        dist.gather(self.send, self.recv, dst=0)
+        if self.rank != 0:
+            return None
+        for r in range(1, self.world_size):
+            flat.index_copy_(1, self.index[r], self.recv[r][:, :self.counts[r]])
         return stats
-    import torch.distributed as dist
-    out.copy_(stats)
-    dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
-    return out if rank == 0 else None
 
 
 class FrameRenderer:
@@ -72,11 +100,10 @@ class FrameRenderer:
             self.dev_pixels = self.host_pixels.to(self.dev)
         # [0] mean, [1] variance: one tensor so that the frame crosses NVLink in a single reduce
         self.stats = torch.zeros((2, nx, ny, self.bins), dtype=torch.float64, device=self.dev)
-        self.out = torch.zeros_like(self.stats) if world_size > 1 else None
+        self.gather = backend_reduce or TileGather(nx, ny, self.bins, tile, rank, world_size, self.dev)
         self.host_stats = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self._reduce = backend_reduce
 
     def _render(self, seed, pixels, count=False, time_trace=False):
         return self.accel.render_device(self.cam, self.cfg, self.spectral, self.camera.rng_mode, seed, pixels,
@@ -84,8 +111,8 @@ class FrameRenderer:
                                         passes=self.passes, seed_stride=self.nx * self.ny)[2]
 
     def _assemble(self):
-        """single reduce(sum) of the (mean, variance) frame to rank 0"""
-        return reduce_frame(self.stats, self.out, self.rank, self.world_size)
+        """the single collective: owned tiles gathered on rank 0"""
+        return self.gather(self.stats)
 
     def step_device(self, seed, time_trace=False):
         """One frame with everything resident in HBM.  Returns this rank's ray counter (device tensor).
@@ -108,24 +135,30 @@ class FrameRenderer:
         frame = self._assemble()
         d2h = 8
         if self.rank == 0:
+            # two pinned staging buffers: the device->host copy always lands in the one the pipeline's frame does NOT
+            # view, so an accumulating pipeline combines (frame so far, new pass) and never (new, new)
             if self.host_stats is None:
-                self.host_stats = torch.zeros(self.stats.shape, dtype=torch.float64).pin_memory()
-            self.host_stats.copy_(frame, non_blocking=True)
-            d2h += self.host_stats.numel() * 8
+                self.host_stats = [torch.zeros(self.stats.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+                self._frame_buf = None
+            k = 0 if self._frame_buf != 0 else 1
+            self.host_stats[k].copy_(frame, non_blocking=True)
+            d2h += self.host_stats[k].numel() * 8
         n = int(rays.item())    # device->host read of the step's ray counter; synchronises the stream
         if self.rank == 0:
             torch.cuda.current_stream(self.dev).synchronize()
             pipe = self.camera.pipelines[0]
-            hs = self.host_stats.numpy()
+            hs = self.host_stats[k].numpy()
             if pipe.frame is None or pipe.frame.shape != (self.nx, self.ny, self.bins) or not pipe.accumulate:
                 from .observer import StatsArray3D
                 f = StatsArray3D.__new__(StatsArray3D)
                 f.nx, f.ny, f.nz = self.nx, self.ny, self.bins
                 f.mean, f.variance = hs[0], hs[1]
                 f.samples = np.full((self.nx, self.ny, self.bins), self.camera.pixel_samples, dtype=np.int32) \
-                    if getattr(self, "_samples", None) is None else self._samples
-                self._samples = f.samples
+                    if getattr(self, "_samples", None) is None or pipe.accumulate else self._samples
+                if not pipe.accumulate:
+                    self._samples = f.samples
                 pipe.frame = f
+                self._frame_buf = k
             else:
                 pipe._samples = self.camera.pixel_samples
                 pipe._spectral_slices = self.camera._slice_spectrum()

@@ -197,6 +197,40 @@ class Accelerator:
         return mean, variance, rays.value
 
 
+    # ---- RenderEngine.run + Pipeline.update for a whole slice (the drop-in engine's form) --------------------------
+    def render_slice(self, camera, config, spectral, rng_mode, seed, pixels=None, passes=1, seed_stride=0):
+        """Renders like ``render`` but keeps the slice on the device (rsb_render_slice); returns the ray count.  Follow
+        with ``update_frame`` (once per pipeline) and / or ``read_slice``."""
+        rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
+        rays = C.c_uint64(0)
+        pix, n = None, camera.nx * camera.ny
+        if pixels is not None:
+            pix = cabi.as_i32(pixels).reshape(-1, 2)
+            n = pix.shape[0]
+        cabi.check(self.lib.rsb_render_slice(self.device.ctx, self.scene, C.byref(camera), C.byref(config), C.byref(spectral),
+                                             C.byref(rng), int(passes), int(seed_stride), n, cabi.ptr(pix, C.c_int32), C.byref(rays)))
+        self._slice_shape = (camera.nx, camera.ny, config.bins)
+        return rays.value
+
+    def read_slice(self):
+        """(mean, variance) of the slice rendered last, (nx, ny, slice_bins); unlisted pixels are zero"""
+        mean = np.zeros(self._slice_shape, dtype=np.float64)
+        variance = np.zeros(self._slice_shape, dtype=np.float64)
+        cabi.check(self.lib.rsb_slice_read(self.device.ctx, cabi.ptr(mean, C.c_double), cabi.ptr(variance, C.c_double)))
+        return mean, variance
+
+    def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
+        """SpectralPowerPipeline2D.update for every listed pixel of the slice rendered last: merges it into the HOST
+        frame arrays (StatsArray3D.mean / .variance / .samples, modified in place) with combine_samples, on the device
+        (rsb_slice_update_frame).  ``frame_is_empty``: the frame holds no samples yet (skips its upload)."""
+        for a, dt in ((frame_mean, np.float64), (frame_variance, np.float64), (frame_samples, np.int32)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable and a.ndim == 3):
+                raise TypeError("frame arrays must be writable C-contiguous (nx, ny, bins) float64 / int32 numpy arrays")
+        cabi.check(self.lib.rsb_slice_update_frame(self.device.ctx, int(frame_mean.shape[2]), int(slice_offset), int(bool(frame_is_empty)),
+                                                   cabi.ptr(frame_mean, C.c_double), cabi.ptr(frame_variance, C.c_double),
+                                                   cabi.ptr(frame_samples, C.c_int32)))
+
+
 def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None):
     """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160), or, with
     ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137)"""

@@ -39,9 +39,22 @@ _MATERIALS = {
 WORLD_KD = dict(max_depth=0, min_items=1, hit_cost=80.0, empty_bonus=0.2)
 
 
+_EVALUATED = ("evaluate_surface", "evaluate_volume", "evaluate_shading", "hit", "next_intersection", "contains",
+              "bounding_box", "bounding_sphere")
+
+
 def _classify(obj, table, what):
+    """Row type of a primitive / material: its own class, or a base class it inherits every evaluated method from
+    unchanged.  A subclass that overrides hit / evaluate_surface / ... is NOT its base class to the device (which
+    never calls back into Python): it is rejected like any unknown type -- no silent fallback."""
     for cls in type(obj).__mro__:
         if cls.__name__ in table:
+            if cls is not type(obj):
+                changed = [m for m in _EVALUATED if getattr(type(obj), m, None) is not getattr(cls, m, None)]
+                if changed:
+                    raise NotImplementedError(
+                        "%s %r overrides %s of %s: the B200 path evaluates the stock %s only and never calls back into "
+                        "Python; there is no CPU fallback" % (what, type(obj).__name__, ", ".join(changed), cls.__name__, cls.__name__))
             return table[cls.__name__]
     raise NotImplementedError(
         "%s %r is not supported by the B200 path (supported: %s); there is no CPU fallback"

@@ -424,6 +424,11 @@ class PinholeCamera(Observer):
                 p.update_slice(tasks, slice_id, mean, variance)
         for p in self.pipelines:
             p.finalise()
+        # the next observe() draws from fresh streams (the reference's single global stream simply keeps running):
+        # a progressive loop -- observe() again and again into accumulating pipelines, demos/cornell_box.py:160-174 --
+        # must not redraw the samples it already has.  Call c of a loop started at seed s uses the streams
+        # s + ((c*passes + p)*n_slices + slice)*nx*ny + y*nx + x; assign ``seed`` to restart a sequence.
+        self.seed += passes * len(slices) * nx * ny
         self.render_complete = True
 
 

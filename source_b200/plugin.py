@@ -112,7 +112,11 @@ class CudaRenderEngine(RenderEngine):
     Random streams: pixel (x, y) of slice k draws from the reference generator seeded with
     ``seed + k*nx*ny + y*nx + x`` (``rng="mt"``), i.e. exactly what a SerialEngine would produce if
     ``raysect.core.math.random.seed`` were called with that value before each pixel task; ``rng="philox"``
-    uses counter-based streams instead (faster, statistically equivalent).
+    uses counter-based streams instead (faster, statistically equivalent).  After the last slice of an
+    ``observe()`` the engine's ``seed`` moves past every stream that call used (``+= passes*n_slices*nx*ny``), so
+    the progressive / adaptive loops of the demos (``while not camera.render_complete: camera.observe()`` into an
+    accumulating pipeline) draw NEW samples on every pass, as the reference's free-running global stream does;
+    assign ``engine.seed`` to restart a sequence.
 
     ``bulk_update=True`` writes the slice straight into each pipeline's ``frame`` arrays (StatsArray3D)
     with the reference's combine rule instead of calling ``update`` once per pixel.
@@ -228,26 +232,41 @@ class CudaRenderEngine(RenderEngine):
         # The power pipeline's pixel processor scales every sample by the pixel sensitivity (power.pyx:478-481), the
         # radiance pipeline's does not (radiance.pyx:256-260) -- the same as a sensitivity of exactly 1.0.  One render
         # per distinct sensitivity; the pixel streams are keyed on the pixel, so both see the very same paths.
+        def sens_of(p):
+            return 1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)
+        kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
+        n_slices = len(slice_offsets(observer.spectral_bins, observer.spectral_rays))
+        offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
+        seed = self.seed + slice_id * nx * ny
+        fast = self.bulk_update and not isinstance(accel, list) and hasattr(accel, "render_slice")
         frames, rays = {}, 0
-        for p in pipelines:
-            sensitivity = 1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)
-            if sensitivity not in frames:
-                kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
-                cam = camera_for(sensitivity)
-                if isinstance(accel, list):
-                    mean, variance, rays = self._render_on_devices(
-                        accel, pix, 16, lambda a, p: a.render(cam, cfg, a.flat.spectral(
-                            template.min_wavelength, template.max_wavelength, template.bins), self.rng_mode,
-                            self.seed + slice_id * nx * ny, p, **kw))
-                else:
-                    mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode,
-                                                        self.seed + slice_id * nx * ny, pix, **kw)
+        for sensitivity in dict.fromkeys(sens_of(p) for p in pipelines):
+            cam = camera_for(sensitivity)
+            if fast:
+                # one device render per distinct sensitivity, kept on the device and merged into every pipeline frame that
+                # wants it with the reference's combine rule (power.pyx:424-437 -> statsarray.pyx:780-857) -- no per-pixel
+                # Python, no host-side gather / scatter
+                rays = accel.render_slice(cam, cfg, spectral, self.rng_mode, seed, pix, **kw)
+                for p in pipelines:
+                    if sens_of(p) == sensitivity:
+                        fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
+                        accel.update_frame(fm, fv, fs, offset, frame_is_empty=not fs[:, :, offset:offset + template.bins].any())
+            elif isinstance(accel, list):
+                mean, variance, rays = self._render_on_devices(
+                    accel, pix, 16, lambda a, p: a.render(cam, cfg, a.flat.spectral(
+                        template.min_wavelength, template.max_wavelength, template.bins), self.rng_mode, seed, p, **kw))
                 frames[sensitivity] = (mean, variance)
-        per_pipeline = [frames[1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)]
-                        for p in pipelines]
+            else:
+                mean, variance, rays = accel.render(cam, cfg, spectral, self.rng_mode, seed, pix, **kw)
+                frames[sensitivity] = (mean, variance)
         self.ray_count += rays
+        if slice_id == n_slices - 1:
+            self.seed += self.passes * n_slices * nx * ny     # the next observe() draws from fresh streams
+        if fast:
+            observer._update_statistics(rays)
+            return
+        per_pipeline = [frames[sens_of(p)] for p in pipelines]
         if self.bulk_update:
-            offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
             for p, (mean, variance) in zip(pipelines, per_pipeline):
                 self._bulk_update([p], pix, offset, mean, variance, observer.pixel_samples)
             # statistics hook of the observer: one update carrying the whole ray count

@@ -118,6 +118,32 @@ class HostScene:
         return mean, variance, rays.value
 
 
+    # the drop-in engine's whole-slice form (Accelerator.render_slice / update_frame), restated with numpy
+    def render_slice(self, camera, config, spectral, rng_mode, seed, pixels=None, passes=1, seed_stride=0):
+        mean, variance, rays = self.render(camera, config, spectral, rng_mode, seed, pixels, passes=passes, seed_stride=seed_stride)
+        pix = None if pixels is None else cabi.as_i32(pixels).reshape(-1, 2)
+        self._slice = (mean, variance, pix, camera.pixel_samples * passes)
+        return rays
+
+    def read_slice(self):
+        return self._slice[0].copy(), self._slice[1].copy()
+
+    def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
+        from source_b200.observer import combine_samples
+        mean, variance, pix, samples = self._slice
+        sl = slice(slice_offset, slice_offset + mean.shape[2])
+        if pix is None:
+            xs, ys = (a.reshape(-1) for a in np.meshgrid(np.arange(mean.shape[0]), np.arange(mean.shape[1]), indexing="ij"))
+        else:
+            xs, ys = pix[:, 0], pix[:, 1]
+        if frame_is_empty:
+            assert not frame_samples[:, :, sl].any()
+        mt, vt, nt = combine_samples(frame_mean[xs, ys, sl], frame_variance[xs, ys, sl], frame_samples[xs, ys, sl],
+                                     mean[xs, ys], np.maximum(variance[xs, ys], 0.0), samples)
+        frame_mean[xs, ys, sl] = mt
+        frame_variance[xs, ys, sl] = vt
+        frame_samples[xs, ys, sl] = nt
+
     def _render_passes(self, camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride):
         """rsb_render_passes restated with the sequential pieces: one render per pass, merged in pass order into an
         empty frame with StatsArray3D.combine_samples (hs_frame_combine)."""

@@ -115,8 +115,9 @@ def cornell_camera(api, world, pixels=(128, 128), samples=1, bins=15, spectral_r
     pipeline = a.SpectralPowerPipeline2D()
     camera = a.PinholeCamera(pixels, parent=world, transform=a.translate(0, 0, -3.3) * a.rotate(0, 0, 0),
                              pipelines=[pipeline], frame_sampler=a.FullFrameSampler2D())
-    camera.spectral_rays = spectral_rays
+    camera.spectral_rays = 1             # (rays <= bins is checked by both setters: settle the bins first)
     camera.spectral_bins = bins
+    camera.spectral_rays = spectral_rays
     camera.pixel_samples = samples
     camera.ray_importance_sampling = importance
     camera.ray_important_path_weight = path_weight
@@ -137,8 +138,9 @@ def orthographic_camera(api, world, pixels=(20, 16), width=2.4, samples=3, bins=
     pipeline = a.SpectralPowerPipeline2D()
     camera = a.OrthographicCamera(pixels, width, parent=world, pipelines=[pipeline], frame_sampler=a.FullFrameSampler2D(),
                                   transform=transform if transform is not None else a.translate(0.05, -0.1, -3.3) * a.rotate(4, -3, 2))
-    camera.spectral_rays = spectral_rays
+    camera.spectral_rays = 1             # (rays <= bins is checked by both setters: settle the bins first)
     camera.spectral_bins = bins
+    camera.spectral_rays = spectral_rays
     camera.pixel_samples = samples
     camera.ray_importance_sampling = True
     camera.ray_important_path_weight = 0.25

@@ -1,4 +1,4 @@
-"""N > 1 host logic on CPU: tile partition + the single reduce(sum) of the frame, world_size 2 over gloo."""
+"""N > 1 host logic on CPU: tile partition + the single collective (gather of owned tiles), world_size 2 over gloo."""
 import os
 import socket
 
@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from source_b200.distributed import reduce_frame, tile_pixels
+from source_b200.distributed import TileGather, tile_pixels
 
 
 def test_tile_partition_is_a_disjoint_cover():
@@ -32,28 +32,31 @@ def _worker(rank, world_size, port, nx, ny, bins, q):
     try:
         ix, iy, ib = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(bins), indexing="ij")
         full = np.stack([np.sin(ix * 0.37 + iy * 1.91 + ib * 0.11) * 1e3, np.cos(ix * 0.7 - iy * 0.3 + ib) ** 2])
-        stats = torch.zeros((2, nx, ny, bins), dtype=torch.float64)
+        stats = torch.full((2, nx, ny, bins), 123.0, dtype=torch.float64)      # foreign rows hold leftovers, as after a previous frame
         px = tile_pixels(nx, ny, 16, rank, world_size)
-        stats[:, px[:, 0], px[:, 1], :] = torch.from_numpy(full[:, px[:, 0], px[:, 1], :])
-        out = torch.zeros_like(stats)
-        for _ in range(2):      # twice: the rank's own buffer must stay zero outside its tiles between frames
-            frame = reduce_frame(stats, out, rank, world_size)
+        gather = TileGather(nx, ny, bins, 16, rank, world_size, torch.device("cpu"))
+        ok = True
+        for k in range(2):      # twice: buffers are reused from frame to frame
+            stats[:, px[:, 0], px[:, 1], :] = torch.from_numpy(full[:, px[:, 0], px[:, 1], :]) + k
+            frame = gather(stats)
+            if rank == 0:
+                ok = ok and bool(np.array_equal(frame.numpy(), full + k))   # bit-exact: rows are copied
+            else:
+                assert frame is None
         if rank == 0:
-            q.put(bool(np.array_equal(frame.numpy(), full)))   # bit-exact: the sum only ever adds zeros
-        else:
-            assert frame is None
+            q.put(ok)
     finally:
         dist.destroy_process_group()
 
 
-def test_reduce_assembles_frame_bit_exactly_world_size_2():
+def test_gather_assembles_frame_bit_exactly_world_size_2():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 40, 33, 5, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 40, 50, 5, q)) for r in range(2)]
     for p in procs:
         p.start()
     ok = q.get(timeout=120)
@@ -65,7 +68,7 @@ def test_reduce_assembles_frame_bit_exactly_world_size_2():
 
 def _render_worker(rank, world_size, port, q):
     """each rank renders ITS tiles of a Cornell frame (host build of the device code, 2 accumulated passes) into an
-    otherwise-zero frame; rank 0 checks the reduced frame against the single-process render of the whole frame"""
+    otherwise-zero frame; rank 0 checks the gathered frame against the single-process render of the whole frame"""
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path[:0] = [os.path.dirname(here), here]
@@ -88,8 +91,7 @@ def _render_worker(rank, world_size, port, q):
         px = tile_pixels(nx, ny, 8, rank, world_size)
         m, v, rays = be.render(cam, cfg, sp, cabi.RNG_MT19937_64, seed, px, passes=passes, seed_stride=nx * ny)
         stats = torch.from_numpy(np.stack([m, v]))
-        out = torch.zeros_like(stats)
-        frame = reduce_frame(stats, out, rank, world_size)
+        frame = TileGather(nx, ny, bins, 8, rank, world_size, torch.device("cpu"))(stats)
         total = torch.tensor([rays], dtype=torch.int64)
         dist.all_reduce(total)
         if rank == 0:

@@ -126,3 +126,54 @@ def test_single_visit_walk_on_mesh_free_scenes(lib):
     parity.edge(_Mode(2))
     parity.spheres(_Mode(2))
     parity.parabola(_Mode(2), exact=True)
+
+
+def test_config5_sphere_field_at_size(lib):
+    """10,000 spheres from the reference generator after seed(7), the device sweep's own rays (both orders)"""
+    hostsim_api.build()
+    stream = hostsim_api.rng_uniform(7, 40000)
+    for mode in (0, 2):
+        be, _ = parity.sweep10k(_Mode(mode), stream)
+        be.close()
+
+
+def test_reference_bunny_fixture(lib):
+    import os
+    import scenes
+    if not os.path.exists(scenes.BUNNY_RSM):
+        pytest.skip("demos/resources/stanford_bunny.rsm did not travel with this snapshot (oracle/_ref/resources)")
+    hostsim_api.build()
+    for mode in (0, 1):
+        parity.bunny_rsm(_Mode(mode))
+
+
+def test_config4_million_triangle_bunny(lib):
+    import os
+    import scenes
+    if not os.path.exists(scenes.BUNNY_OBJ) and not os.path.exists(os.path.join(scenes.MESH_CACHE, "bunny_1000000.rsm")):
+        pytest.skip("demos/resources/stanford_bunny.obj did not travel with this snapshot (oracle/_ref/resources)")
+    hostsim_api.build()
+    for mode in (0, 1):
+        be, _ = parity.cornell_bunny_1m(_Mode(mode))
+        be.close()
+
+
+def test_progressive_loop_draws_fresh_samples_every_pass(make_backend):
+    """observe() called three times on ONE camera into an accumulating pipeline (demos/cornell_box.py:160-174) == the
+    reference's own loop (golden cornell_16x12_s2_p3_b16_r4: three observe() calls, re-seeded per pass / slice / pixel):
+    the camera's seed moves past the streams each call used, so no pass repeats the samples of another."""
+    import scenes
+    import source_b200 as api
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(16, 12), samples=2, bins=16, spectral_rays=4, path_weight=0.5)
+    cam.seed = 999
+    pipe.accumulate = True
+    world._accel = parity._Accel(make_backend(parity.flatten_world(world)))
+    world._rebuild = False
+    means = []
+    for _ in range(3):
+        cam.observe()
+        means.append(pipe.frame.mean.copy())
+    world._accel.close()
+    assert not np.array_equal(means[0], means[1]) and not np.array_equal(means[1], means[2])
+    parity.compare_frame(pipe.frame, parity.golden("cornell_16x12_s2_p3_b16_r4"), exact=True)

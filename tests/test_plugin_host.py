@@ -76,9 +76,14 @@ def test_render_engine_matches_serial_reference(api, reference, bulk):
     np.testing.assert_array_equal(np.array(f.samples), n_ref)
     np.testing.assert_array_equal(np.array(f.mean), m_ref)
     np.testing.assert_array_equal(np.array(f.variance), v_ref)
-    # accumulate=True: a second observe() merges into the frame with the reference's combine rule
-    cam.observe()
+    # accumulate=True: a second observe() on the SAME engine draws from fresh streams (the engine's seed has moved past
+    # the ones the first call used) and merges into the frame with the reference's combine rule -- the progressive
+    # loop of demos/cornell_box.py:160-174.  Reference: its second pass re-seeded with the advanced base.
+    m1 = np.array(pipe2.frame.mean)
+    pipe.accumulate = True
+    reference.oracle_render(cam, pipe, 555 + 3 * 12 * 10)
     cam2.observe()
+    assert not np.array_equal(np.array(pipe2.frame.mean), m1)
     np.testing.assert_array_equal(np.array(pipe2.frame.samples), np.array(pipe.frame.samples))
     np.testing.assert_array_equal(np.array(pipe2.frame.mean), np.array(pipe.frame.mean))
     np.testing.assert_array_equal(np.array(pipe2.frame.variance), np.array(pipe.frame.variance))
@@ -513,3 +518,34 @@ def test_render_engine_over_several_devices_equals_one_device(api, reference):
     np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
     np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
     assert engine.ray_count > 0 and m_ref[mask].sum() > 0 and not np.array(pipe2.frame.mean)[~mask].any()
+
+
+def test_subclasses_that_override_evaluated_methods_are_rejected(api):
+    """no silent fallback: a user subclass is its base class to the device only if it inherits hit / evaluate_surface /
+    ... unchanged"""
+    from raysect.optical.material import Lambert
+    from raysect.primitive import Sphere
+    from source_b200.flatten import flatten_world
+
+    class Tagged(Lambert):
+        pass
+
+    class Glowing(Lambert):
+        def evaluate_surface(self, *args, **kwargs):
+            return None
+
+    class Fuzzy(Sphere):
+        def hit(self, ray):
+            return None
+
+    world = api.World()
+    api.Sphere(0.5, world, api.translate(0, 0, 0), Tagged(api.ConstantSF(0.5)))
+    flatten_world(world)
+    world = api.World()
+    api.Sphere(0.5, world, api.translate(0, 0, 0), Glowing(api.ConstantSF(0.5)))
+    with pytest.raises(NotImplementedError, match="overrides evaluate_surface"):
+        flatten_world(world)
+    world = api.World()
+    Fuzzy(0.5, world, api.translate(0, 0, 0), api.AbsorbingSurface())
+    with pytest.raises(NotImplementedError, match="overrides hit"):
+        flatten_world(world)
