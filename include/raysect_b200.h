@@ -87,9 +87,12 @@ typedef struct RsbSceneDesc {
     const int32_t* prim_mesh;       /* mesh row, else -1 */
     const int32_t* prim_parent;     /* enclosing CSG row, -1 for world-level primitives */
     const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone/parabola r,h */
-    const double* prim_to_local;    /* [n][12] rows 0..2 of Node.to_local() (parent space -> local) */
-    const double* prim_to_root;     /* [n][12] rows 0..2 of Node.to_root() */
-    const double* prim_root_inv;    /* [n][12] rows 0..2 of to_root().inverse() (Normal3D.transform, normal.pyx:241) */
+    /* matrices travel as [13]: rows 0..2 of the AffineMatrix3D, then its m33.  The bottom row of an affine matrix is
+     * (0, 0, 0, m33); Point3D.transform divides by it (raysect/core/math/point.pyx:272-281), and AffineMatrix3D.inverse()
+     * of a non-rigid chain can leave m33 = 1 - 1 ulp, so it is carried instead of assumed. */
+    const double* prim_to_local;    /* [n][13] Node.to_local() (parent space -> local) */
+    const double* prim_to_root;     /* [n][13] Node.to_root() */
+    const double* prim_root_inv;    /* [n][13] to_root().inverse() (Normal3D.transform, normal.pyx:241) */
     const double* prim_bbox;        /* [n][6] Primitive.bounding_box() lower,upper in the parent space */
     const uint8_t* world_kdtree;    /* serialised _PrimitiveKDTree stream */
     int64_t world_kdtree_bytes;
@@ -116,7 +119,8 @@ typedef struct RsbCamera {
     int32_t kind;
     double image_delta, image_start_x, image_start_y;
     double sensitivity;
-    double to_root[12];
+    double to_root[12];       /* rows 0..2 of the observer's to_root() */
+    double to_root_w;         /* its m33 (see RsbSceneDesc) */
 } RsbCamera;
 
 /* optical Ray template (raysect/optical/ray.pyx:85-126) for one spectral slice */
@@ -289,6 +293,25 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
 int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
                      const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride,
                      int64_t n_pixels, const int32_t* pixels, uint64_t* ray_count);
+
+/*
+ * Every spectral slice of an observe() at once (observer.pyx:299-340: the reference calls RenderEngine.run once per
+ * slice, one after the other; with spectral_rays = 512 that is 512 renders of a frame).  Slices are independent pixel
+ * streams exactly like accumulated passes, so they are rendered CONCURRENTLY: work item (pass p, slice k, pixel) draws
+ * from the streams seeded rng->seed + (p*n_slices + k)*seed_stride + y*nx + x (the engine's per-slice seeds when
+ * seed_stride = nx*ny), is shaded with slice k's material rows / tables (spectral[k]; all slices have config->bins bins,
+ * the same materials and tables) and lands in bins [k*bins, (k+1)*bins) of a frame with n_slices*bins bins per pixel.
+ * rsb_render_slices keeps that frame on the device as the held slice (slice_bins = n_slices*bins) for
+ * rsb_slice_update_frame / rsb_slice_read; the _dev form writes mean_dev / variance_dev [(nx, ny, n_slices*bins)].
+ */
+int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+                      const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices,
+                      uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels, uint64_t* ray_count);
+int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera,
+                          const RsbRayConfig* config, const RsbSpectral* spectral, const RsbRngDesc* rng,
+                          int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                          const int32_t* pixels_dev, double* mean_dev, double* variance_dev, uint64_t* ray_count_dev,
+                          int32_t count);
 int rsb_slice_read(uint64_t ctx, double* mean, double* variance);
 int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offset, int32_t frame_is_empty,
                            double* frame_mean, double* frame_variance, int32_t* frame_samples);

@@ -28,10 +28,12 @@ static v3 cross3(v3 a, v3 b) { return V(a.y * b.z - b.y * a.z, a.z * b.x - b.z *
 /* core/math/vector.pyx:313-337 */
 static v3 norm3(v3 a) { double t = a.x * a.x + a.y * a.y + a.z * a.z; t = 1.0 / sqrt(t); return V(a.x * t, a.y * t, a.z * t); }
 static double len3(v3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
-/* core/math/point.pyx:253-281 (w == 1 for affine matrices) */
+/* core/math/point.pyx:253-281; m = rows 0..2 then m33 (the bottom row of an affine matrix is (0, 0, 0, m33)) */
 static v3 xpoint(const double* m, v3 p) {
-    return V(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
-             m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+    double w = 0.0 * p.x + 0.0 * p.y + 0.0 * p.z + m[12];
+    w = 1.0 / w;
+    return V((m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3]) * w, (m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7]) * w,
+             (m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]) * w);
 }
 /* core/math/vector.pyx:339-366 */
 static v3 xvec(const double* m, v3 v) {
@@ -211,9 +213,9 @@ typedef struct prim_state {
 typedef struct { scene_t* s; prim_state* st; int hit_leaf; /* world kd leaf in which the last World.hit accepted its hit */ } ctx_t;
 
 static const double* P_params(scene_t* s, int id) { return s->d->prim_params + 6 * (size_t)id; }
-static const double* P_tl(scene_t* s, int id) { return s->d->prim_to_local + 12 * (size_t)id; }
-static const double* P_tr(scene_t* s, int id) { return s->d->prim_to_root + 12 * (size_t)id; }
-static const double* P_ri(scene_t* s, int id) { return s->d->prim_root_inv + 12 * (size_t)id; }
+static const double* P_tl(scene_t* s, int id) { return s->d->prim_to_local + 13 * (size_t)id; }
+static const double* P_tr(scene_t* s, int id) { return s->d->prim_to_root + 13 * (size_t)id; }
+static const double* P_ri(scene_t* s, int id) { return s->d->prim_root_inv + 13 * (size_t)id; }
 static const double* P_bb(scene_t* s, int id) { return s->d->prim_bbox + 6 * (size_t)id; }
 
 static void finish(isect* it, scene_t* s, int id, double t, v3 d, v3 hit, v3 in, v3 out, v3 n, int exiting_ge) {
@@ -947,7 +949,7 @@ static void trace_ka(tracer* T, ray_t ray, int depth, double* spectrum, int keep
         for (int k = 0; k < n_in && k < 16; ++k) {
             int m2 = d->prim_material[inside[k]];
             if (d->mat_type[m2] == RSB_MAT_VOLUME_EMITTER) {                  /* homogeneous.pyx:66-91, uniform.pyx:129-131 */
-                const double* w2p = d->prim_to_local + 12 * (size_t)inside[k];
+                const double* w2p = d->prim_to_local + 13 * (size_t)inside[k];
                 v3 ls = xpoint(w2p, start), le = xpoint(w2p, ray.o);
                 double len = len3(V(ls.x - le.x, ls.y - le.y, ls.z - le.z));   /* end.vector_to(start).get_length() */
                 if (len == 0) continue;
@@ -1134,7 +1136,7 @@ int ro_render(const RsbSceneDesc* d, const RsbCamera* cam, const RsbRayConfig* c
             ray_t r;
             r.o = xpoint(cam->to_root, V(0, 0, 0)); r.d = xvec(cam->to_root, dir); r.maxd = cfg->max_distance;
             if (cam->kind == RSB_CAMERA_ORTHOGRAPHIC) {                     /* orthographic.pyx:139-167 */
-                const double p2l[12] = {1, 0, 0, pixel_x, 0, 1, 0, pixel_y, 0, 0, 1, 0};   /* translate(pixel_x, pixel_y, 0) */
+                const double p2l[13] = {1, 0, 0, pixel_x, 0, 1, 0, pixel_y, 0, 0, 1, 0, 1};   /* translate(pixel_x, pixel_y, 0) */
                 dir = V(0, 0, 1);                                           /* dir.z = 1: projection weight 1 */
                 r.o = xpoint(cam->to_root, xpoint(p2l, V(jx, jy, 0)));
                 r.d = xvec(cam->to_root, dir);

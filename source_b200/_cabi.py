@@ -94,6 +94,7 @@ class RsbCamera(C.Structure):
         ("image_start_y", C.c_double),
         ("sensitivity", C.c_double),
         ("to_root", C.c_double * 12),
+        ("to_root_w", C.c_double),
     ]
 
 
@@ -176,6 +177,11 @@ SIGNATURES = {
                              C.POINTER(RsbRngDesc), C.c_int64, c_int32_p, c_double_p, c_double_p, c_uint64_p]),
     "rsb_render_slice": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
                                    C.POINTER(RsbRngDesc), C.c_int32, _U64, C.c_int64, c_int32_p, c_uint64_p]),
+    "rsb_render_slices": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
+                                    C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, c_int32_p, c_uint64_p]),
+    "rsb_render_slices_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),
+                                        C.POINTER(RsbSpectral), C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, _VP,
+                                        _VP, _VP, _VP, C.c_int32]),
     "rsb_slice_read": (C.c_int, [_U64, c_double_p, c_double_p]),
     "rsb_slice_update_frame": (C.c_int, [_U64, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "rsb_render_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),

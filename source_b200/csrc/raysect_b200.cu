@@ -791,6 +791,7 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->philox_idx = c.take<uint32_t>(P);
     st->jit_mti = c.take<int32_t>(P);
     st->work = c.take<int32_t>(P);
+    st->group = c.take<int32_t>(P);
     st->additive = c.take<int32_t>(P);
     st->ended = c.take<int32_t>(2 * P);
     st->n_ended = c.take<unsigned int>(2);
@@ -958,6 +959,14 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
                           const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride,
                           int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
                           uint64_t* ray_count_dev, int32_t count) {
+    return rsb_render_slices_dev(ctx, scene, cuda_stream, camera, config, spectral, rng, n_passes, 1, seed_stride, n_pixels, pixels_dev,
+                                 mean_dev, variance_dev, ray_count_dev, count);
+}
+
+int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
+                          const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride,
+                          int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
+                          uint64_t* ray_count_dev, int32_t count) {
     Context* c = as_ctx(ctx);
     DeviceScene* ds = as_scene(scene);
     if (!c || !ds || !camera || !config || !spectral || !rng || !mean_dev || !variance_dev || !ray_count_dev)
@@ -979,6 +988,11 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     if (rng->seed == 0) return fail(RSB_ERR_ARG, "rng seed must be >= 1");
     if (rng->mode != RSB_RNG_MT19937_64 && rng->mode != RSB_RNG_PHILOX) return fail(RSB_ERR_ARG, "unknown rng mode");
     if (n_passes < 1 || n_passes > 1024) return fail(RSB_ERR_ARG, "rsb_render_passes: the number of passes must be in [1, 1024]");
+    if (n_slices < 1 || n_slices > 65536) return fail(RSB_ERR_ARG, "rsb_render_slices: the number of slices must be in [1, 65536]");
+    for (int k = 1; k < n_slices; ++k)
+        if (spectral[k].bins != spectral->bins || spectral[k].n_materials != spectral->n_materials ||
+            (spectral[k].n_tables > 0 ? spectral[k].n_tables : spectral[k].n_materials) != (spectral->n_tables > 0 ? spectral->n_tables : spectral->n_materials))
+            return fail(RSB_ERR_ARG, "rsb_render_slices: every slice must have the same number of bins, materials and tables");
     if (!pixels_dev) n_pixels = (int64_t)camera->nx * camera->ny;
     if (n_pixels <= 0) return RSB_OK;
     cudaStream_t caller = (cudaStream_t)cuda_stream;
@@ -991,23 +1005,35 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         RSB_CUDA(cudaStreamWaitEvent(st, c->ev_in, 0));
     }
 
-    // ---- per-slice material table -----------------------------------------------------------------
+    // ---- per-slice material rows and spectral tables ------------------------------------------------------
     int nm = ds->n_materials;
-    std::vector<Material> mats((size_t)nm);
-    for (int i = 0; i < nm; ++i) {
-        Material& m = mats[i];
-        memset(&m, 0, sizeof(m));
-        m.type = ds->mat_type[i];
-        m.transmission_only = ds->mat_transmission_only[i];
-        m.table = i;
-        m.table2 = spectral->table2 ? spectral->table2[i] : -1;
-        m.scale = spectral->scale ? spectral->scale[i] : 1.0;
-        m.index_in = spectral->index_in ? spectral->index_in[i] : 1.0;
-        m.index_out = spectral->index_out ? spectral->index_out[i] : 1.0;
+    std::vector<Material> mats((size_t)nm * n_slices);
+    const size_t tb = (size_t)n_tables * spectral->bins;
+    // per slice: the tables, followed by their natural logs (exp(length * ln T) form of the Beer-Lambert pow in the replay)
+    std::vector<double> both(tb * 2 * (size_t)n_slices);
+    for (int k = 0; k < n_slices; ++k) {
+        const RsbSpectral& sk = spectral[k];
+        if ((sk.table2 == nullptr) != (spectral->table2 == nullptr)) return fail(RSB_ERR_ARG, "rsb_render_slices: inconsistent second tables");
+        for (int i = 0; i < nm; ++i) {
+            Material& m = mats[(size_t)k * nm + i];
+            memset(&m, 0, sizeof(m));
+            m.type = ds->mat_type[i];
+            m.transmission_only = ds->mat_transmission_only[i];
+            m.table = i;
+            m.table2 = sk.table2 ? sk.table2[i] : -1;
+            m.scale = sk.scale ? sk.scale[i] : 1.0;
+            m.index_in = sk.index_in ? sk.index_in[i] : 1.0;
+            m.index_out = sk.index_out ? sk.index_out[i] : 1.0;
+        }
+        double* dst = both.data() + (size_t)k * 2 * tb;
+        for (size_t i = 0; i < tb; ++i) {
+            dst[i] = sk.tables[i];
+            dst[tb + i] = log(sk.tables[i]);
+        }
     }
-    size_t mat_bytes = (((size_t)nm * sizeof(Material) + 15) / 16) * 16;
-    size_t tab_bytes = (((size_t)n_tables * spectral->bins * 8 + 15) / 16) * 16;
-    size_t tab_alloc = (size_t)n_tables * spectral->bins * 16 + 16;
+    size_t mat_bytes = ((mats.size() * sizeof(Material) + 15) / 16) * 16;
+    size_t tab_bytes = ((tb * 8 + 15) / 16) * 16;
+    size_t tab_alloc = both.size() * 8 + 16;
     if (c->mats_cap < mat_bytes) {
         cudaFree(c->d_mats);
         c->d_mats = nullptr; c->mats_cap = 0;
@@ -1020,13 +1046,7 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         RSB_CUDA(cudaMalloc(&c->d_tables, tab_alloc));
         c->tables_cap = tab_alloc;
     }
-    RSB_CUDA(cudaMemcpyAsync(c->d_mats, mats.data(), (size_t)nm * sizeof(Material), cudaMemcpyHostToDevice, st));
-    // tables, followed by their natural logs (exp(length * ln T) form of the Beer-Lambert pow in the replay)
-    std::vector<double> both((size_t)n_tables * spectral->bins * 2);
-    for (size_t i = 0; i < (size_t)n_tables * spectral->bins; ++i) {
-        both[i] = spectral->tables[i];
-        both[(size_t)n_tables * spectral->bins + i] = log(spectral->tables[i]);
-    }
+    RSB_CUDA(cudaMemcpyAsync(c->d_mats, mats.data(), mats.size() * sizeof(Material), cudaMemcpyHostToDevice, st));
     RSB_CUDA(cudaMemcpyAsync(c->d_tables, both.data(), both.size() * 8, cudaMemcpyHostToDevice, st));
     // the two host staging buffers above are stack/heap temporaries: make the copies complete before returning
     RSB_CUDA(cudaStreamSynchronize(st));
@@ -1057,7 +1077,9 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.cam.image_start_x = camera->image_start_x;
     a.cam.image_start_y = camera->image_start_y;
     a.cam.sensitivity = camera->sensitivity;
-    memcpy(a.cam.to_root, camera->to_root, sizeof(a.cam.to_root));
+    memcpy(a.cam.to_root, camera->to_root, 12 * sizeof(double));
+    if (camera->to_root_w == 0.0) return fail(RSB_ERR_ARG, "rsb_render: RsbCamera.to_root_w (m33 of the camera transform) is zero");
+    a.cam.to_root[12] = 1.0 / camera->to_root_w;
     a.mean = mean_dev;
     a.variance = variance_dev;
     a.ray_count = (unsigned long long*)ray_count_dev;
@@ -1069,11 +1091,13 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.seed = rng->seed;
     a.seed_stride = seed_stride;
     a.n_passes = n_passes;
+    a.n_slices = n_slices;
+    a.frame_bins = n_slices * config->bins;
     for (int i = 0; i < ds->n_materials; ++i)
         if (ds->mat_type[i] == RSB_MAT_VOLUME_EMITTER) a.has_additive = 1;
     a.n_pix_pass = n_pixels;
     a.pixels = pixels_dev;
-    a.frame_elems = (long long)camera->nx * camera->ny * config->bins;
+    a.frame_elems = (long long)camera->nx * camera->ny * a.frame_bins;
     if (n_passes > 1) {
         size_t need_pass = (size_t)2 * (size_t)(n_passes - 1) * (size_t)a.frame_elems * sizeof(double);
         if (c->pass_bytes < need_pass) {
@@ -1088,7 +1112,7 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.n_items = ds->n_world_items;
     a.staged = ds->stage_bytes ? 1 : 0;
     size_t smem_scene = ds->stage_bytes, smem_shade = ds->stage_bytes, smem_tables = 0;
-    if (smem_shade + mat_bytes <= kMaxStageBytes && 2 * tab_bytes <= kMaxStageBytes) {
+    if (n_slices == 1 && smem_shade + mat_bytes <= kMaxStageBytes && 2 * tab_bytes <= kMaxStageBytes) {
         a.tables_staged = 1;
         smem_shade += mat_bytes;
         smem_tables = 2 * tab_bytes;
@@ -1102,7 +1126,7 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     // Pixels are processed in chunks so that the up-front MT19937-64 state of a chunk (5 KB per pixel) stays
     // within a fixed HBM budget; a 1024 x 1024 frame is one chunk (5.2 GB).
     bool mt = rng->mode == RSB_RNG_MT19937_64;
-    const long long n_work = (long long)n_pixels * n_passes;   // work items: (pass, pixel task)
+    const long long n_work = (long long)n_pixels * n_passes * n_slices;   // work items: (pass, slice, pixel task)
     long long chunk_cap = std::min<long long>(n_work, c->chunk_items);
     long long P = std::min<long long>(chunk_cap, (long long)c->sm_count * c->slots_per_sm);
     P = std::max<long long>(P, 1);
@@ -1156,8 +1180,8 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     }
     if (rc) return rc;
     if (n_passes > 1) {
-        long long total = (long long)n_pixels * config->bins;
-        k_pass_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, camera->ny, config->bins, n_passes,
+        long long total = (long long)n_pixels * a.frame_bins;
+        k_pass_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, camera->ny, a.frame_bins, n_passes,
                                                                     camera->pixel_samples, a.frame_elems, a.pass_mean, a.pass_variance,
                                                                     mean_dev, variance_dev);
         RSB_CUDA(cudaGetLastError());
@@ -1188,12 +1212,19 @@ int rsb_render(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbR
 int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                      const RsbRngDesc* rng, int32_t n_passes, uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels,
                      uint64_t* ray_count) {
+    return rsb_render_slices(ctx, scene, camera, config, spectral, rng, n_passes, 1, seed_stride, n_pixels, pixels, ray_count);
+}
+
+int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                      const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                      const int32_t* pixels, uint64_t* ray_count) {
     Context* c = as_ctx(ctx);
     if (!c || !as_scene(scene) || !camera || !config || !ray_count) return fail(RSB_ERR_ARG, "rsb_render_slice: null argument");
+    if (n_slices < 1) return fail(RSB_ERR_ARG, "rsb_render_slices: the number of slices must be at least 1");
     RSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     c->slice.valid = false;
-    const size_t frame = (size_t)camera->nx * camera->ny * config->bins;
+    const size_t frame = (size_t)camera->nx * camera->ny * config->bins * n_slices;
     if (!pixels) n_pixels = (int64_t)camera->nx * camera->ny;
     if (n_pixels < 0) return fail(RSB_ERR_ARG, "rsb_render_slice: negative pixel count");
     if (c->slice_cap < 2 * frame) {
@@ -1215,7 +1246,7 @@ int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, cons
     if (pixels && n_pixels > 0) RSB_CUDA(cudaMemcpyAsync(c->d_slice_pix, pixels, (size_t)n_pixels * 8, cudaMemcpyHostToDevice, st));
     RSB_CUDA(cudaEventRecord(c->ev0, st));
     if (n_pixels > 0) {
-        int rc = rsb_render_passes_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, seed_stride, n_pixels,
+        int rc = rsb_render_slices_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels,
                                        pixels ? c->d_slice_pix : nullptr, c->d_slice, c->d_slice + frame, (uint64_t*)c->d_slice_rays, 1);
         if (rc) return rc;
     }
@@ -1225,7 +1256,7 @@ int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, cons
     RSB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
     *ray_count += rays;
-    c->slice.nx = camera->nx; c->slice.ny = camera->ny; c->slice.bins = config->bins;
+    c->slice.nx = camera->nx; c->slice.ny = camera->ny; c->slice.bins = config->bins * n_slices;
     c->slice.samples = camera->pixel_samples * n_passes;
     c->slice.n_pixels = n_pixels;
     c->slice.listed = pixels != nullptr;

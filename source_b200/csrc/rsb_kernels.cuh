@@ -371,6 +371,7 @@ struct WfSlots {
     uint32_t* philox_idx;   // [P] draws so far (Philox) / cursor of the pixel's path stream (MT19937-64)
     int32_t* jit_mti;       // [P] cursor of the pixel's jitter stream (MT19937-64)
     int32_t* work;          // [P] index (within the current pixel chunk) of the pixel the slot is rendering
+    int32_t* group;         // [P] stream group of that work item: pass * n_slices + slice
     int32_t* additive;      // [P] the path in flight has logged an emitting volume (only touched when has_additive)
     int32_t* pix_mti;       // [n_chunk][2] MT19937-64 cursors of every pixel of the chunk: path stream, jitter stream
     unsigned long long* pix_mt;   // [n_chunk][2][312] their state words (seeded up front by k_wf_seed)
@@ -398,6 +399,8 @@ struct WfArgs {
     long long frame_elems;      // nx * ny * bins
     unsigned long long seed_stride;   // pass p draws from streams seeded seed + p * seed_stride + y * nx + x
     int32_t n_passes;
+    int32_t n_slices;           // spectral slices rendered concurrently; `sp` describes slice 0, slice k follows at strides
+    int32_t frame_bins;         // bins of a frame row = n_slices * sp.bins
     int32_t has_additive;       // the scene has volume emitters: dark path ends may still have to be replayed
     unsigned long long* ray_count;
     unsigned long long* work_counter;
@@ -413,10 +416,25 @@ struct WfArgs {
     int32_t wave;
 };
 
-// Pass (accumulated observe() call) of the work item a slot is rendering
-__device__ __forceinline__ int wf_pass_of(const WfArgs& a, int slot) {
-    if (a.n_passes <= 1) return 0;
-    return (int)((unsigned long long)(a.item_base + a.st.work[slot]) / (unsigned long long)a.n_pix_pass);
+// Stream group of the work item a slot is rendering: (accumulated observe() call) * n_slices + (spectral slice).  Every
+// group is an independent set of pixel streams, seeded seed + group * seed_stride + y * nx + x.
+__device__ __forceinline__ int wf_group_of(const WfArgs& a, int slot) {
+    if (a.n_passes * a.n_slices <= 1) return 0;
+    return a.st.group[slot];
+}
+__device__ __forceinline__ int wf_pass_of(const WfArgs& a, int slot) { return a.n_slices > 1 ? wf_group_of(a, slot) / a.n_slices : wf_group_of(a, slot); }
+__device__ __forceinline__ int wf_slice_of(const WfArgs& a, int slot) { return a.n_slices > 1 ? wf_group_of(a, slot) % a.n_slices : 0; }
+
+// Per-slice material rows and spectral tables: slice k's block follows slice 0's ([n_materials] rows; [2][n_tables][bins]
+// doubles: the tables, then their logs)
+__device__ __forceinline__ Spectral wf_slice_spectral(const Spectral& sp, int slice) {
+    Spectral s = sp;
+    if (slice > 0) {
+        s.mats = sp.mats + (size_t)slice * sp.n_materials;
+        s.tables = sp.tables + (size_t)slice * 2 * sp.n_tables * sp.bins;
+        s.tables_ln = s.tables + (size_t)sp.n_tables * sp.bins;
+    }
+    return s;
 }
 
 // The cursors of the pixel stream a slot is rendering are kept per SLOT (copied from the pixel's seeded cursors
@@ -432,7 +450,7 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
         rng.mt.mti = (int)a.st.philox_idx[slot];
     } else {
         long long pixel_id = (long long)a.st.py[slot] * a.cam.nx + a.st.px[slot];
-        rng.px.init(a.seed + (unsigned long long)wf_pass_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id,
+        rng.px.init(a.seed + (unsigned long long)wf_group_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id,
                     (uint32_t)a.st.sample[slot]);
         rng.px.idx = a.st.philox_idx[slot];
     }
@@ -475,11 +493,11 @@ __device__ __forceinline__ void wf_push_ended(const WfArgs& a, int slot) {
 }
 
 // Pixel (x, y) of work item w of the current chunk (FullFrameSampler2D task list, or the whole frame); returns
-// the pass the item belongs to
+// the stream group (pass * n_slices + slice) the item belongs to
 __device__ __forceinline__ int wf_pixel_of(const WfArgs& a, unsigned long long w, int* px, int* py) {
     unsigned long long g = w + (unsigned long long)a.item_base;
     int pass = 0;
-    if (a.n_passes > 1) {
+    if (a.n_passes * a.n_slices > 1) {
         pass = (int)(g / (unsigned long long)a.n_pix_pass);
         g -= (unsigned long long)pass * (unsigned long long)a.n_pix_pass;
     }
@@ -523,10 +541,11 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
             atomicAdd(a.n_idle, 1u);
             return;
         }
-        wf_pixel_of(a, w, &px, &py);
+        const int group = wf_pixel_of(a, w, &px, &py);
         a.st.px[slot] = px;
         a.st.py[slot] = py;
         a.st.work[slot] = (int32_t)w;
+        if (a.n_passes * a.n_slices > 1) a.st.group[slot] = group;
         if (RNGMODE == RNG_MT19937_64) {
             a.st.philox_idx[slot] = (uint32_t)a.st.pix_mti[2 * w];
             a.st.jit_mti[slot] = a.st.pix_mti[2 * w + 1];
@@ -547,7 +566,7 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
         a.st.jit_mti[slot] = jit.mt.mti;
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
-        jit.px.init(a.seed + (unsigned long long)wf_pass_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);
+        jit.px.init(a.seed + (unsigned long long)wf_group_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);
         u1 = jit.uniform();
         u2 = jit.uniform();
         a.st.philox_idx[slot] = jit.px.idx;
@@ -738,7 +757,9 @@ __device__ __forceinline__ void wf_shade_list(const WfArgs& a, const Scene& sc, 
         log.n = a.st.log_n[slot];
         log.overflow = 0;
         log.additive = 0;
-        int r = path_shade<MAT, FEAT>(sc, sp, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
+        // (concurrent spectral slices: the slot's slice has its own material rows -- refractive indices -- and tables)
+        const Spectral sps = a.n_slices > 1 ? wf_slice_spectral(sp, wf_slice_of(a, slot)) : sp;
+        int r = path_shade<MAT, FEAT>(sc, sps, a.cfg, ps, rec, a.st.norm[slot], rng, stack, log, stats);
         a.st.log_n[slot] = log.n;
         if (log.overflow) atomicExch(a.overflow_flag, 1);
         if ((FEAT & RSB_FEAT_RARE_MATERIALS) && log.additive) a.st.additive[slot] = 1;
@@ -834,8 +855,12 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         log.capacity = a.log_capacity;
         log.n = a.st.log_n[slot];
         log.overflow = 0;
-        size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * bins;
-        const int pass = wf_pass_of(a, slot);
+        // frame rows hold frame_bins = n_slices * bins values: slice k owns bins [k * bins, (k + 1) * bins)
+        const int group = wf_group_of(a, slot);
+        const int pass = a.n_slices > 1 ? group / a.n_slices : group;
+        const int slice = a.n_slices > 1 ? group % a.n_slices : 0;
+        size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * a.frame_bins + (size_t)slice * bins;
+        const Spectral sps = a.n_slices > 1 ? wf_slice_spectral(sp, slice) : sp;
         double* m = (pass ? a.pass_mean + (size_t)(pass - 1) * a.frame_elems : a.mean) + row;
         double* v = (pass ? a.pass_variance + (size_t)(pass - 1) * a.frame_elems : a.variance) + row;
         const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
@@ -862,8 +887,8 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
                     __syncwarp();
                     for (int j = 0; j < cnt; ++j) {
                         const LogEntry e = wlog[j];
-                        if (ha) xa = apply_entry(xa, e.op, e.table, e.v, sp, ba);
-                        if (hb) xb = apply_entry(xb, e.op, e.table, e.v, sp, bb);
+                        if (ha) xa = apply_entry(xa, e.op, e.table, e.v, sps, ba);
+                        if (hb) xb = apply_entry(xb, e.op, e.table, e.v, sps, bb);
                     }
                 }
             }

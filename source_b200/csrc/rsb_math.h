@@ -50,13 +50,18 @@ RSB_HD V3 normalise(const V3& a) {
     return v3(a.x * t, a.y * t, a.z * t);
 }
 
-// raysect/core/math/point.pyx:253-281 (Point3D.transform).  m = rows 0..2 of an affine
-// 4x4 (row-major 3x4).  The reference also forms w = m30*x+m31*y+m32*z+m33 and multiplies
-// by 1/w; for an affine matrix w == 1.0 exactly, so the product is the identity.
+// raysect/core/math/point.pyx:253-281 (Point3D.transform).  m = rows 0..2 of an affine 4x4 (row-major 3x4) followed
+// by m[12] = 1.0 / m33.  The reference forms w = m30*x + m31*y + m32*z + m33, then w = 1.0 / w, and multiplies every
+// component by it; the bottom row of an affine matrix is (0, 0, 0, m33), so w is the per-matrix constant m33 -- exactly
+// 1.0 for matrices built from translations, rotations and scalings, but AffineMatrix3D.inverse() of a non-rigid chain
+// can leave m33 = 1 - 1 ulp.  The reciprocal is formed once per matrix on the host (the same IEEE division) and the
+// three multiplies are kept: x * 1.0 is x, anything else is what the reference computes.
+#define RSB_MAT_WORDS 13
 RSB_HD V3 xform_point(const double* m, const V3& p) {
-    return v3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3],
-              m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
-              m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+    const double w = m[12];
+    return v3((m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3]) * w,
+              (m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7]) * w,
+              (m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]) * w);
 }
 
 // raysect/core/math/vector.pyx:339-366 (Vector3D.transform)

@@ -43,7 +43,7 @@ struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.
     int32_t kind;
     double image_delta, image_start_x, image_start_y;
     double sensitivity;
-    double to_root[12];
+    double to_root[RSB_MAT_WORDS];   // rows 0..2, then 1 / m33
 };
 
 enum LogOp : int32_t {
@@ -595,7 +595,7 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
         // OrthographicCamera._generate_rays (orthographic.pyx:139-167): the sample point is moved to the pixel with
         // Point3D.transform(translate(pixel_x, pixel_y, 0)) and the ray leaves it along +z; "non-physical camera
         // samples radiance directly": projection weight 1
-        const double pixel_to_local[12] = {1.0, 0.0, 0.0, pixel_x, 0.0, 1.0, 0.0, pixel_y, 0.0, 0.0, 1.0, 0.0};
+        const double pixel_to_local[RSB_MAT_WORDS] = {1.0, 0.0, 0.0, pixel_x, 0.0, 1.0, 0.0, pixel_y, 0.0, 0.0, 1.0, 0.0, 1.0};
         V3 origin = xform_point(pixel_to_local, v3(jx, jy, 0.0));
         *weight = 1.0;
         *o = xform_point(cam.to_root, origin);

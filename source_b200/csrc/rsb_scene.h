@@ -66,10 +66,10 @@ struct __attribute__((aligned(16))) Prim {
     int32_t parent;     // enclosing CSG row, -1 for world-level primitives
     int32_t pad0, pad1;
     // -- lines 1..2
-    double to_local[12]; // parent space -> local, rows 0..2 of the affine matrix
-    double to_root[12];  // local -> parent space
-    double root_inv[12]; // AffineMatrix3D.inverse() of to_root as the reference recomputes it inside
-                         // Normal3D.transform (raysect/core/math/normal.pyx:241-247); CSG children only
+    double to_local[RSB_MAT_WORDS]; // parent space -> local: rows 0..2 of the affine matrix, then 1 / m33 (rsb_math.h xform_point)
+    double to_root[RSB_MAT_WORDS];  // local -> parent space
+    double root_inv[RSB_MAT_WORDS]; // AffineMatrix3D.inverse() of to_root as the reference recomputes it inside
+                                    // Normal3D.transform (raysect/core/math/normal.pyx:241-247); CSG children only
 };
 
 struct __attribute__((aligned(16))) F4 {

@@ -77,9 +77,14 @@ int pack_scene(const RsbSceneDesc* d, PackedScene* out, std::string* err) {
         p.child_b = d->prim_child_b[i];
         p.mesh = d->prim_mesh[i];
         p.parent = d->prim_parent[i];
-        memcpy(p.to_local, d->prim_to_local + 12 * (size_t)i, 96);
-        memcpy(p.to_root, d->prim_to_root + 12 * (size_t)i, 96);
-        memcpy(p.root_inv, d->prim_root_inv + 12 * (size_t)i, 96);
+        // [13] per matrix: rows 0..2, then m33; the device keeps 1 / m33 (Point3D.transform's `w = 1.0 / w`, point.pyx:276)
+        const double* src[3] = {d->prim_to_local + 13 * (size_t)i, d->prim_to_root + 13 * (size_t)i, d->prim_root_inv + 13 * (size_t)i};
+        double* dst[3] = {p.to_local, p.to_root, p.root_inv};
+        for (int k = 0; k < 3; ++k) {
+            memcpy(dst[k], src[k], 96);
+            if (src[k][12] == 0.0) { *err = "Bad matrix transform, 4th element of homogeneous coordinate is zero."; return RSB_ERR_ARG; }
+            dst[k][12] = 1.0 / src[k][12];
+        }
     }
     out->n_world = d->n_world;
 

@@ -212,6 +212,28 @@ class Accelerator:
         self._slice_shape = (camera.nx, camera.ny, config.bins)
         return rays.value
 
+    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None):
+        """Every spectral slice of an observe() in one call (rsb_render_slices): ``spectrals`` = one RsbSpectral per
+        slice (all with ``config.bins`` bins); slice k of pass p draws from the streams seeded
+        ``seed + (p*len(spectrals) + k)*seed_stride + y*nx + x`` (``seed_stride`` defaults to nx*ny: the per-slice seeds
+        of the engine / mirror camera).  The frame with ``len(spectrals)*config.bins`` bins per pixel stays on the device
+        as the held slice; returns the ray count."""
+        rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
+        rays = C.c_uint64(0)
+        pix, n = None, camera.nx * camera.ny
+        if pixels is not None:
+            pix = cabi.as_i32(pixels).reshape(-1, 2)
+            n = pix.shape[0]
+        arr = (cabi.RsbSpectral * len(spectrals))()
+        for k, sp in enumerate(spectrals):
+            C.memmove(C.byref(arr[k]), C.byref(sp), C.sizeof(cabi.RsbSpectral))
+        stride = camera.nx * camera.ny if seed_stride is None else int(seed_stride)
+        cabi.check(self.lib.rsb_render_slices(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
+                                              int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32), C.byref(rays)))
+        self._keep = list(spectrals)      # the tables the descriptors point at must outlive the call
+        self._slice_shape = (camera.nx, camera.ny, config.bins * len(spectrals))
+        return rays.value
+
     def read_slice(self):
         """(mean, variance) of the slice rendered last, (nx, ny, slice_bins); unlisted pixels are zero"""
         mean = np.zeros(self._slice_shape, dtype=np.float64)
@@ -254,6 +276,9 @@ def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None):
     cam.sensitivity = float(sensitivity)
     for k, v in enumerate(float(to_root[i, j]) for i in range(3) for j in range(4)):
         cam.to_root[k] = v
+    if [float(to_root[3, j]) for j in range(3)] != [0.0, 0.0, 0.0]:
+        raise NotImplementedError("the observer's transform is not affine (bottom row %r)" % ([float(to_root[3, j]) for j in range(4)],))
+    cam.to_root_w = float(to_root[3, 3])
     return cam
 
 

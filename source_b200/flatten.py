@@ -61,21 +61,15 @@ def _classify(obj, table, what):
         % (what, type(obj).__name__, ", ".join(sorted(table))))
 
 
-_warned_w = [False]
-
-
 def mat34(m):
-    """Rows 0..2 of an AffineMatrix3D.  The device transforms points with these rows only; Raysect's Point3D.transform
-    also divides by w = m30 x + m31 y + m32 z + m33 (point.pyx:272-281).  For an affine matrix w is exactly 1, but
-    AffineMatrix3D.inverse() of a non-rigid transform can leave m33 one ulp off 1.0: hit distances then deviate from
-    Raysect's by a few ulp (primitive ids do not).  Warn once; see DESIGN.md section 8."""
-    bottom = [float(m[3, j]) for j in range(4)]
-    if bottom != [0.0, 0.0, 0.0, 1.0] and not _warned_w[0]:
-        import warnings
-        _warned_w[0] = True
-        warnings.warn("a primitive transform is not exactly affine (bottom row %r): the B200 path ignores the homogeneous "
-                      "divide, so intersection distances may differ from Raysect's in the last few ulp" % (bottom,))
-    return [float(m[i, j]) for i in range(3) for j in range(4)]
+    """An AffineMatrix3D as the C ABI carries it: rows 0..2, then m33 (13 values).  Raysect's Point3D.transform divides
+    by w = m30 x + m31 y + m32 z + m33 (point.pyx:272-281); the bottom row of an affine matrix is (0, 0, 0, m33), and
+    AffineMatrix3D.inverse() of a non-rigid chain can leave m33 one ulp off 1.0 -- the device multiplies by 1 / m33
+    exactly as the reference does."""
+    if [float(m[3, j]) for j in range(3)] != [0.0, 0.0, 0.0]:
+        raise NotImplementedError("a primitive transform is not affine (bottom row %r): projective transforms are not "
+                                  "supported by the B200 path; there is no CPU fallback" % ([float(m[3, j]) for j in range(4)],))
+    return [float(m[i, j]) for i in range(3) for j in range(4)] + [float(m[3, 3])]
 
 
 def _box6(b):
@@ -276,9 +270,9 @@ def flatten_world(world, world_kdtree=None):
     flat.prim_mesh = cabi.as_i32([r["mesh"] for r in rows])
     flat.prim_parent = cabi.as_i32([r["parent"] for r in rows])
     flat.prim_params = cabi.as_f64([r["params"] for r in rows], (n, 6))
-    flat.prim_to_local = cabi.as_f64([r["to_local"] for r in rows], (n, 12))
-    flat.prim_to_root = cabi.as_f64([r["to_root"] for r in rows], (n, 12))
-    flat.prim_root_inv = cabi.as_f64([r["root_inv"] for r in rows], (n, 12))
+    flat.prim_to_local = cabi.as_f64([r["to_local"] for r in rows], (n, 13))
+    flat.prim_to_root = cabi.as_f64([r["to_root"] for r in rows], (n, 13))
+    flat.prim_root_inv = cabi.as_f64([r["root_inv"] for r in rows], (n, 13))
     flat.prim_bbox = cabi.as_f64([r["bbox"] for r in rows], (n, 6))
 
     if world_kdtree is None:

@@ -405,10 +405,32 @@ class PinholeCamera(Observer):
                 cam.sensitivity = sens
                 cams[sens] = cam
         self.ray_count = 0
-        for slice_id, s in enumerate(slices):
-            cfg = ray_config(s.bins, s.min_wavelength, s.max_wavelength, self.ray_extinction_prob,
-                             self.ray_extinction_min_depth, self.ray_max_depth, self.ray_importance_sampling,
-                             self.ray_important_path_weight)
+
+        def sens_of(p):
+            return 1.0 if getattr(p, "radiance", False) else float(self.sensitivity)
+
+        def config_of(s):
+            return ray_config(s.bins, s.min_wavelength, s.max_wavelength, self.ray_extinction_prob, self.ray_extinction_min_depth,
+                              self.ray_max_depth, self.ray_importance_sampling, self.ray_important_path_weight)
+        if len(slices) > 1 and len({s.bins for s in slices}) == 1 and hasattr(accel, "render_slices"):
+            # Every spectral slice is an independent set of pixel streams (the reference renders them one after the other,
+            # observer.pyx:299-305): all of them in ONE device render (rsb_render_slices), slice k of pass p drawing from
+            # the streams seeded seed + (p*n_slices + k)*nx*ny + y*nx + x -- the seeds the per-slice loop below uses.
+            cfg = config_of(slices[0])
+            spectrals = [accel.flat.spectral(s.min_wavelength, s.max_wavelength, s.bins) for s in slices]
+            for sens, cam in cams.items():
+                rays = accel.render_slices(cam, cfg, spectrals, self.rng_mode, self.seed, tasks, passes=passes)
+                for p in self.pipelines:
+                    if sens_of(p) == sens:
+                        f = p.frame
+                        p._samples = self.pixel_samples * passes
+                        accel.update_frame(f.mean, f.variance, f.samples, 0, frame_is_empty=not f.samples.any())
+            self.ray_count += rays
+            slices_done = True
+        else:
+            slices_done = False
+        for slice_id, s in enumerate(slices if not slices_done else []):
+            cfg = config_of(s)
             spectral = accel.flat.spectral(s.min_wavelength, s.max_wavelength, s.bins)
             # each slice is an independent pass with its own streams (the reference's single global stream
             # simply keeps running): offset the seed by the slice so passes are not correlated
@@ -420,7 +442,7 @@ class PinholeCamera(Observer):
                 frames[sens] = (mean, variance)
             self.ray_count += rays
             for p in self.pipelines:
-                mean, variance = frames[1.0 if getattr(p, "radiance", False) else float(self.sensitivity)]
+                mean, variance = frames[sens_of(p)]
                 p.update_slice(tasks, slice_id, mean, variance)
         for p in self.pipelines:
             p.finalise()

@@ -228,7 +228,6 @@ class CudaRenderEngine(RenderEngine):
                          template.important_path_weight, template.max_distance)
         spectral = (accel[0] if isinstance(accel, list) else accel).flat.spectral(
             template.min_wavelength, template.max_wavelength, template.bins)
-        pix = np.asarray(tasks, dtype=np.int32).reshape(-1, 2)
         # The power pipeline's pixel processor scales every sample by the pixel sensitivity (power.pyx:478-481), the
         # radiance pipeline's does not (radiance.pyx:256-260) -- the same as a sensitivity of exactly 1.0.  One render
         # per distinct sensitivity; the pixel streams are keyed on the pixel, so both see the very same paths.
@@ -239,10 +238,41 @@ class CudaRenderEngine(RenderEngine):
         offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
         seed = self.seed + slice_id * nx * ny
         fast = self.bulk_update and not isinstance(accel, list) and hasattr(accel, "render_slice")
+        # a stock FullFrameSampler2D without a mask lists every pixel exactly once (sampler2d.pyx:75-102), in shuffled
+        # order; pixel streams are keyed on the pixel, so "the whole frame" says the same in zero bytes
+        from itertools import chain
+        from raysect.optical.observer import FullFrameSampler2D
+        if fast and type(observer.frame_sampler) is FullFrameSampler2D and len(tasks) == nx * ny:
+            pix = None
+        else:
+            pix = np.fromiter(chain.from_iterable(tasks), dtype=np.int32, count=2 * len(tasks)).reshape(-1, 2)
+        # Every spectral slice at once (observer.pyx:299-305 calls run() once per slice, one after the other): slices are
+        # independent pixel streams, so the first run() of an observe() renders ALL of them concurrently
+        # (rsb_render_slices; slice k draws from the seeds the per-slice path uses) and merges the whole frame into the
+        # pipelines; the run() calls for slices 1.. find their work done.
+        all_slices = None
+        if fast and n_slices > 1 and hasattr(accel, "render_slices"):
+            spec = observer._slice_spectrum()
+            if len({sl.bins for sl in spec}) == 1:
+                all_slices = spec
+        if all_slices is not None and slice_id > 0:
+            if slice_id == n_slices - 1:
+                self.seed += self.passes * n_slices * nx * ny
+            return
         frames, rays = {}, 0
         for sensitivity in dict.fromkeys(sens_of(p) for p in pipelines):
             cam = camera_for(sensitivity)
-            if fast:
+            if all_slices is not None:
+                cfg0 = ray_config(all_slices[0].bins, all_slices[0].min_wavelength, all_slices[0].max_wavelength, template.extinction_prob,
+                                  template.extinction_min_depth, template.max_depth, template.importance_sampling,
+                                  template.important_path_weight, template.max_distance)
+                spectrals = [accel.flat.spectral(sl.min_wavelength, sl.max_wavelength, sl.bins) for sl in all_slices]
+                rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes)
+                for p in pipelines:
+                    if sens_of(p) == sensitivity:
+                        fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
+                        accel.update_frame(fm, fv, fs, 0, frame_is_empty=not fs.any())
+            elif fast:
                 # one device render per distinct sensitivity, kept on the device and merged into every pipeline frame that
                 # wants it with the reference's combine rule (power.pyx:424-437 -> statsarray.pyx:780-857) -- no per-pixel
                 # Python, no host-side gather / scatter

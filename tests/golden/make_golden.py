@@ -33,12 +33,11 @@ def save(name, **arrays):
 
 
 def assert_affine(world):
-    """The device path carries rows 0..2 of every transform (RsbSceneDesc): AffineMatrix3D.inverse() can leave m33 one
-    ulp off 1.0, and Point3D.transform then divides by w (point.pyx:272-281) -- a documented limitation (DESIGN.md
-    section 8: t deviates by a few ulp, ids do not); the golden scenes stay on exactly affine matrices."""
+    """The device path carries rows 0..2 and m33 of every transform (RsbSceneDesc); the first three elements of the
+    bottom row must be zero (projective matrices are rejected by the flattener)."""
     for p in world.primitives:
         for m in (p.to_local(), p.to_root()):
-            assert [m[3, j] for j in range(4)] == [0.0, 0.0, 0.0, 1.0], (type(p).__name__, [m[3, j] for j in range(4)])
+            assert [m[3, j] for j in range(3)] == [0.0, 0.0, 0.0], (type(p).__name__, [m[3, j] for j in range(4)])
 
 
 def hits(world, o, d, md=None):
@@ -235,6 +234,35 @@ def bunny_goldens():
     print("cornell + 1M bunny: hits %d of %d (mesh %d), points inside %d" % ((g["primitive"] >= 0).sum(), len(o), (g["triangle"] >= 0).sum(), (cc > 0).sum()))
 
 
+def w_goldens():
+    """transforms whose inverse has m33 = 1 - 1 ulp: Point3D.transform's division by w is live (point.pyx:272-281)"""
+    world = scenes.w_scene(api)
+    off = [p.to_local()[3, 3] - 1.0 for p in world.primitives]
+    assert sum(1 for x in off if x != 0.0) >= 6, off
+    o, d = scenes.zoo_rays(4000, seed=33)
+    r = harness.oracle_hit(world, o, d)
+    leaf, mesh_leaf, _ = harness.oracle_hit_nodes(world, o, d, hits=r)
+    stream = harness.world_kdtree_stream(world)
+    pts = np.random.default_rng(34).uniform([-2.6, -1.5, -1.2], [2.6, 2.9, 1.2], (3000, 3))
+    cc, cp = harness.oracle_contains(world, pts)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(20, 16), samples=3, bins=6, path_weight=0.3)
+    cam.transform = api.translate(0, 0.3, -4.5) * scenes.w_transforms(api, 1, seed=5)[0]       # the observer's to_root as well
+    mean, var, n = harness.oracle_render(cam, pipe, 6160)
+    save("w_hits_and_frame", primitive=r["primitive"], distance=r["distance"], exiting=r["exiting"], geometry=r["geometry"],
+         triangle=r["triangle"], uvw=r["uvw"], leaf=leaf, mesh_leaf=mesh_leaf, tree_sha256=digest(stream), tree_bytes=np.int64(len(stream)),
+         contains_count=cc, contains_prims=cp, mean=mean, variance=var, samples=n, m33_minus_1=np.array(off))
+    print("w scene: hits %d of %d, points inside %d, m33 - 1: %s" % ((r["primitive"] >= 0).sum(), len(o), (cc > 0).sum(), off))
+
+
+def prism_512_golden():
+    """BASELINE config 3 shape on a small frame: 512 spectral bins traced as 512 spectral rays (one bin per slice)"""
+    world = scenes.prism_scene(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(12, 10), samples=2, bins=512, spectral_rays=512, path_weight=0.75)
+    cam.transform = api.translate(0.3, 0.2, -2.2) * api.rotate(5, -3, 0)
+    mean, var, n = harness.oracle_render(cam, pipe, 2718)
+    save("prism_12x10_s2_b512_r512", mean=mean, variance=var, samples=n)
+
+
 def sweep_goldens():
     """BASELINE config 5 at size: 10,000 spheres drawn from the reference generator after seed(7); the first 20,000 rays
     of the device sweep (seed 2024; incoherent order and Morton order) restated in numpy, hit by the reference"""
@@ -254,6 +282,10 @@ def sweep_goldens():
 def main():
     if "--bunny-only" in sys.argv:
         return bunny_goldens()
+    if "--w-only" in sys.argv:
+        return w_goldens()
+    if "--prism512-only" in sys.argv:
+        return prism_512_golden()
     if "--sweep-only" in sys.argv:
         return sweep_goldens()
     if "--nodes-only" in sys.argv:
@@ -340,6 +372,8 @@ def main():
     nodes_goldens()
     bunny_goldens()
     sweep_goldens()
+    w_goldens()
+    prism_512_golden()
 
     # 6. dispersive CSG prism: one spectral ray per bin
     world = scenes.prism_scene(api)

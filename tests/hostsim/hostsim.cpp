@@ -213,7 +213,8 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     cam.nx = camera->nx; cam.ny = camera->ny; cam.pixel_samples = camera->pixel_samples; cam.kind = camera->kind;
     cam.image_delta = camera->image_delta; cam.image_start_x = camera->image_start_x; cam.image_start_y = camera->image_start_y;
     cam.sensitivity = camera->sensitivity;
-    memcpy(cam.to_root, camera->to_root, sizeof(cam.to_root));
+    memcpy(cam.to_root, camera->to_root, 12 * sizeof(double));
+    cam.to_root[12] = 1.0 / camera->to_root_w;
 
     int cap = 6 * (std::max(cfg.max_depth, cfg.extinction_min_depth) + 2);
     std::vector<LogEntry> logbuf((size_t)cap);

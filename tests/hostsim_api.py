@@ -125,6 +125,21 @@ class HostScene:
         self._slice = (mean, variance, pix, camera.pixel_samples * passes)
         return rays
 
+    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None):
+        """rsb_render_slices restated with the sequential pieces: one render per slice with the slice's own seed base"""
+        nx, ny, bins = camera.nx, camera.ny, config.bins
+        stride = nx * ny if seed_stride is None else seed_stride
+        n = len(spectrals)
+        mean, variance, total = np.zeros((nx, ny, bins * n)), np.zeros((nx, ny, bins * n)), 0
+        for k, sp in enumerate(spectrals):
+            m, v, rays = self.render(camera, config, sp, rng_mode, seed + k * stride, pixels, passes=passes, seed_stride=n * stride)
+            mean[:, :, k * bins:(k + 1) * bins] = m
+            variance[:, :, k * bins:(k + 1) * bins] = v
+            total += rays
+        pix = None if pixels is None else cabi.as_i32(pixels).reshape(-1, 2)
+        self._slice = (mean, variance, pix, camera.pixel_samples * passes)
+        return total
+
     def read_slice(self):
         return self._slice[0].copy(), self._slice[1].copy()
 

@@ -661,3 +661,44 @@ def cornell_mesh_rays(n=4000, seed=14):
     d = tgt - o
     d /= np.linalg.norm(d, axis=1)[:, None]
     return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
+# ---- transforms whose inverse is not exactly affine: AffineMatrix3D.inverse() of a non-rigid chain can leave m33 = 1 - 1 ulp,
+# ---- and Point3D.transform divides by it (raysect/core/math/point.pyx:272-281)
+def w_transforms(api, count, seed=0):
+    """`count` non-rigid chains translate * rotate * (scale + shear), drawn from a fixed stream and kept only if the
+    bottom-right element of their inverse differs from 1.0 (about one random chain in eight)"""
+    a = api
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        s = rng.uniform(0.5, 1.8, 3)
+        sh = rng.uniform(-0.4, 0.4, 3)
+        m = a.AffineMatrix3D([[s[0], sh[0], sh[1], 0], [0, s[1], sh[2], 0], [0, 0, s[2], 0], [0, 0, 0, 1]])
+        t = a.translate(*rng.uniform(-1, 1, 3)) * a.rotate(*rng.uniform(-90, 90, 3)) * m
+        if t.inverse()[3, 3] != 1.0:
+            out.append(t)
+    return out
+
+
+def w_scene(api):
+    """every primitive type, a CSG tree (operands included) and a mesh under transforms whose to_local() has m33 != 1"""
+    a = api
+    world = a.World()
+    lam = a.Lambert(a.ConstantSF(0.6))
+    t = w_transforms(a, 9)
+    place = [(-1.7, 0.3, 0.1), (-0.5, -0.4, 0.2), (0.8, -0.5, 0.0), (1.9, -0.3, 0.2), (0.4, 1.2, 0.0), (-1.2, 1.4, 0.1)]
+
+    def at(k):
+        return a.translate(*place[k]) * t[k]
+    a.Sphere(0.45, world, at(0), lam)
+    a.Box(a.Point3D(-0.35, -0.3, -0.25), a.Point3D(0.4, 0.45, 0.5), world, at(1), lam)
+    a.Cylinder(0.3, 0.9, world, at(2), lam)
+    a.Cone(0.4, 0.8, world, at(3), lam)
+    a.Subtract(a.Box(a.Point3D(-0.4, -0.4, -0.4), a.Point3D(0.4, 0.4, 0.4), transform=t[6]),
+               a.Sphere(0.45, transform=a.translate(0.1, 0, 0) * t[7]), world, at(4), lam)
+    verts, tris, normals = icosphere(2, radius=0.4, bumps=0.15)
+    a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=world, transform=at(5), material=lam)
+    a.Box(a.Point3D(-3, -0.05, -3), a.Point3D(3, 0, 3), world, a.translate(0, -1.6, 0), lam)
+    a.Sphere(0.3, world, a.translate(0.2, 2.8, -1.0) * t[8], a.UniformSurfaceEmitter(a.ConstantSF(1.0), 3.0))
+    return world

@@ -77,6 +77,14 @@ def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 
 
+def test_transforms_with_m33_off_one_bit_exact(make_backend):
+    parity.w_matrices(make_backend, exact=True)
+
+
+def test_prism_512_spectral_slices_bit_exact(make_backend):
+    parity.prism_512(make_backend, exact=True)
+
+
 def test_c_oracle_vs_host_build_on_fresh_inputs(make_backend):
     """two independent formulations (recursive iterators vs event lists / log replay) on inputs without goldens"""
     import hostsim_api

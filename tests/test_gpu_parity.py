@@ -46,6 +46,16 @@ def test_parabola_primitive(make_backend):
     parity.parabola(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.0)
 
 
+def test_transforms_with_m33_off_one(make_backend):
+    fr = parity.w_matrices(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+    print("divergent pixel fraction:", fr)
+
+
+def test_prism_512_spectral_slices_rendered_concurrently(make_backend):
+    fr = parity.prism_512(make_backend, exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+    print("divergent pixel fraction:", fr)
+
+
 def test_sphere_field(make_backend):
     parity.spheres(make_backend)
 

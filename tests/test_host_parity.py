@@ -78,6 +78,14 @@ def test_prism_csg_dispersion_bit_exact(make_backend):
     parity.prism(make_backend, exact=True)
 
 
+def test_prism_512_spectral_slices_bit_exact(make_backend):
+    parity.prism_512(make_backend, exact=True)
+
+
+def test_transforms_with_m33_off_one_bit_exact(make_backend):
+    parity.w_matrices(make_backend, exact=True)
+
+
 def test_philox_mode_statistics(make_backend):
     """The counter-based stream must estimate the same radiance: compare frame-integrated power of a
     Philox render with the MT19937 golden within 5 standard errors of the golden's own variance."""

@@ -39,8 +39,10 @@ ncuworld)
 list)
   timeout 900 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -c 200 --csv \
     --log-file $O/${TAG}_sweep_launches.csv python tools_sweep.py --n 4e6 --mesh-subdiv 8 --order random > $O/${TAG}_list.log 2>&1; tail -n 2 $O/${TAG}_list.log ;;
-bench)
-  timeout 900 python bench.py --steps 2 --warmup 1 --e2e-steps 1 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; cut -c1-600 $O/${TAG}_bench.json; tail -n 3 $O/${TAG}_bench.err ;;
+bench|bench:*)
+  A=${S#bench:}; [ "$A" = "bench" ] && A="--steps 2 --warmup 1 --e2e-steps 1"
+  A="${A//_/ }"
+  timeout 1500 python bench.py $A > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; python tools_bench_show.py $O/${TAG}_bench.json; tail -n 5 $O/${TAG}_bench.err ;;
 listmesh)
   RSB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -s 600 -c 400 --csv \
     --log-file $O/${TAG}_rendermesh_launches.csv python tools_render_mesh.py --pixels 1024 --spp 4 > $O/${TAG}_listmesh.log 2>&1; tail -n 2 $O/${TAG}_listmesh.log
