@@ -42,7 +42,18 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 WORKLOAD = dict(name="cornell_box 1024x1024 x 256 spp x 64 bins (BASELINE configs[1])", pixels=1024, spp=256, bins=64)
 CPU_SAMPLE = dict(pixels=512, spp=16, bins=64)      # >= 5 s per observe(): MulticoreEngine's per-call fork is amortised
 CPU_SERIAL_SAMPLE = dict(pixels=128, spp=8, bins=64)
-DEFAULT_PASSES = 8   # 256 spp = 8 accumulated observe() passes of 32 spp (the reference's progressive-render loop)
+# The frame's samples are rendered as P accumulated observe() passes (the reference's progressive-render loop,
+# demos/cornell_box.py:160-174), concurrently: P x pixels independent streams.  P = 8 per GPU keeps ~8 M streams per rank
+# whatever N is, so that every wave of every rank stays as wide as the single-GPU ones (at N = 8 with P = 8 a rank holds
+# 1 M streams for 1.2 M slots: its 659 waves ran 42 % full in round 1).
+PASSES_PER_GPU = 8
+
+
+def auto_passes(spp, n_gpus):
+    p = PASSES_PER_GPU * n_gpus
+    while p > 1 and (spp % p or spp // p < 4):
+        p //= 2
+    return max(1, p)
 RAY_CFG = dict(extinction_prob=0.01, extinction_min_depth=3, max_depth=500, importance_sampling=True,
                important_path_weight=0.25)   # demos/cornell_box.py:147-156
 MIN_WL, MAX_WL = 375.0, 740.0               # observer defaults, observer.pyx:116-117
@@ -275,27 +286,34 @@ def phase_shares(stats_sum, total_ms):
 
 
 def timed_frames(cx, renderer, steps, warmup, seed0):
-    """K frames device-resident: (total_ms max over ranks, rays summed over ranks, per-step phase times of rank 0, launches, waves)"""
+    """K frames device-resident: (total_ms max over ranks, rays summed over ranks, per-step kernel times of rank 0).
+    The K timed frames run without any instrumentation; the per-kernel device times come from ONE extra frame (same
+    seed as the first timed one) whose waves are bracketed with CUDA events on the launch stream."""
     torch = cx.torch
     for i in range(warmup):
         renderer.step_device(seed=seed0 + i)
     cx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays_t = torch.zeros(1, dtype=torch.int64, device=cx.dev)
-    acc = dict(trace_ms=0.0, shade_ms=0.0, finalize_ms=0.0, regen_ms=0.0, trace_launches=0, launches=0, waves=0)
+    launches = waves = 0
     cx.barrier()
     e0.record()
     for i in range(steps):
-        rays_t += renderer.step_device(seed=seed0 + 100 + i, time_trace=True)
+        rays_t += renderer.step_device(seed=seed0 + 100 + i)
         rs = cx.device.render_stats()
-        for k in acc:
-            acc[k] += rs[k]
+        launches += rs["launches"]
+        waves += rs["waves"]
     e1.record()
     cx.barrier()
     total_ms = cx.reduce(e0.elapsed_time(e1), "max")
     if cx.world_size > 1:
         cx.dist.all_reduce(rays_t, op=cx.dist.ReduceOp.SUM)
-    return total_ms, int(rays_t.item()), {k: v / steps for k, v in acc.items()}
+    renderer.step_device(seed=seed0 + 100, time_trace=True)
+    cx.barrier()
+    rs = cx.device.render_stats()
+    per_step = {k: rs[k] for k in ("trace_ms", "shade_ms", "finalize_ms", "regen_ms", "trace_launches")}
+    per_step["launches"], per_step["waves"] = launches / steps, waves / steps
+    return total_ms, int(rays_t.item()), per_step
 
 
 def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kernel):
@@ -375,7 +393,8 @@ def run_c4(cx, args):
     world._device = cx.device
     accel = world.build_accelerator()
     setup_s = time.time() - t0
-    renderer = FrameRenderer(cam, accel, cx.rank, cx.world_size, tile=16, passes=args.passes)
+    passes = auto_passes(C4["spp"], cx.world_size)
+    renderer = FrameRenderer(cam, accel, cx.rank, cx.world_size, tile=16, passes=passes)
     steps = max(1, min(args.steps, 3))
     total_ms, rays, per_step = timed_frames(cx, renderer, steps, 1, 1000)
     ms_step = total_ms / steps
@@ -383,6 +402,7 @@ def run_c4(cx, args):
                           "trace phase = k_rq_walk (world walk) + k_rq_mesh (Mesh.hit) + k_rq_walk (resume)")
     out = {"workload": name, "Mrays_per_s": rays / total_ms / 1e3, "frames_per_s": 1e3 / ms_step, "ms_per_step": ms_step,
            "rays_per_step": rays / steps, "steps": steps, "n_gpus": cx.world_size, "scaling": "strong", "setup_s": setup_s,
+           "passes": passes,
            "waves_per_step": per_step["waves"], "roofline": roof}
     if note:
         out["note"] = note
@@ -479,6 +499,8 @@ def run_ours(args):
         w["pixels"] = args.pixels
     if args.spp:
         w["spp"] = args.spp
+    if not args.passes:
+        args.passes = auto_passes(w["spp"], cx.world_size)
     if w["spp"] % args.passes:
         raise SystemExit("bench.py: --passes must divide the samples per pixel")
     world = scenes.cornell_box(api)
@@ -590,8 +612,9 @@ def main():
     ap.add_argument("--rng", default="mt", choices=["mt", "philox"])
     ap.add_argument("--pixels", type=int, default=0, help="override frame size (development only)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (development only)")
-    ap.add_argument("--passes", type=int, default=DEFAULT_PASSES,
-                    help="render the frame's samples as this many accumulated observe() passes, concurrently")
+    ap.add_argument("--passes", type=int, default=0,
+                    help="render the frame's samples as this many accumulated observe() passes, concurrently "
+                         "(default: 8 per GPU, at least 4 samples per pass)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--configs", default="C4,C5,C3", help="comma list of the extra configurations to measure, or 'none'")
     ap.add_argument("--no-cpu", action="store_true")

@@ -71,12 +71,13 @@ struct Context {
     long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
-    long long chunk_items = 8LL << 20;  // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (5 KB each)
+    long long chunk_items = 16LL << 20; // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (2.5 KB + 16 B per sample each)
     unsigned int* h_idle = nullptr;     // pinned
     RsbRenderStats render_stats{};
     int slots_per_sm = 8192;            // RSB_SLOTS_PER_SM: pixel streams in flight per SM (wavefront width)
     bool use_graphs = true;             // RSB_NO_GRAPH=1 launches the wave kernels one by one (debugging)
     std::vector<cudaEvent_t> event_pool;
+    unsigned long long* d_mt_table = nullptr;   // seed-independent part of MT19937-64's seed(d) (rsb_rng.h mt_seed_table)
     Material* d_mats = nullptr;
     double* d_tables = nullptr;
     size_t mats_cap = 0, tables_cap = 0;
@@ -314,6 +315,12 @@ int rsb_context_create(int device, uint64_t* ctx) {
     RSB_CUDA(cudaMalloc(&c->d_scalars, 8 * sizeof(unsigned long long)));
     RSB_CUDA(cudaMemset(c->d_scalars, 0, 8 * sizeof(unsigned long long)));
     RSB_CUDA(cudaMallocHost(&c->h_idle, sizeof(unsigned int)));
+    {
+        uint64_t table[RSB_MT_NN];
+        mt_seed_table(table);
+        RSB_CUDA(cudaMalloc(&c->d_mt_table, sizeof(table)));
+        RSB_CUDA(cudaMemcpy(c->d_mt_table, table, sizeof(table), cudaMemcpyHostToDevice));
+    }
     if (const char* ng = getenv("RSB_NO_GRAPH")) c->use_graphs = !(ng[0] == '1');
     if (const char* sp = getenv("RSB_CHUNK_ITEMS")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->chunk_items = v; }
     if (const char* sp = getenv("RSB_RQ_CHUNK")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->rq_chunk = v; }
@@ -340,6 +347,7 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFreeHost(c->h_idle);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     cudaFree(c->d_mats);
+    cudaFree(c->d_mt_table);
     cudaFree(c->d_tables);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -764,7 +772,7 @@ struct Carver {
     }
 };
 
-size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t chunk, WfSlots* st, bool mesh, RqBuf* rq) {
+size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t chunk, int spp, WfSlots* st, bool mesh, RqBuf* rq) {
     Carver c{base};
     memset(rq, 0, sizeof(*rq));
     if (mesh) {
@@ -789,7 +797,6 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->status = c.take<int32_t>(P);
     st->log_n = c.take<int32_t>(P);
     st->philox_idx = c.take<uint32_t>(P);
-    st->jit_mti = c.take<int32_t>(P);
     st->work = c.take<int32_t>(P);
     st->group = c.take<int32_t>(P);
     st->additive = c.take<int32_t>(P);
@@ -797,8 +804,9 @@ size_t carve_slots(unsigned char* base, size_t P, size_t cap, bool mt, size_t ch
     st->n_ended = c.take<unsigned int>(2);
     st->hit_list = c.take<int32_t>(4 * P);
     st->n_hit = c.take<unsigned int>(4);
-    st->pix_mti = mt ? c.take<int32_t>(2 * chunk) : nullptr;
-    st->pix_mt = mt ? c.take<unsigned long long>(chunk * 2 * RSB_MT_NN) : nullptr;
+    st->pix_mti = mt ? c.take<int32_t>(chunk) : nullptr;
+    st->pix_mt = mt ? c.take<unsigned long long>(chunk * RSB_MT_NN) : nullptr;
+    st->pix_jitter = mt ? c.take<double>(chunk * 2 * (size_t)spp) : nullptr;
     st->log = c.take<LogEntry>(P * cap);
     if (mesh) {
         rq->ray = st->ray;
@@ -843,7 +851,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     RsbRenderStats& rs = c->render_stats;
     rs.slots = std::max<int64_t>(rs.slots, a.n_slots);
     if (RNGMODE == RNG_MT19937_64) {
-        k_wf_seed<<<(unsigned int)((a.n_pixels + threads - 1) / threads), threads, 0, st>>>(a);
+        k_wf_seed<<<(unsigned int)((a.n_pixels + 32 * RSB_SEED_WARPS - 1) / (32 * RSB_SEED_WARPS)), 32 * RSB_SEED_WARPS, 0, st>>>(a);
         rs.launches += 1;
     }
     k_wf_init<RNGMODE><<<grid, threads, 0, st>>>(a);
@@ -1132,7 +1140,7 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     P = std::max<long long>(P, 1);
     WfSlots probe;
     RqBuf rq;
-    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe, ds->has_mesh, &rq);
+    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &probe, ds->has_mesh, &rq);
     if (c->slot_bytes < need) {
         // the per-slot path log grows with ray_max_depth (48 KB per slot at Raysect's default 500): narrow the wavefront
         // and the seeded chunk until the pool fits what the device has left (another context, another process, ...)
@@ -1142,7 +1150,7 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         while (need > free_b - free_b / 8 && (P > (long long)c->sm_count * 128 || chunk_cap > P)) {
             if (chunk_cap > P) chunk_cap = std::max<long long>(P, chunk_cap / 2);
             else { P = std::max<long long>((long long)c->sm_count * 128, P * 3 / 4); chunk_cap = std::min(chunk_cap, P); }
-            need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &probe, ds->has_mesh, &rq);
+            need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &probe, ds->has_mesh, &rq);
         }
     }
     if (c->slot_bytes < need) {
@@ -1151,7 +1159,8 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
         RSB_CUDA(cudaMalloc(&c->d_slots, need));
         c->slot_bytes = need;
     }
-    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, &a.st, ds->has_mesh, &rq);
+    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &a.st, ds->has_mesh, &rq);
+    a.st.mt_table = c->d_mt_table;
     if (count & RSB_RENDER_COUNT) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const bool time_trace = (count & RSB_RENDER_TIME_TRACE) != 0;
     count &= RSB_RENDER_COUNT;

@@ -369,12 +369,14 @@ struct WfSlots {
     int32_t* status;        // [P]
     int32_t* log_n;         // [P]
     uint32_t* philox_idx;   // [P] draws so far (Philox) / cursor of the pixel's path stream (MT19937-64)
-    int32_t* jit_mti;       // [P] cursor of the pixel's jitter stream (MT19937-64)
     int32_t* work;          // [P] index (within the current pixel chunk) of the pixel the slot is rendering
     int32_t* group;         // [P] stream group of that work item: pass * n_slices + slice
     int32_t* additive;      // [P] the path in flight has logged an emitting volume (only touched when has_additive)
-    int32_t* pix_mti;       // [n_chunk][2] MT19937-64 cursors of every pixel of the chunk: path stream, jitter stream
-    unsigned long long* pix_mt;   // [n_chunk][2][312] their state words (seeded up front by k_wf_seed)
+    int32_t* pix_mti;       // [n_chunk] MT19937-64 cursor of every stream of the chunk after its 2*spp jitter draws
+    unsigned long long* pix_mt;   // [n_chunk][312] their state words (seeded up front by k_wf_seed)
+    double* pix_jitter;     // [n_chunk][2*spp] the jitter draws of every stream: uniform() number 0 .. 2*spp-1 of seed(...),
+                            // which RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
+    const unsigned long long* mt_table;   // [312] seed-independent part of seed(d) (rsb_rng.h mt_seed_table)
     LogEntry* log;          // [P][log_capacity]
     int32_t* ended;         // [2][P] compacted lists of ended slots (double buffered by wave parity)
     unsigned int* n_ended;  // [2]
@@ -445,7 +447,7 @@ __device__ __forceinline__ void wf_load_rng(const WfArgs& a, int slot, Rng& rng)
     rng.mode = RNGMODE;
     if (RNGMODE == RNG_MT19937_64) {
         size_t w = (size_t)a.st.work[slot];
-        rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN);
+        rng.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * RSB_MT_NN;
         rng.mt.stride = 1;
         rng.mt.mti = (int)a.st.philox_idx[slot];
     } else {
@@ -509,22 +511,61 @@ __device__ __forceinline__ int wf_pixel_of(const WfArgs& a, unsigned long long w
     return pass;
 }
 
-// 1 thread = 1 pixel of the chunk: seed(seed + y*nx + x) for both cursors of the pixel's stream, all pixels in
-// parallel and ahead of time (seeding is a 935-step dependent chain; done lazily inside the wave loop it put
-// the latency of one chain on the critical path of every wave).
-__global__ void __launch_bounds__(128) k_wf_seed(const __grid_constant__ WfArgs a) {
-    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= a.n_pixels) return;
-    int px, py;
-    const int pass = wf_pixel_of(a, (unsigned long long)w, &px, &py);
-    long long pixel_id = (long long)py * a.cam.nx + px;
-    uint64_t* base = reinterpret_cast<uint64_t*>(a.st.pix_mt) + (size_t)w * (2 * RSB_MT_NN);
-    int jm, pm;
-    // the jitter cursor starts at draw 0, the path cursor after the 2*spp draws that
-    // RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
-    mt_seed_pair(a.seed + (unsigned long long)pass * a.seed_stride + (unsigned long long)pixel_id, 2 * a.cam.pixel_samples, base + RSB_MT_NN, &jm, base, &pm);
-    a.st.pix_mti[2 * w] = pm;
-    a.st.pix_mti[2 * w + 1] = jm;
+// 1 warp = 32 streams of the chunk: seed(seed + group*stride + y*nx + x) for every stream ahead of time (seeding is a
+// dependent chain; done lazily inside the wave loop it put the latency of one chain on the critical path of every
+// wave).  Round 1 ran the full 935-step init_by_array64 twice per stream (a jitter cursor and a path cursor) with
+// every thread writing its own 5 KB row word by word: 119 ms per 8 M streams, all of it uncoalesced 8-byte stores.
+// Now: 312 steps per stream (rsb_rng.h mt_seed_fast: the rest is a seed-independent table), ONE state per stream, the
+// words of 32 streams transposed through shared memory so that every store instruction writes 256 contiguous bytes of
+// one stream, and the 2*spp jitter draws taken right away into a small per-stream table.
+#define RSB_SEED_WARPS 4
+__global__ void __launch_bounds__(32 * RSB_SEED_WARPS) k_wf_seed(const __grid_constant__ WfArgs a) {
+    __shared__ uint64_t tile_all[RSB_SEED_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t (*tile)[33] = tile_all[warp];
+    const long long w0 = ((long long)blockIdx.x * RSB_SEED_WARPS + warp) * 32;
+    if (w0 >= a.n_pixels) return;
+    const long long w = w0 + lane;
+    const bool valid = w < a.n_pixels;
+    const uint64_t* T = reinterpret_cast<const uint64_t*>(a.st.mt_table);
+    uint64_t d = 1;
+    if (valid) {
+        int px, py;
+        const int group = wf_pixel_of(a, (unsigned long long)w, &px, &py);
+        d = a.seed + (unsigned long long)group * a.seed_stride + (unsigned long long)((long long)py * a.cam.nx + px);
+    }
+    uint64_t* state = reinterpret_cast<uint64_t*>(a.st.pix_mt);
+    const int rows = (int)((a.n_pixels - w0) < 32 ? (a.n_pixels - w0) : 32);
+    const uint64_t m1 = mt_seed_first(T, d);
+    uint64_t prev = m1;
+    for (int i0 = 0; i0 < RSB_MT_NN; i0 += 32) {
+        const int n = RSB_MT_NN - i0 < 32 ? RSB_MT_NN - i0 : 32;
+        for (int k = 0; k < n; ++k) {
+            const int i = i0 + k;
+            uint64_t v;
+            if (i == 0) v = 9223372036854775808ULL;
+            else if (i == 1) v = 0;                       // written last: it needs word 311
+            else { prev = mt_seed_step(__ldg(T + i), prev, i); v = prev; }
+            tile[lane][k] = v;
+        }
+        __syncwarp();
+        // row r of the tile = words i0 .. i0+n-1 of stream w0 + r: one coalesced store per stream
+        for (int r = 0; r < rows; ++r)
+            if (lane < n) state[(size_t)(w0 + r) * RSB_MT_NN + i0 + lane] = tile[r][lane];
+        __syncwarp();
+    }
+    if (!valid) return;
+    uint64_t* mine = state + (size_t)w * RSB_MT_NN;
+    mine[1] = mt_seed_last(m1, prev);
+    // the jitter draws: the first 2*spp outputs of the stream, regenerating its words lazily in place like every draw
+    Mt19937_64 g;
+    g.mt = mine;
+    g.stride = 1;
+    g.mti = RSB_MT_NN;
+    const int nj = 2 * a.cam.pixel_samples;
+    double* jit = a.st.pix_jitter + (size_t)w * nj;
+    for (int k = 0; k < nj; ++k) jit[k] = (double)(g.next_u64() >> 11) * (1.0 / 9007199254740992.0);
+    a.st.pix_mti[w] = g.mti;
 }
 
 // Next sample of the slot's pixel, or the next pixel from the work counter; PinholeCamera._generate_rays for
@@ -546,10 +587,7 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
         a.st.py[slot] = py;
         a.st.work[slot] = (int32_t)w;
         if (a.n_passes * a.n_slices > 1) a.st.group[slot] = group;
-        if (RNGMODE == RNG_MT19937_64) {
-            a.st.philox_idx[slot] = (uint32_t)a.st.pix_mti[2 * w];
-            a.st.jit_mti[slot] = a.st.pix_mti[2 * w + 1];
-        }
+        if (RNGMODE == RNG_MT19937_64) a.st.philox_idx[slot] = (uint32_t)a.st.pix_mti[w];
         s = 0;
     }
     a.st.sample[slot] = s;
@@ -557,13 +595,10 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     jit.mode = RNGMODE;
     double u1, u2;
     if (RNGMODE == RNG_MT19937_64) {
-        size_t w = (size_t)a.st.work[slot];
-        jit.mt.mt = reinterpret_cast<uint64_t*>(a.st.pix_mt) + w * (2 * RSB_MT_NN) + RSB_MT_NN;
-        jit.mt.stride = 1;
-        jit.mt.mti = a.st.jit_mti[slot];
-        u1 = jit.uniform();
-        u2 = jit.uniform();
-        a.st.jit_mti[slot] = jit.mt.mti;
+        // draws 2s and 2s+1 of the stream, taken when it was seeded (k_wf_seed)
+        const double2 j2 = *reinterpret_cast<const double2*>(a.st.pix_jitter + ((size_t)a.st.work[slot] * spp + (size_t)s) * 2);
+        u1 = j2.x;
+        u2 = j2.y;
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
         jit.px.init(a.seed + (unsigned long long)wf_group_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);

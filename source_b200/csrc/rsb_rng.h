@@ -102,6 +102,46 @@ struct Mt19937_64 {
     }
 };
 
+// seed(d) in 312 dependent steps instead of 935.  seed(d) keys init_by_array64 with (0, ..., 0, d) (random.pyx:215-243),
+// so init_genrand64(19650218) and the first 311 steps of the first mixing loop (key word 0, random.pyx:141-154) do not
+// depend on d: their result is one constant table T (mt_seed_table).  What is left per stream: the 312th step of that
+// loop (the only one that adds d), the 311 steps of the second loop, and mt[0] = 2^63.
+RSB_HD void mt_seed_table(uint64_t* T) {
+    T[0] = 19650218ULL;
+    for (int i = 1; i < RSB_MT_NN; ++i) T[i] = 6364136223846793005ULL * (T[i - 1] ^ (T[i - 1] >> 62)) + (uint64_t)i;
+    for (int k = 0; k < RSB_MT_NN - 1; ++k) {
+        const int i = k + 1;
+        T[i] = (T[i] ^ ((T[i - 1] ^ (T[i - 1] >> 62)) * 3935559000370003845ULL)) + (uint64_t)k;
+    }
+    T[0] = T[RSB_MT_NN - 1];     // i reached NN: mt[0] = mt[NN - 1], i = 1
+}
+
+// word 1 after the first mixing loop's last step (i = 1, j = 311: the step that adds d)
+RSB_HD uint64_t mt_seed_first(const uint64_t* T, uint64_t d) {
+    return (T[1] ^ ((T[0] ^ (T[0] >> 62)) * 3935559000370003845ULL)) + d + (uint64_t)(RSB_MT_NN - 1);
+}
+// second mixing loop, word i (2 <= i < NN) from the word before it
+RSB_HD uint64_t mt_seed_step(uint64_t t_i, uint64_t prev, int i) {
+    return (t_i ^ ((prev ^ (prev >> 62)) * 2862933555777941757ULL)) - (uint64_t)i;
+}
+// ... and its last step, back at i = 1 with mt[0] = the new mt[NN - 1]
+RSB_HD uint64_t mt_seed_last(uint64_t m1, uint64_t m_last) {
+    return (m1 ^ ((m_last ^ (m_last >> 62)) * 2862933555777941757ULL)) - 1ULL;
+}
+
+// the same state Mt19937_64::seed(d) leaves, through the table (serial form: tests, and the statement the warp-
+// cooperative k_wf_seed follows)
+RSB_HD void mt_seed_fast(const uint64_t* T, uint64_t d, uint64_t* m) {
+    const uint64_t m1 = mt_seed_first(T, d);
+    uint64_t prev = m1;
+    for (int i = 2; i < RSB_MT_NN; ++i) {
+        prev = mt_seed_step(T[i], prev, i);
+        m[i] = prev;
+    }
+    m[1] = mt_seed_last(m1, prev);
+    m[0] = 9223372036854775808ULL;
+}
+
 // Seeds a pixel's two cursors in one pass over a thread-private scratch array (local memory, L1 resident)
 // instead of running the 935-step initialisation chain and the 2*spp-draw skip as dependent round trips to
 // the HBM-resident state: `jitter` receives the state right after seed(d) (cursor at draw 0), `path` the

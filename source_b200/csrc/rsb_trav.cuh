@@ -290,23 +290,23 @@ struct MeshPool {
     int32_t* rs_pack;     // [T] ix | iy << 2 | iz << 4 of the lane's ray-space permutation (mesh.pyx:566-610)
     float* rs_s;          // [3][T] sx, sy, sz
     int32_t* mesh_idx;    // [T]
-    const F4** tri_base;  // [T] triangle rows of the lane's mesh
     float4* res;          // warp: [CAP] (t, u, v, w); t = NaN: no hit
-    int32_t* tri;         // warp: [CAP] triangle id of the pair
+    int32_t* item;        // warp: [CAP] index of the pair's triangle in the mesh's leaf item list; then its triangle id
     int32_t* own;         // warp: [CAP] lane that owns the pair
     const double* ax0;    // RayAx storage of thread 0: rows 0..2 mesh-local origin, row 9 ray.max_distance
 };
 
 #define RQ_AX_ROWS 10
 #define RQ_POOL_WARP_BYTES (RQ_POOL_CAP * 24)
-#define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 28 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
+#define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 20 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
 
 // MeshData._trace_leaf (mesh.pyx:520-563) for every lane with `in_leaf`, the (ray, triangle) pairs dealt out evenly
-// over the warp: the lanes that stand at a leaf publish (owner lane, triangle id) for each of their triangles in one
-// list, every lane of the warp then tests the pairs p = lane, lane + 32, ... with the OWNER's mesh-local origin and
-// ray-space shear (read from shared memory, where the owner left them when it picked the ray up), and the owner
-// replays _trace_leaf's comparison -- `t < distance`, first of equal-t triangles wins -- over its own results in leaf
-// order: the same values through the same comparisons as the sequential loop.  All 32 lanes.
+// over the warp: the lanes that hold a leaf publish (owner lane, item index) for each of their triangles in one
+// list, every lane of the warp then tests the pairs p = lane, lane + 32, ... -- triangle id and rows fetched by the
+// tester, so the loads of a round are all in flight together -- with the OWNER's mesh-local origin and ray-space shear
+// (read from shared memory, where the owner left them when it picked the ray up), and the owner replays _trace_leaf's
+// comparison -- `t < distance`, first of equal-t triangles wins -- over its own results in leaf order: the same values
+// through the same comparisons as the sequential loop.  All 32 lanes.
 template <class Stats>
 __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& cs, bool in_leaf, int off, int cnt, double d0, MeshHit* mh,
                                                Stats& stats) {
@@ -323,7 +323,6 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
     const int excl = incl - c;
     const int total = __shfl_sync(RSB_FULL_MASK, incl, 31);
     if (total == 0) return false;
-    const int32_t* items = c > 0 ? sc.meshes[cs.mesh_idx[threadIdx.x]].tree.items + off : nullptr;
     double distance = d0;
     int closest = -1;
     float cu = 0, cv = 0, cw = 0;
@@ -333,15 +332,15 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
         __syncwarp();
         for (int j = j0; j < j1; ++j) {
             const int p = excl + j - base;
-            cs.tri[p] = items[j];
+            cs.item[p] = off + j;
             cs.own[p] = lane;
         }
         __syncwarp();
         const int lim = total - base < RQ_POOL_CAP ? total - base : RQ_POOL_CAP;
         for (int p = lane; p < lim; p += 32) {
             const int ot = tid0 + cs.own[p];      // the owner's thread index within the CTA
-            const int tri = cs.tri[p];
-            const F4* rows = cs.tri_base[ot] + 3 * (size_t)tri;
+            const Mesh& m = sc.meshes[cs.mesh_idx[ot]];
+            const int tri = m.tree.items[cs.item[p]];
             const double* ax = cs.ax0 + ot;
             const V3 o = v3(ax[0], ax[T], ax[2 * T]);
             const double md = ax[9 * T];
@@ -351,7 +350,8 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
             rs.sx = cs.rs_s[ot]; rs.sy = cs.rs_s[T + ot]; rs.sz = cs.rs_s[2 * T + ot];
             float h[4];
             stats.tri_test();
-            const bool hit = mesh_hit_triangle(rows, o, md, rs, h);
+            const bool hit = mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, md, rs, h);
+            cs.item[p] = tri;
             cs.res[p] = hit ? make_float4(h[3], h[0], h[1], h[2]) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
         }
         __syncwarp();
@@ -362,7 +362,7 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
                 const double t = (double)r.x;
                 if (t < distance) {
                     distance = t;
-                    closest = cs.tri[p];
+                    closest = cs.item[p];
                     cu = r.y; cv = r.z; cw = r.w;
                 }
             }
@@ -388,11 +388,20 @@ __device__ __forceinline__ void rq_answer(RqSusp* s, bool hit, const MeshHit& mh
     }
 }
 
+// Mesh.hit for the queries of one round.  Persistent lanes: a lane picks the next query when its own is answered.  Every
+// trip gives each travelling lane a bounded number of node visits, then the triangles of the leaves the lanes hold are
+// tested in one pooled pass.  A lane that reaches a non-empty leaf does not wait for that pass: it PARKS the leaf
+// (offset, count, search distance, node id) and walks on towards its next leaf as if the parked one held no hit -- true
+// for ~90 % of the leaves a ray visits -- and only stops at the following leaf while one is still parked.  When the
+// pooled pass finds a hit in the parked leaf the walk beyond it is simply dropped (MeshData.trace returns at the first
+// leaf with a hit, kdtree3d.pyx:692-700): the answer is the same, a lane just never idles through other lanes' descents.
+// (The counting build walks without looking ahead, so that its counters are exactly the reference's visits.)
 template <bool COUNT>
 __global__ void __launch_bounds__(RQ_THREADS, RQ_MESH_BLOCKS)
 k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int T = RQ_THREADS;
+    constexpr bool AHEAD = !COUNT;
     typedef typename StatsSel<COUNT>::type Stats;
     Stats stats;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -408,23 +417,25 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
     MeshPool cs;
     {
         unsigned char* base = smem + RQ_AX_ROWS * 8 * T + RQ_SCAP * 12 * T;
-        cs.tri_base = reinterpret_cast<const F4**>(base);
-        cs.rs_pack = reinterpret_cast<int32_t*>(base + 8 * T);
-        cs.rs_s = reinterpret_cast<float*>(base + 12 * T);
-        cs.mesh_idx = reinterpret_cast<int32_t*>(base + 24 * T);
-        unsigned char* w = base + 28 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
+        cs.rs_pack = reinterpret_cast<int32_t*>(base);
+        cs.rs_s = reinterpret_cast<float*>(base + 4 * T);
+        cs.mesh_idx = reinterpret_cast<int32_t*>(base + 16 * T);
+        unsigned char* w = base + 20 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
         cs.res = reinterpret_cast<float4*>(w);
-        cs.tri = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
-        cs.own = cs.tri + RQ_POOL_CAP;
+        cs.item = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
+        cs.own = cs.item + RQ_POOL_CAP;
         cs.ax0 = ax0;
     }
     const unsigned int n_q = b.ctr[round];
     const int2* queue = b.queue + (size_t)round * b.cap;
     unsigned int* cursor = b.ctr + 4 + round;
-    enum { IDLE = 0, DESCEND = 1, LEAF = 2 };
+    enum { IDLE = 0, DESCEND = 1, LEAF = 2, END = 3 };   // END: the walk ran out of nodes (a parked leaf may still be open)
     int st = IDLE, q = 0, node = 0, sp = 0, off = 0, cnt = 0;
     double tmin = 0.0, tmax = 0.0, md = 0.0;
     const KdNode* nodes = nullptr;
+    bool parked = false;                                 // a leaf whose triangles are waiting for the pooled pass
+    int p_off = 0, p_cnt = 0, p_node = 0;
+    double p_d0 = 0.0;
     bool exhausted = n_q == 0;
     for (;;) {
         // ---- refill: idle lanes take the next queries, a batch at a time so that the set-up runs with a filled warp
@@ -454,7 +465,6 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
                 cs.rs_pack[tid] = rs.ix | (rs.iy << 2) | (rs.iz << 4);
                 cs.rs_s[tid] = rs.sx; cs.rs_s[T + tid] = rs.sy; cs.rs_s[2 * T + tid] = rs.sz;
                 cs.mesh_idx[tid] = P.mesh;
-                cs.tri_base[tid] = m.tri;
                 KdCursor c;
                 if (kd_begin(m.tree, ax, c)) {
                     nodes = m.tree.nodes;
@@ -473,33 +483,37 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
             if (st == DESCEND) {
                 const int r = kd_visit(nodes, ax, stk, node, sp, tmin, tmax, off, cnt, stats);
                 if (r == VISIT_LEAF) st = LEAF;
-                else if (r == VISIT_DONE) {
-                    MeshHit none;
-                    rq_answer(b.susp + q, false, none);
-                    st = IDLE;
-                }
+                else if (r == VISIT_DONE) st = END;
+            }
+            if (st == LEAF && !parked) {
+                parked = true;
+                p_off = off; p_cnt = cnt; p_node = node;
+                p_d0 = md < tmax ? md : tmax;            // min(ray.max_distance, max_range), mesh.pyx:535
+                if (AHEAD) st = kd_pop(stk, node, sp, tmin, tmax) ? DESCEND : END;
             }
             if (!__any_sync(RSB_FULL_MASK, st == DESCEND)) break;
         }
-        // ---- leaf phase: pooled triangle tests once enough lanes stand at a leaf (or nobody can move)
-        const unsigned at_leaf = __ballot_sync(RSB_FULL_MASK, st == LEAF);
+        // ---- leaf phase: pooled triangle tests once enough lanes hold a leaf (or nobody can move)
+        const unsigned holding = __ballot_sync(RSB_FULL_MASK, parked);
         const unsigned moving = __ballot_sync(RSB_FULL_MASK, st == DESCEND);
-        if (at_leaf != 0 && (__popc(at_leaf) >= RQ_LEAF_MIN || moving == 0)) {
+        if (holding != 0 && (__popc(holding) >= RQ_LEAF_MIN || moving == 0)) {
             MeshHit mh;
-            const double d0 = md < tmax ? md : tmax;     // min(ray.max_distance, max_range), mesh.pyx:535
-            const bool leaf_hit = mesh_leaf_pool(sc, cs, st == LEAF, off, cnt, d0, &mh, stats);
-            if (st == LEAF) {
+            const bool leaf_hit = mesh_leaf_pool(sc, cs, parked, p_off, p_cnt, p_d0, &mh, stats);
+            if (parked) {
+                parked = false;
                 if (leaf_hit) {
-                    mh.node = node;
+                    mh.node = p_node;
                     rq_answer(b.susp + q, true, mh);
                     st = IDLE;
-                } else if (kd_pop(stk, node, sp, tmin, tmax)) {
-                    st = DESCEND;
-                } else {
-                    rq_answer(b.susp + q, false, mh);
-                    st = IDLE;
+                } else if (!AHEAD) {
+                    st = kd_pop(stk, node, sp, tmin, tmax) ? DESCEND : END;
                 }
             }
+        }
+        if (st == END && !parked) {
+            MeshHit none;
+            rq_answer(b.susp + q, false, none);
+            st = IDLE;
         }
     }
     if (COUNT) {
@@ -538,10 +552,14 @@ k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* 
     leaf.best = &rec;
     leaf.stats = &stats;
     unsigned int* cursor = b.ctr + 8;
-    enum { IDLE = 0, DESCEND = 1, LEAF = 2 };
+    constexpr bool AHEAD = !COUNT;                       // walk on past a parked leaf (see k_rq_mesh); the counting build does not
+    enum { IDLE = 0, DESCEND = 1, LEAF = 2, END = 3 };
     int st = IDLE, node = 0, sp = 0, off = 0, cnt = 0;
     long long q = 0;
     double tmin = 0.0, tmax = 0.0;
+    bool parked = false;
+    int p_off = 0, p_cnt = 0, p_node = 0;
+    double p_tmax = 0.0;
     bool exhausted = n <= 0;
     unsigned long long traced = 0;
     for (;;) {
@@ -581,33 +599,38 @@ k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* 
         }
 #pragma unroll 1
         for (int v = 0; v < RQ_VISITS; ++v) {
-            bool done = false;
             if (st == DESCEND) {
                 const int r = kd_visit(sc.world.nodes, leaf.ax, stk, node, sp, tmin, tmax, off, cnt, stats);
                 if (r == VISIT_LEAF) st = LEAF;
-                else if (r == VISIT_DONE) { done = true; st = IDLE; }
+                else if (r == VISIT_DONE) st = END;
             }
-            if (__any_sync(RSB_FULL_MASK, done)) cl.commit(q, done, false, rec);
+            if (st == LEAF && !parked) {
+                parked = true;
+                p_off = off; p_cnt = cnt; p_node = node; p_tmax = tmax;
+                if (AHEAD) st = kd_pop(stk, node, sp, tmin, tmax) ? DESCEND : END;
+            }
             if (!__any_sync(RSB_FULL_MASK, st == DESCEND)) break;
         }
-        const unsigned at_leaf = __ballot_sync(RSB_FULL_MASK, st == LEAF);
+        const unsigned holding = __ballot_sync(RSB_FULL_MASK, parked);
         const unsigned moving = __ballot_sync(RSB_FULL_MASK, st == DESCEND);
-        if (at_leaf != 0 && (__popc(at_leaf) >= RQ_LEAF_MIN || moving == 0)) {
-            bool done = false, hit = false;
-            if (st == LEAF) {
-                if (leaf(off, cnt, tmax)) {
-                    rec.node = node;
+        bool done = false, hit = false;
+        if (holding != 0 && (__popc(holding) >= RQ_LEAF_MIN || moving == 0)) {
+            if (parked) {
+                parked = false;
+                if (leaf(p_off, p_cnt, p_tmax)) {
+                    rec.node = p_node;
                     done = hit = true;
                     st = IDLE;
-                } else if (kd_pop(stk, node, sp, tmin, tmax)) {
-                    st = DESCEND;
-                } else {
-                    done = true;
-                    st = IDLE;
+                } else if (!AHEAD) {
+                    st = kd_pop(stk, node, sp, tmin, tmax) ? DESCEND : END;
                 }
             }
-            cl.commit(q, done, hit, rec);
         }
+        if (st == END && !parked) {
+            done = true;
+            st = IDLE;
+        }
+        if (__any_sync(RSB_FULL_MASK, done)) cl.commit(q, done, hit, rec);
     }
     if (COUNT) {
         __syncwarp();

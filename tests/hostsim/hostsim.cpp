@@ -163,6 +163,22 @@ int hs_contains_batch(uint64_t scene, int64_t n, const double* points, int32_t c
     return 0;
 }
 
+// the state seed(d) leaves: fast = 0 the reference's init_by_array64 restated (Mt19937_64::seed), 1 the 312-step form
+// through the seed-independent table (mt_seed_fast, what k_wf_seed runs)
+int hs_mt_state(uint64_t seed, int32_t fast, uint64_t* out) {
+    if (fast) {
+        uint64_t T[RSB_MT_NN];
+        mt_seed_table(T);
+        mt_seed_fast(T, seed, out);
+    } else {
+        Mt19937_64 g;
+        g.mt = out;
+        g.stride = 1;
+        g.seed(seed);
+    }
+    return 0;
+}
+
 int hs_rng_uniform(uint64_t seed, int64_t n, double* out) {
     std::vector<uint64_t> state(RSB_MT_NN);
     Rng rng;

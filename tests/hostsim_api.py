@@ -41,6 +41,7 @@ def lib():
         _lib.hs_hit_batch_mode.argtypes = [C.c_uint64, C.c_int32, C.c_int64] + [C.c_void_p] * 11
         _lib.hs_contains_batch.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib.hs_rng_uniform.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
+        _lib.hs_mt_state.argtypes = [C.c_uint64, C.c_int32, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_uint64, C.POINTER(cabi.RsbCamera), C.POINTER(cabi.RsbRayConfig),
                                    C.POINTER(cabi.RsbSpectral), C.POINTER(cabi.RsbRngDesc), C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
@@ -187,4 +188,10 @@ class HostScene:
 def rng_uniform(seed, n):
     out = np.zeros(n)
     lib().hs_rng_uniform(int(seed), n, _p(out))
+    return out
+
+
+def mt_state(seed, fast):
+    out = np.zeros(312, dtype=np.uint64)
+    lib().hs_mt_state(int(seed), int(fast), _p(out))
     return out

@@ -21,6 +21,14 @@ def test_rng_known_answers():
     assert g["uniform"][0] == 0.8114659955555504
 
 
+def test_seed_through_the_seed_independent_table_is_init_by_array64(lib):
+    """seed(d) keys init_by_array64 with (0, ..., 0, d): 623 of its 935 steps do not depend on d.  The 312-step form the
+    device seeds its streams with must leave exactly the state of the restated reference algorithm."""
+    hostsim_api.build()
+    for d in (1, 2, 77, 1234567890, 2**63 + 12345, 2**64 - 1, 999 + 5 * 1024 * 1024):
+        np.testing.assert_array_equal(hostsim_api.mt_state(d, 1), hostsim_api.mt_state(d, 0))
+
+
 def test_zoo_hits_contains(make_backend):
     parity.zoo(make_backend)
 

@@ -51,6 +51,16 @@ rendermesh|rendermesh:*)
   A=${S#rendermesh:}; [ "$A" = "rendermesh" ] && A="--pixels 1024 --spp 16"
   A="${A//_/ }"
   timeout 900 python tools_render_mesh.py $A > $O/${TAG}_rendermesh.json 2> $O/${TAG}_rendermesh.err; echo "rendermesh $A"; cut -c1-500 $O/${TAG}_rendermesh.json; tail -n 3 $O/${TAG}_rendermesh.err ;;
+listprism)
+  RSB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -s 300 -c 600 --csv \
+    --log-file $O/${TAG}_prism_launches.csv python tools_render_prism.py --pixels 256 --rays 128 --bins 128 > $O/${TAG}_listprism.log 2>&1; tail -n 2 $O/${TAG}_listprism.log
+  python tools_kernel_summary.py $O/${TAG}_prism_launches.csv > $O/${TAG}_prism_launch_summary.txt 2>&1; cat $O/${TAG}_prism_launch_summary.txt ;;
+prism|prism:*)
+  A=${S#prism:}; [ "$A" = "prism" ] && A=""
+  A="${A//_/ }"
+  for CH in ${PRISM_CHUNKS:-8388608}; do
+    RSB_CHUNK_ITEMS=$CH timeout 900 python tools_render_prism.py $A > $O/${TAG}_prism_$CH.json 2> $O/${TAG}_prism_$CH.err; echo "prism chunk $CH $A"; cut -c1-400 $O/${TAG}_prism_$CH.json; tail -n 2 $O/${TAG}_prism_$CH.err
+  done ;;
 *) echo "unknown step $S" ;;
 esac
 done
