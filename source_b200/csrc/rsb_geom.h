@@ -725,7 +725,15 @@ RSB_HD bool mesh_hit_triangle(const F4* tri, const V3& o, double max_distance, c
     } else {
         if (t > 0.0f || (double)t < max_distance * (double)det) return false;
     }
+    // mesh.pyx:705: the reciprocal is formed in double and rounded to float.  A double holds more than 2 * 24 + 2
+    // significand bits, so that double rounding is the correctly rounded float quotient (Figueroa 1995) as long as the
+    // quotient is a normal float: on the device one IEEE float division replaces the ~40-instruction double one.
+#ifdef __CUDA_ARCH__
+    const float adet = fabsf(det);
+    float det_reciprocal = (adet > 1e-30f && adet < 1e30f) ? __fdiv_rn(1.0f, det) : (float)(1.0 / (double)det);
+#else
     float det_reciprocal = (float)(1.0 / (double)det);
+#endif
     out[0] = u * det_reciprocal;
     out[1] = v * det_reciprocal;
     out[2] = w * det_reciprocal;

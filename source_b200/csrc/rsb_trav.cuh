@@ -26,7 +26,7 @@ namespace rsb {
 
 #define RQ_THREADS RSB_RENDER_THREADS
 #ifndef RQ_SCAP
-#define RQ_SCAP 8            // far-child stack entries kept in shared memory (deeper ones spill to local memory)
+#define RQ_SCAP 10           // far-child stack entries kept in shared memory (deeper ones spill to local memory)
 #endif
 #ifndef RQ_VISITS
 #define RQ_VISITS 6          // node visits per lane per trip
@@ -45,9 +45,6 @@ namespace rsb {
 #endif
 #ifndef RQ_WALK_BLOCKS
 #define RQ_WALK_BLOCKS 4     // k_rq_walk (world-level walk of scenes with meshes)
-#endif
-#ifndef RQ_POOL_CAP
-#define RQ_POOL_CAP 64       // (ray, triangle) pairs a warp tests per pooled round
 #endif
 #define RQ_WORLD_STACK (RSB_KD_STACK / 2)   // world-level far-child entries a parked walk carries: the world half of the stack
 #define RQ_MAX_ROUNDS 2      // Mesh.hit rounds before the last resume finishes whatever is left in place
@@ -287,26 +284,30 @@ k_rq_walk(Scene sc, int n_items, Client cl, RqBuf b, long long n, int round, Dev
 
 // ---- k_rq_mesh --------------------------------------------------------------------------------------------
 struct MeshPool {
-    int32_t* rs_pack;     // [T] ix | iy << 2 | iz << 4 of the lane's ray-space permutation (mesh.pyx:566-610)
-    float* rs_s;          // [3][T] sx, sy, sz
-    int32_t* mesh_idx;    // [T]
-    float4* res;          // warp: [CAP] (t, u, v, w); t = NaN: no hit
-    int32_t* item;        // warp: [CAP] index of the pair's triangle in the mesh's leaf item list; then its triangle id
-    int32_t* own;         // warp: [CAP] lane that owns the pair
-    const double* ax0;    // RayAx storage of thread 0: rows 0..2 mesh-local origin, row 9 ray.max_distance
+    int32_t* rs_pack;      // [T] ix | iy << 2 | iz << 4 of the lane's ray-space permutation (mesh.pyx:566-610)
+    float* rs_s;           // [3][T] sx, sy, sz
+    int32_t* mesh_idx;     // [T]
+    int32_t* lane_of_rank; // warp: [32] k-th lane (in lane order) that holds a leaf
+    const double* ax0;     // RayAx storage of thread 0: rows 0..2 mesh-local origin, row 9 ray.max_distance
 };
 
 #define RQ_AX_ROWS 10
-#define RQ_POOL_WARP_BYTES (RQ_POOL_CAP * 24)
+#define RQ_POOL_WARP_BYTES 128
 #define RQ_MESH_SMEM (RQ_AX_ROWS * 8 * RQ_THREADS + RQ_SCAP * 12 * RQ_THREADS + 20 * RQ_THREADS + (RQ_THREADS / 32) * RQ_POOL_WARP_BYTES)
 
-// MeshData._trace_leaf (mesh.pyx:520-563) for every lane with `in_leaf`, the (ray, triangle) pairs dealt out evenly
-// over the warp: the lanes that hold a leaf publish (owner lane, item index) for each of their triangles in one
-// list, every lane of the warp then tests the pairs p = lane, lane + 32, ... -- triangle id and rows fetched by the
-// tester, so the loads of a round are all in flight together -- with the OWNER's mesh-local origin and ray-space shear
-// (read from shared memory, where the owner left them when it picked the ray up), and the owner replays _trace_leaf's
-// comparison -- `t < distance`, first of equal-t triangles wins -- over its own results in leaf order: the same values
-// through the same comparisons as the sequential loop.  All 32 lanes.
+// MeshData._trace_leaf (mesh.pyx:520-563) for every lane with `in_leaf`, the (ray, triangle) pairs of all those leaves
+// dealt out evenly over the warp, 32 pairs per round, everything in registers and shuffles:
+//   * pair g belongs to the lane whose range [excl, excl + cnt) of the prefix sum brackets it.  The ranges that START
+//     inside the round's window are flagged in one mask (redux.or), so the rank of g's owner among the leaf-holding
+//     lanes is a popcount, and a 32-entry table maps ranks to lanes;
+//   * the tester fetches the triangle and runs _hit_triangle with the OWNER's mesh-local origin, max_distance and
+//     ray-space shear (left in shared memory by the owner when it picked the ray up);
+//   * a segmented min-scan over the lanes of one owner leaves the owner's closest triangle of the round in the last lane
+//     of its segment -- on equal t the EARLIER pair, i.e. the first in leaf order -- and the owner applies the
+//     reference's `t < distance` to it.  Taking the minimum first and comparing once accepts exactly the triangle the
+//     sequential loop ends up with: the loop keeps the first of the smallest t below the starting distance.
+// (Round 2's first version went through shared memory with per-owner loops for the pair list and for the result scan:
+// 22 % of the kernel's warp instructions ran with ~3 of 32 lanes.)  All 32 lanes.
 template <class Stats>
 __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& cs, bool in_leaf, int off, int cnt, double d0, MeshHit* mh,
                                                Stats& stats) {
@@ -323,24 +324,30 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
     const int excl = incl - c;
     const int total = __shfl_sync(RSB_FULL_MASK, incl, 31);
     if (total == 0) return false;
+    const unsigned hold = __ballot_sync(RSB_FULL_MASK, c > 0);
+    __syncwarp();
+    if (c > 0) cs.lane_of_rank[__popc(hold & ((1u << lane) - 1))] = lane;
+    __syncwarp();
+    const float INF = __int_as_float(0x7f800000);
     double distance = d0;
     int closest = -1;
     float cu = 0, cv = 0, cw = 0;
-    for (int base = 0; base < total; base += RQ_POOL_CAP) {
-        const int j0 = base > excl ? base - excl : 0;
-        const int j1 = base + RQ_POOL_CAP - excl < c ? base + RQ_POOL_CAP - excl : c;
-        __syncwarp();
-        for (int j = j0; j < j1; ++j) {
-            const int p = excl + j - base;
-            cs.item[p] = off + j;
-            cs.own[p] = lane;
-        }
-        __syncwarp();
-        const int lim = total - base < RQ_POOL_CAP ? total - base : RQ_POOL_CAP;
-        for (int p = lane; p < lim; p += 32) {
-            const int ot = tid0 + cs.own[p];      // the owner's thread index within the CTA
+    for (int base = 0; base < total; base += 32) {
+        const int g = base + lane;
+        const bool valid = g < total;
+        const int rel = excl - base;
+        const unsigned heads = __reduce_or_sync(RSB_FULL_MASK, (c > 0 && rel >= 0 && rel < 32) ? (1u << rel) : 0u);
+        const int n_before = __popc(__ballot_sync(RSB_FULL_MASK, c > 0 && rel < 0));
+        const int rank = n_before + __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+        const int owner = valid ? cs.lane_of_rank[rank] : lane;
+        const int o_excl = __shfl_sync(RSB_FULL_MASK, excl, owner);
+        const int o_off = __shfl_sync(RSB_FULL_MASK, off, owner);
+        float t = INF, u = 0.f, v = 0.f, w = 0.f;
+        int tri = -1;
+        if (valid) {
+            const int ot = tid0 + owner;           // the owner's thread index within the CTA
             const Mesh& m = sc.meshes[cs.mesh_idx[ot]];
-            const int tri = m.tree.items[cs.item[p]];
+            tri = m.tree.items[o_off + (g - o_excl)];
             const double* ax = cs.ax0 + ot;
             const V3 o = v3(ax[0], ax[T], ax[2 * T]);
             const double md = ax[9 * T];
@@ -350,25 +357,35 @@ __device__ __forceinline__ bool mesh_leaf_pool(const Scene& sc, const MeshPool& 
             rs.sx = cs.rs_s[ot]; rs.sy = cs.rs_s[T + ot]; rs.sz = cs.rs_s[2 * T + ot];
             float h[4];
             stats.tri_test();
-            const bool hit = mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, md, rs, h);
-            cs.item[p] = tri;
-            cs.res[p] = hit ? make_float4(h[3], h[0], h[1], h[2]) : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+            if (mesh_hit_triangle(m.tri + 3 * (size_t)tri, o, md, rs, h)) { t = h[3]; u = h[0]; v = h[1]; w = h[2]; }
         }
-        __syncwarp();
-        for (int j = j0; j < j1; ++j) {
-            const int p = excl + j - base;
-            const float4 r = cs.res[p];
-            if (r.x == r.x) {
-                const double t = (double)r.x;
-                if (t < distance) {
-                    distance = t;
-                    closest = cs.item[p];
-                    cu = r.y; cv = r.z; cw = r.w;
-                }
-            }
+        // segmented inclusive min-scan: lanes of one owner are contiguous
+        const int key = valid ? owner : -1 - lane;
+        float ts = t;
+        int src = lane;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const float t2 = __shfl_up_sync(RSB_FULL_MASK, ts, dlt);
+            const int s2 = __shfl_up_sync(RSB_FULL_MASK, src, dlt);
+            const int k2 = __shfl_up_sync(RSB_FULL_MASK, key, dlt);
+            if (lane >= dlt && k2 == key && t2 <= ts) { ts = t2; src = s2; }
+        }
+        // the owner reads the last lane of its segment in this window
+        int e = -1;
+        if (c > 0 && rel < 32 && rel + c > 0) e = (rel + c < 32 ? rel + c : 32) - 1;
+        const int from = e >= 0 ? e : lane;
+        const float wt = __shfl_sync(RSB_FULL_MASK, ts, from);
+        const int wsrc = __shfl_sync(RSB_FULL_MASK, src, from);
+        const int wtri = __shfl_sync(RSB_FULL_MASK, tri, wsrc);
+        const float wu = __shfl_sync(RSB_FULL_MASK, u, wsrc);
+        const float wv = __shfl_sync(RSB_FULL_MASK, v, wsrc);
+        const float ww = __shfl_sync(RSB_FULL_MASK, w, wsrc);
+        if (e >= 0 && (double)wt < distance) {
+            distance = (double)wt;
+            closest = wtri;
+            cu = wu; cv = wv; cw = ww;
         }
     }
-    __syncwarp();
     if (closest < 0) return false;
     mh->t = (double)(float)distance;
     mh->tri = closest;
@@ -420,10 +437,7 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
         cs.rs_pack = reinterpret_cast<int32_t*>(base);
         cs.rs_s = reinterpret_cast<float*>(base + 4 * T);
         cs.mesh_idx = reinterpret_cast<int32_t*>(base + 16 * T);
-        unsigned char* w = base + 20 * T + (tid >> 5) * RQ_POOL_WARP_BYTES;
-        cs.res = reinterpret_cast<float4*>(w);
-        cs.item = reinterpret_cast<int32_t*>(w + RQ_POOL_CAP * 16);
-        cs.own = cs.item + RQ_POOL_CAP;
+        cs.lane_of_rank = reinterpret_cast<int32_t*>(base + 20 * T + (tid >> 5) * RQ_POOL_WARP_BYTES);
         cs.ax0 = ax0;
     }
     const unsigned int n_q = b.ctr[round];
@@ -552,7 +566,11 @@ k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* 
     leaf.best = &rec;
     leaf.stats = &stats;
     unsigned int* cursor = b.ctr + 8;
-    constexpr bool AHEAD = !COUNT;                       // walk on past a parked leaf (see k_rq_mesh); the counting build does not
+    // Two variations measured SLOWER on the 10,000-sphere field and left out: walking on past a parked leaf as k_rq_mesh does
+    // (951 vs 1045 Mrays/s: a leaf of analytic primitives holds the ray's hit far more often than a mesh leaf, so the
+    // look-ahead is mostly thrown away), and pooling the (ray, item) pairs of the leaf phase over the warp like the
+    // triangle tests (917 vs 1045: 1.3 items per non-empty leaf do not pay for the pool's bookkeeping).
+    constexpr bool AHEAD = false;
     enum { IDLE = 0, DESCEND = 1, LEAF = 2, END = 3 };
     int st = IDLE, node = 0, sp = 0, off = 0, cnt = 0;
     long long q = 0;

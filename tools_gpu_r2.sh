@@ -38,7 +38,8 @@ ncuworld)
   cat $O/${TAG}_ncu_full_k_rq_world.txt ;;
 list)
   timeout 900 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -c 200 --csv \
-    --log-file $O/${TAG}_sweep_launches.csv python tools_sweep.py --n 4e6 --mesh-subdiv 8 --order random > $O/${TAG}_list.log 2>&1; tail -n 2 $O/${TAG}_list.log ;;
+    --log-file $O/${TAG}_sweep_launches.csv python tools_sweep.py --n ${LIST_N:-4e6} --mesh-subdiv 8 --order ${NCU_ORDER:-random} > $O/${TAG}_list.log 2>&1; tail -n 2 $O/${TAG}_list.log
+  python tools_kernel_summary.py $O/${TAG}_sweep_launches.csv > $O/${TAG}_sweep_launch_summary.txt 2>&1; cat $O/${TAG}_sweep_launch_summary.txt ;;
 bench|bench:*)
   A=${S#bench:}; [ "$A" = "bench" ] && A="--steps 2 --warmup 1 --e2e-steps 1"
   A="${A//_/ }"

@@ -92,6 +92,9 @@ if sym:
             a = agg[k]
             a[0] += f(r, "Instructions Executed"); a[1] += f(r, "Thread Instructions Executed"); a[2] += f(r, "# Samples"); a[3] += 1
         ts = sum(a[2] for a in agg.values())
+        print("source lines by executed warp-instructions (lane fill tells where divergence costs):")
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][0])[:40]:
+            print("   %-16s:%-4s static %4d  inst %5.2f%%  samples %5.2f%%  lanes %.1f" % (k[0] if k else "?", k[1] if k else "", a[3], 100 * a[0] / ti, 100 * a[2] / max(ts, 1), a[1] / max(a[0], 1)))
         print("hot source lines (by stall samples):")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][2])[:22]:
             print("   %-16s:%-4s static %4d  inst %5.2f%%  samples %5.2f%%  lanes %.1f" % (k[0] if k else "?", k[1] if k else "", a[3], 100 * a[0] / ti, 100 * a[2] / max(ts, 1), a[1] / max(a[0], 1)))
