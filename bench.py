@@ -313,6 +313,14 @@ def timed_frames(cx, renderer, steps, warmup, seed0):
     rs = cx.device.render_stats()
     per_step = {k: rs[k] for k in ("trace_ms", "shade_ms", "finalize_ms", "regen_ms", "trace_launches")}
     per_step["launches"], per_step["waves"] = launches / steps, waves / steps
+    # the collective alone (N > 1): one more assembly of the frame that is already there
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    e2.record()
+    renderer._assemble()
+    e3.record()
+    cx.barrier()
+    per_step["assemble_ms"] = cx.reduce(e2.elapsed_time(e3), "max")
     return total_ms, int(rays_t.item()), per_step
 
 
@@ -329,7 +337,10 @@ def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kerne
             "algorithmic_bytes_per_launch": alg / launches, "algorithmic_bytes_per_step": alg,
             "whole_step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (total_ms_step * 1e-3) / 1e9,
                            "frac": alg_step / (total_ms_step * 1e-3) / 1e9 / cx.peak},
-            "phases": phase_shares(per_step, total_ms_step), "peak_source": cx.peak_source, "counters": counters}
+            "phases": phase_shares(per_step, total_ms_step), "peak_source": cx.peak_source, "counters": counters,
+            "collective": None if cx.world_size == 1 else {
+                "kind": "one NCCL gather of every rank's own tile rows to rank 0 (distributed.TileGather)",
+                "ms_per_step": per_step["assemble_ms"], "share_of_step": per_step["assemble_ms"] / total_ms_step}}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -351,13 +362,17 @@ def plugin_e2e(cx, w, args, steps):
     cam.observe()                       # warm-up: allocations, kernel loading
     cx.torch.cuda.synchronize()
     eng.ray_count = 0
+    parts = {"flatten_upload_s": 0.0, "render_s": 0.0, "update_s": 0.0}
     t0 = time.perf_counter()
     for _ in range(steps):
         cam.observe()
+        for k in parts:
+            parts[k] += eng.timing.get(k, 0.0) / steps
     dt = time.perf_counter() - t0
+    parts["reference_host_s"] = dt / steps - sum(parts.values())    # observe() outside the engine: task list generation, pipeline set-up
     frame_bytes = w["pixels"] * w["pixels"] * w["bins"] * 20
     return {"value": eng.ray_count / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": w["pixels"] * w["pixels"] * 8 + 8 * w["bins"] * 16,
-            "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": dt / steps,
+            "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": dt / steps, "breakdown": parts,
             "path": "raysect PinholeCamera.observe() -> CudaRenderEngine.run (rsb_render_slice + rsb_slice_update_frame) -> "
                     "SpectralPowerPipeline2D.frame numpy arrays; wall clock"}
 

@@ -666,7 +666,10 @@ __device__ __forceinline__ void wf_append_lists(const WfArgs& a, int list, int s
     }
 }
 
-// 1 thread = 1 slot.  (Persistent lanes with batched refill -- the form k_hit_sweep uses -- were tried here twice.
+// 1 thread = 1 slot.  (Round 2 tried the visit-per-trip walk of rsb_trav.cuh -- k_rq_world with the slots as queries -- in
+// this kernel's place for the Cornell scene: 0.294 vs 0.220 ms per wave, 1,199 vs 1,471 Mrays/s for the frame: a staged
+// 89-node tree is too short a walk to pay for persistent lanes, and the lists it emits are less ordered.)
+// (Persistent lanes with batched refill -- the form k_hit_sweep uses -- were tried here twice.
 // Round-1 first attempt: 208 vs 129 us per 262k-ray wave.  Second attempt, after the kernel had lost its RNG
 // state and most of its instructions: 14.4 instead of 10.9 active lanes per instruction and 18 % fewer warp
 // instructions, yet 143 vs 131 us per 1M-ray wave, and the lists it emits are less ordered, which cost

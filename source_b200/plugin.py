@@ -156,6 +156,7 @@ class CudaRenderEngine(RenderEngine):
         self._accel = None
         self._accel_world = None
         self.ray_count = 0
+        self.timing = {}      # seconds spent in the last run(): flatten + upload, device render, frame update (diagnostics)
 
     def worker_count(self):
         return len(self._devices) if self._devices else 1
@@ -210,9 +211,12 @@ class CudaRenderEngine(RenderEngine):
                 raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D "
                                           "pipelines; %r is host-side post-processing of that spectral frame"
                                           % type(p).__name__)
+        import time
         slice_id, template = render_args[0], render_args[1]
         world = observer.root
+        t0 = time.perf_counter()
         accel = self._accelerator_for(world, slice_id)
+        self.timing = {"flatten_upload_s": time.perf_counter() - t0, "render_s": 0.0, "update_s": 0.0}
         nx, ny = observer.pixels
         if observer.pixel_samples % self.passes:
             raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
@@ -267,20 +271,28 @@ class CudaRenderEngine(RenderEngine):
                                   template.extinction_min_depth, template.max_depth, template.importance_sampling,
                                   template.important_path_weight, template.max_distance)
                 spectrals = [accel.flat.spectral(sl.min_wavelength, sl.max_wavelength, sl.bins) for sl in all_slices]
+                t0 = time.perf_counter()
                 rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes)
+                t1 = time.perf_counter()
                 for p in pipelines:
                     if sens_of(p) == sensitivity:
                         fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
                         accel.update_frame(fm, fv, fs, 0, frame_is_empty=not fs.any())
+                self.timing["render_s"] += t1 - t0
+                self.timing["update_s"] += time.perf_counter() - t1
             elif fast:
                 # one device render per distinct sensitivity, kept on the device and merged into every pipeline frame that
                 # wants it with the reference's combine rule (power.pyx:424-437 -> statsarray.pyx:780-857) -- no per-pixel
                 # Python, no host-side gather / scatter
+                t0 = time.perf_counter()
                 rays = accel.render_slice(cam, cfg, spectral, self.rng_mode, seed, pix, **kw)
+                t1 = time.perf_counter()
                 for p in pipelines:
                     if sens_of(p) == sensitivity:
                         fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
                         accel.update_frame(fm, fv, fs, offset, frame_is_empty=not fs[:, :, offset:offset + template.bins].any())
+                self.timing["render_s"] += t1 - t0
+                self.timing["update_s"] += time.perf_counter() - t1
             elif isinstance(accel, list):
                 mean, variance, rays = self._render_on_devices(
                     accel, pix, 16, lambda a, p: a.render(cam, cfg, a.flat.spectral(
