@@ -335,8 +335,9 @@ def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kerne
             "traffic": None, "kernel": kernel, "kernel_ms": trace_ms / launches, "launches_per_step": per_step["trace_launches"],
             "kernel_ms_per_step": trace_ms, "kernel_share_of_step": trace_ms / total_ms_step,
             "algorithmic_bytes_per_launch": alg / launches, "algorithmic_bytes_per_step": alg,
-            "whole_step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (total_ms_step * 1e-3) / 1e9,
-                           "frac": alg_step / (total_ms_step * 1e-3) / 1e9 / cx.peak},
+            # whole step, per GPU: every rank's share of the frame's algorithmic bytes against the step time
+            "whole_step": {"algorithmic_bytes": alg_step, "achieved": alg_step / cx.world_size / (total_ms_step * 1e-3) / 1e9,
+                           "frac": alg_step / cx.world_size / (total_ms_step * 1e-3) / 1e9 / cx.peak},
             "phases": phase_shares(per_step, total_ms_step), "peak_source": cx.peak_source, "counters": counters,
             "collective": None if cx.world_size == 1 else {
                 "kind": "one NCCL gather of every rank's own tile rows to rank 0 (distributed.TileGather)",

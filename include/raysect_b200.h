@@ -315,6 +315,12 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
 int rsb_slice_read(uint64_t ctx, double* mean, double* variance);
 int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offset, int32_t frame_is_empty,
                            double* frame_mean, double* frame_variance, int32_t* frame_samples);
+/* Page-lock / release a caller-owned host buffer (cudaHostRegister / cudaHostUnregister).  The drop-in engine pins the
+ * pipeline's StatsArray3D buffers from a helper thread while the device renders, so that rsb_slice_update_frame's
+ * copies do not crawl through freshly allocated, never-touched pageable memory.  Pinning an already pinned buffer
+ * and releasing an unpinned one are no-ops. */
+int rsb_host_pin(uint64_t ctx, void* ptr, int64_t bytes);
+int rsb_host_unpin(uint64_t ctx, void* ptr);
 
 /*
  * SpectralPowerPipeline2D.update -> StatsArray3D.combine_samples (power.pyx:424-437, statsarray.pyx:780-857):

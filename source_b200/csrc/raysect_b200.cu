@@ -1256,7 +1256,7 @@ int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, con
     RSB_CUDA(cudaEventRecord(c->ev0, st));
     if (n_pixels > 0) {
         int rc = rsb_render_slices_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels,
-                                       pixels ? c->d_slice_pix : nullptr, c->d_slice, c->d_slice + frame, (uint64_t*)c->d_slice_rays, 1);
+                                       pixels ? c->d_slice_pix : nullptr, c->d_slice, c->d_slice + frame, (uint64_t*)c->d_slice_rays, 0);
         if (rc) return rc;
     }
     RSB_CUDA(cudaEventRecord(c->ev1, st));
@@ -1353,6 +1353,28 @@ int rsb_render_passes(uint64_t ctx, uint64_t scene, const RsbCamera* camera, con
         memcpy(mean + row, m.data() + row, bins * 8);
         memcpy(variance + row, v.data() + row, bins * 8);
     }
+    return RSB_OK;
+}
+
+// Page-lock / release a caller-owned host buffer (cudaHostRegister): the drop-in engine pins the pipeline's frame arrays
+// from a helper thread WHILE the device renders, so that rsb_slice_update_frame's copies run at PCIe speed instead of
+// through the driver's staging of freshly allocated, never-touched pageable memory.
+int rsb_host_pin(uint64_t ctx, void* ptr, int64_t bytes) {
+    Context* c = as_ctx(ctx);
+    if (!c || !ptr || bytes <= 0) return fail(RSB_ERR_ARG, "rsb_host_pin: bad arguments");
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RSB_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RSB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return RSB_OK;
+}
+
+int rsb_host_unpin(uint64_t ctx, void* ptr) {
+    Context* c = as_ctx(ctx);
+    if (!c || !ptr) return fail(RSB_ERR_ARG, "rsb_host_unpin: bad arguments");
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();      // not registered (any more): nothing to release
     return RSB_OK;
 }
 

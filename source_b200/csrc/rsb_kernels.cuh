@@ -691,6 +691,10 @@ __global__ void __launch_bounds__(128, (FEAT & RSB_FEAT_CSG) ? RSB_TRACE_MIN_BLO
     const bool in_range = slot < P;
     const int cs = in_range ? slot : 0;
     const int status = a.st.status[cs];
+    // Sparse waves (the drain at the end of a frame, where a few long paths are left -- a third of the waves of an
+    // 8-GPU frame): a CTA without a live slot leaves before it stages the scene.  9,472 CTAs staging 4.5 KB each were
+    // the floor of a nearly empty wave (0.125 ms for an eighth of the rays of a 0.220 ms wave).
+    if (!__syncthreads_or(in_range && status == SLOT_ALIVE)) return;
     const double normalisation = a.st.norm[cs];
     PathState ps;
     ps.o = v3(a.st.ray[0 * PP + cs], a.st.ray[1 * PP + cs], a.st.ray[2 * PP + cs]);

@@ -234,6 +234,17 @@ class Accelerator:
         self._slice_shape = (camera.nx, camera.ny, config.bins * len(spectrals))
         return rays.value
 
+    def pin(self, *arrays):
+        """page-lock numpy buffers (rsb_host_pin); returns a callable that releases them"""
+        ptrs = [(a.ctypes.data, a.nbytes) for a in arrays if a.nbytes]
+        for ptr, n in ptrs:
+            cabi.check(self.lib.rsb_host_pin(self.device.ctx, C.c_void_p(ptr), n))
+
+        def release():
+            for ptr, _ in ptrs:
+                self.lib.rsb_host_unpin(self.device.ctx, C.c_void_p(ptr))
+        return release
+
     def read_slice(self):
         """(mean, variance) of the slice rendered last, (nx, ny, slice_bins); unlisted pixels are zero"""
         mean = np.zeros(self._slice_shape, dtype=np.float64)

@@ -161,6 +161,52 @@ class CudaRenderEngine(RenderEngine):
     def worker_count(self):
         return len(self._devices) if self._devices else 1
 
+    # -- the pipelines' frame buffers are made ready WHILE the device renders -----------------------------------------
+    # pipeline.initialise() hands every observe() a freshly allocated StatsArray3D when the pipeline does not accumulate:
+    # 1.3 GB of never-touched pageable memory at 1024^2 x 64 bins, into which a device->host copy crawls at ~4 GB/s
+    # (0.30 s of a 2.56 s observe()).  While the render call runs the host has nothing else to do, so helper threads
+    #   * fault the pages of an EMPTY frame in by storing the zeros it already holds (no driver involved: page-locking
+    #     them instead made the copy 10x faster but held a driver lock that cost the concurrent render 0.2 s), or
+    #   * page-lock the buffers of a frame that carries samples -- the accumulating frame of a progressive loop, which
+    #     lives across observe() calls -- once, and keep them locked until another frame shows up.
+    _READY_MIN_BYTES = 64 << 20
+
+    def _frames_ready_start(self, accel, pipelines, empty):
+        import threading
+        arrays = []
+        for p in pipelines:
+            arrays.append((np.asarray(p.frame.mean), empty[id(p)]))
+            arrays.append((np.asarray(p.frame.variance), empty[id(p)]))
+            arrays.append((np.asarray(p.frame.samples), empty[id(p)]))
+        if sum(a.nbytes for a, _ in arrays) < self._READY_MIN_BYTES:
+            return []
+        pinned = getattr(self, "_pinned", {})
+        live = {a.ctypes.data for a, _ in arrays}
+        for ptr in [k for k in pinned if k not in live]:       # frames that are gone: release their locks
+            pinned.pop(ptr)()
+        self._pinned = pinned
+        threads = []
+        for a, is_empty in arrays:
+            if is_empty:
+                th = threading.Thread(target=a.fill, args=(0,))
+            elif hasattr(accel, "pin") and a.ctypes.data not in pinned:
+                def lock(a=a):
+                    try:
+                        pinned[a.ctypes.data] = accel.pin(a)
+                    except Exception:        # an optimisation only: pageable copies still work
+                        pass
+                th = threading.Thread(target=lock)
+            else:
+                continue
+            th.start()
+            threads.append(th)
+        return threads
+
+    @staticmethod
+    def _frames_ready_wait(threads):
+        for th in threads:
+            th.join()
+
     def _accelerator_for(self, world, slice_id):
         # a new observe() starts at slice 0: re-flatten there so scene edits between renders are picked up
         if self._accel is None or self._accel_world is not world or slice_id == 0:
@@ -272,12 +318,15 @@ class CudaRenderEngine(RenderEngine):
                                   template.important_path_weight, template.max_distance)
                 spectrals = [accel.flat.spectral(sl.min_wavelength, sl.max_wavelength, sl.bins) for sl in all_slices]
                 t0 = time.perf_counter()
+                empty = {id(p): not np.asarray(p.frame.samples).any() for p in pipelines}
+                ready = self._frames_ready_start(accel, [p for p in pipelines if sens_of(p) == sensitivity], empty)
                 rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes)
+                self._frames_ready_wait(ready)
                 t1 = time.perf_counter()
                 for p in pipelines:
                     if sens_of(p) == sensitivity:
                         fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
-                        accel.update_frame(fm, fv, fs, 0, frame_is_empty=not fs.any())
+                        accel.update_frame(fm, fv, fs, 0, frame_is_empty=empty[id(p)])
                 self.timing["render_s"] += t1 - t0
                 self.timing["update_s"] += time.perf_counter() - t1
             elif fast:
@@ -285,12 +334,17 @@ class CudaRenderEngine(RenderEngine):
                 # wants it with the reference's combine rule (power.pyx:424-437 -> statsarray.pyx:780-857) -- no per-pixel
                 # Python, no host-side gather / scatter
                 t0 = time.perf_counter()
+                empty = {id(p): not np.asarray(p.frame.samples)[:, :, offset:offset + template.bins].any() for p in pipelines}
+                # zeros may only be stored over a frame that is empty in EVERY slice
+                whole = {id(p): slice_id == 0 and not np.asarray(p.frame.samples).any() for p in pipelines}
+                ready = self._frames_ready_start(accel, [p for p in pipelines if sens_of(p) == sensitivity], whole)
                 rays = accel.render_slice(cam, cfg, spectral, self.rng_mode, seed, pix, **kw)
+                self._frames_ready_wait(ready)
                 t1 = time.perf_counter()
                 for p in pipelines:
                     if sens_of(p) == sensitivity:
                         fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
-                        accel.update_frame(fm, fv, fs, offset, frame_is_empty=not fs[:, :, offset:offset + template.bins].any())
+                        accel.update_frame(fm, fv, fs, offset, frame_is_empty=empty[id(p)])
                 self.timing["render_s"] += t1 - t0
                 self.timing["update_s"] += time.perf_counter() - t1
             elif isinstance(accel, list):

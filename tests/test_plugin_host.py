@@ -110,6 +110,42 @@ def test_render_engine_concurrent_passes_match_repeated_observe(api, reference):
         cam2.observe()
 
 
+def test_frame_buffers_are_prepared_while_the_device_renders(api, reference):
+    """The helper threads that fault in / page-lock the pipeline's frame buffers during the render call (large frames
+    only, so the threshold is lowered here) change nothing: an accumulating pipeline observed twice gives the frame of
+    the same run without them, an empty frame is zero-filled, a frame holding samples is locked once and released when
+    another frame replaces it."""
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(10, 8), bins=8, spectral_rays=2)
+    frames, locks = [], []
+
+    class Backend(hostsim_api.HostScene):
+        def pin(self, *arrays):
+            locks.append(("lock", [a.ctypes.data for a in arrays]))
+            return lambda: locks.append(("release",))
+
+    for threshold in (1 << 60, 0):
+        world = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, world, samples=3, **kw)
+        pipe.accumulate = True
+        eng = CudaRenderEngine(seed=31, rng="mt", backend=Backend)
+        eng._READY_MIN_BYTES = threshold
+        cam.render_engine = eng
+        cam.observe()
+        assert not locks                        # an empty frame is only touched, never locked
+        cam.observe()
+        f = pipe.frame
+        frames.append((np.array(f.mean), np.array(f.variance), np.array(f.samples)))
+        if threshold == 0:
+            assert [l[0] for l in locks] == ["lock"] * 3
+            pipe.accumulate = False             # initialise() now replaces the frame: the old locks are released
+            cam.observe()
+            assert [l[0] for l in locks].count("release") == 3
+    for a, b in zip(*frames):
+        np.testing.assert_array_equal(a, b)
+    assert frames[0][2].max() == 6
+
+
 def test_render_engine_on_real_conductor_and_unity_emitter_objects(api, reference):
     """raysect.optical.material.Conductor / UnitySurfaceEmitter objects flattened from a live Raysect scenegraph"""
     from source_b200.plugin import CudaRenderEngine
