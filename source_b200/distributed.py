@@ -6,6 +6,7 @@ pickled (mean, variance) tuples (raysect/core/workflow.py:123-327); pixel random
 pixel, so the frame does not depend on the number of ranks.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -14,10 +15,14 @@ from .engine import camera_desc, ray_config
 
 
 def tile_pixels(nx, ny, tile, rank, world_size):
-    """Pixels (x, y) of the tiles owned by `rank`: tile t (row-major over the tile grid) -> rank t % world_size."""
+    """Pixels (x, y) of the tiles owned by `rank`: tile (i, j) of the tile grid -> rank (i + j) % world_size, the
+    diagonals of the grid.  (Row-major dealing, t % world_size, hands a rank whole stripes of the image whenever the
+    tile-grid width is a multiple of world_size -- 64 tiles across, 8 ranks: every rank one 16-pixel stripe in eight --
+    and the stripes of a Cornell box do not cost the same.)"""
     tx, ty = (nx + tile - 1) // tile, (ny + tile - 1) // tile
     t = np.arange(tx * ty)
-    mine = t[t % world_size == rank]
+    deal = t if os.environ.get("RSB_TILE_DEAL") == "rowmajor" else t // ty + t % ty
+    mine = t[deal % world_size == rank]
     ox, oy = (mine // ty) * tile, (mine % ty) * tile
     dx, dy = np.meshgrid(np.arange(tile), np.arange(tile), indexing="ij")
     x = (ox[:, None, None] + dx[None]).reshape(-1)
