@@ -347,35 +347,48 @@ def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kerne
 # ----------------------------------------------------------------------------------------------------
 def plugin_e2e(cx, w, args, steps):
     """N = 1: the real drop-in seam.  raysect objects, camera.render_engine = CudaRenderEngine(passes), wall clock around
-    camera.observe(): flatten + upload + render + Pipeline.update into pipeline.frame's numpy arrays."""
+    camera.observe(): flatten + upload + render + Pipeline.update into pipeline.frame's numpy arrays.  Measured twice: with
+    camera.frame_sampler = WholeFrameSampler2D() (the headline: both of the reference's plugin seams filled in) and with
+    the stock FullFrameSampler2D, whose nx*ny-tuple task list the reference builds and shuffles in Python before it calls
+    the engine."""
     from oracle import harness
     if not harness.available():
         return None
     import scenes
     api_ref = harness.ref_api()
-    from source_b200.plugin import CudaRenderEngine
-    world = scenes.cornell_box(api_ref)
-    cam, pipe = scenes.cornell_camera(api_ref, world, pixels=(w["pixels"], w["pixels"]), samples=w["spp"], bins=w["bins"],
-                                      path_weight=RAY_CFG["important_path_weight"])
-    pipe.accumulate = False
-    eng = CudaRenderEngine(seed=1, rng=args.rng, device=cx.device, passes=args.passes)
-    cam.render_engine = eng
-    cam.observe()                       # warm-up: allocations, kernel loading
-    cx.torch.cuda.synchronize()
-    eng.ray_count = 0
-    parts = {"flatten_upload_s": 0.0, "render_s": 0.0, "update_s": 0.0}
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cam.observe()
-        for k in parts:
-            parts[k] += eng.timing.get(k, 0.0) / steps
-    dt = time.perf_counter() - t0
-    parts["reference_host_s"] = dt / steps - sum(parts.values())    # observe() outside the engine: task list generation, pipeline set-up
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
+
+    def measure(sampler):
+        world = scenes.cornell_box(api_ref)
+        cam, pipe = scenes.cornell_camera(api_ref, world, pixels=(w["pixels"], w["pixels"]), samples=w["spp"], bins=w["bins"],
+                                          path_weight=RAY_CFG["important_path_weight"])
+        pipe.accumulate = False
+        if sampler is not None:
+            cam.frame_sampler = sampler
+        eng = CudaRenderEngine(seed=1, rng=args.rng, device=cx.device, passes=args.passes)
+        cam.render_engine = eng
+        cam.observe()                       # warm-up: allocations, kernel loading
+        cx.torch.cuda.synchronize()
+        eng.ray_count = 0
+        parts = {"flatten_upload_s": 0.0, "render_s": 0.0, "update_s": 0.0}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cam.observe()
+            for k in parts:
+                parts[k] += eng.timing.get(k, 0.0) / steps
+        dt = time.perf_counter() - t0
+        parts["reference_host_s"] = dt / steps - sum(parts.values())    # observe() outside the engine: task list generation, pipeline set-up
+        return {"value": eng.ray_count / dt / 1e6, "s_per_step": dt / steps, "breakdown": parts}
+
+    stock = measure(None)
+    whole = measure(WholeFrameSampler2D())
     frame_bytes = w["pixels"] * w["pixels"] * w["bins"] * 20
-    return {"value": eng.ray_count / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": w["pixels"] * w["pixels"] * 8 + 8 * w["bins"] * 16,
-            "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": dt / steps, "breakdown": parts,
-            "path": "raysect PinholeCamera.observe() -> CudaRenderEngine.run (rsb_render_slice + rsb_slice_update_frame) -> "
-                    "SpectralPowerPipeline2D.frame numpy arrays; wall clock"}
+    return {"value": whole["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 8 * w["bins"] * 16,
+            "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": whole["s_per_step"], "breakdown": whole["breakdown"],
+            "path": "raysect PinholeCamera.observe(), camera.render_engine = CudaRenderEngine, camera.frame_sampler = WholeFrameSampler2D "
+                    "-> rsb_render_slices + rsb_slice_update_frame -> SpectralPowerPipeline2D.frame numpy arrays; wall clock",
+            "stock_full_frame_sampler": dict(stock, note="same call with the reference's own FullFrameSampler2D: its Python task list "
+                                                          "(nx*ny tuples, shuffled) is built before the engine is called")}
 
 
 def run_c4(cx, args):

@@ -146,6 +146,34 @@ def test_frame_buffers_are_prepared_while_the_device_renders(api, reference):
     assert frames[0][2].max() == 6
 
 
+@pytest.mark.parametrize("bulk", [True, False])
+def test_whole_frame_sampler_equals_full_frame_sampler(api, reference, bulk):
+    """WholeFrameSampler2D ("every pixel once" as one task) gives the frame of the stock FullFrameSampler2D, on the fast
+    path and on the per-pixel update path; a task made for another frame size is refused."""
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D, WholeFrameTask
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=2)
+    frames = []
+    for sampler in (None, WholeFrameSampler2D()):
+        world = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, world, samples=3, **kw)
+        if sampler is not None:
+            cam.frame_sampler = sampler
+        cam.render_engine = CudaRenderEngine(seed=77, rng="mt", backend=hostsim_api.HostScene, bulk_update=bulk)
+        cam.observe()
+        f = pipe.frame
+        frames.append((np.array(f.mean), np.array(f.variance), np.array(f.samples)))
+    for a, b in zip(*frames):
+        np.testing.assert_array_equal(a, b)
+    assert frames[0][2].min() == 3
+
+    class Wrong(WholeFrameSampler2D):
+        def generate_tasks(self, pixels):
+            return [WholeFrameTask((4, 4))]
+    cam.frame_sampler = Wrong()
+    with pytest.raises(ValueError):
+        cam.observe()
+
+
 def test_render_engine_on_real_conductor_and_unity_emitter_objects(api, reference):
     """raysect.optical.material.Conductor / UnitySurfaceEmitter objects flattened from a live Raysect scenegraph"""
     from source_b200.plugin import CudaRenderEngine

@@ -10,6 +10,11 @@ for k in ("e2e", "e2e_cabi"):
     e = d.get(k)
     if e:
         print("  %-8s %.1f Mrays/s  h2d %s d2h %s  %s" % (k, e["value"], e.get("h2d_bytes_per_step"), e.get("d2h_bytes_per_step"), (e.get("path") or "")[:70]))
+        if e.get("breakdown"):
+            print("           breakdown", {a: round(b, 3) for a, b in e["breakdown"].items()})
+        st = e.get("stock_full_frame_sampler")
+        if st:
+            print("           stock sampler %.1f Mrays/s" % st["value"], {a: round(b, 3) for a, b in st["breakdown"].items()})
 if r:
     print("  roofline %s: %.0f GB/s = %.3f of %.0f; kernel %.3f ms x %.0f = share %.3f; whole step frac %.3f" % (
         r.get("kernel"), r["achieved"], r["frac"], r["peak"], r["kernel_ms"], r["launches_per_step"], r["kernel_share_of_step"], r["whole_step"]["frac"]))
