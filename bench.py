@@ -358,11 +358,14 @@ def plugin_e2e(cx, w, args, steps):
     api_ref = harness.ref_api()
     from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
 
-    def measure(sampler):
+    def measure(sampler, rgb_only=False):
         world = scenes.cornell_box(api_ref)
         cam, pipe = scenes.cornell_camera(api_ref, world, pixels=(w["pixels"], w["pixels"]), samples=w["spp"], bins=w["bins"],
                                           path_weight=RAY_CFG["important_path_weight"])
         pipe.accumulate = False
+        if rgb_only:
+            from raysect.optical.observer import RGBPipeline2D
+            cam.pipelines = [RGBPipeline2D(display_progress=False)]
         if sampler is not None:
             cam.frame_sampler = sampler
         eng = CudaRenderEngine(seed=1, rng=args.rng, device=cx.device, passes=args.passes)
@@ -382,11 +385,18 @@ def plugin_e2e(cx, w, args, steps):
 
     stock = measure(None)
     whole = measure(WholeFrameSampler2D())
+    try:
+        rgb = dict(measure(WholeFrameSampler2D(), rgb_only=True),
+                   note="same frame into an RGBPipeline2D alone (the demos' pipeline): per-sample CIE XYZ projection and statistics on the "
+                        "device (rsb_render_slices_xyz, no spectral frame kept), d2h = the (nx, ny, 3) xyz_frame")
+    except Exception as exc:   # noqa: BLE001
+        rgb = {"failed": repr(exc)}
     frame_bytes = w["pixels"] * w["pixels"] * w["bins"] * 20
     return {"value": whole["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 8 * w["bins"] * 16,
             "d2h_bytes_per_step": frame_bytes + 8, "steps": steps, "s_per_step": whole["s_per_step"], "breakdown": whole["breakdown"],
             "path": "raysect PinholeCamera.observe(), camera.render_engine = CudaRenderEngine, camera.frame_sampler = WholeFrameSampler2D "
                     "-> rsb_render_slices + rsb_slice_update_frame -> SpectralPowerPipeline2D.frame numpy arrays; wall clock",
+            "rgb_pipeline": rgb,
             "stock_full_frame_sampler": dict(stock, note="same call with the reference's own FullFrameSampler2D: its Python task list "
                                                           "(nx*ny tuples, shuffled) is built before the engine is called")}
 

@@ -315,6 +315,26 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
 int rsb_slice_read(uint64_t ctx, double* mean, double* variance);
 int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offset, int32_t frame_is_empty,
                            double* frame_mean, double* frame_variance, int32_t* frame_samples);
+/*
+ * RGBPipeline2D on the device (raysect/optical/observer/pipeline/rgb.pyx:216-290, XYZPixelProcessor rgb.pyx:534-562,
+ * spectrum_to_ciexyz raysect/optical/colour.pyx:158-186).  rsb_render_slices_xyz renders like rsb_render_slices and, for
+ * every sample, also projects the sample's spectrum on the CIE curves -- X = sum over the bins, in index order, of
+ * delta_wavelength[k] * sample[i] * resampled_xyz[k][i][0], likewise Y and Z -- and keeps Welford statistics of
+ * X, Y, Z times the camera's sensitivity per work item (pass, slice, pixel): what XYZPixelProcessor.add_sample /
+ * pack_results produce per pixel task.  resampled_xyz is [n_slices][bins][3] (colour.resample_ciexyz of every slice's
+ * wavelength range), delta_wavelength [n_slices] (Spectrum.delta_wavelength of the slice).  keep_spectral = 0 drops the
+ * per-bin statistics altogether (an observer with RGB pipelines only: no (nx, ny, bins) frame exists anywhere);
+ * otherwise the spectral frame is held exactly as after rsb_render_slices.
+ * rsb_slice_update_xyz_frame is RGBPipeline2D.update + finalise for the listed pixels: per pass, the slices' means and
+ * variances are summed in slice order (rgb.pyx:259-265) and merged into the HOST xyz_frame arrays ((nx, ny, 3) mean /
+ * variance f64, samples i32) with StatsArray3D.combine_samples(samples = pixel_samples), pass after pass.
+ */
+int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+                          const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices,
+                          uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels, const double* resampled_xyz,
+                          const double* delta_wavelength, int32_t keep_spectral, uint64_t* ray_count);
+int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance,
+                               int32_t* xyz_samples);
 /* Page-lock / release a caller-owned host buffer (cudaHostRegister / cudaHostUnregister).  The drop-in engine pins the
  * pipeline's StatsArray3D buffers from a helper thread while the device renders, so that rsb_slice_update_frame's
  * copies do not crawl through freshly allocated, never-touched pageable memory.  Pinning an already pinned buffer

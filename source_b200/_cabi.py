@@ -182,6 +182,10 @@ SIGNATURES = {
     "rsb_render_slices_dev": (C.c_int, [_U64, _U64, _VP, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig),
                                         C.POINTER(RsbSpectral), C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, _VP,
                                         _VP, _VP, _VP, C.c_int32]),
+    "rsb_render_slices_xyz": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
+                                        C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, c_int32_p, c_double_p,
+                                        c_double_p, C.c_int32, c_uint64_p]),
+    "rsb_slice_update_xyz_frame": (C.c_int, [_U64, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "rsb_host_pin": (C.c_int, [_U64, _VP, C.c_int64]),
     "rsb_host_unpin": (C.c_int, [_U64, _VP]),
     "rsb_slice_read": (C.c_int, [_U64, c_double_p, c_double_p]),

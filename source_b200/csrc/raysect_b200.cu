@@ -65,7 +65,18 @@ struct Context {
     int32_t* d_frame_samples = nullptr;
     size_t frame_cap = 0;               // elements
     unsigned long long* d_slice_rays = nullptr;
-    struct { int32_t nx = 0, ny = 0, bins = 0, samples = 0; int64_t n_pixels = 0; bool listed = false, valid = false; } slice;
+    struct {
+        int32_t nx = 0, ny = 0, bins = 0, samples = 0; int64_t n_pixels = 0; bool listed = false, valid = false;
+        bool has_bins = false, has_xyz = false;      // which statistics the render kept (spectral frame / XYZ work items)
+        int32_t n_passes = 0, n_slices = 0, pass_samples = 0;
+    } slice;
+    // RGB side of rsb_render_slices_xyz: curves [n_slices][bins][3] | delta [n_slices] | mean [work items][3] | variance [same];
+    // the (nx, ny, 3) host frames pass through d_xyz_frame (mean | variance) and d_xyz_samples
+    double* d_xyz = nullptr;
+    size_t xyz_cap = 0;                 // doubles
+    double* d_xyz_frame = nullptr;
+    int32_t* d_xyz_samples = nullptr;
+    size_t xyz_frame_cap = 0;           // elements
     unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
     size_t rq_bytes = 0;
     long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
@@ -340,6 +351,9 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_pass);
     cudaFree(c->d_rq);
     cudaFree(c->d_slice);
+    cudaFree(c->d_xyz);
+    cudaFree(c->d_xyz_frame);
+    cudaFree(c->d_xyz_samples);
     cudaFree(c->d_slice_pix);
     cudaFree(c->d_frame);
     cudaFree(c->d_frame_samples);
@@ -845,6 +859,8 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
+    if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * a.sp.bins * sizeof(double);   // and one spectrum row per warp (RGB)
+    if (smem_tables > 200 * 1024) return fail(RSB_ERR_UNSUPPORTED, "rsb_render: too many bins per slice for the RGB projection (shared memory)");
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
     a.wave = 0;
@@ -971,13 +987,35 @@ int rsb_render_passes_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
                                  mean_dev, variance_dev, ray_count_dev, count);
 }
 
+// device-resident XYZ side of a render: curves and per-work-item statistics (see WfArgs)
+struct XyzDev {
+    const double* tab = nullptr;
+    const double* delta = nullptr;
+    double* mean = nullptr;
+    double* variance = nullptr;
+};
+
+static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
+                              const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride,
+                              int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
+                              uint64_t* ray_count_dev, int32_t count, const XyzDev& xyz);
+
 int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
                           const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride,
                           int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
                           uint64_t* ray_count_dev, int32_t count) {
+    if (!mean_dev || !variance_dev) return fail(RSB_ERR_ARG, "rsb_render: null argument");
+    return render_slices_impl(ctx, scene, cuda_stream, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels_dev,
+                              mean_dev, variance_dev, ray_count_dev, count, XyzDev{});
+}
+
+static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
+                              const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride,
+                              int64_t n_pixels, const int32_t* pixels_dev, double* mean_dev, double* variance_dev,
+                              uint64_t* ray_count_dev, int32_t count, const XyzDev& xyz) {
     Context* c = as_ctx(ctx);
     DeviceScene* ds = as_scene(scene);
-    if (!c || !ds || !camera || !config || !spectral || !rng || !mean_dev || !variance_dev || !ray_count_dev)
+    if (!c || !ds || !camera || !config || !spectral || !rng || !ray_count_dev || (!mean_dev != !variance_dev) || (!mean_dev && !xyz.mean))
         return fail(RSB_ERR_ARG, "rsb_render: null argument");
     if (camera->nx < 1 || camera->ny < 1 || camera->pixel_samples < 1) return fail(RSB_ERR_ARG, "rsb_render: bad camera");
     if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC)
@@ -1090,6 +1128,10 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.cam.to_root[12] = 1.0 / camera->to_root_w;
     a.mean = mean_dev;
     a.variance = variance_dev;
+    a.xyz_tab = xyz.tab;
+    a.xyz_delta = xyz.delta;
+    a.xyz_mean = xyz.mean;
+    a.xyz_variance = xyz.variance;
     a.ray_count = (unsigned long long*)ray_count_dev;
     a.work_counter = c->d_scalars;
     a.n_idle = (unsigned int*)(c->d_scalars + 1);
@@ -1106,7 +1148,7 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
     a.n_pix_pass = n_pixels;
     a.pixels = pixels_dev;
     a.frame_elems = (long long)camera->nx * camera->ny * a.frame_bins;
-    if (n_passes > 1) {
+    if (n_passes > 1 && mean_dev) {
         size_t need_pass = (size_t)2 * (size_t)(n_passes - 1) * (size_t)a.frame_elems * sizeof(double);
         if (c->pass_bytes < need_pass) {
             cudaFree(c->d_pass);
@@ -1188,7 +1230,7 @@ int rsb_render_slices_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, const
 #undef RSB_RUN_PX
     }
     if (rc) return rc;
-    if (n_passes > 1) {
+    if (n_passes > 1 && mean_dev) {
         long long total = (long long)n_pixels * a.frame_bins;
         k_pass_combine<<<grid_for(c, total, 256, 8), 256, 0, st>>>(n_pixels, pixels_dev, camera->ny, a.frame_bins, n_passes,
                                                                     camera->pixel_samples, a.frame_elems, a.pass_mean, a.pass_variance,
@@ -1224,23 +1266,46 @@ int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, cons
     return rsb_render_slices(ctx, scene, camera, config, spectral, rng, n_passes, 1, seed_stride, n_pixels, pixels, ray_count);
 }
 
-int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
-                      const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
-                      const int32_t* pixels, uint64_t* ray_count) {
+static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                              const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                              const int32_t* pixels, const double* resampled_xyz, const double* delta_wavelength, bool keep_spectral,
+                              uint64_t* ray_count) {
     Context* c = as_ctx(ctx);
     if (!c || !as_scene(scene) || !camera || !config || !ray_count) return fail(RSB_ERR_ARG, "rsb_render_slice: null argument");
     if (n_slices < 1) return fail(RSB_ERR_ARG, "rsb_render_slices: the number of slices must be at least 1");
+    if (n_passes < 1) return fail(RSB_ERR_ARG, "rsb_render_passes: the number of passes must be in [1, 1024]");
+    if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
+    const bool want_xyz = resampled_xyz != nullptr;
+    if (want_xyz && !delta_wavelength) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: null argument");
+    if (!want_xyz && !keep_spectral) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: nothing to render (no XYZ curves, no spectral frame)");
     RSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     c->slice.valid = false;
     const size_t frame = (size_t)camera->nx * camera->ny * config->bins * n_slices;
     if (!pixels) n_pixels = (int64_t)camera->nx * camera->ny;
     if (n_pixels < 0) return fail(RSB_ERR_ARG, "rsb_render_slice: negative pixel count");
-    if (c->slice_cap < 2 * frame) {
+    if (keep_spectral && c->slice_cap < 2 * frame) {
         cudaFree(c->d_slice);
         c->d_slice = nullptr; c->slice_cap = 0;
         RSB_CUDA(cudaMalloc(&c->d_slice, 2 * frame * sizeof(double)));
         c->slice_cap = 2 * frame;
+    }
+    XyzDev xyz;
+    if (want_xyz) {
+        const size_t n_tab = (size_t)n_slices * config->bins * 3, n_work = (size_t)n_pixels * n_passes * n_slices;
+        const size_t need = n_tab + (size_t)n_slices + 2 * 3 * n_work;
+        if (c->xyz_cap < need) {
+            cudaFree(c->d_xyz);
+            c->d_xyz = nullptr; c->xyz_cap = 0;
+            RSB_CUDA(cudaMalloc(&c->d_xyz, std::max<size_t>(1, need) * sizeof(double)));
+            c->xyz_cap = need;
+        }
+        RSB_CUDA(cudaMemcpyAsync(c->d_xyz, resampled_xyz, n_tab * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(c->d_xyz + n_tab, delta_wavelength, (size_t)n_slices * 8, cudaMemcpyHostToDevice, st));
+        xyz.tab = c->d_xyz;
+        xyz.delta = c->d_xyz + n_tab;
+        xyz.mean = c->d_xyz + n_tab + n_slices;
+        xyz.variance = xyz.mean + 3 * n_work;
     }
     if (!c->d_slice_rays) RSB_CUDA(cudaMalloc(&c->d_slice_rays, 8));
     if (pixels && c->slice_pix_cap < (size_t)n_pixels) {
@@ -1251,12 +1316,13 @@ int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, con
     }
     RSB_CUDA(cudaMemsetAsync(c->d_slice_rays, 0, 8, st));
     // unlisted pixels of the slice read as zero
-    RSB_CUDA(cudaMemsetAsync(c->d_slice, 0, 2 * frame * sizeof(double), st));
+    if (keep_spectral) RSB_CUDA(cudaMemsetAsync(c->d_slice, 0, 2 * frame * sizeof(double), st));
     if (pixels && n_pixels > 0) RSB_CUDA(cudaMemcpyAsync(c->d_slice_pix, pixels, (size_t)n_pixels * 8, cudaMemcpyHostToDevice, st));
     RSB_CUDA(cudaEventRecord(c->ev0, st));
     if (n_pixels > 0) {
-        int rc = rsb_render_slices_dev(ctx, scene, st, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels,
-                                       pixels ? c->d_slice_pix : nullptr, c->d_slice, c->d_slice + frame, (uint64_t*)c->d_slice_rays, 0);
+        int rc = render_slices_impl(ctx, scene, st, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels,
+                                    pixels ? c->d_slice_pix : nullptr, keep_spectral ? c->d_slice : nullptr,
+                                    keep_spectral ? c->d_slice + frame : nullptr, (uint64_t*)c->d_slice_rays, 0, xyz);
         if (rc) return rc;
     }
     RSB_CUDA(cudaEventRecord(c->ev1, st));
@@ -1269,14 +1335,74 @@ int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, con
     c->slice.samples = camera->pixel_samples * n_passes;
     c->slice.n_pixels = n_pixels;
     c->slice.listed = pixels != nullptr;
+    c->slice.has_bins = keep_spectral;
+    c->slice.has_xyz = want_xyz;
+    c->slice.n_passes = n_passes; c->slice.n_slices = n_slices; c->slice.pass_samples = camera->pixel_samples;
     c->slice.valid = true;
+    return RSB_OK;
+}
+
+int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                      const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                      const int32_t* pixels, uint64_t* ray_count) {
+    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, nullptr, nullptr,
+                              true, ray_count);
+}
+
+int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                          const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                          const int32_t* pixels, const double* resampled_xyz, const double* delta_wavelength, int32_t keep_spectral,
+                          uint64_t* ray_count) {
+    if (!resampled_xyz || !delta_wavelength) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: null argument");
+    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, resampled_xyz,
+                              delta_wavelength, keep_spectral != 0, ray_count);
+}
+
+int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance, int32_t* xyz_samples) {
+    Context* c = as_ctx(ctx);
+    if (!c || !xyz_mean || !xyz_variance || !xyz_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_xyz_frame: null argument");
+    if (!c->slice.valid || !c->slice.has_xyz)
+        return fail(RSB_ERR_ARG, "rsb_slice_update_xyz_frame: no rendered XYZ statistics are held (call rsb_render_slices_xyz first)");
+    if (c->slice.n_pixels == 0) return RSB_OK;
+    RSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t elems = (size_t)c->slice.nx * c->slice.ny * 3;
+    if (c->xyz_frame_cap < elems) {
+        cudaFree(c->d_xyz_frame); cudaFree(c->d_xyz_samples);
+        c->d_xyz_frame = nullptr; c->d_xyz_samples = nullptr; c->xyz_frame_cap = 0;
+        RSB_CUDA(cudaMalloc(&c->d_xyz_frame, 2 * elems * sizeof(double)));
+        RSB_CUDA(cudaMalloc(&c->d_xyz_samples, elems * sizeof(int32_t)));
+        c->xyz_frame_cap = elems;
+    }
+    double* d_fm = c->d_xyz_frame;
+    double* d_fv = c->d_xyz_frame + elems;
+    if (frame_is_empty) {
+        RSB_CUDA(cudaMemsetAsync(d_fm, 0, 2 * elems * sizeof(double), st));
+        RSB_CUDA(cudaMemsetAsync(c->d_xyz_samples, 0, elems * sizeof(int32_t), st));
+    } else {
+        RSB_CUDA(cudaMemcpyAsync(d_fm, xyz_mean, elems * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(d_fv, xyz_variance, elems * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(c->d_xyz_samples, xyz_samples, elems * 4, cudaMemcpyHostToDevice, st));
+    }
+    const size_t n_tab = (size_t)c->slice.bins * 3;     // slice.bins = n_slices * bins per slice
+    const size_t n_work = (size_t)c->slice.n_pixels * c->slice.n_passes * c->slice.n_slices;
+    const double* wm = c->d_xyz + n_tab + c->slice.n_slices;
+    const double* wv = wm + 3 * n_work;
+    k_xyz_combine<<<grid_for(c, (long long)c->slice.n_pixels * 3, 256, 4), 256, 0, st>>>(
+        c->slice.n_pixels, c->slice.listed ? c->d_slice_pix : nullptr, c->slice.ny, c->slice.n_passes, c->slice.n_slices, c->slice.pass_samples,
+        wm, wv, d_fm, d_fv, c->d_xyz_samples);
+    RSB_CUDA(cudaGetLastError());
+    RSB_CUDA(cudaMemcpyAsync(xyz_mean, d_fm, elems * 8, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpyAsync(xyz_variance, d_fv, elems * 8, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpyAsync(xyz_samples, c->d_xyz_samples, elems * 4, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaStreamSynchronize(st));
     return RSB_OK;
 }
 
 int rsb_slice_read(uint64_t ctx, double* mean, double* variance) {
     Context* c = as_ctx(ctx);
     if (!c || !mean || !variance) return fail(RSB_ERR_ARG, "rsb_slice_read: null argument");
-    if (!c->slice.valid) return fail(RSB_ERR_ARG, "rsb_slice_read: no rendered slice is held (call rsb_render_slice first)");
+    if (!c->slice.valid || !c->slice.has_bins) return fail(RSB_ERR_ARG, "rsb_slice_read: no rendered slice is held (call rsb_render_slice first)");
     RSB_CUDA(cudaSetDevice(c->device));
     const size_t frame = (size_t)c->slice.nx * c->slice.ny * c->slice.bins;
     RSB_CUDA(cudaMemcpyAsync(mean, c->d_slice, frame * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1289,7 +1415,8 @@ int rsb_slice_update_frame(uint64_t ctx, int32_t frame_bins, int32_t slice_offse
                            double* frame_variance, int32_t* frame_samples) {
     Context* c = as_ctx(ctx);
     if (!c || !frame_mean || !frame_variance || !frame_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_frame: null argument");
-    if (!c->slice.valid) return fail(RSB_ERR_ARG, "rsb_slice_update_frame: no rendered slice is held (call rsb_render_slice first)");
+    if (!c->slice.valid || !c->slice.has_bins)
+        return fail(RSB_ERR_ARG, "rsb_slice_update_frame: no rendered slice is held (call rsb_render_slice first)");
     const int nx = c->slice.nx, ny = c->slice.ny, sb = c->slice.bins;
     if (slice_offset < 0 || slice_offset + sb > frame_bins)
         return fail(RSB_ERR_ARG, "The slice offset plus the bin count extends beyond the full bin count.");

@@ -399,6 +399,13 @@ struct WfArgs {
     double* pass_mean;          // [n_passes - 1][frame_elems] frames of passes 1.., merged by k_pass_combine
     double* pass_variance;
     long long frame_elems;      // nx * ny * bins
+    // RGBPipeline2D (rgb.pyx:216-290): every sample's spectrum is also projected on the CIE XYZ curves and the three
+    // tristimulus values get their own per-work-item Welford statistics.  Null xyz_mean = no RGB pipeline; null mean = no
+    // spectral pipeline (the per-bin statistics are then not kept at all).
+    const double* xyz_tab;      // [n_slices][bins][3]: resample_ciexyz of every slice's wavelength range
+    const double* xyz_delta;    // [n_slices]: Spectrum.delta_wavelength of every slice
+    double* xyz_mean;           // [work items][3], work item g = group * n_pix_pass + task (group = pass * n_slices + slice)
+    double* xyz_variance;
     unsigned long long seed_stride;   // pass p draws from streams seeded seed + p * seed_stride + y * nx + x
     int32_t n_passes;
     int32_t n_slices;           // spectral slices rendered concurrently; `sp` describes slice 0, slice k follows at strides
@@ -880,6 +887,9 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     }
     // 32 log entries per warp, staged in shared memory and read back as one broadcast LDS.128 per entry
     LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;
+    // RGB: the sample's spectrum, one row of `bins` doubles per warp, behind the log windows
+    double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * sp.bins;
+    const bool keep_bins = a.mean != nullptr, keep_xyz = a.xyz_mean != nullptr;
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
     const unsigned int n = a.st.n_ended[par];
@@ -903,8 +913,8 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         const int slice = a.n_slices > 1 ? group % a.n_slices : 0;
         size_t row = ((size_t)a.st.px[slot] * a.cam.ny + a.st.py[slot]) * a.frame_bins + (size_t)slice * bins;
         const Spectral sps = a.n_slices > 1 ? wf_slice_spectral(sp, slice) : sp;
-        double* m = (pass ? a.pass_mean + (size_t)(pass - 1) * a.frame_elems : a.mean) + row;
-        double* v = (pass ? a.pass_variance + (size_t)(pass - 1) * a.frame_elems : a.variance) + row;
+        double* m = keep_bins ? (pass ? a.pass_mean + (size_t)(pass - 1) * a.frame_elems : a.mean) + row : nullptr;
+        double* v = keep_bins ? (pass ? a.pass_variance + (size_t)(pass - 1) * a.frame_elems : a.variance) + row : nullptr;
         const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
         // (with emitting volumes in the scene a path that ended dark may still carry what they added on the way)
         const bool emit = status == SLOT_ENDED_EMIT || (a.has_additive && a.st.additive[slot] != 0);
@@ -914,7 +924,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             const int ba = b0 + lane, bb = b0 + 32 + lane;
             const bool ha = ba < bins, hb = bb < bins;
             double ma = 0, va = 0, mb = 0, vb = 0;
-            if (s > 0) {
+            if (s > 0 && keep_bins) {
                 if (ha) { ma = m[ba]; va = v[ba]; }
                 if (hb) { mb = m[bb]; vb = v[bb]; }
             }
@@ -936,15 +946,72 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (ha) {
                 double x = xa * w;              // spectrum.mul_scalar(projection_weight), observer.pyx:408
-                x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
-                welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
+                if (keep_xyz) wspec[ba] = x;
+                if (keep_bins) {
+                    x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
+                    welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
+                }
             }
             if (hb) {
                 double x = xb * w;
-                x = x * a.cam.sensitivity;
-                welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
+                if (keep_xyz) wspec[bb] = x;
+                if (keep_bins) {
+                    x = x * a.cam.sensitivity;
+                    welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
+                }
             }
         }
+        if (keep_xyz) {
+            // XYZPixelProcessor.add_sample (rgb.pyx:550-558): spectrum_to_ciexyz sums delta * sample * curve over the bins
+            // in index order (colour.pyx:178-186) -- a serial chain, so lanes 0..2 walk one curve each -- then the
+            // tristimulus value times the sensitivity enters the channel's running statistics
+            __syncwarp();
+            if (lane < 3) {
+                const double delta = a.xyz_delta[slice];
+                const double* curve = a.xyz_tab + ((size_t)slice * bins) * 3 + lane;
+                double acc = 0.0;
+                for (int i = 0; i < bins; ++i) acc += delta * wspec[i] * __ldg(curve + 3 * i);
+                const size_t item = ((size_t)a.item_base + (size_t)a.st.work[slot]) * 3 + lane;
+                double pm = 0, pv = 0;
+                if (s > 0) { pm = a.xyz_mean[item]; pv = a.xyz_variance[item]; }
+                welford_add_r(acc * a.cam.sensitivity, pm, pv, s, r_nn, r_nn1, a.xyz_mean + item, a.xyz_variance + item);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// RGBPipeline2D.update + finalise for every listed pixel (rgb.pyx:249-290): the per-slice (mean, variance) of a pass are
+// summed in slice order into the pass's working values, which are merged into the frame with combine_samples; the passes
+// of a pixel are merged in order by the same thread, one thread per (pixel, channel).
+__global__ void k_xyz_combine(long long n_pixels, const int32_t* __restrict__ pixels, int ny, int n_passes, int n_slices, int samples,
+                              const double* __restrict__ xyz_mean, const double* __restrict__ xyz_variance,
+                              double* __restrict__ fmean, double* __restrict__ fvar, int32_t* __restrict__ fsamples) {
+    long long total = n_pixels * 3;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        long long p = i / 3;
+        int ch = (int)(i % 3);
+        long long row = pixels ? ((long long)pixels[2 * p] * ny + pixels[2 * p + 1]) : p;
+        long long dst = row * 3 + ch;
+        double fm = fmean[dst], fv = fvar[dst];
+        int fn = fsamples[dst];
+        for (int pass = 0; pass < n_passes; ++pass) {
+            double wm = 0.0, wv = 0.0;
+            for (int k = 0; k < n_slices; ++k) {
+                long long src = (((long long)pass * n_slices + k) * n_pixels + p) * 3 + ch;
+                wm += xyz_mean[src];
+                wv += xyz_variance[src];
+            }
+            if (wv < 0) wv = 0;   // statsarray.pyx:647-650
+            double mt, vt;
+            int nt;
+            stats_combine(fm, fv, fn, wm, wv, samples, &mt, &vt, &nt);
+            fm = mt; fv = vt; fn = nt;
+        }
+        fmean[dst] = fm;
+        fvar[dst] = fv;
+        fsamples[dst] = fn;
     }
 }
 

@@ -212,12 +212,18 @@ class Accelerator:
         self._slice_shape = (camera.nx, camera.ny, config.bins)
         return rays.value
 
-    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None):
+    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None, xyz=None,
+                      keep_spectral=True):
         """Every spectral slice of an observe() in one call (rsb_render_slices): ``spectrals`` = one RsbSpectral per
         slice (all with ``config.bins`` bins); slice k of pass p draws from the streams seeded
         ``seed + (p*len(spectrals) + k)*seed_stride + y*nx + x`` (``seed_stride`` defaults to nx*ny: the per-slice seeds
         of the engine / mirror camera).  The frame with ``len(spectrals)*config.bins`` bins per pixel stays on the device
-        as the held slice; returns the ray count."""
+        as the held slice; returns the ray count.
+
+        ``xyz`` = (resampled_xyz, delta_wavelength) -- ``(n_slices, bins, 3)`` CIE curves resampled on every slice's range
+        (colour.resample_ciexyz) and every slice's Spectrum.delta_wavelength -- also keeps what RGBPipeline2D's pixel
+        processors would (rsb_render_slices_xyz), for ``update_xyz_frame``; ``keep_spectral=False`` then drops the per-bin
+        frame."""
         rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
         rays = C.c_uint64(0)
         pix, n = None, camera.nx * camera.ny
@@ -228,11 +234,34 @@ class Accelerator:
         for k, sp in enumerate(spectrals):
             C.memmove(C.byref(arr[k]), C.byref(sp), C.sizeof(cabi.RsbSpectral))
         stride = camera.nx * camera.ny if seed_stride is None else int(seed_stride)
-        cabi.check(self.lib.rsb_render_slices(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
-                                              int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32), C.byref(rays)))
+        if xyz is None:
+            if not keep_spectral:
+                raise ValueError("nothing to render: no XYZ curves and no spectral frame")
+            cabi.check(self.lib.rsb_render_slices(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
+                                                  int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32), C.byref(rays)))
+        else:
+            curves = np.ascontiguousarray(xyz[0], dtype=np.float64)
+            delta = np.ascontiguousarray(xyz[1], dtype=np.float64).reshape(-1)
+            if curves.shape != (len(spectrals), config.bins, 3) or delta.shape != (len(spectrals),):
+                raise ValueError("xyz must be ((n_slices, bins, 3) curves, (n_slices,) delta_wavelength)")
+            cabi.check(self.lib.rsb_render_slices_xyz(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
+                                                      int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32),
+                                                      cabi.ptr(curves, C.c_double), cabi.ptr(delta, C.c_double), int(bool(keep_spectral)),
+                                                      C.byref(rays)))
         self._keep = list(spectrals)      # the tables the descriptors point at must outlive the call
         self._slice_shape = (camera.nx, camera.ny, config.bins * len(spectrals))
         return rays.value
+
+    def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
+        """RGBPipeline2D.update + finalise for every listed pixel of the render done last with ``xyz=``: merges its XYZ
+        statistics into the HOST ``xyz_frame`` arrays ((nx, ny, 3) StatsArray3D buffers, modified in place) on the device
+        (rsb_slice_update_xyz_frame)."""
+        shape = self._slice_shape[:2] + (3,)
+        for a, dt in ((xyz_mean, np.float64), (xyz_variance, np.float64), (xyz_samples, np.int32)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable and a.shape == shape):
+                raise TypeError("xyz frame arrays must be writable C-contiguous (nx, ny, 3) float64 / int32 numpy arrays")
+        cabi.check(self.lib.rsb_slice_update_xyz_frame(self.device.ctx, int(bool(frame_is_empty)), cabi.ptr(xyz_mean, C.c_double),
+                                                       cabi.ptr(xyz_variance, C.c_double), cabi.ptr(xyz_samples, C.c_int32)))
 
     def pin(self, *arrays):
         """page-lock numpy buffers (rsb_host_pin); returns a callable that releases them"""

@@ -188,13 +188,14 @@ class CudaRenderEngine(RenderEngine):
     #     lives across observe() calls -- once, and keep them locked until another frame shows up.
     _READY_MIN_BYTES = 64 << 20
 
-    def _frames_ready_start(self, accel, pipelines, empty):
+    def _frames_ready_start(self, accel, pipelines, empty, frame_of):
         import threading
         arrays = []
         for p in pipelines:
-            arrays.append((np.asarray(p.frame.mean), empty[id(p)]))
-            arrays.append((np.asarray(p.frame.variance), empty[id(p)]))
-            arrays.append((np.asarray(p.frame.samples), empty[id(p)]))
+            f = frame_of(p)
+            arrays.append((np.asarray(f.mean), empty[id(p)]))
+            arrays.append((np.asarray(f.variance), empty[id(p)]))
+            arrays.append((np.asarray(f.samples), empty[id(p)]))
         if sum(a.nbytes for a, _ in arrays) < self._READY_MIN_BYTES:
             return []
         pinned = getattr(self, "_pinned", {})
@@ -262,7 +263,7 @@ class CudaRenderEngine(RenderEngine):
         return mean, variance, rays
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import (OrthographicCamera, PinholeCamera, SpectralPowerPipeline2D,
+        from raysect.optical.observer import (OrthographicCamera, PinholeCamera, RGBPipeline2D, SpectralPowerPipeline2D,
                                               SpectralRadiancePipeline2D)
         observer = getattr(render, "__self__", None)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera)):
@@ -270,10 +271,13 @@ class CudaRenderEngine(RenderEngine):
                                       "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
-            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D)):
-                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D "
-                                          "pipelines; %r is host-side post-processing of that spectral frame"
-                                          % type(p).__name__)
+            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D)):
+                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D / RGBPipeline2D "
+                                          "pipelines; got %r (no CPU fallback)" % type(p).__name__)
+        rgb = [p for p in pipelines if isinstance(p, RGBPipeline2D)]
+
+        def frame_of(p):
+            return p.xyz_frame if isinstance(p, RGBPipeline2D) else p.frame
         import time
         slice_id, template = render_args[0], render_args[1]
         world = observer.root
@@ -322,10 +326,15 @@ class CudaRenderEngine(RenderEngine):
         # (rsb_render_slices; slice k draws from the seeds the per-slice path uses) and merges the whole frame into the
         # pipelines; the run() calls for slices 1.. find their work done.
         all_slices = None
-        if fast and n_slices > 1 and hasattr(accel, "render_slices"):
+        if fast and (n_slices > 1 or rgb) and hasattr(accel, "render_slices"):
             spec = observer._slice_spectrum()
             if len({sl.bins for sl in spec}) == 1:
                 all_slices = spec
+        if rgb and all_slices is None:
+            # XYZPixelProcessor's per-sample projection (rgb.pyx:550-558) runs inside the device's accumulate kernel and the
+            # slices of a pixel are summed before they enter the frame (rgb.pyx:259-265): the all-slices device path only
+            raise NotImplementedError("RGBPipeline2D needs CudaRenderEngine's whole-slice device path: bulk_update=True, one device, "
+                                      "spectral slices of equal size (spectral_bins divisible by spectral_rays)")
         if all_slices is not None and slice_id > 0:
             if slice_id == n_slices - 1:
                 self.seed += self.passes * n_slices * nx * ny
@@ -339,14 +348,26 @@ class CudaRenderEngine(RenderEngine):
                                   template.important_path_weight, template.max_distance)
                 spectrals = [accel.flat.spectral(sl.min_wavelength, sl.max_wavelength, sl.bins) for sl in all_slices]
                 t0 = time.perf_counter()
-                empty = {id(p): not np.asarray(p.frame.samples).any() for p in pipelines}
-                ready = self._frames_ready_start(accel, [p for p in pipelines if sens_of(p) == sensitivity], empty)
-                rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes)
+                group = [p for p in pipelines if sens_of(p) == sensitivity]
+                empty = {id(p): not np.asarray(frame_of(p).samples).any() for p in group}
+                ready = self._frames_ready_start(accel, group, empty, frame_of)
+                xyz = None
+                if any(p in rgb for p in group):
+                    # what RGBPipeline2D.initialise hands its pixel processors (rgb.pyx:232-233), and the delta_wavelength
+                    # of the slice's Spectrum (spectrum.pyx: (max - min) / bins)
+                    from raysect.optical.colour import resample_ciexyz
+                    xyz = (np.stack([np.asarray(resample_ciexyz(sl.min_wavelength, sl.max_wavelength, sl.bins)) for sl in all_slices]),
+                           np.array([(sl.max_wavelength - sl.min_wavelength) / sl.bins for sl in all_slices]))
+                xkw = dict(xyz=xyz, keep_spectral=any(p not in rgb for p in group)) if xyz is not None else {}
+                rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes, **xkw)
                 self._frames_ready_wait(ready)
                 t1 = time.perf_counter()
-                for p in pipelines:
-                    if sens_of(p) == sensitivity:
-                        fm, fv, fs = np.asarray(p.frame.mean), np.asarray(p.frame.variance), np.asarray(p.frame.samples)
+                for p in group:
+                    f = frame_of(p)
+                    fm, fv, fs = np.asarray(f.mean), np.asarray(f.variance), np.asarray(f.samples)
+                    if p in rgb:
+                        accel.update_xyz_frame(fm, fv, fs, frame_is_empty=empty[id(p)])
+                    else:
                         accel.update_frame(fm, fv, fs, 0, frame_is_empty=empty[id(p)])
                 self.timing["render_s"] += t1 - t0
                 self.timing["update_s"] += time.perf_counter() - t1
@@ -358,7 +379,7 @@ class CudaRenderEngine(RenderEngine):
                 empty = {id(p): not np.asarray(p.frame.samples)[:, :, offset:offset + template.bins].any() for p in pipelines}
                 # zeros may only be stored over a frame that is empty in EVERY slice
                 whole = {id(p): slice_id == 0 and not np.asarray(p.frame.samples).any() for p in pipelines}
-                ready = self._frames_ready_start(accel, [p for p in pipelines if sens_of(p) == sensitivity], whole)
+                ready = self._frames_ready_start(accel, [p for p in pipelines if sens_of(p) == sensitivity], whole, frame_of)
                 rays = accel.render_slice(cam, cfg, spectral, self.rng_mode, seed, pix, **kw)
                 self._frames_ready_wait(ready)
                 t1 = time.perf_counter()

@@ -193,7 +193,9 @@ int hs_rng_uniform(uint64_t seed, int64_t n, double* out) {
 // serial equivalent of k_render (same per-pixel stream definition, same per-bin arithmetic)
 int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
               const RsbRngDesc* rngd, int64_t n_pixels, const int32_t* pixels, double* mean, double* variance,
-              uint64_t* ray_count, uint64_t* counters /* optional: branches, leaves, items, prim_tests, tri_tests, paths, segments */) {
+              uint64_t* ray_count, uint64_t* counters /* optional: branches, leaves, items, prim_tests, tri_tests, paths, segments */,
+              const double* xyz_curves /* optional [bins][3] */, double xyz_delta, double* xyz_mean /* [n_pixels][3], per task */,
+              double* xyz_variance) {
     HostScene* h = reinterpret_cast<HostScene*>(scene);
     int nm = (int)h->ps.mat_type.size();
     if (spectral->n_materials != nm) { g_err = "spectral tables do not match the scene's materials"; return RSB_ERR_ARG; }
@@ -284,13 +286,18 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
             *ray_count += rays;
             paths += 1;
             segments += rays;
+            double tri[3] = {0.0, 0.0, 0.0};
             for (int b = 0; b < bins; ++b) {
                 double x = 0.0;
                 if (res == PATH_EMITTED) x = replay_bin(log, sp, b);
                 x = x * weight;
+                if (xyz_curves)
+                    for (int ch = 0; ch < 3; ++ch) tri[ch] += xyz_delta * x * xyz_curves[3 * b + ch];
                 x = x * cam.sensitivity;
                 welford_add(x, m + b, v + b, s);
             }
+            if (xyz_curves)
+                for (int ch = 0; ch < 3; ++ch) welford_add(tri[ch] * cam.sensitivity, xyz_mean + 3 * w + ch, xyz_variance + 3 * w + ch, s);
         }
     }
     if (counters) {

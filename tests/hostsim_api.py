@@ -44,7 +44,8 @@ def lib():
         _lib.hs_mt_state.argtypes = [C.c_uint64, C.c_int32, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_uint64, C.POINTER(cabi.RsbCamera), C.POINTER(cabi.RsbRayConfig),
                                    C.POINTER(cabi.RsbSpectral), C.POINTER(cabi.RsbRngDesc), C.c_int64, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_double,
+                                   C.c_void_p, C.c_void_p]
         _lib.hs_frame_combine.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
@@ -95,9 +96,11 @@ class HostScene:
         return count, prims
 
     def render(self, camera, config, spectral, rng_mode, seed, pixels=None, mean=None, variance=None, passes=1,
-               seed_stride=0):
+               seed_stride=0, xyz=None):
+        """``xyz`` = ((bins, 3) curves, delta_wavelength): the per-task XYZ statistics of every pass are left in
+        ``self._xyz_passes`` as [(mean (n, 3), variance (n, 3)), ...]"""
         if passes > 1:
-            return self._render_passes(camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride)
+            return self._render_passes(camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride, xyz)
         nx, ny, bins = camera.nx, camera.ny, config.bins
         if mean is None:
             mean = np.zeros((nx, ny, bins))
@@ -110,8 +113,15 @@ class HostScene:
             pix = cabi.as_i32(pixels).reshape(-1, 2)
             n = pix.shape[0]
         counters = np.zeros(7, dtype=np.uint64)
+        curves = xm = xv = None
+        if xyz is not None:
+            curves = np.ascontiguousarray(xyz[0], dtype=np.float64)
+            assert curves.shape == (bins, 3)
+            xm, xv = np.zeros((n, 3)), np.zeros((n, 3))
         rc = lib().hs_render(self.scene, C.byref(camera), C.byref(config), C.byref(spectral), C.byref(rng), n, _p(pix),
-                             _p(mean), _p(variance), C.byref(rays), _p(counters))
+                             _p(mean), _p(variance), C.byref(rays), _p(counters), _p(curves), float(xyz[1]) if xyz is not None else 0.0,
+                             _p(xm), _p(xv))
+        self._xyz_passes = [(xm, xv)] if xyz is not None else None
         if rc:
             raise cabi.RsbError(rc, lib().hs_last_error().decode())
         self.counters = dict(zip(("branches", "leaves", "items", "prim_tests", "tri_tests", "paths", "segments"),
@@ -126,20 +136,46 @@ class HostScene:
         self._slice = (mean, variance, pix, camera.pixel_samples * passes)
         return rays
 
-    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None):
-        """rsb_render_slices restated with the sequential pieces: one render per slice with the slice's own seed base"""
+    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None, xyz=None,
+                      keep_spectral=True):
+        """rsb_render_slices(_xyz) restated with the sequential pieces: one render per slice with the slice's own seed base"""
         nx, ny, bins = camera.nx, camera.ny, config.bins
         stride = nx * ny if seed_stride is None else seed_stride
         n = len(spectrals)
         mean, variance, total = np.zeros((nx, ny, bins * n)), np.zeros((nx, ny, bins * n)), 0
+        xyz_slices = []
         for k, sp in enumerate(spectrals):
-            m, v, rays = self.render(camera, config, sp, rng_mode, seed + k * stride, pixels, passes=passes, seed_stride=n * stride)
+            m, v, rays = self.render(camera, config, sp, rng_mode, seed + k * stride, pixels, passes=passes, seed_stride=n * stride,
+                                     xyz=None if xyz is None else (np.asarray(xyz[0])[k], np.asarray(xyz[1]).reshape(-1)[k]))
+            xyz_slices.append(self._xyz_passes)
             mean[:, :, k * bins:(k + 1) * bins] = m
             variance[:, :, k * bins:(k + 1) * bins] = v
             total += rays
         pix = None if pixels is None else cabi.as_i32(pixels).reshape(-1, 2)
-        self._slice = (mean, variance, pix, camera.pixel_samples * passes)
+        self._slice = (mean, variance, pix, camera.pixel_samples * passes) if keep_spectral else None
+        self._xyz = None if xyz is None else (xyz_slices, pix, camera.pixel_samples, (nx, ny))
         return total
+
+    def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
+        """rsb_slice_update_xyz_frame restated with numpy: per pass, the slices' statistics summed in slice order, merged
+        with combine_samples"""
+        from source_b200.observer import combine_samples
+        slices, pix, samples, (nx, ny) = self._xyz
+        if pix is None:
+            xs, ys = (a.reshape(-1) for a in np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij"))
+        else:
+            xs, ys = pix[:, 0], pix[:, 1]
+        if frame_is_empty:
+            assert not xyz_samples.any()
+        for p in range(len(slices[0])):
+            wm, wv = np.zeros((len(xs), 3)), np.zeros((len(xs), 3))
+            for parts in slices:
+                wm = wm + parts[p][0]
+                wv = wv + parts[p][1]
+            mt, vt, nt = combine_samples(xyz_mean[xs, ys], xyz_variance[xs, ys], xyz_samples[xs, ys], wm, np.maximum(wv, 0.0), samples)
+            xyz_mean[xs, ys] = mt
+            xyz_variance[xs, ys] = vt
+            xyz_samples[xs, ys] = nt
 
     def read_slice(self):
         return self._slice[0].copy(), self._slice[1].copy()
@@ -160,15 +196,17 @@ class HostScene:
         frame_variance[xs, ys, sl] = vt
         frame_samples[xs, ys, sl] = nt
 
-    def _render_passes(self, camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride):
+    def _render_passes(self, camera, config, spectral, rng_mode, seed, pixels, mean, variance, passes, seed_stride, xyz=None):
         """rsb_render_passes restated with the sequential pieces: one render per pass, merged in pass order into an
         empty frame with StatsArray3D.combine_samples (hs_frame_combine)."""
         nx, ny, bins = camera.nx, camera.ny, config.bins
         fm, fv = np.zeros((nx, ny, bins)), np.zeros((nx, ny, bins))
         fs = np.zeros((nx, ny, bins), dtype=np.int32)
         total = 0
+        xyz_passes = []
         for p in range(passes):
-            m, v, rays = self.render(camera, config, spectral, rng_mode, seed + p * seed_stride, pixels)
+            m, v, rays = self.render(camera, config, spectral, rng_mode, seed + p * seed_stride, pixels, xyz=xyz)
+            xyz_passes.extend(self._xyz_passes or [])
             total += rays
             lib().hs_frame_combine(nx * ny, bins, 0, bins, _p(m), _p(v), camera.pixel_samples, _p(fm), _p(fv), _p(fs))
         if mean is None:
@@ -182,6 +220,7 @@ class HostScene:
             listed[pix[:, 0], pix[:, 1]] = True
         mean[listed] = fm[listed]
         variance[listed] = fv[listed]
+        self._xyz_passes = xyz_passes if xyz is not None else None
         return mean, variance, total
 
 

@@ -219,6 +219,40 @@ def test_plugin_on_device_against_live_reference(device, reference):
     print("plugin render divergent fraction", fr)
 
 
+@pytest.mark.parametrize("passes,rgb_only", [(1, False), (2, False), (2, True)])
+def test_rgb_pipeline_on_device_against_live_reference(device, reference, passes, rgb_only):
+    """RGBPipeline2D (+ a spectral pipeline) through CudaRenderEngine on the B200 vs the reference's serial render feeding
+    the same pipelines: the XYZ frame within 1e-6 relative (no divergent pixel), sample counts exact; with the RGB pipeline
+    alone the device keeps no spectral frame at all."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
+    kw = dict(pixels=(20, 16), bins=12, spectral_rays=2)
+    w1 = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, w1, samples=3, sensitivity=1.7, **kw)
+    rgb = RGBPipeline2D(display_progress=False, accumulate=passes > 1)
+    cam.pipelines = [pipe, rgb]
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 31337, passes=passes)
+    x_ref = dict(mean=np.array(rgb.xyz_frame.mean), variance=np.array(rgb.xyz_frame.variance), samples=np.array(rgb.xyz_frame.samples))
+    assert x_ref["mean"].max() > 0
+    w2 = scenes.cornell_box(api)
+    cam2, pipe2 = scenes.cornell_camera(api, w2, samples=3 * passes, sensitivity=1.7, **kw)
+    rgb2 = RGBPipeline2D(display_progress=False)
+    cam2.pipelines = [rgb2] if rgb_only else [pipe2, rgb2]
+    cam2.frame_sampler = WholeFrameSampler2D()
+    cam2.render_engine = CudaRenderEngine(seed=31337, rng="mt", device=device, passes=passes)
+    cam2.observe()
+
+    class X:  # noqa: E701
+        mean, variance, samples = np.array(rgb2.xyz_frame.mean), np.array(rgb2.xyz_frame.variance), np.array(rgb2.xyz_frame.samples)
+    print("xyz divergent fraction", parity.compare_frame(X, x_ref, exact=False, rtol=1e-6, max_divergent_fraction=0.0))
+    if not rgb_only:
+        class F:  # noqa: E701
+            mean, variance, samples = np.array(pipe2.frame.mean), np.array(pipe2.frame.variance), np.array(pipe2.frame.samples)
+        parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+
+
 def test_hit_sweep_device_generated_rays(device):
     """config-5 style sweep: rays generated on device; hits/sum(t) must agree with the batched API on the same rays"""
     import ctypes as C

@@ -174,6 +174,82 @@ def test_whole_frame_sampler_equals_full_frame_sampler(api, reference, bulk):
         cam.observe()
 
 
+def _rgb_reference(api, reference, passes, seed, sensitivity, **kw):
+    from raysect.optical.observer import RGBPipeline2D
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, samples=2, sensitivity=sensitivity, **kw)
+    rgb = RGBPipeline2D(display_progress=False, accumulate=passes > 1)
+    cam.pipelines = [pipe, rgb]
+    spectral = reference.oracle_render(cam, pipe, seed, passes=passes)
+    f = rgb.xyz_frame
+    return spectral, (np.array(f.mean), np.array(f.variance), np.array(f.samples))
+
+
+@pytest.mark.parametrize("passes,spectral_rays", [(1, 1), (1, 2), (3, 2)])
+def test_rgb_pipeline_matches_serial_reference(api, reference, passes, spectral_rays):
+    """RGBPipeline2D fed by CudaRenderEngine == the reference's SerialEngine feeding it through XYZPixelProcessor
+    (rgb.pyx:534-562) / update / finalise (rgb.pyx:249-290), bit for bit: next to a spectral pipeline (one render keeps
+    both statistics), on its own (no spectral frame is kept), with several slices (their XYZ means are summed before the
+    frame sees them) and with concurrent passes (== repeated observe() into an accumulating pipeline)."""
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=spectral_rays)
+    (m_ref, v_ref, n_ref), xyz_ref = _rgb_reference(api, reference, passes, 4242, 2.5, **kw)
+    assert xyz_ref[2].max() == 2 * passes and xyz_ref[0].max() > 0
+    for with_spectral in (True, False):
+        world = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, world, samples=2 * passes, sensitivity=2.5, **kw)
+        rgb = RGBPipeline2D(display_progress=False)
+        cam.pipelines = [pipe, rgb] if with_spectral else [rgb]
+        cam.render_engine = CudaRenderEngine(seed=4242, rng="mt", backend=hostsim_api.HostScene, passes=passes)
+        cam.observe()
+        f = rgb.xyz_frame
+        for ours, ref in zip((f.mean, f.variance, f.samples), xyz_ref):
+            np.testing.assert_array_equal(np.array(ours), ref)
+        if with_spectral:
+            np.testing.assert_array_equal(np.array(pipe.frame.mean), m_ref)
+            np.testing.assert_array_equal(np.array(pipe.frame.variance), v_ref)
+            np.testing.assert_array_equal(np.array(pipe.frame.samples), n_ref)
+
+
+def test_rgb_pipeline_accumulates_over_observes_and_feeds_the_rgb_adaptive_sampler(api, reference):
+    """An accumulating RGBPipeline2D observed twice through CudaRenderEngine == two reference passes, and the stock
+    RGBAdaptiveSampler2D (sampler2d.pyx) driving the engine from that pipeline's xyz_frame picks pixel lists the engine
+    renders without touching the others."""
+    from raysect.optical.observer import RGBAdaptiveSampler2D, RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=2)
+    _, xyz_ref = _rgb_reference(api, reference, 2, 515, None, **kw)
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, samples=2, **kw)
+    rgb = RGBPipeline2D(display_progress=False, accumulate=True)
+    cam.pipelines = [rgb]
+    cam.render_engine = CudaRenderEngine(seed=515, rng="mt", backend=hostsim_api.HostScene)
+    cam.observe()
+    cam.observe()
+    f = rgb.xyz_frame
+    for ours, ref in zip((f.mean, f.variance, f.samples), xyz_ref):
+        np.testing.assert_array_equal(np.array(ours), ref)
+    cam.frame_sampler = RGBAdaptiveSampler2D(rgb, ratio=4, fraction=0.3, min_samples=5, cutoff=0.0001)
+    before = np.array(f.samples)
+    cam.observe()
+    after = np.array(rgb.xyz_frame.samples)
+    grown = (after - before)[:, :, 0]
+    assert set(np.unique(grown)) <= {0, 2} and 0 < (grown > 0).sum()
+    assert (before[:, :, 0][grown == 0] == after[:, :, 0][grown == 0]).all()
+
+
+def test_rgb_pipeline_needs_the_whole_slice_device_path(api):
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, pixels=(4, 4), bins=8)
+    cam.pipelines = [RGBPipeline2D(display_progress=False)]
+    cam.render_engine = CudaRenderEngine(seed=3, rng="mt", backend=hostsim_api.HostScene, bulk_update=False)
+    with pytest.raises(NotImplementedError):
+        cam.observe()
+
+
 def test_render_engine_on_real_conductor_and_unity_emitter_objects(api, reference):
     """raysect.optical.material.Conductor / UnitySurfaceEmitter objects flattened from a live Raysect scenegraph"""
     from source_b200.plugin import CudaRenderEngine
@@ -415,10 +491,10 @@ def test_render_engine_with_real_orthographic_camera(api, reference):
 
 
 def test_unsupported_objects_fail_loudly(api):
-    from raysect.optical.observer import RGBPipeline2D
+    from raysect.optical.observer import PowerPipeline2D
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
-    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[RGBPipeline2D()], frame_sampler=api.FullFrameSampler2D())
+    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[PowerPipeline2D(display_progress=False)], frame_sampler=api.FullFrameSampler2D())
     cam.quiet = True
     cam.render_engine = CudaRenderEngine(backend=hostsim_api.HostScene)
     with pytest.raises(NotImplementedError):

@@ -12,6 +12,9 @@ for k in ("e2e", "e2e_cabi"):
         print("  %-8s %.1f Mrays/s  h2d %s d2h %s  %s" % (k, e["value"], e.get("h2d_bytes_per_step"), e.get("d2h_bytes_per_step"), (e.get("path") or "")[:70]))
         if e.get("breakdown"):
             print("           breakdown", {a: round(b, 3) for a, b in e["breakdown"].items()})
+        rg = e.get("rgb_pipeline")
+        if rg:
+            print("           rgb pipeline only", ("%.1f Mrays/s" % rg["value"]) if "value" in rg else rg, {a: round(b, 3) for a, b in (rg.get("breakdown") or {}).items()})
         st = e.get("stock_full_frame_sampler")
         if st:
             print("           stock sampler %.1f Mrays/s" % st["value"], {a: round(b, 3) for a, b in st["breakdown"].items()})
