@@ -335,6 +335,21 @@ int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera,
                           const double* delta_wavelength, int32_t keep_spectral, uint64_t* ray_count);
 int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance,
                                int32_t* xyz_samples);
+/*
+ * Several GPUs driven from ONE process (the reference's user runs one Python interpreter; its MulticoreEngine forks
+ * workers and pickles per-pixel results back, raysect/core/workflow.py:123-327).  A communicator joins contexts on
+ * different devices and enables peer access between them.  After every member has rendered ITS pixel list of the same
+ * frame (rsb_render_slice(s), one host thread per context), rsb_comm_gather_slices makes the root's held slice the whole
+ * result: one kernel per peer on the root's device loads the rows of that peer's listed pixels straight out of the peer's
+ * memory (NVLink / NVSwitch peer mapping) and stores them in place -- copies only, exact -- and the root's task list
+ * becomes the union of all lists, ready for ONE rsb_slice_update_frame.  Pixel lists must be disjoint.  XYZ statistics
+ * (rsb_render_slices_xyz) are per work item and stay with their owners: call rsb_slice_update_xyz_frame on every member
+ * BEFORE the gather (the xyz_frame is 3 values per pixel).  One process per GPU (torch.distributed / NCCL,
+ * source_b200/distributed.py) remains the form bench.py scales with.
+ */
+int rsb_comm_create(int32_t n_contexts, const uint64_t* contexts, uint64_t* comm);
+int rsb_comm_destroy(uint64_t comm);
+int rsb_comm_gather_slices(uint64_t comm, int32_t root);
 /* Page-lock / release a caller-owned host buffer (cudaHostRegister / cudaHostUnregister).  The drop-in engine pins the
  * pipeline's StatsArray3D buffers from a helper thread while the device renders, so that rsb_slice_update_frame's
  * copies do not crawl through freshly allocated, never-touched pageable memory.  Pinning an already pinned buffer

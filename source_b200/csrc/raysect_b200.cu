@@ -1505,6 +1505,104 @@ int rsb_host_unpin(uint64_t ctx, void* ptr) {
     return RSB_OK;
 }
 
+// ---- several GPUs in one process -----------------------------------------------------------------------------------
+struct Comm {
+    std::vector<Context*> ctx;
+};
+
+int rsb_comm_create(int32_t n, const uint64_t* ctxs, uint64_t* comm) {
+    if (n < 1 || !ctxs || !comm) return fail(RSB_ERR_ARG, "rsb_comm_create: bad arguments");
+    Comm* cm = new Comm();
+    for (int i = 0; i < n; ++i) {
+        Context* c = as_ctx(ctxs[i]);
+        if (!c) { delete cm; return fail(RSB_ERR_ARG, "rsb_comm_create: null context"); }
+        cm->ctx.push_back(c);
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            const int a = cm->ctx[i]->device, b = cm->ctx[j]->device;
+            if (a == b) continue;
+            int can = 0;
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, a, b);
+            if (e != cudaSuccess || !can) {
+                cudaGetLastError();
+                delete cm;
+                return fail(RSB_ERR_UNSUPPORTED, "rsb_comm_create: device " + std::to_string(a) + " cannot map the memory of device " + std::to_string(b));
+            }
+            e = cudaSetDevice(a);
+            if (e == cudaSuccess) e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                delete cm;
+                return fail(RSB_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            }
+        }
+    *comm = reinterpret_cast<uint64_t>(cm);
+    return RSB_OK;
+}
+
+int rsb_comm_destroy(uint64_t comm) {
+    delete reinterpret_cast<Comm*>(comm);
+    return RSB_OK;
+}
+
+int rsb_comm_gather_slices(uint64_t comm, int32_t root) {
+    Comm* cm = reinterpret_cast<Comm*>(comm);
+    if (!cm || root < 0 || root >= (int)cm->ctx.size()) return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: bad arguments");
+    Context* r = cm->ctx[root];
+    if (!r->slice.valid || !r->slice.has_bins) return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: the root holds no rendered slice");
+    int64_t total = r->slice.n_pixels;
+    for (size_t i = 0; i < cm->ctx.size(); ++i) {
+        if ((int)i == root) continue;
+        Context* p = cm->ctx[i];
+        if (!p->slice.valid || !p->slice.has_bins) return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: a member holds no rendered slice");
+        if (p->slice.nx != r->slice.nx || p->slice.ny != r->slice.ny || p->slice.bins != r->slice.bins || p->slice.samples != r->slice.samples)
+            return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: the members rendered different frames");
+        if (p->slice.n_pixels > 0 && !p->slice.listed)
+            return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: every member but the root must have rendered a pixel list (its own tiles)");
+        total += p->slice.n_pixels;
+    }
+    const int64_t frame_pixels = (int64_t)r->slice.nx * r->slice.ny;
+    if (total > frame_pixels) return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: the members' pixel lists overlap");
+    RSB_CUDA(cudaSetDevice(r->device));
+    cudaStream_t st = r->stream;
+    const size_t frame = (size_t)frame_pixels * r->slice.bins;
+    // the root's task list becomes the union of all lists (or "the whole frame")
+    const bool whole = total == frame_pixels;
+    int32_t* d_union = nullptr;
+    if (!whole && total > r->slice.n_pixels) {
+        if (!r->slice.listed && r->slice.n_pixels > 0) return fail(RSB_ERR_ARG, "rsb_comm_gather_slices: the root rendered the whole frame already");
+        RSB_CUDA(cudaMalloc(&d_union, (size_t)total * 8));
+        if (r->slice.n_pixels > 0) RSB_CUDA(cudaMemcpyAsync(d_union, r->d_slice_pix, (size_t)r->slice.n_pixels * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    int64_t at = r->slice.n_pixels;
+    for (size_t i = 0; i < cm->ctx.size(); ++i) {
+        if ((int)i == root) continue;
+        Context* p = cm->ctx[i];
+        if (p->slice.n_pixels == 0) continue;
+        // (every member's render call has synchronised its own stream before it returned)
+        const long long n = (long long)p->slice.n_pixels * r->slice.bins;
+        k_gather_peer_rows<<<grid_for(r, n, 256, 8), 256, 0, st>>>(p->slice.n_pixels, p->d_slice_pix, r->slice.ny, r->slice.bins, p->d_slice,
+                                                                    p->d_slice + frame, r->d_slice, r->d_slice + frame);
+        RSB_CUDA(cudaGetLastError());
+        if (d_union) RSB_CUDA(cudaMemcpyPeerAsync(d_union + 2 * at, r->device, p->d_slice_pix, p->device, (size_t)p->slice.n_pixels * 8, st));
+        at += p->slice.n_pixels;
+    }
+    RSB_CUDA(cudaStreamSynchronize(st));
+    if (d_union) {
+        cudaFree(r->d_slice_pix);
+        r->d_slice_pix = d_union;
+        r->slice_pix_cap = (size_t)total;
+        r->slice.listed = true;
+    } else if (whole) {
+        r->slice.listed = false;
+    }
+    r->slice.n_pixels = total;
+    r->slice.has_xyz = false;     // XYZ work items stay with their owners (rsb_slice_update_xyz_frame on every member)
+    return RSB_OK;
+}
+
 int rsb_frame_combine_dev(uint64_t ctx, void* cuda_stream, int64_t n_pixels_total, int32_t frame_bins, int32_t slice_offset,
                           int32_t slice_bins, int64_t n_pixels, const int32_t* pixels_dev, int32_t ny, const double* mean_dev,
                           const double* variance_dev, int32_t samples, double* frame_mean_dev, double* frame_variance_dev,

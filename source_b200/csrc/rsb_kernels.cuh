@@ -1040,6 +1040,23 @@ __global__ void __launch_bounds__(128) k_wf_regen(const __grid_constant__ WfArgs
     }
 }
 
+// Several GPUs driven from one process (rsb_comm_gather_slices): the root device pulls the frame rows of a PEER's listed
+// pixels out of the peer's memory -- plain loads through the peer mapping, i.e. over NVLink / NVSwitch -- and drops them in
+// place in its own slice.  One thread per 16 bytes; rows are copied, so the root holds bit for bit what the owner wrote.
+__global__ void k_gather_peer_rows(long long n_pixels, const int32_t* __restrict__ peer_pixels, int ny, int bins,
+                                   const double* __restrict__ peer_mean, const double* __restrict__ peer_variance,
+                                   double* __restrict__ mean, double* __restrict__ variance) {
+    const long long total = n_pixels * bins;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long p = i / bins;
+        const int b = (int)(i % bins);
+        const long long at = ((long long)peer_pixels[2 * p] * ny + peer_pixels[2 * p + 1]) * bins + b;
+        mean[at] = peer_mean[at];
+        variance[at] = peer_variance[at];
+    }
+}
+
 // StatsArray3D.combine_samples over the listed pixels of a slice (statsarray.pyx:780-857, power.pyx:424-437)
 __global__ void k_frame_combine(long long n_pixels, const int32_t* __restrict__ pixels, int ny, int frame_bins, int slice_offset,
                                 int slice_bins, const double* __restrict__ mean, const double* __restrict__ variance, int samples,

@@ -181,13 +181,24 @@ RSB_HD double exact_recip(double d) {
     return r;
 }
 
+// A true division on a path that is (almost) never taken.  On the device its operands pass through an empty volatile
+// asm, which pins the division INSIDE the branch that guards it: without that the compiler if-converts
+// `rare ? x / d : shortcut` and every lane runs div.rn.f64's inline sequence -- in the kd descent, at every branch node of
+// every ray: 14.2 % of k_wf_trace's executed instructions in the round-2 profile sat on the "rare" line of div_recip1.
+RSB_HD double div_rare(double x, double d) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x), "+d"(d));
+#endif
+    return x / d;
+}
+
 RSB_HD double div_exact(double x, double d, double r) {
     double ax = fabs(x);
     // +-0 / d for a positive finite d is x itself.  (Left to the division it costs ~100 instructions: CUDA's
     // div.rn.f64 sends a zero numerator down its slow path, and the per-sample Welford update of a dark bin divides
     // zero twice -- 31 % of k_wf_finalize's instructions in the round-1 profile.)
     if (ax == 0.0 && d > 0.0 && d < 1e300) return x;
-    if (r == 0.0 || !(ax > 1e-250 && ax < 1e250)) return x / d;
+    if (r == 0.0 || !(ax > 1e-250 && ax < 1e250)) return div_rare(x, d);
     double q = x * r;
     double e = fma(-d, q, x);
     q = fma(e, r, q);
@@ -228,7 +239,7 @@ RSB_HD double div_recip1(double x, double d, double r, bool unsafe) {
     // the shortcut: q = +-0 and both corrections keep it zero; only the SIGN of a zero quotient may differ from the
     // division's, and the traversal compares plane distances, it never looks at the sign of a zero)
     if (unsafe || ex > 929u) {
-        if (unsafe || x != 0.0) return x / d;
+        if (unsafe || x != 0.0) return div_rare(x, d);
     }
     double q = x * r;
     double e = fma(-d, q, x);

@@ -263,6 +263,19 @@ class Accelerator:
         cabi.check(self.lib.rsb_slice_update_xyz_frame(self.device.ctx, int(bool(frame_is_empty)), cabi.ptr(xyz_mean, C.c_double),
                                                        cabi.ptr(xyz_variance, C.c_double), cabi.ptr(xyz_samples, C.c_int32)))
 
+    def gather_from(self, others):
+        """make this accelerator's held slice the whole multi-device result: the rows of every other member's listed
+        pixels are loaded out of its device's memory by a kernel on this device (rsb_comm_gather_slices)"""
+        if not others:
+            return
+        ctxs = (C.c_uint64 * (1 + len(others)))(self.device.ctx, *[o.device.ctx for o in others])
+        comm = C.c_uint64()
+        cabi.check(self.lib.rsb_comm_create(len(ctxs), ctxs, C.byref(comm)))
+        try:
+            cabi.check(self.lib.rsb_comm_gather_slices(comm.value, 0))
+        finally:
+            self.lib.rsb_comm_destroy(comm.value)
+
     def pin(self, *arrays):
         """page-lock numpy buffers (rsb_host_pin); returns a callable that releases them"""
         ptrs = [(a.ctypes.data, a.nbytes) for a in arrays if a.nbytes]
@@ -291,6 +304,75 @@ class Accelerator:
         cabi.check(self.lib.rsb_slice_update_frame(self.device.ctx, int(frame_mean.shape[2]), int(slice_offset), int(bool(frame_is_empty)),
                                                    cabi.ptr(frame_mean, C.c_double), cabi.ptr(frame_variance, C.c_double),
                                                    cabi.ptr(frame_samples, C.c_int32)))
+
+
+class DeviceGroup:
+    """Several GPUs driven from ONE process, behind the surface of a single ``Accelerator`` (render_slice(s) /
+    update_frame / update_xyz_frame): the pixel tasks of a render are dealt to the members in 16 x 16 tiles
+    (distributed.tile_pixels' diagonal dealing for a whole frame; sorted tile ids round-robin for a task list), every
+    member renders its list on its own device from its own host thread (ctypes releases the GIL), and the first member
+    gathers the others' rows over peer memory (rsb_comm_gather_slices) so that ONE update_frame merges the whole slice
+    into the pipeline's frame.  Pixel streams are keyed on the pixel: the result does not depend on the number of
+    members.  ``members`` need render_slices / update_frame / update_xyz_frame and the first one ``gather_from(others)``
+    (the device Accelerator; the host build of the tests emulates it)."""
+
+    tile = 16
+
+    def __init__(self, members):
+        if not members:
+            raise ValueError("a device group needs at least one member")
+        self.members = list(members)
+        self.flat = self.members[0].flat
+        self._rows_gathered = False
+
+    def close(self):
+        for m in self.members:
+            m.close()
+
+    def _deal(self, nx, ny, pixels):
+        from .distributed import tile_pixels
+        n = len(self.members)
+        if pixels is None:
+            return [tile_pixels(nx, ny, self.tile, k, n) for k in range(n)]
+        pix = cabi.as_i32(pixels).reshape(-1, 2)
+        tile_id = (pix[:, 0] // self.tile).astype(np.int64) * 65536 + (pix[:, 1] // self.tile)
+        rank = np.searchsorted(np.unique(tile_id), tile_id) % n
+        return [np.ascontiguousarray(pix[rank == k]) for k in range(n)]
+
+    def render_slices(self, camera, config, spectrals, rng_mode, seed, pixels=None, passes=1, seed_stride=None, xyz=None,
+                      keep_spectral=True):
+        from concurrent.futures import ThreadPoolExecutor
+        lists = self._deal(camera.nx, camera.ny, pixels)
+        stride = camera.nx * camera.ny if seed_stride is None else int(seed_stride)
+        kw = dict(xyz=xyz, keep_spectral=keep_spectral) if xyz is not None else {}
+
+        def one(job):
+            m, p = job
+            return m.render_slices(camera, config, spectrals, rng_mode, seed, p, passes=passes, seed_stride=stride, **kw)
+        with ThreadPoolExecutor(max_workers=len(self.members)) as pool:
+            rays = sum(pool.map(one, zip(self.members, lists)))
+        self._rows_gathered = False
+        return rays
+
+    def render_slice(self, camera, config, spectral, rng_mode, seed, pixels=None, passes=1, seed_stride=0):
+        return self.render_slices(camera, config, [spectral], rng_mode, seed, pixels, passes=passes, seed_stride=seed_stride)
+
+    def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
+        # XYZ statistics are per work item and stay with their owners: every member merges its own pixels into the
+        # (nx, ny, 3) frame, one after the other (before the spectral rows are gathered)
+        if self._rows_gathered:
+            raise RuntimeError("update_xyz_frame must precede update_frame after a multi-device render")
+        for k, m in enumerate(self.members):
+            m.update_xyz_frame(xyz_mean, xyz_variance, xyz_samples, frame_is_empty=frame_is_empty and k == 0)
+
+    def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
+        if not self._rows_gathered:
+            self.members[0].gather_from(self.members[1:])
+            self._rows_gathered = True
+        self.members[0].update_frame(frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=frame_is_empty)
+
+    def pin(self, *arrays):
+        return self.members[0].pin(*arrays)
 
 
 def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None):

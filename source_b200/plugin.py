@@ -236,6 +236,10 @@ class CudaRenderEngine(RenderEngine):
                 self._devices = [d if hasattr(d, "ctx") or self._backend_factory else Device(int(d)) for d in self._devices]
                 self._accel = [self._backend_factory(flat) if self._backend_factory is not None else _DeviceAccelerator(d, flat)
                                for d in self._devices]
+                if self.bulk_update and all(hasattr(a, "render_slices") for a in self._accel) and hasattr(self._accel[0], "gather_from"):
+                    # whole-slice device path on every GPU; the first one gathers the others' rows over peer memory
+                    from .engine import DeviceGroup
+                    self._accel = DeviceGroup(self._accel)
             elif self._backend_factory is not None:
                 self._accel = self._backend_factory(flat)
             else:
@@ -362,7 +366,7 @@ class CudaRenderEngine(RenderEngine):
                 rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes, **xkw)
                 self._frames_ready_wait(ready)
                 t1 = time.perf_counter()
-                for p in group:
+                for p in sorted(group, key=lambda q: q not in rgb):       # XYZ frames first (DeviceGroup: before the rows are gathered)
                     f = frame_of(p)
                     fm, fv, fs = np.asarray(f.mean), np.asarray(f.variance), np.asarray(f.samples)
                     if p in rgb:

@@ -180,6 +180,24 @@ class HostScene:
     def read_slice(self):
         return self._slice[0].copy(), self._slice[1].copy()
 
+    def gather_from(self, others):
+        """rsb_comm_gather_slices restated with numpy: the rows of every other member's listed pixels are copied in"""
+        mean, variance, pix, samples = self._slice
+        lists = [] if pix is None else [pix]
+        assert pix is not None or not others or all(len(o._slice[2]) == 0 for o in others)
+        for o in others:
+            om, ov, op, osamples = o._slice
+            assert op is not None and osamples == samples and om.shape == mean.shape
+            mean[op[:, 0], op[:, 1]] = om[op[:, 0], op[:, 1]]
+            variance[op[:, 0], op[:, 1]] = ov[op[:, 0], op[:, 1]]
+            lists.append(op)
+        union = np.concatenate(lists) if lists else None
+        if union is not None:
+            assert len(np.unique(union[:, 0].astype(np.int64) * 65536 + union[:, 1])) == len(union), "pixel lists overlap"
+            if len(union) == mean.shape[0] * mean.shape[1]:
+                union = None
+        self._slice = (mean, variance, union, samples)
+
     def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
         from source_b200.observer import combine_samples
         mean, variance, pix, samples = self._slice

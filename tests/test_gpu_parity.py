@@ -253,6 +253,42 @@ def test_rgb_pipeline_on_device_against_live_reference(device, reference, passes
         parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
 
 
+def test_two_devices_in_one_process_equal_one_device(device, reference):
+    """CudaRenderEngine(devices=[0, 1]) (engine.DeviceGroup: tiles dealt to both GPUs, one host thread each, the spectral
+    rows of device 1 pulled into device 0's slice by k_gather_peer_rows over peer memory, XYZ frames merged member by
+    member) gives bit for bit the frames of one device -- whole frame, task mask, passes, RGB + spectral pipelines."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in this process (gpurun --gpus 2)")
+    import scenes
+    api = reference.ref_api()
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.engine import Device, DeviceGroup
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
+    second = Device(1)
+    kw = dict(pixels=(70, 52), bins=12, spectral_rays=2, samples=4)
+    mask = np.ones((70, 52), dtype=bool)
+    mask[20:31, 5:40] = False
+    frames = []
+    for devices, sampler in ((None, "whole"), ([device, second], "whole"), (None, "mask"), ([device, second], "mask")):
+        w = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, w, sensitivity=1.3, **kw)
+        rgb = RGBPipeline2D(display_progress=False)
+        cam.pipelines = [pipe, rgb]
+        cam.frame_sampler = WholeFrameSampler2D() if sampler == "whole" else api.FullFrameSampler2D(mask)
+        eng = CudaRenderEngine(seed=2718, rng="mt", passes=2, **(dict(devices=devices) if devices else dict(device=device)))
+        cam.render_engine = eng
+        cam.observe()
+        assert isinstance(eng._accel, DeviceGroup) == bool(devices)
+        frames.append([np.array(a) for f in (pipe.frame, rgb.xyz_frame) for a in (f.mean, f.variance, f.samples)] + [eng.ray_count])
+    for one, two in ((frames[0], frames[1]), (frames[2], frames[3])):
+        for a, b in zip(one[:-1], two[:-1]):
+            np.testing.assert_array_equal(a, b)
+        assert one[-1] == two[-1] > 0
+    assert frames[0][2].min() == 4 and frames[2][2][~mask].max() == 0 and frames[2][5][mask].min() == 4
+    second.close()
+
+
 def test_hit_sweep_device_generated_rays(device):
     """config-5 style sweep: rays generated on device; hits/sum(t) must agree with the batched API on the same rays"""
     import ctypes as C

@@ -635,9 +635,12 @@ def test_power_and_radiance_pipelines_side_by_side(api, reference, bulk):
     np.testing.assert_array_equal(mrad.frame.variance, np.array(radiance.frame.variance))
 
 
-def test_render_engine_over_several_devices_equals_one_device(api, reference):
-    """CudaRenderEngine(devices=[...]): tiles dealt to three "devices" (three host-build scenes, one thread each), frames
-    summed on the host -- bit-identical to the reference / to a single device, with passes and a partial task mask"""
+@pytest.mark.parametrize("bulk", [True, False])
+def test_render_engine_over_several_devices_equals_one_device(api, reference, bulk):
+    """CudaRenderEngine(devices=[...]): tiles dealt to three "devices" (three host-build scenes, one thread each); with
+    bulk_update the first member gathers the others' rows (DeviceGroup / rsb_comm_gather_slices) and one update_frame
+    merges the slice, without it the frames are summed on the host and fed to update() pixel by pixel -- either way
+    bit-identical to the reference / to a single device, with passes and a partial task mask"""
     from source_b200.plugin import CudaRenderEngine
     kw = dict(pixels=(40, 36), samples=4, bins=4, spectral_rays=2)
     mask = np.ones((40, 36), dtype=bool)
@@ -650,14 +653,39 @@ def test_render_engine_over_several_devices_equals_one_device(api, reference):
     world2 = scenes.cornell_box(api)
     cam2, pipe2 = scenes.cornell_camera(api, world2, **kw)
     cam2.frame_sampler = api.FullFrameSampler2D(mask)
-    engine = CudaRenderEngine(seed=31, rng="mt", backend=hostsim_api.HostScene, passes=2, devices=[0, 1, 2])
+    engine = CudaRenderEngine(seed=31, rng="mt", backend=hostsim_api.HostScene, passes=2, devices=[0, 1, 2], bulk_update=bulk)
     assert engine.worker_count() == 3
     cam2.render_engine = engine
     cam2.observe()
+    from source_b200.engine import DeviceGroup
+    assert isinstance(engine._accel, DeviceGroup) == bulk
     np.testing.assert_array_equal(np.array(pipe2.frame.samples), n_ref)
     np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
     np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
     assert engine.ray_count > 0 and m_ref[mask].sum() > 0 and not np.array(pipe2.frame.mean)[~mask].any()
+
+
+def test_device_group_feeds_rgb_and_spectral_pipelines_of_a_whole_frame(api, reference):
+    """Two "devices", the whole frame in one task (WholeFrameSampler2D -> diagonal tile dealing), an RGB and a spectral
+    pipeline side by side: the XYZ statistics are merged member by member, the spectral rows gathered on the first member
+    -- the frames of the single-device reference run, bit for bit."""
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
+    kw = dict(pixels=(40, 36), bins=6, spectral_rays=2)
+    (m_ref, v_ref, n_ref), xyz_ref = _rgb_reference(api, reference, 1, 77, 1.5, **kw)
+    world = scenes.cornell_box(api)
+    cam, pipe = scenes.cornell_camera(api, world, samples=2, sensitivity=1.5, **kw)
+    rgb = RGBPipeline2D(display_progress=False)
+    cam.pipelines = [pipe, rgb]
+    cam.frame_sampler = WholeFrameSampler2D()
+    cam.render_engine = CudaRenderEngine(seed=77, rng="mt", backend=hostsim_api.HostScene, devices=[0, 1])
+    cam.observe()
+    f = rgb.xyz_frame
+    for ours, ref in zip((f.mean, f.variance, f.samples), xyz_ref):
+        np.testing.assert_array_equal(np.array(ours), ref)
+    np.testing.assert_array_equal(np.array(pipe.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe.frame.variance), v_ref)
+    np.testing.assert_array_equal(np.array(pipe.frame.samples), n_ref)
 
 
 def test_subclasses_that_override_evaluated_methods_are_rejected(api):

@@ -62,6 +62,18 @@ prism|prism:*)
   for CH in ${PRISM_CHUNKS:-8388608}; do
     RSB_CHUNK_ITEMS=$CH timeout 900 python tools_render_prism.py $A > $O/${TAG}_prism_$CH.json 2> $O/${TAG}_prism_$CH.err; echo "prism chunk $CH $A"; cut -c1-400 $O/${TAG}_prism_$CH.json; tail -n 2 $O/${TAG}_prism_$CH.err
   done ;;
+full)
+  timeout 1700 python bench.py > $O/${TAG}_bench_full.json 2> $O/${TAG}_bench_full.err; python tools_bench_show.py $O/${TAG}_bench_full.json; tail -n 3 $O/${TAG}_bench_full.err ;;
+listbench)
+  RSB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -s 2000 -c 800 --csv \
+    --log-file $O/${TAG}_bench_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-plugin --configs none --e2e-steps 1 > $O/${TAG}_listbench.log 2>&1; tail -n 2 $O/${TAG}_listbench.log
+  python tools_kernel_summary.py $O/${TAG}_bench_launches.csv > $O/${TAG}_bench_launch_summary.txt 2>&1; cat $O/${TAG}_bench_launch_summary.txt ;;
+ncuwf:*)
+  K=${S#ncuwf:}
+  RSB_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none -k regex:$K -s 300 -c 1 -f -o $O/${TAG}_full_$K \
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-plugin --configs none --e2e-steps 1 > $O/${TAG}_ncu_$K.log 2>&1
+  python tools_ncu_summary.py $O/${TAG}_full_$K.ncu-rep $K > $O/${TAG}_ncu_full_$K.txt 2>&1; rm -f $O/${TAG}_full_$K.ncu-rep
+  head -n 32 $O/${TAG}_ncu_full_$K.txt ;;
 *) echo "unknown step $S" ;;
 esac
 done
