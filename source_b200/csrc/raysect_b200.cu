@@ -859,7 +859,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
-    if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * a.sp.bins * sizeof(double);   // and one spectrum row per warp (RGB)
+    if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * 3 * a.sp.bins * sizeof(double);   // and the XYZ terms of one sample per warp (RGB)
     if (smem_tables > 200 * 1024) return fail(RSB_ERR_UNSUPPORTED, "rsb_render: too many bins per slice for the RGB projection (shared memory)");
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));

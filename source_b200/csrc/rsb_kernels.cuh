@@ -887,8 +887,9 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     }
     // 32 log entries per warp, staged in shared memory and read back as one broadcast LDS.128 per entry
     LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;
-    // RGB: the sample's spectrum, one row of `bins` doubles per warp, behind the log windows
-    double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * sp.bins;
+    // RGB: the sample's three products per bin (delta * sample * curve), one row of 3 * bins doubles per warp, behind the
+    // log windows
+    double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * 3 * sp.bins;
     const bool keep_bins = a.mean != nullptr, keep_xyz = a.xyz_mean != nullptr;
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
@@ -918,6 +919,8 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         const double r_nn = 1.0 / (double)(s + 1), r_nn1 = s > 0 ? 1.0 / (double)s : 0.0;
         // (with emitting volumes in the scene a path that ended dark may still carry what they added on the way)
         const bool emit = status == SLOT_ENDED_EMIT || (a.has_additive && a.st.additive[slot] != 0);
+        const double xyz_delta = keep_xyz ? a.xyz_delta[slice] : 0.0;
+        const double* xyz_curve = keep_xyz ? a.xyz_tab + (size_t)slice * bins * 3 : nullptr;
         for (int b0 = 0; b0 < bins; b0 += 64) {
             // two bins per lane per pass; the statistics rows are fetched before the replay so that their
             // latency overlaps it
@@ -946,7 +949,13 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (ha) {
                 double x = xa * w;              // spectrum.mul_scalar(projection_weight), observer.pyx:408
-                if (keep_xyz) wspec[ba] = x;
+                if (keep_xyz) {
+                    // the terms of spectrum_to_ciexyz's sums (colour.pyx:182-184), delta * sample * curve, formed by the
+                    // bin's own lane; only the additions below are a serial chain
+                    const double dx = xyz_delta * x;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) wspec[3 * ba + ch] = dx * __ldg(xyz_curve + 3 * ba + ch);
+                }
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
                     welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
@@ -954,7 +963,11 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (hb) {
                 double x = xb * w;
-                if (keep_xyz) wspec[bb] = x;
+                if (keep_xyz) {
+                    const double dx = xyz_delta * x;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) wspec[3 * bb + ch] = dx * __ldg(xyz_curve + 3 * bb + ch);
+                }
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;
                     welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
@@ -963,14 +976,14 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         }
         if (keep_xyz) {
             // XYZPixelProcessor.add_sample (rgb.pyx:550-558): spectrum_to_ciexyz sums delta * sample * curve over the bins
-            // in index order (colour.pyx:178-186) -- a serial chain, so lanes 0..2 walk one curve each -- then the
-            // tristimulus value times the sensitivity enters the channel's running statistics
+            // in index order (colour.pyx:178-186) -- a serial chain of additions, so lanes 0..2 walk one channel each
+            // (the terms are in shared memory already: the chain is bins x one DADD) -- then the tristimulus value times
+            // the sensitivity enters the channel's running statistics
             __syncwarp();
             if (lane < 3) {
-                const double delta = a.xyz_delta[slice];
-                const double* curve = a.xyz_tab + ((size_t)slice * bins) * 3 + lane;
                 double acc = 0.0;
-                for (int i = 0; i < bins; ++i) acc += delta * wspec[i] * __ldg(curve + 3 * i);
+#pragma unroll 8
+                for (int i = 0; i < bins; ++i) acc += wspec[3 * i + lane];
                 const size_t item = ((size_t)a.item_base + (size_t)a.st.work[slot]) * 3 + lane;
                 double pm = 0, pv = 0;
                 if (s > 0) { pm = a.xyz_mean[item]; pv = a.xyz_variance[item]; }

@@ -182,9 +182,11 @@ RSB_HD double exact_recip(double d) {
 }
 
 // A true division on a path that is (almost) never taken.  On the device its operands pass through an empty volatile
-// asm, which pins the division INSIDE the branch that guards it: without that the compiler if-converts
-// `rare ? x / d : shortcut` and every lane runs div.rn.f64's inline sequence -- in the kd descent, at every branch node of
-// every ray: 14.2 % of k_wf_trace's executed instructions in the round-2 profile sat on the "rare" line of div_recip1.
+// asm, which pins the division inside the branch that guards it (the compiler may otherwise if-convert
+// `rare ? x / d : shortcut` and run div.rn.f64's inline sequence on every lane).  Measured: nvcc 12.9 did not if-convert
+// these sites -- k_wf_trace's SASS is identical with and without the pin (6,152 instructions) -- so this is a guard, not
+// a speed-up; the 14 % of k_wf_trace's instructions that ncu attributes to div_recip1's guard line are the exponent
+// window test and the branch themselves, executed once per kd branch node.
 RSB_HD double div_rare(double x, double d) {
 #ifdef __CUDA_ARCH__
     asm volatile("" : "+d"(x), "+d"(d));
