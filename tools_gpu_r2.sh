@@ -12,7 +12,7 @@ testk:*)
   timeout 900 python -m pytest tests -m gpu -x -q -k "$K" > $O/${TAG}_pytest_k.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_k.log
   tail -n 25 $O/${TAG}_pytest_k.log ;;
 sanitize)
-  timeout 900 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q -k "zoo or mesh_hits or edge" > $O/${TAG}_sanitize.log 2>&1
+  timeout 900 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q -k "zoo or mesh_hits or edge or rgb_pipeline_on_device" > $O/${TAG}_sanitize.log 2>&1
   tail -n 12 $O/${TAG}_sanitize.log ;;
 sweep|sweep:*)
   L=${S#sweep:}; [ "$L" = "sweep" ] && L=""
