@@ -235,6 +235,17 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
                       uint64_t* out_hits_dev, double* out_sum_t_dev, uint64_t* out_xor_prim_dev, int32_t count);
 
 /*
+ * Incoherent query batches (rays after a diffuse bounce, a user's unordered batch) put 32 unrelated kd walks into every
+ * warp.  With reordering on, rsb_hit_batch(_dev) and rsb_hit_sweep_dev sort each pipeline pass (<= 4 Mi queries) on a
+ * 20-bit coherence key first -- origin cell and octahedral direction cell, normalised to the extent the batch covers,
+ * Morton-interleaved; one counting sort on the device -- traverse the permuted copy and write every answer back at the
+ * caller's index.  The answers are the same (queries are independent; the reference's World.hit has no notion of order).
+ * Off by default (an already coherent batch gains nothing and pays the sort); RSB_RQ_REORDER=1 turns it on at context
+ * creation.
+ */
+int rsb_set_query_reorder(uint64_t ctx, int32_t on);
+
+/*
  * Accelerator.contains == World.contains (world.pyx:148-168): points [n][3]; out_count[n];
  * out_prims[n][cap] primitive ids in the reference's list order (kd leaf order).
  */

@@ -189,6 +189,7 @@ SIGNATURES = {
     "rsb_comm_create": (C.c_int, [C.c_int32, c_uint64_p, c_uint64_p]),
     "rsb_comm_destroy": (C.c_int, [_U64]),
     "rsb_comm_gather_slices": (C.c_int, [_U64, C.c_int32]),
+    "rsb_set_query_reorder": (C.c_int, [_U64, C.c_int32]),
     "rsb_host_pin": (C.c_int, [_U64, _VP, C.c_int64]),
     "rsb_host_unpin": (C.c_int, [_U64, _VP]),
     "rsb_slice_read": (C.c_int, [_U64, c_double_p, c_double_p]),

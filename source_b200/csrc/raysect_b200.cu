@@ -80,6 +80,7 @@ struct Context {
     unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
     size_t rq_bytes = 0;
     long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
+    bool query_reorder = false;         // rsb_set_query_reorder / RSB_RQ_REORDER=1: sort every batch on its coherence key first
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
     long long chunk_items = 16LL << 20; // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (2.5 KB + 16 B per sample each)
@@ -98,6 +99,7 @@ struct Context {
 };
 
 const size_t kMaxStageBytes = 96 * 1024;
+const long long kReorderMin = 4096;      // smaller batches are traversed as they come
 
 // Kernels are instantiated per scene feature set (rsb_geom.h RSB_FEAT_*): analytic primitives only, + meshes, or
 // everything (meshes and CSG), and world-level data staged in shared memory vs read from HBM/L2.  M(COUNT, FEAT) is expanded
@@ -334,6 +336,7 @@ int rsb_context_create(int device, uint64_t* ctx) {
     }
     if (const char* ng = getenv("RSB_NO_GRAPH")) c->use_graphs = !(ng[0] == '1');
     if (const char* sp = getenv("RSB_CHUNK_ITEMS")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->chunk_items = v; }
+    if (const char* sp = getenv("RSB_RQ_REORDER")) c->query_reorder = atoi(sp) != 0;
     if (const char* sp = getenv("RSB_RQ_CHUNK")) { long long v = atoll(sp); if (v >= 1024 && v <= (64LL << 20)) c->rq_chunk = v; }
     if (const char* sp = getenv("RSB_SLOTS_PER_SM")) { int v = atoi(sp); if (v >= 32 && v <= 65536) c->slots_per_sm = v; }
     *ctx = reinterpret_cast<uint64_t>(c);
@@ -492,9 +495,17 @@ struct RqHost {
     RqBuf b;
     double* ray;     // [6][cap]
     double* md;      // [cap]
+    // reordering of incoherent batches (rsb_trav.cuh, rq_reorder): permuted copy of the rays, permutation, sort scratch
+    double* ray2 = nullptr;
+    double* md2 = nullptr;
+    int32_t* perm = nullptr;
+    unsigned int* key = nullptr;
+    unsigned int* hist = nullptr;         // [RQ_KEY_BINS]
+    unsigned int* block_sums = nullptr;   // [1024]
+    unsigned int* bounds = nullptr;       // [10]
 };
 
-size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out) {
+size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out, bool reorder = false) {
     size_t off = 0;
     auto take = [&](size_t bytes) -> unsigned char* {
         off = (off + 255) & ~(size_t)255;
@@ -515,6 +526,15 @@ size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out) {
         out->b.susp_stack = reinterpret_cast<KdStackEntry*>(take(cap * RQ_WORLD_STACK * sizeof(KdStackEntry)));
         out->b.queue = reinterpret_cast<int2*>(take((size_t)(RQ_MAX_ROUNDS + 1) * cap * sizeof(int2)));
     }
+    if (reorder) {
+        out->ray2 = reinterpret_cast<double*>(take(6 * cap * sizeof(double)));
+        out->md2 = reinterpret_cast<double*>(take(cap * sizeof(double)));
+        out->perm = reinterpret_cast<int32_t*>(take(cap * sizeof(int32_t)));
+        out->key = reinterpret_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
+        out->hist = reinterpret_cast<unsigned int*>(take((size_t)RQ_KEY_BINS * sizeof(unsigned int)));
+        out->block_sums = reinterpret_cast<unsigned int*>(take(1024 * sizeof(unsigned int)));
+        out->bounds = reinterpret_cast<unsigned int*>(take(16 * sizeof(unsigned int)));
+    }
     out->b.ray = out->ray;
     out->b.ray_stride = (long long)cap;
     out->b.md = out->md;
@@ -523,15 +543,35 @@ size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out) {
     return (off + 255) & ~(size_t)255;
 }
 
-int rq_reserve(Context* c, long long cap, bool park, RqHost* out) {
-    size_t need = rq_carve(nullptr, (size_t)cap, park, out);
+int rq_reserve(Context* c, long long cap, bool park, RqHost* out, bool reorder = false) {
+    size_t need = rq_carve(nullptr, (size_t)cap, park, out, reorder);
     if (c->rq_bytes < need) {
         cudaFree(c->d_rq);
         c->d_rq = nullptr; c->rq_bytes = 0;
         RSB_CUDA(cudaMalloc(&c->d_rq, need));
         c->rq_bytes = need;
     }
-    rq_carve(c->d_rq, (size_t)cap, park, out);
+    rq_carve(c->d_rq, (size_t)cap, park, out, reorder);
+    return RSB_OK;
+}
+
+// Sort the m queries in rq.ray / rq.md on their coherence key (rsb_trav.cuh) into rq.ray2 / rq.md2 and point the
+// pipeline at the permuted copy; rq.b.perm maps a slot back to the caller's index.
+int rq_reorder(Context* c, RqHost& rq, long long m, bool has_md, cudaStream_t st) {
+    RSB_CUDA(cudaMemsetAsync(rq.bounds, 0xFF, 5 * sizeof(unsigned int), st));
+    RSB_CUDA(cudaMemsetAsync(rq.bounds + 5, 0, 5 * sizeof(unsigned int), st));
+    RSB_CUDA(cudaMemsetAsync(rq.hist, 0, (size_t)RQ_KEY_BINS * sizeof(unsigned int), st));
+    const int grid = grid_for(c, m, 256, 8);
+    k_ro_bounds<<<grid, 256, 0, st>>>(m, rq.ray, rq.b.ray_stride, rq.bounds);
+    k_ro_keys<<<grid, 256, 0, st>>>(m, rq.ray, rq.b.ray_stride, rq.bounds, rq.key, rq.hist);
+    k_ro_scan_bins<<<RQ_KEY_BINS / 1024, 1024, 0, st>>>(rq.hist, rq.block_sums);
+    k_ro_scan_blocks<<<1, 1024, 0, st>>>(rq.block_sums);
+    k_ro_scatter<<<grid, 256, 0, st>>>(m, rq.key, rq.hist, rq.block_sums, rq.ray, rq.b.ray_stride, has_md ? rq.md : nullptr, rq.perm,
+                                      rq.ray2, rq.md2);
+    RSB_CUDA(cudaGetLastError());
+    rq.b.ray = rq.ray2;
+    if (has_md) rq.b.md = rq.md2;
+    rq.b.perm = rq.perm;
     return RSB_OK;
 }
 
@@ -591,6 +631,13 @@ int rq_trace(Context* c, DeviceScene* ds, const RqBuf& b, long long n, cudaStrea
 
 extern "C" {
 
+int rsb_set_query_reorder(uint64_t ctx, int32_t on) {
+    Context* c = as_ctx(ctx);
+    if (!c) return fail(RSB_ERR_ARG, "null context");
+    c->query_reorder = on != 0;
+    return RSB_OK;
+}
+
 int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n, const double* origins,
                       const double* directions, const double* max_distance, int32_t* out_prim, double* out_t,
                       int32_t* out_sub, uint8_t* out_flags, int32_t* out_node, double* out_geom, float* out_uvw,
@@ -604,7 +651,7 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const long long chunk = std::min<long long>(n, c->rq_chunk);
     RqHost rq;
-    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq);
+    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq, c->query_reorder);
     if (rc) return rc;
     const int feat = ds->has_csg ? RSB_FEAT_ALL : (ds->has_mesh ? RSB_FEAT_MESH : 0);
     for (long long off = 0; off < n; off += chunk) {
@@ -612,6 +659,12 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
         const int grid = grid_for(c, m, 256, 8);
         k_rq_batch_in<<<grid, 256, 0, st>>>(m, origins + 3 * off, directions + 3 * off, max_distance ? max_distance + off : nullptr, rq.ray,
                                             rq.b.ray_stride, rq.md);
+        if (c->query_reorder && m >= kReorderMin) {
+            rc = rq_reorder(c, rq, m, true, st);
+            if (rc) return rc;
+        } else {
+            rq.b.ray = rq.ray; rq.b.md = rq.md; rq.b.perm = nullptr;
+        }
         rc = rq_trace(c, ds, rq.b, m, st, count != 0);
         if (rc) return rc;
         const int ogrid = grid_for(c, m, 128, 16);
@@ -700,7 +753,7 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const long long chunk = std::min<long long>(n, c->rq_chunk);
     RqHost rq;
-    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq);
+    int rc = rq_reserve(c, chunk, ds->has_mesh, &rq, c->query_reorder);
     if (rc) return rc;
     rq.b.md = nullptr;          // every ray of a sweep is unbounded
     rq.b.md_all = RSB_INF;
@@ -709,6 +762,12 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
         const int grid = grid_for(c, m, 256, 8);
         k_rq_sweep_gen<<<grid, 256, 0, st>>>(m, first_index + off, seed, origin[0], origin[1], origin[2], target[0], target[1], target[2],
                                              half_window, order_log2, rq.ray, rq.b.ray_stride);
+        if (c->query_reorder && m >= kReorderMin) {
+            rc = rq_reorder(c, rq, m, false, st);
+            if (rc) return rc;
+        } else {
+            rq.b.ray = rq.ray; rq.b.perm = nullptr;
+        }
         rc = rq_trace(c, ds, rq.b, m, st, count != 0);
         if (rc) return rc;
         k_rq_sweep_reduce<<<grid, 256, 0, st>>>(rq.b, m, first_index + off, (unsigned long long*)out_hits_dev, out_sum_t_dev,

@@ -1,6 +1,8 @@
 """GPU suite: the CUDA kernels, called through the C ABI, against the golden vectors of the compiled
 reference.  ids, kd trees, t and local-space geometry are bit-exact; rendered frames are held to the
 north-star tolerance (1e-6 relative) with the path-divergence rate reported."""
+import os
+
 import numpy as np
 import pytest
 
@@ -440,6 +442,72 @@ def test_hit_sweep_equals_hit_batch_on_the_same_rays(device, kind, order):
     assert np.uint64(xr.item() & 0xFFFFFFFFFFFFFFFF) == np.bitwise_xor.reduce(key)
     assert abs(sum_t.item() - r.distance[hit].sum()) <= 1e-9 * r.distance[hit].sum()
     acc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["spheres", "mesh"])
+def test_query_reordering_changes_no_answer(kind):
+    """rsb_set_query_reorder: every pipeline pass is sorted on its coherence key, traversed as a permuted copy and written
+    back at the caller's index.  Same answers, bit for bit, as the unsorted run -- ids, distances, kd nodes, geometry,
+    barycentrics -- for a shared-origin batch (all 20 key bits on the direction), for rays with scattered origins,
+    per-ray max_distance, NaN / zero directions, over several pipeline passes; and the sweep's checksums agree."""
+    import ctypes as C
+    import torch
+    import scenes
+    import source_b200 as api
+    from source_b200 import _cabi as cabi
+    from source_b200.engine import Device
+    old = os.environ.get("RSB_RQ_CHUNK")
+    os.environ["RSB_RQ_CHUNK"] = "40000"          # several passes per batch
+    try:
+        dev = Device(0)
+    finally:
+        if old is None:
+            del os.environ["RSB_RQ_CHUNK"]
+        else:
+            os.environ["RSB_RQ_CHUNK"] = old
+    if kind == "spheres":
+        world = scenes.random_spheres(api, 3000, seed=7)
+        origin, target, half = (0.0, 0.0, -4.0), (0.0, 0.0, 0.0), 0.9
+    else:
+        verts, tris, normals = scenes.icosphere(5, radius=0.45, bumps=0.1)
+
+        def extra(a, w):
+            a.Mesh(verts, tris, normals, smoothing=True, closed=True, parent=w, transform=a.translate(0.1, -0.5, 0.1) * a.rotate(20, 10, 0),
+                   material=a.Lambert(a.ConstantSF(0.7)))
+        world = scenes.cornell_box(api, glass=False, extra=extra)
+        origin, target, half = (0.0, 0.0, -3.3), (0.1, -0.5, 0.1), 0.6
+    acc = dev.build(world)
+    n = 150000
+    o1, d1, _ = scenes.sweep_rays(2024, 0, n, origin, target, half, 0)
+    rng = np.random.default_rng(5)
+    o2 = rng.uniform(-1.2, 1.2, (n, 3))
+    d2 = rng.normal(size=(n, 3))
+    d2[:50] = 0.0
+    d2[50:100, 1] = np.nan
+    md2 = np.where(rng.uniform(size=n) < 0.3, rng.uniform(0.0, 2.0, n), np.inf)
+    answers = []
+    for on in (False, True):
+        dev.set_query_reorder(on)
+        ra = acc.hit_batch(o1, d1, geometry=True)
+        rb = acc.hit_batch(o2, d2, md2, geometry=True)
+        hits = torch.zeros(1, dtype=torch.int64, device="cuda")
+        sum_t = torch.zeros(1, dtype=torch.float64, device="cuda")
+        xr = torch.zeros(1, dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), n, 77, 2024, (C.c_double * 3)(*origin),
+                                             (C.c_double * 3)(*target), half, 0, C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()),
+                                             C.c_void_p(xr.data_ptr()), 0))
+        torch.cuda.synchronize()
+        answers.append((ra, rb, hits.item(), xr.item(), sum_t.item()))
+    (a0, b0, h0, x0, s0), (a1, b1, h1, x1, s1) = answers
+    assert (a0.primitive >= 0).sum() > n // 2 and (b0.primitive >= 0).sum() > n // 20
+    for r0, r1 in ((a0, a1), (b0, b1)):
+        for name in ("primitive", "distance", "sub", "exiting", "node", "geometry", "uvw"):
+            np.testing.assert_array_equal(getattr(r0, name), getattr(r1, name), err_msg=name)
+    assert h0 == h1 and x0 == x1 and abs(s0 - s1) <= 1e-9 * abs(s0)
+    acc.close()
+    dev.close()
 
 
 @pytest.mark.gpu

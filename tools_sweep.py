@@ -29,8 +29,9 @@ def main():
     ap.add_argument("--n", type=float, nargs="+", default=[1e5, 1e6, 1e7, 1e8])
     ap.add_argument("--mesh-subdiv", type=int, default=0, help="also sweep a Cornell box holding a 20*4^k-triangle mesh")
     ap.add_argument("--no-spheres", action="store_true", help="skip the sphere field (profiling the mesh scene)")
-    ap.add_argument("--order", nargs="+", default=["random", "morton"], choices=["random", "morton"],
-                    help="random: every ray aims anywhere in the window (incoherent); morton: rays walk a grid of cells along the "
+    ap.add_argument("--order", nargs="+", default=["random", "sorted", "morton"], choices=["random", "sorted", "morton"],
+                    help="random: every ray aims anywhere in the window (incoherent); sorted: the same random rays with the "
+                         "library's query reordering on (rsb_set_query_reorder); morton: rays walk a grid of cells along the "
                          "Morton curve (coherent, like the pixels of an observer)")
     args = ap.parse_args()
     dev = Device(0)
@@ -44,6 +45,7 @@ def main():
             sweep_order(name, acc, origin, target, half, ns, order_name)
 
     def sweep_order(name, acc, origin, target, half, ns, order_name):
+        dev.set_query_reorder(order_name == "sorted")
         hits = torch.zeros(1, dtype=torch.int64, device="cuda")
         sum_t = torch.zeros(1, dtype=torch.float64, device="cuda")
         xr = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -52,7 +54,7 @@ def main():
 
         def run(n, count):
             # "morton": a 2^g x 2^g grid of cells along the Morton curve with about one ray per cell (primary rays of an image)
-            order = 0 if order_name == "random" else max(1, int(math.log(max(n, 4), 4)))
+            order = 0 if order_name in ("random", "sorted") else max(1, int(math.log(max(n, 4), 4)))
             hits.zero_(); sum_t.zero_(); xr.zero_()
             cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), int(n), 0, 2024, o3, t3, half, order,
                                                  C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()), count))
