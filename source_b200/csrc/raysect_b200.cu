@@ -80,7 +80,7 @@ struct Context {
     unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
     size_t rq_bytes = 0;
     long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
-    bool query_reorder = false;         // rsb_set_query_reorder / RSB_RQ_REORDER=1: sort every batch on its coherence key first
+    bool query_reorder = true;          // rsb_set_query_reorder / RSB_RQ_REORDER=0: sort every batch on its coherence key first
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
     long long chunk_items = 16LL << 20; // RSB_CHUNK_ITEMS: pixel streams seeded up front per chunk (2.5 KB + 16 B per sample each)
@@ -495,9 +495,7 @@ struct RqHost {
     RqBuf b;
     double* ray;     // [6][cap]
     double* md;      // [cap]
-    // reordering of incoherent batches (rsb_trav.cuh, rq_reorder): permuted copy of the rays, permutation, sort scratch
-    double* ray2 = nullptr;
-    double* md2 = nullptr;
+    // reordering of incoherent batches (rsb_trav.cuh, rq_reorder): permutation and sort scratch
     int32_t* perm = nullptr;
     unsigned int* key = nullptr;
     unsigned int* hist = nullptr;         // [RQ_KEY_BINS]
@@ -527,8 +525,6 @@ size_t rq_carve(unsigned char* base, size_t cap, bool park, RqHost* out, bool re
         out->b.queue = reinterpret_cast<int2*>(take((size_t)(RQ_MAX_ROUNDS + 1) * cap * sizeof(int2)));
     }
     if (reorder) {
-        out->ray2 = reinterpret_cast<double*>(take(6 * cap * sizeof(double)));
-        out->md2 = reinterpret_cast<double*>(take(cap * sizeof(double)));
         out->perm = reinterpret_cast<int32_t*>(take(cap * sizeof(int32_t)));
         out->key = reinterpret_cast<unsigned int*>(take(cap * sizeof(unsigned int)));
         out->hist = reinterpret_cast<unsigned int*>(take((size_t)RQ_KEY_BINS * sizeof(unsigned int)));
@@ -555,22 +551,20 @@ int rq_reserve(Context* c, long long cap, bool park, RqHost* out, bool reorder =
     return RSB_OK;
 }
 
-// Sort the m queries in rq.ray / rq.md on their coherence key (rsb_trav.cuh) into rq.ray2 / rq.md2 and point the
-// pipeline at the permuted copy; rq.b.perm maps a slot back to the caller's index.
-int rq_reorder(Context* c, RqHost& rq, long long m, bool has_md, cudaStream_t st) {
+// Slot order of the m queries of `src` (the caller's arrays, or the sweep's generator) by coherence key (rsb_trav.cuh):
+// rq.perm[slot] = query.  The input stage fills the pipeline in that order; the output stage writes answers back through it.
+template <class Source>
+int rq_reorder(Context* c, RqHost& rq, long long m, const Source& src, cudaStream_t st) {
     RSB_CUDA(cudaMemsetAsync(rq.bounds, 0xFF, 5 * sizeof(unsigned int), st));
     RSB_CUDA(cudaMemsetAsync(rq.bounds + 5, 0, 5 * sizeof(unsigned int), st));
     RSB_CUDA(cudaMemsetAsync(rq.hist, 0, (size_t)RQ_KEY_BINS * sizeof(unsigned int), st));
     const int grid = grid_for(c, m, 256, 8);
-    k_ro_bounds<<<grid, 256, 0, st>>>(m, rq.ray, rq.b.ray_stride, rq.bounds);
-    k_ro_keys<<<grid, 256, 0, st>>>(m, rq.ray, rq.b.ray_stride, rq.bounds, rq.key, rq.hist);
+    k_ro_bounds<Source><<<grid, 256, 0, st>>>(m, src, rq.bounds);
+    k_ro_keys<Source><<<grid, 256, 0, st>>>(m, src, rq.bounds, rq.key, rq.hist);
     k_ro_scan_bins<<<RQ_KEY_BINS / 1024, 1024, 0, st>>>(rq.hist, rq.block_sums);
     k_ro_scan_blocks<<<1, 1024, 0, st>>>(rq.block_sums);
-    k_ro_scatter<<<grid, 256, 0, st>>>(m, rq.key, rq.hist, rq.block_sums, rq.ray, rq.b.ray_stride, has_md ? rq.md : nullptr, rq.perm,
-                                      rq.ray2, rq.md2);
+    k_ro_scatter<<<grid, 256, 0, st>>>(m, rq.key, rq.hist, rq.block_sums, rq.perm);
     RSB_CUDA(cudaGetLastError());
-    rq.b.ray = rq.ray2;
-    if (has_md) rq.b.md = rq.md2;
     rq.b.perm = rq.perm;
     return RSB_OK;
 }
@@ -657,14 +651,13 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     for (long long off = 0; off < n; off += chunk) {
         const long long m = std::min<long long>(chunk, n - off);
         const int grid = grid_for(c, m, 256, 8);
-        k_rq_batch_in<<<grid, 256, 0, st>>>(m, origins + 3 * off, directions + 3 * off, max_distance ? max_distance + off : nullptr, rq.ray,
-                                            rq.b.ray_stride, rq.md);
+        rq.b.perm = nullptr;
         if (c->query_reorder && m >= kReorderMin) {
-            rc = rq_reorder(c, rq, m, true, st);
+            rc = rq_reorder(c, rq, m, BatchSource{origins + 3 * off, directions + 3 * off}, st);
             if (rc) return rc;
-        } else {
-            rq.b.ray = rq.ray; rq.b.md = rq.md; rq.b.perm = nullptr;
         }
+        k_rq_batch_in<<<grid, 256, 0, st>>>(m, origins + 3 * off, directions + 3 * off, max_distance ? max_distance + off : nullptr, rq.b.perm,
+                                            rq.ray, rq.b.ray_stride, rq.md);
         rc = rq_trace(c, ds, rq.b, m, st, count != 0);
         if (rc) return rc;
         const int ogrid = grid_for(c, m, 128, 16);
@@ -760,14 +753,13 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     for (long long off = 0; off < n; off += chunk) {
         const long long m = std::min<long long>(chunk, n - off);
         const int grid = grid_for(c, m, 256, 8);
-        k_rq_sweep_gen<<<grid, 256, 0, st>>>(m, first_index + off, seed, origin[0], origin[1], origin[2], target[0], target[1], target[2],
-                                             half_window, order_log2, rq.ray, rq.b.ray_stride);
-        if (c->query_reorder && m >= kReorderMin) {
-            rc = rq_reorder(c, rq, m, false, st);
+        const SweepSource src{first_index + off, seed, origin[0], origin[1], origin[2], target[0], target[1], target[2], half_window, order_log2};
+        rq.b.perm = nullptr;
+        if (c->query_reorder && m >= kReorderMin && order_log2 == 0) {      // (order_log2 > 0: the caller asked for coherent rays)
+            rc = rq_reorder(c, rq, m, src, st);
             if (rc) return rc;
-        } else {
-            rq.b.ray = rq.ray; rq.b.perm = nullptr;
         }
+        k_rq_sweep_gen<<<grid, 256, 0, st>>>(m, src, rq.b.perm, rq.ray, rq.b.ray_stride);
         rc = rq_trace(c, ds, rq.b, m, st, count != 0);
         if (rc) return rc;
         k_rq_sweep_reduce<<<grid, 256, 0, st>>>(rq.b, m, first_index + off, (unsigned long long*)out_hits_dev, out_sum_t_dev,

@@ -661,13 +661,16 @@ k_rq_world(Scene sc, int n_items, Client cl, RqBuf b, long long n, DevCounters* 
 
 // ---- ray sources / sinks of the batch and sweep entry points ------------------------------------------------
 // [n][3] origins, directions (+ max_distance) -> the pipeline's SoA rows
+// slot j of the pipeline takes the caller's query perm[j] (reordered batches) or j
 __global__ void k_rq_batch_in(long long n, const double* __restrict__ origins, const double* __restrict__ directions,
-                              const double* __restrict__ max_distance, double* __restrict__ ray, long long stride, double* __restrict__ md) {
+                              const double* __restrict__ max_distance, const int32_t* __restrict__ perm, double* __restrict__ ray,
+                              long long stride, double* __restrict__ md) {
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        ray[i] = origins[3 * i]; ray[stride + i] = origins[3 * i + 1]; ray[2 * stride + i] = origins[3 * i + 2];
-        ray[3 * stride + i] = directions[3 * i]; ray[4 * stride + i] = directions[3 * i + 1]; ray[5 * stride + i] = directions[3 * i + 2];
-        md[i] = max_distance ? max_distance[i] : RSB_INF;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += step) {
+        const long long i = perm ? perm[j] : j;
+        ray[j] = origins[3 * i]; ray[stride + j] = origins[3 * i + 1]; ray[2 * stride + j] = origins[3 * i + 2];
+        ray[3 * stride + j] = directions[3 * i]; ray[4 * stride + j] = directions[3 * i + 1]; ray[5 * stride + j] = directions[3 * i + 2];
+        md[j] = max_distance ? max_distance[i] : RSB_INF;
     }
 }
 
@@ -737,9 +740,9 @@ __device__ __forceinline__ float ro_decode(unsigned int u) {
 }
 
 // the five sort coordinates of a ray: origin x, y, z and the octahedral image (u, v) of its direction
-__device__ __forceinline__ void ro_coords(const double* __restrict__ ray, long long stride, long long i, float* c) {
-    c[0] = (float)ray[i]; c[1] = (float)ray[stride + i]; c[2] = (float)ray[2 * stride + i];
-    const float dx = (float)ray[3 * stride + i], dy = (float)ray[4 * stride + i], dz = (float)ray[5 * stride + i];
+__device__ __forceinline__ void ro_coords(const V3& o, const V3& d, float* c) {
+    c[0] = (float)o.x; c[1] = (float)o.y; c[2] = (float)o.z;
+    const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
     const float l1 = fabsf(dx) + fabsf(dy) + fabsf(dz);
     float u = dx / l1, v = dy / l1;
     if (dz < 0.f) {
@@ -750,14 +753,17 @@ __device__ __forceinline__ void ro_coords(const double* __restrict__ ray, long l
 }
 
 // bounds[0..4] = minima, bounds[5..9] = maxima (ro_encode'd); initialised to 0xFFFFFFFF / 0 by the host
-__global__ void k_ro_bounds(long long n, const double* __restrict__ ray, long long stride, unsigned int* __restrict__ bounds) {
+template <class Source>
+__global__ void k_ro_bounds(long long n, Source src, unsigned int* __restrict__ bounds) {
     float lo[5], hi[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) { lo[k] = 3.4e38f; hi[k] = -3.4e38f; }
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         float c[5];
-        ro_coords(ray, stride, i, c);
+        V3 o, d;
+        src.get(i, o, d);
+        ro_coords(o, d, c);
 #pragma unroll
         for (int k = 0; k < 5; ++k)
             if (fabsf(c[k]) < 1e30f) { lo[k] = fminf(lo[k], c[k]); hi[k] = fmaxf(hi[k], c[k]); }      // (NaN and infinities sort first)
@@ -788,8 +794,9 @@ __device__ __forceinline__ unsigned int ro_spread2(unsigned int x) {      // 10 
 // key of every query + histogram.  A batch whose origins coincide (a camera, a probe point: extent below 1e-4 of the
 // direction-independent scale) spends all 20 bits on the direction (1024 x 1024 cells); otherwise 2 bits per origin axis
 // lead and 7 + 7 direction bits follow.
-__global__ void k_ro_keys(long long n, const double* __restrict__ ray, long long stride, const unsigned int* __restrict__ bounds,
-                          unsigned int* __restrict__ key, unsigned int* __restrict__ hist) {
+template <class Source>
+__global__ void k_ro_keys(long long n, Source src, const unsigned int* __restrict__ bounds, unsigned int* __restrict__ key,
+                          unsigned int* __restrict__ hist) {
     float lo[5], inv[5];
     float origin_extent = 0.f, origin_scale = 0.f;
 #pragma unroll
@@ -806,7 +813,9 @@ __global__ void k_ro_keys(long long n, const double* __restrict__ ray, long long
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         float c[5];
-        ro_coords(ray, stride, i, c);
+        V3 o, d;
+        src.get(i, o, d);
+        ro_coords(o, d, c);
         int q[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -876,19 +885,16 @@ __global__ void __launch_bounds__(1024) k_ro_scan_blocks(unsigned int* __restric
     block_sums[threadIdx.x] = (warp ? warp_tot[warp - 1] : 0u) + x - v;
 }
 
-// slot of every query (the bin's running cursor starts at its exclusive offset) and the permuted copy of its ray
+// slot of every query: the bin's running cursor starts at its exclusive offset.  Only the 4-byte permutation is scattered;
+// the input stage then READS the caller's rays (or generates the sweep's) in slot order and writes them coalesced.
+// (First version: this kernel also moved the six SoA components of every ray -- 24 M scattered 8-byte stores per 4 M rays,
+// 0.81 ms, a fifth of the whole sorted sweep.)
 __global__ void k_ro_scatter(long long n, const unsigned int* __restrict__ key, unsigned int* __restrict__ hist,
-                             const unsigned int* __restrict__ block_sums, const double* __restrict__ ray, long long stride,
-                             const double* __restrict__ md, int32_t* __restrict__ perm, double* __restrict__ ray_out,
-                             double* __restrict__ md_out) {
+                             const unsigned int* __restrict__ block_sums, int32_t* __restrict__ perm) {
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         const unsigned int k = key[i];
-        const long long j = (long long)block_sums[k >> 10] + atomicAdd(hist + k, 1u);
-        perm[j] = (int32_t)i;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) ray_out[c * stride + j] = ray[c * stride + i];
-        if (md) md_out[j] = md[i];
+        perm[(long long)block_sums[k >> 10] + atomicAdd(hist + k, 1u)] = (int32_t)i;
     }
 }
 
@@ -906,10 +912,12 @@ __device__ __forceinline__ unsigned int morton_compact(unsigned long long x) {
 // over the whole window, independently per ray (incoherent, like rays after a diffuse bounce).  order_log2 = g > 0: the
 // window is a 2^g x 2^g grid of cells walked along the Morton curve, ray `index` jitters inside cell index mod 4^g --
 // neighbouring indices are neighbouring cells, the way an observer hands out the pixels of an image (primary rays).
-__global__ void k_rq_sweep_gen(long long n, long long first_index, unsigned long long seed, double ox, double oy, double oz, double tx,
-                               double ty, double tz, double half_window, int order_log2, double* __restrict__ ray, long long stride) {
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+struct SweepSource {
+    long long first_index;
+    unsigned long long seed;
+    double ox, oy, oz, tx, ty, tz, half_window;
+    int order_log2;
+    __device__ __forceinline__ void get(long long i, V3& o, V3& d) const {
         const unsigned long long index = (unsigned long long)(first_index + i);
         Philox4x32 px;
         px.init(seed, index, 0u);
@@ -922,9 +930,29 @@ __global__ void k_rq_sweep_gen(long long n, long long first_index, unsigned long
             u2 = ((double)morton_compact(cell >> 1) + u2) * inv;
         }
         const V3 p = v3(tx + (2.0 * u1 - 1.0) * half_window, ty + (2.0 * u2 - 1.0) * half_window, tz);
-        const V3 d = normalise(v3(p.x - ox, p.y - oy, p.z - oz));
-        ray[i] = ox; ray[stride + i] = oy; ray[2 * stride + i] = oz;
-        ray[3 * stride + i] = d.x; ray[4 * stride + i] = d.y; ray[5 * stride + i] = d.z;
+        o = v3(ox, oy, oz);
+        d = normalise(v3(p.x - ox, p.y - oy, p.z - oz));
+    }
+};
+
+// the caller's arrays of rsb_hit_batch
+struct BatchSource {
+    const double* origins;
+    const double* directions;
+    __device__ __forceinline__ void get(long long i, V3& o, V3& d) const {
+        o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        d = v3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+    }
+};
+
+// slot j of the pipeline takes ray perm[j] of the sweep (reordered) or ray j
+__global__ void k_rq_sweep_gen(long long n, SweepSource src, const int32_t* __restrict__ perm, double* __restrict__ ray, long long stride) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += step) {
+        V3 o, d;
+        src.get(perm ? perm[j] : j, o, d);
+        ray[j] = o.x; ray[stride + j] = o.y; ray[2 * stride + j] = o.z;
+        ray[3 * stride + j] = d.x; ray[4 * stride + j] = d.y; ray[5 * stride + j] = d.z;
     }
 }
 

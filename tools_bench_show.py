@@ -29,7 +29,7 @@ for key, c in (d.get("configs") or {}).items():
         continue
     if key == "C5":
         for s in c["sweeps"]:
-            print("  C5 %-6s %.0e rays: %.1f Mrays/s  frac %.3f  hit %.3f" % (s["order"], s["rays"], s["Mrays_per_s"], s["roofline"]["frac"], s["hit_fraction"]))
+            print("  C5 %-15s %.0e rays: %.1f Mrays/s  frac %.3f  hit %.3f" % (s["order"], s["rays"], s["Mrays_per_s"], s["roofline"]["frac"], s["hit_fraction"]))
     else:
         rf = c.get("roofline") or {}
         print("  %s %.1f Mrays/s  %.2f frames/s  %.0f ms/step  trace frac %s  share %s  setup %s" % (

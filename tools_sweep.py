@@ -30,8 +30,8 @@ def main():
     ap.add_argument("--mesh-subdiv", type=int, default=0, help="also sweep a Cornell box holding a 20*4^k-triangle mesh")
     ap.add_argument("--no-spheres", action="store_true", help="skip the sphere field (profiling the mesh scene)")
     ap.add_argument("--order", nargs="+", default=["random", "sorted", "morton"], choices=["random", "sorted", "morton"],
-                    help="random: every ray aims anywhere in the window (incoherent); sorted: the same random rays with the "
-                         "library's query reordering on (rsb_set_query_reorder); morton: rays walk a grid of cells along the "
+                    help="random: every ray aims anywhere in the window (incoherent), query reordering switched off; sorted: the same "
+                         "random rays with the library's default query reordering (rsb_set_query_reorder); morton: rays walk a grid of cells along the "
                          "Morton curve (coherent, like the pixels of an observer)")
     args = ap.parse_args()
     dev = Device(0)
@@ -45,7 +45,7 @@ def main():
             sweep_order(name, acc, origin, target, half, ns, order_name)
 
     def sweep_order(name, acc, origin, target, half, ns, order_name):
-        dev.set_query_reorder(order_name == "sorted")
+        dev.set_query_reorder(order_name != "random")
         hits = torch.zeros(1, dtype=torch.int64, device="cuda")
         sum_t = torch.zeros(1, dtype=torch.float64, device="cuda")
         xr = torch.zeros(1, dtype=torch.int64, device="cuda")
