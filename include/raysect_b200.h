@@ -111,8 +111,12 @@ typedef struct RsbSceneDesc {
 /* PinholeCamera state after _update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-167), or
  * OrthographicCamera state (imaging/orthographic.pyx:132-137): image_delta = width / nx, rays leave the pixel's
  * jittered position on the z = 0 plane along +z with projection weight 1 (orthographic.pyx:139-167). */
+/* CCDArray (imaging/ccd.pyx:40-151): image_delta = width / nx, every sample leaves a uniformly drawn point of its pixel in a
+ * cosine-weighted direction over the hemisphere in front of the sensor, projection weight 0.5; sensitivity = pixel area x
+ * 2 pi (ccd.pyx:150-151).  Its pixel task draws all its points first and all its directions after them (ccd.pyx:130-131). */
 #define RSB_CAMERA_PINHOLE 0
 #define RSB_CAMERA_ORTHOGRAPHIC 1
+#define RSB_CAMERA_CCD 2
 typedef struct RsbCamera {
     int32_t nx, ny;
     int32_t pixel_samples;

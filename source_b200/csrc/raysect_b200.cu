@@ -1069,7 +1069,7 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     if (!c || !ds || !camera || !config || !spectral || !rng || !ray_count_dev || (!mean_dev != !variance_dev) || (!mean_dev && !xyz.mean))
         return fail(RSB_ERR_ARG, "rsb_render: null argument");
     if (camera->nx < 1 || camera->ny < 1 || camera->pixel_samples < 1) return fail(RSB_ERR_ARG, "rsb_render: bad camera");
-    if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC)
+    if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC && camera->kind != RSB_CAMERA_CCD)
         return fail(RSB_ERR_UNSUPPORTED, "rsb_render: unknown camera kind");
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");
@@ -1233,7 +1233,7 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     P = std::max<long long>(P, 1);
     WfSlots probe;
     RqBuf rq;
-    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &probe, ds->has_mesh, &rq);
+    size_t need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples * camera_jitter_pairs(camera->kind), &probe, ds->has_mesh, &rq);
     if (c->slot_bytes < need) {
         // the per-slot path log grows with ray_max_depth (48 KB per slot at Raysect's default 500): narrow the wavefront
         // and the seeded chunk until the pool fits what the device has left (another context, another process, ...)
@@ -1243,7 +1243,7 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
         while (need > free_b - free_b / 8 && (P > (long long)c->sm_count * 128 || chunk_cap > P)) {
             if (chunk_cap > P) chunk_cap = std::max<long long>(P, chunk_cap / 2);
             else { P = std::max<long long>((long long)c->sm_count * 128, P * 3 / 4); chunk_cap = std::min(chunk_cap, P); }
-            need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &probe, ds->has_mesh, &rq);
+            need = carve_slots(nullptr, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples * camera_jitter_pairs(camera->kind), &probe, ds->has_mesh, &rq);
         }
     }
     if (c->slot_bytes < need) {
@@ -1252,7 +1252,7 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
         RSB_CUDA(cudaMalloc(&c->d_slots, need));
         c->slot_bytes = need;
     }
-    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples, &a.st, ds->has_mesh, &rq);
+    carve_slots(c->d_slots, (size_t)P, (size_t)a.log_capacity, mt, (size_t)chunk_cap, camera->pixel_samples * camera_jitter_pairs(camera->kind), &a.st, ds->has_mesh, &rq);
     a.st.mt_table = c->d_mt_table;
     if (count & RSB_RENDER_COUNT) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
     const bool time_trace = (count & RSB_RENDER_TIME_TRACE) != 0;

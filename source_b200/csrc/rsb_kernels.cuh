@@ -374,7 +374,7 @@ struct WfSlots {
     int32_t* additive;      // [P] the path in flight has logged an emitting volume (only touched when has_additive)
     int32_t* pix_mti;       // [n_chunk] MT19937-64 cursor of every stream of the chunk after its 2*spp jitter draws
     unsigned long long* pix_mt;   // [n_chunk][312] their state words (seeded up front by k_wf_seed)
-    double* pix_jitter;     // [n_chunk][2*spp] the jitter draws of every stream: uniform() number 0 .. 2*spp-1 of seed(...),
+    double* pix_jitter;     // [n_chunk][2*spp] ([4*spp] for a CCD) the jitter draws of every stream: uniform() number 0 .. 2*spp-1 of seed(...),
                             // which RectangleSampler3D.samples(spp) consumes before any tracing (pinhole.pyx:183)
     const unsigned long long* mt_table;   // [312] seed-independent part of seed(d) (rsb_rng.h mt_seed_table)
     LogEntry* log;          // [P][log_capacity]
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(32 * RSB_SEED_WARPS) k_wf_seed(const __grid_co
     g.mt = mine;
     g.stride = 1;
     g.mti = RSB_MT_NN;
-    const int nj = 2 * a.cam.pixel_samples;
+    const int nj = 2 * camera_jitter_pairs(a.cam.kind) * a.cam.pixel_samples;
     double* jit = a.st.pix_jitter + (size_t)w * nj;
     for (int k = 0; k < nj; ++k) jit[k] = (double)(g.next_u64() >> 11) * (1.0 / 9007199254740992.0);
     a.st.pix_mti[w] = g.mti;
@@ -600,22 +600,31 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     a.st.sample[slot] = s;
     Rng jit;
     jit.mode = RNGMODE;
-    double u1, u2;
+    double u1, u2, u3 = 0.0, u4 = 0.0;
+    const int pairs = camera_jitter_pairs(a.cam.kind);
     if (RNGMODE == RNG_MT19937_64) {
-        // draws 2s and 2s+1 of the stream, taken when it was seeded (k_wf_seed)
-        const double2 j2 = *reinterpret_cast<const double2*>(a.st.pix_jitter + ((size_t)a.st.work[slot] * spp + (size_t)s) * 2);
+        // draws 2s and 2s+1 of the stream, taken when it was seeded (k_wf_seed); a CCD's direction draws follow the point
+        // draws of ALL the task's samples: 2*spp + 2s, 2*spp + 2s + 1
+        const double* jit_row = a.st.pix_jitter + (size_t)a.st.work[slot] * spp * 2 * pairs;
+        const double2 j2 = *reinterpret_cast<const double2*>(jit_row + 2 * (size_t)s);
         u1 = j2.x;
         u2 = j2.y;
+        if (pairs == 2) {
+            const double2 j4 = *reinterpret_cast<const double2*>(jit_row + 2 * (size_t)spp + 2 * (size_t)s);
+            u3 = j4.x;
+            u4 = j4.y;
+        }
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
         jit.px.init(a.seed + (unsigned long long)wf_group_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);
         u1 = jit.uniform();
         u2 = jit.uniform();
+        if (pairs == 2) { u3 = jit.uniform(); u4 = jit.uniform(); }
         a.st.philox_idx[slot] = jit.px.idx;
     }
     V3 o, d;
     double weight;
-    pinhole_ray(a.cam, px, py, u1, u2, &o, &d, &weight);
+    pinhole_ray(a.cam, px, py, u1, u2, &o, &d, &weight, u3, u4);
     const size_t P = (size_t)a.n_slots;
     a.st.ray[0 * P + slot] = o.x; a.st.ray[1 * P + slot] = o.y; a.st.ray[2 * P + slot] = o.z;
     a.st.ray[3 * P + slot] = d.x; a.st.ray[4 * P + slot] = d.y; a.st.ray[5 * P + slot] = d.z;

@@ -37,7 +37,7 @@ struct Spectral {    // per spectral slice: what SpectralFunction.sample()/avera
     int32_t n_tables;
 };
 
-struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1)
+struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1) | CCDArray (kind 2)
     int32_t nx, ny;
     int32_t pixel_samples;
     int32_t kind;
@@ -102,12 +102,19 @@ RSB_HD V3 vector_cone_uniform(Rng& rng, double theta) {
     return v3(r * cos(phi), r * sin(phi), z);
 }
 
-RSB_HD V3 hemisphere_cosine_sample(Rng& rng) {
-    double r = sqrt(rng.uniform());
-    double phi = 2.0 * RSB_PI * rng.uniform();
+// HemisphereCosineSampler.sample (core/math/sampler/solidangle.pyx:228-233) for the two draws it takes, in draw order
+RSB_HD V3 hemisphere_cosine_from(double u1, double u2) {
+    double r = sqrt(u1);
+    double phi = 2.0 * RSB_PI * u2;
     double x = r * cos(phi);
     double y = r * sin(phi);
     return v3(x, y, sqrt(max0(1.0 - x * x - y * y)));
+}
+
+RSB_HD V3 hemisphere_cosine_sample(Rng& rng) {
+    double u1 = rng.uniform();
+    double u2 = rng.uniform();
+    return hemisphere_cosine_from(u1, u2);
 }
 
 // ----- RoughConductor (raysect/optical/material/conductor.pyx:157-344): GGX facet distribution, Smith shadowing
@@ -581,7 +588,13 @@ RSB_HD void stats_combine(double mx, double vx, int nx, double my, double vy, in
 
 // PinholeCamera._generate_rays for one sample (pinhole.pyx:169-204): jitter (u1, u2) -> local
 // direction + projection weight, then _render_pixel's camera->world transform (observer.pyx:400-403).
-RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2, V3* o, V3* d, double* weight) {
+// uniform() draws a camera takes per pixel task BEFORE any ray is traced, per sample: 2 (the point on the pixel), or 4 for the
+// CCD, which draws all its pixel points first and all its directions after them (ccd.pyx:130-131)
+RSB_HD int camera_jitter_pairs(int kind) { return kind == 2 ? 2 : 1; }
+
+// (u1, u2): the sample's point draws; (u3, u4): its direction draws (CCDArray only)
+RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2, V3* o, V3* d, double* weight, double u3 = 0.0,
+                        double u4 = 0.0) {
     double pixel_x = cam.image_start_x - cam.image_delta * (px + 0.5);
     double pixel_y = cam.image_start_y - cam.image_delta * (py + 0.5);
     // RectangleSampler3D.sample (surface3d.pyx:197-198): width = height = image_delta, offsets 0.5*width
@@ -600,6 +613,18 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
         *weight = 1.0;
         *o = xform_point(cam.to_root, origin);
         *d = xform_vector(cam.to_root, v3(0.0, 0.0, 1.0));
+        return;
+    }
+    if (cam.kind == 2) {
+        // CCDArray._generate_rays (imaging/ccd.pyx:114-148): point on the pixel and a cosine-weighted direction over the
+        // hemisphere in front of the sensor, both moved to the pixel with .transform(translate(pixel_x, pixel_y, 0));
+        // "projected area cosine is implicit in distribution": weight 0.5
+        const double pixel_to_local[RSB_MAT_WORDS] = {1.0, 0.0, 0.0, pixel_x, 0.0, 1.0, 0.0, pixel_y, 0.0, 0.0, 1.0, 0.0, 1.0};
+        V3 origin = xform_point(pixel_to_local, v3(jx, jy, 0.0));
+        V3 direction = xform_vector(pixel_to_local, hemisphere_cosine_from(u3, u4));
+        *weight = 0.5;
+        *o = xform_point(cam.to_root, origin);
+        *d = xform_vector(cam.to_root, direction);
         return;
     }
     V3 dir = normalise(v3(jx + pixel_x, jy + pixel_y, 0.0 + 1.0));

@@ -380,15 +380,17 @@ class DeviceGroup:
         return self.members[0].pin(*arrays)
 
 
-def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None):
+def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None, ccd=False):
     """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160), or, with
-    ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137)"""
+    ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137) /
+    with ``ccd`` CCDArray._update_image_geometry (imaging/ccd.pyx:106-112; ``sensitivity`` = pixel area x 2 pi,
+    ccd.pyx:150-151)"""
     cam = cabi.RsbCamera()
     if width is not None:
         if width <= 0:
             raise ValueError("width can not be less than or equal to 0 meters.")
         image_delta = width / nx
-        cam.kind = cabi.CAMERA_ORTHOGRAPHIC
+        cam.kind = cabi.CAMERA_CCD if ccd else cabi.CAMERA_ORTHOGRAPHIC
     else:
         max_pixels = max(nx, ny)
         if max_pixels <= 1:

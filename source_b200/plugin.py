@@ -267,11 +267,11 @@ class CudaRenderEngine(RenderEngine):
         return mean, variance, rays
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import (OrthographicCamera, PinholeCamera, RGBPipeline2D, SpectralPowerPipeline2D,
+        from raysect.optical.observer import (CCDArray, OrthographicCamera, PinholeCamera, RGBPipeline2D, SpectralPowerPipeline2D,
                                               SpectralRadiancePipeline2D)
         observer = getattr(render, "__self__", None)
-        if not isinstance(observer, (PinholeCamera, OrthographicCamera)):
-            raise NotImplementedError("CudaRenderEngine renders PinholeCamera and OrthographicCamera observers; got %r "
+        if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray)):
+            raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera and CCDArray observers; got %r "
                                       "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
@@ -293,6 +293,9 @@ class CudaRenderEngine(RenderEngine):
             raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
                              % (observer.pixel_samples, self.passes))
         def camera_for(sensitivity):
+            if isinstance(observer, CCDArray):
+                return camera_desc(nx, ny, observer.pixel_samples // self.passes, None, sensitivity, observer.to_root(),
+                                   width=observer.width, ccd=True)
             if isinstance(observer, OrthographicCamera):
                 return camera_desc(nx, ny, observer.pixel_samples // self.passes, None, sensitivity,
                                    observer.to_root(), width=observer.width)
@@ -306,8 +309,11 @@ class CudaRenderEngine(RenderEngine):
         # The power pipeline's pixel processor scales every sample by the pixel sensitivity (power.pyx:478-481), the
         # radiance pipeline's does not (radiance.pyx:256-260) -- the same as a sensitivity of exactly 1.0.  One render
         # per distinct sensitivity; the pixel streams are keyed on the pixel, so both see the very same paths.
+        # (pinhole / orthographic: the observer's `sensitivity`; CCD: pixel area x 2 pi, ccd.pyx:150-151)
+        pixel_sensitivity = float(observer._pixel_sensitivity(0, 0))
+
         def sens_of(p):
-            return 1.0 if isinstance(p, SpectralRadiancePipeline2D) else float(observer.sensitivity)
+            return 1.0 if isinstance(p, SpectralRadiancePipeline2D) else pixel_sensitivity
         kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
         n_slices = len(slice_offsets(observer.spectral_bins, observer.spectral_rays))
         offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]

@@ -252,19 +252,27 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
         rng.mode = rngd->mode; jit.mode = rngd->mode;
         rng.mt.mt = st_path.data(); rng.mt.stride = 1; rng.mt.mti = RSB_MT_NN;
         jit.mt.mt = st_jit.data(); jit.mt.stride = 1; jit.mt.mti = RSB_MT_NN;
+        const int pairs = camera_jitter_pairs(cam.kind);
+        std::vector<double> pre((size_t)2 * pairs * spp);
         if (rngd->mode == RNG_MT19937_64) {
-            mt_seed_pair(rngd->seed + (uint64_t)pixel_id, 2 * spp, st_jit.data(), &jit.mt.mti, st_path.data(), &rng.mt.mti);
+            mt_seed_pair(rngd->seed + (uint64_t)pixel_id, 2 * pairs * spp, st_jit.data(), &jit.mt.mti, st_path.data(), &rng.mt.mti);
+            for (size_t k = 0; k < pre.size(); ++k) pre[k] = jit.uniform();      // the task's up-front draws, in draw order
         }
         double* m = mean + frame_row * bins;
         double* v = variance + frame_row * bins;
         for (int s = 0; s < spp; ++s) {
             if (rngd->mode == RNG_PHILOX) rng.px.init(rngd->seed, (uint64_t)pixel_id, (uint32_t)s);
-            double u1, u2;
-            if (rngd->mode == RNG_MT19937_64) { u1 = jit.uniform(); u2 = jit.uniform(); }
-            else { u1 = rng.uniform(); u2 = rng.uniform(); }
+            double u1, u2, u3 = 0.0, u4 = 0.0;
+            if (rngd->mode == RNG_MT19937_64) {
+                u1 = pre[2 * s]; u2 = pre[2 * s + 1];
+                if (pairs == 2) { u3 = pre[2 * spp + 2 * s]; u4 = pre[2 * spp + 2 * s + 1]; }
+            } else {
+                u1 = rng.uniform(); u2 = rng.uniform();
+                if (pairs == 2) { u3 = rng.uniform(); u4 = rng.uniform(); }
+            }
             V3 o, d;
             double weight;
-            pinhole_ray(cam, px, py, u1, u2, &o, &d, &weight);
+            pinhole_ray(cam, px, py, u1, u2, &o, &d, &weight, u3, u4);
             PathLog log;
             log.base = logbuf.data(); log.stride = 1; log.capacity = cap; log.n = 0; log.overflow = 0;
             uint32_t rays = 0;

@@ -291,6 +291,44 @@ def test_two_devices_in_one_process_equal_one_device(device, reference):
     second.close()
 
 
+def test_ccd_array_on_device_against_live_reference(device, reference):
+    """CCDArray (a bare sensor inside the Cornell box) with its default RGB pipeline and a spectral one through
+    CudaRenderEngine on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.optical.observer import CCDArray, RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+
+    def camera(world, samples):
+        pipe, rgb = api.SpectralPowerPipeline2D(), RGBPipeline2D(display_progress=False, accumulate=True)
+        cam = CCDArray((18, 14), width=0.4, parent=world, transform=api.translate(0.1, -0.05, -0.9) * api.rotate(8, -5, 3),
+                       pipelines=[pipe, rgb])
+        cam.spectral_rays = 1
+        cam.spectral_bins = 12
+        cam.spectral_rays = 2
+        cam.pixel_samples = samples
+        cam.ray_extinction_min_depth = 2
+        cam.ray_extinction_prob = 0.1
+        cam.quiet = True
+        return cam, pipe, rgb
+    cam, pipe, rgb = camera(scenes.cornell_box(api), 3)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 8086, passes=2)
+    x_ref = dict(mean=np.array(rgb.xyz_frame.mean), variance=np.array(rgb.xyz_frame.variance), samples=np.array(rgb.xyz_frame.samples))
+    cam2, pipe2, rgb2 = camera(scenes.cornell_box(api), 6)
+    cam2.render_engine = CudaRenderEngine(seed=8086, rng="mt", device=device, passes=2)
+    cam2.observe()
+
+    class F:  # noqa: E701
+        mean, variance, samples = np.array(pipe2.frame.mean), np.array(pipe2.frame.variance), np.array(pipe2.frame.samples)
+
+    class X:  # noqa: E701
+        mean, variance, samples = np.array(rgb2.xyz_frame.mean), np.array(rgb2.xyz_frame.variance), np.array(rgb2.xyz_frame.samples)
+    assert m_ref.max() > 0
+    print("ccd divergent fractions", parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6,
+                                                           max_divergent_fraction=0.0),
+          parity.compare_frame(X, x_ref, exact=False, rtol=1e-6, max_divergent_fraction=0.0))
+
+
 def test_hit_sweep_device_generated_rays(device):
     """config-5 style sweep: rays generated on device; hits/sum(t) must agree with the batched API on the same rays"""
     import ctypes as C

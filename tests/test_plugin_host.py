@@ -490,6 +490,43 @@ def test_render_engine_with_real_orthographic_camera(api, reference):
     assert m_ref.sum() > 0
 
 
+def _ccd_camera(api, world, pipelines, samples, bins=8, spectral_rays=2, pixels=(9, 7)):
+    from raysect.optical.observer import CCDArray
+    cam = CCDArray(pixels, width=0.4, parent=world, transform=api.translate(0.1, -0.05, -0.9) * api.rotate(8, -5, 3), pipelines=pipelines)
+    cam.spectral_rays = 1
+    cam.spectral_bins = bins
+    cam.spectral_rays = spectral_rays
+    cam.pixel_samples = samples
+    cam.ray_extinction_min_depth = 2
+    cam.ray_extinction_prob = 0.1
+    cam.quiet = True
+    return cam
+
+
+@pytest.mark.parametrize("passes", [1, 2])
+def test_ccd_array_matches_serial_reference(api, reference, passes):
+    """CCDArray (imaging/ccd.pyx): a bare sensor inside the Cornell box -- every sample leaves a random point of its pixel
+    in a cosine-weighted direction, the pixel task drawing all its points before all its directions -- through
+    CudaRenderEngine == the reference's SerialEngine, bit for bit, for the spectral and the (default) RGB pipeline."""
+    from raysect.optical.observer import RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    world = scenes.cornell_box(api)
+    pipe, rgb = api.SpectralPowerPipeline2D(), RGBPipeline2D(display_progress=False, accumulate=passes > 1)
+    cam = _ccd_camera(api, world, [pipe, rgb], samples=3)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 616, passes=passes)
+    assert m_ref.max() > 0 and n_ref.min() == 3 * passes
+    world2 = scenes.cornell_box(api)
+    pipe2, rgb2 = api.SpectralPowerPipeline2D(), RGBPipeline2D(display_progress=False)
+    cam2 = _ccd_camera(api, world2, [pipe2, rgb2], samples=3 * passes)
+    cam2.render_engine = CudaRenderEngine(seed=616, rng="mt", backend=hostsim_api.HostScene, passes=passes)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.samples), n_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    for name in ("mean", "variance", "samples"):
+        np.testing.assert_array_equal(np.array(getattr(rgb2.xyz_frame, name)), np.array(getattr(rgb.xyz_frame, name)))
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import PowerPipeline2D
     from source_b200.plugin import CudaRenderEngine
