@@ -144,15 +144,16 @@ typedef struct RsbSpectral {
     int32_t bins;
     int32_t n_materials;
     const double* tables;     /* [n_materials][bins] reflectivity | (surface or volume) emission | transmission | conductor index n */
-    const double* scale;      /* [n_materials] emitter scale | RoughConductor roughness */
-    const double* index_in;   /* [n_materials] dielectric index.average() */
-    const double* index_out;  /* [n_materials] dielectric external_index.average() */
+    const double* scale;      /* [n_materials] emitter scale | RoughConductor roughness | Checkerboard scale1 */
+    const double* index_in;   /* [n_materials] dielectric index.average() | Checkerboard scale2 */
+    const double* index_out;  /* [n_materials] dielectric external_index.average() | Checkerboard 1 / width */
     /* materials that sample TWO spectral functions (Conductor: index n -> row i, extinction k -> row table2[i]):
      * `tables` then holds n_tables >= n_materials rows, the extra rows after the per-material ones.
      * n_tables == 0 means n_materials rows and no second tables (table2 may be NULL). */
     int32_t n_tables;
     int32_t pad;
-    const int32_t* table2;    /* [n_materials] row of the material's second table, or -1 */
+    const int32_t* table2;    /* [n_materials] row of the material's second table, or -1.  An RSB_MAT_EMITTER with a second
+                               * table is a Checkerboard (emitter/checkerboard.pyx:38-146): emission of square two */
 } RsbSpectral;
 
 typedef struct RsbRngDesc {

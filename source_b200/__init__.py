@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 from .math3d import (AffineMatrix3D, BoundingBox3D, BoundingSphere3D, Normal3D, Point3D, Vector3D, rotate, rotate_x,
                      rotate_y, rotate_z, translate)
 from .spectral import ConstantSF, InterpolatedSF, NumericallyIntegratedSF, Sellmeier, SpectralFunction
-from .material import (AbsorbingSurface, Conductor, Dielectric, Lambert, Material, RoughConductor, UniformSurfaceEmitter,
+from .material import (AbsorbingSurface, Checkerboard, Conductor, Dielectric, Lambert, Material, RoughConductor, UniformSurfaceEmitter,
                        UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter, schott)
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Parabola, Primitive, Ray,
                          Sphere, Subtract, Union, World)

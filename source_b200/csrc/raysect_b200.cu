@@ -1080,6 +1080,8 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
         if ((ds->mat_type[i] == RSB_MAT_CONDUCTOR || ds->mat_type[i] == RSB_MAT_ROUGH_CONDUCTOR) &&
             (!spectral->table2 || spectral->table2[i] < 0 || spectral->table2[i] >= n_tables))
             return fail(RSB_ERR_ARG, "rsb_render: a Conductor needs its extinction table (RsbSpectral.table2)");
+    for (int i = 0; i < ds->n_materials && spectral->table2; ++i)
+        if (spectral->table2[i] >= n_tables) return fail(RSB_ERR_ARG, "rsb_render: RsbSpectral.table2 points past the tables");
     if (config->important_path_weight < 0 || config->important_path_weight > 1.0)
         return fail(RSB_ERR_ARG, "Important path weight must be in the range [0, 1].");
     if (rng->seed == 0) return fail(RSB_ERR_ARG, "rng seed must be >= 1");

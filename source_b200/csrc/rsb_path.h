@@ -102,6 +102,15 @@ RSB_HD V3 vector_cone_uniform(Rng& rng, double theta) {
     return v3(r * cos(phi), r * sin(phi), z);
 }
 
+// Checkerboard._flip (emitter/checkerboard.pyx:129-146): the coordinate rounded to the nanometre, its cell parity
+// (C fmod of |rwidth * p| by 2), inverted for negative coordinates
+RSB_HD bool checkerboard_flip(bool v, double p, double rwidth) {
+    p = round(p * 1e9) / 1e9;
+    if (fmod(fabs(rwidth * p), 2.0) >= 1.0) v = !v;
+    if (p < 0) v = !v;
+    return v;
+}
+
 // HemisphereCosineSampler.sample (core/math/sampler/solidangle.pyx:228-233) for the two draws it takes, in draw order
 RSB_HD V3 hemisphere_cosine_from(double u1, double u2) {
     double r = sqrt(u1);
@@ -308,7 +317,18 @@ RSB_HD int path_shade(const Scene& sc, const Spectral& sp, const RayConfig& cfg,
         log_volumes<FEAT>(sc, sp, o, w_hit, stack, log, stats);
 
         if (mtype == MAT_EMITTER) {
-            log.push(LOG_EMIT, mat.table, mat.scale);
+            if (mat.table2 >= 0) {
+                // Checkerboard.evaluate_surface (emitter/checkerboard.pyx:101-127): the parity of the LOCAL hit point's cell
+                // along x, y, z picks square one (row table, scale) or square two (row table2, index_in)
+                bool v = false;
+                v = checkerboard_flip(v, is.hit.x, mat.index_out);
+                v = checkerboard_flip(v, is.hit.y, mat.index_out);
+                v = checkerboard_flip(v, is.hit.z, mat.index_out);
+                if (v) log.push(LOG_EMIT, mat.table, mat.scale);
+                else log.push(LOG_EMIT, mat.table2, mat.index_in);
+            } else {
+                log.push(LOG_EMIT, mat.table, mat.scale);
+            }
             stats.table_read();
             return PATH_EMITTED;
         }

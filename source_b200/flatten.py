@@ -28,6 +28,7 @@ _SHAPES = {
 _MATERIALS = {
     "AbsorbingSurface": cabi.MAT_ABSORBER, "UniformSurfaceEmitter": cabi.MAT_EMITTER,
     "UnitySurfaceEmitter": cabi.MAT_EMITTER,     # emitter/unity.pyx:65-76: every bin 1.0 = a constant table, scale 1
+    "Checkerboard": cabi.MAT_EMITTER,            # emitter/checkerboard.pyx:38-146: two emission spectra, picked by the hit point
     "Lambert": cabi.MAT_LAMBERT, "Dielectric": cabi.MAT_DIELECTRIC,
     # HomogeneousVolumeEmitter subclasses with a direction-independent emission_function (homogeneous.pyx:40-93)
     "UniformVolumeEmitter": cabi.MAT_VOLUME_EMITTER, "UnityVolumeEmitter": cabi.MAT_VOLUME_EMITTER,
@@ -125,7 +126,9 @@ class FlatScene:
         (raysect/optical/spectralfunction.pyx:140-216); evaluated by the object model itself."""
         n = len(self.materials)
         # materials that sample two spectral functions (Conductor: index, extinction) get an extra table row each
-        second = [i for i, t in enumerate(self.mat_type) if t in (cabi.MAT_CONDUCTOR, cabi.MAT_ROUGH_CONDUCTOR)]
+        # (and Checkerboard: the emission of its second kind of square)
+        second = [i for i, (m, t) in enumerate(zip(self.materials, self.mat_type))
+                  if t in (cabi.MAT_CONDUCTOR, cabi.MAT_ROUGH_CONDUCTOR) or hasattr(m, "emission_spectrum2")]
         table2 = np.full(n, -1, dtype=np.int32)
         for j, i in enumerate(second):
             table2[i] = n + j
@@ -136,6 +139,14 @@ class FlatScene:
         for i, (m, t) in enumerate(zip(self.materials, self.mat_type)):
             if t == cabi.MAT_LAMBERT:
                 tables[i] = np.asarray(lambert_reflectivity(m).sample(min_wavelength, max_wavelength, bins))
+            elif t == cabi.MAT_EMITTER and hasattr(m, "emission_spectrum2"):
+                # Checkerboard (checkerboard.pyx:101-127): square one -> (row i, scale), square two -> (row table2[i], index_in);
+                # index_out carries 1 / width (its _rwidth)
+                tables[i] = np.asarray(m.emission_spectrum1.sample(min_wavelength, max_wavelength, bins))
+                tables[table2[i]] = np.asarray(m.emission_spectrum2.sample(min_wavelength, max_wavelength, bins))
+                scale[i] = m.scale1
+                index_in[i] = m.scale2
+                index_out[i] = 1.0 / m.width
             elif t in (cabi.MAT_EMITTER, cabi.MAT_VOLUME_EMITTER) and not hasattr(m, "emission_spectrum"):
                 tables[i] = 1.0     # Unity{Surface,Volume}Emitter (emitter/unity.pyx:73-75, 98): samples[:] = 1.0; 1.0 * 1.0 is exact
             elif t in (cabi.MAT_EMITTER, cabi.MAT_VOLUME_EMITTER):

@@ -50,6 +50,23 @@ class UniformSurfaceEmitter(Material):
         self.importance = 1.0
 
 
+class Checkerboard(Material):
+    """emitter/checkerboard.pyx:38-146: alternating squares of two emission spectra, picked by the local hit point"""
+
+    def __init__(self, width=1.0, emission_spectrum1=None, emission_spectrum2=None, scale1=0.25, scale2=0.5):
+        super().__init__()
+        if emission_spectrum1 is None or emission_spectrum2 is None:
+            raise TypeError("the stand-alone mirror has no d65_white: pass both emission spectra")
+        if width == 0:
+            raise ZeroDivisionError("float division")
+        self.width = float(width)
+        self.emission_spectrum1 = emission_spectrum1
+        self.emission_spectrum2 = emission_spectrum2
+        self.scale1 = float(scale1)
+        self.scale2 = float(scale2)
+        self.importance = 1.0
+
+
 class Conductor(Material):
     """conductor.pyx:39-147: specular reflection off a metal with complex refractive index n + ik (Fresnel)"""
 

@@ -527,6 +527,37 @@ def test_ccd_array_matches_serial_reference(api, reference, passes):
         np.testing.assert_array_equal(np.array(getattr(rgb2.xyz_frame, name)), np.array(getattr(rgb.xyz_frame, name)))
 
 
+def test_checkerboard_emitter_matches_serial_reference(api, reference):
+    """Checkerboard (emitter/checkerboard.pyx): the demos' favourite light -- squares of two emission spectra picked by
+    the parity of the local hit point's cell.  A rotated, translated checkerboard slab lighting a Lambert sphere and seen
+    directly, squares 0.23 m wide so that many cells (and negative coordinates) are hit: bit-exact frame."""
+    from raysect.optical.material import Checkerboard
+    from source_b200.plugin import CudaRenderEngine
+
+    def scene():
+        world = api.World()
+        api.Box(api.Point3D(-1.5, -0.05, -1.5), api.Point3D(1.5, 0.0, 1.5), parent=world,
+                transform=api.translate(0.1, -0.6, 0.3) * api.rotate(20, 5, -8),
+                material=Checkerboard(0.23, api.ConstantSF(1.0), api.InterpolatedSF([300, 500, 800], [0.2, 1.5, 0.4]), 0.3, 2.0))
+        api.Sphere(0.35, parent=world, transform=api.translate(-0.2, 0.0, 0.2), material=api.Lambert(api.ConstantSF(0.8)))
+        return world
+    kw = dict(pixels=(14, 11), samples=3, bins=9, spectral_rays=1)
+    w1 = scene()
+    cam, pipe = scenes.cornell_camera(api, w1, **kw)
+    cam.transform = api.translate(0, 0.3, -2.6) * api.rotate(0, -8, 0)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 1212)
+    w2 = scene()
+    cam2, pipe2 = scenes.cornell_camera(api, w2, **kw)
+    cam2.transform = api.translate(0, 0.3, -2.6) * api.rotate(0, -8, 0)
+    cam2.render_engine = CudaRenderEngine(seed=1212, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    # both kinds of square are seen: the frame holds pixels lit at both scales
+    lit = m_ref.sum(axis=2)
+    assert (lit > 0).sum() > 40 and len(np.unique(np.round(m_ref[:, :, 0][m_ref[:, :, 0] > 0], 12))) > 3
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import PowerPipeline2D
     from source_b200.plugin import CudaRenderEngine
