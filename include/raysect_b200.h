@@ -354,6 +354,27 @@ int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera,
 int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance,
                                int32_t* xyz_samples);
 /*
+ * The general form: up to RSB_PROJ_MAX projection channels per render, each summing one curve times the sample's spectrum
+ * over the bins in the operation order of the pixel processor it stands for, so that one render can feed an RGBPipeline2D
+ * (3 channels RSB_PROJ_XYZ: delta * sample * curve, the sum times the sensitivity), PowerPipeline2D's (one channel
+ * RSB_PROJ_POWER each: sample * filter * sensitivity * delta, raysect/optical/observer/pipeline/mono/power.pyx:768-779) and
+ * RadiancePipeline2D's (RSB_PROJ_RADIANCE: sample * filter * delta, mono/radiance.pyx:184-195) side by side.  curves is
+ * [n_slices][bins][n_channels].  rsb_slice_update_proj_frame merges channels [channel0, channel0 + n_channels) into HOST
+ * frame arrays with n_channels values per pixel ((nx, ny, 3) xyz_frame; (nx, ny) StatsArray2D of the mono pipelines) as
+ * the pipelines' update + finalise do (slices of a pass summed, passes merged with combine_samples; mono/power.pyx:516-556).
+ */
+#define RSB_PROJ_XYZ 0
+#define RSB_PROJ_POWER 1
+#define RSB_PROJ_RADIANCE 2
+#define RSB_PROJ_MAX 8
+int rsb_render_slices_proj(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config,
+                           const RsbSpectral* spectral, const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices,
+                           uint64_t seed_stride, int64_t n_pixels, const int32_t* pixels, int32_t n_channels,
+                           const int32_t* channel_mode, const double* curves, const double* delta_wavelength,
+                           int32_t keep_spectral, uint64_t* ray_count);
+int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channels, int32_t frame_is_empty,
+                                double* frame_mean, double* frame_variance, int32_t* frame_samples);
+/*
  * Several GPUs driven from ONE process (the reference's user runs one Python interpreter; its MulticoreEngine forks
  * workers and pickles per-pixel results back, raysect/core/workflow.py:123-327).  A communicator joins contexts on
  * different devices and enables peer access between them.  After every member has rendered ITS pixel list of the same

@@ -20,6 +20,7 @@ PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INT
 PRIM_PARABOLA = -1   # analytic primitives are the types <= PRIM_CONE (include/raysect_b200.h)
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER, MAT_ROUGH_CONDUCTOR = range(7)
 CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD = 0, 1, 2
+PROJ_XYZ, PROJ_POWER, PROJ_RADIANCE, PROJ_MAX = 0, 1, 2, 8
 RNG_MT19937_64, RNG_PHILOX = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -186,6 +187,10 @@ SIGNATURES = {
                                         C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, c_int32_p, c_double_p,
                                         c_double_p, C.c_int32, c_uint64_p]),
     "rsb_slice_update_xyz_frame": (C.c_int, [_U64, C.c_int32, c_double_p, c_double_p, c_int32_p]),
+    "rsb_render_slices_proj": (C.c_int, [_U64, _U64, C.POINTER(RsbCamera), C.POINTER(RsbRayConfig), C.POINTER(RsbSpectral),
+                                         C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, c_int32_p, C.c_int32, c_int32_p,
+                                         c_double_p, c_double_p, C.c_int32, c_uint64_p]),
+    "rsb_slice_update_proj_frame": (C.c_int, [_U64, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "rsb_comm_create": (C.c_int, [C.c_int32, c_uint64_p, c_uint64_p]),
     "rsb_comm_destroy": (C.c_int, [_U64]),
     "rsb_comm_gather_slices": (C.c_int, [_U64, C.c_int32]),

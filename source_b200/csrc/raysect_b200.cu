@@ -68,7 +68,7 @@ struct Context {
     struct {
         int32_t nx = 0, ny = 0, bins = 0, samples = 0; int64_t n_pixels = 0; bool listed = false, valid = false;
         bool has_bins = false, has_xyz = false;      // which statistics the render kept (spectral frame / XYZ work items)
-        int32_t n_passes = 0, n_slices = 0, pass_samples = 0;
+        int32_t n_passes = 0, n_slices = 0, pass_samples = 0, n_channels = 0, slice_bins = 0;
     } slice;
     // RGB side of rsb_render_slices_xyz: curves [n_slices][bins][3] | delta [n_slices] | mean [work items][3] | variance [same];
     // the (nx, ny, 3) host frames pass through d_xyz_frame (mean | variance) and d_xyz_samples
@@ -910,7 +910,7 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (smem_shade > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_shade<RNGMODE, COUNT, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_shade));
     smem_tables += (threads / 32) * 32 * sizeof(LogEntry);   // k_wf_finalize: one 32-entry log window per warp
-    if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * 3 * a.sp.bins * sizeof(double);   // and the XYZ terms of one sample per warp (RGB)
+    if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * a.proj_channels * a.sp.bins * sizeof(double);   // and the projection terms of one sample per warp
     if (smem_tables > 200 * 1024) return fail(RSB_ERR_UNSUPPORTED, "rsb_render: too many bins per slice for the RGB projection (shared memory)");
     if (smem_tables > 48 * 1024)
         RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
@@ -1044,6 +1044,8 @@ struct XyzDev {
     const double* delta = nullptr;
     double* mean = nullptr;
     double* variance = nullptr;
+    int32_t n_channels = 0;
+    int32_t mode[RSB_PROJ_MAX] = {0};
 };
 
 static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, const RsbCamera* camera, const RsbRayConfig* config,
@@ -1185,6 +1187,8 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     a.xyz_delta = xyz.delta;
     a.xyz_mean = xyz.mean;
     a.xyz_variance = xyz.variance;
+    a.proj_channels = xyz.n_channels;
+    for (int k = 0; k < RSB_PROJ_MAX; ++k) a.proj_mode[k] = xyz.mode[k];
     a.ray_count = (unsigned long long*)ray_count_dev;
     a.work_counter = c->d_scalars;
     a.n_idle = (unsigned int*)(c->d_scalars + 1);
@@ -1321,15 +1325,20 @@ int rsb_render_slice(uint64_t ctx, uint64_t scene, const RsbCamera* camera, cons
 
 static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                               const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
-                              const int32_t* pixels, const double* resampled_xyz, const double* delta_wavelength, bool keep_spectral,
-                              uint64_t* ray_count) {
+                              const int32_t* pixels, int32_t n_channels, const int32_t* channel_mode, const double* resampled_xyz,
+                              const double* delta_wavelength, bool keep_spectral, uint64_t* ray_count) {
     Context* c = as_ctx(ctx);
     if (!c || !as_scene(scene) || !camera || !config || !ray_count) return fail(RSB_ERR_ARG, "rsb_render_slice: null argument");
     if (n_slices < 1) return fail(RSB_ERR_ARG, "rsb_render_slices: the number of slices must be at least 1");
     if (n_passes < 1) return fail(RSB_ERR_ARG, "rsb_render_passes: the number of passes must be in [1, 1024]");
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     const bool want_xyz = resampled_xyz != nullptr;
-    if (want_xyz && !delta_wavelength) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: null argument");
+    if (want_xyz && (!delta_wavelength || !channel_mode)) return fail(RSB_ERR_ARG, "rsb_render_slices_proj: null argument");
+    if (want_xyz && (n_channels < 1 || n_channels > RSB_PROJ_MAX))
+        return fail(RSB_ERR_ARG, "rsb_render_slices_proj: the number of projection channels must be in [1, 8]");
+    for (int k = 0; want_xyz && k < n_channels; ++k)
+        if (channel_mode[k] != RSB_PROJ_XYZ && channel_mode[k] != RSB_PROJ_POWER && channel_mode[k] != RSB_PROJ_RADIANCE)
+            return fail(RSB_ERR_ARG, "rsb_render_slices_proj: unknown channel mode");
     if (!want_xyz && !keep_spectral) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: nothing to render (no XYZ curves, no spectral frame)");
     RSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -1345,8 +1354,8 @@ static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* cam
     }
     XyzDev xyz;
     if (want_xyz) {
-        const size_t n_tab = (size_t)n_slices * config->bins * 3, n_work = (size_t)n_pixels * n_passes * n_slices;
-        const size_t need = n_tab + (size_t)n_slices + 2 * 3 * n_work;
+        const size_t n_tab = (size_t)n_slices * config->bins * n_channels, n_work = (size_t)n_pixels * n_passes * n_slices;
+        const size_t need = n_tab + (size_t)n_slices + 2 * (size_t)n_channels * n_work;
         if (c->xyz_cap < need) {
             cudaFree(c->d_xyz);
             c->d_xyz = nullptr; c->xyz_cap = 0;
@@ -1358,7 +1367,9 @@ static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* cam
         xyz.tab = c->d_xyz;
         xyz.delta = c->d_xyz + n_tab;
         xyz.mean = c->d_xyz + n_tab + n_slices;
-        xyz.variance = xyz.mean + 3 * n_work;
+        xyz.variance = xyz.mean + (size_t)n_channels * n_work;
+        xyz.n_channels = n_channels;
+        for (int k = 0; k < n_channels; ++k) xyz.mode[k] = channel_mode[k];
     }
     if (!c->d_slice_rays) RSB_CUDA(cudaMalloc(&c->d_slice_rays, 8));
     if (pixels && c->slice_pix_cap < (size_t)n_pixels) {
@@ -1390,6 +1401,8 @@ static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* cam
     c->slice.listed = pixels != nullptr;
     c->slice.has_bins = keep_spectral;
     c->slice.has_xyz = want_xyz;
+    c->slice.n_channels = want_xyz ? n_channels : 0;
+    c->slice.slice_bins = config->bins;
     c->slice.n_passes = n_passes; c->slice.n_slices = n_slices; c->slice.pass_samples = camera->pixel_samples;
     c->slice.valid = true;
     return RSB_OK;
@@ -1398,28 +1411,40 @@ static int render_slices_host(uint64_t ctx, uint64_t scene, const RsbCamera* cam
 int rsb_render_slices(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                       const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
                       const int32_t* pixels, uint64_t* ray_count) {
-    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, nullptr, nullptr,
-                              true, ray_count);
+    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, 0, nullptr, nullptr,
+                              nullptr, true, ray_count);
+}
+
+int rsb_render_slices_proj(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
+                           const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
+                           const int32_t* pixels, int32_t n_channels, const int32_t* channel_mode, const double* curves,
+                           const double* delta_wavelength, int32_t keep_spectral, uint64_t* ray_count) {
+    if (!curves || !delta_wavelength || !channel_mode) return fail(RSB_ERR_ARG, "rsb_render_slices_proj: null argument");
+    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, n_channels,
+                              channel_mode, curves, delta_wavelength, keep_spectral != 0, ray_count);
 }
 
 int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
                           const RsbRngDesc* rng, int32_t n_passes, int32_t n_slices, uint64_t seed_stride, int64_t n_pixels,
                           const int32_t* pixels, const double* resampled_xyz, const double* delta_wavelength, int32_t keep_spectral,
                           uint64_t* ray_count) {
-    if (!resampled_xyz || !delta_wavelength) return fail(RSB_ERR_ARG, "rsb_render_slices_xyz: null argument");
-    return render_slices_host(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, resampled_xyz,
-                              delta_wavelength, keep_spectral != 0, ray_count);
+    const int32_t modes[3] = {RSB_PROJ_XYZ, RSB_PROJ_XYZ, RSB_PROJ_XYZ};
+    return rsb_render_slices_proj(ctx, scene, camera, config, spectral, rng, n_passes, n_slices, seed_stride, n_pixels, pixels, 3, modes,
+                                  resampled_xyz, delta_wavelength, keep_spectral, ray_count);
 }
 
-int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance, int32_t* xyz_samples) {
+int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channels, int32_t frame_is_empty, double* frame_mean,
+                                double* frame_variance, int32_t* frame_samples) {
     Context* c = as_ctx(ctx);
-    if (!c || !xyz_mean || !xyz_variance || !xyz_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_xyz_frame: null argument");
+    if (!c || !frame_mean || !frame_variance || !frame_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_proj_frame: null argument");
     if (!c->slice.valid || !c->slice.has_xyz)
-        return fail(RSB_ERR_ARG, "rsb_slice_update_xyz_frame: no rendered XYZ statistics are held (call rsb_render_slices_xyz first)");
+        return fail(RSB_ERR_ARG, "rsb_slice_update_proj_frame: no rendered projection statistics are held (call rsb_render_slices_proj first)");
+    if (channel0 < 0 || n_channels < 1 || channel0 + n_channels > c->slice.n_channels)
+        return fail(RSB_ERR_ARG, "rsb_slice_update_proj_frame: channel range outside the rendered channels");
     if (c->slice.n_pixels == 0) return RSB_OK;
     RSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    const size_t elems = (size_t)c->slice.nx * c->slice.ny * 3;
+    const size_t elems = (size_t)c->slice.nx * c->slice.ny * n_channels;
     if (c->xyz_frame_cap < elems) {
         cudaFree(c->d_xyz_frame); cudaFree(c->d_xyz_samples);
         c->d_xyz_frame = nullptr; c->d_xyz_samples = nullptr; c->xyz_frame_cap = 0;
@@ -1433,23 +1458,31 @@ int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz
         RSB_CUDA(cudaMemsetAsync(d_fm, 0, 2 * elems * sizeof(double), st));
         RSB_CUDA(cudaMemsetAsync(c->d_xyz_samples, 0, elems * sizeof(int32_t), st));
     } else {
-        RSB_CUDA(cudaMemcpyAsync(d_fm, xyz_mean, elems * 8, cudaMemcpyHostToDevice, st));
-        RSB_CUDA(cudaMemcpyAsync(d_fv, xyz_variance, elems * 8, cudaMemcpyHostToDevice, st));
-        RSB_CUDA(cudaMemcpyAsync(c->d_xyz_samples, xyz_samples, elems * 4, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(d_fm, frame_mean, elems * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(d_fv, frame_variance, elems * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(c->d_xyz_samples, frame_samples, elems * 4, cudaMemcpyHostToDevice, st));
     }
-    const size_t n_tab = (size_t)c->slice.bins * 3;     // slice.bins = n_slices * bins per slice
+    const int nch = c->slice.n_channels;
+    const size_t n_tab = (size_t)c->slice.n_slices * c->slice.slice_bins * nch;
     const size_t n_work = (size_t)c->slice.n_pixels * c->slice.n_passes * c->slice.n_slices;
     const double* wm = c->d_xyz + n_tab + c->slice.n_slices;
-    const double* wv = wm + 3 * n_work;
-    k_xyz_combine<<<grid_for(c, (long long)c->slice.n_pixels * 3, 256, 4), 256, 0, st>>>(
+    const double* wv = wm + (size_t)nch * n_work;
+    k_xyz_combine<<<grid_for(c, (long long)c->slice.n_pixels * n_channels, 256, 4), 256, 0, st>>>(
         c->slice.n_pixels, c->slice.listed ? c->d_slice_pix : nullptr, c->slice.ny, c->slice.n_passes, c->slice.n_slices, c->slice.pass_samples,
-        wm, wv, d_fm, d_fv, c->d_xyz_samples);
+        nch, channel0, n_channels, wm, wv, d_fm, d_fv, c->d_xyz_samples);
     RSB_CUDA(cudaGetLastError());
-    RSB_CUDA(cudaMemcpyAsync(xyz_mean, d_fm, elems * 8, cudaMemcpyDeviceToHost, st));
-    RSB_CUDA(cudaMemcpyAsync(xyz_variance, d_fv, elems * 8, cudaMemcpyDeviceToHost, st));
-    RSB_CUDA(cudaMemcpyAsync(xyz_samples, c->d_xyz_samples, elems * 4, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpyAsync(frame_mean, d_fm, elems * 8, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpyAsync(frame_variance, d_fv, elems * 8, cudaMemcpyDeviceToHost, st));
+    RSB_CUDA(cudaMemcpyAsync(frame_samples, c->d_xyz_samples, elems * 4, cudaMemcpyDeviceToHost, st));
     RSB_CUDA(cudaStreamSynchronize(st));
     return RSB_OK;
+}
+
+int rsb_slice_update_xyz_frame(uint64_t ctx, int32_t frame_is_empty, double* xyz_mean, double* xyz_variance, int32_t* xyz_samples) {
+    Context* c = as_ctx(ctx);
+    if (c && c->slice.valid && c->slice.has_xyz && c->slice.n_channels != 3)
+        return fail(RSB_ERR_ARG, "rsb_slice_update_xyz_frame: the held statistics are not those of rsb_render_slices_xyz");
+    return rsb_slice_update_proj_frame(ctx, 0, 3, frame_is_empty, xyz_mean, xyz_variance, xyz_samples);
 }
 
 int rsb_slice_read(uint64_t ctx, double* mean, double* variance) {

@@ -402,10 +402,15 @@ struct WfArgs {
     // RGBPipeline2D (rgb.pyx:216-290): every sample's spectrum is also projected on the CIE XYZ curves and the three
     // tristimulus values get their own per-work-item Welford statistics.  Null xyz_mean = no RGB pipeline; null mean = no
     // spectral pipeline (the per-bin statistics are then not kept at all).
-    const double* xyz_tab;      // [n_slices][bins][3]: resample_ciexyz of every slice's wavelength range
+    // Generalised to "projection channels": every channel sums one curve times the sample's spectrum over the bins, in the
+    // operation order of the pixel processor it stands for (proj_mode: RSB_PROJ_XYZ rgb.pyx:550-558 / colour.pyx:178-186;
+    // RSB_PROJ_POWER mono/power.pyx:768-779; RSB_PROJ_RADIANCE mono/radiance.pyx:184-195).
+    const double* xyz_tab;      // [n_slices][bins][proj_channels]: the curves resampled on every slice's wavelength range
     const double* xyz_delta;    // [n_slices]: Spectrum.delta_wavelength of every slice
-    double* xyz_mean;           // [work items][3], work item g = group * n_pix_pass + task (group = pass * n_slices + slice)
+    double* xyz_mean;           // [work items][proj_channels], work item g = group * n_pix_pass + task (group = pass * n_slices + slice)
     double* xyz_variance;
+    int32_t proj_channels;      // 1 .. RSB_PROJ_MAX
+    int32_t proj_mode[8];
     unsigned long long seed_stride;   // pass p draws from streams seeded seed + p * seed_stride + y * nx + x
     int32_t n_passes;
     int32_t n_slices;           // spectral slices rendered concurrently; `sp` describes slice 0, slice k follows at strides
@@ -879,6 +884,23 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
     }
 }
 
+// The term a bin contributes to every projection channel, in the pixel processor's own operation order:
+//   XYZ       delta * sample * curve                      (spectrum_to_ciexyz, colour.pyx:182-184)
+//   POWER     sample * filter * sensitivity * delta       (PowerPixelProcessor.add_sample, mono/power.pyx:776-777)
+//   RADIANCE  sample * filter * delta                     (RadiancePixelProcessor.add_sample, mono/radiance.pyx:192-193)
+__device__ __forceinline__ void proj_terms(const WfArgs& a, int nch, double x, double delta, const double* __restrict__ curve,
+                                           double* __restrict__ out) {
+    for (int ch = 0; ch < nch; ++ch) {
+        const double cv = __ldg(curve + ch);
+        const int mode = a.proj_mode[ch];
+        double t;
+        if (mode == RSB_PROJ_XYZ) t = (delta * x) * cv;
+        else if (mode == RSB_PROJ_POWER) t = ((x * cv) * a.cam.sensitivity) * delta;
+        else t = (x * cv) * delta;
+        out[ch] = t;
+    }
+}
+
 // 1 warp = 1 ended path: the reference's unwind (per-bin multiplies), projection weight, sensitivity and
 // PixelProcessor.add_sample (Welford) for bins lane, lane+32, ...
 template <int RNGMODE, bool COUNT>
@@ -896,9 +918,10 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     }
     // 32 log entries per warp, staged in shared memory and read back as one broadcast LDS.128 per entry
     LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;
-    // RGB: the sample's three products per bin (delta * sample * curve), one row of 3 * bins doubles per warp, behind the
-    // log windows
-    double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * 3 * sp.bins;
+    // projections (RGB / mono pipelines): the sample's per-bin terms of every channel, one row of channels * bins doubles
+    // per warp, behind the log windows
+    const int nch = a.proj_channels;
+    double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * nch * sp.bins;
     const bool keep_bins = a.mean != nullptr, keep_xyz = a.xyz_mean != nullptr;
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
@@ -929,7 +952,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         // (with emitting volumes in the scene a path that ended dark may still carry what they added on the way)
         const bool emit = status == SLOT_ENDED_EMIT || (a.has_additive && a.st.additive[slot] != 0);
         const double xyz_delta = keep_xyz ? a.xyz_delta[slice] : 0.0;
-        const double* xyz_curve = keep_xyz ? a.xyz_tab + (size_t)slice * bins * 3 : nullptr;
+        const double* xyz_curve = keep_xyz ? a.xyz_tab + (size_t)slice * bins * nch : nullptr;
         for (int b0 = 0; b0 < bins; b0 += 64) {
             // two bins per lane per pass; the statistics rows are fetched before the replay so that their
             // latency overlaps it
@@ -958,13 +981,9 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (ha) {
                 double x = xa * w;              // spectrum.mul_scalar(projection_weight), observer.pyx:408
-                if (keep_xyz) {
-                    // the terms of spectrum_to_ciexyz's sums (colour.pyx:182-184), delta * sample * curve, formed by the
-                    // bin's own lane; only the additions below are a serial chain
-                    const double dx = xyz_delta * x;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) wspec[3 * ba + ch] = dx * __ldg(xyz_curve + 3 * ba + ch);
-                }
+                // the terms of the pixel processors' sums, formed by the bin's own lane; only the additions below are a
+                // serial chain
+                if (keep_xyz) proj_terms(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * ba, wspec + (size_t)nch * ba);
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
                     welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
@@ -972,11 +991,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (hb) {
                 double x = xb * w;
-                if (keep_xyz) {
-                    const double dx = xyz_delta * x;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) wspec[3 * bb + ch] = dx * __ldg(xyz_curve + 3 * bb + ch);
-                }
+                if (keep_xyz) proj_terms(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * bb, wspec + (size_t)nch * bb);
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;
                     welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
@@ -985,43 +1000,48 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
         }
         if (keep_xyz) {
             // XYZPixelProcessor.add_sample (rgb.pyx:550-558): spectrum_to_ciexyz sums delta * sample * curve over the bins
-            // in index order (colour.pyx:178-186) -- a serial chain of additions, so lanes 0..2 walk one channel each
+            // in index order (colour.pyx:178-186) -- a serial chain of additions, so lanes 0..channels-1 walk one channel each
             // (the terms are in shared memory already: the chain is bins x one DADD) -- then the tristimulus value times
             // the sensitivity enters the channel's running statistics
             __syncwarp();
-            if (lane < 3) {
+            if (lane < nch) {
                 double acc = 0.0;
 #pragma unroll 8
-                for (int i = 0; i < bins; ++i) acc += wspec[3 * i + lane];
-                const size_t item = ((size_t)a.item_base + (size_t)a.st.work[slot]) * 3 + lane;
+                for (int i = 0; i < bins; ++i) acc += wspec[nch * i + lane];
+                const size_t item = ((size_t)a.item_base + (size_t)a.st.work[slot]) * nch + lane;
                 double pm = 0, pv = 0;
                 if (s > 0) { pm = a.xyz_mean[item]; pv = a.xyz_variance[item]; }
-                welford_add_r(acc * a.cam.sensitivity, pm, pv, s, r_nn, r_nn1, a.xyz_mean + item, a.xyz_variance + item);
+                // (XYZ: the tristimulus value times the sensitivity, rgb.pyx:556-558; the mono processors fold the
+                // sensitivity into their terms or ignore it)
+                const double value = a.proj_mode[lane] == RSB_PROJ_XYZ ? acc * a.cam.sensitivity : acc;
+                welford_add_r(value, pm, pv, s, r_nn, r_nn1, a.xyz_mean + item, a.xyz_variance + item);
             }
             __syncwarp();
         }
     }
 }
 
-// RGBPipeline2D.update + finalise for every listed pixel (rgb.pyx:249-290): the per-slice (mean, variance) of a pass are
-// summed in slice order into the pass's working values, which are merged into the frame with combine_samples; the passes
-// of a pixel are merged in order by the same thread, one thread per (pixel, channel).
+// RGBPipeline2D / PowerPipeline2D / RadiancePipeline2D .update + finalise for every listed pixel (rgb.pyx:249-290,
+// mono/power.pyx:516-556): the per-slice (mean, variance) of a pass are summed in slice order into the pass's working
+// values, which are merged into the frame with combine_samples; the passes of a pixel are merged in order by the same
+// thread, one thread per (pixel, channel).  The frame holds `nc` channels per pixel, channels [c0, c0 + nc) of the `nch`
+// projection channels of the render.
 __global__ void k_xyz_combine(long long n_pixels, const int32_t* __restrict__ pixels, int ny, int n_passes, int n_slices, int samples,
-                              const double* __restrict__ xyz_mean, const double* __restrict__ xyz_variance,
+                              int nch, int c0, int nc, const double* __restrict__ xyz_mean, const double* __restrict__ xyz_variance,
                               double* __restrict__ fmean, double* __restrict__ fvar, int32_t* __restrict__ fsamples) {
-    long long total = n_pixels * 3;
+    long long total = n_pixels * nc;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        long long p = i / 3;
-        int ch = (int)(i % 3);
+        long long p = i / nc;
+        int ch = (int)(i % nc);
         long long row = pixels ? ((long long)pixels[2 * p] * ny + pixels[2 * p + 1]) : p;
-        long long dst = row * 3 + ch;
+        long long dst = row * nc + ch;
         double fm = fmean[dst], fv = fvar[dst];
         int fn = fsamples[dst];
         for (int pass = 0; pass < n_passes; ++pass) {
             double wm = 0.0, wv = 0.0;
             for (int k = 0; k < n_slices; ++k) {
-                long long src = (((long long)pass * n_slices + k) * n_pixels + p) * 3 + ch;
+                long long src = (((long long)pass * n_slices + k) * n_pixels + p) * nch + c0 + ch;
                 wm += xyz_mean[src];
                 wv += xyz_variance[src];
             }

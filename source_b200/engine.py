@@ -225,10 +225,11 @@ class Accelerator:
         of the engine / mirror camera).  The frame with ``len(spectrals)*config.bins`` bins per pixel stays on the device
         as the held slice; returns the ray count.
 
-        ``xyz`` = (resampled_xyz, delta_wavelength) -- ``(n_slices, bins, 3)`` CIE curves resampled on every slice's range
-        (colour.resample_ciexyz) and every slice's Spectrum.delta_wavelength -- also keeps what RGBPipeline2D's pixel
-        processors would (rsb_render_slices_xyz), for ``update_xyz_frame``; ``keep_spectral=False`` then drops the per-bin
-        frame."""
+        ``xyz`` = (curves, delta_wavelength[, modes]) -- ``(n_slices, bins, n_channels)`` curves resampled on every slice's
+        range, every slice's Spectrum.delta_wavelength and one ``cabi.PROJ_*`` mode per channel (default: three PROJ_XYZ
+        channels = colour.resample_ciexyz for an RGBPipeline2D) -- also keeps what the pipelines' pixel processors would
+        (rsb_render_slices_proj), for ``update_xyz_frame`` / ``update_proj_frame``; ``keep_spectral=False`` then drops the
+        per-bin frame."""
         rng = cabi.RsbRngDesc(mode=int(rng_mode), seed=int(seed))
         rays = C.c_uint64(0)
         pix, n = None, camera.nx * camera.ny
@@ -241,21 +242,38 @@ class Accelerator:
         stride = camera.nx * camera.ny if seed_stride is None else int(seed_stride)
         if xyz is None:
             if not keep_spectral:
-                raise ValueError("nothing to render: no XYZ curves and no spectral frame")
+                raise ValueError("nothing to render: no projection curves and no spectral frame")
             cabi.check(self.lib.rsb_render_slices(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
                                                   int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32), C.byref(rays)))
         else:
             curves = np.ascontiguousarray(xyz[0], dtype=np.float64)
             delta = np.ascontiguousarray(xyz[1], dtype=np.float64).reshape(-1)
-            if curves.shape != (len(spectrals), config.bins, 3) or delta.shape != (len(spectrals),):
-                raise ValueError("xyz must be ((n_slices, bins, 3) curves, (n_slices,) delta_wavelength)")
-            cabi.check(self.lib.rsb_render_slices_xyz(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
-                                                      int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32),
-                                                      cabi.ptr(curves, C.c_double), cabi.ptr(delta, C.c_double), int(bool(keep_spectral)),
-                                                      C.byref(rays)))
+            if curves.ndim != 3 or curves.shape[:2] != (len(spectrals), config.bins) or delta.shape != (len(spectrals),):
+                raise ValueError("xyz must be ((n_slices, bins, n_channels) curves, (n_slices,) delta_wavelength[, modes])")
+            modes = np.ascontiguousarray(xyz[2] if len(xyz) > 2 else [cabi.PROJ_XYZ] * curves.shape[2], dtype=np.int32)
+            if modes.shape != (curves.shape[2],):
+                raise ValueError("one projection mode per channel")
+            cabi.check(self.lib.rsb_render_slices_proj(self.device.ctx, self.scene, C.byref(camera), C.byref(config), arr, C.byref(rng),
+                                                       int(passes), len(spectrals), stride, n, cabi.ptr(pix, C.c_int32),
+                                                       int(curves.shape[2]), cabi.ptr(modes, C.c_int32), cabi.ptr(curves, C.c_double),
+                                                       cabi.ptr(delta, C.c_double), int(bool(keep_spectral)), C.byref(rays)))
         self._keep = list(spectrals)      # the tables the descriptors point at must outlive the call
         self._slice_shape = (camera.nx, camera.ny, config.bins * len(spectrals))
         return rays.value
+
+    def update_proj_frame(self, channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=False):
+        """Pipeline.update + finalise for every listed pixel of the render done last with ``xyz=``: merges projection channels
+        ``channel0 ..`` into the HOST frame arrays -- (nx, ny, k) or, for one channel, (nx, ny) StatsArray buffers, modified in
+        place -- on the device (rsb_slice_update_proj_frame)."""
+        nx, ny = self._slice_shape[:2]
+        k = 1 if frame_mean.ndim == 2 else frame_mean.shape[2]
+        for a, dt in ((frame_mean, np.float64), (frame_variance, np.float64), (frame_samples, np.int32)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable
+                    and a.shape in ((nx, ny, k), (nx, ny)) and a.size == nx * ny * k):
+                raise TypeError("frame arrays must be writable C-contiguous (nx, ny[, channels]) float64 / int32 numpy arrays")
+        cabi.check(self.lib.rsb_slice_update_proj_frame(self.device.ctx, int(channel0), int(k), int(bool(frame_is_empty)),
+                                                        cabi.ptr(frame_mean, C.c_double), cabi.ptr(frame_variance, C.c_double),
+                                                        cabi.ptr(frame_samples, C.c_int32)))
 
     def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
         """RGBPipeline2D.update + finalise for every listed pixel of the render done last with ``xyz=``: merges its XYZ
@@ -369,6 +387,12 @@ class DeviceGroup:
             raise RuntimeError("update_xyz_frame must precede update_frame after a multi-device render")
         for k, m in enumerate(self.members):
             m.update_xyz_frame(xyz_mean, xyz_variance, xyz_samples, frame_is_empty=frame_is_empty and k == 0)
+
+    def update_proj_frame(self, channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=False):
+        if self._rows_gathered:
+            raise RuntimeError("update_proj_frame must precede update_frame after a multi-device render")
+        for k, m in enumerate(self.members):
+            m.update_proj_frame(channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=frame_is_empty and k == 0)
 
     def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
         if not self._rows_gathered:

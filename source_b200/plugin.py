@@ -267,18 +267,19 @@ class CudaRenderEngine(RenderEngine):
         return mean, variance, rays
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import (CCDArray, OrthographicCamera, PinholeCamera, RGBPipeline2D, SpectralPowerPipeline2D,
-                                              SpectralRadiancePipeline2D)
+        from raysect.optical.observer import (CCDArray, OrthographicCamera, PinholeCamera, PowerPipeline2D, RadiancePipeline2D,
+                                              RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D)
         observer = getattr(render, "__self__", None)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray)):
             raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera and CCDArray observers; got %r "
                                       "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
-            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D)):
-                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D / RGBPipeline2D "
-                                          "pipelines; got %r (no CPU fallback)" % type(p).__name__)
-        rgb = [p for p in pipelines if isinstance(p, RGBPipeline2D)]
+            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D)):
+                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D / RGBPipeline2D / "
+                                          "PowerPipeline2D / RadiancePipeline2D pipelines; got %r (no CPU fallback)" % type(p).__name__)
+        # pipelines whose pixel processors PROJECT every sample's spectrum on curves (CIE XYZ; a filter): done on the device
+        rgb = [p for p in pipelines if isinstance(p, (RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D))]
 
         def frame_of(p):
             return p.xyz_frame if isinstance(p, RGBPipeline2D) else p.frame
@@ -313,7 +314,12 @@ class CudaRenderEngine(RenderEngine):
         pixel_sensitivity = float(observer._pixel_sensitivity(0, 0))
 
         def sens_of(p):
-            return 1.0 if isinstance(p, SpectralRadiancePipeline2D) else pixel_sensitivity
+            if isinstance(p, SpectralRadiancePipeline2D):
+                return 1.0
+            if isinstance(p, RadiancePipeline2D):
+                # (its processor ignores the sensitivity, mono/radiance.pyx:184-195: it rides with whichever render there is)
+                return pixel_sensitivity if any(not isinstance(q, (SpectralRadiancePipeline2D, RadiancePipeline2D)) for q in pipelines) else 1.0
+            return pixel_sensitivity
         kw = dict(passes=self.passes, seed_stride=observer.spectral_rays * nx * ny) if self.passes > 1 else {}
         n_slices = len(slice_offsets(observer.spectral_bins, observer.spectral_rays))
         offset = slice_offsets(observer.spectral_bins, observer.spectral_rays)[slice_id]
@@ -343,8 +349,8 @@ class CudaRenderEngine(RenderEngine):
         if rgb and all_slices is None:
             # XYZPixelProcessor's per-sample projection (rgb.pyx:550-558) runs inside the device's accumulate kernel and the
             # slices of a pixel are summed before they enter the frame (rgb.pyx:259-265): the all-slices device path only
-            raise NotImplementedError("RGBPipeline2D needs CudaRenderEngine's whole-slice device path: bulk_update=True, one device, "
-                                      "spectral slices of equal size (spectral_bins divisible by spectral_rays)")
+            raise NotImplementedError("RGBPipeline2D / PowerPipeline2D / RadiancePipeline2D need CudaRenderEngine's whole-slice device "
+                                      "path: bulk_update=True, spectral slices of equal size (spectral_bins divisible by spectral_rays)")
         if all_slices is not None and slice_id > 0:
             if slice_id == n_slices - 1:
                 self.seed += self.passes * n_slices * nx * ny
@@ -361,22 +367,39 @@ class CudaRenderEngine(RenderEngine):
                 group = [p for p in pipelines if sens_of(p) == sensitivity]
                 empty = {id(p): not np.asarray(frame_of(p).samples).any() for p in group}
                 ready = self._frames_ready_start(accel, group, empty, frame_of)
-                xyz = None
+                xyz, channel_of = None, {}
                 if any(p in rgb for p in group):
-                    # what RGBPipeline2D.initialise hands its pixel processors (rgb.pyx:232-233), and the delta_wavelength
-                    # of the slice's Spectrum (spectrum.pyx: (max - min) / bins)
+                    # the curves the pipelines' initialise() hands their pixel processors (rgb.pyx:232-233: resample_ciexyz;
+                    # mono/power.pyx:501: filter.sample_mv), one set per slice, and the delta_wavelength of the slice's
+                    # Spectrum (spectrum.pyx:132: (max - min) / bins)
                     from raysect.optical.colour import resample_ciexyz
-                    xyz = (np.stack([np.asarray(resample_ciexyz(sl.min_wavelength, sl.max_wavelength, sl.bins)) for sl in all_slices]),
-                           np.array([(sl.max_wavelength - sl.min_wavelength) / sl.bins for sl in all_slices]))
+                    curves, modes = [], []
+                    for p in group:
+                        if p not in rgb:
+                            continue
+                        channel_of[id(p)] = len(modes)
+                        if isinstance(p, RGBPipeline2D):
+                            curves.append(np.stack([np.asarray(resample_ciexyz(sl.min_wavelength, sl.max_wavelength, sl.bins)) for sl in all_slices]))
+                            modes += [cabi.PROJ_XYZ] * 3
+                        else:
+                            curves.append(np.stack([np.asarray(p.filter.sample(sl.min_wavelength, sl.max_wavelength, sl.bins))[:, None]
+                                                    for sl in all_slices]))
+                            # (RadiancePipeline2D subclasses PowerPipeline2D, mono/radiance.pyx:121)
+                            modes.append(cabi.PROJ_RADIANCE if isinstance(p, RadiancePipeline2D) else cabi.PROJ_POWER)
+                    if len(modes) > cabi.PROJ_MAX:
+                        raise NotImplementedError("more than %d projection channels in one observe() (an RGB pipeline takes 3, a mono "
+                                                  "pipeline 1)" % cabi.PROJ_MAX)
+                    xyz = (np.concatenate(curves, axis=2), np.array([(sl.max_wavelength - sl.min_wavelength) / sl.bins for sl in all_slices]),
+                           modes)
                 xkw = dict(xyz=xyz, keep_spectral=any(p not in rgb for p in group)) if xyz is not None else {}
                 rays = accel.render_slices(cam, cfg0, spectrals, self.rng_mode, self.seed, pix, passes=self.passes, **xkw)
                 self._frames_ready_wait(ready)
                 t1 = time.perf_counter()
-                for p in sorted(group, key=lambda q: q not in rgb):       # XYZ frames first (DeviceGroup: before the rows are gathered)
+                for p in sorted(group, key=lambda q: q not in rgb):       # projected frames first (DeviceGroup: before the rows are gathered)
                     f = frame_of(p)
                     fm, fv, fs = np.asarray(f.mean), np.asarray(f.variance), np.asarray(f.samples)
                     if p in rgb:
-                        accel.update_xyz_frame(fm, fv, fs, frame_is_empty=empty[id(p)])
+                        accel.update_proj_frame(channel_of[id(p)], fm, fv, fs, frame_is_empty=empty[id(p)])
                     else:
                         accel.update_frame(fm, fv, fs, 0, frame_is_empty=empty[id(p)])
                 self.timing["render_s"] += t1 - t0

@@ -194,8 +194,8 @@ int hs_rng_uniform(uint64_t seed, int64_t n, double* out) {
 int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* config, const RsbSpectral* spectral,
               const RsbRngDesc* rngd, int64_t n_pixels, const int32_t* pixels, double* mean, double* variance,
               uint64_t* ray_count, uint64_t* counters /* optional: branches, leaves, items, prim_tests, tri_tests, paths, segments */,
-              const double* xyz_curves /* optional [bins][3] */, double xyz_delta, double* xyz_mean /* [n_pixels][3], per task */,
-              double* xyz_variance) {
+              const double* xyz_curves /* optional [bins][n_channels] */, double xyz_delta, double* xyz_mean /* [n_pixels][n_channels], per task */,
+              double* xyz_variance, int32_t n_channels, const int32_t* channel_mode /* RSB_PROJ_* per channel */) {
     HostScene* h = reinterpret_cast<HostScene*>(scene);
     int nm = (int)h->ps.mat_type.size();
     if (spectral->n_materials != nm) { g_err = "spectral tables do not match the scene's materials"; return RSB_ERR_ARG; }
@@ -294,18 +294,26 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
             *ray_count += rays;
             paths += 1;
             segments += rays;
-            double tri[3] = {0.0, 0.0, 0.0};
+            double tri[RSB_PROJ_MAX] = {0.0};
             for (int b = 0; b < bins; ++b) {
                 double x = 0.0;
                 if (res == PATH_EMITTED) x = replay_bin(log, sp, b);
                 x = x * weight;
                 if (xyz_curves)
-                    for (int ch = 0; ch < 3; ++ch) tri[ch] += xyz_delta * x * xyz_curves[3 * b + ch];
+                    for (int ch = 0; ch < n_channels; ++ch) {
+                        const double cv = xyz_curves[n_channels * b + ch];
+                        // the pixel processors' own expressions: colour.pyx:182-184, mono/power.pyx:777, mono/radiance.pyx:193
+                        if (channel_mode[ch] == RSB_PROJ_XYZ) tri[ch] += xyz_delta * x * cv;
+                        else if (channel_mode[ch] == RSB_PROJ_POWER) tri[ch] += x * cv * cam.sensitivity * xyz_delta;
+                        else tri[ch] += x * cv * xyz_delta;
+                    }
                 x = x * cam.sensitivity;
                 welford_add(x, m + b, v + b, s);
             }
             if (xyz_curves)
-                for (int ch = 0; ch < 3; ++ch) welford_add(tri[ch] * cam.sensitivity, xyz_mean + 3 * w + ch, xyz_variance + 3 * w + ch, s);
+                for (int ch = 0; ch < n_channels; ++ch)
+                    welford_add(channel_mode[ch] == RSB_PROJ_XYZ ? tri[ch] * cam.sensitivity : tri[ch], xyz_mean + n_channels * w + ch,
+                                xyz_variance + n_channels * w + ch, s);
         }
     }
     if (counters) {

@@ -45,7 +45,7 @@ def lib():
         _lib.hs_render.argtypes = [C.c_uint64, C.POINTER(cabi.RsbCamera), C.POINTER(cabi.RsbRayConfig),
                                    C.POINTER(cabi.RsbSpectral), C.POINTER(cabi.RsbRngDesc), C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_double,
-                                   C.c_void_p, C.c_void_p]
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         _lib.hs_frame_combine.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
@@ -113,14 +113,17 @@ class HostScene:
             pix = cabi.as_i32(pixels).reshape(-1, 2)
             n = pix.shape[0]
         counters = np.zeros(7, dtype=np.uint64)
-        curves = xm = xv = None
+        curves = xm = xv = modes = None
+        nch = 0
         if xyz is not None:
             curves = np.ascontiguousarray(xyz[0], dtype=np.float64)
-            assert curves.shape == (bins, 3)
-            xm, xv = np.zeros((n, 3)), np.zeros((n, 3))
+            nch = curves.shape[1]
+            assert curves.shape == (bins, nch)
+            modes = np.ascontiguousarray(xyz[2] if len(xyz) > 2 else [cabi.PROJ_XYZ] * nch, dtype=np.int32)
+            xm, xv = np.zeros((n, nch)), np.zeros((n, nch))
         rc = lib().hs_render(self.scene, C.byref(camera), C.byref(config), C.byref(spectral), C.byref(rng), n, _p(pix),
                              _p(mean), _p(variance), C.byref(rays), _p(counters), _p(curves), float(xyz[1]) if xyz is not None else 0.0,
-                             _p(xm), _p(xv))
+                             _p(xm), _p(xv), nch, _p(modes))
         self._xyz_passes = [(xm, xv)] if xyz is not None else None
         if rc:
             raise cabi.RsbError(rc, lib().hs_last_error().decode())
@@ -146,7 +149,7 @@ class HostScene:
         xyz_slices = []
         for k, sp in enumerate(spectrals):
             m, v, rays = self.render(camera, config, sp, rng_mode, seed + k * stride, pixels, passes=passes, seed_stride=n * stride,
-                                     xyz=None if xyz is None else (np.asarray(xyz[0])[k], np.asarray(xyz[1]).reshape(-1)[k]))
+                                     xyz=None if xyz is None else (np.asarray(xyz[0])[k], np.asarray(xyz[1]).reshape(-1)[k]) + tuple(xyz[2:]))
             xyz_slices.append(self._xyz_passes)
             mean[:, :, k * bins:(k + 1) * bins] = m
             variance[:, :, k * bins:(k + 1) * bins] = v
@@ -157,10 +160,17 @@ class HostScene:
         return total
 
     def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
-        """rsb_slice_update_xyz_frame restated with numpy: per pass, the slices' statistics summed in slice order, merged
+        self.update_proj_frame(0, xyz_mean, xyz_variance, xyz_samples, frame_is_empty)
+
+    def update_proj_frame(self, channel0, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
+        """rsb_slice_update_proj_frame restated with numpy: per pass, the slices' statistics summed in slice order, merged
         with combine_samples"""
         from source_b200.observer import combine_samples
         slices, pix, samples, (nx, ny) = self._xyz
+        flat2d = xyz_mean.ndim == 2
+        if flat2d:
+            xyz_mean, xyz_variance, xyz_samples = (a.reshape(nx, ny, 1) for a in (xyz_mean, xyz_variance, xyz_samples))
+        nc = xyz_mean.shape[2]
         if pix is None:
             xs, ys = (a.reshape(-1) for a in np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij"))
         else:
@@ -168,10 +178,10 @@ class HostScene:
         if frame_is_empty:
             assert not xyz_samples.any()
         for p in range(len(slices[0])):
-            wm, wv = np.zeros((len(xs), 3)), np.zeros((len(xs), 3))
+            wm, wv = np.zeros((len(xs), nc)), np.zeros((len(xs), nc))
             for parts in slices:
-                wm = wm + parts[p][0]
-                wv = wv + parts[p][1]
+                wm = wm + parts[p][0][:, channel0:channel0 + nc]
+                wv = wv + parts[p][1][:, channel0:channel0 + nc]
             mt, vt, nt = combine_samples(xyz_mean[xs, ys], xyz_variance[xs, ys], xyz_samples[xs, ys], wm, np.maximum(wv, 0.0), samples)
             xyz_mean[xs, ys] = mt
             xyz_variance[xs, ys] = vt

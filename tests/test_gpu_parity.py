@@ -291,6 +291,39 @@ def test_two_devices_in_one_process_equal_one_device(device, reference):
     second.close()
 
 
+def test_mono_pipelines_on_device_against_live_reference(device, reference):
+    """PowerPipeline2D (filtered) + RadiancePipeline2D + RGBPipeline2D + a spectral pipeline from ONE device render (5
+    projection channels) vs the reference's serial render feeding the same pipelines: 1e-6 relative, no divergent pixel."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.optical.observer import PowerPipeline2D, RadiancePipeline2D, RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
+    kw = dict(pixels=(20, 16), bins=12, spectral_rays=2)
+    filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+
+    def camera(samples, accumulate):
+        cam, pipe = scenes.cornell_camera(api, scenes.cornell_box(api), samples=samples, sensitivity=2.2, **kw)
+        extra = [PowerPipeline2D(filter=filt, display_progress=False, accumulate=accumulate),
+                 RadiancePipeline2D(display_progress=False, accumulate=accumulate), RGBPipeline2D(display_progress=False, accumulate=accumulate)]
+        cam.pipelines = [extra[0], pipe, extra[1], extra[2]]
+        return cam, pipe, extra
+    cam, pipe, extra = camera(3, True)
+    reference.oracle_render(cam, pipe, 777, passes=2)
+    cam2, pipe2, extra2 = camera(6, False)
+    cam2.frame_sampler = WholeFrameSampler2D()
+    cam2.render_engine = CudaRenderEngine(seed=777, rng="mt", device=device, passes=2)
+    cam2.observe()
+    for ref_p, our_p in zip([pipe] + extra, [pipe2] + extra2):
+        fr, fo = (getattr(q, "xyz_frame", None) or q.frame for q in (ref_p, our_p))
+        shape3 = lambda a: np.array(a).reshape(20, 16, -1)     # noqa: E731
+
+        class F:  # noqa: E701
+            mean, variance, samples = shape3(fo.mean), shape3(fo.variance), shape3(fo.samples)
+        assert shape3(fr.mean).max() > 0
+        parity.compare_frame(F, dict(mean=shape3(fr.mean), variance=shape3(fr.variance), samples=shape3(fr.samples)), exact=False,
+                             rtol=1e-6, max_divergent_fraction=0.0)
+
+
 def test_ccd_array_on_device_against_live_reference(device, reference):
     """CCDArray (a bare sensor inside the Cornell box) with its default RGB pipeline and a spectral one through
     CudaRenderEngine on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""

@@ -212,6 +212,47 @@ def test_rgb_pipeline_matches_serial_reference(api, reference, passes, spectral_
             np.testing.assert_array_equal(np.array(pipe.frame.samples), n_ref)
 
 
+@pytest.mark.parametrize("passes", [1, 2])
+def test_mono_power_and_radiance_pipelines_match_serial_reference(api, reference, passes):
+    """PowerPipeline2D (sample * filter * sensitivity * delta summed over the bins, mono/power.pyx:768-779) and
+    RadiancePipeline2D (sample * filter * delta, mono/radiance.pyx:184-195), each with its own filter, next to an RGB and a
+    spectral pipeline: ONE device render feeds all four (5 projection channels), every frame bit for bit the reference's."""
+    from raysect.optical.observer import PowerPipeline2D, RadiancePipeline2D, RGBPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=2)
+    filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+
+    def camera(samples, accumulate):
+        world = scenes.cornell_box(api)
+        cam, pipe = scenes.cornell_camera(api, world, samples=samples, sensitivity=3.0, **kw)
+        power = PowerPipeline2D(filter=filt, display_progress=False, accumulate=accumulate)
+        radiance = RadiancePipeline2D(display_progress=False, accumulate=accumulate)
+        rgb = RGBPipeline2D(display_progress=False, accumulate=accumulate)
+        cam.pipelines = [power, pipe, radiance, rgb]
+        return cam, pipe, power, radiance, rgb
+
+    def frames(pipe, power, radiance, rgb):
+        return [np.array(getattr(f, name)) for f in (pipe.frame, power.frame, radiance.frame, rgb.xyz_frame)
+                for name in ("mean", "variance", "samples")]
+    cam, pipe, power, radiance, rgb = camera(2, passes > 1)
+    reference.oracle_render(cam, pipe, 909, passes=passes)
+    ref = frames(pipe, power, radiance, rgb)
+    assert ref[3].max() > 0 and ref[6].max() > 0 and ref[5].max() == 2 * passes
+    cam2, pipe2, power2, radiance2, rgb2 = camera(2 * passes, False)
+    cam2.render_engine = CudaRenderEngine(seed=909, rng="mt", backend=hostsim_api.HostScene, passes=passes)
+    cam2.observe()
+    for ours, theirs in zip(frames(pipe2, power2, radiance2, rgb2), ref):
+        np.testing.assert_array_equal(ours, theirs)
+    # mono pipelines alone: no spectral frame is kept, the radiance pipeline rides with the power render
+    cam3, pipe3, power3, radiance3, rgb3 = camera(2 * passes, False)
+    cam3.pipelines = [radiance3, power3]
+    cam3.render_engine = CudaRenderEngine(seed=909, rng="mt", backend=hostsim_api.HostScene, passes=passes)
+    cam3.observe()
+    mono = [np.array(getattr(f, name)) for f in (power3.frame, radiance3.frame) for name in ("mean", "variance", "samples")]
+    for ours, theirs in zip(mono, ref[3:9]):
+        np.testing.assert_array_equal(ours, theirs)
+
+
 def test_rgb_pipeline_accumulates_over_observes_and_feeds_the_rgb_adaptive_sampler(api, reference):
     """An accumulating RGBPipeline2D observed twice through CudaRenderEngine == two reference passes, and the stock
     RGBAdaptiveSampler2D (sampler2d.pyx) driving the engine from that pipeline's xyz_frame picks pixel lists the engine
@@ -559,10 +600,11 @@ def test_checkerboard_emitter_matches_serial_reference(api, reference):
 
 
 def test_unsupported_objects_fail_loudly(api):
-    from raysect.optical.observer import PowerPipeline2D
+    from raysect.optical.observer import BayerPipeline2D
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
-    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[PowerPipeline2D(display_progress=False)], frame_sampler=api.FullFrameSampler2D())
+    bayer = BayerPipeline2D(api.ConstantSF(1.0), api.ConstantSF(1.0), api.ConstantSF(1.0), display_progress=False)
+    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[bayer], frame_sampler=api.FullFrameSampler2D())
     cam.quiet = True
     cam.render_engine = CudaRenderEngine(backend=hostsim_api.HostScene)
     with pytest.raises(NotImplementedError):
