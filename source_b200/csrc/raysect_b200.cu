@@ -913,7 +913,17 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
     if (a.xyz_mean) smem_tables += (size_t)(threads / 32) * a.proj_channels * a.sp.bins * sizeof(double);   // and the projection terms of one sample per warp
     if (smem_tables > 200 * 1024) return fail(RSB_ERR_UNSUPPORTED, "rsb_render: too many bins per slice for the RGB projection (shared memory)");
     if (smem_tables > 48 * 1024)
-        RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+    {
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+        RSB_CUDA(cudaFuncSetAttribute(k_wf_finalize<RNGMODE, COUNT, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tables));
+    }
+    // the accumulate kernel that holds exactly the projection code this render needs
+    int fin_kind = 0;
+    if (a.xyz_mean) {
+        fin_kind = -1;
+        if (a.proj_channels == 3 && a.proj_mode[0] == RSB_PROJ_XYZ && a.proj_mode[1] == RSB_PROJ_XYZ && a.proj_mode[2] == RSB_PROJ_XYZ) fin_kind = 3;
+    }
     a.wave = 0;
     RsbRenderStats& rs = c->render_stats;
     rs.slots = std::max<int64_t>(rs.slots, a.n_slots);
@@ -965,7 +975,9 @@ int run_wavefront(Context* c, WfArgs& a, size_t smem_scene, size_t smem_shade, s
             if (mark(b, 1)) return RSB_ERR_CUDA;
             k_wf_shade<RNGMODE, COUNT, FEAT><<<shade_grid, threads, smem_shade, s>>>(a);
             if (mark(b, 2)) return RSB_ERR_CUDA;
-            k_wf_finalize<RNGMODE, COUNT><<<fin_grid, threads, smem_tables, s>>>(a);
+            if (fin_kind == 0) k_wf_finalize<RNGMODE, COUNT, 0><<<fin_grid, threads, smem_tables, s>>>(a);
+            else if (fin_kind == 3) k_wf_finalize<RNGMODE, COUNT, 3><<<fin_grid, threads, smem_tables, s>>>(a);
+            else k_wf_finalize<RNGMODE, COUNT, -1><<<fin_grid, threads, smem_tables, s>>>(a);
             if (mark(b, 3)) return RSB_ERR_CUDA;
             k_wf_regen<RNGMODE, COUNT><<<regen_grid, threads, 0, s>>>(a);
             if (mark(b, 4)) return RSB_ERR_CUDA;

@@ -888,22 +888,32 @@ __global__ void __launch_bounds__(128, RSB_SHADE_MIN_BLOCKS) k_wf_shade(const __
 //   XYZ       delta * sample * curve                      (spectrum_to_ciexyz, colour.pyx:182-184)
 //   POWER     sample * filter * sensitivity * delta       (PowerPixelProcessor.add_sample, mono/power.pyx:776-777)
 //   RADIANCE  sample * filter * delta                     (RadiancePixelProcessor.add_sample, mono/radiance.pyx:192-193)
+template <int NCH>
 __device__ __forceinline__ void proj_terms(const WfArgs& a, int nch, double x, double delta, const double* __restrict__ curve,
                                            double* __restrict__ out) {
-    for (int ch = 0; ch < nch; ++ch) {
-        const double cv = __ldg(curve + ch);
-        const int mode = a.proj_mode[ch];
-        double t;
-        if (mode == RSB_PROJ_XYZ) t = (delta * x) * cv;
-        else if (mode == RSB_PROJ_POWER) t = ((x * cv) * a.cam.sensitivity) * delta;
-        else t = (x * cv) * delta;
-        out[ch] = t;
+    if constexpr (NCH == 3) {
+        const double dx = delta * x;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) out[ch] = dx * __ldg(curve + ch);
+    } else {
+        for (int ch = 0; ch < nch; ++ch) {
+            const double cv = __ldg(curve + ch);
+            const int mode = a.proj_mode[ch];
+            double t;
+            if (mode == RSB_PROJ_XYZ) t = (delta * x) * cv;
+            else if (mode == RSB_PROJ_POWER) t = ((x * cv) * a.cam.sensitivity) * delta;
+            else t = (x * cv) * delta;
+            out[ch] = t;
+        }
     }
 }
 
 // 1 warp = 1 ended path: the reference's unwind (per-bin multiplies), projection weight, sensitivity and
 // PixelProcessor.add_sample (Welford) for bins lane, lane+32, ...
-template <int RNGMODE, bool COUNT>
+// NCH: projection channels compiled in -- 0: none (the spectral pipelines' kernel, nothing of the projection code in it: the
+// generic form cost it 14 registers and 5 % of its time), 3: the three CIE XYZ channels of an RGB pipeline alone (unrolled),
+// -1: a.proj_channels channels of any mode.
+template <int RNGMODE, bool COUNT, int NCH>
 __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     Spectral sp = a.sp;
@@ -920,9 +930,9 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
     LogEntry* wlog = reinterpret_cast<LogEntry*>(smem + tab_bytes) + (threadIdx.x >> 5) * 32;
     // projections (RGB / mono pipelines): the sample's per-bin terms of every channel, one row of channels * bins doubles
     // per warp, behind the log windows
-    const int nch = a.proj_channels;
+    const int nch = NCH >= 0 ? NCH : a.proj_channels;
     double* wspec = reinterpret_cast<double*>(smem + tab_bytes + (blockDim.x >> 5) * 32 * sizeof(LogEntry)) + (size_t)(threadIdx.x >> 5) * nch * sp.bins;
-    const bool keep_bins = a.mean != nullptr, keep_xyz = a.xyz_mean != nullptr;
+    const bool keep_bins = a.mean != nullptr, keep_xyz = NCH != 0;
     const int par = a.wave & 1;
     const int lane = threadIdx.x & 31;
     const unsigned int n = a.st.n_ended[par];
@@ -983,7 +993,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
                 double x = xa * w;              // spectrum.mul_scalar(projection_weight), observer.pyx:408
                 // the terms of the pixel processors' sums, formed by the bin's own lane; only the additions below are a
                 // serial chain
-                if (keep_xyz) proj_terms(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * ba, wspec + (size_t)nch * ba);
+                if (keep_xyz) proj_terms<NCH>(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * ba, wspec + (size_t)nch * ba);
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;      // add_sample(spectrum, sensitivity), power.pyx:478-481
                     welford_add_r(x, ma, va, s, r_nn, r_nn1, m + ba, v + ba);
@@ -991,7 +1001,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
             }
             if (hb) {
                 double x = xb * w;
-                if (keep_xyz) proj_terms(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * bb, wspec + (size_t)nch * bb);
+                if (keep_xyz) proj_terms<NCH>(a, nch, x, xyz_delta, xyz_curve + (size_t)nch * bb, wspec + (size_t)nch * bb);
                 if (keep_bins) {
                     x = x * a.cam.sensitivity;
                     welford_add_r(x, mb, vb, s, r_nn, r_nn1, m + bb, v + bb);
@@ -1013,7 +1023,7 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
                 if (s > 0) { pm = a.xyz_mean[item]; pv = a.xyz_variance[item]; }
                 // (XYZ: the tristimulus value times the sensitivity, rgb.pyx:556-558; the mono processors fold the
                 // sensitivity into their terms or ignore it)
-                const double value = a.proj_mode[lane] == RSB_PROJ_XYZ ? acc * a.cam.sensitivity : acc;
+                const double value = (NCH == 3 || a.proj_mode[lane] == RSB_PROJ_XYZ) ? acc * a.cam.sensitivity : acc;
                 welford_add_r(value, pm, pv, s, r_nn, r_nn1, a.xyz_mean + item, a.xyz_variance + item);
             }
             __syncwarp();
