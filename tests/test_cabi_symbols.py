@@ -49,6 +49,32 @@ def test_device_entry_points_fail_loudly_without_gpu(lib):
         Device(0)
 
 
+def test_round2_entry_points_reject_bad_arguments_without_touching_a_device(lib):
+    """the argument checks of the entry points added in round 2 run before any CUDA call: null handles, empty
+    communicators and channel counts out of range come back as RSB_ERR_ARG with a message, on a machine without a GPU"""
+    z = np.zeros(4)
+    zi = np.zeros(4, dtype=np.int32)
+    pd, pi = cabi.ptr(z, C.c_double), cabi.ptr(zi, C.c_int32)
+    comm = C.c_uint64()
+    calls = [
+        lambda: lib.rsb_set_query_reorder(0, 1),
+        lambda: lib.rsb_comm_create(0, None, C.byref(comm)),
+        lambda: lib.rsb_comm_create(1, (C.c_uint64 * 1)(0), C.byref(comm)),
+        lambda: lib.rsb_comm_gather_slices(0, 0),
+        lambda: lib.rsb_slice_update_frame(0, 4, 0, 1, pd, pd, pi),
+        lambda: lib.rsb_slice_update_xyz_frame(0, 1, pd, pd, pi),
+        lambda: lib.rsb_slice_update_proj_frame(0, 0, 1, 1, pd, pd, pi),
+        lambda: lib.rsb_slice_read(0, pd, pd),
+        lambda: lib.rsb_host_pin(0, None, 16),
+        lambda: lib.rsb_render_slices_xyz(0, 0, None, None, None, None, 1, 1, 0, 0, None, None, None, 1, None),
+        lambda: lib.rsb_render_slices_proj(0, 0, None, None, None, None, 1, 1, 0, 0, None, 9, pi, pd, pd, 1, None),
+    ]
+    for k, call in enumerate(calls):
+        assert call() == cabi.ERR_ARG, k
+        assert lib.rsb_last_error()
+    assert lib.rsb_comm_destroy(0) == 0
+
+
 def test_kdtree_builder_stream_roundtrip_and_errors(lib):
     from source_b200.flatten import kdtree_build
     rng = np.random.default_rng(0)
