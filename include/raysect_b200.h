@@ -245,7 +245,7 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
  * 20-bit coherence key first -- origin cell and octahedral direction cell, normalised to the extent the batch covers,
  * Morton-interleaved; one counting sort on the device -- traverse the permuted copy and write every answer back at the
  * caller's index.  The answers are the same (queries are independent; the reference's World.hit has no notion of order).
- * On by default (measured on a B200: 10,000 spheres 943 -> 1,657 Mrays/s, 1.3 M triangles 631 -> 771 on independent random
+ * On by default (measured on a B200: 10,000 spheres 943 -> 1,732 Mrays/s, 1.3 M triangles 631 -> 862 on independent random
  * rays; an already coherent batch pays the key + scatter passes for nothing, about 8 %: turn it off for those);
  * RSB_RQ_REORDER=0 turns it off at context creation.  A sweep generated along the Morton curve (order_log2 > 0) is never
  * sorted.

@@ -32,7 +32,11 @@ namespace rsb {
 #define RQ_VISITS 6          // node visits per lane per trip
 #endif
 #ifndef RQ_LEAF_MIN
-#define RQ_LEAF_MIN 8        // lanes standing at a leaf that trigger the leaf phase while other lanes still descend
+#define RQ_LEAF_MIN 8        // lanes standing at a leaf that trigger the leaf phase while other lanes still descend (k_rq_world)
+#endif
+#ifndef RQ_MESH_LEAF_MIN
+#define RQ_MESH_LEAF_MIN 4   // the same for k_rq_mesh, whose pooled leaf phase is cheap to enter: 4 against 8 measured +3 % on the
+                             // 1.3 M-triangle sweep (sorted 862 -> 890, morton 904 -> 923 Mrays/s) and -1.5 % in k_rq_world
 #endif
 #ifndef RQ_REFILL
 #define RQ_REFILL 8          // idle lanes that trigger a refill from the queue
@@ -511,7 +515,7 @@ k_rq_mesh(Scene sc, RqBuf b, int round, DevCounters* counters) {
         // ---- leaf phase: pooled triangle tests once enough lanes hold a leaf (or nobody can move)
         const unsigned holding = __ballot_sync(RSB_FULL_MASK, parked);
         const unsigned moving = __ballot_sync(RSB_FULL_MASK, st == DESCEND);
-        if (holding != 0 && (__popc(holding) >= RQ_LEAF_MIN || moving == 0)) {
+        if (holding != 0 && (__popc(holding) >= RQ_MESH_LEAF_MIN || moving == 0)) {
             MeshHit mh;
             const bool leaf_hit = mesh_leaf_pool(sc, cs, parked, p_off, p_cnt, p_d0, &mh, stats);
             if (parked) {

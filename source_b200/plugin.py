@@ -201,7 +201,7 @@ class CudaRenderEngine(RenderEngine):
         pinned = getattr(self, "_pinned", {})
         live = {a.ctypes.data for a, _ in arrays}
         for ptr in [k for k in pinned if k not in live]:       # frames that are gone: release their locks
-            pinned.pop(ptr)()
+            pinned.pop(ptr)[0]()
         self._pinned = pinned
         threads = []
         for a, is_empty in arrays:
@@ -210,7 +210,7 @@ class CudaRenderEngine(RenderEngine):
             elif hasattr(accel, "pin") and a.ctypes.data not in pinned:
                 def lock(a=a):
                     try:
-                        pinned[a.ctypes.data] = accel.pin(a)
+                        pinned[a.ctypes.data] = (accel.pin(a), a)      # (the array stays alive while it is page-locked)
                     except Exception:        # an optimisation only: pageable copies still work
                         pass
                 th = threading.Thread(target=lock)

@@ -60,7 +60,7 @@ def main():
                                                  C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()), count))
         for n in ns:
             n = int(n)
-            run(min(n, 10**6), 0)           # warm-up
+            run(min(n, 10**7), 0)           # warm-up (at size: the chunk buffers are allocated on first use)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 3 if n <= 10**8 else 1
