@@ -374,6 +374,11 @@ int rsb_render_slices_proj(uint64_t ctx, uint64_t scene, const RsbCamera* camera
                            int32_t keep_spectral, uint64_t* ray_count);
 int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channels, int32_t frame_is_empty,
                                 double* frame_mean, double* frame_variance, int32_t* frame_samples);
+/* BayerPipeline2D (raysect/optical/observer/pipeline/bayer.pyx:307-387): channels channel0 .. channel0 + 2 are its red, green
+ * and blue filters (RSB_PROJ_POWER); pixel (x, y) of the (nx, ny) frame takes the channel its mosaic position selects,
+ * (0, 1, 1, 2)[(x % 2) + 2 (y % 2)] (bayer.pyx:109, 345-347). */
+int rsb_slice_update_bayer_frame(uint64_t ctx, int32_t channel0, int32_t frame_is_empty, double* frame_mean,
+                                 double* frame_variance, int32_t* frame_samples);
 /*
  * Several GPUs driven from ONE process (the reference's user runs one Python interpreter; its MulticoreEngine forks
  * workers and pickles per-pixel results back, raysect/core/workflow.py:123-327).  A communicator joins contexts on

@@ -191,6 +191,7 @@ SIGNATURES = {
                                          C.POINTER(RsbRngDesc), C.c_int32, C.c_int32, _U64, C.c_int64, c_int32_p, C.c_int32, c_int32_p,
                                          c_double_p, c_double_p, C.c_int32, c_uint64_p]),
     "rsb_slice_update_proj_frame": (C.c_int, [_U64, C.c_int32, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
+    "rsb_slice_update_bayer_frame": (C.c_int, [_U64, C.c_int32, C.c_int32, c_double_p, c_double_p, c_int32_p]),
     "rsb_comm_create": (C.c_int, [C.c_int32, c_uint64_p, c_uint64_p]),
     "rsb_comm_destroy": (C.c_int, [_U64]),
     "rsb_comm_gather_slices": (C.c_int, [_U64, C.c_int32]),

@@ -1445,8 +1445,21 @@ int rsb_render_slices_xyz(uint64_t ctx, uint64_t scene, const RsbCamera* camera,
                                   resampled_xyz, delta_wavelength, keep_spectral, ray_count);
 }
 
+static int slice_update_proj(uint64_t ctx, int32_t channel0, int32_t n_channels, bool bayer, int32_t frame_is_empty, double* frame_mean,
+                             double* frame_variance, int32_t* frame_samples);
+
 int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channels, int32_t frame_is_empty, double* frame_mean,
                                 double* frame_variance, int32_t* frame_samples) {
+    return slice_update_proj(ctx, channel0, n_channels, false, frame_is_empty, frame_mean, frame_variance, frame_samples);
+}
+
+int rsb_slice_update_bayer_frame(uint64_t ctx, int32_t channel0, int32_t frame_is_empty, double* frame_mean, double* frame_variance,
+                                 int32_t* frame_samples) {
+    return slice_update_proj(ctx, channel0, 3, true, frame_is_empty, frame_mean, frame_variance, frame_samples);
+}
+
+static int slice_update_proj(uint64_t ctx, int32_t channel0, int32_t n_channels, bool bayer, int32_t frame_is_empty, double* frame_mean,
+                             double* frame_variance, int32_t* frame_samples) {
     Context* c = as_ctx(ctx);
     if (!c || !frame_mean || !frame_variance || !frame_samples) return fail(RSB_ERR_ARG, "rsb_slice_update_proj_frame: null argument");
     if (!c->slice.valid || !c->slice.has_xyz)
@@ -1456,7 +1469,8 @@ int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channe
     if (c->slice.n_pixels == 0) return RSB_OK;
     RSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    const size_t elems = (size_t)c->slice.nx * c->slice.ny * n_channels;
+    const int frame_channels = bayer ? 1 : n_channels;       // values per pixel of the host frame
+    const size_t elems = (size_t)c->slice.nx * c->slice.ny * frame_channels;
     if (c->xyz_frame_cap < elems) {
         cudaFree(c->d_xyz_frame); cudaFree(c->d_xyz_samples);
         c->d_xyz_frame = nullptr; c->d_xyz_samples = nullptr; c->xyz_frame_cap = 0;
@@ -1479,9 +1493,9 @@ int rsb_slice_update_proj_frame(uint64_t ctx, int32_t channel0, int32_t n_channe
     const size_t n_work = (size_t)c->slice.n_pixels * c->slice.n_passes * c->slice.n_slices;
     const double* wm = c->d_xyz + n_tab + c->slice.n_slices;
     const double* wv = wm + (size_t)nch * n_work;
-    k_xyz_combine<<<grid_for(c, (long long)c->slice.n_pixels * n_channels, 256, 4), 256, 0, st>>>(
+    k_xyz_combine<<<grid_for(c, (long long)c->slice.n_pixels * frame_channels, 256, 4), 256, 0, st>>>(
         c->slice.n_pixels, c->slice.listed ? c->d_slice_pix : nullptr, c->slice.ny, c->slice.n_passes, c->slice.n_slices, c->slice.pass_samples,
-        nch, channel0, n_channels, wm, wv, d_fm, d_fv, c->d_xyz_samples);
+        nch, channel0, frame_channels, bayer ? 1 : 0, wm, wv, d_fm, d_fv, c->d_xyz_samples);
     RSB_CUDA(cudaGetLastError());
     RSB_CUDA(cudaMemcpyAsync(frame_mean, d_fm, elems * 8, cudaMemcpyDeviceToHost, st));
     RSB_CUDA(cudaMemcpyAsync(frame_variance, d_fv, elems * 8, cudaMemcpyDeviceToHost, st));

@@ -1036,8 +1036,10 @@ __global__ void __launch_bounds__(128) k_wf_finalize(const __grid_constant__ WfA
 // values, which are merged into the frame with combine_samples; the passes of a pixel are merged in order by the same
 // thread, one thread per (pixel, channel).  The frame holds `nc` channels per pixel, channels [c0, c0 + nc) of the `nch`
 // projection channels of the render.
+// `bayer`: BayerPipeline2D (pipeline/bayer.pyx:339-349): ONE value per pixel, taken from channel c0 + mosaic[(x % 2) + 2 (y % 2)]
+// of the three filter channels, mosaic = (0, 1, 1, 2) = red, green / green, blue (bayer.pyx:109).
 __global__ void k_xyz_combine(long long n_pixels, const int32_t* __restrict__ pixels, int ny, int n_passes, int n_slices, int samples,
-                              int nch, int c0, int nc, const double* __restrict__ xyz_mean, const double* __restrict__ xyz_variance,
+                              int nch, int c0, int nc, int bayer, const double* __restrict__ xyz_mean, const double* __restrict__ xyz_variance,
                               double* __restrict__ fmean, double* __restrict__ fvar, int32_t* __restrict__ fsamples) {
     long long total = n_pixels * nc;
     long long stride = (long long)gridDim.x * blockDim.x;
@@ -1046,6 +1048,11 @@ __global__ void k_xyz_combine(long long n_pixels, const int32_t* __restrict__ pi
         int ch = (int)(i % nc);
         long long row = pixels ? ((long long)pixels[2 * p] * ny + pixels[2 * p + 1]) : p;
         long long dst = row * nc + ch;
+        if (bayer) {
+            const int x = (int)(row / ny), y = (int)(row % ny);
+            const int index = (x % 2) + 2 * (y % 2);
+            ch = index == 0 ? 0 : (index == 3 ? 2 : 1);
+        }
         double fm = fmean[dst], fv = fvar[dst];
         int fn = fsamples[dst];
         for (int pass = 0; pass < n_passes; ++pass) {

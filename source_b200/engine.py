@@ -275,6 +275,17 @@ class Accelerator:
                                                         cabi.ptr(frame_mean, C.c_double), cabi.ptr(frame_variance, C.c_double),
                                                         cabi.ptr(frame_samples, C.c_int32)))
 
+    def update_bayer_frame(self, channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=False):
+        """BayerPipeline2D: the (nx, ny) frame takes, per pixel, the one of the three filter channels ``channel0 ..
+        channel0 + 2`` its mosaic position selects (rsb_slice_update_bayer_frame)."""
+        nx, ny = self._slice_shape[:2]
+        for a, dt in ((frame_mean, np.float64), (frame_variance, np.float64), (frame_samples, np.int32)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable and a.shape == (nx, ny)):
+                raise TypeError("frame arrays must be writable C-contiguous (nx, ny) float64 / int32 numpy arrays")
+        cabi.check(self.lib.rsb_slice_update_bayer_frame(self.device.ctx, int(channel0), int(bool(frame_is_empty)),
+                                                         cabi.ptr(frame_mean, C.c_double), cabi.ptr(frame_variance, C.c_double),
+                                                         cabi.ptr(frame_samples, C.c_int32)))
+
     def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
         """RGBPipeline2D.update + finalise for every listed pixel of the render done last with ``xyz=``: merges its XYZ
         statistics into the HOST ``xyz_frame`` arrays ((nx, ny, 3) StatsArray3D buffers, modified in place) on the device
@@ -393,6 +404,12 @@ class DeviceGroup:
             raise RuntimeError("update_proj_frame must precede update_frame after a multi-device render")
         for k, m in enumerate(self.members):
             m.update_proj_frame(channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=frame_is_empty and k == 0)
+
+    def update_bayer_frame(self, channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=False):
+        if self._rows_gathered:
+            raise RuntimeError("update_bayer_frame must precede update_frame after a multi-device render")
+        for k, m in enumerate(self.members):
+            m.update_bayer_frame(channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=frame_is_empty and k == 0)
 
     def update_frame(self, frame_mean, frame_variance, frame_samples, slice_offset, frame_is_empty=False):
         if not self._rows_gathered:

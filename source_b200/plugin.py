@@ -267,19 +267,20 @@ class CudaRenderEngine(RenderEngine):
         return mean, variance, rays
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
-        from raysect.optical.observer import (CCDArray, OrthographicCamera, PinholeCamera, PowerPipeline2D, RadiancePipeline2D,
-                                              RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D)
+        from raysect.optical.observer import (BayerPipeline2D, CCDArray, OrthographicCamera, PinholeCamera, PowerPipeline2D,
+                                              RadiancePipeline2D, RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D)
         observer = getattr(render, "__self__", None)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray)):
             raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera and CCDArray observers; got %r "
                                       "(no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
-            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D)):
-                raise NotImplementedError("CudaRenderEngine feeds SpectralPowerPipeline2D / SpectralRadiancePipeline2D / RGBPipeline2D / "
-                                          "PowerPipeline2D / RadiancePipeline2D pipelines; got %r (no CPU fallback)" % type(p).__name__)
-        # pipelines whose pixel processors PROJECT every sample's spectrum on curves (CIE XYZ; a filter): done on the device
-        rgb = [p for p in pipelines if isinstance(p, (RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D))]
+            if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D,
+                                  BayerPipeline2D)):
+                raise NotImplementedError("CudaRenderEngine feeds the 2D pipelines of raysect.optical.observer (SpectralPower, "
+                                          "SpectralRadiance, RGB, Power, Radiance, Bayer); got %r (no CPU fallback)" % type(p).__name__)
+        # pipelines whose pixel processors PROJECT every sample's spectrum on curves (CIE XYZ; filters): done on the device
+        rgb = [p for p in pipelines if isinstance(p, (RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D, BayerPipeline2D))]
 
         def frame_of(p):
             return p.xyz_frame if isinstance(p, RGBPipeline2D) else p.frame
@@ -381,6 +382,12 @@ class CudaRenderEngine(RenderEngine):
                         if isinstance(p, RGBPipeline2D):
                             curves.append(np.stack([np.asarray(resample_ciexyz(sl.min_wavelength, sl.max_wavelength, sl.bins)) for sl in all_slices]))
                             modes += [cabi.PROJ_XYZ] * 3
+                        elif isinstance(p, BayerPipeline2D):
+                            # one PowerPixelProcessor per filter (bayer.pyx:322-330); the mosaic picks per pixel at update time
+                            curves.append(np.stack([np.stack([np.asarray(f.sample(sl.min_wavelength, sl.max_wavelength, sl.bins))
+                                                              for f in (p.red_filter, p.green_filter, p.blue_filter)], axis=1)
+                                                    for sl in all_slices]))
+                            modes += [cabi.PROJ_POWER] * 3
                         else:
                             curves.append(np.stack([np.asarray(p.filter.sample(sl.min_wavelength, sl.max_wavelength, sl.bins))[:, None]
                                                     for sl in all_slices]))
@@ -398,7 +405,9 @@ class CudaRenderEngine(RenderEngine):
                 for p in sorted(group, key=lambda q: q not in rgb):       # projected frames first (DeviceGroup: before the rows are gathered)
                     f = frame_of(p)
                     fm, fv, fs = np.asarray(f.mean), np.asarray(f.variance), np.asarray(f.samples)
-                    if p in rgb:
+                    if isinstance(p, BayerPipeline2D):
+                        accel.update_bayer_frame(channel_of[id(p)], fm, fv, fs, frame_is_empty=empty[id(p)])
+                    elif p in rgb:
                         accel.update_proj_frame(channel_of[id(p)], fm, fv, fs, frame_is_empty=empty[id(p)])
                     else:
                         accel.update_frame(fm, fv, fs, 0, frame_is_empty=empty[id(p)])

@@ -162,6 +162,17 @@ class HostScene:
     def update_xyz_frame(self, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
         self.update_proj_frame(0, xyz_mean, xyz_variance, xyz_samples, frame_is_empty)
 
+    def update_bayer_frame(self, channel0, frame_mean, frame_variance, frame_samples, frame_is_empty=False):
+        """rsb_slice_update_bayer_frame restated: the three filter channels merged into a scratch (nx, ny, 3) copy of the
+        frame, then every pixel keeps the channel its mosaic position selects"""
+        nx, ny = frame_mean.shape
+        m3, v3, s3 = (np.repeat(a[:, :, None], 3, axis=2).copy() for a in (frame_mean, frame_variance, frame_samples))
+        self.update_proj_frame(channel0, m3, v3, s3, frame_is_empty)
+        xs, ys = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        sel = np.array([0, 1, 1, 2])[(xs % 2) + 2 * (ys % 2)]
+        for dst, src in ((frame_mean, m3), (frame_variance, v3), (frame_samples, s3)):
+            dst[:, :] = np.take_along_axis(src, sel[:, :, None], axis=2)[:, :, 0]
+
     def update_proj_frame(self, channel0, xyz_mean, xyz_variance, xyz_samples, frame_is_empty=False):
         """rsb_slice_update_proj_frame restated with numpy: per pass, the slices' statistics summed in slice order, merged
         with combine_samples"""

@@ -292,20 +292,23 @@ def test_two_devices_in_one_process_equal_one_device(device, reference):
 
 
 def test_mono_pipelines_on_device_against_live_reference(device, reference):
-    """PowerPipeline2D (filtered) + RadiancePipeline2D + RGBPipeline2D + a spectral pipeline from ONE device render (5
-    projection channels) vs the reference's serial render feeding the same pipelines: 1e-6 relative, no divergent pixel."""
+    """PowerPipeline2D (filtered) + RadiancePipeline2D + RGBPipeline2D + BayerPipeline2D + a spectral pipeline from ONE device
+    render (8 projection channels) vs the reference's serial render feeding the same pipelines: 1e-6 relative, no divergent
+    pixel."""
     import scenes
     api = reference.ref_api()
-    from raysect.optical.observer import PowerPipeline2D, RadiancePipeline2D, RGBPipeline2D
+    from raysect.optical.observer import BayerPipeline2D, PowerPipeline2D, RadiancePipeline2D, RGBPipeline2D
     from source_b200.plugin import CudaRenderEngine, WholeFrameSampler2D
     kw = dict(pixels=(20, 16), bins=12, spectral_rays=2)
     filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+    rgb_filters = [api.InterpolatedSF([300, 550, 800], v) for v in ([0.0, 0.2, 1.0], [0.1, 1.0, 0.1], [1.0, 0.3, 0.0])]
 
     def camera(samples, accumulate):
         cam, pipe = scenes.cornell_camera(api, scenes.cornell_box(api), samples=samples, sensitivity=2.2, **kw)
         extra = [PowerPipeline2D(filter=filt, display_progress=False, accumulate=accumulate),
-                 RadiancePipeline2D(display_progress=False, accumulate=accumulate), RGBPipeline2D(display_progress=False, accumulate=accumulate)]
-        cam.pipelines = [extra[0], pipe, extra[1], extra[2]]
+                 RadiancePipeline2D(display_progress=False, accumulate=accumulate), RGBPipeline2D(display_progress=False, accumulate=accumulate),
+                 BayerPipeline2D(*rgb_filters, display_progress=False, accumulate=accumulate)]
+        cam.pipelines = [extra[0], pipe, extra[1], extra[2], extra[3]]
         return cam, pipe, extra
     cam, pipe, extra = camera(3, True)
     reference.oracle_render(cam, pipe, 777, passes=2)

@@ -253,6 +253,36 @@ def test_mono_power_and_radiance_pipelines_match_serial_reference(api, reference
         np.testing.assert_array_equal(ours, theirs)
 
 
+@pytest.mark.parametrize("passes", [1, 2])
+def test_bayer_pipeline_matches_serial_reference(api, reference, passes):
+    """BayerPipeline2D (pipeline/bayer.pyx): three filters, the mosaic (red, green / green, blue) picks one per pixel.  The
+    device keeps all three filtered totals per work item and the update takes each pixel's own: the reference's frame, bit
+    for bit, next to a spectral pipeline and with a task mask."""
+    from raysect.optical.observer import BayerPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=2)
+    filters = [api.InterpolatedSF([300, 550, 800], v) for v in ([0.0, 0.2, 1.0], [0.1, 1.0, 0.1], [1.0, 0.3, 0.0])]
+    mask = np.ones((9, 7), dtype=bool)
+    mask[3:5, 2:6] = False
+
+    def camera(samples, accumulate):
+        cam, pipe = scenes.cornell_camera(api, scenes.cornell_box(api), samples=samples, sensitivity=1.9, **kw)
+        bayer = BayerPipeline2D(*filters, display_progress=False, accumulate=accumulate)
+        cam.pipelines = [bayer, pipe]
+        cam.frame_sampler = api.FullFrameSampler2D(mask)
+        return cam, pipe, bayer
+    cam, pipe, bayer = camera(2, passes > 1)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 2001, passes=passes)
+    cam2, pipe2, bayer2 = camera(2 * passes, False)
+    cam2.render_engine = CudaRenderEngine(seed=2001, rng="mt", backend=hostsim_api.HostScene, passes=passes)
+    cam2.observe()
+    for name in ("mean", "variance", "samples"):
+        np.testing.assert_array_equal(np.array(getattr(bayer2.frame, name)), np.array(getattr(bayer.frame, name)))
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    bm = np.array(bayer.frame.mean)
+    assert bm[mask].max() > 0 and not bm[~mask].any() and np.array(bayer.frame.samples)[mask].min() == 2 * passes
+
+
 def test_rgb_pipeline_accumulates_over_observes_and_feeds_the_rgb_adaptive_sampler(api, reference):
     """An accumulating RGBPipeline2D observed twice through CudaRenderEngine == two reference passes, and the stock
     RGBAdaptiveSampler2D (sampler2d.pyx) driving the engine from that pipeline's xyz_frame picks pixel lists the engine
@@ -600,11 +630,13 @@ def test_checkerboard_emitter_matches_serial_reference(api, reference):
 
 
 def test_unsupported_objects_fail_loudly(api):
-    from raysect.optical.observer import BayerPipeline2D
+    from raysect.optical.observer import Pipeline2D
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
-    bayer = BayerPipeline2D(api.ConstantSF(1.0), api.ConstantSF(1.0), api.ConstantSF(1.0), display_progress=False)
-    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[bayer], frame_sampler=api.FullFrameSampler2D())
+
+    class HomeMadePipeline(Pipeline2D):
+        pass
+    cam = api.PinholeCamera((4, 4), parent=world, pipelines=[HomeMadePipeline()], frame_sampler=api.FullFrameSampler2D())
     cam.quiet = True
     cam.render_engine = CudaRenderEngine(backend=hostsim_api.HostScene)
     with pytest.raises(NotImplementedError):
