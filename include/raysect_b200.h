@@ -241,7 +241,7 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
 
 /*
  * Incoherent query batches (rays after a diffuse bounce, a user's unordered batch) put 32 unrelated kd walks into every
- * warp.  With reordering on, rsb_hit_batch(_dev) and rsb_hit_sweep_dev sort each pipeline pass (<= 4 Mi queries) on a
+ * warp.  With reordering on, rsb_hit_batch(_dev) and rsb_hit_sweep_dev sort each pipeline pass (up to 64 Mi queries) on a
  * 20-bit coherence key first -- origin cell and octahedral direction cell, normalised to the extent the batch covers,
  * Morton-interleaved; one counting sort on the device -- traverse the permuted copy and write every answer back at the
  * caller's index.  The answers are the same (queries are independent; the reference's World.hit has no notion of order).

@@ -79,7 +79,7 @@ struct Context {
     size_t xyz_frame_cap = 0;           // elements
     unsigned char* d_rq = nullptr;      // query pipeline arrays (rsb_trav.cuh: RqBuf)
     size_t rq_bytes = 0;
-    long long rq_chunk = 4LL << 20;     // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep
+    long long rq_chunk = 0;             // RSB_RQ_CHUNK: queries per pipeline pass of rsb_hit_batch / rsb_hit_sweep; 0 = rq_pass_size()
     bool query_reorder = true;          // rsb_set_query_reorder / RSB_RQ_REORDER=0: sort every batch on its coherence key first
     double* d_pass = nullptr;           // frames of passes 1.. of a multi-pass render: [2][n_passes - 1][frame]
     size_t pass_bytes = 0;
@@ -551,6 +551,23 @@ int rq_reserve(Context* c, long long cap, bool park, RqHost* out, bool reorder =
     return RSB_OK;
 }
 
+// Queries per pipeline pass.  A pass is sorted as a whole (rq_reorder), so the larger it is the smaller the part of the scene
+// a stretch of consecutive warps works in: 1e8 independent random rays over 10,000 spheres run at 1,800 / 1,987 / 2,193 Mrays/s
+// with passes of 4 Mi / 16 Mi / 64 Mi queries (47 / 52 / 57 % of the HBM roofline).  Mesh-free scenes: 64 Mi (108 B of pipeline
+// state per query); scenes with meshes park a walk per query (~800 B): 16 Mi (1.3 M triangles: 922 / 990 / 1,000 Mrays/s).  Never
+// more than half of the device memory that is free right now, or what the buffers already hold.
+long long rq_pass_size(Context* c, DeviceScene* ds, long long n) {
+    if (c->rq_chunk > 0) return std::min<long long>(n, c->rq_chunk);
+    long long pass = std::min<long long>(n, ds->has_mesh ? (16LL << 20) : (64LL << 20));
+    RqHost probe;
+    const size_t per_query = rq_carve(nullptr, (size_t)1 << 20, ds->has_mesh, &probe, c->query_reorder) >> 20;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return std::min<long long>(pass, 4LL << 20); }
+    const size_t budget = std::max(c->rq_bytes, free_b / 2);
+    const long long fit = (long long)(budget / std::max<size_t>(per_query, 1));
+    return std::max<long long>(std::min(pass, fit), std::min<long long>(n, 1LL << 16));
+}
+
 // Slot order of the m queries of `src` (the caller's arrays, or the sweep's generator) by coherence key (rsb_trav.cuh):
 // rq.perm[slot] = query.  The input stage fills the pipeline in that order; the output stage writes answers back through it.
 template <class Source>
@@ -643,7 +660,7 @@ int rsb_hit_batch_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-    const long long chunk = std::min<long long>(n, c->rq_chunk);
+    const long long chunk = rq_pass_size(c, ds, n);
     RqHost rq;
     int rc = rq_reserve(c, chunk, ds->has_mesh, &rq, c->query_reorder);
     if (rc) return rc;
@@ -744,7 +761,7 @@ int rsb_hit_sweep_dev(uint64_t ctx, uint64_t scene, void* cuda_stream, int64_t n
     cudaStream_t st = (cudaStream_t)cuda_stream;
     RSB_CUDA(cudaSetDevice(c->device));
     if (count) RSB_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), st));
-    const long long chunk = std::min<long long>(n, c->rq_chunk);
+    const long long chunk = rq_pass_size(c, ds, n);
     RqHost rq;
     int rc = rq_reserve(c, chunk, ds->has_mesh, &rq, c->query_reorder);
     if (rc) return rc;
