@@ -27,6 +27,7 @@ reference's ray counter (primary rays + daughters spawned, raysect/optical/ray.p
 same workloads and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import gc
 import json
 import math
 import os
@@ -470,7 +471,11 @@ def run_c5(cx, args):
         cabi.check(dev.lib.rsb_hit_sweep_dev(dev.ctx, acc.scene, C.c_void_p(st), int(n), int(first), C5["seed"], o3, t3, scenes.SWEEP_HALF,
                                              int(order), C.c_void_p(hits.data_ptr()), C.c_void_p(sum_t.data_ptr()), C.c_void_p(xr.data_ptr()),
                                              count))
-    sweep(0, 7 * 10**7, 0)                                      # warm-up at size: a full 64 Mi-query pass allocates the pipeline buffers
+    # warm-up: a full 64 Mi-query pass allocates the pipeline buffers; three of them (~0.3 s of device work) also bring the
+    # clocks back up after the host-side scene build, during which the device sat idle
+    for _ in range(3):
+        sweep(0, 2 * 10**8, 0)
+    torch.cuda.synchronize()
     out = {"workload": C5["name"], "n_gpus": cx.world_size, "scaling": "strong",
            "partition": "contiguous ray ranges per rank, no data-path collective" if cx.world_size > 1 else "single GPU", "sweeps": []}
     # random: every ray independent (incoherent), the library as shipped: each 4 Mi-ray pass is sorted on a coherence key
@@ -484,21 +489,27 @@ def run_c5(cx, args):
             lo = n * cx.rank // cx.world_size
             hi = n * (cx.rank + 1) // cx.world_size
             sweep(lo, min(hi - lo, 10**7), order)               # untimed: the first pass in a new mode pays one-off set-up
-            hits.zero_()
-            cx.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sweep(lo, hi - lo, order)
-            e1.record()
-            cx.barrier()
-            ms = cx.reduce(e0.elapsed_time(e1), "max")
+            # a 1e7-ray sweep is 5 ms of device time inside a call that also talks to the driver (memory query, launches): it
+            # is timed three times and the MEDIAN reported (a stray 15 ms host stall showed up in one of them after the 1 M-
+            # triangle workload had run in the same process); the 1e9-ray sweep once
+            times = []
+            for _ in range(3 if n <= 10**8 else 1):
+                hits.zero_()
+                cx.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sweep(lo, hi - lo, order)
+                e1.record()
+                cx.barrier()
+                times.append(cx.reduce(e0.elapsed_time(e1), "max"))
+            ms = statistics.median(times)
             h = cx.reduce(int(hits.item()), "sum", torch.int64)
             sweep(lo, min(hi - lo, 10**7), order, 1)            # counting pass on (a prefix of) this rank's rays
             torch.cuda.synchronize()
             c = dev.counters()
             per_ray = trace_algorithmic_bytes(c) / c["rays"]
             achieved = per_ray * (hi - lo) / (ms * 1e-3) / 1e9   # this rank's rays against the slowest rank's time: per-GPU figure
-            out["sweeps"].append({"order": order_name, "rays": n, "ms": ms, "Mrays_per_s": n / ms / 1e3, "hit_fraction": h / n,
+            out["sweeps"].append({"order": order_name, "rays": n, "ms": ms, "ms_all": times, "Mrays_per_s": n / ms / 1e3, "hit_fraction": h / n,
                                   "roofline": {"bound": "hbm", "kernel": "k_rq_world", "achieved": achieved, "peak": cx.peak, "unit": "GB/s",
                                                "frac": achieved / cx.peak, "algorithmic_bytes_per_ray": per_ray,
                                                "per_ray": {k: c[k] / c["rays"] for k in ("branches", "leaves", "items", "prim_tests")}}})
@@ -605,10 +616,15 @@ def run_ours(args):
     for key, fn in (("C4", run_c4), ("C5", run_c5), ("C3", run_c3)):
         if key not in which or (key == "C3" and cx.world_size > 1):
             continue
+        # (garbage of the previous workload -- scenes holding GB of device memory -- is collected HERE, not by a collector
+        # run that lands inside the next workload's timed region: its cudaFree calls stall the device)
+        gc.collect()
+        torch.cuda.empty_cache()
         try:
             configs[key] = fn(cx, args)
         except Exception as exc:   # noqa: BLE001
             configs[key] = {"failed": repr(exc)}
+        gc.collect()
         torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1 only): the compiled reference in a clean subprocess --------------------
