@@ -117,6 +117,11 @@ typedef struct RsbSceneDesc {
 #define RSB_CAMERA_PINHOLE 0
 #define RSB_CAMERA_ORTHOGRAPHIC 1
 #define RSB_CAMERA_CCD 2
+/* VectorCamera (imaging/vector.pyx:44-156): every pixel has its own origin and viewing direction (pixel_origins /
+ * pixel_directions, [nx][ny][3] doubles, observer-local).  Pixels off the edge of the image are sub-sampled: per sample two
+ * draws (point_square) interpolate the direction between the four diagonal neighbours' with Vector3D.slerp; an edge pixel
+ * traces its own direction and draws nothing.  Projection weight 1. */
+#define RSB_CAMERA_VECTOR 3
 typedef struct RsbCamera {
     int32_t nx, ny;
     int32_t pixel_samples;
@@ -125,6 +130,8 @@ typedef struct RsbCamera {
     double sensitivity;
     double to_root[12];       /* rows 0..2 of the observer's to_root() */
     double to_root_w;         /* its m33 (see RsbSceneDesc) */
+    const double* pixel_origins;      /* RSB_CAMERA_VECTOR only, else NULL */
+    const double* pixel_directions;
 } RsbCamera;
 
 /* optical Ray template (raysect/optical/ray.pyx:85-126) for one spectral slice */

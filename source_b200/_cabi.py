@@ -19,7 +19,7 @@ PRIM_PARABOLA = -1
 PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INTERSECT, PRIM_SUBTRACT = range(8)
 PRIM_PARABOLA = -1   # analytic primitives are the types <= PRIM_CONE (include/raysect_b200.h)
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER, MAT_ROUGH_CONDUCTOR = range(7)
-CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD = 0, 1, 2
+CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD, CAMERA_VECTOR = 0, 1, 2, 3
 PROJ_XYZ, PROJ_POWER, PROJ_RADIANCE, PROJ_MAX = 0, 1, 2, 8
 RNG_MT19937_64, RNG_PHILOX = 0, 1
 
@@ -96,6 +96,8 @@ class RsbCamera(C.Structure):
         ("sensitivity", C.c_double),
         ("to_root", C.c_double * 12),
         ("to_root_w", C.c_double),
+        ("pixel_origins", c_double_p),
+        ("pixel_directions", c_double_p),
     ]
 
 

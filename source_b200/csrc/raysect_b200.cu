@@ -74,6 +74,8 @@ struct Context {
     // the (nx, ny, 3) host frames pass through d_xyz_frame (mean | variance) and d_xyz_samples
     double* d_xyz = nullptr;
     size_t xyz_cap = 0;                 // doubles
+    double* d_campix = nullptr;         // VectorCamera: per-pixel origins | directions
+    size_t campix_cap = 0;              // doubles
     double* d_xyz_frame = nullptr;
     int32_t* d_xyz_samples = nullptr;
     size_t xyz_frame_cap = 0;           // elements
@@ -355,6 +357,7 @@ int rsb_context_destroy(uint64_t ctx) {
     cudaFree(c->d_rq);
     cudaFree(c->d_slice);
     cudaFree(c->d_xyz);
+    cudaFree(c->d_campix);
     cudaFree(c->d_xyz_frame);
     cudaFree(c->d_xyz_samples);
     cudaFree(c->d_slice_pix);
@@ -1100,7 +1103,10 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     if (!c || !ds || !camera || !config || !spectral || !rng || !ray_count_dev || (!mean_dev != !variance_dev) || (!mean_dev && !xyz.mean))
         return fail(RSB_ERR_ARG, "rsb_render: null argument");
     if (camera->nx < 1 || camera->ny < 1 || camera->pixel_samples < 1) return fail(RSB_ERR_ARG, "rsb_render: bad camera");
-    if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC && camera->kind != RSB_CAMERA_CCD)
+    if (camera->kind == RSB_CAMERA_VECTOR && (!camera->pixel_origins || !camera->pixel_directions))
+        return fail(RSB_ERR_ARG, "rsb_render: a vector camera needs pixel_origins and pixel_directions");
+    if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC && camera->kind != RSB_CAMERA_CCD &&
+        camera->kind != RSB_CAMERA_VECTOR)
         return fail(RSB_ERR_UNSUPPORTED, "rsb_render: unknown camera kind");
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");
@@ -1208,6 +1214,21 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     a.cam.image_start_y = camera->image_start_y;
     a.cam.sensitivity = camera->sensitivity;
     memcpy(a.cam.to_root, camera->to_root, 12 * sizeof(double));
+    if (camera->kind == RSB_CAMERA_VECTOR) {
+        // per-pixel origins and directions of the VectorCamera: [nx][ny][3] each, uploaded per render (grow-only buffer)
+        const size_t n3 = (size_t)camera->nx * camera->ny * 3;
+        if (c->campix_cap < 2 * n3) {
+            cudaFree(c->d_campix);
+            c->d_campix = nullptr; c->campix_cap = 0;
+            RSB_CUDA(cudaMalloc(&c->d_campix, 2 * n3 * sizeof(double)));
+            c->campix_cap = 2 * n3;
+        }
+        RSB_CUDA(cudaMemcpyAsync(c->d_campix, camera->pixel_origins, n3 * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaMemcpyAsync(c->d_campix + n3, camera->pixel_directions, n3 * 8, cudaMemcpyHostToDevice, st));
+        RSB_CUDA(cudaStreamSynchronize(st));        // the caller's arrays may go away after the call
+        a.cam.pixel_origins = c->d_campix;
+        a.cam.pixel_directions = c->d_campix + n3;
+    }
     if (camera->to_root_w == 0.0) return fail(RSB_ERR_ARG, "rsb_render: RsbCamera.to_root_w (m33 of the camera transform) is zero");
     a.cam.to_root[12] = 1.0 / camera->to_root_w;
     a.mean = mean_dev;

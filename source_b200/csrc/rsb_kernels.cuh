@@ -576,6 +576,11 @@ __global__ void __launch_bounds__(32 * RSB_SEED_WARPS) k_wf_seed(const __grid_co
     g.mti = RSB_MT_NN;
     const int nj = 2 * camera_jitter_pairs(a.cam.kind) * a.cam.pixel_samples;
     double* jit = a.st.pix_jitter + (size_t)w * nj;
+    if (a.cam.kind == 3) {
+        int px, py;
+        wf_pixel_of(a, (unsigned long long)w, &px, &py);
+        if (!camera_pixel_draws(a.cam, px, py)) { a.st.pix_mti[w] = g.mti; return; }     // an edge pixel of a VectorCamera draws nothing
+    }
     for (int k = 0; k < nj; ++k) jit[k] = (double)(g.next_u64() >> 11) * (1.0 / 9007199254740992.0);
     a.st.pix_mti[w] = g.mti;
 }
@@ -622,8 +627,12 @@ __device__ __forceinline__ void wf_regenerate(const WfArgs& a, int slot) {
     } else {
         long long pixel_id = (long long)py * a.cam.nx + px;
         jit.px.init(a.seed + (unsigned long long)wf_group_of(a, slot) * a.seed_stride, (unsigned long long)pixel_id, (uint32_t)s);
-        u1 = jit.uniform();
-        u2 = jit.uniform();
+        if (camera_pixel_draws(a.cam, px, py)) {
+            u1 = jit.uniform();
+            u2 = jit.uniform();
+        } else {
+            u1 = u2 = 0.0;
+        }
         if (pairs == 2) { u3 = jit.uniform(); u4 = jit.uniform(); }
         a.st.philox_idx[slot] = jit.px.idx;
     }

@@ -37,13 +37,15 @@ struct Spectral {    // per spectral slice: what SpectralFunction.sample()/avera
     int32_t n_tables;
 };
 
-struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1) | CCDArray (kind 2)
+struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1) | CCDArray (kind 2) | VectorCamera (kind 3)
     int32_t nx, ny;
     int32_t pixel_samples;
     int32_t kind;
     double image_delta, image_start_x, image_start_y;
     double sensitivity;
     double to_root[RSB_MAT_WORDS];   // rows 0..2, then 1 / m33
+    const double* pixel_origins;     // VectorCamera (kind 3): [nx][ny][3] per-pixel origin and viewing direction
+    const double* pixel_directions;
 };
 
 enum LogOp : int32_t {
@@ -612,6 +614,32 @@ RSB_HD void stats_combine(double mx, double vx, int nx, double my, double vy, in
 // CCD, which draws all its pixel points first and all its directions after them (ccd.pyx:130-131)
 RSB_HD int camera_jitter_pairs(int kind) { return kind == 2 ? 2 : 1; }
 
+// VectorCamera._generate_rays (imaging/vector.pyx:124-125): only pixels off the edge of the image are sub-sampled -- an edge
+// pixel's task draws NOTHING before its rays are traced
+RSB_HD bool camera_pixel_draws(const Camera& cam, int px, int py) {
+    return cam.kind != 3 || (0 < px && px < cam.nx - 1 && 0 < py && py < cam.ny - 1);
+}
+
+// Vector3D.slerp (core/math/vector.pyx:501-604)
+RSB_HD V3 vector_slerp(const V3& a, const V3& b, double t) {
+    const V3 an = normalise(a), bn = normalise(b);
+    const double a_magnitude = sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    const double b_magnitude = sqrt(b.x * b.x + b.y * b.y + b.z * b.z);
+    double angle = acos(an.x * bn.x + an.y * bn.y + an.z * bn.z);
+    V3 v;
+    if (angle < 1e-12) {
+        v = an;
+    } else {
+        angle *= t;
+        const double d = an.x * bn.x + an.y * bn.y + an.z * bn.z;
+        const V3 e = normalise(v3(bn.x - an.x * d, bn.y - an.y * d, bn.z - an.z * d));
+        const double c = cos(angle), s = sin(angle);
+        v = v3(an.x * c + e.x * s, an.y * c + e.y * s, an.z * c + e.z * s);
+    }
+    const double m = (1 - t) * a_magnitude + t * b_magnitude;
+    return v3(v.x * m, v.y * m, v.z * m);
+}
+
 // (u1, u2): the sample's point draws; (u3, u4): its direction draws (CCDArray only)
 RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2, V3* o, V3* d, double* weight, double u3 = 0.0,
                         double u4 = 0.0) {
@@ -621,6 +649,29 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
     // The two uniform() calls are arguments of one C call in the Cython output,
     // new_point3d(uniform()*w - ow, uniform()*h - oh, 0), and gcc evaluates call arguments right to left:
     // the FIRST draw of a sample lands in y, the SECOND in x (verified against the compiled reference).
+    if (cam.kind == 3) {
+        // VectorCamera._generate_rays (imaging/vector.pyx:107-153): the pixel's own origin; off the edge of the image the
+        // direction is interpolated between the four diagonal neighbours' (point_square draws: new_point2d(uniform(),
+        // uniform()) -- arguments evaluated right to left, so the FIRST draw is y), at the edge it is the pixel's own
+        const size_t at = ((size_t)px * cam.ny + py) * 3;
+        const V3 origin = v3(cam.pixel_origins[at], cam.pixel_origins[at + 1], cam.pixel_origins[at + 2]);
+        V3 direction;
+        if (camera_pixel_draws(cam, px, py)) {
+            const double sx = u2, sy = u1;
+            const double* D = cam.pixel_directions;
+            const size_t r0 = ((size_t)(px - 1) * cam.ny + py) * 3, r1 = ((size_t)(px + 1) * cam.ny + py) * 3;
+            const V3 v1 = v3(D[r0 - 3], D[r0 - 2], D[r0 - 1]), v2 = v3(D[r0 + 3], D[r0 + 4], D[r0 + 5]);
+            const V3 v3_ = v3(D[r1 + 3], D[r1 + 4], D[r1 + 5]), v4 = v3(D[r1 - 3], D[r1 - 2], D[r1 - 1]);
+            const V3 v14 = vector_slerp(v1, v4, sx), v23 = vector_slerp(v2, v3_, sx);
+            direction = normalise(vector_slerp(v14, v23, sy));
+        } else {
+            direction = v3(cam.pixel_directions[at], cam.pixel_directions[at + 1], cam.pixel_directions[at + 2]);
+        }
+        *weight = 1.0;
+        *o = xform_point(cam.to_root, origin);
+        *d = xform_vector(cam.to_root, direction);
+        return;
+    }
     double half = 0.5 * cam.image_delta;
     double jy = u1 * cam.image_delta - half;
     double jx = u2 * cam.image_delta - half;

@@ -421,13 +421,24 @@ class DeviceGroup:
         return self.members[0].pin(*arrays)
 
 
-def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None, ccd=False):
+def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None, ccd=False, vector=None):
     """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160), or, with
     ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137) /
     with ``ccd`` CCDArray._update_image_geometry (imaging/ccd.pyx:106-112; ``sensitivity`` = pixel area x 2 pi,
     ccd.pyx:150-151)"""
     cam = cabi.RsbCamera()
-    if width is not None:
+    if vector is not None:
+        # VectorCamera (imaging/vector.pyx:44-156): ``vector`` = (pixel_origins, pixel_directions), (nx, ny, 3) float64 each
+        origins = np.ascontiguousarray(vector[0], dtype=np.float64)
+        directions = np.ascontiguousarray(vector[1], dtype=np.float64)
+        if origins.shape != (nx, ny, 3) or directions.shape != (nx, ny, 3):
+            raise ValueError("Pixel arrays must have equal shapes.")
+        cam.kind = cabi.CAMERA_VECTOR
+        cam.pixel_origins = cabi.ptr(origins, C.c_double)
+        cam.pixel_directions = cabi.ptr(directions, C.c_double)
+        cam._keep = (origins, directions)
+        image_delta = 0.0
+    elif width is not None:
         if width <= 0:
             raise ValueError("width can not be less than or equal to 0 meters.")
         image_delta = width / nx

@@ -225,6 +225,18 @@ class CudaRenderEngine(RenderEngine):
         for th in threads:
             th.join()
 
+    def _vector_pixels(self, observer):
+        """(nx, ny, 3) float64 arrays of a VectorCamera's per-pixel Point3D / Vector3D objects (imaging/vector.pyx:84-86; the
+        object arrays are read-only attributes, so the conversion is done once per array pair)"""
+        key = (id(observer.pixel_origins), id(observer.pixel_directions))
+        cached = getattr(self, "_vector_cache", None)
+        if cached is None or cached[0] != key:
+            nx, ny = observer.pixel_origins.shape
+            o = np.array([[c for pt in row for c in (pt.x, pt.y, pt.z)] for row in observer.pixel_origins], dtype=np.float64).reshape(nx, ny, 3)
+            d = np.array([[c for v in row for c in (v.x, v.y, v.z)] for row in observer.pixel_directions], dtype=np.float64).reshape(nx, ny, 3)
+            self._vector_cache = (key, o, d, observer.pixel_origins, observer.pixel_directions)    # (the arrays stay alive with their ids)
+        return self._vector_cache[1], self._vector_cache[2]
+
     def _accelerator_for(self, world, slice_id):
         # a new observe() starts at slice 0: re-flatten there so scene edits between renders are picked up
         if self._accel is None or self._accel_world is not world or slice_id == 0:
@@ -268,11 +280,12 @@ class CudaRenderEngine(RenderEngine):
 
     def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
         from raysect.optical.observer import (BayerPipeline2D, CCDArray, OrthographicCamera, PinholeCamera, PowerPipeline2D,
-                                              RadiancePipeline2D, RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D)
+                                              RadiancePipeline2D, RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D,
+                                              VectorCamera)
         observer = getattr(render, "__self__", None)
-        if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray)):
-            raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera and CCDArray observers; got %r "
-                                      "(no CPU fallback)" % type(observer).__name__)
+        if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray, VectorCamera)):
+            raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera, CCDArray and VectorCamera observers; "
+                                      "got %r (no CPU fallback)" % type(observer).__name__)
         pipelines = list(observer.pipelines)
         for p in pipelines:
             if not isinstance(p, (SpectralPowerPipeline2D, SpectralRadiancePipeline2D, RGBPipeline2D, PowerPipeline2D, RadiancePipeline2D,
@@ -295,6 +308,9 @@ class CudaRenderEngine(RenderEngine):
             raise ValueError("the observer's pixel_samples (%d) must be a multiple of the engine's passes (%d)"
                              % (observer.pixel_samples, self.passes))
         def camera_for(sensitivity):
+            if isinstance(observer, VectorCamera):
+                return camera_desc(nx, ny, observer.pixel_samples // self.passes, None, sensitivity, observer.to_root(),
+                                   vector=self._vector_pixels(observer))
             if isinstance(observer, CCDArray):
                 return camera_desc(nx, ny, observer.pixel_samples // self.passes, None, sensitivity, observer.to_root(),
                                    width=observer.width, ccd=True)

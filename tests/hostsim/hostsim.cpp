@@ -233,6 +233,8 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
     cam.sensitivity = camera->sensitivity;
     memcpy(cam.to_root, camera->to_root, 12 * sizeof(double));
     cam.to_root[12] = 1.0 / camera->to_root_w;
+    cam.pixel_origins = camera->pixel_origins;
+    cam.pixel_directions = camera->pixel_directions;
 
     int cap = 6 * (std::max(cfg.max_depth, cfg.extinction_min_depth) + 2);
     std::vector<LogEntry> logbuf((size_t)cap);
@@ -253,10 +255,11 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
         rng.mt.mt = st_path.data(); rng.mt.stride = 1; rng.mt.mti = RSB_MT_NN;
         jit.mt.mt = st_jit.data(); jit.mt.stride = 1; jit.mt.mti = RSB_MT_NN;
         const int pairs = camera_jitter_pairs(cam.kind);
-        std::vector<double> pre((size_t)2 * pairs * spp);
+        const bool draws = camera_pixel_draws(cam, px, py);      // (an edge pixel of a VectorCamera draws nothing up front)
+        std::vector<double> pre((size_t)2 * pairs * spp, 0.0);
         if (rngd->mode == RNG_MT19937_64) {
-            mt_seed_pair(rngd->seed + (uint64_t)pixel_id, 2 * pairs * spp, st_jit.data(), &jit.mt.mti, st_path.data(), &rng.mt.mti);
-            for (size_t k = 0; k < pre.size(); ++k) pre[k] = jit.uniform();      // the task's up-front draws, in draw order
+            mt_seed_pair(rngd->seed + (uint64_t)pixel_id, draws ? 2 * pairs * spp : 0, st_jit.data(), &jit.mt.mti, st_path.data(), &rng.mt.mti);
+            for (size_t k = 0; draws && k < pre.size(); ++k) pre[k] = jit.uniform();      // the task's up-front draws, in draw order
         }
         double* m = mean + frame_row * bins;
         double* v = variance + frame_row * bins;
@@ -267,7 +270,7 @@ int hs_render(uint64_t scene, const RsbCamera* camera, const RsbRayConfig* confi
                 u1 = pre[2 * s]; u2 = pre[2 * s + 1];
                 if (pairs == 2) { u3 = pre[2 * spp + 2 * s]; u4 = pre[2 * spp + 2 * s + 1]; }
             } else {
-                u1 = rng.uniform(); u2 = rng.uniform();
+                if (draws) { u1 = rng.uniform(); u2 = rng.uniform(); } else { u1 = u2 = 0.0; }
                 if (pairs == 2) { u3 = rng.uniform(); u4 = rng.uniform(); }
             }
             V3 o, d;

@@ -327,6 +327,49 @@ def test_mono_pipelines_on_device_against_live_reference(device, reference):
                              rtol=1e-6, max_divergent_fraction=0.0)
 
 
+def test_vector_camera_on_device_against_live_reference(device, reference):
+    """VectorCamera (per-pixel origins / directions, slerp sub-sampling off the edge, no draws at the edge) with an RGB and a
+    spectral pipeline on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.core import Point3D, Vector3D
+    from raysect.optical.observer import RGBPipeline2D, VectorCamera
+    from source_b200.plugin import CudaRenderEngine
+    nx, ny = 14, 11
+    origins = np.empty((nx, ny), dtype=object)
+    directions = np.empty((nx, ny), dtype=object)
+    for x in range(nx):
+        for y in range(ny):
+            origins[x, y] = Point3D(0.02 * (x - nx / 2), 0.02 * (y - ny / 2), 0.0)
+            directions[x, y] = Vector3D(-0.9 * (x + 0.5 - nx / 2) / nx, -0.9 * (y + 0.5 - ny / 2) / ny, 1.0 + 0.01 * x * y)
+
+    def camera(world):
+        pipe, rgb = api.SpectralPowerPipeline2D(), RGBPipeline2D(display_progress=False)
+        cam = VectorCamera(origins, directions, frame_sampler=api.FullFrameSampler2D(), pipelines=[pipe, rgb], sensitivity=1.4,
+                           parent=world, transform=api.translate(0.05, 0.0, -3.1) * api.rotate(3, -2, 1))
+        cam.spectral_rays = 1
+        cam.spectral_bins = 12
+        cam.spectral_rays = 2
+        cam.pixel_samples = 4
+        cam.quiet = True
+        return cam, pipe, rgb
+    cam, pipe, rgb = camera(scenes.cornell_box(api))
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 3030)
+    x_ref = dict(mean=np.array(rgb.xyz_frame.mean), variance=np.array(rgb.xyz_frame.variance), samples=np.array(rgb.xyz_frame.samples))
+    cam2, pipe2, rgb2 = camera(scenes.cornell_box(api))
+    cam2.render_engine = CudaRenderEngine(seed=3030, rng="mt", device=device)
+    cam2.observe()
+
+    class F:  # noqa: E701
+        mean, variance, samples = np.array(pipe2.frame.mean), np.array(pipe2.frame.variance), np.array(pipe2.frame.samples)
+
+    class X:  # noqa: E701
+        mean, variance, samples = np.array(rgb2.xyz_frame.mean), np.array(rgb2.xyz_frame.variance), np.array(rgb2.xyz_frame.samples)
+    assert m_ref[0].max() > 0 and m_ref[5, 5].max() > 0
+    parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+    parity.compare_frame(X, x_ref, exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+
+
 def test_ccd_array_on_device_against_live_reference(device, reference):
     """CCDArray (a bare sensor inside the Cornell box) with its default RGB pipeline and a spectral one through
     CudaRenderEngine on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""
