@@ -365,7 +365,7 @@ def test_vector_camera_on_device_against_live_reference(device, reference):
 
     class X:  # noqa: E701
         mean, variance, samples = np.array(rgb2.xyz_frame.mean), np.array(rgb2.xyz_frame.variance), np.array(rgb2.xyz_frame.samples)
-    assert m_ref[0].max() > 0 and m_ref[5, 5].max() > 0
+    assert m_ref[0].max() > 0 and m_ref[1:-1, 1:-1].max() > 0      # edge and interior pixels both see light
     parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
     parity.compare_frame(X, x_ref, exact=False, rtol=1e-6, max_divergent_fraction=0.0)
 
