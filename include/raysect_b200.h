@@ -39,6 +39,8 @@ extern "C" {
 #define RSB_PRIM_UNION 5
 #define RSB_PRIM_INTERSECT 6
 #define RSB_PRIM_SUBTRACT 7
+#define RSB_PRIM_TORUS (-2)    /* raysect/primitive/torus.pyx; params: major radius, minor radius.  World-level only (a torus has
+                                  up to four crossings; the CSG operand interface here carries two) */
 #define RSB_PRIM_PARABOLA (-1) /* raysect/primitive/parabola.pyx; params: radius, height.  (Analytic primitives are the
                                   types <= RSB_PRIM_CONE, meshes 4, CSG operators >= 5: the new analytic type takes -1.) */
 
@@ -86,7 +88,7 @@ typedef struct RsbSceneDesc {
     const int32_t* prim_child_b;
     const int32_t* prim_mesh;       /* mesh row, else -1 */
     const int32_t* prim_parent;     /* enclosing CSG row, -1 for world-level primitives */
-    const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone/parabola r,h */
+    const double* prim_params;      /* [n][6] sphere r | box lower,upper | cylinder/cone/parabola r,h | torus R,r */
     /* matrices travel as [13]: rows 0..2 of the AffineMatrix3D, then its m33.  The bottom row of an affine matrix is
      * (0, 0, 0, m33); Point3D.transform divides by it (raysect/core/math/point.pyx:272-281), and AffineMatrix3D.inverse()
      * of a non-rigid chain can leave m33 = 1 - 1 ulp, so it is carried instead of assumed. */

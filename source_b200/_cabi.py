@@ -18,6 +18,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_OVERFLOW = 0, 1, 2, 3, 4
 PRIM_PARABOLA = -1
 PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INTERSECT, PRIM_SUBTRACT = range(8)
 PRIM_PARABOLA = -1   # analytic primitives are the types <= PRIM_CONE (include/raysect_b200.h)
+PRIM_TORUS = -2
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER, MAT_ROUGH_CONDUCTOR = range(7)
 CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD, CAMERA_VECTOR = 0, 1, 2, 3
 PROJ_XYZ, PROJ_POWER, PROJ_RADIANCE, PROJ_MAX = 0, 1, 2, 8

@@ -426,9 +426,77 @@ RSB_HD void parabola_geometry(const double* params, const V3& o, const V3& d, do
     is->exiting = dot(d, n) >= 0.0;
 }
 
+// raysect/primitive/torus.pyx:156-262 (hit).  params: major radius, minor radius.  The quartic's sorted real roots; the
+// first one inside [0, max_distance] is the hit, the next one (if inside the range) is what next_intersection() would
+// hand out.  Tori are world-level primitives here (not CSG operands: those need all four crossings).
+RSB_HD int torus_crossings(const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
+    const double major = params[0], minor = params[1];
+    double sq_origin_xy = o.x * o.x + o.y * o.y;
+    double sq_direction_xy = d.x * d.x + d.y * d.y;
+    double sq_origin = sq_origin_xy + o.z * o.z;
+    double sq_direction = sq_direction_xy + d.z * d.z;
+    double origin_direction_xy = o.x * d.x + o.y * d.y;
+    double origin_dot_direction = origin_direction_xy + o.z * d.z;
+    double sq_r = minor * minor;
+    double sq_R = major * major;
+    double R2_r2 = sq_R - sq_r;
+    double a = sq_direction * sq_direction;
+    double b = 4.0 * sq_direction * origin_dot_direction;
+    double c = 2.0 * (2.0 * origin_dot_direction * origin_dot_direction + sq_direction * (sq_origin + R2_r2)) - 4.0 * sq_R * sq_direction_xy;
+    double dd = 4.0 * origin_dot_direction * (sq_origin + R2_r2) - 8.0 * sq_R * origin_direction_xy;
+    double e = (sq_origin + R2_r2) * (sq_origin + R2_r2) - 4.0 * sq_R * sq_origin_xy;
+    double t[4];
+    int num = solve_quartic(a, b, c, dd, e, &t[0], &t[1], &t[2], &t[3]);
+    if (num == 0) return 0;
+    if (num == 1) {
+        if (t[0] > max_distance || t[0] < 0.0) return 0;
+        out[0].t = t[0]; out[0].code = 0;
+        return 1;
+    }
+    if (num == 2) {
+        if (t[0] > t[1]) swap_dbl(&t[0], &t[1]);
+        t[2] = t[1]; t[3] = t[1];
+    } else if (num == 3) {
+        sort_three_doubles(&t[0], &t[1], &t[2]);
+        t[3] = t[2];
+    } else if (num == 4) {
+        sort_four_doubles(&t[0], &t[1], &t[2], &t[3]);
+    } else {
+        return 0;
+    }
+    if (t[0] > max_distance || t[3] < 0.0) return 0;
+    for (int i = 0; i < num - 1; ++i) {
+        if (t[i] >= 0.0) {
+            out[0].t = t[i]; out[0].code = 0;
+            if (t[i + 1] <= max_distance) { out[1].t = t[i + 1]; out[1].code = 0; return 2; }
+            return 1;
+        }
+    }
+    if (t[num - 1] <= max_distance) {
+        out[0].t = t[num - 1]; out[0].code = 0;
+        return 1;
+    }
+    return 0;
+}
+
+// torus.pyx:294-327 (_generate_intersection)
+RSB_HD void torus_geometry(const double* params, const V3& o, const V3& d, double t, Isect* is) {
+    const double EPSILON = 1e-9;
+    V3 hit = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    double alpha = params[0] / hypot(hit.x, hit.y);
+    V3 n = normalise(v3((1.0 - alpha) * hit.x, (1.0 - alpha) * hit.y, hit.z));
+    double delta_x = EPSILON * n.x, delta_y = EPSILON * n.y, delta_z = EPSILON * n.z;
+    is->hit = hit;
+    is->normal = n;
+    is->inside = v3(hit.x - delta_x, hit.y - delta_y, hit.z - delta_z);
+    is->outside = v3(hit.x + delta_x, hit.y + delta_y, hit.z + delta_z);
+    is->exiting = dot(d, n) >= 0.0;
+}
+
 RSB_HD int analytic_crossings(int type, const double* params, const V3& o, const V3& d, double max_distance, Crossing* out) {
     switch (type) {
         case PRIM_PARABOLA: return parabola_crossings(params, o, d, max_distance, out);
+        case PRIM_TORUS: return torus_crossings(params, o, d, max_distance, out);
         case PRIM_SPHERE: return sphere_crossings(params, o, d, max_distance, out);
         case PRIM_BOX: return box_crossings(params, o, d, max_distance, out);
         case PRIM_CYLINDER: return cylinder_crossings(params, o, d, max_distance, out);
@@ -443,6 +511,7 @@ RSB_HD void analytic_geometry(int type, const double* params, const V3& o, const
         case PRIM_BOX: box_geometry(params, o, d, t, code, is); break;
         case PRIM_CYLINDER: cylinder_geometry(params, o, d, t, code, is); break;
         case PRIM_PARABOLA: parabola_geometry(params, o, d, t, code, is); break;
+        case PRIM_TORUS: torus_geometry(params, o, d, t, is); break;
         default: cone_geometry(params, o, d, t, code, is); break;
     }
 }
@@ -464,6 +533,14 @@ RSB_HD bool analytic_contains(int type, const double* params, const V3& p) {
         case PRIM_CYLINDER: {
             bool slab = (0.0 <= p.z) && (p.z <= params[1]);
             return slab && ((p.x * p.x + p.y * p.y) <= (params[0] * params[0]));
+        }
+        case PRIM_TORUS: {      // torus.pyx:329-343
+            double distance_xy = p.x * p.x + p.y * p.y;
+            double distance_sqr = distance_xy + p.z * p.z;
+            double sq_R = params[0] * params[0];
+            double R2_r2 = sq_R - params[1] * params[1];
+            double discriminant = distance_sqr * distance_sqr + 2.0 * distance_sqr * R2_r2 + R2_r2 * R2_r2 - 4.0 * sq_R * distance_xy;
+            return discriminant <= 0.0;
         }
         case PRIM_PARABOLA: {   // parabola.pyx:344-363
             double radius = params[0], height = params[1];

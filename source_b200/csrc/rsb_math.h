@@ -108,6 +108,166 @@ RSB_HD bool solve_quadratic(double a, double b, double c, double* t0, double* t1
     return true;
 }
 
+// ---- quartic roots (raysect/core/math/cython/utility.pyx:423-733), for the torus ------------------------------------------
+// Transcribed operation for operation -- including one_newton_step's derivative, which is not the derivative of the quartic
+// (utility.pyx:676: ((4x + 3b)x + 2d)x + e) -- because the roots' bits are the hit distances.
+#ifndef RSB_PI
+#define RSB_PI 3.14159265358979323846
+#endif
+#define RSB_EQN_EPS 1.0e-9
+RSB_HD bool eqn_is_zero(double v) { return v < RSB_EQN_EPS && v > -RSB_EQN_EPS; }     // utility.pxd:91-92
+RSB_HD void swap_dbl(double* a, double* b) { double t = *a; *a = *b; *b = t; }
+RSB_HD void sort_three_doubles(double* a, double* b, double* c) {                       // utility.pxd:69-75
+    if (*a > *b) swap_dbl(a, b);
+    if (*b > *c) {
+        swap_dbl(b, c);
+        if (*a > *c) swap_dbl(a, c);
+    }
+}
+RSB_HD void sort_four_doubles(double* a, double* b, double* c, double* d) {             // utility.pxd:77-89
+    if (*a > *b) swap_dbl(a, b);
+    if (*b > *c) swap_dbl(b, c);
+    if (*c > *d) swap_dbl(c, d);
+    if (*a > *b) swap_dbl(a, b);
+    if (*b > *c) swap_dbl(b, c);
+    if (*a > *b) swap_dbl(a, b);
+}
+
+// utility.pyx:423-497
+RSB_HD int solve_cubic(double a, double b, double c, double d, double* t0, double* t1, double* t2) {
+    b /= a;
+    c /= a;
+    d /= a;
+    double sq_b = b * b;
+    double q = (3.0 * c - sq_b) / 9.0;
+    double r = (c * b - 3.0 * d) / 6.0 - b * sq_b / 27.0;
+    double cb_q = q * q * q;
+    double D = cb_q + r * r;
+    if (D > 0) {
+        double A = cbrt(fabs(r) + sqrt(D));
+        double z0;
+        if (r < 0) z0 = q / A - A;
+        else z0 = A - q / A;
+        *t0 = z0 - b / 3.0;
+        *t1 = -0.5 * z0 - b / 3.0;
+        *t2 = 0.5 * sqrt(3.0) * (A + q / A);
+        return 1;
+    }
+    double phi;
+    if (eqn_is_zero(q)) phi = 0.0;
+    else phi = acos(r / sqrt(-cb_q)) / 3.0;
+    double u = 2.0 * sqrt(-q);
+    *t0 = u * cos(phi) - b / 3.0;
+    *t1 = -u * cos(phi + RSB_PI / 3.0) - b / 3.0;
+    *t2 = -u * cos(phi - RSB_PI / 3.0) - b / 3.0;
+    return 3;
+}
+
+// utility.pyx:500-555
+RSB_HD int solve_biquadratic(double a, double c, double e, double* t0, double* t1, double* t2, double* t3) {
+    double s0, s1;
+    if (!solve_quadratic(a, c, e, &s0, &s1)) return 0;
+    if (s0 > s1) swap_dbl(&s0, &s1);
+    if (s0 >= 0) {
+        double sx0 = sqrt(s0), sx1 = sqrt(s1);
+        *t0 = -sx1; *t1 = -sx0; *t2 = sx0; *t3 = sx1;
+        return 4;
+    } else if (s1 >= 0) {
+        double sx1 = sqrt(s1);
+        *t0 = -sx1; *t1 = sx1;
+        return 2;
+    }
+    return 0;
+}
+
+// utility.pyx:558-664 (_solve_depressed_quartic): x^4 + p x^2 + q x + r through the resolvent cubic (Van der Waerden)
+RSB_HD int solve_depressed_quartic(double p, double q, double r, double* t0, double* t1, double* t2, double* t3) {
+    double sigma = q > 0 ? 1.0 : -1.0;
+    if (eqn_is_zero(q)) return solve_biquadratic(1.0, p, r, t0, t1, t2, t3);
+    int num = solve_cubic(1.0, -2.0 * p, p * p - 4.0 * r, q * q, t0, t1, t2);
+    double A, B;
+    if (num > 1) {
+        sort_three_doubles(t0, t1, t2);
+        if (!(*t0 <= 0)) return 0;
+        double s0 = sqrt(-*t0);
+        A = -*t1 - *t2 - 2.0 * sigma * sqrt(*t1 * *t2);
+        B = -*t1 - *t2 + 2.0 * sigma * sqrt(*t1 * *t2);
+        if (A >= 0 && B >= 0) {
+            double sq_A = sqrt(A), sq_B = sqrt(B);
+            *t0 = 0.5 * (s0 + sq_A); *t1 = 0.5 * (s0 - sq_A); *t2 = 0.5 * (-s0 + sq_B); *t3 = 0.5 * (-s0 - sq_B);
+            return 4;
+        } else if (A < 0 && B >= 0) {
+            double sq_B = sqrt(B);
+            *t0 = 0.5 * (-s0 + sq_B); *t1 = 0.5 * (-s0 - sq_B);
+            return 2;
+        } else if (A >= 0 && B < 0) {
+            double sq_A = sqrt(A);
+            *t0 = 0.5 * (s0 + sq_A); *t1 = 0.5 * (s0 - sq_A);
+            return 2;
+        }
+        return 0;
+    }
+    if (!(*t0 <= 0)) return 0;
+    double s0 = sqrt(-*t0);
+    A = -2.0 * *t1 - 2.0 * sigma * sqrt(*t1 * *t1 + *t2 * *t2);
+    B = -2.0 * *t1 + 2.0 * sigma * sqrt(*t1 * *t1 + *t2 * *t2);
+    if (A >= 0 && B >= 0) {
+        double sq_A = sqrt(A), sq_B = sqrt(B);
+        *t0 = 0.5 * (s0 + sq_A); *t1 = 0.5 * (s0 - sq_A); *t2 = 0.5 * (-s0 + sq_B); *t3 = 0.5 * (-s0 - sq_B);
+        return 4;
+    } else if (A < 0 && B >= 0) {
+        double sq_B = sqrt(B);
+        *t0 = 0.5 * (-s0 + sq_B); *t1 = 0.5 * (-s0 - sq_B);
+        return 2;
+    } else if (A >= 0 && B < 0) {
+        double sq_A = sqrt(A);
+        *t0 = 0.5 * (s0 + sq_A); *t1 = 0.5 * (s0 - sq_A);
+        return 2;
+    }
+    return 0;
+}
+
+// utility.pyx:667-680
+RSB_HD void one_newton_step(double b, double c, double d, double e, double* x) {
+    double dfx = ((4.0 * *x + 3 * b) * *x + 2.0 * d) * *x + e;
+    if (!eqn_is_zero(dfx)) {
+        double fx = (((*x + b) * *x + c) * *x + d) * *x + e;
+        *x = *x - fx / dfx;
+    }
+}
+
+// utility.pyx:683-733.  Roots the reference leaves undefined are carried as 0.0 here (it reads and shifts uninitialised
+// memory; no caller looks at them).
+RSB_HD int solve_quartic(double a, double b, double c, double d, double e, double* t0, double* t1, double* t2, double* t3) {
+    b /= a;
+    c /= a;
+    d /= a;
+    e /= a;
+    double sq_b = b * b;
+    double p = c - 3 * sq_b / 8.0;
+    double q = sq_b * b / 8.0 - 0.5 * b * c + d;
+    double r = -3.0 * sq_b * sq_b / 256.0 + sq_b * c / 16.0 - b * d / 4.0 + e;
+    int num;
+    *t0 = 0.0; *t1 = 0.0; *t2 = 0.0; *t3 = 0.0;
+    if (eqn_is_zero(r)) {
+        *t0 = 0;
+        num = 1 + solve_cubic(1.0, 0.0, p, q, t1, t2, t3);
+    } else {
+        num = solve_depressed_quartic(p, q, r, t0, t1, t2, t3);
+    }
+    *t0 -= b / 4.0;
+    *t1 -= b / 4.0;
+    *t2 -= b / 4.0;
+    *t3 -= b / 4.0;
+    if (num > 0) {
+        one_newton_step(b, c, d, e, t0);
+        one_newton_step(b, c, d, e, t1);
+    }
+    if (num > 2) one_newton_step(b, c, d, e, t2);
+    if (num > 3) one_newton_step(b, c, d, e, t3);
+    return num;
+}
+
 // raysect/core/boundingbox.pyx:200-245 (_slab)
 RSB_HD void box_slab(double origin, double direction, double lower, double upper, double* front, double* back) {
     double tmin, tmax;

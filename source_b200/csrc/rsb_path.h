@@ -14,7 +14,9 @@
 
 namespace rsb {
 
+#ifndef RSB_PI
 #define RSB_PI 3.14159265358979323846
+#endif
 #define RSB_1_PI 0.31830988618379067154
 
 struct RayConfig {   // optical Ray template fields, raysect/optical/ray.pyx:85-126

@@ -18,6 +18,7 @@ enum PrimType : int32_t {
     PRIM_BOX = 1,
     PRIM_CYLINDER = 2,
     PRIM_PARABOLA = -1,   // raysect/primitive/parabola.pyx (analytic primitives are the types <= PRIM_CONE)
+    PRIM_TORUS = -2,      // raysect/primitive/torus.pyx (world-level only: not a CSG operand)
     PRIM_CONE = 3,
     PRIM_MESH = 4,
     PRIM_UNION = 5,

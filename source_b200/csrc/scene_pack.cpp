@@ -26,6 +26,7 @@ namespace {
 int csg_depth_and_leaves(const RsbSceneDesc* d, int id, int depth, int* leaves, std::string* err) {
     if (id < 0 || id >= d->n_primitives) { *err = "CSG operand row out of range"; return -1; }
     int t = d->prim_type[id];
+    if (t == RSB_PRIM_TORUS && depth > 0) { *err = "Torus operands inside CSG are not supported on the device path"; return -1; }
     if (t <= RSB_PRIM_CONE) { *leaves += 1; return depth; }
     if (t == RSB_PRIM_MESH) { *err = "Mesh operands inside CSG are not supported on the device path"; return -1; }
     if (depth > 16) { *err = "CSG tree too deep (cycle?)"; return -1; }
@@ -45,7 +46,7 @@ int pack_scene(const RsbSceneDesc* d, PackedScene* out, std::string* err) {
     }
     for (int i = 0; i < d->n_primitives; ++i) {
         int t = d->prim_type[i];
-        if (t < RSB_PRIM_PARABOLA || t > RSB_PRIM_SUBTRACT) { *err = "unsupported primitive type in row " + std::to_string(i); return RSB_ERR_UNSUPPORTED; }
+        if (t < RSB_PRIM_TORUS || t > RSB_PRIM_SUBTRACT) { *err = "unsupported primitive type in row " + std::to_string(i); return RSB_ERR_UNSUPPORTED; }
         if (t == RSB_PRIM_MESH && (d->prim_mesh[i] < 0 || d->prim_mesh[i] >= d->n_meshes)) { *err = "mesh row out of range"; return RSB_ERR_ARG; }
         if (i < d->n_world && (d->prim_material[i] < 0 || d->prim_material[i] >= d->n_materials)) {
             *err = "material row out of range for primitive " + std::to_string(i);

@@ -22,7 +22,7 @@ from . import _cabi as cabi
 
 _SHAPES = {
     "Sphere": cabi.PRIM_SPHERE, "Box": cabi.PRIM_BOX, "Cylinder": cabi.PRIM_CYLINDER, "Cone": cabi.PRIM_CONE,
-    "Parabola": cabi.PRIM_PARABOLA,
+    "Parabola": cabi.PRIM_PARABOLA, "Torus": cabi.PRIM_TORUS,
     "Mesh": cabi.PRIM_MESH, "Union": cabi.PRIM_UNION, "Intersect": cabi.PRIM_INTERSECT, "Subtract": cabi.PRIM_SUBTRACT,
 }
 _MATERIALS = {
@@ -243,6 +243,11 @@ def flatten_world(world, world_kdtree=None):
             row["params"][0] = p.radius
         elif t == cabi.PRIM_BOX:
             row["params"] = [p.lower.x, p.lower.y, p.lower.z, p.upper.x, p.upper.y, p.upper.z]
+        elif t == cabi.PRIM_TORUS:
+            if not top_level:
+                raise NotImplementedError("Torus as a CSG operand (a torus has up to four crossings; operands here carry two)")
+            row["params"][0] = p.major_radius
+            row["params"][1] = p.minor_radius
         elif t in (cabi.PRIM_CYLINDER, cabi.PRIM_CONE, cabi.PRIM_PARABOLA):
             row["params"][0] = p.radius
             row["params"][1] = p.height

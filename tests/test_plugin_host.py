@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import hostsim_api
+import parity
 import scenes
 
 pytestmark = pytest.mark.ref
@@ -665,6 +666,56 @@ def test_vector_camera_matches_serial_reference(api, reference):
     assert m_ref[0].max() > 0 and m_ref[3, 3].max() > 0      # edge and interior pixels both see light
 
 
+def test_torus_matches_reference(api, reference):
+    """Torus (primitive/torus.pyx; quartic roots by Van der Waerden's method + one Newton step, core/math/cython/utility.pyx:
+    423-733): World.hit ids / distances / local geometry / exiting and World.contains against the reference's own KDTree on
+    rays through, past, tangent to and from inside two tori; then a rendered frame with a torus lamp and a glass torus."""
+    from raysect.primitive import Torus
+    from source_b200.plugin import CudaAccelerator, CudaRenderEngine
+
+    def scene():
+        world = api.World()
+        Torus(1.0, 0.35, parent=world, transform=api.translate(0.1, -0.2, 0.3) * api.rotate(25, 40, 10),
+              material=api.UniformSurfaceEmitter(api.ConstantSF(1.0), 0.8))
+        Torus(0.6, 0.6, parent=world, transform=api.translate(-0.4, 0.9, 1.4) * api.rotate(-70, 15, 0), material=api.schott("N-BK7"))
+        api.Sphere(0.3, parent=world, transform=api.translate(0.1, -0.2, 0.3), material=api.Lambert(api.ConstantSF(0.7)))
+        return world
+    rng = np.random.default_rng(11)
+    n = 3000
+    o = rng.uniform(-2.5, 2.5, (n, 3))
+    d = rng.normal(size=(n, 3))
+    o[:600] = rng.uniform(-0.2, 0.2, (600, 3)) + np.array([0.1, -0.2, 0.3])          # from inside the first torus' hole / tube region
+    d[600:900] = (np.array([0.1, -0.2, 0.3]) - o[600:900]) + rng.normal(scale=0.3, size=(300, 3))
+    md = np.where(rng.uniform(size=n) < 0.3, rng.uniform(0.2, 3.0, n), np.inf)
+    world = scene()
+    ref = reference.oracle_hit(world, o, d, md)
+    pts = rng.uniform(-1.6, 1.6, (2000, 3))
+    ref_cnt, ref_prims = reference.oracle_contains(world, pts)
+    acc = CudaAccelerator(backend=hostsim_api.HostScene)
+    world.accelerator = acc
+    world.build_accelerator(force=True)
+    r = acc.hit_batch(o, d, md, geometry=True)
+    assert (ref["primitive"] == 0).sum() > 150 and (ref["primitive"] == 1).sum() > 60 and ref["exiting"][ref["primitive"] >= 0].any()
+    parity.check_hits(r, ref)
+    cnt, prims = acc.contains_batch(pts, 4)
+    np.testing.assert_array_equal(cnt, ref_cnt)
+    for k in range(len(pts)):
+        assert sorted(prims[k, :cnt[k]].tolist()) == sorted(ref_prims[k, :ref_cnt[k]].tolist())
+    assert ref_cnt.max() >= 1 and (ref_cnt > 0).sum() > 50
+    # a frame
+    kw = dict(pixels=(12, 10), samples=3, bins=8, spectral_rays=1)
+    cam, pipe = scenes.cornell_camera(api, scene(), **kw)
+    cam.transform = api.translate(0, 0, -3.5)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 404)
+    cam2, pipe2 = scenes.cornell_camera(api, scene(), **kw)
+    cam2.transform = api.translate(0, 0, -3.5)
+    cam2.render_engine = CudaRenderEngine(seed=404, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    np.testing.assert_array_equal(np.array(pipe2.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(pipe2.frame.variance), v_ref)
+    assert (m_ref.sum(axis=2) > 0).sum() > 20
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import Pipeline2D
     from source_b200.plugin import CudaRenderEngine
@@ -678,9 +729,14 @@ def test_unsupported_objects_fail_loudly(api):
     with pytest.raises(NotImplementedError):
         cam.observe()
     from raysect.primitive import Torus
+    from raysect.primitive.lens.spherical import BiConvex
     from source_b200.plugin import CudaAccelerator
-    Torus(1.0, 0.2, world, material=api.AbsorbingSurface())
+    lens = BiConvex(0.2, 0.05, 0.3, 0.3, parent=world, material=api.AbsorbingSurface())      # an EncapsulatedPrimitive
     world.accelerator = CudaAccelerator(backend=hostsim_api.HostScene)
+    with pytest.raises(NotImplementedError):
+        world.build_accelerator(force=True)
+    lens.parent = None
+    api.Union(Torus(1.0, 0.2), api.Sphere(0.5), parent=world, material=api.AbsorbingSurface())      # a torus as a CSG operand
     with pytest.raises(NotImplementedError):
         world.build_accelerator(force=True)
 
