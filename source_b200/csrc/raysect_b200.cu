@@ -410,7 +410,8 @@ int rsb_scene_create(uint64_t ctx, const RsbSceneDesc* d, uint64_t* scene) {
     ds->sc.n_prims = (int32_t)ps.prims.size();
     for (const Prim& pr : ps.prims) {
         if (pr.type == PRIM_MESH) ds->has_mesh = true;
-        if (pr.type >= PRIM_UNION) ds->has_csg = true;
+        // (has_csg = "needs the full-featured kernel instantiations": CSG trees, and the torus with its quartic solver)
+        if (pr.type >= PRIM_UNION || pr.type == PRIM_TORUS) ds->has_csg = true;
     }
     for (int32_t i = 0; i < ps.n_world; ++i)
         if (ps.prims[i].type == PRIM_MESH) ds->n_mesh_prims += 1;
