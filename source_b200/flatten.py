@@ -62,6 +62,27 @@ def _classify(obj, table, what):
         % (what, type(obj).__name__, ", ".join(sorted(table))))
 
 
+def _encapsulated(p):
+    """The primitive an ``EncapsulatedPrimitive`` (raysect/primitive/utility.pyx:36-96; the lens library's base class) hides.
+    Its hit / next_intersection / contains / bounding_box hand the WORLD ray or point straight to that primitive, which hangs
+    under a private local root with ``transform = wrapper.to_root()``, and only re-label the Intersection (utility.pyx:74-96)
+    -- so to the device the wrapper IS the inner primitive with the inner primitive's own matrices.  The attribute is a
+    private cdef field; the garbage collector's view of the object exposes it."""
+    import gc
+    base = next((c for c in type(p).__mro__ if c.__name__ == "EncapsulatedPrimitive"), None)
+    if base is None:
+        return None
+    changed = [m for m in _EVALUATED if getattr(type(p), m, None) is not getattr(base, m, None)]
+    if changed:
+        raise NotImplementedError("primitive %r overrides %s of EncapsulatedPrimitive: the B200 path never calls back into Python; "
+                                  "there is no CPU fallback" % (type(p).__name__, ", ".join(changed)))
+    inner = [o for o in gc.get_referents(p)
+             if o is not p and hasattr(o, "hit") and hasattr(o, "bounding_box") and type(getattr(o, "parent", None)).__name__ == "BridgeNode"]
+    if len(inner) != 1:
+        raise NotImplementedError("cannot find the primitive encapsulated by %r" % type(p).__name__)
+    return inner[0]
+
+
 def mat34(m):
     """An AffineMatrix3D as the C ABI carries it: rows 0..2, then m33 (13 values).  Raysect's Point3D.transform divides
     by w = m30 x + m31 y + m32 z + m33 (point.pyx:272-281); the bottom row of an affine matrix is (0, 0, 0, m33), and
@@ -220,6 +241,7 @@ def flatten_world(world, world_kdtree=None):
     rows = []          # dict rows
     mesh_descs, mesh_index, keep = [], {}, []
     material_index = {}
+    encapsulated = {}      # id(EncapsulatedPrimitive) -> the primitive it hides
 
     def material_row(material):
         key = id(material)
@@ -230,6 +252,11 @@ def flatten_world(world, world_kdtree=None):
         return material_index[key]
 
     def add(p, parent_row, top_level):
+        inner = _encapsulated(p)
+        if inner is not None:
+            # (lenses: EncapsulatedPrimitive(Intersect(Intersect(Sphere, Sphere), Cylinder)) and the like)
+            encapsulated[id(p)] = inner
+            return add(inner, parent_row, top_level)
         t = _classify(p, _SHAPES, "primitive")
         row = dict(type=t, material=-1, a=-1, b=-1, mesh=-1, parent=parent_row, params=[0.0] * 6,
                    to_local=mat34(p.to_local()), to_root=mat34(p.to_root()), root_inv=mat34(p.to_local()),
@@ -266,6 +293,7 @@ def flatten_world(world, world_kdtree=None):
         rows.append(row)
     # then CSG operands, depth first
     def expand(p, my_row):
+        p = encapsulated.get(id(p), p)
         t = rows[my_row]["type"]
         if t < cabi.PRIM_UNION:
             return

@@ -88,9 +88,13 @@ class CudaAccelerator(Accelerator):
             return None
         prim = self._primitives[i]
         g = r.geometry[0]
+        # (an EncapsulatedPrimitive -- a lens -- re-labels the Intersection of the primitive it hides: the matrices it carries
+        # are that primitive's, utility.pyx:74-86)
+        from .flatten import _encapsulated
+        frame = _encapsulated(prim) or prim
         return Intersection(ray, float(r.distance[0]), prim, Point3D(g[0], g[1], g[2]), Point3D(g[3], g[4], g[5]),
                             Point3D(g[6], g[7], g[8]), Normal3D(g[9], g[10], g[11]), bool(r.exiting[0]),
-                            prim.to_local(), prim.to_root())
+                            frame.to_local(), frame.to_root())
 
     def contains(self, point):
         if self._accel is None:
