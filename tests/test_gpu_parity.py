@@ -422,6 +422,47 @@ def test_torus_on_device_against_live_reference(device, reference):
                                                                  rtol=1e-6, max_divergent_fraction=0.06))
 
 
+def test_lens_library_on_device_against_live_reference(device, reference):
+    """Lenses (EncapsulatedPrimitive around CSG trees) on the B200: hits bit-exact against the reference's KDTree (only
+    + - * / sqrt involved), a frame through the lenses within 1e-6 with no divergent pixel."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.primitive.lens.spherical import BiConvex, Meniscus
+    from source_b200.plugin import CudaAccelerator, CudaRenderEngine
+
+    def scene():
+        world = api.World()
+        glass = api.schott("N-BK7")
+        BiConvex(0.8, 0.25, 1.2, 1.5, parent=world, transform=api.translate(-0.5, 0.0, 0.0) * api.rotate(10, 5, 0), material=glass)
+        Meniscus(0.7, 0.12, 0.9, 1.4, parent=world, transform=api.translate(0.5, 0.1, 0.2) * api.rotate(-8, 12, 3), material=glass)
+        api.Box(api.Point3D(-2, -2, 2.0), api.Point3D(2, 2, 2.1), parent=world,
+                material=api.UniformSurfaceEmitter(api.InterpolatedSF([300, 550, 800], [0.3, 1.0, 0.5])))
+        return world
+    rng = np.random.default_rng(8)
+    n = 3000
+    o = np.c_[rng.uniform(-1.2, 1.2, (n, 2)), rng.uniform(-2.0, -1.0, n)]
+    d = np.c_[rng.normal(scale=0.25, size=(n, 2)), np.ones(n)]
+    world = scene()
+    ref = reference.oracle_hit(world, o, d)
+    acc = CudaAccelerator(device=device)
+    world.accelerator = acc
+    world.build_accelerator(force=True)
+    assert (ref["primitive"] == 0).sum() > 100 and (ref["primitive"] == 1).sum() > 100
+    parity.check_hits(acc.hit_batch(o, d, geometry=True), ref)
+    kw = dict(pixels=(20, 16), samples=3, bins=8, spectral_rays=2)
+    cam, pipe = scenes.cornell_camera(api, scene(), **kw)
+    cam.transform = api.translate(0, 0, -2.5)
+    m_ref, v_ref, n_ref = reference.oracle_render(cam, pipe, 606)
+    cam2, pipe2 = scenes.cornell_camera(api, scene(), **kw)
+    cam2.transform = api.translate(0, 0, -2.5)
+    cam2.render_engine = CudaRenderEngine(seed=606, rng="mt", device=device)
+    cam2.observe()
+
+    class F:  # noqa: E701
+        mean, variance, samples = np.array(pipe2.frame.mean), np.array(pipe2.frame.variance), np.array(pipe2.frame.samples)
+    parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
+
+
 def test_ccd_array_on_device_against_live_reference(device, reference):
     """CCDArray (a bare sensor inside the Cornell box) with its default RGB pipeline and a spectral one through
     CudaRenderEngine on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""
