@@ -498,9 +498,11 @@ def run_c5(cx, args):
                 hits.zero_()
                 cx.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                gc.disable()                                    # (no collector pass between the call's return and e1.record())
                 e0.record()
                 sweep(lo, hi - lo, order)
                 e1.record()
+                gc.enable()
                 cx.barrier()
                 times.append(cx.reduce(e0.elapsed_time(e1), "max"))
             ms = min(times)
