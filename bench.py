@@ -491,10 +491,10 @@ def run_c5(cx, args):
             sweep(lo, min(hi - lo, 10**7), order)               # untimed: the first pass in a new mode pays one-off set-up
             # a 1e7-ray sweep is 5 ms of device time inside a call that also talks to the driver (memory query, a dozen launches):
             # host-side stalls of 1-70 ms land in some of them (seen after the plugin / 1 M-triangle workloads had run in the same
-            # process; they only ever ADD time).  It is timed three times and the BEST reported, all three kept in `ms_all`; the
+            # process; they only ever ADD time).  It is timed seven times and the BEST reported, all seven kept in `ms_all`; the
             # 1e9-ray sweep is timed once
             times = []
-            for _ in range(3 if n <= 10**8 else 1):
+            for _ in range(7 if n <= 10**8 else 1):
                 hits.zero_()
                 cx.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
