@@ -564,6 +564,9 @@ long long rq_pass_size(Context* c, DeviceScene* ds, long long n) {
     if (c->rq_chunk > 0) return std::min<long long>(n, c->rq_chunk);
     long long pass = std::min<long long>(n, ds->has_mesh ? (16LL << 20) : (64LL << 20));
     RqHost probe;
+    // (buffers that already hold this pass need no look at the device's free memory: cudaMemGetInfo is a driver round trip
+    // that would otherwise sit inside every call)
+    if (rq_carve(nullptr, (size_t)pass, ds->has_mesh, &probe, c->query_reorder) <= c->rq_bytes) return pass;
     const size_t per_query = rq_carve(nullptr, (size_t)1 << 20, ds->has_mesh, &probe, c->query_reorder) >> 20;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return std::min<long long>(pass, 4LL << 20); }
