@@ -489,10 +489,9 @@ def run_c5(cx, args):
             lo = n * cx.rank // cx.world_size
             hi = n * (cx.rank + 1) // cx.world_size
             sweep(lo, min(hi - lo, 10**7), order)               # untimed: the first pass in a new mode pays one-off set-up
-            # a 1e7-ray sweep is 5 ms of device time inside a call that also talks to the driver (memory query, a dozen launches):
-            # host-side stalls of 1-70 ms land in some of them (seen after the plugin / 1 M-triangle workloads had run in the same
-            # process; they only ever ADD time).  It is timed seven times and the BEST reported, all seven kept in `ms_all`; the
-            # 1e9-ray sweep is timed once
+            # a 1e7-ray sweep is 5 ms of device time: it is timed seven times and the BEST reported, all seven kept in `ms_all`
+            # (a driver round trip inside the call once put 10-90 ms stalls into some of them: profiles/README.md, round 2, item
+            # 11); the 1e9-ray sweep is timed once
             times = []
             for _ in range(7 if n <= 10**8 else 1):
                 hits.zero_()
@@ -616,8 +615,7 @@ def run_ours(args):
     # ---- the other configurations of the metric --------------------------------------------------------
     configs = {}
     which = [] if args.configs == "none" else args.configs.split(",")
-    # (C5 first: its 1e7-ray sweeps are 5 ms of device time each, and measured right after the 1 M-triangle workload in the same
-    # process they came out 2-7x slow, erratically -- never in a process that had not run C4 -- while the 1e9-ray sweeps did not move)
+    # (C5 first: the shortest timed regions of the line, measured before the multi-GB workloads churn the allocator)
     for key, fn in (("C5", run_c5), ("C4", run_c4), ("C3", run_c3)):
         if key not in which or (key == "C3" and cx.world_size > 1):
             continue
