@@ -124,6 +124,11 @@ typedef struct RsbSceneDesc {
  * draws (point_square) interpolate the direction between the four diagonal neighbours' with Vector3D.slerp; an edge pixel
  * traces its own direction and draws nothing.  Projection weight 1. */
 #define RSB_CAMERA_VECTOR 3
+/* Pixel (raysect/optical/observer/nonimaging/pixel.pyx:60-173), a 0-D observer: the (nx, ny) "frame" holds one entry per TASK
+ * of the observer (Observer0D._generate_tasks, base/observer.pyx:634-649: pixel_samples split into tasks of samples_per_task =
+ * pixel_samples of this descriptor); every task samples the same rectangle at the observer's origin -- image_delta = x_width,
+ * image_start_x = y_width -- with cosine-weighted directions, weight 0.5; sensitivity = solid angle x collection area. */
+#define RSB_CAMERA_PIXEL 4
 typedef struct RsbCamera {
     int32_t nx, ny;
     int32_t pixel_samples;

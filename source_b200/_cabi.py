@@ -20,7 +20,7 @@ PRIM_SPHERE, PRIM_BOX, PRIM_CYLINDER, PRIM_CONE, PRIM_MESH, PRIM_UNION, PRIM_INT
 PRIM_PARABOLA = -1   # analytic primitives are the types <= PRIM_CONE (include/raysect_b200.h)
 PRIM_TORUS = -2
 MAT_ABSORBER, MAT_EMITTER, MAT_LAMBERT, MAT_DIELECTRIC, MAT_CONDUCTOR, MAT_VOLUME_EMITTER, MAT_ROUGH_CONDUCTOR = range(7)
-CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD, CAMERA_VECTOR = 0, 1, 2, 3
+CAMERA_PINHOLE, CAMERA_ORTHOGRAPHIC, CAMERA_CCD, CAMERA_VECTOR, CAMERA_PIXEL = 0, 1, 2, 3, 4
 PROJ_XYZ, PROJ_POWER, PROJ_RADIANCE, PROJ_MAX = 0, 1, 2, 8
 RNG_MT19937_64, RNG_PHILOX = 0, 1
 

@@ -1110,7 +1110,7 @@ static int render_slices_impl(uint64_t ctx, uint64_t scene, void* cuda_stream, c
     if (camera->kind == RSB_CAMERA_VECTOR && (!camera->pixel_origins || !camera->pixel_directions))
         return fail(RSB_ERR_ARG, "rsb_render: a vector camera needs pixel_origins and pixel_directions");
     if (camera->kind != RSB_CAMERA_PINHOLE && camera->kind != RSB_CAMERA_ORTHOGRAPHIC && camera->kind != RSB_CAMERA_CCD &&
-        camera->kind != RSB_CAMERA_VECTOR)
+        camera->kind != RSB_CAMERA_VECTOR && camera->kind != RSB_CAMERA_PIXEL)
         return fail(RSB_ERR_UNSUPPORTED, "rsb_render: unknown camera kind");
     if (config->bins < 1) return fail(RSB_ERR_ARG, "Number of bins cannot be less than 1.");
     if (config->bins != spectral->bins) return fail(RSB_ERR_ARG, "rsb_render: ray bins and spectral table bins differ");

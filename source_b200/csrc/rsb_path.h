@@ -39,7 +39,7 @@ struct Spectral {    // per spectral slice: what SpectralFunction.sample()/avera
     int32_t n_tables;
 };
 
-struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1) | CCDArray (kind 2) | VectorCamera (kind 3)
+struct Camera {      // PinholeCamera, raysect/optical/observer/imaging/pinhole.pyx:148-207 | OrthographicCamera (kind 1) | CCDArray (kind 2) | VectorCamera (kind 3) | Pixel (kind 4)
     int32_t nx, ny;
     int32_t pixel_samples;
     int32_t kind;
@@ -614,7 +614,7 @@ RSB_HD void stats_combine(double mx, double vx, int nx, double my, double vy, in
 // direction + projection weight, then _render_pixel's camera->world transform (observer.pyx:400-403).
 // uniform() draws a camera takes per pixel task BEFORE any ray is traced, per sample: 2 (the point on the pixel), or 4 for the
 // CCD, which draws all its pixel points first and all its directions after them (ccd.pyx:130-131)
-RSB_HD int camera_jitter_pairs(int kind) { return kind == 2 ? 2 : 1; }
+RSB_HD int camera_jitter_pairs(int kind) { return (kind == 2 || kind == 4) ? 2 : 1; }
 
 // VectorCamera._generate_rays (imaging/vector.pyx:124-125): only pixels off the edge of the image are sub-sampled -- an edge
 // pixel's task draws NOTHING before its rays are traced
@@ -686,6 +686,17 @@ RSB_HD void pinhole_ray(const Camera& cam, int px, int py, double u1, double u2,
         *weight = 1.0;
         *o = xform_point(cam.to_root, origin);
         *d = xform_vector(cam.to_root, v3(0.0, 0.0, 1.0));
+        return;
+    }
+    if (cam.kind == 4) {
+        // Pixel._generate_rays (nonimaging/pixel.pyx:152-170), a 0-D observer: every "pixel" of the frame is one TASK of the
+        // same x_width x y_width rectangle at the observer's origin (image_delta = x_width, image_start_x = y_width).  A
+        // RectangleSampler3D point (first draw -> y, second -> x, as above) and a cosine-weighted direction; weight 0.5
+        const double w = cam.image_delta, h = cam.image_start_x;
+        V3 origin = v3(u2 * w - 0.5 * w, u1 * h - 0.5 * h, 0.0);
+        *weight = 0.5;
+        *o = xform_point(cam.to_root, origin);
+        *d = xform_vector(cam.to_root, hemisphere_cosine_from(u3, u4));
         return;
     }
     if (cam.kind == 2) {

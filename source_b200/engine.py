@@ -421,12 +421,27 @@ class DeviceGroup:
         return self.members[0].pin(*arrays)
 
 
-def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None, ccd=False, vector=None):
+def camera_desc(nx, ny, pixel_samples, fov, sensitivity, to_root, width=None, ccd=False, vector=None, pixel=None):
     """PinholeCamera._update_image_geometry (raysect/optical/observer/imaging/pinhole.pyx:148-160), or, with
     ``width`` (and ``fov`` None), OrthographicCamera._update_image_geometry (imaging/orthographic.pyx:132-137) /
     with ``ccd`` CCDArray._update_image_geometry (imaging/ccd.pyx:106-112; ``sensitivity`` = pixel area x 2 pi,
     ccd.pyx:150-151)"""
     cam = cabi.RsbCamera()
+    if pixel is not None:
+        # Pixel, a 0-D observer (nonimaging/pixel.pyx): ``pixel`` = (x_width, y_width); (nx, ny) = (number of tasks, 1)
+        x_width, y_width = float(pixel[0]), float(pixel[1])
+        if x_width <= 0 or y_width <= 0:
+            raise RuntimeError("Pixel widths must be greater than zero.")
+        cam.kind = cabi.CAMERA_PIXEL
+        cam.nx, cam.ny, cam.pixel_samples = int(nx), int(ny), int(pixel_samples)
+        cam.image_delta, cam.image_start_x, cam.image_start_y = x_width, y_width, 0.0
+        cam.sensitivity = float(sensitivity)
+        for k, v in enumerate(float(to_root[i, j]) for i in range(3) for j in range(4)):
+            cam.to_root[k] = v
+        if [float(to_root[3, j]) for j in range(3)] != [0.0, 0.0, 0.0]:
+            raise NotImplementedError("the observer's transform is not affine")
+        cam.to_root_w = float(to_root[3, 3])
+        return cam
     if vector is not None:
         # VectorCamera (imaging/vector.pyx:44-156): ``vector`` = (pixel_origins, pixel_directions), (nx, ny, 3) float64 each
         origins = np.ascontiguousarray(vector[0], dtype=np.float64)

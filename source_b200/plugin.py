@@ -229,6 +229,78 @@ class CudaRenderEngine(RenderEngine):
         for th in threads:
             th.join()
 
+    def _run_pixel(self, observer, tasks, update, render_args, update_args, update_kwargs):
+        """``Pixel`` (optical/observer/nonimaging/pixel.pyx), a 0-D observer: its tasks are (samples,) tuples
+        (Observer0D._generate_tasks, base/observer.pyx:634-649) all sampling the same rectangle.  The device renders them as the
+        pixels of an (n_tasks, 1) frame -- task k of slice s draws from the stream seeded ``seed + s*n_tasks + k`` -- and every
+        task's packed result goes through the observer's own ``update`` (0-D pipelines merge task by task, spectral/power.pyx:
+        137-150, mono/power.pyx:125-133): spectral pipelines get (mean[bins], variance[bins]), the mono ones the statistics of
+        their filtered total (a projection channel of the accumulate kernel)."""
+        from raysect.optical.observer import PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D, SpectralRadiancePipeline0D
+        slice_id, template = render_args[0], render_args[1]
+        pipelines = list(observer.pipelines)
+        for p in pipelines:
+            if not isinstance(p, (SpectralPowerPipeline0D, SpectralRadiancePipeline0D, PowerPipeline0D, RadiancePipeline0D)):
+                raise NotImplementedError("CudaRenderEngine feeds the 0D pipelines SpectralPower, SpectralRadiance, Power, Radiance; "
+                                          "got %r (no CPU fallback)" % type(p).__name__)
+        if self.passes != 1:
+            raise ValueError("a 0-D observer splits its samples into tasks itself (samples_per_task): use passes=1")
+        counts = {int(t[0]) for t in tasks}
+        if len(counts) != 1:
+            raise NotImplementedError("Pixel with pixel_samples (%d) not a multiple of samples_per_task (%d): the device renders "
+                                      "tasks of equal size" % (observer.pixel_samples, observer.samples_per_task))
+        spp, n_tasks = counts.pop(), len(tasks)
+        accel = self._accelerator_for(observer.root, slice_id)
+        if isinstance(accel, list) or not hasattr(accel, "read_slice"):
+            raise NotImplementedError("0-D observers render on one device")
+        n_slices = len(slice_offsets(observer.spectral_bins, observer.spectral_rays))
+        cfg = ray_config(template.bins, template.min_wavelength, template.max_wavelength, template.extinction_prob,
+                         template.extinction_min_depth, template.max_depth, template.importance_sampling,
+                         template.important_path_weight, template.max_distance)
+        spectral = accel.flat.spectral(template.min_wavelength, template.max_wavelength, template.bins)
+        delta = (template.max_wavelength - template.min_wavelength) / template.bins
+        pixel_sensitivity = float(observer._pixel_sensitivity())
+
+        def is_mono(p):
+            return isinstance(p, PowerPipeline0D)                  # (RadiancePipeline0D subclasses it, mono/radiance.pyx:40)
+
+        def sens_of(p):
+            radiance = isinstance(p, (SpectralRadiancePipeline0D, RadiancePipeline0D))
+            if isinstance(p, RadiancePipeline0D):       # its processor ignores the sensitivity: rides with whichever render there is
+                return pixel_sensitivity if any(not isinstance(q, (SpectralRadiancePipeline0D, RadiancePipeline0D)) for q in pipelines) else 1.0
+            return 1.0 if radiance else pixel_sensitivity
+        packed, rays = {}, 0
+        for sensitivity in dict.fromkeys(sens_of(p) for p in pipelines):
+            group = [p for p in pipelines if sens_of(p) == sensitivity]
+            cam = camera_desc(n_tasks, 1, spp, None, sensitivity, observer.to_root(), pixel=(observer.x_width, observer.y_width))
+            mono = [p for p in group if is_mono(p)]
+            xyz = None
+            if mono:
+                curves = np.stack([np.asarray(p.filter.sample(template.min_wavelength, template.max_wavelength, template.bins)) for p in mono],
+                                  axis=1)[None]
+                modes = [cabi.PROJ_RADIANCE if isinstance(p, RadiancePipeline0D) else cabi.PROJ_POWER for p in mono]
+                xyz = (curves, np.array([delta]), modes)
+            keep = any(not is_mono(p) for p in group)
+            kw = dict(xyz=xyz, keep_spectral=keep) if xyz is not None else {}
+            rays = accel.render_slices(cam, cfg, [spectral], self.rng_mode, self.seed + slice_id * n_tasks, None, passes=1,
+                                       seed_stride=n_tasks, **kw)
+            if keep:
+                mean, variance = accel.read_slice()                # (n_tasks, 1, bins)
+                for p in group:
+                    if not is_mono(p):
+                        packed[id(p)] = [(np.ascontiguousarray(mean[k, 0]), np.ascontiguousarray(variance[k, 0])) for k in range(n_tasks)]
+            for ch, p in enumerate(mono):
+                # the per-task statistics of the channel: "merged" into an empty (n_tasks, 1) frame they come back as they are
+                m, v, s = np.zeros((n_tasks, 1)), np.zeros((n_tasks, 1)), np.zeros((n_tasks, 1), dtype=np.int32)
+                accel.update_proj_frame(ch, m, v, s, frame_is_empty=True)
+                packed[id(p)] = [(float(m[k, 0]), float(v[k, 0])) for k in range(n_tasks)]
+        self.ray_count += rays
+        if slice_id == n_slices - 1:
+            self.seed += n_slices * n_tasks
+        share, extra = divmod(rays, n_tasks)
+        for k, task in enumerate(tasks):
+            update((task, [packed[id(p)][k] for p in pipelines], share + (extra if k == 0 else 0)), *update_args, **update_kwargs)
+
     def _vector_pixels(self, observer):
         """(nx, ny, 3) float64 arrays of a VectorCamera's per-pixel Point3D / Vector3D objects (imaging/vector.pyx:84-86; the
         object arrays are read-only attributes, so the conversion is done once per array pair)"""
@@ -287,6 +359,9 @@ class CudaRenderEngine(RenderEngine):
                                               RadiancePipeline2D, RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D,
                                               VectorCamera)
         observer = getattr(render, "__self__", None)
+        from raysect.optical.observer import Pixel
+        if isinstance(observer, Pixel):
+            return self._run_pixel(observer, tasks, update, render_args, update_args, update_kwargs)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray, VectorCamera)):
             raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera, CCDArray and VectorCamera observers; "
                                       "got %r (no CPU fallback)" % type(observer).__name__)

@@ -463,6 +463,48 @@ def test_lens_library_on_device_against_live_reference(device, reference):
     parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
 
 
+def test_pixel_observer_on_device_against_live_reference(device, reference):
+    """Pixel, a 0-D observer (tasks as the pixels of an (n_tasks, 1) frame) with a spectral and two mono 0-D pipelines on the
+    B200 vs the reference driven by an engine that re-seeds per (slice, task): accumulated statistics within 1e-6 relative."""
+    import scenes
+    api = reference.ref_api()
+    from raysect.core.math.random import seed as reseed
+    from raysect.core.workflow import RenderEngine
+    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D
+    from source_b200.plugin import CudaRenderEngine
+    filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+
+    def observer(world):
+        pipes = [SpectralPowerPipeline0D(display_progress=False), PowerPipeline0D(filter=filt), RadiancePipeline0D()]
+        px = Pixel(pipes, x_width=0.3, y_width=0.2, parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2),
+                   pixel_samples=60, samples_per_task=10, spectral_bins=12, spectral_rays=2, quiet=True)
+        px.ray_extinction_min_depth = 2
+        px.ray_extinction_prob = 0.1
+        return px, pipes
+
+    class Reseeding(RenderEngine):
+        def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
+            slice_id = render_args[0]
+            for k, task in enumerate(tasks):
+                reseed(5150 + slice_id * len(tasks) + k)
+                update(render(task, *render_args, **render_kwargs), *update_args, **update_kwargs)
+
+        def worker_count(self):
+            return 1
+    px, pipes = observer(scenes.cornell_box(api))
+    px.render_engine = Reseeding()
+    px.observe()
+    px2, pipes2 = observer(scenes.cornell_box(api))
+    px2.render_engine = CudaRenderEngine(seed=5150, rng="mt", device=device)
+    px2.observe()
+    np.testing.assert_array_equal(np.array(pipes2[0].samples.samples), np.array(pipes[0].samples.samples))
+    np.testing.assert_allclose(np.array(pipes2[0].samples.mean), np.array(pipes[0].samples.mean), rtol=1e-6)
+    np.testing.assert_allclose(np.array(pipes2[0].samples.variance), np.array(pipes[0].samples.variance), rtol=1e-6)
+    for a, b in zip(pipes2[1:], pipes[1:]):
+        assert a.value.samples == b.value.samples == 60 and b.value.mean > 0
+        assert abs(a.value.mean - b.value.mean) <= 1e-6 * b.value.mean and abs(a.value.variance - b.value.variance) <= 1e-6 * b.value.variance
+
+
 def test_ccd_array_on_device_against_live_reference(device, reference):
     """CCDArray (a bare sensor inside the Cornell box) with its default RGB pipeline and a spectral one through
     CudaRenderEngine on the B200 vs the reference's serial render: 1e-6 relative, no divergent pixel."""

@@ -777,6 +777,49 @@ def test_lens_library_matches_reference(api, reference):
     assert (m_ref.sum(axis=2) > 0).sum() > 60
 
 
+def test_pixel_observer_matches_serial_reference(api, reference):
+    """Pixel (nonimaging/pixel.pyx), a 0-D observer, with a spectral and two mono 0-D pipelines: four tasks of 5 samples, two
+    spectral slices.  The reference is driven by an engine that re-seeds before every task with the seed the device's stream
+    for that (slice, task) uses; every pipeline's accumulated statistics must come out bit for bit."""
+    from raysect.core.math.random import seed as reseed
+    from raysect.core.workflow import RenderEngine
+    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D
+    from source_b200.plugin import CudaRenderEngine
+    filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+
+    def observer(world):
+        pipes = [SpectralPowerPipeline0D(display_progress=False), PowerPipeline0D(filter=filt), RadiancePipeline0D()]
+        px = Pixel(pipes, x_width=0.3, y_width=0.2, parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2),
+                   pixel_samples=20, samples_per_task=5, spectral_bins=8, spectral_rays=2, quiet=True)
+        px.ray_extinction_min_depth = 2
+        px.ray_extinction_prob = 0.1
+        return px, pipes
+
+    class Reseeding(RenderEngine):
+        def run(self, tasks, render, update, render_args=(), render_kwargs={}, update_args=(), update_kwargs={}):
+            slice_id = render_args[0]
+            for k, task in enumerate(tasks):
+                reseed(5150 + slice_id * len(tasks) + k)
+                update(render(task, *render_args, **render_kwargs), *update_args, **update_kwargs)
+
+        def worker_count(self):
+            return 1
+    px, pipes = observer(scenes.cornell_box(api))
+    px.render_engine = Reseeding()
+    px.observe()
+    px2, pipes2 = observer(scenes.cornell_box(api))
+    px2.render_engine = CudaRenderEngine(seed=5150, rng="mt", backend=hostsim_api.HostScene)
+    px2.observe()
+    for name in ("mean", "variance", "samples"):
+        np.testing.assert_array_equal(np.array(getattr(pipes2[0].samples, name)), np.array(getattr(pipes[0].samples, name)))
+    for a, b in zip(pipes2[1:], pipes[1:]):
+        assert (a.value.mean, a.value.variance, a.value.samples) == (b.value.mean, b.value.variance, b.value.samples)
+    assert pipes[1].value.mean > 0 and pipes[2].value.mean > 0 and pipes[1].value.samples == 20
+    px2.pixel_samples = 18
+    with pytest.raises(NotImplementedError):
+        px2.observe()
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import Pipeline2D
     from source_b200.plugin import CudaRenderEngine
