@@ -230,13 +230,16 @@ class CudaRenderEngine(RenderEngine):
             th.join()
 
     def _run_pixel(self, observer, tasks, update, render_args, update_args, update_kwargs):
-        """``Pixel`` (optical/observer/nonimaging/pixel.pyx), a 0-D observer: its tasks are (samples,) tuples
+        """``Pixel`` (optical/observer/nonimaging/pixel.pyx) and ``SightLine`` (nonimaging/sightline.pyx: every ray leaves the
+        origin along +z with weight 1 and nothing is drawn -- the edge pixel of a VectorCamera whose arrays say (0, 0, 0) and
+        (0, 0, 1)), 0-D observers: their tasks are (samples,) tuples
         (Observer0D._generate_tasks, base/observer.pyx:634-649) all sampling the same rectangle.  The device renders them as the
         pixels of an (n_tasks, 1) frame -- task k of slice s draws from the stream seeded ``seed + s*n_tasks + k`` -- and every
         task's packed result goes through the observer's own ``update`` (0-D pipelines merge task by task, spectral/power.pyx:
         137-150, mono/power.pyx:125-133): spectral pipelines get (mean[bins], variance[bins]), the mono ones the statistics of
         their filtered total (a projection channel of the accumulate kernel)."""
-        from raysect.optical.observer import PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D, SpectralRadiancePipeline0D
+        from raysect.optical.observer import (PowerPipeline0D, RadiancePipeline0D, SightLine, SpectralPowerPipeline0D,
+                                              SpectralRadiancePipeline0D)
         slice_id, template = render_args[0], render_args[1]
         pipelines = list(observer.pipelines)
         for p in pipelines:
@@ -247,8 +250,8 @@ class CudaRenderEngine(RenderEngine):
             raise ValueError("a 0-D observer splits its samples into tasks itself (samples_per_task): use passes=1")
         counts = {int(t[0]) for t in tasks}
         if len(counts) != 1:
-            raise NotImplementedError("Pixel with pixel_samples (%d) not a multiple of samples_per_task (%d): the device renders "
-                                      "tasks of equal size" % (observer.pixel_samples, observer.samples_per_task))
+            raise NotImplementedError("%s with pixel_samples (%d) not a multiple of samples_per_task (%d): the device renders "
+                                      "tasks of equal size" % (type(observer).__name__, observer.pixel_samples, observer.samples_per_task))
         spp, n_tasks = counts.pop(), len(tasks)
         accel = self._accelerator_for(observer.root, slice_id)
         if isinstance(accel, list) or not hasattr(accel, "read_slice"):
@@ -272,7 +275,12 @@ class CudaRenderEngine(RenderEngine):
         packed, rays = {}, 0
         for sensitivity in dict.fromkeys(sens_of(p) for p in pipelines):
             group = [p for p in pipelines if sens_of(p) == sensitivity]
-            cam = camera_desc(n_tasks, 1, spp, None, sensitivity, observer.to_root(), pixel=(observer.x_width, observer.y_width))
+            if isinstance(observer, SightLine):
+                directions = np.zeros((n_tasks, 1, 3))
+                directions[:, :, 2] = 1.0
+                cam = camera_desc(n_tasks, 1, spp, None, sensitivity, observer.to_root(), vector=(np.zeros((n_tasks, 1, 3)), directions))
+            else:
+                cam = camera_desc(n_tasks, 1, spp, None, sensitivity, observer.to_root(), pixel=(observer.x_width, observer.y_width))
             mono = [p for p in group if is_mono(p)]
             xyz = None
             if mono:
@@ -359,8 +367,8 @@ class CudaRenderEngine(RenderEngine):
                                               RadiancePipeline2D, RGBPipeline2D, SpectralPowerPipeline2D, SpectralRadiancePipeline2D,
                                               VectorCamera)
         observer = getattr(render, "__self__", None)
-        from raysect.optical.observer import Pixel
-        if isinstance(observer, Pixel):
+        from raysect.optical.observer import Pixel, SightLine
+        if isinstance(observer, (Pixel, SightLine)):
             return self._run_pixel(observer, tasks, update, render_args, update_args, update_kwargs)
         if not isinstance(observer, (PinholeCamera, OrthographicCamera, CCDArray, VectorCamera)):
             raise NotImplementedError("CudaRenderEngine renders PinholeCamera, OrthographicCamera, CCDArray and VectorCamera observers; "

@@ -463,21 +463,23 @@ def test_lens_library_on_device_against_live_reference(device, reference):
     parity.compare_frame(F, dict(mean=m_ref, variance=v_ref, samples=n_ref), exact=False, rtol=1e-6, max_divergent_fraction=0.0)
 
 
-def test_pixel_observer_on_device_against_live_reference(device, reference):
+@pytest.mark.parametrize("kind", ["pixel", "sightline"])
+def test_pixel_observer_on_device_against_live_reference(device, reference, kind):
     """Pixel, a 0-D observer (tasks as the pixels of an (n_tasks, 1) frame) with a spectral and two mono 0-D pipelines on the
     B200 vs the reference driven by an engine that re-seeds per (slice, task): accumulated statistics within 1e-6 relative."""
     import scenes
     api = reference.ref_api()
     from raysect.core.math.random import seed as reseed
     from raysect.core.workflow import RenderEngine
-    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D
+    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SightLine, SpectralPowerPipeline0D
     from source_b200.plugin import CudaRenderEngine
     filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
 
     def observer(world):
         pipes = [SpectralPowerPipeline0D(display_progress=False), PowerPipeline0D(filter=filt), RadiancePipeline0D()]
-        px = Pixel(pipes, x_width=0.3, y_width=0.2, parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2),
-                   pixel_samples=60, samples_per_task=10, spectral_bins=12, spectral_rays=2, quiet=True)
+        kw = dict(parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2), pixel_samples=60, samples_per_task=10,
+                  spectral_bins=12, spectral_rays=2, quiet=True)
+        px = Pixel(pipes, x_width=0.3, y_width=0.2, **kw) if kind == "pixel" else SightLine(pipelines=pipes, sensitivity=2.5, **kw)
         px.ray_extinction_min_depth = 2
         px.ray_extinction_prob = 0.1
         return px, pipes

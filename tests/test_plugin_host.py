@@ -777,20 +777,23 @@ def test_lens_library_matches_reference(api, reference):
     assert (m_ref.sum(axis=2) > 0).sum() > 60
 
 
-def test_pixel_observer_matches_serial_reference(api, reference):
+@pytest.mark.parametrize("kind", ["pixel", "sightline"])
+def test_pixel_observer_matches_serial_reference(api, reference, kind):
     """Pixel (nonimaging/pixel.pyx), a 0-D observer, with a spectral and two mono 0-D pipelines: four tasks of 5 samples, two
     spectral slices.  The reference is driven by an engine that re-seeds before every task with the seed the device's stream
     for that (slice, task) uses; every pipeline's accumulated statistics must come out bit for bit."""
     from raysect.core.math.random import seed as reseed
     from raysect.core.workflow import RenderEngine
-    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SpectralPowerPipeline0D
+    from raysect.optical.observer import Pixel, PowerPipeline0D, RadiancePipeline0D, SightLine, SpectralPowerPipeline0D
     from source_b200.plugin import CudaRenderEngine
     filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
 
     def observer(world):
         pipes = [SpectralPowerPipeline0D(display_progress=False), PowerPipeline0D(filter=filt), RadiancePipeline0D()]
-        px = Pixel(pipes, x_width=0.3, y_width=0.2, parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2),
-                   pixel_samples=20, samples_per_task=5, spectral_bins=8, spectral_rays=2, quiet=True)
+        kw = dict(parent=world, transform=api.translate(0.1, -0.1, -0.9) * api.rotate(6, -4, 2), pixel_samples=20, samples_per_task=5,
+                  spectral_bins=8, spectral_rays=2, quiet=True)
+        # (SightLine: a single line of sight, nonimaging/sightline.pyx -- the same 0-D machinery, no draws before the trace)
+        px = Pixel(pipes, x_width=0.3, y_width=0.2, **kw) if kind == "pixel" else SightLine(pipelines=pipes, sensitivity=2.5, **kw)
         px.ray_extinction_min_depth = 2
         px.ray_extinction_prob = 0.1
         return px, pipes
