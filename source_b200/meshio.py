@@ -1,4 +1,4 @@
-"""Mesh file importers with the reference's call signatures (raysect/primitive/mesh/obj.py, stl.py).
+"""Mesh file importers with the reference's call signatures (raysect/primitive/mesh/obj.py, stl.py, ply.py).
 
 ``import_obj(filename, scaling=1.0, **mesh_kwargs)`` and ``import_stl(filename, scaling=1.0, mode=..., **mesh_kwargs)``
 return a ``source_b200.Mesh``; its kd-tree is built by this package's bit-exact SAH builder and the triangles go to
@@ -112,3 +112,86 @@ def _load_stl_binary(filename, scaling):
     vertices = (scaling * rec.astype(np.float64)).reshape(-1, 3)
     triangles = np.arange(3 * count, dtype=np.int32).reshape(count, 3)
     return vertices, triangles
+
+
+PLY_AUTOMATIC, PLY_ASCII, PLY_BINARY = "auto", "ascii", "binary"
+_PLY_SCALARS = {"char": "b", "int8": "b", "uchar": "B", "uint8": "B", "short": "h", "int16": "h", "ushort": "H", "uint16": "H",
+                "int": "i", "int32": "i", "uint": "I", "uint32": "I", "float": "f", "float32": "f", "double": "d", "float64": "d"}
+
+
+def import_ply(filename, scaling=1.0, mode=PLY_AUTOMATIC, **kwargs):
+    """PLYHandler.import_ply (raysect/primitive/mesh/ply.py:47-200): vertices scaled by ``scaling`` in double precision,
+    triangles as written, smoothing off.  ``mode`` is kept for the signature; the header says which format the file has.
+    Reads what the reference reads and writes -- ascii and binary little-endian, float x / y / z, faces as
+    ``list uchar int vertex_index(es)`` -- and, unlike it, any other scalar properties on the vertices (skipped), uint / int
+    index types and big-endian files.  Faces that are not triangles are refused, as in the reference."""
+    mode = mode.lower()
+    if mode not in (PLY_AUTOMATIC, PLY_ASCII, PLY_BINARY):
+        raise ValueError("Unrecognised import mode, valid values are: {}".format((PLY_AUTOMATIC, PLY_ASCII, PLY_BINARY)))
+    with open(filename, "rb") as f:
+        blob = f.read()
+    end = blob.find(b"end_header")
+    if not blob.startswith(b"ply") or end < 0:
+        raise ValueError("This file is not a valid PLY file.")
+    body = blob[blob.index(b"\n", end) + 1:]
+    fmt, elements = None, []
+    for raw in blob[:end].decode("ascii", "replace").splitlines()[1:]:
+        words = raw.split()
+        if not words or words[0] in ("comment", "obj_info"):
+            continue
+        if words[0] == "format":
+            fmt = words[1]
+        elif words[0] == "element":
+            elements.append((words[1], int(words[2]), []))
+        elif words[0] == "property" and elements:
+            elements[-1][2].append(words[1:])
+    if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+        raise ValueError("This file is not a valid PLY file.")
+    if (mode == PLY_ASCII) != (fmt == "ascii") and mode != PLY_AUTOMATIC:
+        raise ValueError("This file is not a valid PLY file.")
+    vertices = triangles = None
+    tokens = iter(body.split()) if fmt == "ascii" else None
+    endian, at = "<" if fmt != "binary_big_endian" else ">", 0
+
+    def scalar(kind):
+        nonlocal at
+        if tokens is not None:
+            return float(next(tokens)) if kind in ("f", "d") else int(next(tokens))
+        (v,) = struct.unpack_from(endian + kind, body, at)
+        at += struct.calcsize(kind)
+        return v
+    for name, count, props in elements:
+        kinds = []
+        for p in props:
+            if p[0] == "list":
+                kinds.append(("list", _PLY_SCALARS[p[1]], _PLY_SCALARS[p[2]], p[3]))
+            else:
+                kinds.append(("scalar", _PLY_SCALARS[p[0]], None, p[1]))
+        if name == "vertex":
+            cols = {k[3]: i for i, k in enumerate(kinds)}
+            if not all(c in cols and kinds[cols[c]][0] == "scalar" for c in "xyz"):
+                raise ValueError("This file is not a valid PLY file.")
+            vertices = np.empty((count, 3))
+        elif name == "face":
+            triangles = np.empty((count, 3), dtype=np.int32)
+        for i in range(count):
+            row = []
+            for k in kinds:
+                if k[0] == "scalar":
+                    row.append(scalar(k[1]))
+                else:
+                    row.append([scalar(k[2]) for _ in range(scalar(k[1]))])
+            if name == "vertex":
+                vertices[i] = [row[cols[c]] for c in "xyz"]
+            elif name == "face":
+                corners = next((r for r, k in zip(row, kinds) if k[0] == "list" and k[3] in ("vertex_index", "vertex_indices")), None)
+                if corners is None:
+                    raise ValueError("This file is not a valid PLY file.")
+                if len(corners) != 3:
+                    raise ValueError("Raysect meshes can only handle triangles.")
+                triangles[i] = corners
+    if vertices is None or triangles is None:
+        raise ValueError("This file is not a valid PLY file.")
+    vertices *= scaling
+    kwargs.setdefault("smoothing", False)
+    return Mesh(vertices, triangles, **kwargs)

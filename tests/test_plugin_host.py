@@ -548,6 +548,59 @@ def test_mesh_importers_match_reference_importers(api, reference, tmp_path):
         assert (ref["primitive"] >= 0).sum() > 60
 
 
+def test_ply_importer_matches_reference(api, reference, tmp_path):
+    """source_b200.import_ply on the files the reference's own export_ply writes, binary little-endian and ascii.  The
+    reference's reader refuses its writer's header (`vertex_index` written, ply.py:116, `vertex_indices` expected, :115 / :175):
+    with that one word patched its binary reader gives the mirror's arrays and kd-tree stream exactly; the ascii result is held
+    to the arrays written.  Plus a big-endian file with extra vertex properties and uint indices, and a quad that must be
+    refused."""
+    import io
+    import struct
+    import source_b200 as mirror
+    from raysect.primitive import export_ply, import_ply
+    from source_b200.flatten import rsm_kdtree_stream
+    verts, tris, _ = scenes.icosphere(2, radius=0.4, bumps=0.1)
+    tris = np.ascontiguousarray(np.asarray(tris)[:, :3])
+    src = api.Mesh(verts, tris, smoothing=False, closed=True)
+    for mode in ("binary", "ascii"):
+        path = str(tmp_path / ("sphere_%s.ply" % mode))
+        export_ply(src, path, mode=mode)
+        mm = mirror.import_ply(path, scaling=1.5, parent=mirror.World(), material=mirror.AbsorbingSurface())
+        assert mm.data.triangles.shape == (len(tris), 3) and not mm.data.smoothing
+        np.testing.assert_array_equal(mm.data.triangles, np.asarray(tris, dtype=np.int32))
+        if mode == "binary":
+            patched = str(tmp_path / "sphere_binary_patched.ply")
+            with open(path, "rb") as f, open(patched, "wb") as g:
+                g.write(f.read().replace(b"int vertex_index\n", b"int vertex_indices\n", 1))
+            rm = import_ply(patched, scaling=1.5, mode="binary", parent=api.World(), material=api.AbsorbingSurface())
+            mm = mirror.import_ply(patched, scaling=1.5, parent=mirror.World(), material=mirror.AbsorbingSurface())
+            np.testing.assert_array_equal(mm.data.vertices, np.array(rm.data.vertices))
+            buf = io.BytesIO()
+            rm.data.save(buf)
+            blob = buf.getvalue()
+            assert bytes(mm.data.kdtree_stream) == blob[rsm_kdtree_stream(blob):]
+        else:
+            np.testing.assert_allclose(mm.data.vertices, (np.asarray(verts, dtype=np.float32).astype(np.float64) * 1.5).astype(np.float32),
+                                       rtol=2e-6)
+    big = tmp_path / "big_endian.ply"
+    with open(big, "wb") as f:
+        f.write(b"ply\nformat binary_big_endian 1.0\ncomment extra properties\nelement vertex 3\nproperty double x\nproperty double y\n"
+                b"property double z\nproperty uchar red\nelement face 1\nproperty list uchar uint vertex_indices\nend_header\n")
+        for v in ((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.5)):
+            f.write(struct.pack(">dddB", *v, 200))
+        f.write(struct.pack(">BIII", 3, 0, 1, 2))
+    mm = mirror.import_ply(str(big), scaling=2.0)
+    np.testing.assert_array_equal(mm.data.vertices, np.array([[0, 0, 0], [2, 0, 0], [0, 2, 1]], dtype=np.float32))
+    np.testing.assert_array_equal(mm.data.triangles, [[0, 1, 2]])
+    quad = tmp_path / "quad.ply"
+    quad.write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\nelement face 1\n"
+                    "property list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n")
+    with pytest.raises(ValueError):
+        mirror.import_ply(str(quad))
+    with pytest.raises(ValueError):
+        mirror.import_ply(str(quad), mode="nonsense")
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
