@@ -19,6 +19,6 @@ from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, Mes
                          Sphere, Subtract, Union, World)
 from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
                        SpectralPowerPipeline2D, SpectralRadiancePipeline2D, SpectralSlice, StatsArray3D)
-from .meshio import import_obj, import_ply, import_stl
+from .meshio import import_obj, import_ply, import_stl, import_vtk
 from .engine import Accelerator, Device, default_device
 from ._cabi import RNG_MT19937_64, RNG_PHILOX, RsbError

@@ -1,4 +1,4 @@
-"""Mesh file importers with the reference's call signatures (raysect/primitive/mesh/obj.py, stl.py, ply.py).
+"""Mesh file importers with the reference's call signatures (raysect/primitive/mesh/obj.py, stl.py, ply.py, vtk.py).
 
 ``import_obj(filename, scaling=1.0, **mesh_kwargs)`` and ``import_stl(filename, scaling=1.0, mode=..., **mesh_kwargs)``
 return a ``source_b200.Mesh``; its kd-tree is built by this package's bit-exact SAH builder and the triangles go to
@@ -193,5 +193,45 @@ def import_ply(filename, scaling=1.0, mode=PLY_AUTOMATIC, **kwargs):
     if vertices is None or triangles is None:
         raise ValueError("This file is not a valid PLY file.")
     vertices *= scaling
+    kwargs.setdefault("smoothing", False)
+    return Mesh(vertices, triangles, **kwargs)
+
+
+VTK_AUTOMATIC, VTK_ASCII, VTK_BINARY = "auto", "ascii", "binary"
+
+
+def import_vtk(filename, scaling=1.0, mode=VTK_AUTOMATIC, **kwargs):
+    """VTKHandler.import_vtk (raysect/primitive/mesh/vtk.py:49-140): legacy ASCII "DataFile Version 2.0" files holding an
+    UNSTRUCTURED_GRID of triangular cells (cell type 5); vertices scaled in double precision, smoothing off, the mesh named
+    after the file's title line unless ``name`` is given.  Binary .vtk files are not read (the reference does not read them
+    either)."""
+    mode = mode.lower()
+    if mode == VTK_BINARY:
+        raise NotImplementedError("The binary .vtk loading routine has not been implemented yet.")
+    if mode not in (VTK_AUTOMATIC, VTK_ASCII):
+        raise ValueError("Unrecognised import mode, valid values are: {}".format((VTK_ASCII, VTK_BINARY)))
+    with open(filename, "r") as f:
+        lines = [ln.strip() for ln in f]
+    if len(lines) < 5 or lines[0] != "# vtk DataFile Version 2.0" or lines[2] != "ASCII":
+        if mode == VTK_AUTOMATIC:
+            raise NotImplementedError("The binary .vtk loading routine has not been implemented yet.")
+        raise ValueError("This file is not a valid ASCII VTK file.")
+    if lines[3] != "DATASET UNSTRUCTURED_GRID":
+        raise RuntimeError("Unrecognised dataset encountered in vtk file.")
+    words = lines[4].split()
+    if len(words) != 3 or words[0] != "POINTS" or words[2] != "float":
+        raise RuntimeError("Unrecognised dataset encountered in vtk file.")
+    n_points = int(words[1])
+    vertices = np.array([[float(c) * scaling for c in lines[5 + i].split()[:3]] for i in range(n_points)]).reshape(n_points, 3)
+    at = 5 + n_points
+    words = lines[at].split()
+    if not words or words[0] != "CELLS":
+        raise RuntimeError("Unrecognised dataset encountered in vtk file.")
+    n_cells = int(words[1])
+    triangles = np.array([[int(c) for c in lines[at + 1 + i].split()[1:4]] for i in range(n_cells)], dtype=np.int32).reshape(n_cells, 3)
+    at += 1 + n_cells
+    if lines[at].split()[0] != "CELL_TYPES" or any(int(lines[at + 1 + i]) != 5 for i in range(n_cells)):
+        raise ValueError("Raysect meshes can only handle triangles.")
+    kwargs.setdefault("name", lines[1] or "VTKMesh")
     kwargs.setdefault("smoothing", False)
     return Mesh(vertices, triangles, **kwargs)

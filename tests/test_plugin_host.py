@@ -601,6 +601,42 @@ def test_ply_importer_matches_reference(api, reference, tmp_path):
         mirror.import_ply(str(quad), mode="nonsense")
 
 
+def test_vtk_importer_matches_reference(api, reference, tmp_path):
+    """source_b200.import_vtk against raysect.primitive.import_vtk on a legacy ASCII unstructured grid of triangles: identical
+    arrays, kd-tree stream and mesh name; binary mode and non-triangular cells are refused like the reference refuses them."""
+    import io
+    import source_b200 as mirror
+    from raysect.primitive import import_vtk
+    from source_b200.flatten import rsm_kdtree_stream
+    verts, tris, _ = scenes.icosphere(2, radius=0.4, bumps=0.1)
+    tris = np.asarray(tris)[:, :3]
+    path = tmp_path / "sphere.vtk"
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 2.0\nbumpy sphere\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS %d float\n" % len(verts))
+        for v in verts:
+            f.write("%r %r %r\n" % (float(v[0]), float(v[1]), float(v[2])))
+        f.write("CELLS %d %d\n" % (len(tris), 4 * len(tris)))
+        for tri in tris:
+            f.write("3 %d %d %d\n" % tuple(tri))
+        f.write("CELL_TYPES %d\n" % len(tris) + "5\n" * len(tris))
+    rm = import_vtk(str(path), scaling=0.8, parent=api.World(), material=api.AbsorbingSurface())
+    mm = mirror.import_vtk(str(path), scaling=0.8, parent=mirror.World(), material=mirror.AbsorbingSurface())
+    np.testing.assert_array_equal(mm.data.vertices, np.array(rm.data.vertices))
+    np.testing.assert_array_equal(mm.data.triangles, np.array(rm.data.triangles))
+    assert mm.name == rm.name == "bumpy sphere" and not mm.data.smoothing
+    buf = io.BytesIO()
+    rm.data.save(buf)
+    blob = buf.getvalue()
+    assert bytes(mm.data.kdtree_stream) == blob[rsm_kdtree_stream(blob):]
+    with pytest.raises(NotImplementedError):
+        mirror.import_vtk(str(path), mode="binary")
+    bad = tmp_path / "quad.vtk"
+    bad.write_text("# vtk DataFile Version 2.0\nq\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS 3 float\n0 0 0\n1 0 0\n0 1 0\nCELLS 1 4\n"
+                   "3 0 1 2\nCELL_TYPES 1\n9\n")
+    with pytest.raises(ValueError):
+        mirror.import_vtk(str(bad))
+
+
 def test_render_engine_with_real_orthographic_camera(api, reference):
     from source_b200.plugin import CudaRenderEngine
     world = scenes.cornell_box(api)
