@@ -325,6 +325,23 @@ def timed_frames(cx, renderer, steps, warmup, seed0):
     return total_ms, int(rays_t.item()), per_step
 
 
+def captured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of ``kernel`` from the committed `ncu --set full` capture of
+    this bench command (profiles/r2n_ncu_full_<kernel>.txt; a mid-frame launch over the same 1.2 M-slot wave).  A figure from a
+    profile, not from this run: the file is named next to it; None when the summary is not there."""
+    try:
+        path = os.path.join(ROOT, "profiles", "r2n_ncu_full_%s.txt" % kernel)
+        total = 0.0
+        for line in open(path):
+            words = line.split()
+            if len(words) >= 3 and words[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[words[2]]
+                total += float(words[1]) * unit
+        return (total, os.path.relpath(path, ROOT)) if total > 0 else (None, None)
+    except Exception:   # noqa: BLE001
+        return None, None
+
+
 def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kernel):
     counters = renderer.count_pass(seed=seed)
     alg_step = algorithmic_bytes(counters, bins, spp)
@@ -332,8 +349,9 @@ def frame_roofline(cx, renderer, total_ms_step, per_step, bins, spp, seed, kerne
     trace_ms = per_step["trace_ms"]
     achieved = alg / (trace_ms * 1e-3) / 1e9 if trace_ms else None
     launches = max(1.0, per_step["trace_launches"])
+    traffic, traffic_source = captured_traffic(kernel) if cx.world_size == 1 else (None, None)
     return {"bound": "hbm", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak if achieved else None,
-            "traffic": None, "kernel": kernel, "kernel_ms": trace_ms / launches, "launches_per_step": per_step["trace_launches"],
+            "traffic": traffic, "traffic_source": traffic_source, "kernel": kernel, "kernel_ms": trace_ms / launches, "launches_per_step": per_step["trace_launches"],
             "kernel_ms_per_step": trace_ms, "kernel_share_of_step": trace_ms / total_ms_step,
             "algorithmic_bytes_per_launch": alg / launches, "algorithmic_bytes_per_step": alg,
             # whole step, per GPU: every rank's share of the frame's algorithmic bytes against the step time
