@@ -284,6 +284,33 @@ def test_bayer_pipeline_matches_serial_reference(api, reference, passes):
     assert bm[mask].max() > 0 and not bm[~mask].any() and np.array(bayer.frame.samples)[mask].min() == 2 * passes
 
 
+def test_mono_pipeline_accumulates_and_feeds_the_mono_adaptive_sampler(api, reference):
+    """An accumulating PowerPipeline2D observed twice through CudaRenderEngine == two reference passes (its frame goes up to
+    the device, is merged there and comes back), and the stock MonoAdaptiveSampler2D drives the engine from that frame."""
+    from raysect.optical.observer import MonoAdaptiveSampler2D, PowerPipeline2D
+    from source_b200.plugin import CudaRenderEngine
+    kw = dict(pixels=(9, 7), bins=8, spectral_rays=2)
+    filt = api.InterpolatedSF([300, 450, 600, 800], [0.1, 1.0, 0.6, 0.2])
+    cam, pipe = scenes.cornell_camera(api, scenes.cornell_box(api), samples=2, **kw)
+    power = PowerPipeline2D(filter=filt, display_progress=False, accumulate=True)
+    cam.pipelines = [pipe, power]
+    reference.oracle_render(cam, pipe, 1357, passes=2)
+    ref = [np.array(getattr(power.frame, n)) for n in ("mean", "variance", "samples")]
+    cam2, pipe2 = scenes.cornell_camera(api, scenes.cornell_box(api), samples=2, **kw)
+    power2 = PowerPipeline2D(filter=filt, display_progress=False, accumulate=True)
+    cam2.pipelines = [power2]
+    cam2.render_engine = CudaRenderEngine(seed=1357, rng="mt", backend=hostsim_api.HostScene)
+    cam2.observe()
+    cam2.observe()
+    for ours, theirs in zip((power2.frame.mean, power2.frame.variance, power2.frame.samples), ref):
+        np.testing.assert_array_equal(np.array(ours), theirs)
+    cam2.frame_sampler = MonoAdaptiveSampler2D(power2, ratio=4, fraction=0.3, min_samples=5, cutoff=0.0001)
+    before = np.array(power2.frame.samples)
+    cam2.observe()
+    grown = np.array(power2.frame.samples) - before
+    assert set(np.unique(grown)) <= {0, 2} and 0 < (grown > 0).sum()
+
+
 def test_rgb_pipeline_accumulates_over_observes_and_feeds_the_rgb_adaptive_sampler(api, reference):
     """An accumulating RGBPipeline2D observed twice through CudaRenderEngine == two reference passes, and the stock
     RGBAdaptiveSampler2D (sampler2d.pyx) driving the engine from that pipeline's xyz_frame picks pixel lists the engine
