@@ -17,8 +17,8 @@ from .material import (AbsorbingSurface, Checkerboard, Conductor, Dielectric, La
                        UniformVolumeEmitter, UnitySurfaceEmitter, UnityVolumeEmitter, schott)
 from .scenegraph import (Box, Cone, Cylinder, Intersect, Intersection, Mesh, MeshData, Node, Parabola, Primitive, Ray,
                          Sphere, Subtract, Union, World)
-from .observer import (FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
-                       SpectralPowerPipeline2D, SpectralRadiancePipeline2D, SpectralSlice, StatsArray3D)
+from .observer import (CCDArray, FullFrameSampler2D, Observer, OrthographicCamera, PinholeCamera, SpectralAdaptiveSampler2D,
+                       SpectralPowerPipeline2D, SpectralRadiancePipeline2D, SpectralSlice, StatsArray3D, VectorCamera)
 from .meshio import import_obj, import_ply, import_stl, import_vtk
 from .engine import Accelerator, Device, default_device
 from ._cabi import RNG_MT19937_64, RNG_PHILOX, RsbError

@@ -6,6 +6,8 @@ The per-pixel inner loop (_render_pixel: ray generation, Ray.trace, add_sample) 
 this module keeps the reference's orchestration: one render pass per spectral slice, results merged
 into an accumulating StatsArray3D frame with the reference's combine rule.
 """
+import math
+
 import numpy as np
 
 from . import _cabi as cabi
@@ -477,3 +479,54 @@ class OrthographicCamera(PinholeCamera):
     def _camera_desc(self, pixel_samples):
         nx, ny = self._pixels
         return camera_desc(nx, ny, pixel_samples, None, self.sensitivity, self.to_root(), width=self._width)
+
+
+class CCDArray(OrthographicCamera):
+    """raysect/optical/observer/imaging/ccd.pyx:40-151: a bare ``width`` metres wide sensor of square pixels; every sample
+    leaves a uniformly drawn point of its pixel in a cosine-weighted direction over the hemisphere in front of the sensor
+    (projection weight 0.5); a pixel's sensitivity is its area times 2 pi (ccd.pyx:150-151)."""
+
+    def __init__(self, pixels=(720, 480), width=0.035, frame_sampler=None, pipelines=None, parent=None, transform=None, name=None):
+        super().__init__(pixels, width, None, frame_sampler, pipelines, parent, transform, name)
+
+    @property
+    def sensitivity(self):
+        nx = self._pixels[0]
+        return math.pow(self._width / nx, 2.0) * 2 * math.pi
+
+    @sensitivity.setter
+    def sensitivity(self, value):
+        if value not in (None, 1.0):
+            raise AttributeError("a CCDArray's sensitivity follows from its pixel area (ccd.pyx:150-151)")
+
+    def _camera_desc(self, pixel_samples):
+        nx, ny = self._pixels
+        return camera_desc(nx, ny, pixel_samples, None, self.sensitivity, self.to_root(), width=self._width, ccd=True)
+
+
+class VectorCamera(PinholeCamera):
+    """raysect/optical/observer/imaging/vector.pyx:44-156: every pixel has its own origin and viewing direction
+    (``pixel_origins`` / ``pixel_directions``: (nx, ny, 3) arrays, or (nx, ny) object arrays of Point3D / Vector3D, in the
+    observer's space); pixels off the edge of the image are sub-sampled by interpolating between the diagonal neighbours'
+    directions, edge pixels trace their own direction."""
+
+    def __init__(self, pixel_origins, pixel_directions, frame_sampler=None, pipelines=None, sensitivity=None, parent=None,
+                 transform=None, name=None):
+        def as_array(a):
+            a = np.asarray(a)
+            if a.dtype == object:
+                a = np.array([[[v.x, v.y, v.z] for v in row] for row in a], dtype=np.float64)
+            return np.ascontiguousarray(a, dtype=np.float64)
+        origins, directions = as_array(pixel_origins), as_array(pixel_directions)
+        if origins.ndim != 3 or origins.shape[2] != 3:
+            raise ValueError("Pixel arrays must have 2 dimensions.")
+        if origins.shape != directions.shape:
+            raise ValueError("Pixel arrays must have equal shapes.")
+        super().__init__(origins.shape[:2], None, sensitivity, frame_sampler, pipelines, parent, transform, name)
+        self.pixel_origins, self.pixel_directions = origins, directions
+
+    def _camera_desc(self, pixel_samples):
+        nx, ny = self._pixels
+        return camera_desc(nx, ny, pixel_samples, None, self.sensitivity, self.to_root(),
+                           vector=(self.pixel_origins, self.pixel_directions))
+

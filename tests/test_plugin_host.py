@@ -939,6 +939,67 @@ def test_pixel_observer_matches_serial_reference(api, reference, kind):
         px2.observe()
 
 
+def test_mirror_ccd_array_and_vector_camera_match_reference(api, reference):
+    """The stand-alone mirror's CCDArray and VectorCamera (no Raysect needed at run time) against the reference's, through the
+    host build: identical spectral frames."""
+    import source_b200 as mirror
+    from raysect.core import Point3D, Vector3D
+    from raysect.optical.observer import CCDArray, VectorCamera
+
+    def settle(cam):
+        cam.spectral_rays = 1
+        cam.spectral_bins = 8
+        cam.spectral_rays = 2
+        cam.pixel_samples = 3
+        cam.ray_extinction_min_depth = 2
+        cam.ray_extinction_prob = 0.1
+        return cam
+
+    def observe_on_host_build(world, cam, seed):
+        from source_b200 import _cabi as cabi
+        from source_b200.flatten import flatten_world
+        cam.seed, cam.rng_mode = seed, cabi.RNG_MT19937_64
+        world._accel = parity._Accel(hostsim_api.HostScene(flatten_world(world)))
+        world._rebuild = False
+        cam.observe()
+        world._accel.close()
+        world._accel, world._rebuild = None, True
+    # CCD
+    pipe = api.SpectralPowerPipeline2D()
+    cam = settle(CCDArray((9, 7), width=0.4, parent=scenes.cornell_box(api), transform=api.translate(0.1, -0.05, -0.9) * api.rotate(8, -5, 3),
+                          pipelines=[pipe]))
+    cam.quiet = True
+    m_ref, v_ref, _ = reference.oracle_render(cam, pipe, 4711)
+    mworld = scenes.cornell_box(mirror)
+    mpipe = mirror.SpectralPowerPipeline2D()
+    mcam = settle(mirror.CCDArray((9, 7), width=0.4, parent=mworld, transform=mirror.translate(0.1, -0.05, -0.9) * mirror.rotate(8, -5, 3),
+                                  pipelines=[mpipe]))
+    observe_on_host_build(mworld, mcam, 4711)
+    np.testing.assert_array_equal(np.array(mpipe.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(mpipe.frame.variance), v_ref)
+    # vector camera
+    nx, ny = 8, 7
+    o_arr, d_arr = np.zeros((nx, ny, 3)), np.zeros((nx, ny, 3))
+    origins, directions = np.empty((nx, ny), dtype=object), np.empty((nx, ny), dtype=object)
+    for x in range(nx):
+        for y in range(ny):
+            o_arr[x, y] = (0.02 * (x - nx / 2), 0.02 * (y - ny / 2), 0.0)
+            d_arr[x, y] = (-0.9 * (x + 0.5 - nx / 2) / nx, -0.9 * (y + 0.5 - ny / 2) / ny, 1.0 + 0.01 * x * y)
+            origins[x, y], directions[x, y] = Point3D(*o_arr[x, y]), Vector3D(*d_arr[x, y])
+    pipe = api.SpectralPowerPipeline2D()
+    cam = settle(VectorCamera(origins, directions, frame_sampler=api.FullFrameSampler2D(), pipelines=[pipe], sensitivity=1.4,
+                              parent=scenes.cornell_box(api), transform=api.translate(0.05, 0.0, -3.1) * api.rotate(3, -2, 1)))
+    cam.quiet = True
+    m_ref, v_ref, _ = reference.oracle_render(cam, pipe, 3030)
+    mworld = scenes.cornell_box(mirror)
+    mpipe = mirror.SpectralPowerPipeline2D()
+    mcam = settle(mirror.VectorCamera(o_arr, d_arr, pipelines=[mpipe], sensitivity=1.4, parent=mworld,
+                                      transform=mirror.translate(0.05, 0.0, -3.1) * mirror.rotate(3, -2, 1)))
+    observe_on_host_build(mworld, mcam, 3030)
+    np.testing.assert_array_equal(np.array(mpipe.frame.mean), m_ref)
+    np.testing.assert_array_equal(np.array(mpipe.frame.variance), v_ref)
+
+
 def test_unsupported_objects_fail_loudly(api):
     from raysect.optical.observer import Pipeline2D
     from source_b200.plugin import CudaRenderEngine
